@@ -1,0 +1,184 @@
+"""CPU tests pinning the oracle (oracle/kalman_np.py, oracle/kalman_torch.py).
+
+1. against golden vectors produced by executing the reference's own source (tests/golden/generate_golden.py);
+2. against the reference's scipy-MVN identity test (tests/statespace/test_distributions.py:96-119);
+3. against a textbook, jitter-free Kalman filter + RTS smoother standing in for statsmodels, at the
+   reference's own tolerance atol=rtol=1e-6 (tests/statespace/test_kalman_filter.py:30-31,232-269);
+4. the reference's invariants (test_kalman_filter.py:216-224, 277-301).
+"""
+
+import numpy as np
+import pytest
+from conftest import golden_names, load_golden
+from numpy.testing import assert_allclose
+from scipy import stats
+
+from oracle import kalman_np as onp
+from oracle import kalman_torch as oth
+
+NAMES = ("a0", "P0", "c", "d", "T", "Z", "R", "H", "Q")
+OUT_NAMES = ("filtered_states", "predicted_states", "observed_states", "filtered_covariances",
+             "predicted_covariances", "observed_covariances", "loglike_obs")
+ALL = golden_names()
+
+
+def _args(ins):
+    return [ins["y"]] + [ins[k] for k in NAMES]
+
+
+def _ill_conditioned(name):
+    # partially-missing p>1 cases divide by the 1e-8 jitter: values ~1e6..1e8
+    return "missing" in name and ("p2" in name or "p3" in name or "p5" in name)
+
+
+@pytest.mark.parametrize("name", ALL)
+def test_numpy_oracle_matches_reference_outputs(name):
+    kind, ins, ref = load_golden(name)
+    outs = onp.kalman_filter(kind, *_args(ins))
+    rtol = 1e-6 if _ill_conditioned(name) else 1e-10
+    for n, o in zip(OUT_NAMES, outs):
+        scale = max(1.0, np.abs(ref[n]).max())
+        assert_allclose(o.reshape(ref[n].shape), ref[n], rtol=rtol, atol=rtol * scale, err_msg=f"{name}:{n}")
+    sm_a, sm_P = onp.kalman_smoother(ins["T"], ins["R"], ins["Q"], outs[0], outs[3])
+    stol = 1e-5 if ("nile" in name or _ill_conditioned(name)) else 1e-8  # pinv of cond~1e14 matrices on Nile
+    assert_allclose(sm_a, ref["smoothed_states"], rtol=stol, atol=stol * max(1, np.abs(sm_a).max()))
+    assert_allclose(sm_P, ref["smoothed_covariances"], rtol=stol, atol=stol * max(1, np.abs(sm_P).max()))
+
+
+@pytest.mark.parametrize("name", ALL)
+def test_torch_oracle_matches_reference_logp_and_grad(name):
+    kind, ins, ref = load_golden(name)
+    logp, grads = oth.logp_and_grad(kind, *_args(ins))
+    rtol = 1e-6 if _ill_conditioned(name) else 1e-9
+    assert_allclose(logp, ref["loglike_obs"].sum(), rtol=rtol)
+    for k in NAMES:
+        g_ref = ref["grad_" + k]
+        scale = max(np.abs(g_ref).max(), 1e-300)
+        assert_allclose(grads[k], g_ref, rtol=0, atol=rtol * scale, err_msg=f"{name}: d/d{k}")
+
+
+def test_torch_oracle_batched_equals_per_series():
+    from pymc_experimental_b200 import synth
+
+    cfg = synth.random_dense(4, 12, 4, 2, 3, seed=7)
+    for kind in ("standard", "univariate", "cholesky"):
+        logp, grads = oth.logp_and_grad(kind, cfg["y"], *[cfg[k] for k in NAMES])
+        for b in range(4):
+            lp1, g1 = oth.logp_and_grad(kind, cfg["y"][b], *[cfg[k][b] for k in NAMES])
+            assert_allclose(logp[b], lp1, rtol=1e-12)
+            for k in NAMES:
+                assert_allclose(grads[k][b], g1[k], rtol=1e-9, atol=1e-12)
+
+
+def test_gradient_matches_finite_differences():
+    from pymc_experimental_b200 import synth
+
+    cfg = synth.random_dense(1, 10, 3, 2, 2, seed=11)
+    args = [cfg["y"][0]] + [cfg[k][0] for k in NAMES]
+    for kind in ("standard", "univariate", "cholesky"):
+        _, grads = oth.logp_and_grad(kind, *args)
+        for k_idx, k in enumerate(NAMES):
+            x = args[1 + k_idx]
+            it = np.nditer(x, flags=["multi_index"])
+            for _ in it:
+                idx = it.multi_index
+                h = 1e-6
+                xp, xm = x.copy(), x.copy()
+                xp[idx] += h
+                xm[idx] -= h
+                g = grads[k][idx]
+                if k in ("P0", "H", "Q") and idx[0] != idx[1] and kind != "cholesky":
+                    # LAPACK posv reads one triangle: only symmetric perturbations are well defined on the
+                    # NumPy side; compare with the sum of the two entry-wise gradients
+                    xp[idx[::-1]] += h
+                    xm[idx[::-1]] -= h
+                    g = g + grads[k][idx[::-1]]
+                ap, am = list(args), list(args)
+                ap[1 + k_idx], am[1 + k_idx] = xp, xm
+                fd = (onp.kalman_logp(kind, *ap) - onp.kalman_logp(kind, *am)) / (2 * h)
+                assert_allclose(g, fd, rtol=2e-5, atol=2e-6, err_msg=f"{kind} d/d{k}{idx}")
+
+
+@pytest.mark.parametrize("kind", ["standard", "univariate", "cholesky"])
+def test_loglike_vectors_agree_with_scipy_mvn(kind):
+    """reference: tests/statespace/test_distributions.py:96-119 (k_endog = 1, atol=rtol=1e-5 there)."""
+    _, ins, _ = load_golden("nile_standard_miss0")
+    if kind == "cholesky":
+        ins = dict(ins, P0=np.linalg.cholesky(ins["P0"]))
+    outs = onp.kalman_filter(kind, *_args(ins))
+    obs_mu, obs_cov, ll = outs[2], outs[5], outs[6]
+    for t in range(len(ll)):
+        ref = stats.multivariate_normal.logpdf(ins["y"][t], mean=obs_mu[t], cov=obs_cov[t])
+        assert_allclose(ll[t], ref, rtol=1e-7, atol=1e-7)
+
+
+def _textbook_filter_smoother(y, a0, P0, T, Z, R, H, Q):
+    """Durbin & Koopman (2012) eqs 4.24 / 4.44: plain covariance filter + RTS smoother, no jitter, missing
+    observations skipped.  Independent of the oracle; stands in for statsmodels' KalmanFilter."""
+    n, m = len(y), len(a0)
+    a, P = a0.copy(), P0.copy()
+    fa, fP, pa, pP, ll = [], [], [], [], []
+    RQR = R @ Q @ R.T
+    for t in range(n):
+        pa.append(a), pP.append(P)
+        if np.isnan(y[t]).all():
+            af, Pf = a, P
+            ll.append(0.0)
+        else:
+            v = y[t] - Z @ a
+            F = Z @ P @ Z.T + H
+            Fi = np.linalg.inv(F)
+            K = P @ Z.T @ Fi
+            af = a + K @ v
+            Pf = P - K @ Z @ P
+            ll.append(-0.5 * (len(v) * np.log(2 * np.pi) + np.log(np.linalg.det(F)) + v @ Fi @ v))
+        fa.append(af), fP.append(Pf)
+        a, P = T @ af, T @ Pf @ T.T + RQR
+    fa, fP, pa, pP = map(np.array, (fa, fP, pa, pP))
+    sa, sP = fa.copy(), fP.copy()
+    for t in range(n - 2, -1, -1):
+        Pp = T @ fP[t] @ T.T + RQR
+        G = fP[t] @ T.T @ np.linalg.inv(Pp)
+        sa[t] = fa[t] + G @ (sa[t + 1] - T @ fa[t])
+        sP[t] = fP[t] + G @ (sP[t + 1] - Pp) @ G.T
+    return fa, pa, sa, fP, pP, sP, np.array(ll)
+
+
+@pytest.mark.parametrize("kind", ["standard", "univariate", "cholesky"])
+@pytest.mark.parametrize("n_missing", [0, 5])
+def test_filters_match_textbook_filter_on_nile(kind, n_missing):
+    """reference: tests/statespace/test_kalman_filter.py:232-269 (statsmodels replaced by a textbook filter;
+    same tolerances, smoothed covariances compared from index 5 on as there)."""
+    _, ins, _ = load_golden(f"nile_standard_miss{n_missing}")
+    fa, pa, sa, fP, pP, sP, ll = _textbook_filter_smoother(
+        ins["y"], ins["a0"], ins["P0"], ins["T"], ins["Z"], ins["R"], ins["H"], ins["Q"])
+    if kind == "cholesky":
+        ins = dict(ins, P0=np.linalg.cholesky(ins["P0"]))
+    outs = onp.kalman_filter(kind, *_args(ins))
+    sm_a, sm_P = onp.kalman_smoother(ins["T"], ins["R"], ins["Q"], outs[0], outs[3])
+    tol = dict(atol=1e-6, rtol=1e-6)
+    assert_allclose(outs[0], fa, **tol)
+    assert_allclose(outs[1], pa, **tol)
+    assert_allclose(outs[3], fP, **tol)
+    assert_allclose(outs[4], pP, **tol)
+    assert_allclose(outs[6], ll, **tol)
+    assert_allclose(outs[6].sum(), ll.sum(), **tol)
+    assert_allclose(sm_a, sa, **tol)
+    assert_allclose(sm_P[5:], sP[5:], **tol)
+
+
+@pytest.mark.parametrize("kind", ["standard", "univariate", "cholesky"])
+def test_last_smoother_is_last_filtered_and_covariances_psd(kind):
+    """reference: test_kalman_filter.py:216-224 and :277-301."""
+    _, ins, _ = load_golden("nile_standard_miss5")
+    if kind == "cholesky":
+        ins = dict(ins, P0=np.linalg.cholesky(ins["P0"]))
+    outs = onp.kalman_filter(kind, *_args(ins))
+    sm_a, sm_P = onp.kalman_smoother(ins["T"], ins["R"], ins["Q"], outs[0], outs[3])
+    assert_allclose(sm_a[-1], outs[0][-1])
+    assert_allclose(sm_P[-1], outs[3][-1])
+    if kind == "univariate":  # the reference's PSD test skips the univariate filter (test_kalman_filter.py:274)
+        return
+    for cov in (outs[3], outs[4], sm_P):  # filtered, predicted, smoothed covariances
+        assert (np.linalg.eigvalsh(0.5 * (cov + np.swapaxes(cov, -1, -2))) > 0).all()
+        assert_allclose(cov, np.swapaxes(cov, -1, -2), rtol=1e-6, atol=1e-6)
