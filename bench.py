@@ -1,0 +1,389 @@
+#!/usr/bin/env python
+"""bench.py -- Kalman logp+grad state-steps/s (batched series) on B200, next to the CPU oracle.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload C2] [--impl b200|reference]
+
+One "step" = one batched evaluation of sum_t ll_t AND its gradient w.r.t. all nine state-space matrices
+(workload C3: filter + smoother) over the whole synthetic batch of the workload, through the C ABI
+(libbkf.so).  Default workload = BASELINE.json configs[1]: SARIMA(1,1,1)x(1,0,1,12), UnivariateFilter,
+16384 draws x T=500 per GPU.  Prints ONE JSON line (rank 0).
+
+  value   state-steps/s with inputs already resident in HBM (device pointers), CUDA-event timed, max over ranks,
+          includes the final NCCL all-gather of the packed [logp | grads] buffer when N > 1 (weak scaling:
+          every rank owns a full batch of draws).
+  e2e     the same metric through the same C-ABI call with HOST (pinned) buffers: H2D of all inputs and D2H of
+          logp + gradients inside the timed region.
+  roofline / cpu_baseline: see DESIGN.md "Measurement".
+"""
+
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "kalman_logp_grad_state_steps_per_sec"
+UNIT = "state-steps/s"
+NAMES = ("a0", "P0", "c", "d", "T", "Z", "R", "H", "Q")
+
+WORKLOADS = {
+    # name: (synth fn name, filter kind, default B per GPU, default T, mode)
+    "C1": ("local_level", "standard", 1, 100, "logp_grad"),
+    "C2": ("sarima", "univariate", 16384, 500, "logp_grad"),
+    "C3": ("structural", "standard", 8192, 240, "filter_smooth"),
+    "C4": ("varmax", "cholesky", 512, 1000, "logp_grad"),
+    "C5": ("ets", "standard", 1_000_000, 100, "logp_grad"),
+}
+DESCR = {
+    "C1": "local-level structural (m=2,p=1,r=2) StandardFilter logp+grad",
+    "C2": "SARIMA(1,1,1)x(1,0,1,12) (m=15,p=1,r=1) UnivariateFilter logp+grad",
+    "C3": "structural trend+seasonal(12)+cycle (m=15,p=1,r=5) StandardFilter + KalmanSmoother",
+    "C4": "VARMAX(2,0) k_endog=16 (m=32,p=16,r=16) SquareRootFilter logp+grad",
+    "C5": "ETS(A,Ad,N) (m=3,p=1,r=1) StandardFilter logp+grad",
+}
+
+
+# ---- algorithmic cost model (dense, mul and add each count 1) -----------------------
+def fwd_flops(kind, m, p, r):
+    if kind == "standard":
+        return 8 * m**3 + m**2 * (6 * p + 2 * r + 10) + m * (6 * p**2 + 2 * r**2 + 4 * p + 1) + p**3 + 3 * p**2 + 3 * p
+    if kind == "univariate":
+        return 4 * m**3 + m**2 * (5 * p + 2 * r + 8) + m * (7 * p + 2 * r**2 + 1) + 6 * p
+    return (4 / 3 * (p + m) ** 3 + 2 * m**3 + 2 * m**2 * (r + 2 * m / 3) + 2 * p * m**2 + 2 * m**2
+            + 2 * m * r**2 + (p**3 + r**3) / 3)
+
+
+def smoother_flops(m, r):
+    return 36 * m**3 + 2 * m**2 * r + 2 * m * r**2 + 14 * m**2
+
+
+def step_model(kind, mode, m, p, r):
+    """Algorithmic flops and HBM bytes per state-step, split per kernel class."""
+    f = fwd_flops(kind, m, p, r)
+    spill = (m + m * m) * 8
+    if mode == "logp_grad":
+        return {"forward": (f, 8 * p + spill), "backward": (2 * f, 8 * p + spill)}
+    return {"forward": (f, 8 * p + spill), "smoother": (smoother_flops(m, r), 2 * spill)}
+
+
+# ---- helpers -------------------------------------------------------------------------------------------
+class ClockSampler:
+    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx = gpu_index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={self.idx}", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits",
+                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, smax, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1]))
+                smax.append(float(r[2]))
+            except (ValueError, IndexError):
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(smax) if smax else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def make_workload(name, B, T, seed_offset=0):
+    from pymc_experimental_b200 import synth
+
+    fn, kind, _, _, mode = WORKLOADS[name]
+    cfg = getattr(synth, fn)(B, T) if seed_offset == 0 else getattr(synth, fn)(B, T, seed=synth.SEED_BASE + 100 + seed_offset)
+    return cfg, kind, mode
+
+
+# ---- CPU arm (oracle port; also the `--impl reference` arm) ----------------------------------------------
+def cpu_run(name, kind, mode, cfg, sample_B):
+    """One pass of the oracle over the first sample_B series of the workload; returns seconds."""
+    import torch
+
+    from oracle import kalman_np as onp
+    from oracle import kalman_torch as oth
+
+    sub = {k: cfg[k][:sample_B] for k in NAMES}
+    y = cfg["y"] if cfg["y"].ndim == 2 else cfg["y"][:sample_B]
+    t0 = time.perf_counter()
+    if mode == "logp_grad":
+        oth.logp_and_grad(kind, y, *[sub[k] for k in NAMES])
+    else:
+        with torch.no_grad():
+            for b in range(sample_B):
+                outs = onp.kalman_filter(kind, y if y.ndim == 2 else y[b], *[sub[k][b] for k in NAMES])
+                onp.kalman_smoother(sub["T"][b], sub["R"][b], sub["Q"][b], outs[0], outs[3])
+    return time.perf_counter() - t0
+
+
+def cpu_sample_size(name, mode):
+    return {"C1": 1, "C2": 256, "C3": 16, "C4": 16, "C5": 4096}[name] if mode == "logp_grad" else 16
+
+
+def cpu_baseline(name, kind, mode, cfg, T, steps=1):
+    import torch
+
+    sB = min(cpu_sample_size(name, mode), cfg["a0"].shape[0])
+    best = min(cpu_run(name, kind, mode, cfg, sB) for _ in range(steps))
+    cores = torch.get_num_threads() if mode == "logp_grad" else 1
+    return {
+        "value": sB * T / best, "unit": UNIT, "cores": cores, "kind": "port",
+        "sample": f"{sB} series x T={T} of the same workload, oracle/kalman_torch.py (batched torch.float64 "
+                  f"autograd)" if mode == "logp_grad" else
+                  f"{sB} series x T={T}, oracle/kalman_np.py filter+smoother (NumPy/LAPACK, Python loop)",
+        "seconds": best,
+    }
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    name = args.workload
+    _, kind, dB, dT, mode = WORKLOADS[name]
+    T = args.T or dT
+    sB = cpu_sample_size(name, mode)
+    cfg, kind, mode = make_workload(name, sB, T)
+    for _ in range(args.warmup):
+        cpu_run(name, kind, mode, cfg, sB)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        cpu_run(name, kind, mode, cfg, sB)
+    dt = time.perf_counter() - t0
+    import torch
+
+    cores = torch.get_num_threads() if mode == "logp_grad" else 1
+    value = sB * T * args.steps / dt
+    sample = f"each step = {sB} series x T={T} of workload {name} through the CPU oracle (restatement of the " \
+             f"reference's PyTensor filter; PyTensor itself is not installable here)"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"{name}: {DESCR[name]}", "series_per_step": sB, "T": T},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+# ---- GPU arm ------------------------------------------------------------------------------------------------
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+
+    from pymc_experimental_b200.engine import F32, F64, KalmanEngine
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the engine has no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    name = args.workload
+    _, kind, dB, dT, mode = WORKLOADS[name]
+    B = args.batch or dB
+    T = args.T or dT
+    dtype = torch.float64 if args.dtype == "f64" else torch.float32
+    npdtype = np.float64 if args.dtype == "f64" else np.float32
+    cfg, kind, mode = make_workload(name, B, T, seed_offset=rank)
+    m, r = cfg["R"].shape[-2:]
+    p = cfg["Z"].shape[-2]
+    eng = KalmanEngine(local_rank)
+    jitter = 1e-8 if args.dtype == "f64" else 1e-6
+
+    # device-resident inputs
+    dargs = [torch.as_tensor(cfg["y"], dtype=dtype, device=dev)] + [torch.as_tensor(cfg[k], dtype=dtype, device=dev) for k in NAMES]
+    layout, total = eng.packed_layout(B, m, p, r)
+    packed = torch.empty(total, dtype=dtype, device=dev)
+    gathered = torch.empty(total * world, dtype=dtype, device=dev) if world > 1 else None
+
+    def device_step():
+        if mode == "logp_grad":
+            out = eng.logp_grad(kind, *dargs, packed_out=packed, cov_jitter=jitter)
+            if world > 1:  # the only inter-GPU traffic: one all-gather of [logp | grads] over NVLink
+                dist.all_gather_into_tensor(gathered, packed)
+            return out
+        return eng.filter_smooth(kind, *dargs, cov_jitter=jitter)
+
+    # host (pinned) buffers for the end-to-end arm
+    def pinned(a):
+        t = torch.empty(a.shape, dtype=dtype, pin_memory=True)
+        t.copy_(torch.as_tensor(a, dtype=dtype))
+        return t.numpy()
+
+    hargs = [pinned(cfg["y"])] + [pinned(cfg[k]) for k in NAMES]
+    h2d = sum(a.nbytes for a in hargs)
+
+    def host_step():
+        if mode == "logp_grad":
+            logp, grads, _ = eng.logp_grad(kind, *hargs, dtype=npdtype, cov_jitter=jitter)
+            return logp.nbytes + sum(g.nbytes for g in grads.values())
+        ll, sa, sP, _ = eng.filter_smooth(kind, *hargs, dtype=npdtype, cov_jitter=jitter)
+        return ll.nbytes + sa.nbytes + sP.nbytes
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- warm-up ----
+    for _ in range(max(args.warmup, 3)):
+        device_step()
+    barrier()
+
+    # ---- timed region: device-resident ----
+    fp64_peak = eng.measure_fma_peak(F64 if args.dtype == "f64" else F32)
+    eng.enable_timing(True)
+    launches0 = eng.launch_count
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    barrier()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for _ in range(args.steps):
+        device_step()
+    ev1.record()
+    barrier()
+    ms = ev0.elapsed_time(ev1)
+    clocks = sampler.stop()
+    launches = eng.launch_count - launches0
+    ktimes = eng.kernel_times()
+    eng.enable_timing(False)
+    t_ms = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
+    ms = float(t_ms.item())
+    units_per_step = B * T * world
+    value = units_per_step * args.steps / (ms * 1e-3)
+
+    # ---- timed region: end to end through host buffers ----
+    host_step()
+    barrier()
+    t0 = time.perf_counter()
+    d2h = 0
+    for _ in range(args.steps):
+        d2h = host_step()
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    t_e = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t_e, op=dist.ReduceOp.MAX)
+    e2e_value = units_per_step * args.steps / float(t_e.item())
+
+    # ---- roofline of the dominant kernel ----
+    model = step_model(kind, mode, m, p, r)
+    hbm_peak, peak_src = load_peaks()
+    dom = max((k for k in model if ktimes[k][1] > 0), key=lambda k: ktimes[k][0])
+    dom_ms = ktimes[dom][0] / ktimes[dom][1]
+    flops, bytes_ = model[dom]
+    ach_tf = flops * B * T / (dom_ms * 1e-3) / 1e12
+    ach_gbs = bytes_ * B * T / (dom_ms * 1e-3) / 1e9
+    t_fp = flops / (fp64_peak * 1e12)
+    t_hbm = bytes_ / (hbm_peak * 1e9)
+    if t_fp >= t_hbm:
+        roof = {"bound": "fp64" if args.dtype == "f64" else "fp32", "achieved": ach_tf, "peak": fp64_peak,
+                "unit": "TFLOP/s", "frac": ach_tf / fp64_peak, "traffic": None}
+    else:
+        roof = {"bound": "hbm", "achieved": ach_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": ach_gbs / hbm_peak,
+                "traffic": None}
+    roof.update({
+        "kernel": dom, "kernel_ms": dom_ms, "kernel_share_of_step": ktimes[dom][0] / (ms if ms > 0 else 1.0),
+        "algorithmic_flops_per_state_step": flops, "algorithmic_bytes_per_state_step": bytes_,
+        "achieved_tflops": ach_tf, "fma_peak_tflops": fp64_peak, "fma_peak_source": "bkf_measure_fma_peak (live)",
+        "achieved_hbm_gbs": ach_gbs, "hbm_peak_gbs": hbm_peak, "hbm_peak_source": peak_src,
+        "all_kernels_ms": {k: (v[0] / v[1] if v[1] else None) for k, v in ktimes.items()},
+    })
+
+    line = None
+    if rank == 0:
+        cpu = cpu_baseline(name, kind, mode, cfg, T) if world == 1 and not args.no_cpu else None
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
+            "config": {"workload": f"{name}: {DESCR[name]}", "series_per_gpu": B, "T": T, "m": int(m), "p": int(p),
+                       "r": int(r), "mode": mode, "kernel_path": eng.last_path,
+                       "l2": "working set (trajectory workspace + parameters) exceeds the 126 MB L2; no explicit flush",
+                       "parallelism": f"independent series sharded over {world} GPU(s); one final NCCL all-gather"},
+            "clocks": clocks, "gpu_launches": int(launches),
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
+            "roofline": roof,
+        }
+        if cpu is not None:
+            line["cpu_baseline"] = cpu
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return line
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="C2", choices=sorted(WORKLOADS))
+    ap.add_argument("--batch", type=int, default=0, help="series per GPU (default: the workload's)")
+    ap.add_argument("--T", type=int, default=0, help="time steps (default: the workload's)")
+    ap.add_argument("--dtype", default="f64", choices=["f64", "f32"])
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

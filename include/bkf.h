@@ -1,0 +1,127 @@
+/*
+ * bkf.h -- C ABI of libbkf.so, the B200 (sm_100a) batched Kalman engine.
+ *
+ * This is the drop-in boundary for the hot path of pymc_extras.statespace (paths relative to the reference
+ * repository pymc-devs/pymc-experimental):
+ *
+ *   bkf_filter_forward    replaces  BaseFilter.build_graph + kalman_step + _postprocess_scan_results
+ *                                   pymc_extras/statespace/filters/kalman_filter.py:144-308 (Standard :549-617,
+ *                                   SquareRoot :629-750, Univariate :769-820)
+ *   bkf_filter_logp_grad  replaces  sum(loglike_obs) and pytensor.grad(...) through Scan.L_op of the same graph
+ *                                   (the logp + dlogp function NUTS evaluates)
+ *   bkf_smooth            replaces  KalmanSmoother.build_graph, filters/kalman_smoother.py:66-126
+ *   bkf_filter_smooth     fuses     filter forward + smoother (PyMCStateSpace._build_smoother_graph,
+ *                                   core/statespace.py:903-951) without materialising the filter outputs
+ *
+ * The reference has no FFI of its own (it is pure Python over PyTensor); the reference-side binding is a
+ * PyTensor Op whose perform() calls these entry points through ctypes -- see INTEGRATION.md.
+ *
+ * Conventions
+ *   - All arrays are C-contiguous, row-major, dtype = problem.dtype (float64 or float32), caller-owned.
+ *     The library never frees or retains caller pointers past the call.
+ *   - problem.mem says whether the pointers are host (NumPy) or device (CUDA, same device as the handle).
+ *   - Batch axis first: a0 [B,m], P0 [B,m,m], c [B,m], d [B,p], T [B,m,m], Z [B,p,m], R [B,m,r], H [B,p,p],
+ *     Q [B,r,r].  Bit i of problem.shared_mask (BKF_PARAM_* order) set means "parameter i has no batch axis
+ *     and is shared by every series".  y is [B,n,p], or [n,p] when problem.y_shared != 0.
+ *   - Outputs: filtered_states [B,n,m], predicted_states [B,n,m], observed_states [B,n,po],
+ *     filtered_covariances [B,n,m,m], predicted_covariances [B,n,m,m], observed_covariances [B,n,po,po],
+ *     loglike_obs [B,n]; po = p, except po = 1 for the univariate filter (kalman_filter.py:808-813).
+ *     Any output pointer may be NULL (not computed / not copied back).
+ *   - Gradients have the shape of the corresponding input (always with the batch axis, also for shared
+ *     parameters: the caller reduces over B if it shares them).  Every matrix entry is an independent
+ *     variable (no symmetrisation of dP0, dH, dQ), as pytensor.grad of the reference formulas yields.
+ *   - Return value: 0 on success; < 0 is a call failure (bad argument, unsupported configuration, CUDA
+ *     error) described by bkf_last_error().  Numerical trouble of a single series (non-PD F, non-finite
+ *     logp) never fails the call: it is reported in status[b] (BKF_STATUS_*).
+ *   - A handle owns one device, one workspace and uses one stream; it is not thread-safe.  Create one handle
+ *     per host thread / process (PyMC forks one process per chain: create lazily after the fork).
+ */
+#ifndef BKF_H
+#define BKF_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BKF_VERSION 1
+
+/* filter kinds == FILTER_FACTORY keys of pymc_extras/statespace/core/statespace.py:51-55 */
+enum { BKF_STANDARD = 0, BKF_UNIVARIATE = 1, BKF_CHOLESKY = 2 };
+enum { BKF_F64 = 0, BKF_F32 = 1 };
+enum { BKF_MEM_HOST = 0, BKF_MEM_DEVICE = 1 };
+/* parameter order == MATRIX_NAMES of pymc_extras/statespace/utils/constants.py:24 */
+enum { BKF_PARAM_A0 = 0, BKF_PARAM_P0, BKF_PARAM_C, BKF_PARAM_D, BKF_PARAM_T, BKF_PARAM_Z, BKF_PARAM_R,
+       BKF_PARAM_H, BKF_PARAM_Q, BKF_NPARAM };
+
+/* call-level error codes */
+enum { BKF_OK = 0, BKF_ERR_ARG = -1, BKF_ERR_UNSUPPORTED = -2, BKF_ERR_CUDA = -3, BKF_ERR_NOMEM = -4 };
+/* per-series status bits */
+enum { BKF_STATUS_OK = 0, BKF_STATUS_NOT_PD = 1, BKF_STATUS_NONFINITE = 2 };
+
+typedef struct bkf_handle bkf_handle;
+
+typedef struct bkf_problem {
+    int kind;              /* BKF_STANDARD / BKF_UNIVARIATE / BKF_CHOLESKY */
+    int dtype;             /* BKF_F64 / BKF_F32 */
+    int mem;               /* BKF_MEM_HOST / BKF_MEM_DEVICE: where every pointer of the call lives */
+    int B;                 /* number of independent series / parameter draws */
+    int n;                 /* time steps */
+    int m, p, r;           /* k_states, k_endog, k_posdef */
+    int y_shared;          /* 1: y is [n,p] and shared by all series */
+    unsigned shared_mask;  /* bit BKF_PARAM_x: parameter x has no batch axis */
+    unsigned tv_mask;      /* bit BKF_PARAM_x: parameter x carries a leading time axis (not supported yet) */
+    double cov_jitter;     /* JITTER_DEFAULT: 1e-8 (f64) / 1e-6 (f32), utils/constants.py:20 */
+    double missing_fill;   /* MISSING_FILL = -9999.0, utils/constants.py:19 */
+} bkf_problem;
+
+int bkf_version(void);
+int bkf_create(int device, bkf_handle** out);
+int bkf_destroy(bkf_handle* h);
+const char* bkf_last_error(const bkf_handle* h);
+/* Launch on this CUDA stream (a cudaStream_t passed as void*); NULL = the legacy default stream. */
+int bkf_set_stream(bkf_handle* h, void* cuda_stream);
+/* Number of kernels this handle has launched so far (bench.py's gpu_launches). */
+long long bkf_launch_count(const bkf_handle* h);
+/* Name of the kernel path picked by the last call ("generic_warp", "subwarp_m15", ...). */
+const char* bkf_last_path(const bkf_handle* h);
+
+/* Kernel timing for bench.py's roofline: when enabled, every kernel launch is bracketed by CUDA events on the
+ * handle's stream.  bkf_kernel_time_ms synchronises those events and returns the accumulated device time and
+ * launch count of one kernel class since the last bkf_reset_timing. */
+enum { BKF_KERNEL_FORWARD = 0, BKF_KERNEL_BACKWARD = 1, BKF_KERNEL_SMOOTHER = 2, BKF_NKERNEL };
+int bkf_enable_timing(bkf_handle* h, int on);
+int bkf_reset_timing(bkf_handle* h);
+int bkf_kernel_time_ms(bkf_handle* h, int kernel_class, double* total_ms, long long* launches);
+/* DFMA / FFMA issue-rate microbenchmark (register-resident FMA chains on every SM): the measured FP64 / FP32
+ * pipe peak in TFLOP/s that roofline fractions are quoted against (MEASURED_PEAKS.json has no such entry). */
+int bkf_measure_fma_peak(bkf_handle* h, int dtype, double* tflops);
+
+int bkf_filter_forward(bkf_handle* h, const bkf_problem* prob, const void* y, const void* a0, const void* P0,
+                       const void* c, const void* d, const void* T, const void* Z, const void* R, const void* H,
+                       const void* Q, void* filtered_states, void* predicted_states, void* observed_states,
+                       void* filtered_covariances, void* predicted_covariances, void* observed_covariances,
+                       void* loglike_obs, int* status);
+
+/* logp[b] = sum_t loglike_obs[b,t];  g_x = d(sum_t ll_cotangent[b,t] * loglike_obs[b,t]) / dx
+ * (ll_cotangent == NULL means all ones, the NUTS case).  Any g_* pointer may be NULL. */
+int bkf_filter_logp_grad(bkf_handle* h, const bkf_problem* prob, const void* y, const void* a0, const void* P0,
+                         const void* c, const void* d, const void* T, const void* Z, const void* R,
+                         const void* H, const void* Q, const void* ll_cotangent, void* logp, void* g_a0,
+                         void* g_P0, void* g_c, void* g_d, void* g_T, void* g_Z, void* g_R, void* g_H,
+                         void* g_Q, int* status);
+
+/* Uses prob->{dtype,mem,B,n,m,r,shared_mask(T,R,Q),cov_jitter}.  filtered_* are [B,n,m] / [B,n,m,m]. */
+int bkf_smooth(bkf_handle* h, const bkf_problem* prob, const void* T, const void* R, const void* Q,
+               const void* filtered_states, const void* filtered_covariances, void* smoothed_states,
+               void* smoothed_covariances, int* status);
+
+/* Filter forward followed by the smoother; loglike_obs / smoothed_* may be NULL. */
+int bkf_filter_smooth(bkf_handle* h, const bkf_problem* prob, const void* y, const void* a0, const void* P0,
+                      const void* c, const void* d, const void* T, const void* Z, const void* R, const void* H,
+                      const void* Q, void* loglike_obs, void* smoothed_states, void* smoothed_covariances,
+                      int* status);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BKF_H */

@@ -1,0 +1,500 @@
+// bkf_api.cu -- the C ABI of libbkf.so (include/bkf.h): handle, staging of host buffers, kernel dispatch.
+//
+// No torch types, no exceptions across the boundary.  Host pointers (NumPy) are staged through a grow-only
+// device workspace owned by the handle; device pointers are used in place.
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "bkf_common.cuh"
+#include "bkf_launch.h"
+
+using namespace bkf;
+
+enum Slot {
+    S_Y = 0, S_A0, S_P0, S_C, S_D, S_T, S_Z, S_R, S_H, S_Q,            // inputs
+    S_FA, S_PA, S_OM, S_FP, S_PP, S_OC, S_LL,                          // forward outputs
+    S_TRAJ, S_COT, S_LOGP, S_GA0, S_GP0, S_GC, S_GD, S_GT, S_GZ, S_GR, S_GH, S_GQ, S_STATUS,
+    S_SMA, S_SMP, S_WFA, S_WFP, S_NSLOT
+};
+
+struct bkf_handle {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    std::string err;
+    std::string path = "none";
+    long long launches = 0;
+    struct Buf { void* p = nullptr; size_t cap = 0; };
+    Buf slots[S_NSLOT];
+    // optional per-kernel timing (bench.py roofline)
+    bool timing = false;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev[BKF_NKERNEL];
+    size_t ev_used[BKF_NKERNEL] = {0, 0, 0};
+    double ms_total[BKF_NKERNEL] = {0, 0, 0};
+    long long ms_launches[BKF_NKERNEL] = {0, 0, 0};
+};
+
+// RAII bracket: records start/stop events around one kernel launch when timing is on.
+struct KernelTimer {
+    bkf_handle* h;
+    int cls;
+    cudaEvent_t stop = nullptr;
+    KernelTimer(bkf_handle* h_, int cls_) : h(h_), cls(cls_) {
+        if (!h->timing) return;
+        auto& v = h->ev[cls];
+        if (h->ev_used[cls] == v.size()) {
+            cudaEvent_t a, b;
+            cudaEventCreate(&a);
+            cudaEventCreate(&b);
+            v.emplace_back(a, b);
+        }
+        auto& pr = v[h->ev_used[cls]++];
+        cudaEventRecord(pr.first, h->stream);
+        stop = pr.second;
+    }
+    ~KernelTimer() {
+        if (stop) cudaEventRecord(stop, h->stream);
+    }
+};
+
+static void collect_timing(bkf_handle* h) {
+    for (int c = 0; c < BKF_NKERNEL; ++c) {
+        for (size_t i = 0; i < h->ev_used[c]; ++i) {
+            float ms = 0;
+            cudaEventSynchronize(h->ev[c][i].second);
+            if (cudaEventElapsedTime(&ms, h->ev[c][i].first, h->ev[c][i].second) == cudaSuccess) {
+                h->ms_total[c] += ms;
+                h->ms_launches[c] += 1;
+            }
+        }
+        h->ev_used[c] = 0;
+    }
+}
+
+static int fail(bkf_handle* h, int code, const std::string& msg) {
+    if (h) h->err = msg;
+    return code;
+}
+
+static int cuda_fail(bkf_handle* h, cudaError_t e, const char* what) {
+    return fail(h, BKF_ERR_CUDA, std::string(what) + ": " + cudaGetErrorString(e));
+}
+
+static void* ensure(bkf_handle* h, int slot, size_t bytes, int* rc) {
+    auto& b = h->slots[slot];
+    if (bytes == 0) bytes = 8;
+    if (b.cap < bytes) {
+        if (b.p) cudaFree(b.p);
+        b.p = nullptr;
+        b.cap = 0;
+        size_t want = bytes + bytes / 8;
+        cudaError_t e = cudaMalloc(&b.p, want);
+        if (e != cudaSuccess) {
+            e = cudaMalloc(&b.p, bytes);
+            want = bytes;
+        }
+        if (e != cudaSuccess) {
+            *rc = fail(h, BKF_ERR_NOMEM, std::string("cudaMalloc failed: ") + cudaGetErrorString(e));
+            cudaGetLastError();
+            return nullptr;
+        }
+        b.cap = want;
+    }
+    return b.p;
+}
+
+extern "C" int bkf_version(void) { return BKF_VERSION; }
+
+extern "C" int bkf_create(int device, bkf_handle** out) {
+    if (!out) return BKF_ERR_ARG;
+    *out = nullptr;
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || device < 0 || device >= ndev) {
+        cudaGetLastError();
+        return BKF_ERR_CUDA;  // no CUDA device: there is no CPU fallback by design
+    }
+    e = cudaSetDevice(device);
+    if (e != cudaSuccess) return BKF_ERR_CUDA;
+    bkf_handle* h = new (std::nothrow) bkf_handle();
+    if (!h) return BKF_ERR_NOMEM;
+    h->device = device;
+    *out = h;
+    return BKF_OK;
+}
+
+extern "C" int bkf_destroy(bkf_handle* h) {
+    if (!h) return BKF_OK;
+    cudaSetDevice(h->device);
+    for (auto& b : h->slots)
+        if (b.p) cudaFree(b.p);
+    for (auto& v : h->ev)
+        for (auto& pr : v) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
+    delete h;
+    return BKF_OK;
+}
+
+extern "C" const char* bkf_last_error(const bkf_handle* h) { return h ? h->err.c_str() : "null handle"; }
+extern "C" const char* bkf_last_path(const bkf_handle* h) { return h ? h->path.c_str() : "none"; }
+extern "C" long long bkf_launch_count(const bkf_handle* h) { return h ? h->launches : 0; }
+extern "C" int bkf_enable_timing(bkf_handle* h, int on) {
+    if (!h) return BKF_ERR_ARG;
+    h->timing = on != 0;
+    return BKF_OK;
+}
+extern "C" int bkf_reset_timing(bkf_handle* h) {
+    if (!h) return BKF_ERR_ARG;
+    collect_timing(h);
+    for (int c = 0; c < BKF_NKERNEL; ++c) { h->ms_total[c] = 0; h->ms_launches[c] = 0; }
+    return BKF_OK;
+}
+extern "C" int bkf_kernel_time_ms(bkf_handle* h, int cls, double* total_ms, long long* launches) {
+    if (!h || cls < 0 || cls >= BKF_NKERNEL) return BKF_ERR_ARG;
+    cudaSetDevice(h->device);
+    collect_timing(h);
+    if (total_ms) *total_ms = h->ms_total[cls];
+    if (launches) *launches = h->ms_launches[cls];
+    return BKF_OK;
+}
+
+// FMA-pipe peak: 8 independent FMA chains per thread, 1024 threads x 4 CTAs per SM, no memory traffic.
+template <typename R>
+__global__ void fma_peak_kernel(R* out, int iters) {
+    R a0 = R(threadIdx.x) * R(1e-6), a1 = a0 + R(1), a2 = a0 + R(2), a3 = a0 + R(3), a4 = a0 + R(4), a5 = a0 + R(5),
+      a6 = a0 + R(6), a7 = a0 + R(7);
+    const R x = R(0.999999), y = R(1e-9);
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            a0 = fma(a0, x, y); a1 = fma(a1, x, y); a2 = fma(a2, x, y); a3 = fma(a3, x, y);
+            a4 = fma(a4, x, y); a5 = fma(a5, x, y); a6 = fma(a6, x, y); a7 = fma(a7, x, y);
+        }
+    }
+    R s = ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
+    if (s == R(-1)) out[0] = s;
+}
+
+extern "C" int bkf_measure_fma_peak(bkf_handle* h, int dtype, double* tflops) {
+    if (!h || !tflops) return BKF_ERR_ARG;
+    cudaError_t e = cudaSetDevice(h->device);
+    if (e != cudaSuccess) return cuda_fail(h, e, "cudaSetDevice");
+    int rc = BKF_OK;
+    void* out = ensure(h, S_STATUS, 64, &rc);
+    if (!out) return rc;
+    cudaDeviceProp prop;
+    cudaGetDeviceProperties(&prop, h->device);
+    const int grid = prop.multiProcessorCount * 4, block = 512;
+    const int iters = dtype == BKF_F64 ? 4096 : 16384;
+    cudaEvent_t a, b;
+    cudaEventCreate(&a);
+    cudaEventCreate(&b);
+    double best = 0;
+    for (int rep = 0; rep < 4; ++rep) {
+        cudaEventRecord(a, h->stream);
+        if (dtype == BKF_F64) fma_peak_kernel<double><<<grid, block, 0, h->stream>>>((double*)out, iters);
+        else fma_peak_kernel<float><<<grid, block, 0, h->stream>>>((float*)out, iters);
+        cudaEventRecord(b, h->stream);
+        cudaEventSynchronize(b);
+        float ms = 0;
+        cudaEventElapsedTime(&ms, a, b);
+        double flops = 2.0 * 64.0 * iters * (double)grid * block;
+        if (rep > 0 && ms > 0) best = fmax(best, flops / (ms * 1e-3) / 1e12);
+    }
+    cudaEventDestroy(a);
+    cudaEventDestroy(b);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return cuda_fail(h, e, "fma peak kernel");
+    *tflops = best;
+    return BKF_OK;
+}
+
+extern "C" int bkf_set_stream(bkf_handle* h, void* s) {
+    if (!h) return BKF_ERR_ARG;
+    h->stream = reinterpret_cast<cudaStream_t>(s);
+    return BKF_OK;
+}
+
+// ----------------------------------------------------------------------------------------------------
+static size_t param_elems(const bkf_problem* P, int which) {
+    size_t m = P->m, p = P->p, r = P->r;
+    switch (which) {
+        case BKF_PARAM_A0: case BKF_PARAM_C: return m;
+        case BKF_PARAM_P0: case BKF_PARAM_T: return m * m;
+        case BKF_PARAM_D: return p;
+        case BKF_PARAM_Z: return p * m;
+        case BKF_PARAM_R: return m * r;
+        case BKF_PARAM_H: return p * p;
+        case BKF_PARAM_Q: return r * r;
+    }
+    return 0;
+}
+
+static int validate(bkf_handle* h, const bkf_problem* P, bool need_obs) {
+    if (!h) return BKF_ERR_ARG;
+    if (!P) return fail(h, BKF_ERR_ARG, "null problem");
+    if (P->kind < BKF_STANDARD || P->kind > BKF_CHOLESKY) return fail(h, BKF_ERR_ARG, "unknown filter kind");
+    if (P->dtype != BKF_F64 && P->dtype != BKF_F32) return fail(h, BKF_ERR_ARG, "unknown dtype");
+    if (P->mem != BKF_MEM_HOST && P->mem != BKF_MEM_DEVICE) return fail(h, BKF_ERR_ARG, "unknown memory space");
+    if (P->B < 0 || P->n < 1 || P->m < 1 || P->r < 1 || (need_obs && P->p < 1))
+        return fail(h, BKF_ERR_ARG, "non-positive dimension");
+    if (P->tv_mask != 0)
+        return fail(h, BKF_ERR_UNSUPPORTED, "time-varying state-space matrices are not supported yet");
+    cudaError_t e = cudaSetDevice(h->device);
+    if (e != cudaSuccess) return cuda_fail(h, e, "cudaSetDevice");
+    return BKF_OK;
+}
+
+// Stage an input: returns the device pointer to use (the caller's own pointer in device mode).
+template <typename R>
+static const R* stage_in(bkf_handle* h, const bkf_problem* P, int slot, const void* src, size_t elems, int* rc) {
+    if (*rc != BKF_OK || !src) return reinterpret_cast<const R*>(src);
+    if (P->mem == BKF_MEM_DEVICE) return reinterpret_cast<const R*>(src);
+    void* d = ensure(h, slot, elems * sizeof(R), rc);
+    if (!d) return nullptr;
+    cudaError_t e = cudaMemcpyAsync(d, src, elems * sizeof(R), cudaMemcpyHostToDevice, h->stream);
+    if (e != cudaSuccess) { *rc = cuda_fail(h, e, "H2D copy"); return nullptr; }
+    return reinterpret_cast<const R*>(d);
+}
+
+// Prepare an output: device pointer the kernels write to (NULL if the caller passed NULL).
+template <typename R>
+static R* stage_out(bkf_handle* h, const bkf_problem* P, int slot, void* dst, size_t elems, int* rc) {
+    if (*rc != BKF_OK || !dst) return nullptr;
+    if (P->mem == BKF_MEM_DEVICE) return reinterpret_cast<R*>(dst);
+    return reinterpret_cast<R*>(ensure(h, slot, elems * sizeof(R), rc));
+}
+
+template <typename R>
+static void copy_back(bkf_handle* h, const bkf_problem* P, void* dst, const R* dev, size_t elems, int* rc) {
+    if (*rc != BKF_OK || !dst || P->mem == BKF_MEM_DEVICE) return;
+    cudaError_t e = cudaMemcpyAsync(dst, dev, elems * sizeof(R), cudaMemcpyDeviceToHost, h->stream);
+    if (e != cudaSuccess) *rc = cuda_fail(h, e, "D2H copy");
+}
+
+static int finish(bkf_handle* h, const bkf_problem* P, int rc) {
+    if (rc != BKF_OK) return rc;
+    if (P->mem == BKF_MEM_HOST) {
+        cudaError_t e = cudaStreamSynchronize(h->stream);
+        if (e != cudaSuccess) return cuda_fail(h, e, "kernel execution");
+    } else {
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) return cuda_fail(h, e, "kernel launch");
+    }
+    return BKF_OK;
+}
+
+template <typename R>
+static void fill_inputs(bkf_handle* h, const bkf_problem* P, KArgs<R>& g, const void* y, const void* const* prm,
+                        int* rc) {
+    std::memset(&g, 0, sizeof(g));
+    g.kind = P->kind; g.B = P->B; g.n = P->n; g.m = P->m; g.p = P->p; g.r = P->r; g.y_shared = P->y_shared;
+    g.shared_mask = P->shared_mask;
+    g.jitter = (R)P->cov_jitter;
+    g.fill = (R)P->missing_fill;
+    size_t B = P->B;
+    if (y) g.y = stage_in<R>(h, P, S_Y, y, (P->y_shared ? 1 : B) * (size_t)P->n * P->p, rc);
+    const R** dst[BKF_NPARAM] = {&g.a0, &g.P0, &g.c, &g.d, &g.T, &g.Z, &g.Rm, &g.H, &g.Q};
+    for (int i = 0; i < BKF_NPARAM; ++i) {
+        if (!prm[i]) continue;
+        size_t nb = ((P->shared_mask >> i) & 1u) ? 1 : B;
+        *dst[i] = stage_in<R>(h, P, S_A0 + i, prm[i], nb * param_elems(P, i), rc);
+    }
+}
+
+static bool any_null(const void* const* p, int n) {
+    for (int i = 0; i < n; ++i)
+        if (!p[i]) return true;
+    return false;
+}
+
+// ----------------------------------------------------------------------------------------------------
+template <typename R>
+static int forward_impl(bkf_handle* h, const bkf_problem* P, const void* y, const void* const* prm, void* fa,
+                        void* pa, void* om, void* fP, void* pP, void* oc, void* ll, int* status) {
+    int rc = BKF_OK;
+    KArgs<R> g;
+    fill_inputs<R>(h, P, g, y, prm, &rc);
+    const size_t B = P->B, n = P->n, m = P->m, p = P->p;
+    const size_t po = P->kind == BKF_UNIVARIATE ? 1 : p;
+    g.filt_a = stage_out<R>(h, P, S_FA, fa, B * n * m, &rc);
+    g.pred_a = stage_out<R>(h, P, S_PA, pa, B * n * m, &rc);
+    g.obs_mu = stage_out<R>(h, P, S_OM, om, B * n * po, &rc);
+    g.filt_P = stage_out<R>(h, P, S_FP, fP, B * n * m * m, &rc);
+    g.pred_P = stage_out<R>(h, P, S_PP, pP, B * n * m * m, &rc);
+    g.obs_cov = stage_out<R>(h, P, S_OC, oc, B * n * po * po, &rc);
+    g.ll = stage_out<R>(h, P, S_LL, ll, B * n, &rc);
+    int* dstatus = nullptr;
+    if (status) dstatus = P->mem == BKF_MEM_DEVICE ? status : (int*)ensure(h, S_STATUS, B * sizeof(int), &rc);
+    g.status = dstatus;
+    if (rc != BKF_OK) return rc;
+    if (B == 0) return BKF_OK;
+    const char* err = "";
+    { KernelTimer kt(h, BKF_KERNEL_FORWARD); rc = gen::launch_forward<R>(g, h->stream, &err); }
+    if (rc != BKF_OK) return fail(h, rc, err);
+    h->path = "generic_warp";
+    h->launches += 1;
+    copy_back<R>(h, P, fa, g.filt_a, B * n * m, &rc);
+    copy_back<R>(h, P, pa, g.pred_a, B * n * m, &rc);
+    copy_back<R>(h, P, om, g.obs_mu, B * n * po, &rc);
+    copy_back<R>(h, P, fP, g.filt_P, B * n * m * m, &rc);
+    copy_back<R>(h, P, pP, g.pred_P, B * n * m * m, &rc);
+    copy_back<R>(h, P, oc, g.obs_cov, B * n * po * po, &rc);
+    copy_back<R>(h, P, ll, g.ll, B * n, &rc);
+    if (status && P->mem == BKF_MEM_HOST && rc == BKF_OK) {
+        cudaError_t e = cudaMemcpyAsync(status, dstatus, B * sizeof(int), cudaMemcpyDeviceToHost, h->stream);
+        if (e != cudaSuccess) rc = cuda_fail(h, e, "D2H copy");
+    }
+    return finish(h, P, rc);
+}
+
+extern "C" int bkf_filter_forward(bkf_handle* h, const bkf_problem* P, const void* y, const void* a0, const void* P0,
+                                  const void* c, const void* d, const void* T, const void* Z, const void* R,
+                                  const void* H, const void* Q, void* fa, void* pa, void* om, void* fP, void* pP,
+                                  void* oc, void* ll, int* status) {
+    int rc = validate(h, P, true);
+    if (rc != BKF_OK) return rc;
+    const void* prm[BKF_NPARAM] = {a0, P0, c, d, T, Z, R, H, Q};
+    if (!y || any_null(prm, BKF_NPARAM)) return fail(h, BKF_ERR_ARG, "null input pointer");
+    return P->dtype == BKF_F64 ? forward_impl<double>(h, P, y, prm, fa, pa, om, fP, pP, oc, ll, status)
+                               : forward_impl<float>(h, P, y, prm, fa, pa, om, fP, pP, oc, ll, status);
+}
+
+// ----------------------------------------------------------------------------------------------------
+template <typename R>
+static int logp_grad_impl(bkf_handle* h, const bkf_problem* P, const void* y, const void* const* prm,
+                          const void* cot, void* logp, void* const* grads, int* status) {
+    int rc = BKF_OK;
+    KArgs<R> g;
+    fill_inputs<R>(h, P, g, y, prm, &rc);
+    const size_t B = P->B, n = P->n, m = P->m;
+    bool want_grad = false;
+    for (int i = 0; i < BKF_NPARAM; ++i) want_grad = want_grad || grads[i];
+    if (cot) g.ll_cot = stage_in<R>(h, P, S_COT, cot, B * n, &rc);
+    g.logp = stage_out<R>(h, P, S_LOGP, logp, B, &rc);
+    R** gdst[BKF_NPARAM] = {&g.g_a0, &g.g_P0, &g.g_c, &g.g_d, &g.g_T, &g.g_Z, &g.g_R, &g.g_H, &g.g_Q};
+    for (int i = 0; i < BKF_NPARAM; ++i)
+        *gdst[i] = stage_out<R>(h, P, S_GA0 + i, grads[i], B * param_elems(P, i), &rc);
+    if (want_grad) g.traj = (R*)ensure(h, S_TRAJ, B * n * (m + m * m) * sizeof(R), &rc);
+    int* dstatus = nullptr;
+    if (status) dstatus = P->mem == BKF_MEM_DEVICE ? status : (int*)ensure(h, S_STATUS, B * sizeof(int), &rc);
+    g.status = dstatus;
+    if (rc != BKF_OK) return rc;
+    if (B == 0) return BKF_OK;
+    const char* err = "";
+    { KernelTimer kt(h, BKF_KERNEL_FORWARD); rc = gen::launch_forward<R>(g, h->stream, &err); }
+    if (rc != BKF_OK) return fail(h, rc, err);
+    h->launches += 1;
+    if (want_grad) {
+        { KernelTimer kt(h, BKF_KERNEL_BACKWARD); rc = gen::launch_backward<R>(g, h->stream, &err); }
+        if (rc != BKF_OK) return fail(h, rc, err);
+        h->launches += 1;
+    }
+    h->path = "generic_warp";
+    copy_back<R>(h, P, logp, g.logp, B, &rc);
+    for (int i = 0; i < BKF_NPARAM; ++i) copy_back<R>(h, P, grads[i], *gdst[i], B * param_elems(P, i), &rc);
+    if (status && P->mem == BKF_MEM_HOST && rc == BKF_OK) {
+        cudaError_t e = cudaMemcpyAsync(status, dstatus, B * sizeof(int), cudaMemcpyDeviceToHost, h->stream);
+        if (e != cudaSuccess) rc = cuda_fail(h, e, "D2H copy");
+    }
+    return finish(h, P, rc);
+}
+
+extern "C" int bkf_filter_logp_grad(bkf_handle* h, const bkf_problem* P, const void* y, const void* a0,
+                                    const void* P0, const void* c, const void* d, const void* T, const void* Z,
+                                    const void* R, const void* H, const void* Q, const void* ll_cotangent,
+                                    void* logp, void* g_a0, void* g_P0, void* g_c, void* g_d, void* g_T, void* g_Z,
+                                    void* g_R, void* g_H, void* g_Q, int* status) {
+    int rc = validate(h, P, true);
+    if (rc != BKF_OK) return rc;
+    const void* prm[BKF_NPARAM] = {a0, P0, c, d, T, Z, R, H, Q};
+    if (!y || any_null(prm, BKF_NPARAM)) return fail(h, BKF_ERR_ARG, "null input pointer");
+    void* grads[BKF_NPARAM] = {g_a0, g_P0, g_c, g_d, g_T, g_Z, g_R, g_H, g_Q};
+    return P->dtype == BKF_F64 ? logp_grad_impl<double>(h, P, y, prm, ll_cotangent, logp, grads, status)
+                               : logp_grad_impl<float>(h, P, y, prm, ll_cotangent, logp, grads, status);
+}
+
+// ----------------------------------------------------------------------------------------------------
+template <typename R>
+static int smooth_impl(bkf_handle* h, const bkf_problem* P, const void* T, const void* Rm, const void* Q,
+                       const void* fa, const void* fP, void* sa, void* sP, int* status) {
+    int rc = BKF_OK;
+    KArgs<R> g;
+    const void* prm[BKF_NPARAM] = {nullptr, nullptr, nullptr, nullptr, T, nullptr, Rm, nullptr, Q};
+    bkf_problem P2 = *P;
+    P2.p = P2.p > 0 ? P2.p : 1;
+    fill_inputs<R>(h, &P2, g, nullptr, prm, &rc);
+    const size_t B = P->B, n = P->n, m = P->m;
+    g.sm_filt_a = stage_in<R>(h, P, S_WFA, fa, B * n * m, &rc);
+    g.sm_filt_P = stage_in<R>(h, P, S_WFP, fP, B * n * m * m, &rc);
+    g.sm_a = stage_out<R>(h, P, S_SMA, sa, B * n * m, &rc);
+    g.sm_P = stage_out<R>(h, P, S_SMP, sP, B * n * m * m, &rc);
+    (void)status;
+    if (rc != BKF_OK) return rc;
+    if (B == 0) return BKF_OK;
+    const char* err = "";
+    { KernelTimer kt(h, BKF_KERNEL_SMOOTHER); rc = gen::launch_smoother<R>(g, h->stream, &err); }
+    if (rc != BKF_OK) return fail(h, rc, err);
+    h->launches += 1;
+    h->path = "generic_warp";
+    copy_back<R>(h, P, sa, g.sm_a, B * n * m, &rc);
+    copy_back<R>(h, P, sP, g.sm_P, B * n * m * m, &rc);
+    return finish(h, P, rc);
+}
+
+extern "C" int bkf_smooth(bkf_handle* h, const bkf_problem* P, const void* T, const void* R, const void* Q,
+                          const void* fa, const void* fP, void* sa, void* sP, int* status) {
+    int rc = validate(h, P, false);
+    if (rc != BKF_OK) return rc;
+    if (!T || !R || !Q || !fa || !fP) return fail(h, BKF_ERR_ARG, "null input pointer");
+    return P->dtype == BKF_F64 ? smooth_impl<double>(h, P, T, R, Q, fa, fP, sa, sP, status)
+                               : smooth_impl<float>(h, P, T, R, Q, fa, fP, sa, sP, status);
+}
+
+// ----------------------------------------------------------------------------------------------------
+template <typename R>
+static int filter_smooth_impl(bkf_handle* h, const bkf_problem* P, const void* y, const void* const* prm, void* ll,
+                              void* sa, void* sP, int* status) {
+    int rc = BKF_OK;
+    KArgs<R> g;
+    fill_inputs<R>(h, P, g, y, prm, &rc);
+    const size_t B = P->B, n = P->n, m = P->m;
+    g.ll = stage_out<R>(h, P, S_LL, ll, B * n, &rc);
+    g.filt_a = (R*)ensure(h, S_WFA, B * n * m * sizeof(R), &rc);
+    g.filt_P = (R*)ensure(h, S_WFP, B * n * m * m * sizeof(R), &rc);
+    int* dstatus = nullptr;
+    if (status) dstatus = P->mem == BKF_MEM_DEVICE ? status : (int*)ensure(h, S_STATUS, B * sizeof(int), &rc);
+    g.status = dstatus;
+    g.sm_filt_a = g.filt_a;
+    g.sm_filt_P = g.filt_P;
+    g.sm_a = stage_out<R>(h, P, S_SMA, sa, B * n * m, &rc);
+    g.sm_P = stage_out<R>(h, P, S_SMP, sP, B * n * m * m, &rc);
+    if (rc != BKF_OK) return rc;
+    if (B == 0) return BKF_OK;
+    const char* err = "";
+    { KernelTimer kt(h, BKF_KERNEL_FORWARD); rc = gen::launch_forward<R>(g, h->stream, &err); }
+    if (rc != BKF_OK) return fail(h, rc, err);
+    { KernelTimer kt(h, BKF_KERNEL_SMOOTHER); rc = gen::launch_smoother<R>(g, h->stream, &err); }
+    if (rc != BKF_OK) return fail(h, rc, err);
+    h->launches += 2;
+    h->path = "generic_warp";
+    copy_back<R>(h, P, ll, g.ll, B * n, &rc);
+    copy_back<R>(h, P, sa, g.sm_a, B * n * m, &rc);
+    copy_back<R>(h, P, sP, g.sm_P, B * n * m * m, &rc);
+    if (status && P->mem == BKF_MEM_HOST && rc == BKF_OK) {
+        cudaError_t e = cudaMemcpyAsync(status, dstatus, B * sizeof(int), cudaMemcpyDeviceToHost, h->stream);
+        if (e != cudaSuccess) rc = cuda_fail(h, e, "D2H copy");
+    }
+    return finish(h, P, rc);
+}
+
+extern "C" int bkf_filter_smooth(bkf_handle* h, const bkf_problem* P, const void* y, const void* a0, const void* P0,
+                                 const void* c, const void* d, const void* T, const void* Z, const void* R,
+                                 const void* H, const void* Q, void* ll, void* sa, void* sP, int* status) {
+    int rc = validate(h, P, true);
+    if (rc != BKF_OK) return rc;
+    const void* prm[BKF_NPARAM] = {a0, P0, c, d, T, Z, R, H, Q};
+    if (!y || any_null(prm, BKF_NPARAM)) return fail(h, BKF_ERR_ARG, "null input pointer");
+    return P->dtype == BKF_F64 ? filter_smooth_impl<double>(h, P, y, prm, ll, sa, sP, status)
+                               : filter_smooth_impl<float>(h, P, y, prm, ll, sa, sP, status);
+}

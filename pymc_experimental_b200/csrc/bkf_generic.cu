@@ -1,0 +1,1006 @@
+// bkf_generic.cu -- generic (any m, p, r that fits shared memory) warp-per-series kernels.
+//
+// One warp owns one time-sequential filter; every matrix of that series lives in the warp's shared-memory
+// arena and the warp's 32 lanes split each small dense operation.  This family is the always-available
+// correct path (and the fallback for shapes without a specialised kernel); the hot shapes of BASELINE.json
+// are served by the register-tiled kernels in bkf_subwarp.cu / bkf_thread.cu.
+//
+// Formulas: see bkf_common.cuh for the reference file:line map; the adjoint recurrences are those of
+// SURVEY.md Appendix B (Standard) and their rank-1 analogue (Univariate).
+#include "bkf_common.cuh"
+#include "bkf_launch.h"
+
+namespace bkf {
+namespace gen {
+
+enum { SET = 0, ADD = 1, SUB = 2 };
+
+// C[M,N] (row-major) (op)= sum_k A(i,k) * B(k,j) with A(i,k) = A[i*as0 + k*as1], B(k,j) = B[k*bs0 + j*bs1]
+template <int MODE, typename R>
+__device__ __forceinline__ void mm(R* __restrict__ C, const R* __restrict__ A, int as0, int as1,
+                                   const R* __restrict__ Bm, int bs0, int bs1, int M, int N, int K, int lane) {
+    for (int idx = lane; idx < M * N; idx += 32) {
+        int i = idx / N, j = idx - i * N;
+        const R* a = A + i * as0;
+        const R* b = Bm + j * bs1;
+        R acc = 0;
+        for (int k = 0; k < K; ++k) acc = fma(a[k * as1], b[k * bs0], acc);
+        if (MODE == SET) C[idx] = acc;
+        else if (MODE == ADD) C[idx] += acc;
+        else C[idx] -= acc;
+    }
+    __syncwarp();
+}
+
+// y[M] (op)= sum_k A(i,k) x[k]
+template <int MODE, typename R>
+__device__ __forceinline__ void mv(R* __restrict__ y, const R* __restrict__ A, int as0, int as1,
+                                   const R* __restrict__ x, int M, int K, int lane) {
+    for (int i = lane; i < M; i += 32) {
+        R acc = 0;
+        for (int k = 0; k < K; ++k) acc = fma(A[i * as0 + k * as1], x[k], acc);
+        if (MODE == SET) y[i] = acc;
+        else if (MODE == ADD) y[i] += acc;
+        else y[i] -= acc;
+    }
+    __syncwarp();
+}
+
+template <typename R>
+__device__ __forceinline__ void wcopy(R* __restrict__ dst, const R* __restrict__ src, int n, int lane) {
+    for (int i = lane; i < n; i += 32) dst[i] = src[i];
+    __syncwarp();
+}
+template <typename R>
+__device__ __forceinline__ void wzero(R* dst, int n, int lane) {
+    for (int i = lane; i < n; i += 32) dst[i] = 0;
+    __syncwarp();
+}
+
+// D = 0.5 (X + X^T) [+ Add] [+ jit * I]      (utilities.py:57-59 followed by stabilize :50-54)
+template <typename R>
+__device__ __forceinline__ void sym_into(R* __restrict__ D, const R* __restrict__ X, const R* __restrict__ Add,
+                                         R jit, int m, int lane) {
+    for (int idx = lane; idx < m * m; idx += 32) {
+        int i = idx / m, j = idx - i * m;
+        R v = R(0.5) * (X[idx] + X[j * m + i]);
+        if (Add) v += Add[idx];
+        if (i == j) v += jit;
+        D[idx] = v;
+    }
+    __syncwarp();
+}
+
+// In-place lower Cholesky of the k x k matrix A (reads the lower triangle), executed by lane 0.
+// Returns false when a pivot is not positive.
+template <typename R>
+__device__ bool chol_lower(R* A, int k, int lane) {
+    int ok = 1;
+    if (lane == 0) {
+        for (int j = 0; j < k; ++j) {
+            R s = A[j * k + j];
+            for (int q = 0; q < j; ++q) s -= A[j * k + q] * A[j * k + q];
+            if (!(s > 0)) { ok = 0; s = R(NAN); }
+            R ljj = sqrt(s);
+            A[j * k + j] = ljj;
+            for (int i = j + 1; i < k; ++i) {
+                R t = A[i * k + j];
+                for (int q = 0; q < j; ++q) t -= A[i * k + q] * A[j * k + q];
+                A[i * k + j] = t / ljj;
+            }
+        }
+    }
+    ok = __shfl_sync(0xffffffffu, ok, 0);
+    __syncwarp();
+    return ok != 0;
+}
+
+// x <- (L L^T)^{-1} x for one right-hand side held by ONE lane (x has stride xs).
+template <typename R>
+__device__ __forceinline__ void chol_solve_vec(const R* L, int k, R* x, int xs) {
+    for (int i = 0; i < k; ++i) {
+        R t = x[i * xs];
+        for (int q = 0; q < i; ++q) t -= L[i * k + q] * x[q * xs];
+        x[i * xs] = t / L[i * k + i];
+    }
+    for (int i = k - 1; i >= 0; --i) {
+        R t = x[i * xs];
+        for (int q = i + 1; q < k; ++q) t -= L[q * k + i] * x[q * xs];
+        x[i * xs] = t / L[i * k + i];
+    }
+}
+
+// ----------------------------------------------------------------------------------------------------
+// shared-memory arena of one warp
+// ----------------------------------------------------------------------------------------------------
+template <typename R>
+struct Arena {
+    // parameters
+    R *T, *Z, *RQR, *H, *c, *d;
+    // carried prediction and per-step scratch
+    R *a, *P, *w, *ym, *v, *Zm, *Hm, *PZT, *F, *Lf, *K, *KH, *Lm, *X, *Y, *Pf, *af, *wv;
+    // univariate
+    R *Kst, *Fst, *vst, *zfst, *Pu;
+    // backward
+    R *abar, *Pbar, *G, *gT, *gZ, *gH, *gc, *gd, *Gsum, *Kbar, *PZTbar, *Fbar, *Finv, *Lbar, *Zmbar, *Hmbar,
+        *vbar, *afbar, *tmp_mp;
+};
+
+__host__ __device__ inline size_t arena_elems(int m, int p, int r, bool backward) {
+    size_t mm_ = (size_t)m * m, mp = (size_t)m * p, pp = (size_t)p * p;
+    size_t fwd = /*T,RQR,P,Lm,X,Y,Pf,Pu*/ 8 * mm_ + /*Z,Zm,PZT,K,KH,Kst*/ 6 * mp + /*H,Hm,F,Lf*/ 4 * pp +
+                 /*c,a,af*/ 3 * (size_t)m + /*d,w,ym,v,wv,Fst,vst,zfst*/ 8 * (size_t)p;
+    size_t bwd = /*Pbar,G,gT,Gsum,Lbar*/ 5 * mm_ + /*gZ,Kbar,PZTbar,Zmbar,tmp_mp*/ 5 * mp +
+                 /*gH,Fbar,Finv,Hmbar*/ 4 * pp + /*abar,gc,afbar*/ 3 * (size_t)m + /*gd,vbar*/ 2 * (size_t)p;
+    size_t tot = fwd + (backward ? bwd : 0);
+    return (tot + 1) & ~(size_t)1;
+}
+
+template <typename R>
+__device__ void carve(Arena<R>& A, R* s, int m, int p, int r, bool backward) {
+    size_t mm_ = (size_t)m * m, mp = (size_t)m * p, pp = (size_t)p * p;
+    auto take = [&](size_t n) { R* q = s; s += n; return q; };
+    A.T = take(mm_); A.RQR = take(mm_); A.P = take(mm_); A.Lm = take(mm_); A.X = take(mm_); A.Y = take(mm_);
+    A.Pf = take(mm_); A.Pu = take(mm_);
+    A.Z = take(mp); A.Zm = take(mp); A.PZT = take(mp); A.K = take(mp); A.KH = take(mp); A.Kst = take(mp);
+    A.H = take(pp); A.Hm = take(pp); A.F = take(pp); A.Lf = take(pp);
+    A.c = take(m); A.a = take(m); A.af = take(m);
+    A.d = take(p); A.w = take(p); A.ym = take(p); A.v = take(p); A.wv = take(p); A.Fst = take(p);
+    A.vst = take(p); A.zfst = take(p);
+    if (backward) {
+        A.Pbar = take(mm_); A.G = take(mm_); A.gT = take(mm_); A.Gsum = take(mm_); A.Lbar = take(mm_);
+        A.gZ = take(mp); A.Kbar = take(mp); A.PZTbar = take(mp); A.Zmbar = take(mp); A.tmp_mp = take(mp);
+        A.gH = take(pp); A.Fbar = take(pp); A.Finv = take(pp); A.Hmbar = take(pp);
+        A.abar = take(m); A.gc = take(m); A.afbar = take(m);
+        A.gd = take(p); A.vbar = take(p);
+    }
+}
+
+// dst = sym(R Q R^T) for global-memory R [m,r], Q [r,r] (once per series; no r <= m assumption). tmp: m*m.
+template <typename R>
+__device__ void rqr_sym(R* dst, R* tmp, const R* __restrict__ Rg, const R* __restrict__ Qg, int m, int r, int lane) {
+    for (int idx = lane; idx < m * m; idx += 32) {
+        int i = idx / m, j = idx - i * m;
+        R acc = 0;
+        for (int k = 0; k < r; ++k) {
+            R rq = 0;  // (R Q)[i,k]
+            for (int l = 0; l < r; ++l) rq = fma(Rg[i * r + l], Qg[l * r + k], rq);
+            acc = fma(rq, Rg[j * r + k], acc);
+        }
+        tmp[idx] = acc;
+    }
+    __syncwarp();
+    sym_into<R>(dst, tmp, nullptr, R(0), m, lane);
+}
+
+// Load T, Z, H, c, d and RQR = sym(R Q R^T) (kalman_filter.py:408, second term) for series b.
+template <typename R>
+__device__ void load_params(const KArgs<R>& g, Arena<R>& A, int b, int lane) {
+    const int m = g.m, p = g.p, r = g.r;
+    wcopy(A.T, param_ptr(g.T, g.shared_mask, BKF_PARAM_T, b, (size_t)m * m), m * m, lane);
+    wcopy(A.Z, param_ptr(g.Z, g.shared_mask, BKF_PARAM_Z, b, (size_t)p * m), p * m, lane);
+    wcopy(A.H, param_ptr(g.H, g.shared_mask, BKF_PARAM_H, b, (size_t)p * p), p * p, lane);
+    wcopy(A.c, param_ptr(g.c, g.shared_mask, BKF_PARAM_C, b, (size_t)m), m, lane);
+    wcopy(A.d, param_ptr(g.d, g.shared_mask, BKF_PARAM_D, b, (size_t)p), p, lane);
+    const R* Rg = param_ptr(g.Rm, g.shared_mask, BKF_PARAM_R, b, (size_t)m * r);
+    const R* Qg = param_ptr(g.Q, g.shared_mask, BKF_PARAM_Q, b, (size_t)r * r);
+    rqr_sym(A.RQR, A.Y, Rg, Qg, m, r, lane);
+}
+
+// a+ = T af + c ; P+ = sym(T Pf T^T) + RQR         (kalman_filter.py:407-408).  Leaves X = T Pf.
+template <typename R>
+__device__ __forceinline__ void predict(Arena<R>& A, int m, int lane) {
+    mv<SET>(A.a, A.T, m, 1, A.af, m, m, lane);
+    for (int i = lane; i < m; i += 32) A.a[i] += A.c[i];
+    mm<SET>(A.X, A.T, m, 1, A.Pf, m, 1, m, m, m, lane);
+    mm<SET>(A.Y, A.X, m, 1, A.T, 1, m, m, m, m, lane);
+    sym_into<R>(A.P, A.Y, A.RQR, R(0), m, lane);
+}
+
+// ----------------------------------------------------------------------------------------------------
+// StandardFilter.update + stabilize (kalman_filter.py:352-360, 594-617, 536).
+// In: A.a, A.P, y_t.  Out: A.af, A.Pf (jittered), A.v, A.Zm, A.Hm, A.PZT, A.F, A.Lf, A.K, A.Lm, A.wv.
+// Returns ll; *flag_out = all-missing; *ok = F positive definite.
+// ----------------------------------------------------------------------------------------------------
+template <typename R>
+__device__ R std_update(const KArgs<R>& g, Arena<R>& A, const R* yt, R* obs_mu, R* obs_cov, bool* flag_out,
+                        bool* ok, int lane) {
+    const int m = g.m, p = g.p;
+    for (int o = lane; o < p; o += 32) {
+        R yv = yt[o];
+        bool miss = is_missing(yv, g.fill, true);
+        A.w[o] = miss ? R(0) : R(1);
+        A.ym[o] = miss ? R(0) : yv;
+    }
+    __syncwarp();
+    R nobs = 0;
+    for (int o = 0; o < p; ++o) nobs += A.w[o];
+    const bool flag = (nobs == R(0));
+    for (int idx = lane; idx < p * m; idx += 32) A.Zm[idx] = A.w[idx / m] * A.Z[idx];
+    for (int idx = lane; idx < p * p; idx += 32) A.Hm[idx] = A.w[idx / p] * A.H[idx];
+    __syncwarp();
+    // y_hat = d + Zm a ; v = ym - y_hat
+    for (int o = lane; o < p; o += 32) {
+        R acc = 0;
+        for (int j = 0; j < m; ++j) acc = fma(A.Zm[o * m + j], A.a[j], acc);
+        R yh = A.d[o] + acc;
+        A.v[o] = A.ym[o] - yh;
+        if (obs_mu) obs_mu[o] = yh;
+    }
+    // PZT = P Zm^T ; F = Zm PZT + (Hm + eps I)
+    mm<SET>(A.PZT, A.P, m, 1, A.Zm, 1, m, m, p, m, lane);
+    mm<SET>(A.F, A.Zm, m, 1, A.PZT, p, 1, p, p, m, lane);
+    for (int idx = lane; idx < p * p; idx += 32) {
+        int o = idx / p, q = idx - o * p;
+        R f = A.F[idx] + (A.Hm[idx] + (o == q ? g.jitter : R(0)));
+        A.F[idx] = f;
+        A.Lf[idx] = f;
+        if (obs_cov) obs_cov[idx] = f;
+    }
+    __syncwarp();
+    *ok = chol_lower(A.Lf, p, lane);
+    // K = PZT F^{-1} (row i of K solves F k = pzt_i, F symmetric) ; wv = F^{-1} v
+    for (int idx = lane; idx < m * p; idx += 32) A.K[idx] = A.PZT[idx];
+    for (int o = lane; o < p; o += 32) A.wv[o] = A.v[o];
+    __syncwarp();
+    for (int i = lane; i < m + 1; i += 32) {
+        if (i < m) chol_solve_vec(A.Lf, p, A.K + i * p, 1);
+        else chol_solve_vec(A.Lf, p, A.wv, 1);
+    }
+    __syncwarp();
+    // Lm = I - K Zm ; af = a + K v
+    mm<SET>(A.Lm, A.K, p, 1, A.Zm, m, 1, m, m, p, lane);
+    for (int idx = lane; idx < m * m; idx += 32) A.Lm[idx] = ((idx / m) == (idx % m) ? R(1) : R(0)) - A.Lm[idx];
+    for (int i = lane; i < m; i += 32) {
+        R acc = 0;
+        for (int o = 0; o < p; ++o) acc = fma(A.K[i * p + o], A.v[o], acc);
+        A.af[i] = A.a[i] + acc;
+    }
+    __syncwarp();
+    // Pf = sym(Lm P Lm^T) + sym(K Hm K^T) + eps I
+    mm<SET>(A.X, A.Lm, m, 1, A.P, m, 1, m, m, m, lane);
+    mm<SET>(A.Y, A.X, m, 1, A.Lm, 1, m, m, m, m, lane);
+    mm<SET>(A.KH, A.K, p, 1, A.Hm, p, 1, m, p, p, lane);
+    mm<SET>(A.X, A.KH, p, 1, A.K, 1, p, m, m, p, lane);
+    for (int idx = lane; idx < m * m; idx += 32) {
+        int i = idx / m, j = idx - i * m;
+        R v1 = R(0.5) * (A.Y[idx] + A.Y[j * m + i]);
+        R v2 = R(0.5) * (A.X[idx] + A.X[j * m + i]);
+        A.Pf[idx] = (v1 + v2) + (i == j ? g.jitter : R(0));
+    }
+    __syncwarp();
+    // ll = -0.5 (log 2pi + log det F + v' F^{-1} v)   (:609-615; log2pi counted once)
+    R quad = 0, logdet = 0;
+    for (int o = 0; o < p; ++o) {
+        quad = fma(A.v[o], A.wv[o], quad);
+        logdet += log(A.Lf[o * p + o]);
+    }
+    logdet = (p == 1) ? log(A.F[0]) : R(2) * logdet;
+    *flag_out = flag;
+    return flag ? R(0) : R(-0.5) * (R(kLog2Pi) + logdet + quad);
+}
+
+// ----------------------------------------------------------------------------------------------------
+// UnivariateFilter inner loop + symmetrise/stabilise (kalman_filter.py:769-815).
+// In: A.a, A.P.  Out: A.af, A.Pf (sym + jitter), A.Pu (P before symmetrisation), A.Kst/Fst/vst/zfst, A.w.
+// ----------------------------------------------------------------------------------------------------
+template <typename R>
+__device__ R uni_update(const KArgs<R>& g, Arena<R>& A, const R* yt, R* obs_mu, R* obs_cov, int lane) {
+    const int m = g.m, p = g.p;
+    for (int o = lane; o < p; o += 32) {
+        R yv = yt[o];
+        bool miss = isnan(yv);  // :792 -- the fill value is ignored here
+        A.w[o] = miss ? R(0) : R(1);
+        A.ym[o] = miss ? R(0) : yv;
+    }
+    wcopy(A.af, A.a, m, lane);
+    wcopy(A.Pu, A.P, m * m, lane);
+    R llsum = 0;
+    int nnz = 0;
+    for (int o = 0; o < p; ++o) {
+        const R wo = A.w[o];
+        const R* z = A.Z + o * m;
+        R yh = 0;
+        for (int j = 0; j < m; ++j) yh = fma(wo * z[j], A.af[j], yh);
+        yh += A.d[o];
+        const R v = A.ym[o] - yh;
+        // pz = P z^T  (kept in K row o), F0 = z pz + H_oo
+        for (int i = lane; i < m; i += 32) {
+            R acc = 0;
+            for (int j = 0; j < m; ++j) acc = fma(A.Pu[i * m + j], wo * z[j], acc);
+            A.Kst[o * m + i] = acc;
+        }
+        __syncwarp();
+        R F0 = 0;
+        for (int j = 0; j < m; ++j) F0 = fma(wo * z[j], A.Kst[o * m + j], F0);
+        F0 += wo * A.H[o * p + o];
+        const bool zf = (F0 == R(0)) || (wo == R(0));
+        const R F = F0 + g.jitter;
+        const R keep = zf ? R(0) : R(1);
+        __syncwarp();
+        for (int i = lane; i < m; i += 32) A.Kst[o * m + i] = A.Kst[o * m + i] / F * keep;
+        __syncwarp();
+        for (int i = lane; i < m; i += 32) A.af[i] = fma(A.Kst[o * m + i], v, A.af[i]);
+        for (int idx = lane; idx < m * m; idx += 32) {
+            int i = idx / m, j = idx - i * m;
+            A.Pu[idx] -= (A.Kst[o * m + i] * A.Kst[o * m + j]) * F;
+        }
+        const R lli = zf ? R(0) : log(F) + v * v / F;
+        llsum += lli;
+        nnz += (lli != R(0));
+        if (lane == 0) {
+            A.Fst[o] = F;
+            A.vst[o] = v;
+            A.zfst[o] = keep;
+            if (o == p - 1) {
+                if (obs_mu) obs_mu[0] = yh;
+                if (obs_cov) obs_cov[0] = F;
+            }
+        }
+        __syncwarp();
+    }
+    sym_into<R>(A.Pf, A.Pu, nullptr, g.jitter, m, lane);
+    return R(-0.5) * (R(nnz) * R(kLog2Pi) + llsum);
+}
+
+// ----------------------------------------------------------------------------------------------------
+// Householder QR (R factor only), LAPACK dgeqr2/dlarfg conventions, in place on A[rows, cols] row-major.
+// beta = -sign(alpha) * ||(alpha, x)||, H = I when x == 0 (tau = 0).   
+// ----------------------------------------------------------------------------------------------------
+template <typename R>
+__device__ void householder_r(R* A, int rows, int cols, int lane) {
+    const int kmax = rows < cols ? rows : cols;
+    for (int j = 0; j < kmax; ++j) {
+        R ss = 0;
+        for (int i = j + 1 + lane; i < rows; i += 32) ss = fma(A[i * cols + j], A[i * cols + j], ss);
+        ss = warp_sum(ss);
+        const R alpha = A[j * cols + j];
+        __syncwarp();
+        if (ss == R(0)) continue;  // tau = 0
+        const R nrm = sqrt(fma(alpha, alpha, ss));
+        const R beta = alpha >= R(0) ? -nrm : nrm;
+        const R tau = (beta - alpha) / beta;
+        const R scal = R(1) / (alpha - beta);
+        for (int i = j + 1 + lane; i < rows; i += 32) A[i * cols + j] *= scal;  // v (v_j = 1 implicit)
+        __syncwarp();
+        for (int cidx = j + 1 + lane; cidx < cols; cidx += 32) {
+            R s = A[j * cols + cidx];
+            for (int i = j + 1; i < rows; ++i) s = fma(A[i * cols + j], A[i * cols + cidx], s);
+            s *= tau;
+            A[j * cols + cidx] -= s;
+            for (int i = j + 1; i < rows; ++i) A[i * cols + cidx] = fma(-s, A[i * cols + j], A[i * cols + cidx]);
+        }
+        __syncwarp();
+        if (lane == 0) A[j * cols + j] = beta;
+        for (int i = j + 1 + lane; i < rows; i += 32) A[i * cols + j] = 0;
+        __syncwarp();
+    }
+}
+
+// ----------------------------------------------------------------------------------------------------
+// forward kernel: standard / univariate
+// ----------------------------------------------------------------------------------------------------
+template <typename R>
+__global__ void forward_kernel(KArgs<R> g, int wpc, size_t arena) {
+    extern __shared__ double smem_raw[];
+    R* smem = reinterpret_cast<R*>(smem_raw);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int b = blockIdx.x * wpc + warp;
+    if (b >= g.B) return;
+    const int m = g.m, p = g.p, n = g.n;
+    const int po = (g.kind == BKF_UNIVARIATE) ? 1 : p;
+    Arena<R> A;
+    carve(A, smem + (size_t)warp * arena, m, p, g.r, false);
+    load_params(g, A, b, lane);
+    wcopy(A.a, param_ptr(g.a0, g.shared_mask, BKF_PARAM_A0, b, (size_t)m), m, lane);
+    wcopy(A.P, param_ptr(g.P0, g.shared_mask, BKF_PARAM_P0, b, (size_t)m * m), m * m, lane);
+    const R* yb = g.y_shared ? g.y : g.y + (size_t)b * n * p;
+    const size_t tstride = (size_t)m + (size_t)m * m;
+    R logp = 0;
+    int st = 0;
+    for (int t = 0; t < n; ++t) {
+        const size_t bt = (size_t)b * n + t;
+        if (g.traj) {
+            wcopy(g.traj + bt * tstride, A.a, m, lane);
+            wcopy(g.traj + bt * tstride + m, A.P, m * m, lane);
+        }
+        if (g.pred_a) wcopy(g.pred_a + bt * m, A.a, m, lane);
+        if (g.pred_P) wcopy(g.pred_P + bt * m * m, A.P, m * m, lane);
+        R* om = g.obs_mu ? g.obs_mu + bt * po : nullptr;
+        R* oc = g.obs_cov ? g.obs_cov + bt * po * po : nullptr;
+        R ll;
+        if (g.kind == BKF_STANDARD) {
+            bool flag, ok;
+            ll = std_update(g, A, yb + (size_t)t * p, om, oc, &flag, &ok, lane);
+            if (!ok) st |= BKF_STATUS_NOT_PD;
+        } else {
+            ll = uni_update(g, A, yb + (size_t)t * p, om, oc, lane);
+        }
+        if (g.filt_a) wcopy(g.filt_a + bt * m, A.af, m, lane);
+        if (g.filt_P) wcopy(g.filt_P + bt * m * m, A.Pf, m * m, lane);
+        if (g.ll && lane == 0) g.ll[bt] = ll;
+        logp += ll;
+        predict(A, m, lane);
+    }
+    if (!isfinite(logp)) st |= BKF_STATUS_NONFINITE;
+    if (lane == 0) {
+        if (g.logp) g.logp[b] = logp;
+        if (g.status) g.status[b] = st;
+    }
+}
+
+// ----------------------------------------------------------------------------------------------------
+// forward kernel: square-root filter (kalman_filter.py:629-750).  Arena: see sqrt_arena_elems.
+// ----------------------------------------------------------------------------------------------------
+__host__ __device__ inline size_t sqrt_arena_elems(int m, int p, int r) {
+    size_t n1 = (size_t)(p + m) * (p + m), n2 = (size_t)(m + r) * m;
+    size_t tot = /*T,Pc*/ 2 * (size_t)m * m + /*Z,Zm*/ 2 * (size_t)p * m + /*RQc*/ (size_t)m * r +
+                 /*Hc*/ (size_t)p * p + /*QR work*/ (n1 > n2 ? n1 : n2) + /*a,af,c*/ 3 * (size_t)m +
+                 /*d,w,ym,v,s*/ 5 * (size_t)p + /*Qc*/ (size_t)r * r;
+    return (tot + 1) & ~(size_t)1;
+}
+
+template <typename R>
+__global__ void sqrt_forward_kernel(KArgs<R> g, int wpc, size_t arena) {
+    extern __shared__ double smem_raw[];
+    R* s = reinterpret_cast<R*>(smem_raw);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int b = blockIdx.x * wpc + warp;
+    if (b >= g.B) return;
+    const int m = g.m, p = g.p, r = g.r, n = g.n;
+    s += (size_t)warp * arena;
+    auto take = [&](size_t k) { R* q = s; s += k; return q; };
+    R *T = take((size_t)m * m), *Pc = take((size_t)m * m), *Z = take((size_t)p * m), *Zm = take((size_t)p * m),
+      *RQc = take((size_t)m * r), *Hc = take((size_t)p * p), *Qc = take((size_t)r * r), *a = take(m),
+      *af = take(m), *c = take(m), *d = take(p), *w = take(p), *ym = take(p), *v = take(p), *sv = take(p),
+      *W = s;
+    wcopy(T, param_ptr(g.T, g.shared_mask, BKF_PARAM_T, b, (size_t)m * m), m * m, lane);
+    wcopy(Z, param_ptr(g.Z, g.shared_mask, BKF_PARAM_Z, b, (size_t)p * m), p * m, lane);
+    wcopy(Hc, param_ptr(g.H, g.shared_mask, BKF_PARAM_H, b, (size_t)p * p), p * p, lane);
+    wcopy(Qc, param_ptr(g.Q, g.shared_mask, BKF_PARAM_Q, b, (size_t)r * r), r * r, lane);
+    wcopy(c, param_ptr(g.c, g.shared_mask, BKF_PARAM_C, b, (size_t)m), m, lane);
+    wcopy(d, param_ptr(g.d, g.shared_mask, BKF_PARAM_D, b, (size_t)p), p, lane);
+    wcopy(a, param_ptr(g.a0, g.shared_mask, BKF_PARAM_A0, b, (size_t)m), m, lane);
+    wcopy(Pc, param_ptr(g.P0, g.shared_mask, BKF_PARAM_P0, b, (size_t)m * m), m * m, lane);
+    int st = 0;
+    // H_chol = all(H == 0) ? H : cholesky(H)  (:666) -- time-invariant H, so hoisted out of the loop
+    bool Hzero = true;
+    for (int i = 0; i < p * p; ++i) Hzero = Hzero && (Hc[i] == R(0));
+    if (!Hzero) {
+        if (!chol_lower(Hc, p, lane)) st |= BKF_STATUS_NOT_PD;
+        for (int idx = lane; idx < p * p; idx += 32)
+            if ((idx % p) > (idx / p)) Hc[idx] = 0;
+    }
+    if (!chol_lower(Qc, r, lane)) st |= BKF_STATUS_NOT_PD;
+    for (int idx = lane; idx < r * r; idx += 32)
+        if ((idx % r) > (idx / r)) Qc[idx] = 0;
+    __syncwarp();
+    const R* Rg = param_ptr(g.Rm, g.shared_mask, BKF_PARAM_R, b, (size_t)m * r);
+    mm<SET>(RQc, Rg, r, 1, Qc, r, 1, m, r, r, lane);
+
+    const R* yb = g.y_shared ? g.y : g.y + (size_t)b * n * p;
+    const int N1 = p + m;
+    R logp = 0;
+    auto write_sq = [&](R* dst, const R* L, int k) {  // dst = L L^T  (:733-740)
+        for (int idx = lane; idx < k * k; idx += 32) {
+            int i = idx / k, j = idx - i * k;
+            R acc = 0;
+            for (int q = 0; q < k; ++q) acc = fma(L[i * k + q], L[j * k + q], acc);
+            dst[idx] = acc;
+        }
+    };
+    for (int t = 0; t < n; ++t) {
+        const size_t bt = (size_t)b * n + t;
+        if (g.pred_a) wcopy(g.pred_a + bt * m, a, m, lane);
+        if (g.pred_P) write_sq(g.pred_P + bt * m * m, Pc, m);
+        const R* yt = yb + (size_t)t * p;
+        for (int o = lane; o < p; o += 32) {
+            R yv = yt[o];
+            bool miss = is_missing(yv, g.fill, true);
+            w[o] = miss ? R(0) : R(1);
+            ym[o] = miss ? R(0) : yv;
+        }
+        __syncwarp();
+        R nobs = 0;
+        for (int o = 0; o < p; ++o) nobs += w[o];
+        const bool flag = (nobs == R(0));
+        const bool partial = !flag && (nobs != R(p));
+        for (int idx = lane; idx < p * m; idx += 32) Zm[idx] = w[idx / m] * Z[idx];
+        __syncwarp();
+        for (int o = lane; o < p; o += 32) {
+            R acc = 0;
+            for (int j = 0; j < m; ++j) acc = fma(Zm[o * m + j], a[j], acc);
+            R yh = acc + d[o];
+            v[o] = ym[o] - yh;
+            if (g.obs_mu) g.obs_mu[bt * p + o] = yh;
+        }
+        // W = A_T^T with A_T = [[Hc, Zm Pc], [0, Pc]]  ->  W = [[Hc^T, 0], [(Zm Pc)^T, Pc^T]]   (:675-679)
+        for (int idx = lane; idx < N1 * N1; idx += 32) {
+            int i = idx / N1, j = idx - i * N1;
+            R val;
+            if (i < p) {
+                // masked H: all observed -> chol(H); all missing -> H_masked == 0 -> 0; partially missing ->
+                // cholesky(W H) fails in the reference (not PD): propagate NaN
+                val = (j < p) ? ((flag || Hzero) ? R(0) : (partial ? R(NAN) : Hc[j * p + i])) : R(0);
+            } else if (j < p) {
+                R acc = 0;
+                for (int q = 0; q < m; ++q) acc = fma(Zm[j * m + q], Pc[q * m + (i - p)], acc);
+                val = acc;
+            } else {
+                val = Pc[(j - p) * m + (i - p)];
+            }
+            W[idx] = val;
+        }
+        __syncwarp();
+        householder_r(W, N1, N1, lane);
+        // B = W^T: F_chol = B[:p,:p], K_F_chol = B[p:,:p], P_chol_filtered = B[p:,p:]
+        if (g.obs_cov) {
+            for (int idx = lane; idx < p * p; idx += 32) {
+                int i = idx / p, j = idx - i * p;
+                R acc = 0;  // F_chol F_chol^T, F_chol[i,q] = W[q,i]
+                for (int q = 0; q < p; ++q) acc = fma(W[q * N1 + i], W[q * N1 + j], acc);
+                g.obs_cov[bt * p * p + idx] = acc;
+            }
+        }
+        R ll = 0;
+        if (!flag) {
+            // s = solve_tri(F_chol, v, lower); inner = solve_tri(F_chol, s, lower)   (:686-691, quirk Q3)
+            R quad = 0, logdet = 0;
+            if (lane == 0) {
+                for (int i = 0; i < p; ++i) {
+                    R tt = v[i];
+                    for (int q = 0; q < i; ++q) tt -= W[q * N1 + i] * sv[q];
+                    sv[i] = tt / W[i * N1 + i];
+                }
+                for (int i = 0; i < p; ++i) {  // second lower solve into ym (scratch)
+                    R tt = sv[i];
+                    for (int q = 0; q < i; ++q) tt -= W[q * N1 + i] * ym[q];
+                    ym[i] = tt / W[i * N1 + i];
+                }
+            }
+            __syncwarp();
+            for (int o = 0; o < p; ++o) {
+                quad = fma(v[o], ym[o], quad);
+                logdet += log(fabs(W[o * N1 + o]));
+            }
+            logdet *= R(2);
+            ll = R(-0.5) * (R(p) * (R(kLog2Pi) + logdet) + quad);  // (:696, quirk Q2)
+            for (int i = lane; i < m; i += 32) {
+                R acc = 0;
+                for (int o = 0; o < p; ++o) acc = fma(W[o * N1 + (p + i)], sv[o], acc);
+                af[i] = a[i] + acc;
+            }
+            __syncwarp();
+            for (int idx = lane; idx < m * m; idx += 32) {
+                int i = idx / m, j = idx - i * m;
+                Pc[idx] = W[(p + j) * N1 + (p + i)] + (i == j ? g.jitter : R(0));  // jitter on the factor (Q4)
+            }
+        } else {
+            wcopy(af, a, m, lane);
+            for (int i = lane; i < m; i += 32) Pc[i * m + i] += g.jitter;
+        }
+        __syncwarp();
+        if (g.filt_a) wcopy(g.filt_a + bt * m, af, m, lane);
+        if (g.filt_P) write_sq(g.filt_P + bt * m * m, Pc, m);
+        if (g.ll && lane == 0) g.ll[bt] = ll;
+        logp += ll;
+        // predict: M = [T Pc, R Qc]^T  ((m+r) x m) ; Pc+ = qr_r(M)[:m,:m]^T   (:639-648)
+        for (int idx = lane; idx < (m + r) * m; idx += 32) {
+            int i = idx / m, j = idx - i * m;
+            R val;
+            if (i < m) {
+                R acc = 0;
+                for (int q = 0; q < m; ++q) acc = fma(T[j * m + q], Pc[q * m + i], acc);
+                val = acc;
+            } else {
+                val = RQc[j * r + (i - m)];
+            }
+            W[idx] = val;
+        }
+        mv<SET>(a, T, m, 1, af, m, m, lane);
+        for (int i = lane; i < m; i += 32) a[i] += c[i];
+        __syncwarp();
+        householder_r(W, m + r, m, lane);
+        for (int idx = lane; idx < m * m; idx += 32) {
+            int i = idx / m, j = idx - i * m;
+            Pc[idx] = W[j * m + i];
+        }
+        __syncwarp();
+    }
+    if (!isfinite(logp)) st |= BKF_STATUS_NONFINITE;
+    if (lane == 0) {
+        if (g.logp) g.logp[b] = logp;
+        if (g.status) g.status[b] = st;
+    }
+}
+
+// ----------------------------------------------------------------------------------------------------
+// backward kernel (standard / univariate): reverse sweep over the stored predictions
+// ----------------------------------------------------------------------------------------------------
+template <typename R>
+__global__ void backward_kernel(KArgs<R> g, int wpc, size_t arena) {
+    extern __shared__ double smem_raw[];
+    R* smem = reinterpret_cast<R*>(smem_raw);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int b = blockIdx.x * wpc + warp;
+    if (b >= g.B) return;
+    const int m = g.m, p = g.p, r = g.r, n = g.n;
+    Arena<R> A;
+    carve(A, smem + (size_t)warp * arena, m, p, r, true);
+    load_params(g, A, b, lane);
+    wzero(A.abar, m, lane); wzero(A.Pbar, m * m, lane); wzero(A.gT, m * m, lane); wzero(A.Gsum, m * m, lane);
+    wzero(A.gZ, p * m, lane); wzero(A.gH, p * p, lane); wzero(A.gc, m, lane); wzero(A.gd, p, lane);
+    const R* yb = g.y_shared ? g.y : g.y + (size_t)b * n * p;
+    const size_t tstride = (size_t)m + (size_t)m * m;
+    for (int t = n - 1; t >= 0; --t) {
+        const size_t bt = (size_t)b * n + t;
+        const R gcot = g.ll_cot ? g.ll_cot[bt] : R(1);
+        wcopy(A.a, g.traj + bt * tstride, m, lane);
+        wcopy(A.P, g.traj + bt * tstride + m, m * m, lane);
+        bool flag = false, ok = true;
+        if (g.kind == BKF_STANDARD) std_update(g, A, yb + (size_t)t * p, (R*)nullptr, (R*)nullptr, &flag, &ok, lane);
+        else uni_update(g, A, yb + (size_t)t * p, (R*)nullptr, (R*)nullptr, lane);
+        // ---------------- predict adjoint ----------------
+        // G = S(Pbar+); Gsum += G; gT += G T (Pf + Pf^T) + abar+ af^T; Pfbar = T^T G T; afbar = T^T abar+; gc += abar+
+        sym_into<R>(A.G, A.Pbar, nullptr, R(0), m, lane);
+        for (int idx = lane; idx < m * m; idx += 32) {
+            A.Gsum[idx] += A.G[idx];
+            A.Y[idx] = A.Pf[idx] + A.Pf[(idx % m) * m + idx / m];
+        }
+        __syncwarp();
+        mm<SET>(A.X, A.T, m, 1, A.Y, m, 1, m, m, m, lane);
+        mm<ADD>(A.gT, A.G, m, 1, A.X, m, 1, m, m, m, lane);
+        for (int idx = lane; idx < m * m; idx += 32) A.gT[idx] = fma(A.abar[idx / m], A.af[idx % m], A.gT[idx]);
+        mm<SET>(A.X, A.G, m, 1, A.T, m, 1, m, m, m, lane);
+        mm<SET>(A.Y, A.T, 1, m, A.X, m, 1, m, m, m, lane);  // Y = Pfbar
+        mv<SET>(A.afbar, A.T, 1, m, A.abar, m, m, lane);
+        for (int i = lane; i < m; i += 32) A.gc[i] += A.abar[i];
+        __syncwarp();
+        if (g.kind == BKF_STANDARD) {
+            // ---------------- Joseph-form adjoint ----------------
+            sym_into<R>(A.G, A.Y, nullptr, R(0), m, lane);  // G2
+            for (int idx = lane; idx < m * m; idx += 32) A.Y[idx] = A.P[idx] + A.P[(idx % m) * m + idx / m];
+            __syncwarp();
+            mm<SET>(A.X, A.Lm, m, 1, A.Y, m, 1, m, m, m, lane);
+            mm<SET>(A.Lbar, A.G, m, 1, A.X, m, 1, m, m, m, lane);       // Lbar = G2 Lm (P + P^T)
+            mm<SET>(A.X, A.G, m, 1, A.Lm, m, 1, m, m, m, lane);
+            mm<SET>(A.Pbar, A.Lm, 1, m, A.X, m, 1, m, m, m, lane);       // Pbar = Lm^T G2 Lm
+            for (int idx = lane; idx < p * p; idx += 32) A.Fbar[idx] = A.Hm[idx] + A.Hm[(idx % p) * p + idx / p];
+            __syncwarp();
+            mm<SET>(A.tmp_mp, A.K, p, 1, A.Fbar, p, 1, m, p, p, lane);   // K (Hm + Hm^T)
+            mm<SET>(A.Kbar, A.G, m, 1, A.tmp_mp, p, 1, m, p, m, lane);   // Kbar = G2 K (Hm + Hm^T)
+            mm<SET>(A.tmp_mp, A.G, m, 1, A.K, p, 1, m, p, m, lane);      // G2 K
+            mm<SET>(A.Hmbar, A.K, 1, p, A.tmp_mp, p, 1, p, p, m, lane);  // Hmbar = K^T G2 K
+            // a_f = a + K v
+            wcopy(A.abar, A.afbar, m, lane);
+            for (int idx = lane; idx < m * p; idx += 32) A.Kbar[idx] = fma(A.afbar[idx / p], A.v[idx % p], A.Kbar[idx]);
+            mv<SET>(A.vbar, A.K, 1, p, A.afbar, p, m, lane);
+            // Lm = I - K Zm
+            mm<SUB>(A.Kbar, A.Lbar, m, 1, A.Zm, 1, m, m, p, m, lane);    // Kbar -= Lbar Zm^T
+            mm<SET>(A.Zmbar, A.K, 1, p, A.Lbar, m, 1, p, m, m, lane);    // K^T Lbar
+            for (int idx = lane; idx < p * m; idx += 32) A.Zmbar[idx] = -A.Zmbar[idx];
+            // Finv = F^{-1}
+            for (int idx = lane; idx < p * p; idx += 32) A.Finv[idx] = ((idx / p) == (idx % p)) ? R(1) : R(0);
+            __syncwarp();
+            for (int q = lane; q < p; q += 32) chol_solve_vec(A.Lf, p, A.Finv + q, p);
+            __syncwarp();
+            // ll adjoint
+            for (int idx = lane; idx < p * p; idx += 32) {
+                int o = idx / p, q = idx - o * p;
+                A.Fbar[idx] = flag ? R(0) : R(-0.5) * gcot * (A.Finv[q * p + o] - A.wv[o] * A.wv[q]);
+            }
+            if (!flag)
+                for (int o = lane; o < p; o += 32) A.vbar[o] -= gcot * A.wv[o];
+            __syncwarp();
+            // K = PZT F^{-1}
+            mm<SET>(A.PZTbar, A.Kbar, p, 1, A.Finv, 1, p, m, p, p, lane);  // Kbar F^{-T}
+            mm<SUB>(A.Fbar, A.K, 1, p, A.PZTbar, p, 1, p, p, m, lane);     // Fbar -= K^T PZTbar
+            // F = Zm PZT + Hm + eps I
+            mm<ADD>(A.Zmbar, A.Fbar, p, 1, A.PZT, 1, p, p, m, p, lane);    // Zmbar += Fbar PZT^T
+            mm<ADD>(A.PZTbar, A.Zm, 1, m, A.Fbar, p, 1, m, p, p, lane);    // PZTbar += Zm^T Fbar
+            for (int idx = lane; idx < p * p; idx += 32) A.Hmbar[idx] += A.Fbar[idx];
+            // PZT = P Zm^T
+            mm<ADD>(A.Pbar, A.PZTbar, p, 1, A.Zm, m, 1, m, m, p, lane);    // Pbar += PZTbar Zm
+            mm<ADD>(A.Zmbar, A.PZTbar, 1, p, A.P, m, 1, p, m, m, lane);    // Zmbar += PZTbar^T P
+            // v = ym - d - Zm a
+            for (int o = lane; o < p; o += 32) A.gd[o] -= A.vbar[o];
+            for (int idx = lane; idx < p * m; idx += 32) A.Zmbar[idx] = fma(-A.vbar[idx / m], A.a[idx % m], A.Zmbar[idx]);
+            mv<SUB>(A.abar, A.Zm, 1, m, A.vbar, m, p, lane);               // abar -= Zm^T vbar
+            // mask
+            for (int idx = lane; idx < p * m; idx += 32) A.gZ[idx] = fma(A.w[idx / m], A.Zmbar[idx], A.gZ[idx]);
+            for (int idx = lane; idx < p * p; idx += 32) A.gH[idx] = fma(A.w[idx / p], A.Hmbar[idx], A.gH[idx]);
+            __syncwarp();
+        } else {
+            // ---------------- univariate adjoint ----------------
+            // Pf = 0.5 (Pu + Pu^T) + eps I
+            sym_into<R>(A.Pbar, A.Y, nullptr, R(0), m, lane);
+            wcopy(A.abar, A.afbar, m, lane);
+            const R llbar = R(-0.5) * gcot;
+            for (int o = p - 1; o >= 0; --o) {
+                const R keep = A.zfst[o];
+                if (keep == R(0)) continue;  // K = 0: a, P pass through; no parameter gradient
+                const R F = A.Fst[o], v = A.vst[o], wo = A.w[o];
+                const R* K = A.Kst + o * m;
+                const R* z = A.Z + o * m;  // wo == 1 here
+                // state before this inner update
+                for (int idx = lane; idx < m * m; idx += 32) A.Pu[idx] += (K[idx / m] * K[idx % m]) * F;
+                for (int i = lane; i < m; i += 32) A.af[i] = fma(-K[i], v, A.af[i]);
+                __syncwarp();
+                // Kbar_i = -sum_j (Pbar_ij + Pbar_ji) K_j F + abar_i v   (tmp in X[0:m])
+                R kpk = 0, ka = 0, kk = 0;
+                for (int i = lane; i < m; i += 32) {
+                    R acc = 0;
+                    for (int j = 0; j < m; ++j) acc = fma(A.Pbar[i * m + j] + A.Pbar[j * m + i], K[j], acc);
+                    R pk = 0;
+                    for (int j = 0; j < m; ++j) pk = fma(A.Pbar[i * m + j], K[j], pk);
+                    R kb = fma(-acc, F, A.abar[i] * v);
+                    A.Kbar[i] = kb;
+                    kpk = fma(K[i], pk, kpk);
+                    ka = fma(K[i], A.abar[i], ka);
+                    kk = fma(kb, K[i], kk);
+                }
+                kpk = warp_sum(kpk); ka = warp_sum(ka); kk = warp_sum(kk);
+                R Fbar = -kpk + llbar * (R(1) / F - v * v / (F * F));
+                const R vbar = ka + llbar * R(2) * v / F;
+                Fbar -= kk / F;
+                __syncwarp();
+                // pzbar = Kbar / F + Fbar z ; zbar = Fbar pz + P^T pzbar - vbar a ; (pz = K F)
+                for (int i = lane; i < m; i += 32) A.PZTbar[i] = A.Kbar[i] / F + Fbar * z[i];
+                __syncwarp();
+                const R* pzbar = A.PZTbar;
+                for (int j = lane; j < m; j += 32) {
+                    R acc = 0;
+                    for (int i = 0; i < m; ++i) acc = fma(A.Pu[i * m + j], pzbar[i], acc);
+                    R zb = fma(Fbar, K[j] * F, acc);
+                    zb = fma(-vbar, A.af[j], zb);
+                    A.gZ[o * m + j] = fma(wo, zb, A.gZ[o * m + j]);
+                    A.abar[j] = fma(-vbar, z[j], A.abar[j]);
+                }
+                for (int idx = lane; idx < m * m; idx += 32) A.Pbar[idx] = fma(pzbar[idx / m], z[idx % m], A.Pbar[idx]);
+                if (lane == 0) {
+                    A.gH[o * p + o] = fma(wo, Fbar, A.gH[o * p + o]);
+                    A.gd[o] -= vbar;
+                }
+                __syncwarp();
+            }
+        }
+    }
+    // ---------------- write gradients ----------------
+    auto put = [&](R* dst, const R* src, size_t sz) {
+        if (dst) wcopy(dst + (size_t)b * sz, src, (int)sz, lane);
+    };
+    put(g.g_a0, A.abar, m); put(g.g_P0, A.Pbar, (size_t)m * m); put(g.g_c, A.gc, m); put(g.g_d, A.gd, p);
+    put(g.g_T, A.gT, (size_t)m * m); put(g.g_Z, A.gZ, (size_t)p * m); put(g.g_H, A.gH, (size_t)p * p);
+    // Rbar = Gsum R (Q + Q^T) ; Qbar = R^T Gsum R      (sym(R Q R^T) is time-invariant: sum the cotangents first)
+    const R* Rg = param_ptr(g.Rm, g.shared_mask, BKF_PARAM_R, b, (size_t)m * r);
+    const R* Qg = param_ptr(g.Q, g.shared_mask, BKF_PARAM_Q, b, (size_t)r * r);
+    if (g.g_R) {
+        for (int idx = lane; idx < m * r; idx += 32) {
+            int i = idx / r, j = idx - i * r;
+            R acc = 0;
+            for (int k = 0; k < r; ++k) {
+                R gr = 0;  // (Gsum R)[i,k]
+                for (int l = 0; l < m; ++l) gr = fma(A.Gsum[i * m + l], Rg[l * r + k], gr);
+                acc = fma(gr, Qg[k * r + j] + Qg[j * r + k], acc);
+            }
+            g.g_R[(size_t)b * m * r + idx] = acc;
+        }
+    }
+    if (g.g_Q) {
+        for (int idx = lane; idx < r * r; idx += 32) {
+            int i = idx / r, j = idx - i * r;
+            R acc = 0;
+            for (int k = 0; k < m; ++k) {
+                R gr = 0;  // (Gsum R)[k,j]
+                for (int l = 0; l < m; ++l) gr = fma(A.Gsum[k * m + l], Rg[l * r + j], gr);
+                acc = fma(Rg[k * r + i], gr, acc);
+            }
+            g.g_Q[(size_t)b * r * r + idx] = acc;
+        }
+    }
+}
+
+// ----------------------------------------------------------------------------------------------------
+// smoother kernel (kalman_smoother.py:66-126)
+// ----------------------------------------------------------------------------------------------------
+__host__ __device__ inline size_t smooth_arena_elems(int m, int r) {
+    size_t tot = /*T,RQR,P,Ps,Phat,X,Y,V,G*/ 9 * (size_t)m * m + /*a,as,ahat,lam*/ 4 * (size_t)m;
+    return (tot + 1) & ~(size_t)1;
+}
+
+// Symmetric eigen-decomposition by cyclic Jacobi: A (destroyed; diag -> eigenvalues), V (eigenvectors in columns).
+template <typename R>
+__device__ void jacobi_eig(R* A, R* V, int m, int lane) {
+    for (int idx = lane; idx < m * m; idx += 32) V[idx] = ((idx / m) == (idx % m)) ? R(1) : R(0);
+    __syncwarp();
+    const R tol2 = sizeof(R) == 8 ? R(1e-34) : R(1e-15);
+    for (int sweep = 0; sweep < 30; ++sweep) {
+        R off = 0, dg = 0;
+        for (int idx = lane; idx < m * m; idx += 32) {
+            R x = A[idx];
+            if ((idx / m) == (idx % m)) dg = fma(x, x, dg); else off = fma(x, x, off);
+        }
+        off = warp_sum(off); dg = warp_sum(dg);
+        if (off <= tol2 * dg) break;
+        for (int pi = 0; pi < m - 1; ++pi) {
+            for (int qi = pi + 1; qi < m; ++qi) {
+                const R apq = A[pi * m + qi];
+                const R app = A[pi * m + pi], aqq = A[qi * m + qi];
+                __syncwarp();
+                if (apq == R(0)) continue;
+                const R theta = (aqq - app) / (R(2) * apq);
+                const R tt = (theta >= R(0) ? R(1) : R(-1)) / (fabs(theta) + sqrt(fma(theta, theta, R(1))));
+                const R cs = R(1) / sqrt(fma(tt, tt, R(1))), sn = tt * cs;
+                for (int k = lane; k < m; k += 32) {
+                    if (k != pi && k != qi) {
+                        R akp = A[k * m + pi], akq = A[k * m + qi];
+                        R np_ = cs * akp - sn * akq, nq = sn * akp + cs * akq;
+                        A[k * m + pi] = np_; A[pi * m + k] = np_;
+                        A[k * m + qi] = nq; A[qi * m + k] = nq;
+                    }
+                    R vkp = V[k * m + pi], vkq = V[k * m + qi];
+                    V[k * m + pi] = cs * vkp - sn * vkq;
+                    V[k * m + qi] = sn * vkp + cs * vkq;
+                }
+                if (lane == 0) {
+                    A[pi * m + pi] = app - tt * apq;
+                    A[qi * m + qi] = aqq + tt * apq;
+                    A[pi * m + qi] = 0; A[qi * m + pi] = 0;
+                }
+                __syncwarp();
+            }
+        }
+    }
+}
+
+template <typename R>
+__global__ void smoother_kernel(KArgs<R> g, int wpc, size_t arena, R jitter0) {
+    extern __shared__ double smem_raw[];
+    R* s = reinterpret_cast<R*>(smem_raw);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int b = blockIdx.x * wpc + warp;
+    if (b >= g.B) return;
+    const int m = g.m, r = g.r, n = g.n;
+    s += (size_t)warp * arena;
+    const size_t mm_ = (size_t)m * m;
+    auto take = [&](size_t k) { R* q = s; s += k; return q; };
+    R *T = take(mm_), *RQR = take(mm_), *P = take(mm_), *Ps = take(mm_), *Ph = take(mm_), *X = take(mm_),
+      *Y = take(mm_), *V = take(mm_), *G = take(mm_), *a = take(m), *as = take(m), *ah = take(m), *lam = take(m);
+    wcopy(T, param_ptr(g.T, g.shared_mask, BKF_PARAM_T, b, mm_), m * m, lane);
+    const R* Rg = param_ptr(g.Rm, g.shared_mask, BKF_PARAM_R, b, (size_t)m * r);
+    const R* Qg = param_ptr(g.Q, g.shared_mask, BKF_PARAM_Q, b, (size_t)r * r);
+    rqr_sym(RQR, Y, Rg, Qg, m, r, lane);
+    const R* fa = g.sm_filt_a + (size_t)b * n * m;
+    const R* fP = g.sm_filt_P + (size_t)b * n * mm_;
+    R* oa = g.sm_a ? g.sm_a + (size_t)b * n * m : nullptr;
+    R* oP = g.sm_P ? g.sm_P + (size_t)b * n * mm_ : nullptr;
+    wcopy(as, fa + (size_t)(n - 1) * m, m, lane);
+    wcopy(Ps, fP + (size_t)(n - 1) * mm_, m * m, lane);
+    if (oa) wcopy(oa + (size_t)(n - 1) * m, as, m, lane);
+    if (oP) wcopy(oP + (size_t)(n - 1) * mm_, Ps, m * m, lane);
+    int st = 0;
+    for (int t = n - 2; t >= 0; --t) {
+        wcopy(a, fa + (size_t)t * m, m, lane);
+        wcopy(P, fP + (size_t)t * mm_, m * m, lane);
+        mv<SET>(ah, T, m, 1, a, m, m, lane);  // no state intercept (:122, quirk Q8)
+        mm<SET>(X, T, m, 1, P, m, 1, m, m, m, lane);
+        mm<SET>(Y, X, m, 1, T, 1, m, m, m, m, lane);
+        sym_into<R>(Ph, Y, RQR, g.jitter, m, lane);
+        // pinv(P_hat) (:112): symmetric eigen-decomposition, singular values below 1e-15 * max dropped
+        wcopy(Y, Ph, m * m, lane);
+        jacobi_eig(Y, V, m, lane);
+        R lmax = 0;
+        for (int i = 0; i < m; ++i) lmax = fmax(lmax, fabs(Y[i * m + i]));
+        const R cutoff = R(1e-15) * lmax;
+        for (int i = lane; i < m; i += 32) {
+            R l = Y[i * m + i];
+            lam[i] = fabs(l) > cutoff ? R(1) / l : R(0);
+        }
+        __syncwarp();
+        for (int idx = lane; idx < m * m; idx += 32) {  // Y = V diag(lam) V^T
+            int i = idx / m, j = idx - i * m;
+            R acc = 0;
+            for (int k = 0; k < m; ++k) acc = fma(V[i * m + k] * lam[k], V[j * m + k], acc);
+            X[idx] = acc;
+        }
+        __syncwarp();
+        // G = (pinv T P)^T
+        mm<SET>(Y, X, m, 1, T, m, 1, m, m, m, lane);
+        mm<SET>(X, Y, m, 1, P, m, 1, m, m, m, lane);
+        for (int idx = lane; idx < m * m; idx += 32) G[idx] = X[(idx % m) * m + idx / m];
+        for (int i = lane; i < m; i += 32) ah[i] = as[i] - ah[i];
+        __syncwarp();
+        for (int i = lane; i < m; i += 32) {
+            R acc = 0;
+            for (int k = 0; k < m; ++k) acc = fma(G[i * m + k], ah[k], acc);
+            as[i] = a[i] + acc;
+        }
+        for (int idx = lane; idx < m * m; idx += 32) Y[idx] = Ps[idx] - Ph[idx];
+        __syncwarp();
+        mm<SET>(X, G, m, 1, Y, m, 1, m, m, m, lane);
+        mm<SET>(Y, X, m, 1, G, 1, m, m, m, m, lane);
+        for (int idx = lane; idx < m * m; idx += 32) {
+            int i = idx / m, j = idx - i * m;
+            R val = P[idx] + R(0.5) * (Y[idx] + Y[j * m + i]);
+            if (i == j) val = (val + g.jitter) + jitter0;  // double jitter (:116-117, quirk Q8)
+            Ps[idx] = val;
+        }
+        __syncwarp();
+        if (oa) wcopy(oa + (size_t)t * m, as, m, lane);
+        if (oP) wcopy(oP + (size_t)t * mm_, Ps, m * m, lane);
+    }
+    if (lane == 0 && g.status) g.status[b] |= st;
+}
+
+// ----------------------------------------------------------------------------------------------------
+// host launchers
+// ----------------------------------------------------------------------------------------------------
+static int pick_wpc(size_t arena_bytes, int B) {
+    const size_t budget = 200 * 1024;
+    int wpc = 4;
+    while (wpc > 1 && arena_bytes * wpc > budget) wpc >>= 1;
+    (void)B;
+    return wpc;
+}
+
+template <typename R, typename KernelT>
+static int launch_warp_kernel(KernelT kern, const KArgs<R>& g, size_t arena, cudaStream_t stream, const char** err) {
+    size_t arena_bytes = arena * sizeof(R);
+    if (arena_bytes > 227 * 1024) {
+        *err = "problem too large for the generic shared-memory kernel (m, p, r)";
+        return BKF_ERR_UNSUPPORTED;
+    }
+    int wpc = pick_wpc(arena_bytes, g.B);
+    size_t smem = arena_bytes * wpc;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) { *err = cudaGetErrorString(e); return BKF_ERR_CUDA; }
+    int grid = (g.B + wpc - 1) / wpc;
+    kern<<<grid, 32 * wpc, smem, stream>>>(g, wpc, arena);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) { *err = cudaGetErrorString(e); return BKF_ERR_CUDA; }
+    return BKF_OK;
+}
+
+template <typename R>
+int launch_forward(const KArgs<R>& g, cudaStream_t stream, const char** err) {
+    if (g.kind == BKF_CHOLESKY)
+        return launch_warp_kernel<R>(sqrt_forward_kernel<R>, g, sqrt_arena_elems(g.m, g.p, g.r), stream, err);
+    return launch_warp_kernel<R>(forward_kernel<R>, g, arena_elems(g.m, g.p, g.r, false), stream, err);
+}
+
+template <typename R>
+int launch_backward(const KArgs<R>& g, cudaStream_t stream, const char** err) {
+    if (g.kind == BKF_CHOLESKY) {
+        *err = "gradient of the square-root filter is not implemented yet";
+        return BKF_ERR_UNSUPPORTED;
+    }
+    return launch_warp_kernel<R>(backward_kernel<R>, g, arena_elems(g.m, g.p, g.r, true), stream, err);
+}
+
+template <typename R>
+int launch_smoother(const KArgs<R>& g, cudaStream_t stream, const char** err) {
+    size_t arena = smooth_arena_elems(g.m, g.r);
+    size_t arena_bytes = arena * sizeof(R);
+    if (arena_bytes > 227 * 1024) { *err = "problem too large for the generic smoother kernel"; return BKF_ERR_UNSUPPORTED; }
+    int wpc = pick_wpc(arena_bytes, g.B);
+    size_t smem = arena_bytes * wpc;
+    auto kern = smoother_kernel<R>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) { *err = cudaGetErrorString(e); return BKF_ERR_CUDA; }
+    int grid = (g.B + wpc - 1) / wpc;
+    R jitter0 = sizeof(R) == 8 ? R(1e-8) : R(1e-6);  // JITTER_DEFAULT, utils/constants.py:20
+    kern<<<grid, 32 * wpc, smem, stream>>>(g, wpc, arena, jitter0);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) { *err = cudaGetErrorString(e); return BKF_ERR_CUDA; }
+    return BKF_OK;
+}
+
+template int launch_forward<double>(const KArgs<double>&, cudaStream_t, const char**);
+template int launch_forward<float>(const KArgs<float>&, cudaStream_t, const char**);
+template int launch_backward<double>(const KArgs<double>&, cudaStream_t, const char**);
+template int launch_backward<float>(const KArgs<float>&, cudaStream_t, const char**);
+template int launch_smoother<double>(const KArgs<double>&, cudaStream_t, const char**);
+template int launch_smoother<float>(const KArgs<float>&, cudaStream_t, const char**);
+
+}  // namespace gen
+}  // namespace bkf

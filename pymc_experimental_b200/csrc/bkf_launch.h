@@ -1,0 +1,13 @@
+// bkf_launch.h -- host-side launcher declarations of the kernel families.
+#pragma once
+#include <cuda_runtime.h>
+
+#include "bkf_common.cuh"
+
+namespace bkf {
+namespace gen {  // generic warp-per-series kernels (bkf_generic.cu)
+template <typename R> int launch_forward(const KArgs<R>& g, cudaStream_t stream, const char** err);
+template <typename R> int launch_backward(const KArgs<R>& g, cudaStream_t stream, const char** err);
+template <typename R> int launch_smoother(const KArgs<R>& g, cudaStream_t stream, const char** err);
+}  // namespace gen
+}  // namespace bkf

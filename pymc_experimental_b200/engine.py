@@ -1,0 +1,424 @@
+"""ctypes binding of libbkf.so (include/bkf.h) -- the only way into the CUDA kernels from Python.
+
+There is no CPU fallback: if the shared library is missing or no CUDA device is present, constructing a
+:class:`KalmanEngine` raises.  Arrays may be NumPy arrays (host pointers; the library stages them through its
+device workspace) or ``torch`` CUDA tensors (device pointers, used in place; outputs are returned as torch
+tensors on the same device).
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libbkf.so")
+
+STANDARD, UNIVARIATE, CHOLESKY = 0, 1, 2
+KINDS = {"standard": STANDARD, "univariate": UNIVARIATE, "cholesky": CHOLESKY}
+F64, F32 = 0, 1
+MEM_HOST, MEM_DEVICE = 0, 1
+PARAM_NAMES = ("a0", "P0", "c", "d", "T", "Z", "R", "H", "Q")  # utils/constants.py:24 (x0 == a0)
+STATUS_NOT_PD, STATUS_NONFINITE = 1, 2
+
+# pymc_extras/statespace/utils/constants.py:19-20
+MISSING_FILL = -9999.0
+JITTER_F64, JITTER_F32 = 1e-8, 1e-6
+
+# every symbol include/bkf.h declares (tests check that the library exports all of them)
+ABI_SYMBOLS = (
+    "bkf_version", "bkf_create", "bkf_destroy", "bkf_last_error", "bkf_set_stream", "bkf_launch_count",
+    "bkf_last_path", "bkf_enable_timing", "bkf_reset_timing", "bkf_kernel_time_ms", "bkf_measure_fma_peak",
+    "bkf_filter_forward", "bkf_filter_logp_grad", "bkf_smooth", "bkf_filter_smooth",
+)
+
+
+class BkfProblem(C.Structure):
+    _fields_ = [
+        ("kind", C.c_int), ("dtype", C.c_int), ("mem", C.c_int), ("B", C.c_int), ("n", C.c_int),
+        ("m", C.c_int), ("p", C.c_int), ("r", C.c_int), ("y_shared", C.c_int),
+        ("shared_mask", C.c_uint), ("tv_mask", C.c_uint),
+        ("cov_jitter", C.c_double), ("missing_fill", C.c_double),
+    ]
+
+
+class BkfError(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def load_library():
+    """dlopen libbkf.so and declare the prototypes.  Raises if the library has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise BkfError(
+            f"{LIB_PATH} not found: build it with `python -m pymc_experimental_b200.build` "
+            "(there is no CPU fallback)"
+        )
+    lib = C.CDLL(LIB_PATH)
+    vp, ip = C.c_void_p, C.POINTER(C.c_int)
+    lib.bkf_version.restype = C.c_int
+    lib.bkf_create.argtypes = [C.c_int, C.POINTER(vp)]
+    lib.bkf_destroy.argtypes = [vp]
+    lib.bkf_last_error.argtypes = [vp]
+    lib.bkf_last_error.restype = C.c_char_p
+    lib.bkf_last_path.argtypes = [vp]
+    lib.bkf_last_path.restype = C.c_char_p
+    lib.bkf_set_stream.argtypes = [vp, vp]
+    lib.bkf_launch_count.argtypes = [vp]
+    lib.bkf_launch_count.restype = C.c_longlong
+    lib.bkf_enable_timing.argtypes = [vp, C.c_int]
+    lib.bkf_reset_timing.argtypes = [vp]
+    lib.bkf_kernel_time_ms.argtypes = [vp, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_longlong)]
+    lib.bkf_measure_fma_peak.argtypes = [vp, C.c_int, C.POINTER(C.c_double)]
+    pp = C.POINTER(BkfProblem)
+    lib.bkf_filter_forward.argtypes = [vp, pp] + [vp] * 10 + [vp] * 7 + [vp]
+    lib.bkf_filter_logp_grad.argtypes = [vp, pp] + [vp] * 10 + [vp] + [vp] + [vp] * 9 + [vp]
+    lib.bkf_smooth.argtypes = [vp, pp] + [vp] * 5 + [vp] * 2 + [vp]
+    lib.bkf_filter_smooth.argtypes = [vp, pp] + [vp] * 10 + [vp] * 3 + [vp]
+    _lib = lib
+    return lib
+
+
+def _is_torch(x):
+    return type(x).__module__.startswith("torch")
+
+
+class _Buffers:
+    """Normalises one call's arrays to a single memory space / dtype and hands out raw pointers."""
+
+    def __init__(self, arrays, dtype=None):
+        self.device = any(_is_torch(a) and a.is_cuda for a in arrays if a is not None)
+        if self.device:
+            import torch
+
+            self.torch = torch
+            first = next(a for a in arrays if a is not None and _is_torch(a) and a.is_cuda)
+            self.dev = first.device
+            self.tdtype = first.dtype if dtype is None else dtype
+            if self.tdtype not in (torch.float64, torch.float32):
+                raise BkfError("dtype must be float64 or float32")
+            self.code = F64 if self.tdtype == torch.float64 else F32
+        else:
+            nd = np.dtype(np.float64 if dtype is None else dtype)
+            if nd not in (np.dtype(np.float64), np.dtype(np.float32)):
+                raise BkfError("dtype must be float64 or float32")
+            self.ndtype = nd
+            self.code = F64 if nd == np.float64 else F32
+        self.keep = []
+
+    def inp(self, x):
+        if self.device:
+            t = self.torch.as_tensor(x, dtype=self.tdtype, device=self.dev).contiguous()
+            self.keep.append(t)
+            return t
+        a = np.ascontiguousarray(x, dtype=self.ndtype)
+        self.keep.append(a)
+        return a
+
+    def out(self, shape):
+        if self.device:
+            t = self.torch.empty(shape, dtype=self.tdtype, device=self.dev)
+        else:
+            t = np.empty(shape, dtype=self.ndtype)
+        self.keep.append(t)
+        return t
+
+    def out_int(self, shape):
+        if self.device:
+            t = self.torch.zeros(shape, dtype=self.torch.int32, device=self.dev)
+        else:
+            t = np.zeros(shape, dtype=np.int32)
+        self.keep.append(t)
+        return t
+
+    @staticmethod
+    def ptr(x):
+        if x is None:
+            return None
+        if _is_torch(x):
+            return C.c_void_p(x.data_ptr())
+        return C.c_void_p(x.ctypes.data)
+
+
+_STATIC_NDIM = {"a0": 1, "P0": 2, "c": 1, "d": 1, "T": 2, "Z": 2, "R": 2, "H": 2, "Q": 2}
+
+
+class KalmanEngine:
+    """One handle = one device + one workspace + one stream (not thread-safe; create one per process)."""
+
+    def __init__(self, device: int = 0):
+        self.lib = load_library()
+        h = C.c_void_p()
+        rc = self.lib.bkf_create(int(device), C.byref(h))
+        if rc != 0:
+            raise BkfError(f"bkf_create(device={device}) failed with code {rc}: no usable CUDA device "
+                           "(this engine has no CPU fallback)")
+        self.h = h
+        self.device = int(device)
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.bkf_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ------------------------------------------------------------------------------------------------
+    def set_stream(self, cuda_stream_ptr: int | None):
+        self.lib.bkf_set_stream(self.h, C.c_void_p(cuda_stream_ptr or 0))
+
+    def use_torch_stream(self):
+        import torch
+
+        self.set_stream(torch.cuda.current_stream(self.device).cuda_stream)
+
+    @property
+    def launch_count(self) -> int:
+        return int(self.lib.bkf_launch_count(self.h))
+
+    @property
+    def last_path(self) -> str:
+        return self.lib.bkf_last_path(self.h).decode()
+
+    def enable_timing(self, on=True):
+        self.lib.bkf_enable_timing(self.h, int(on))
+        self.lib.bkf_reset_timing(self.h)
+
+    def kernel_times(self):
+        """{kernel class: (total device ms, launches)} accumulated since enable_timing()."""
+        out = {}
+        for i, name in enumerate(("forward", "backward", "smoother")):
+            ms, nl = C.c_double(0), C.c_longlong(0)
+            self.lib.bkf_kernel_time_ms(self.h, i, C.byref(ms), C.byref(nl))
+            out[name] = (ms.value, nl.value)
+        return out
+
+    def measure_fma_peak(self, dtype=F64) -> float:
+        """Measured DFMA (F64) / FFMA (F32) pipe peak of this device in TFLOP/s."""
+        v = C.c_double(0)
+        self._check(self.lib.bkf_measure_fma_peak(self.h, int(dtype), C.byref(v)))
+        return v.value
+
+    def _check(self, rc):
+        if rc != 0:
+            raise BkfError(f"libbkf error {rc}: {self.lib.bkf_last_error(self.h).decode()}")
+
+    # ------------------------------------------------------------------------------------------------
+    def _problem(self, kind, bufs, y, params, B, cov_jitter, missing_fill_value):
+        """Shape bookkeeping: returns (BkfProblem, y, [nine parameter arrays])."""
+        k = KINDS[kind] if isinstance(kind, str) else int(kind)
+        R = params["R"]
+        Z = params["Z"]
+        m, r = int(R.shape[-2]), int(R.shape[-1])
+        p = int(Z.shape[-2])
+        n = int(y.shape[-2])
+        shared_mask = 0
+        arrs = []
+        for i, name in enumerate(PARAM_NAMES):
+            x = params[name]
+            nd = _STATIC_NDIM[name]
+            if x.ndim == nd:
+                shared_mask |= 1 << i
+            elif x.ndim == nd + 1:
+                if x.shape[0] != B:
+                    raise BkfError(f"{name}: leading batch dimension {x.shape[0]} != {B}")
+            else:
+                raise BkfError(f"{name}: expected {nd} (shared) or {nd + 1} (batched) dims, got {x.ndim}; "
+                               "time-varying matrices are not supported yet")
+            arrs.append(bufs.inp(x))
+        y_shared = int(y.ndim == 2)
+        if y.ndim == 3 and y.shape[0] != B:
+            raise BkfError(f"y: leading batch dimension {y.shape[0]} != {B}")
+        if y.shape[-1] != p:
+            raise BkfError(f"y has {y.shape[-1]} observed series but Z has {p} rows")
+        default_jitter = JITTER_F64 if bufs.code == F64 else JITTER_F32
+        prob = BkfProblem(
+            kind=k, dtype=bufs.code, mem=MEM_DEVICE if bufs.device else MEM_HOST, B=B, n=n, m=m, p=p, r=r,
+            y_shared=y_shared, shared_mask=shared_mask, tv_mask=0,
+            cov_jitter=default_jitter if cov_jitter is None else float(cov_jitter),
+            missing_fill=MISSING_FILL if missing_fill_value is None else float(missing_fill_value),
+        )
+        return prob, bufs.inp(y), arrs
+
+    @staticmethod
+    def _batch_size(y, params):
+        B = None
+        if y.ndim == 3:
+            B = y.shape[0]
+        for name in PARAM_NAMES:
+            x = params[name]
+            if x.ndim == _STATIC_NDIM[name] + 1:
+                if B is not None and x.shape[0] != B:
+                    raise BkfError(f"inconsistent batch sizes ({B} vs {x.shape[0]} for {name})")
+                B = x.shape[0]
+        return B
+
+    # ------------------------------------------------------------------------------------------------
+    def filter(self, kind, y, a0, P0, c, d, T, Z, R, H, Q, cov_jitter=None, missing_fill_value=None,
+               outputs=("filtered_states", "predicted_states", "observed_states", "filtered_covariances",
+                        "predicted_covariances", "observed_covariances", "loglike_obs"), dtype=None):
+        """Batched ``BaseFilter.build_graph`` (kalman_filter.py:144-308).  Returns a dict of the requested
+        outputs plus ``status``; unbatched inputs (no leading B anywhere) return unbatched outputs."""
+        params = dict(zip(PARAM_NAMES, (a0, P0, c, d, T, Z, R, H, Q)))
+        bufs = _Buffers([y, *params.values()], dtype)
+        params = {k_: (v if _is_torch(v) else np.asarray(v)) for k_, v in params.items()}
+        y = y if _is_torch(y) else np.asarray(y)
+        B = self._batch_size(y, params)
+        squeeze = B is None
+        B = 1 if squeeze else int(B)
+        prob, yb, arrs = self._problem(kind, bufs, y, params, B, cov_jitter, missing_fill_value)
+        n, m, p = prob.n, prob.m, prob.p
+        po = 1 if prob.kind == UNIVARIATE else p
+        shapes = {
+            "filtered_states": (B, n, m), "predicted_states": (B, n, m), "observed_states": (B, n, po),
+            "filtered_covariances": (B, n, m, m), "predicted_covariances": (B, n, m, m),
+            "observed_covariances": (B, n, po, po), "loglike_obs": (B, n),
+        }
+        outs = {k_: (bufs.out(shapes[k_]) if k_ in outputs else None) for k_ in shapes}
+        status = bufs.out_int((B,))
+        if bufs.device:
+            self.use_torch_stream()
+        rc = self.lib.bkf_filter_forward(
+            self.h, C.byref(prob), bufs.ptr(yb), *[bufs.ptr(a) for a in arrs],
+            *[bufs.ptr(outs[k_]) for k_ in shapes], bufs.ptr(status))
+        self._check(rc)
+        res = {k_: v for k_, v in outs.items() if v is not None}
+        res["status"] = status
+        if squeeze:
+            res = {k_: v[0] for k_, v in res.items()}
+        return res
+
+    @staticmethod
+    def packed_layout(B, m, p, r):
+        """Offsets (in elements) of [logp | g_a0 | g_P0 | g_c | g_d | g_T | g_Z | g_R | g_H | g_Q] inside one flat
+        buffer of B * (1 + n_grad) elements: the single buffer the multi-GPU gather ships."""
+        sizes = {"logp": 1, "a0": m, "P0": m * m, "c": m, "d": p, "T": m * m, "Z": p * m, "R": m * r,
+                 "H": p * p, "Q": r * r}
+        shapes = {"logp": (B,), "a0": (B, m), "P0": (B, m, m), "c": (B, m), "d": (B, p), "T": (B, m, m),
+                  "Z": (B, p, m), "R": (B, m, r), "H": (B, p, p), "Q": (B, r, r)}
+        off, layout = 0, {}
+        for k_, sz in sizes.items():
+            layout[k_] = (off, B * sz, shapes[k_])
+            off += B * sz
+        return layout, off
+
+    def logp_grad(self, kind, y, a0, P0, c, d, T, Z, R, H, Q, ll_cotangent=None, cov_jitter=None,
+                  missing_fill_value=None, grads=PARAM_NAMES, dtype=None, packed_out=None):
+        """logp[b] = sum_t loglike_obs[b,t] and d(sum_t cot*ll)/d{a0..Q} (reverse-mode adjoint kernels).
+
+        ``packed_out``: optional flat preallocated buffer (see :meth:`packed_layout`); logp and the gradients
+        are then written straight into it (views are returned), so a gather needs no packing kernel."""
+        params = dict(zip(PARAM_NAMES, (a0, P0, c, d, T, Z, R, H, Q)))
+        bufs = _Buffers([y, *params.values()], dtype)
+        params = {k_: (v if _is_torch(v) else np.asarray(v)) for k_, v in params.items()}
+        y = y if _is_torch(y) else np.asarray(y)
+        B = self._batch_size(y, params)
+        squeeze = B is None
+        B = 1 if squeeze else int(B)
+        prob, yb, arrs = self._problem(kind, bufs, y, params, B, cov_jitter, missing_fill_value)
+        n, m, p, r = prob.n, prob.m, prob.p, prob.r
+        gshape = {"a0": (B, m), "P0": (B, m, m), "c": (B, m), "d": (B, p), "T": (B, m, m), "Z": (B, p, m),
+                  "R": (B, m, r), "H": (B, p, p), "Q": (B, r, r)}
+        if packed_out is not None:
+            layout, total = self.packed_layout(B, m, p, r)
+            flat = packed_out.reshape(-1)
+            if flat.shape[0] != total:
+                raise BkfError(f"packed_out must hold {total} elements, got {flat.shape[0]}")
+            view = lambda k_: flat[layout[k_][0]:layout[k_][0] + layout[k_][1]].reshape(layout[k_][2])
+            gouts = {k_: (view(k_) if k_ in grads else None) for k_ in PARAM_NAMES}
+            logp = view("logp")
+        else:
+            gouts = {k_: (bufs.out(gshape[k_]) if k_ in grads else None) for k_ in PARAM_NAMES}
+            logp = bufs.out((B,))
+        status = bufs.out_int((B,))
+        cot = None
+        if ll_cotangent is not None:
+            cot = bufs.inp(ll_cotangent)
+            if tuple(cot.shape) != (B, n) and not (squeeze and tuple(cot.shape) == (n,)):
+                raise BkfError("ll_cotangent must have shape (B, n)")
+        if bufs.device:
+            self.use_torch_stream()
+        rc = self.lib.bkf_filter_logp_grad(
+            self.h, C.byref(prob), bufs.ptr(yb), *[bufs.ptr(a) for a in arrs], bufs.ptr(cot), bufs.ptr(logp),
+            *[bufs.ptr(gouts[k_]) for k_ in PARAM_NAMES], bufs.ptr(status))
+        self._check(rc)
+        g = {k_: v for k_, v in gouts.items() if v is not None}
+        if squeeze:
+            return logp[0], {k_: v[0] for k_, v in g.items()}, status[0]
+        return logp, g, status
+
+    def smooth(self, T, R, Q, filtered_states, filtered_covariances, cov_jitter=None, dtype=None):
+        """Batched ``KalmanSmoother.build_graph`` (kalman_smoother.py:66-105)."""
+        bufs = _Buffers([T, R, Q, filtered_states, filtered_covariances], dtype)
+        conv = lambda v: v if _is_torch(v) else np.asarray(v)
+        T, R, Q, fa, fP = map(conv, (T, R, Q, filtered_states, filtered_covariances))
+        squeeze = fa.ndim == 2
+        if squeeze:
+            fa, fP = fa[None], fP[None]
+        B, n, m = (int(s) for s in fa.shape)
+        r = int(R.shape[-1])
+        shared_mask = 0
+        for name, x, bit in (("T", T, 4), ("R", R, 6), ("Q", Q, 8)):
+            if x.ndim == 2:
+                shared_mask |= 1 << bit
+            elif x.shape[0] != B:
+                raise BkfError(f"{name}: leading batch dimension {x.shape[0]} != {B}")
+        default_jitter = JITTER_F64 if bufs.code == F64 else JITTER_F32
+        prob = BkfProblem(kind=STANDARD, dtype=bufs.code, mem=MEM_DEVICE if bufs.device else MEM_HOST, B=B, n=n,
+                          m=m, p=1, r=r, y_shared=0, shared_mask=shared_mask, tv_mask=0,
+                          cov_jitter=default_jitter if cov_jitter is None else float(cov_jitter),
+                          missing_fill=MISSING_FILL)
+        Tb, Rb, Qb, fab, fPb = map(bufs.inp, (T, R, Q, fa, fP))
+        sa, sP = bufs.out((B, n, m)), bufs.out((B, n, m, m))
+        if bufs.device:
+            self.use_torch_stream()
+        rc = self.lib.bkf_smooth(self.h, C.byref(prob), *[bufs.ptr(x) for x in (Tb, Rb, Qb, fab, fPb, sa, sP)],
+                                 None)
+        self._check(rc)
+        return (sa[0], sP[0]) if squeeze else (sa, sP)
+
+    def filter_smooth(self, kind, y, a0, P0, c, d, T, Z, R, H, Q, cov_jitter=None, missing_fill_value=None,
+                      dtype=None):
+        """Filter forward + RTS smoother in one call (core/statespace.py:903-951); the filtered trajectory
+        stays in the device workspace.  Returns (loglike_obs, smoothed_states, smoothed_covariances, status)."""
+        params = dict(zip(PARAM_NAMES, (a0, P0, c, d, T, Z, R, H, Q)))
+        bufs = _Buffers([y, *params.values()], dtype)
+        params = {k_: (v if _is_torch(v) else np.asarray(v)) for k_, v in params.items()}
+        y = y if _is_torch(y) else np.asarray(y)
+        B = self._batch_size(y, params)
+        squeeze = B is None
+        B = 1 if squeeze else int(B)
+        prob, yb, arrs = self._problem(kind, bufs, y, params, B, cov_jitter, missing_fill_value)
+        n, m = prob.n, prob.m
+        ll, sa, sP = bufs.out((B, n)), bufs.out((B, n, m)), bufs.out((B, n, m, m))
+        status = bufs.out_int((B,))
+        if bufs.device:
+            self.use_torch_stream()
+        rc = self.lib.bkf_filter_smooth(self.h, C.byref(prob), bufs.ptr(yb), *[bufs.ptr(a) for a in arrs],
+                                        bufs.ptr(ll), bufs.ptr(sa), bufs.ptr(sP), bufs.ptr(status))
+        self._check(rc)
+        if squeeze:
+            return ll[0], sa[0], sP[0], status[0]
+        return ll, sa, sP, status
+
+
+_default_engines: dict[tuple[int, int], KalmanEngine] = {}
+
+
+def default_engine(device: int = 0) -> KalmanEngine:
+    """Per-process (fork-safe: keyed by pid) lazily created engine, as a PyTensor Op.perform needs it."""
+    key = (os.getpid(), device)
+    if key not in _default_engines:
+        _default_engines[key] = KalmanEngine(device)
+    return _default_engines[key]
