@@ -216,6 +216,35 @@ extern "C" int bkf_set_stream(bkf_handle* h, void* s) {
 }
 
 // ----------------------------------------------------------------------------------------------------
+// kernel-family dispatch: specialised register-tiled kernels where they exist, the generic path otherwise
+static int run_forward(bkf_handle* h, const KArgs<double>& g, const char** err) {
+    KernelTimer kt(h, BKF_KERNEL_FORWARD);
+    h->launches += 1;
+    if (sw::supported(g.kind, g.m, g.p)) {
+        h->path = "subwarp_f64";
+        return sw::launch_f64(g, false, h->stream, err);
+    }
+    h->path = "generic_warp";
+    return gen::launch_forward<double>(g, h->stream, err);
+}
+static int run_forward(bkf_handle* h, const KArgs<float>& g, const char** err) {
+    KernelTimer kt(h, BKF_KERNEL_FORWARD);
+    h->launches += 1;
+    h->path = "generic_warp";
+    return gen::launch_forward<float>(g, h->stream, err);
+}
+static int run_backward(bkf_handle* h, const KArgs<double>& g, const char** err) {
+    KernelTimer kt(h, BKF_KERNEL_BACKWARD);
+    h->launches += 1;
+    if (sw::supported(g.kind, g.m, g.p)) return sw::launch_f64(g, true, h->stream, err);
+    return gen::launch_backward<double>(g, h->stream, err);
+}
+static int run_backward(bkf_handle* h, const KArgs<float>& g, const char** err) {
+    KernelTimer kt(h, BKF_KERNEL_BACKWARD);
+    h->launches += 1;
+    return gen::launch_backward<float>(g, h->stream, err);
+}
+
 static size_t param_elems(const bkf_problem* P, int which) {
     size_t m = P->m, p = P->p, r = P->r;
     switch (which) {
@@ -330,10 +359,8 @@ static int forward_impl(bkf_handle* h, const bkf_problem* P, const void* y, cons
     if (rc != BKF_OK) return rc;
     if (B == 0) return BKF_OK;
     const char* err = "";
-    { KernelTimer kt(h, BKF_KERNEL_FORWARD); rc = gen::launch_forward<R>(g, h->stream, &err); }
+    rc = run_forward(h, g, &err);
     if (rc != BKF_OK) return fail(h, rc, err);
-    h->path = "generic_warp";
-    h->launches += 1;
     copy_back<R>(h, P, fa, g.filt_a, B * n * m, &rc);
     copy_back<R>(h, P, pa, g.pred_a, B * n * m, &rc);
     copy_back<R>(h, P, om, g.obs_mu, B * n * po, &rc);
@@ -382,15 +409,12 @@ static int logp_grad_impl(bkf_handle* h, const bkf_problem* P, const void* y, co
     if (rc != BKF_OK) return rc;
     if (B == 0) return BKF_OK;
     const char* err = "";
-    { KernelTimer kt(h, BKF_KERNEL_FORWARD); rc = gen::launch_forward<R>(g, h->stream, &err); }
+    rc = run_forward(h, g, &err);
     if (rc != BKF_OK) return fail(h, rc, err);
-    h->launches += 1;
     if (want_grad) {
-        { KernelTimer kt(h, BKF_KERNEL_BACKWARD); rc = gen::launch_backward<R>(g, h->stream, &err); }
+        rc = run_backward(h, g, &err);
         if (rc != BKF_OK) return fail(h, rc, err);
-        h->launches += 1;
     }
-    h->path = "generic_warp";
     copy_back<R>(h, P, logp, g.logp, B, &rc);
     for (int i = 0; i < BKF_NPARAM; ++i) copy_back<R>(h, P, grads[i], *gdst[i], B * param_elems(P, i), &rc);
     if (status && P->mem == BKF_MEM_HOST && rc == BKF_OK) {
@@ -472,12 +496,11 @@ static int filter_smooth_impl(bkf_handle* h, const bkf_problem* P, const void* y
     if (rc != BKF_OK) return rc;
     if (B == 0) return BKF_OK;
     const char* err = "";
-    { KernelTimer kt(h, BKF_KERNEL_FORWARD); rc = gen::launch_forward<R>(g, h->stream, &err); }
+    rc = run_forward(h, g, &err);
     if (rc != BKF_OK) return fail(h, rc, err);
     { KernelTimer kt(h, BKF_KERNEL_SMOOTHER); rc = gen::launch_smoother<R>(g, h->stream, &err); }
     if (rc != BKF_OK) return fail(h, rc, err);
-    h->launches += 2;
-    h->path = "generic_warp";
+    h->launches += 1;
     copy_back<R>(h, P, ll, g.ll, B * n, &rc);
     copy_back<R>(h, P, sa, g.sm_a, B * n * m, &rc);
     copy_back<R>(h, P, sP, g.sm_P, B * n * m * m, &rc);

@@ -37,6 +37,11 @@ def _ill(name):
     return ("missing" in name and any(s in name for s in ("p2", "p3", "p5")))
 
 
+def _diffuse(name):
+    # P0 = 1e6 I (Nile test, config C1): every implementation loses ~6 digits in the first update
+    return "nile" in name or name.startswith("c1_")
+
+
 def _close(actual, desired, rtol, msg):
     scale = max(np.abs(desired).max(), 1e-300)
     assert_allclose(np.asarray(actual).reshape(desired.shape), desired, rtol=0, atol=rtol * scale, err_msg=msg)
@@ -49,7 +54,7 @@ def test_forward_outputs_match_reference_golden(eng, name):
     rtol = 1e-6 if _ill(name) else RTOL64
     assert_allclose(out["loglike_obs"].sum(), ref["loglike_obs"].sum(), rtol=rtol)
     for n in OUT_NAMES:
-        _close(out[n], ref[n], rtol if "nile" not in name else 1e-8, f"{name}:{n}")
+        _close(out[n], ref[n], rtol if not _diffuse(name) else 1e-8, f"{name}:{n}")
 
 
 @pytest.mark.parametrize("name", [n for n in golden_names() if "cholesky" not in n])
@@ -59,7 +64,7 @@ def test_logp_and_gradients_match_reference_golden(eng, name):
     rtol = 1e-6 if _ill(name) else RTOL64
     assert_allclose(logp, ref["loglike_obs"].sum(), rtol=rtol)
     for k in NAMES:
-        _close(grads[k], ref["grad_" + k], rtol if "nile" not in name else 1e-7, f"{name}: d/d{k}")
+        _close(grads[k], ref["grad_" + k], rtol if not _diffuse(name) else 1e-7, f"{name}: d/d{k}")
 
 
 @pytest.mark.parametrize("name", golden_names())
@@ -91,6 +96,39 @@ def test_batched_logp_grad_matches_torch_oracle(eng, kind, shape, missing):
         for b in range(B):
             _close(grads[k][b], ref_g[k][b], RTOL64, f"d/d{k}[{b}]")
     assert (status == 0).all()
+
+
+@pytest.mark.parametrize("kind", ["standard", "univariate"])
+def test_specialised_kernel_path_is_taken_for_m15(eng, kind):
+    from pymc_experimental_b200 import synth
+
+    cfg = synth.sarima(B=5, n=12)
+    eng.logp_grad(kind, cfg["y"], *[cfg[k] for k in NAMES])
+    assert eng.last_path == "subwarp_f64"
+
+
+@pytest.mark.parametrize("kind", ["standard", "univariate"])
+@pytest.mark.parametrize("B", [1, 2, 3, 7, 130])
+def test_subwarp_kernels_ragged_batches_and_asymmetric_P0(eng, kind, B):
+    """m = 15 register-tiled path: batch sizes that leave lanes / sub-warps idle, an asymmetric P0 (gradient
+    convention: every entry independent) and missing values."""
+    from oracle import kalman_torch as oth
+    from pymc_experimental_b200 import synth
+
+    cfg = synth.random_dense(B, 17, 15, 1, 4, seed=40 + B, missing=0.2)
+    rng = np.random.default_rng(B)
+    cfg["P0"] = cfg["P0"] + 0.05 * rng.standard_normal(cfg["P0"].shape)  # not symmetric any more
+    args = [cfg["y"]] + [cfg[k] for k in NAMES]
+    out = eng.filter(kind, *args)
+    ref = oth.kalman_filter(kind, *[__import__("torch").as_tensor(a) for a in args])
+    for got, want in zip([out[n] for n in OUT_NAMES], ref):
+        _close(got, want.numpy(), RTOL64, kind)
+    logp, grads, status = eng.logp_grad(kind, *args)
+    ref_logp, ref_g = oth.logp_and_grad(kind, *args)
+    assert_allclose(logp, ref_logp, rtol=RTOL64)
+    for k in NAMES:
+        for b in range(B):
+            _close(grads[k][b], ref_g[k][b], RTOL64, f"d/d{k}[{b}]")
 
 
 def test_ll_cotangent_is_respected(eng):
