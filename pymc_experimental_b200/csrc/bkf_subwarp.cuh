@@ -474,34 +474,32 @@ __global__ void __launch_bounds__(64) backward_kernel(KArgs<double> g) {
         gc += abar;
         // ================= update adjoint =================
         if (KIND == K_UNI) {
-            if (u.keep != 0.0) {
-                const double llbar = -0.5 * gcot;
-                const double F = u.F, v = u.v;
-                const double pk = dot<M>(Pfb, u.kv);  // (Pu_bar K)_j, Pu_bar = S(Pfbar) ~ Pfbar
-                const double Kbar = fma(-2.0 * F, pk, afbar * v);
-                const double kpk = sub_sum(u.K * pk, LPS);
-                const double ka = sub_sum(u.K * afbar, LPS);
-                const double kk = sub_sum(Kbar * u.K, LPS);
-                const double Fbar = -kpk + llbar * (1.0 / F - v * v / (F * F)) - kk / F;
-                const double vbar = ka + llbar * 2.0 * v / F;
-                const double pzbar = Kbar / F + Fbar * u.zj;
-                if (act) sm[S::VP + j] = pzbar;
-                __syncwarp();
-                double pzv[M];
-                load_vec<M>(sm + S::VP, pzv);
-                const double zbar = fma(Fbar, u.pz, dot<M>(Pc, pzv)) - vbar * a_j;
-                abar = fma(-vbar, u.zj, afbar);
+            // Branch-free on purpose: the series sharing a warp may disagree on `keep` (missing data), and the
+            // shuffles / __syncwarp below must be executed by all 32 lanes.  When keep == 0 (K = 0: a and P pass
+            // through, no parameter gradient) the computed values are discarded by the selects.
+            const bool keep = u.keep != 0.0;
+            const double llbar = -0.5 * gcot;
+            const double F = u.F, v = u.v;
+            const double pk = dot<M>(Pfb, u.kv);  // (Pu_bar K)_j, Pu_bar = S(Pfbar) ~ Pfbar
+            const double Kbar = fma(-2.0 * F, pk, afbar * v);
+            const double kpk = sub_sum(u.K * pk, LPS);
+            const double ka = sub_sum(u.K * afbar, LPS);
+            const double kk = sub_sum(Kbar * u.K, LPS);
+            const double Fbar = -kpk + llbar * (1.0 / F - v * v / (F * F)) - kk / F;
+            const double vbar = ka + llbar * 2.0 * v / F;
+            const double pzbar = Kbar / F + Fbar * u.zj;
+            if (act) sm[S::VP + j] = pzbar;
+            __syncwarp();
+            double pzv[M];
+            load_vec<M>(sm + S::VP, pzv);
+            const double zbar = fma(Fbar, u.pz, dot<M>(Pc, pzv)) - vbar * a_j;
+            abar = keep ? fma(-vbar, u.zj, afbar) : afbar;
 #pragma unroll
-                for (int i = 0; i < M; ++i) Pbar[i] = fma(pzv[i], u.zj, Pfb[i]);
-                gz += zbar;
-                gH += Fbar;
-                gd -= vbar;
-                __syncwarp();
-            } else {
-                abar = afbar;
-#pragma unroll
-                for (int i = 0; i < M; ++i) Pbar[i] = Pfb[i];
-            }
+            for (int i = 0; i < M; ++i) Pbar[i] = keep ? fma(pzv[i], u.zj, Pfb[i]) : Pfb[i];
+            gz += keep ? zbar : 0.0;
+            gH += keep ? Fbar : 0.0;
+            gd -= keep ? vbar : 0.0;
+            __syncwarp();
         } else {
             // G2 = S(Pfbar) ~ Pfbar (symmetric up to rounding): column j doubles as row j
             const double F = u.F, v = u.v, f0 = u.f0;

@@ -71,9 +71,15 @@ def test_logp_and_gradients_match_reference_golden(eng, name):
 def test_smoother_matches_reference_golden(eng, name):
     kind, ins, ref = load_golden(name)
     sa, sP = eng.smooth(ins["T"], ins["R"], ins["Q"], ref["filtered_states"], ref["filtered_covariances"])
-    tol = 1e-4 if ("nile" in name or _ill(name)) else 1e-8  # pinv of cond ~1e14 matrices on Nile
+    tol = 1e-4 if (_diffuse(name) or _ill(name)) else 1e-8
+    lo = 0
+    if _diffuse(name):
+        # P0 = 1e6 I: pinv(P_hat) of a cond ~1e14 matrix decides the first few smoothed covariances; the
+        # reference's own test only compares them from index 5 on (test_kalman_filter.py:243-251)
+        lo = 5
+        _close(sP[:5], ref["smoothed_covariances"][:5], 2e-2, f"{name}: smoothed_covariances[:5]")
     _close(sa, ref["smoothed_states"], tol, f"{name}: smoothed_states")
-    _close(sP, ref["smoothed_covariances"], tol, f"{name}: smoothed_covariances")
+    _close(sP[lo:], ref["smoothed_covariances"][lo:], tol, f"{name}: smoothed_covariances")
     assert_allclose(sa[-1], ref["filtered_states"][-1])  # reference test_kalman_filter.py:216-224
     assert_allclose(sP[-1], ref["filtered_covariances"][-1])
 
