@@ -14,4 +14,8 @@ namespace sw {  // register-tiled sub-warp-per-series kernels, float64, p = 1 (b
 bool supported(int kind, int m, int p);
 int launch_f64(const KArgs<double>& g, bool backward, cudaStream_t stream, const char** err);
 }  // namespace sw
+namespace tps {  // thread-per-series kernels, m <= 4, p = 1 (bkf_thread.cu)
+bool supported(int kind, int m, int p);
+template <typename R> int launch_any(const KArgs<R>& g, bool backward, cudaStream_t stream, const char** err);
+}  // namespace tps
 }  // namespace bkf

@@ -1,4 +1,5 @@
-// bkf_subwarp.cu -- instantiations + dispatcher of the sub-warp kernels (see bkf_subwarp.cuh).
+// bkf_subwarp.cu -- dispatcher of the sub-warp kernels (see bkf_subwarp.cuh); instantiations live in
+// bkf_subwarp_inst_*.cu so that nvcc compiles them in parallel.
 #include "bkf_subwarp.cuh"
 
 #include "bkf_launch.h"
@@ -6,15 +7,23 @@
 namespace bkf {
 namespace sw {
 
+#define BKF_SW_DECL(M) extern template int launch<M>(const KArgs<double>&, bool, cudaStream_t, const char**);
+BKF_SW_DECL(5) BKF_SW_DECL(6) BKF_SW_DECL(7) BKF_SW_DECL(8) BKF_SW_DECL(9) BKF_SW_DECL(10) BKF_SW_DECL(11)
+BKF_SW_DECL(12) BKF_SW_DECL(13) BKF_SW_DECL(14) BKF_SW_DECL(15) BKF_SW_DECL(16)
+#undef BKF_SW_DECL
+
 bool supported(int kind, int m, int p) {
     if (p != 1) return false;
     if (kind != BKF_STANDARD && kind != BKF_UNIVARIATE) return false;
-    return m == 15;
+    return m >= 5 && m <= 16;
 }
 
 int launch_f64(const KArgs<double>& g, bool backward, cudaStream_t stream, const char** err) {
     switch (g.m) {
-        case 15: return launch<15>(g, backward, stream, err);
+#define BKF_SW_CASE(M) case M: return launch<M>(g, backward, stream, err);
+        BKF_SW_CASE(5) BKF_SW_CASE(6) BKF_SW_CASE(7) BKF_SW_CASE(8) BKF_SW_CASE(9) BKF_SW_CASE(10) BKF_SW_CASE(11)
+        BKF_SW_CASE(12) BKF_SW_CASE(13) BKF_SW_CASE(14) BKF_SW_CASE(15) BKF_SW_CASE(16)
+#undef BKF_SW_CASE
     }
     *err = "no sub-warp kernel for this m";
     return BKF_ERR_UNSUPPORTED;

@@ -1,0 +1,8 @@
+// explicit instantiations of the sub-warp kernels for m in {5 6 7 8} (see bkf_subwarp.cuh)
+#include "bkf_subwarp.cuh"
+namespace bkf { namespace sw {
+template int launch<5>(const KArgs<double>&, bool, cudaStream_t, const char**);
+template int launch<6>(const KArgs<double>&, bool, cudaStream_t, const char**);
+template int launch<7>(const KArgs<double>&, bool, cudaStream_t, const char**);
+template int launch<8>(const KArgs<double>&, bool, cudaStream_t, const char**);
+} }

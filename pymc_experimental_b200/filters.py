@@ -1,0 +1,177 @@
+"""Drop-in mirrors of ``pymc_extras.statespace.filters`` backed by the CUDA engine.
+
+Same class names, ``build_graph`` signatures, attributes and output order as the reference:
+
+* ``BaseFilter.build_graph(data, a0, P0, c, d, T, Z, R, H, Q, mode=None, return_updates=False,
+  missing_fill_value=None, cov_jitter=None)``  -- kalman_filter.py:144-238; returns
+  ``[filtered_states, predicted_states, observed_states, filtered_covariances, predicted_covariances,
+  observed_covariances, loglike_obs]`` (kalman_filter.py:298-308) and sets ``seq_names / non_seq_names /
+  n_states / n_shocks / n_endog / mode / missing_fill_value / cov_jitter`` which ``PyMCStateSpace`` reads
+  (core/statespace.py:628, 1267, 2053, 2249).
+* ``KalmanSmoother.build_graph(T, R, Q, filtered_states, filtered_covariances, mode=None, cov_jitter=...)``
+  -- kalman_smoother.py:66-105; returns ``(smoothed_states, smoothed_covariances)``.
+* ``FILTER_FACTORY`` -- core/statespace.py:51-55.
+
+Two calling modes:
+
+1. **symbolic** (PyTensor installed and any input is a PyTensor variable): the graph contains one
+   :class:`~pymc_experimental_b200.pytensor_ops.KalmanFilterOp` whose ``perform`` / ``L_op`` call libbkf.so, so
+   ``pm.sample`` gets logp and dlogp from the GPU.  ``mode`` must be ``None`` (C/Python linker): there is
+   deliberately no JAX / Numba dispatch and no CPU fallback.
+2. **eager** (NumPy arrays or torch CUDA tensors): the kernels run immediately and arrays are returned.  Every
+   input may carry a leading batch axis (series x draws); this is what the tests and the benchmark use, and what a
+   vectorised caller (``pm.sample_posterior_predictive`` over all draws at once) would use.
+"""
+
+from __future__ import annotations
+
+import numpy as np
+
+from .engine import JITTER_F64, MISSING_FILL, default_engine
+
+JITTER_DEFAULT = JITTER_F64  # utils/constants.py:20 for floatX == float64
+PARAM_NAMES = ["c", "d", "T", "Z", "R", "H", "Q"]  # kalman_filter.py:22
+_STATIC_NDIM = {"c": 1, "d": 1, "T": 2, "Z": 2, "R": 2, "H": 2, "Q": 2}
+OUTPUT_NAMES = ["filtered_states", "predicted_states", "observed_states", "filtered_covariances",
+                "predicted_covariances", "observed_covariances", "loglike_obs"]
+
+
+def _is_symbolic(*xs):
+    try:
+        from pytensor.graph.basic import Variable
+    except ImportError:
+        return False
+    return any(isinstance(x, Variable) for x in xs)
+
+
+class BaseFilter:
+    """kalman_filter.py:30-68.  ``kind`` selects the CUDA kernel family."""
+
+    kind: str | None = None
+
+    def __init__(self, mode=None, device: int = 0):
+        self.mode = mode
+        self.seq_names: list[str] = []
+        self.non_seq_names: list[str] = []
+        self.n_states = None
+        self.n_posdef = None
+        self.n_shocks = None
+        self.n_endog = None
+        self.missing_fill_value = None
+        self.cov_jitter = None
+        self.device = device
+
+    def check_params(self, data, a0, P0, c, d, T, Z, R, H, Q):
+        """kalman_filter.py:70-74."""
+        return data, a0, P0, c, d, T, Z, R, H, Q
+
+    def update(self, a, P, y, d, Z, H, all_nan_flag):
+        """kalman_filter.py:413-456: the base class has no update rule."""
+        raise NotImplementedError
+
+    def build_graph(self, data, a0, P0, c, d, T, Z, R, H, Q, mode=None, return_updates=False,
+                    missing_fill_value=None, cov_jitter=None):
+        if self.kind is None:
+            raise NotImplementedError
+        if missing_fill_value is None:
+            missing_fill_value = MISSING_FILL  # kalman_filter.py:197-200
+        if cov_jitter is None:
+            cov_jitter = JITTER_DEFAULT
+        self.mode = mode
+        self.missing_fill_value = missing_fill_value
+        self.cov_jitter = cov_jitter
+        data, a0, P0, c, d, T, Z, R, H, Q = self.check_params(data, a0, P0, c, d, T, Z, R, H, Q)
+
+        if _is_symbolic(data, a0, P0, c, d, T, Z, R, H, Q):
+            if mode not in (None, "FAST_RUN", "FAST_COMPILE"):
+                raise NotImplementedError(
+                    f"mode={mode!r}: the B200 Kalman Ops only run under PyTensor's default C/Python linker "
+                    "(no JAX / Numba dispatch, no CPU fallback)")
+            from . import pytensor_ops
+
+            outs = pytensor_ops.build_filter_graph(self, data, a0, P0, c, d, T, Z, R, H, Q)
+            return (outs, {}) if return_updates else outs
+
+        # ---- eager ----
+        R_shape, Z_shape = np.shape(R), np.shape(Z)
+        self.n_states, self.n_shocks = int(R_shape[-2]), int(R_shape[-1])  # kalman_filter.py:206-210
+        self.n_posdef = self.n_shocks
+        self.n_endog = int(Z_shape[-2])
+        self.seq_names, self.non_seq_names = [], list(PARAM_NAMES)  # time-varying inputs are refused by the engine
+        eng = default_engine(self.device)
+        res = eng.filter(self.kind, data, a0, P0, c, d, T, Z, R, H, Q, cov_jitter=cov_jitter,
+                         missing_fill_value=missing_fill_value)
+        outs = [res[k] for k in OUTPUT_NAMES]
+        self.status = res["status"]
+        return (outs, {}) if return_updates else outs
+
+    def logp_and_grad(self, data, a0, P0, c, d, T, Z, R, H, Q, ll_cotangent=None, missing_fill_value=None,
+                      cov_jitter=None):
+        """Eager ``(sum_t loglike_obs, {name: d/d name})`` -- what ``model.logp_dlogp_function`` needs from the
+        filter."""
+        eng = default_engine(self.device)
+        logp, grads, status = eng.logp_grad(self.kind, data, a0, P0, c, d, T, Z, R, H, Q, ll_cotangent=ll_cotangent,
+                                            cov_jitter=cov_jitter, missing_fill_value=missing_fill_value)
+        self.status = status
+        return logp, grads
+
+
+class StandardFilter(BaseFilter):
+    """kalman_filter.py:544-617."""
+
+    kind = "standard"
+
+
+class UnivariateFilter(BaseFilter):
+    """kalman_filter.py:753-820."""
+
+    kind = "univariate"
+
+
+class SquareRootFilter(BaseFilter):
+    """kalman_filter.py:620-750.  ``P0`` is taken as a Cholesky-like factor, as in the reference."""
+
+    kind = "cholesky"
+
+
+class KalmanSmoother:
+    """kalman_smoother.py:15-126."""
+
+    def __init__(self, mode: str | None = None, device: int = 0):
+        self.mode = mode
+        self.cov_jitter = JITTER_DEFAULT
+        self.seq_names: list[str] = []
+        self.non_seq_names: list[str] = []
+        self.device = device
+
+    def build_graph(self, T, R, Q, filtered_states, filtered_covariances, mode=None, cov_jitter=JITTER_DEFAULT):
+        self.mode = mode
+        self.cov_jitter = cov_jitter
+        if _is_symbolic(T, R, Q, filtered_states, filtered_covariances):
+            if mode not in (None, "FAST_RUN", "FAST_COMPILE"):
+                raise NotImplementedError(f"mode={mode!r} is not supported by the B200 Kalman Ops")
+            from . import pytensor_ops
+
+            return pytensor_ops.build_smoother_graph(self, T, R, Q, filtered_states, filtered_covariances)
+        self.seq_names, self.non_seq_names = [], ["T", "R", "Q"]
+        eng = default_engine(self.device)
+        return eng.smooth(T, R, Q, filtered_states, filtered_covariances, cov_jitter=cov_jitter)
+
+
+# core/statespace.py:51-55
+FILTER_FACTORY = {
+    "standard": StandardFilter,
+    "univariate": UnivariateFilter,
+    "cholesky": SquareRootFilter,
+}
+
+
+def install_into_pymc_extras():
+    """Make every ``PyMCStateSpace`` (SARIMAX, VARMAX, ETS, structural ...) pick up the CUDA filters:
+    overrides the three ``FILTER_FACTORY`` entries and the ``KalmanSmoother`` used by
+    ``pymc_extras.statespace.core.statespace`` (core/statespace.py:51-55, 253-254).  Needs pymc_extras."""
+    import pymc_extras.statespace.core.statespace as ss
+
+    ss.FILTER_FACTORY.update(FILTER_FACTORY)
+    ss.KalmanSmoother = KalmanSmoother
+    return ss.FILTER_FACTORY

@@ -137,6 +137,48 @@ def test_subwarp_kernels_ragged_batches_and_asymmetric_P0(eng, kind, B):
             _close(grads[k][b], ref_g[k][b], RTOL64, f"d/d{k}[{b}]")
 
 
+@pytest.mark.parametrize("kind", ["standard", "univariate"])
+@pytest.mark.parametrize("m", [1, 2, 3, 4])
+def test_thread_per_series_kernels(eng, kind, m):
+    """m <= 4 register-resident path (ETS, local level): asymmetric P0, missing values, odd batch size."""
+    from oracle import kalman_torch as oth
+    from pymc_experimental_b200 import synth
+
+    B = 203
+    cfg = synth.random_dense(B, 21, m, 1, max(1, m - 1), seed=70 + m, missing=0.15)
+    cfg["P0"] = cfg["P0"] + 0.05 * np.random.default_rng(m).standard_normal(cfg["P0"].shape)
+    args = [cfg["y"]] + [cfg[k] for k in NAMES]
+    out = eng.filter(kind, *args)
+    assert eng.last_path == "thread_f64"
+    ref = oth.kalman_filter(kind, *[__import__("torch").as_tensor(a) for a in args])
+    for got, want in zip([out[n] for n in OUT_NAMES], ref):
+        _close(got, want.numpy(), RTOL64, kind)
+    logp, grads, status = eng.logp_grad(kind, *args)
+    ref_logp, ref_g = oth.logp_and_grad(kind, *args)
+    assert_allclose(logp, ref_logp, rtol=RTOL64)
+    for k in NAMES:
+        for b in range(0, B, 17):
+            _close(grads[k][b], ref_g[k][b], RTOL64, f"d/d{k}[{b}]")
+
+
+@pytest.mark.parametrize("m", [5, 6, 8, 9, 12, 16])
+def test_subwarp_kernels_all_sizes(eng, m):
+    from oracle import kalman_torch as oth
+    from pymc_experimental_b200 import synth
+
+    B = 11
+    cfg = synth.random_dense(B, 15, m, 1, 3, seed=90 + m, missing=0.1)
+    args = [cfg["y"]] + [cfg[k] for k in NAMES]
+    for kind in ("standard", "univariate"):
+        logp, grads, status = eng.logp_grad(kind, *args)
+        assert eng.last_path == "subwarp_f64"
+        ref_logp, ref_g = oth.logp_and_grad(kind, *args)
+        assert_allclose(logp, ref_logp, rtol=RTOL64)
+        for k in NAMES:
+            for b in range(B):
+                _close(grads[k][b], ref_g[k][b], RTOL64, f"{kind} m={m} d/d{k}[{b}]")
+
+
 def test_ll_cotangent_is_respected(eng):
     from oracle import kalman_torch as oth
     from pymc_experimental_b200 import synth
