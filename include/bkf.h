@@ -56,7 +56,9 @@ enum { BKF_PARAM_A0 = 0, BKF_PARAM_P0, BKF_PARAM_C, BKF_PARAM_D, BKF_PARAM_T, BK
 /* call-level error codes */
 enum { BKF_OK = 0, BKF_ERR_ARG = -1, BKF_ERR_UNSUPPORTED = -2, BKF_ERR_CUDA = -3, BKF_ERR_NOMEM = -4 };
 /* per-series status bits */
-enum { BKF_STATUS_OK = 0, BKF_STATUS_NOT_PD = 1, BKF_STATUS_NONFINITE = 2 };
+enum { BKF_STATUS_OK = 0, BKF_STATUS_NOT_PD = 1, BKF_STATUS_NONFINITE = 2,
+       BKF_STATUS_SMOOTHER_ILL = 4 /* P_hat too ill-conditioned for the Cholesky smoother: series was re-run with the
+                                      eigen-decomposition pinv (informational) */ };
 
 typedef struct bkf_handle bkf_handle;
 

@@ -16,7 +16,7 @@ enum Slot {
     S_Y = 0, S_A0, S_P0, S_C, S_D, S_T, S_Z, S_R, S_H, S_Q,            // inputs
     S_FA, S_PA, S_OM, S_FP, S_PP, S_OC, S_LL,                          // forward outputs
     S_TRAJ, S_COT, S_LOGP, S_GA0, S_GP0, S_GC, S_GD, S_GT, S_GZ, S_GR, S_GH, S_GQ, S_STATUS,
-    S_SMA, S_SMP, S_WFA, S_WFP, S_NSLOT
+    S_SMA, S_SMP, S_WFA, S_WFP, S_FLAG, S_NSLOT
 };
 
 struct bkf_handle {
@@ -255,6 +255,39 @@ static int run_backward(bkf_handle* h, const KArgs<float>& g, const char** err) 
     return gen::launch_backward<float>(g, h->stream, err);
 }
 
+// Smoother dispatch: Cholesky sub-warp kernel when available; whole-call fallback to the eigen-decomposition
+// pinv of the generic kernel if any series was flagged ill-conditioned (costs one 4-byte readback).
+static int run_smoother(bkf_handle* h, const KArgs<double>& g, const char** err) {
+    const double jitter0 = 1e-8;  // JITTER_DEFAULT (float64), kalman_smoother.py:117
+    if (sw::smoother_supported(g.m)) {
+        int rc = BKF_OK;
+        int* flag = (int*)ensure(h, S_FLAG, sizeof(int), &rc);
+        if (!flag) return rc;
+        cudaMemsetAsync(flag, 0, sizeof(int), h->stream);
+        {
+            KernelTimer kt(h, BKF_KERNEL_SMOOTHER);
+            h->launches += 1;
+            rc = sw::launch_smoother_f64(g, jitter0, flag, h->stream, err);
+        }
+        if (rc != BKF_OK) return rc;
+        int host_flag = 0;
+        cudaError_t e = cudaMemcpyAsync(&host_flag, flag, sizeof(int), cudaMemcpyDeviceToHost, h->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+        if (e != cudaSuccess) { *err = cudaGetErrorString(e); return BKF_ERR_CUDA; }
+        h->path = "subwarp_f64";
+        if (!host_flag) return BKF_OK;
+        h->path = "generic_warp(smoother fallback)";
+    }
+    KernelTimer kt(h, BKF_KERNEL_SMOOTHER);
+    h->launches += 1;
+    return gen::launch_smoother<double>(g, h->stream, err);
+}
+static int run_smoother(bkf_handle* h, const KArgs<float>& g, const char** err) {
+    KernelTimer kt(h, BKF_KERNEL_SMOOTHER);
+    h->launches += 1;
+    return gen::launch_smoother<float>(g, h->stream, err);
+}
+
 static size_t param_elems(const bkf_problem* P, int which) {
     size_t m = P->m, p = P->p, r = P->r;
     switch (which) {
@@ -463,16 +496,23 @@ static int smooth_impl(bkf_handle* h, const bkf_problem* P, const void* T, const
     g.sm_filt_P = stage_in<R>(h, P, S_WFP, fP, B * n * m * m, &rc);
     g.sm_a = stage_out<R>(h, P, S_SMA, sa, B * n * m, &rc);
     g.sm_P = stage_out<R>(h, P, S_SMP, sP, B * n * m * m, &rc);
-    (void)status;
+    int* dstatus = nullptr;
+    if (status) {
+        dstatus = P->mem == BKF_MEM_DEVICE ? status : (int*)ensure(h, S_STATUS, B * sizeof(int), &rc);
+        if (dstatus) cudaMemsetAsync(dstatus, 0, B * sizeof(int), h->stream);
+    }
+    g.status = dstatus;
     if (rc != BKF_OK) return rc;
     if (B == 0) return BKF_OK;
     const char* err = "";
-    { KernelTimer kt(h, BKF_KERNEL_SMOOTHER); rc = gen::launch_smoother<R>(g, h->stream, &err); }
+    rc = run_smoother(h, g, &err);
     if (rc != BKF_OK) return fail(h, rc, err);
-    h->launches += 1;
-    h->path = "generic_warp";
     copy_back<R>(h, P, sa, g.sm_a, B * n * m, &rc);
     copy_back<R>(h, P, sP, g.sm_P, B * n * m * m, &rc);
+    if (status && P->mem == BKF_MEM_HOST && rc == BKF_OK) {
+        cudaError_t e = cudaMemcpyAsync(status, dstatus, B * sizeof(int), cudaMemcpyDeviceToHost, h->stream);
+        if (e != cudaSuccess) rc = cuda_fail(h, e, "D2H copy");
+    }
     return finish(h, P, rc);
 }
 
@@ -508,9 +548,8 @@ static int filter_smooth_impl(bkf_handle* h, const bkf_problem* P, const void* y
     const char* err = "";
     rc = run_forward(h, g, &err);
     if (rc != BKF_OK) return fail(h, rc, err);
-    { KernelTimer kt(h, BKF_KERNEL_SMOOTHER); rc = gen::launch_smoother<R>(g, h->stream, &err); }
+    rc = run_smoother(h, g, &err);
     if (rc != BKF_OK) return fail(h, rc, err);
-    h->launches += 1;
     copy_back<R>(h, P, ll, g.ll, B * n, &rc);
     copy_back<R>(h, P, sa, g.sm_a, B * n * m, &rc);
     copy_back<R>(h, P, sP, g.sm_P, B * n * m * m, &rc);

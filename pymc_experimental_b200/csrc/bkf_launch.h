@@ -13,6 +13,8 @@ template <typename R> int launch_smoother(const KArgs<R>& g, cudaStream_t stream
 namespace sw {  // register-tiled sub-warp-per-series kernels, float64, p = 1 (bkf_subwarp.cu)
 bool supported(int kind, int m, int p);
 int launch_f64(const KArgs<double>& g, bool backward, cudaStream_t stream, const char** err);
+bool smoother_supported(int m);
+int launch_smoother_f64(const KArgs<double>& g, double jitter0, int* any_ill, cudaStream_t stream, const char** err);
 }  // namespace sw
 namespace tps {  // thread-per-series kernels, m <= 4, p = 1 (bkf_thread.cu)
 bool supported(int kind, int m, int p);

@@ -21,7 +21,7 @@ KINDS = {"standard": STANDARD, "univariate": UNIVARIATE, "cholesky": CHOLESKY}
 F64, F32 = 0, 1
 MEM_HOST, MEM_DEVICE = 0, 1
 PARAM_NAMES = ("a0", "P0", "c", "d", "T", "Z", "R", "H", "Q")  # utils/constants.py:24 (x0 == a0)
-STATUS_NOT_PD, STATUS_NONFINITE = 1, 2
+STATUS_NOT_PD, STATUS_NONFINITE, STATUS_SMOOTHER_ILL = 1, 2, 4
 
 # pymc_extras/statespace/utils/constants.py:19-20
 MISSING_FILL = -9999.0

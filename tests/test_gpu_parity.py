@@ -250,6 +250,42 @@ def test_filter_smooth_fused_call(eng):
         _close(sP[b], rP, 1e-8, "smoothed_covariances")
 
 
+@pytest.mark.parametrize("m", [5, 8, 11, 15, 16])
+def test_subwarp_smoother_matches_oracle(eng, m):
+    from oracle import kalman_np as onp
+    from pymc_experimental_b200 import synth
+
+    B, n = 7, 19
+    cfg = synth.random_dense(B, n, m, 1, 3, seed=200 + m, missing=0.1)
+    ll, sa, sP, status = eng.filter_smooth("standard", cfg["y"], *[cfg[k] for k in NAMES])
+    assert eng.last_path == "subwarp_f64"
+    for b in range(B):
+        outs = onp.kalman_filter("standard", cfg["y"][b], *[cfg[k][b] for k in NAMES])
+        ra, rP = onp.kalman_smoother(cfg["T"][b], cfg["R"][b], cfg["Q"][b], outs[0], outs[3])
+        assert_allclose(ll[b], outs[-1], rtol=1e-9, atol=1e-11)
+        _close(sa[b], ra, 1e-8, f"m={m} smoothed_states[{b}]")
+        _close(sP[b], rP, 1e-8, f"m={m} smoothed_covariances[{b}]")
+
+
+def test_ill_conditioned_smoother_falls_back_to_eigen_pinv(eng):
+    """P_hat with pivots spanning > 1e13: the Cholesky smoother flags the series and the call is re-run with the
+    eigen-decomposition pinv (the reference's SVD pinv semantics)."""
+    from oracle import kalman_np as onp
+
+    m, n = 6, 5
+    rng = np.random.default_rng(3)
+    T = np.eye(m)
+    R = np.eye(m)[:, :2]
+    Q = np.eye(2) * 1e-3
+    fa = rng.standard_normal((n, m))
+    fP = np.broadcast_to(np.diag([1e9, 1.0, 1.0, 1e-6, 1.0, 1.0]), (n, m, m)).copy()
+    sa, sP = eng.smooth(T, R, Q, fa, fP)
+    assert "fallback" in eng.last_path
+    ra, rP = onp.kalman_smoother(T, R, Q, fa, fP)
+    _close(sa, ra, 1e-5, "smoothed_states")
+    _close(sP, rP, 1e-5, "smoothed_covariances")
+
+
 def test_empty_batch_and_single_step(eng):
     from pymc_experimental_b200 import synth
 
