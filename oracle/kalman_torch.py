@@ -141,9 +141,15 @@ def sqrt_step(y, a, Pc, c, d, T, Z, R, H, Q, fill, jitter):
     lower = torch.cat([torch.zeros(*bshape, m, p, dtype=a.dtype), Pc.expand(*bshape, m, m)], dim=-1)
     A_T = torch.cat([upper, lower], dim=-2)
     # the all-missing branch (:700-705) does not use B: keep its (singular) QR out of the autograd graph
+    A_T_raw = A_T
     A_T = torch.where(flag[..., None, None], _eye_like(A_T).expand_as(A_T), A_T)
     B = _mT(_qr_r(_mT(A_T)))  # :679
     Fc = B[..., :p, :p]
+    Fc_out = Fc
+    if bool(flag.any()):  # the reported F_chol of an all-missing step is the factor of the real (singular) block
+        with torch.no_grad():
+            B_raw = _mT(_qr_r(_mT(A_T_raw)))
+        Fc_out = torch.where(flag[..., None, None], B_raw[..., :p, :p], Fc)
     KFc = B[..., p:, :p]
     Pcf = B[..., p:, p:]
     # non-degenerate branch (:685-698); guard the triangular solves where the branch is not selected
@@ -165,7 +171,7 @@ def sqrt_step(y, a, Pc, c, d, T, Z, R, H, Q, fill, jitter):
     bshape = torch.broadcast_shapes(TP.shape[:-2], RQ.shape[:-2])
     M = _mT(torch.cat([TP.expand(*bshape, *TP.shape[-2:]), RQ.expand(*bshape, *RQ.shape[-2:])], dim=-1))
     Pc_hat = _mT(_qr_r(M)[..., :m, :m])
-    return a_f, a_hat, y_hat, Pcf, Pc_hat, Fc, ll
+    return a_f, a_hat, y_hat, Pcf, Pc_hat, Fc_out, ll
 
 
 _STEP = {"standard": standard_step, "univariate": univariate_step, "cholesky": sqrt_step}

@@ -220,6 +220,10 @@ extern "C" int bkf_set_stream(bkf_handle* h, void* s) {
 static int run_forward(bkf_handle* h, const KArgs<double>& g, const char** err) {
     KernelTimer kt(h, BKF_KERNEL_FORWARD);
     h->launches += 1;
+    if (g.kind == BKF_CHOLESKY) {
+        h->path = "sqrt_cta";
+        return sq::launch_forward<double>(g, h->stream, err);
+    }
     if (tps::supported(g.kind, g.m, g.p)) {
         h->path = "thread_f64";
         return tps::launch_any<double>(g, false, h->stream, err);
@@ -234,6 +238,10 @@ static int run_forward(bkf_handle* h, const KArgs<double>& g, const char** err) 
 static int run_forward(bkf_handle* h, const KArgs<float>& g, const char** err) {
     KernelTimer kt(h, BKF_KERNEL_FORWARD);
     h->launches += 1;
+    if (g.kind == BKF_CHOLESKY) {
+        h->path = "sqrt_cta";
+        return sq::launch_forward<float>(g, h->stream, err);
+    }
     if (tps::supported(g.kind, g.m, g.p)) {
         h->path = "thread_f32";
         return tps::launch_any<float>(g, false, h->stream, err);
@@ -244,6 +252,7 @@ static int run_forward(bkf_handle* h, const KArgs<float>& g, const char** err) {
 static int run_backward(bkf_handle* h, const KArgs<double>& g, const char** err) {
     KernelTimer kt(h, BKF_KERNEL_BACKWARD);
     h->launches += 1;
+    if (g.kind == BKF_CHOLESKY) return sq::launch_backward<double>(g, h->stream, err);
     if (tps::supported(g.kind, g.m, g.p)) return tps::launch_any<double>(g, true, h->stream, err);
     if (sw::supported(g.kind, g.m, g.p)) return sw::launch_f64(g, true, h->stream, err);
     return gen::launch_backward<double>(g, h->stream, err);
@@ -251,6 +260,7 @@ static int run_backward(bkf_handle* h, const KArgs<double>& g, const char** err)
 static int run_backward(bkf_handle* h, const KArgs<float>& g, const char** err) {
     KernelTimer kt(h, BKF_KERNEL_BACKWARD);
     h->launches += 1;
+    if (g.kind == BKF_CHOLESKY) return sq::launch_backward<float>(g, h->stream, err);
     if (tps::supported(g.kind, g.m, g.p)) return tps::launch_any<float>(g, true, h->stream, err);
     return gen::launch_backward<float>(g, h->stream, err);
 }

@@ -344,40 +344,6 @@ __device__ R uni_update(const KArgs<R>& g, Arena<R>& A, const R* yt, R* obs_mu, 
 }
 
 // ----------------------------------------------------------------------------------------------------
-// Householder QR (R factor only), LAPACK dgeqr2/dlarfg conventions, in place on A[rows, cols] row-major.
-// beta = -sign(alpha) * ||(alpha, x)||, H = I when x == 0 (tau = 0).   
-// ----------------------------------------------------------------------------------------------------
-template <typename R>
-__device__ void householder_r(R* A, int rows, int cols, int lane) {
-    const int kmax = rows < cols ? rows : cols;
-    for (int j = 0; j < kmax; ++j) {
-        R ss = 0;
-        for (int i = j + 1 + lane; i < rows; i += 32) ss = fma(A[i * cols + j], A[i * cols + j], ss);
-        ss = warp_sum(ss);
-        const R alpha = A[j * cols + j];
-        __syncwarp();
-        if (ss == R(0)) continue;  // tau = 0
-        const R nrm = sqrt(fma(alpha, alpha, ss));
-        const R beta = alpha >= R(0) ? -nrm : nrm;
-        const R tau = (beta - alpha) / beta;
-        const R scal = R(1) / (alpha - beta);
-        for (int i = j + 1 + lane; i < rows; i += 32) A[i * cols + j] *= scal;  // v (v_j = 1 implicit)
-        __syncwarp();
-        for (int cidx = j + 1 + lane; cidx < cols; cidx += 32) {
-            R s = A[j * cols + cidx];
-            for (int i = j + 1; i < rows; ++i) s = fma(A[i * cols + j], A[i * cols + cidx], s);
-            s *= tau;
-            A[j * cols + cidx] -= s;
-            for (int i = j + 1; i < rows; ++i) A[i * cols + cidx] = fma(-s, A[i * cols + j], A[i * cols + cidx]);
-        }
-        __syncwarp();
-        if (lane == 0) A[j * cols + j] = beta;
-        for (int i = j + 1 + lane; i < rows; i += 32) A[i * cols + j] = 0;
-        __syncwarp();
-    }
-}
-
-// ----------------------------------------------------------------------------------------------------
 // forward kernel: standard / univariate
 // ----------------------------------------------------------------------------------------------------
 template <typename R>
@@ -421,191 +387,6 @@ __global__ void forward_kernel(KArgs<R> g, int wpc, size_t arena) {
         if (g.ll && lane == 0) g.ll[bt] = ll;
         logp += ll;
         predict(A, m, lane);
-    }
-    if (!isfinite(logp)) st |= BKF_STATUS_NONFINITE;
-    if (lane == 0) {
-        if (g.logp) g.logp[b] = logp;
-        if (g.status) g.status[b] = st;
-    }
-}
-
-// ----------------------------------------------------------------------------------------------------
-// forward kernel: square-root filter (kalman_filter.py:629-750).  Arena: see sqrt_arena_elems.
-// ----------------------------------------------------------------------------------------------------
-__host__ __device__ inline size_t sqrt_arena_elems(int m, int p, int r) {
-    size_t n1 = (size_t)(p + m) * (p + m), n2 = (size_t)(m + r) * m;
-    size_t tot = /*T,Pc*/ 2 * (size_t)m * m + /*Z,Zm*/ 2 * (size_t)p * m + /*RQc*/ (size_t)m * r +
-                 /*Hc*/ (size_t)p * p + /*QR work*/ (n1 > n2 ? n1 : n2) + /*a,af,c*/ 3 * (size_t)m +
-                 /*d,w,ym,v,s*/ 5 * (size_t)p + /*Qc*/ (size_t)r * r;
-    return (tot + 1) & ~(size_t)1;
-}
-
-template <typename R>
-__global__ void sqrt_forward_kernel(KArgs<R> g, int wpc, size_t arena) {
-    extern __shared__ double smem_raw[];
-    R* s = reinterpret_cast<R*>(smem_raw);
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int b = blockIdx.x * wpc + warp;
-    if (b >= g.B) return;
-    const int m = g.m, p = g.p, r = g.r, n = g.n;
-    s += (size_t)warp * arena;
-    auto take = [&](size_t k) { R* q = s; s += k; return q; };
-    R *T = take((size_t)m * m), *Pc = take((size_t)m * m), *Z = take((size_t)p * m), *Zm = take((size_t)p * m),
-      *RQc = take((size_t)m * r), *Hc = take((size_t)p * p), *Qc = take((size_t)r * r), *a = take(m),
-      *af = take(m), *c = take(m), *d = take(p), *w = take(p), *ym = take(p), *v = take(p), *sv = take(p),
-      *W = s;
-    wcopy(T, param_ptr(g.T, g.shared_mask, BKF_PARAM_T, b, (size_t)m * m), m * m, lane);
-    wcopy(Z, param_ptr(g.Z, g.shared_mask, BKF_PARAM_Z, b, (size_t)p * m), p * m, lane);
-    wcopy(Hc, param_ptr(g.H, g.shared_mask, BKF_PARAM_H, b, (size_t)p * p), p * p, lane);
-    wcopy(Qc, param_ptr(g.Q, g.shared_mask, BKF_PARAM_Q, b, (size_t)r * r), r * r, lane);
-    wcopy(c, param_ptr(g.c, g.shared_mask, BKF_PARAM_C, b, (size_t)m), m, lane);
-    wcopy(d, param_ptr(g.d, g.shared_mask, BKF_PARAM_D, b, (size_t)p), p, lane);
-    wcopy(a, param_ptr(g.a0, g.shared_mask, BKF_PARAM_A0, b, (size_t)m), m, lane);
-    wcopy(Pc, param_ptr(g.P0, g.shared_mask, BKF_PARAM_P0, b, (size_t)m * m), m * m, lane);
-    int st = 0;
-    // H_chol = all(H == 0) ? H : cholesky(H)  (:666) -- time-invariant H, so hoisted out of the loop
-    bool Hzero = true;
-    for (int i = 0; i < p * p; ++i) Hzero = Hzero && (Hc[i] == R(0));
-    if (!Hzero) {
-        if (!chol_lower(Hc, p, lane)) st |= BKF_STATUS_NOT_PD;
-        for (int idx = lane; idx < p * p; idx += 32)
-            if ((idx % p) > (idx / p)) Hc[idx] = 0;
-    }
-    if (!chol_lower(Qc, r, lane)) st |= BKF_STATUS_NOT_PD;
-    for (int idx = lane; idx < r * r; idx += 32)
-        if ((idx % r) > (idx / r)) Qc[idx] = 0;
-    __syncwarp();
-    const R* Rg = param_ptr(g.Rm, g.shared_mask, BKF_PARAM_R, b, (size_t)m * r);
-    mm<SET>(RQc, Rg, r, 1, Qc, r, 1, m, r, r, lane);
-
-    const R* yb = g.y_shared ? g.y : g.y + (size_t)b * n * p;
-    const int N1 = p + m;
-    R logp = 0;
-    auto write_sq = [&](R* dst, const R* L, int k) {  // dst = L L^T  (:733-740)
-        for (int idx = lane; idx < k * k; idx += 32) {
-            int i = idx / k, j = idx - i * k;
-            R acc = 0;
-            for (int q = 0; q < k; ++q) acc = fma(L[i * k + q], L[j * k + q], acc);
-            dst[idx] = acc;
-        }
-    };
-    for (int t = 0; t < n; ++t) {
-        const size_t bt = (size_t)b * n + t;
-        if (g.pred_a) wcopy(g.pred_a + bt * m, a, m, lane);
-        if (g.pred_P) write_sq(g.pred_P + bt * m * m, Pc, m);
-        const R* yt = yb + (size_t)t * p;
-        for (int o = lane; o < p; o += 32) {
-            R yv = yt[o];
-            bool miss = is_missing(yv, g.fill, true);
-            w[o] = miss ? R(0) : R(1);
-            ym[o] = miss ? R(0) : yv;
-        }
-        __syncwarp();
-        R nobs = 0;
-        for (int o = 0; o < p; ++o) nobs += w[o];
-        const bool flag = (nobs == R(0));
-        const bool partial = !flag && (nobs != R(p));
-        for (int idx = lane; idx < p * m; idx += 32) Zm[idx] = w[idx / m] * Z[idx];
-        __syncwarp();
-        for (int o = lane; o < p; o += 32) {
-            R acc = 0;
-            for (int j = 0; j < m; ++j) acc = fma(Zm[o * m + j], a[j], acc);
-            R yh = acc + d[o];
-            v[o] = ym[o] - yh;
-            if (g.obs_mu) g.obs_mu[bt * p + o] = yh;
-        }
-        // W = A_T^T with A_T = [[Hc, Zm Pc], [0, Pc]]  ->  W = [[Hc^T, 0], [(Zm Pc)^T, Pc^T]]   (:675-679)
-        for (int idx = lane; idx < N1 * N1; idx += 32) {
-            int i = idx / N1, j = idx - i * N1;
-            R val;
-            if (i < p) {
-                // masked H: all observed -> chol(H); all missing -> H_masked == 0 -> 0; partially missing ->
-                // cholesky(W H) fails in the reference (not PD): propagate NaN
-                val = (j < p) ? ((flag || Hzero) ? R(0) : (partial ? R(NAN) : Hc[j * p + i])) : R(0);
-            } else if (j < p) {
-                R acc = 0;
-                for (int q = 0; q < m; ++q) acc = fma(Zm[j * m + q], Pc[q * m + (i - p)], acc);
-                val = acc;
-            } else {
-                val = Pc[(j - p) * m + (i - p)];
-            }
-            W[idx] = val;
-        }
-        __syncwarp();
-        householder_r(W, N1, N1, lane);
-        // B = W^T: F_chol = B[:p,:p], K_F_chol = B[p:,:p], P_chol_filtered = B[p:,p:]
-        if (g.obs_cov) {
-            for (int idx = lane; idx < p * p; idx += 32) {
-                int i = idx / p, j = idx - i * p;
-                R acc = 0;  // F_chol F_chol^T, F_chol[i,q] = W[q,i]
-                for (int q = 0; q < p; ++q) acc = fma(W[q * N1 + i], W[q * N1 + j], acc);
-                g.obs_cov[bt * p * p + idx] = acc;
-            }
-        }
-        R ll = 0;
-        if (!flag) {
-            // s = solve_tri(F_chol, v, lower); inner = solve_tri(F_chol, s, lower)   (:686-691, quirk Q3)
-            R quad = 0, logdet = 0;
-            if (lane == 0) {
-                for (int i = 0; i < p; ++i) {
-                    R tt = v[i];
-                    for (int q = 0; q < i; ++q) tt -= W[q * N1 + i] * sv[q];
-                    sv[i] = tt / W[i * N1 + i];
-                }
-                for (int i = 0; i < p; ++i) {  // second lower solve into ym (scratch)
-                    R tt = sv[i];
-                    for (int q = 0; q < i; ++q) tt -= W[q * N1 + i] * ym[q];
-                    ym[i] = tt / W[i * N1 + i];
-                }
-            }
-            __syncwarp();
-            for (int o = 0; o < p; ++o) {
-                quad = fma(v[o], ym[o], quad);
-                logdet += log(fabs(W[o * N1 + o]));
-            }
-            logdet *= R(2);
-            ll = R(-0.5) * (R(p) * (R(kLog2Pi) + logdet) + quad);  // (:696, quirk Q2)
-            for (int i = lane; i < m; i += 32) {
-                R acc = 0;
-                for (int o = 0; o < p; ++o) acc = fma(W[o * N1 + (p + i)], sv[o], acc);
-                af[i] = a[i] + acc;
-            }
-            __syncwarp();
-            for (int idx = lane; idx < m * m; idx += 32) {
-                int i = idx / m, j = idx - i * m;
-                Pc[idx] = W[(p + j) * N1 + (p + i)] + (i == j ? g.jitter : R(0));  // jitter on the factor (Q4)
-            }
-        } else {
-            wcopy(af, a, m, lane);
-            for (int i = lane; i < m; i += 32) Pc[i * m + i] += g.jitter;
-        }
-        __syncwarp();
-        if (g.filt_a) wcopy(g.filt_a + bt * m, af, m, lane);
-        if (g.filt_P) write_sq(g.filt_P + bt * m * m, Pc, m);
-        if (g.ll && lane == 0) g.ll[bt] = ll;
-        logp += ll;
-        // predict: M = [T Pc, R Qc]^T  ((m+r) x m) ; Pc+ = qr_r(M)[:m,:m]^T   (:639-648)
-        for (int idx = lane; idx < (m + r) * m; idx += 32) {
-            int i = idx / m, j = idx - i * m;
-            R val;
-            if (i < m) {
-                R acc = 0;
-                for (int q = 0; q < m; ++q) acc = fma(T[j * m + q], Pc[q * m + i], acc);
-                val = acc;
-            } else {
-                val = RQc[j * r + (i - m)];
-            }
-            W[idx] = val;
-        }
-        mv<SET>(a, T, m, 1, af, m, m, lane);
-        for (int i = lane; i < m; i += 32) a[i] += c[i];
-        __syncwarp();
-        householder_r(W, m + r, m, lane);
-        for (int idx = lane; idx < m * m; idx += 32) {
-            int i = idx / m, j = idx - i * m;
-            Pc[idx] = W[j * m + i];
-        }
-        __syncwarp();
     }
     if (!isfinite(logp)) st |= BKF_STATUS_NONFINITE;
     if (lane == 0) {
@@ -963,17 +744,11 @@ static int launch_warp_kernel(KernelT kern, const KArgs<R>& g, size_t arena, cud
 
 template <typename R>
 int launch_forward(const KArgs<R>& g, cudaStream_t stream, const char** err) {
-    if (g.kind == BKF_CHOLESKY)
-        return launch_warp_kernel<R>(sqrt_forward_kernel<R>, g, sqrt_arena_elems(g.m, g.p, g.r), stream, err);
     return launch_warp_kernel<R>(forward_kernel<R>, g, arena_elems(g.m, g.p, g.r, false), stream, err);
 }
 
 template <typename R>
 int launch_backward(const KArgs<R>& g, cudaStream_t stream, const char** err) {
-    if (g.kind == BKF_CHOLESKY) {
-        *err = "gradient of the square-root filter is not implemented yet";
-        return BKF_ERR_UNSUPPORTED;
-    }
     return launch_warp_kernel<R>(backward_kernel<R>, g, arena_elems(g.m, g.p, g.r, true), stream, err);
 }
 

@@ -10,6 +10,10 @@ template <typename R> int launch_forward(const KArgs<R>& g, cudaStream_t stream,
 template <typename R> int launch_backward(const KArgs<R>& g, cudaStream_t stream, const char** err);
 template <typename R> int launch_smoother(const KArgs<R>& g, cudaStream_t stream, const char** err);
 }  // namespace gen
+namespace sq {  // square-root filter, CTA per series (bkf_sqrt.cu)
+template <typename R> int launch_forward(const KArgs<R>& g, cudaStream_t stream, const char** err);
+template <typename R> int launch_backward(const KArgs<R>& g, cudaStream_t stream, const char** err);
+}  // namespace sq
 namespace sw {  // register-tiled sub-warp-per-series kernels, float64, p = 1 (bkf_subwarp.cu)
 bool supported(int kind, int m, int p);
 int launch_f64(const KArgs<double>& g, bool backward, cudaStream_t stream, const char** err);

@@ -1,0 +1,607 @@
+// bkf_sqrt.cu -- SquareRootFilter (kalman_filter.py:620-750): forward and reverse-mode adjoint, one CTA per series.
+//
+// Forward (per step): update via the R factor of the (p+m)x(p+m) matrix A = [[Hc^T, 0], [(Zm Pc)^T, Pc^T]]
+// (kalman_filter.py:675-683), predict via the R factor of M = [T Pcf, R Qc]^T (:644-646).  Householder QR follows
+// LAPACK dgeqr2/dlarfg (beta = -sign(alpha) ||x||, H = I for a zero sub-column) so that the signs of the factors --
+// which the reference's log-likelihood depends on for p > 1 -- match numpy.linalg.qr.
+//
+// Adjoint: for A = Q Rf and an upper-triangular cotangent Rbar,  Abar = A Psi,
+//     Psi = Rf^{-1} copyltu(Rf Rbar^T) Rf^{-T},   copyltu(X) = tril(X) + tril(X,-1)^T
+// (the Q-free form of the standard QR pull-back; it is what autograd through the reference's code yields).
+// cholesky(H), cholesky(Q) are time-invariant: their factor cotangents are summed over t and pulled back once per
+// series with the lower-triangular convention of PyTensor's Cholesky.L_op (tril(S + S^T) - diag(S)).
+// Validated against torch autograd through the reference source (tests/golden, oracle/kalman_torch.py).
+#include "bkf_common.cuh"
+#include "bkf_launch.h"
+
+namespace bkf {
+namespace sq {
+
+enum { SET = 0, ADD = 1, SUB = 2 };
+
+struct Th {
+    int tid, nt;
+};
+
+template <int MODE, typename R>
+__device__ __forceinline__ void mm(R* __restrict__ C, int ldc, const R* __restrict__ A, int as0, int as1,
+                                   const R* __restrict__ Bm, int bs0, int bs1, int M, int N, int K, Th th) {
+    for (int idx = th.tid; idx < M * N; idx += th.nt) {
+        int i = idx / N, j = idx - i * N;
+        const R* a = A + i * as0;
+        const R* b = Bm + j * bs1;
+        R acc = 0;
+        for (int k = 0; k < K; ++k) acc = fma(a[k * as1], b[k * bs0], acc);
+        R* c = C + i * ldc + j;
+        if (MODE == SET) *c = acc;
+        else if (MODE == ADD) *c += acc;
+        else *c -= acc;
+    }
+    __syncthreads();
+}
+
+template <typename R>
+__device__ __forceinline__ void bcopy(R* dst, const R* src, int n, Th th) {
+    for (int i = th.tid; i < n; i += th.nt) dst[i] = src[i];
+    __syncthreads();
+}
+template <typename R>
+__device__ __forceinline__ void bzero(R* dst, int n, Th th) {
+    for (int i = th.tid; i < n; i += th.nt) dst[i] = 0;
+    __syncthreads();
+}
+
+template <typename R>
+__device__ __forceinline__ R block_sum(R v, R* red, Th th) {
+    v = warp_sum(v);
+    if ((th.tid & 31) == 0) red[th.tid >> 5] = v;
+    __syncthreads();
+    R s = 0;
+    for (int w = 0; w < (th.nt + 31) / 32; ++w) s += red[w];
+    __syncthreads();
+    return s;
+}
+
+// In-place R factor of W[rows, cols] (row-major, ld = cols); entries below the diagonal are zeroed.
+template <typename R>
+__device__ void householder_r(R* W, int rows, int cols, R* red, Th th) {
+    const int kmax = rows < cols ? rows : cols;
+    for (int j = 0; j < kmax; ++j) {
+        R ss = 0;
+        for (int i = j + 1 + th.tid; i < rows; i += th.nt) ss = fma(W[i * cols + j], W[i * cols + j], ss);
+        ss = block_sum(ss, red, th);
+        const R alpha = W[j * cols + j];
+        __syncthreads();
+        if (ss == R(0)) continue;  // dlarfg: tau = 0, H = I
+        const R nrm = sqrt(fma(alpha, alpha, ss));
+        const R beta = alpha >= R(0) ? -nrm : nrm;
+        const R tau = (beta - alpha) / beta;
+        const R scal = R(1) / (alpha - beta);
+        for (int i = j + 1 + th.tid; i < rows; i += th.nt) W[i * cols + j] *= scal;
+        __syncthreads();
+        for (int c = j + 1 + th.tid; c < cols; c += th.nt) {
+            R s = W[j * cols + c];
+            for (int i = j + 1; i < rows; ++i) s = fma(W[i * cols + j], W[i * cols + c], s);
+            s *= tau;
+            W[j * cols + c] -= s;
+            for (int i = j + 1; i < rows; ++i) W[i * cols + c] = fma(-s, W[i * cols + j], W[i * cols + c]);
+        }
+        __syncthreads();
+        if (th.tid == 0) W[j * cols + j] = beta;
+        for (int i = j + 1 + th.tid; i < rows; i += th.nt) W[i * cols + j] = 0;
+        __syncthreads();
+    }
+}
+
+// X <- U^{-1} X for upper-triangular U[n,n] (ld = ldu); X element (i, c) at X[i*xs0 + c*xs1], ncols columns.
+template <typename R>
+__device__ void solve_upper(const R* U, int ldu, int n, R* X, int xs0, int xs1, int ncols, Th th) {
+    for (int c = th.tid; c < ncols; c += th.nt) {
+        for (int i = n - 1; i >= 0; --i) {
+            R t = X[i * xs0 + c * xs1];
+            for (int q = i + 1; q < n; ++q) t = fma(-U[i * ldu + q], X[q * xs0 + c * xs1], t);
+            X[i * xs0 + c * xs1] = t / U[i * ldu + i];
+        }
+    }
+    __syncthreads();
+}
+
+// Psi = U^{-1} copyltu(U Rbar^T) U^{-T}  (n x n, symmetric), with Rbar(i,j) = Rb[i*rs0 + j*rs1] for i <= j, 0 below.
+// tmp: n*n scratch.
+template <typename R>
+__device__ void qr_pullback_psi(R* Psi, const R* U, int ldu, int n, const R* Rb, int rs0, int rs1, R* tmp, Th th) {
+    // tmp = U Rbar^T : tmp[i,j] = sum_{k >= max(i,j)} U[i,k] Rbar[j,k]
+    for (int idx = th.tid; idx < n * n; idx += th.nt) {
+        int i = idx / n, j = idx - i * n;
+        R acc = 0;
+        for (int k = (i > j ? i : j); k < n; ++k) acc = fma(U[i * ldu + k], Rb[j * rs0 + k * rs1], acc);
+        tmp[idx] = acc;
+    }
+    __syncthreads();
+    for (int idx = th.tid; idx < n * n; idx += th.nt) {
+        int i = idx / n, j = idx - i * n;
+        Psi[idx] = (i >= j) ? tmp[idx] : tmp[j * n + i];
+    }
+    __syncthreads();
+    solve_upper(U, ldu, n, Psi, n, 1, n, th);  // X = U^{-1} Sym
+    solve_upper(U, ldu, n, Psi, 1, n, n, th);  // Psi = U^{-1} X^T  (in place on the transposed view; symmetric)
+}
+
+// In-place lower Cholesky by thread 0 (tiny p x p / r x r, once per series).
+template <typename R>
+__device__ bool chol_lower(R* A, int k, Th th) {
+    __shared__ int ok_s;
+    if (th.tid == 0) {
+        int ok = 1;
+        for (int j = 0; j < k; ++j) {
+            R s = A[j * k + j];
+            for (int q = 0; q < j; ++q) s -= A[j * k + q] * A[j * k + q];
+            if (!(s > 0)) { ok = 0; s = R(NAN); }
+            R ljj = sqrt(s);
+            A[j * k + j] = ljj;
+            for (int i = j + 1; i < k; ++i) {
+                R t = A[i * k + j];
+                for (int q = 0; q < j; ++q) t -= A[i * k + q] * A[j * k + q];
+                A[i * k + j] = t / ljj;
+            }
+            for (int i = 0; i < j; ++i) A[i * k + j] = 0;
+        }
+        ok_s = ok;
+    }
+    __syncthreads();
+    return ok_s != 0;
+}
+
+// Pull a lower-triangular factor cotangent Lbar back through S = L L^T, PyTensor lower convention, by thread 0.
+// Sbar = tril(2 X) - diag(X),  X = 0.5 L^{-T} (P + P^T) L^{-1},  P = Phi(L^T Lbar).  out may alias nothing; tmp: 2*k*k.
+template <typename R>
+__device__ void chol_pullback(R* out, const R* L, const R* Lbar, int k, R* tmp, Th th) {
+    if (th.tid == 0) {
+        R* P = tmp;
+        R* X = tmp + k * k;
+        for (int i = 0; i < k; ++i)
+            for (int j = 0; j < k; ++j) {
+                R acc = 0;  // (L^T Lbar)[i,j] = sum_q L[q,i] Lbar[q,j], Lbar lower
+                for (int q = (i > j ? i : j); q < k; ++q) acc = fma(L[q * k + i], Lbar[q * k + j], acc);
+                P[i * k + j] = (i > j) ? acc : (i == j ? R(0.5) * acc : R(0));
+            }
+        for (int i = 0; i < k; ++i)
+            for (int j = 0; j < k; ++j) X[i * k + j] = P[i * k + j] + P[j * k + i];
+        // X <- L^{-T} X : solve L^T Y = X column by column (upper-triangular system)
+        for (int c = 0; c < k; ++c)
+            for (int i = k - 1; i >= 0; --i) {
+                R t = X[i * k + c];
+                for (int q = i + 1; q < k; ++q) t -= L[q * k + i] * X[q * k + c];
+                X[i * k + c] = t / L[i * k + i];
+            }
+        // X <- X L^{-1} : solve Y L = X row by row
+        for (int rw = 0; rw < k; ++rw)
+            for (int j = k - 1; j >= 0; --j) {
+                R t = X[rw * k + j];
+                for (int q = j + 1; q < k; ++q) t -= X[rw * k + q] * L[q * k + j];
+                X[rw * k + j] = t / L[j * k + j];
+            }
+        for (int i = 0; i < k; ++i)
+            for (int j = 0; j < k; ++j) {
+                const R s = R(0.5) * X[i * k + j];
+                out[i * k + j] = (i > j) ? R(2) * s : (i == j ? s : R(0));
+            }
+    }
+    __syncthreads();
+}
+
+// ----------------------------------------------------------------------------------------------------
+template <typename R>
+struct Arena {
+    R *T, *Z, *Hc, *Qc, *RQc, *c, *d;        // parameters (factors hoisted: H, Q are time-invariant)
+    R *a, *Pc;                               // carried prediction (factor)
+    R *Zm, *w, *ym, *v, *sv, *inner, *af, *Pcf;
+    R *A0, *Rf, *M0, *Rp;                    // update / predict QR inputs and factors
+    R *red;                                  // block reduction scratch (32)
+    // backward only
+    R *abar, *Pbar, *S1, *Psi, *Abar, *gT, *gZ, *gc, *gd, *Psum, *Hcbar, *afbar, *Pcfbar, *U1, *vbar, *sbar, *t1;
+};
+
+__host__ __device__ inline size_t arena_elems(int m, int p, int r, bool bwd) {
+    size_t mm_ = (size_t)m * m, pm = (size_t)p * m, pp = (size_t)p * p, rr = (size_t)r * r, mr = (size_t)m * r;
+    size_t n1 = (size_t)(p + m) * (p + m), n2 = (size_t)(m + r) * m;
+    size_t fwd = /*T,Pc,Pcf*/ 3 * mm_ + /*Z,Zm*/ 2 * pm + pp + rr + mr + /*c,a,af*/ 3 * (size_t)m +
+                 /*d,w,ym,v,sv,inner*/ 6 * (size_t)p + /*A0,Rf*/ 2 * n1 + /*M0,Rp*/ 2 * n2 + 32;
+    size_t bw = /*Pbar,gT,Psum,Pcfbar,U1*/ 5 * mm_ + /*S1,Psi,Abar*/ 3 * n1 + pm + /*abar,gc,afbar*/ 3 * (size_t)m +
+                /*gd,vbar,sbar,t1*/ 4 * (size_t)p + pp;
+    size_t tot = fwd + (bwd ? bw : 0);
+    return (tot + 1) & ~(size_t)1;
+}
+
+template <typename R>
+__device__ void carve(Arena<R>& A, R* s, int m, int p, int r, bool bwd) {
+    size_t mm_ = (size_t)m * m, pm = (size_t)p * m, pp = (size_t)p * p, rr = (size_t)r * r, mr = (size_t)m * r;
+    size_t n1 = (size_t)(p + m) * (p + m), n2 = (size_t)(m + r) * m;
+    auto take = [&](size_t n) { R* q = s; s += n; return q; };
+    A.T = take(mm_); A.Pc = take(mm_); A.Pcf = take(mm_); A.Z = take(pm); A.Zm = take(pm); A.Hc = take(pp);
+    A.Qc = take(rr); A.RQc = take(mr); A.c = take(m); A.a = take(m); A.af = take(m);
+    A.d = take(p); A.w = take(p); A.ym = take(p); A.v = take(p); A.sv = take(p); A.inner = take(p);
+    A.A0 = take(n1); A.Rf = take(n1); A.M0 = take(n2); A.Rp = take(n2); A.red = take(32);
+    if (bwd) {
+        A.Pbar = take(mm_); A.gT = take(mm_); A.Psum = take(mm_); A.Pcfbar = take(mm_); A.U1 = take(mm_);
+        A.S1 = take(n1); A.Psi = take(n1); A.Abar = take(n1); A.gZ = take(pm);
+        A.abar = take(m); A.gc = take(m); A.afbar = take(m);
+        A.gd = take(p); A.vbar = take(p); A.sbar = take(p); A.t1 = take(p); A.Hcbar = take(pp);
+    }
+}
+
+// Per-series setup shared by forward and backward.  Returns status bits; *Hzero_out = all(H == 0) (:666).
+template <typename R>
+__device__ int setup(const KArgs<R>& g, Arena<R>& A, int b, bool* Hzero_out, Th th) {
+    const int m = g.m, p = g.p, r = g.r;
+    bcopy(A.T, param_ptr(g.T, g.shared_mask, BKF_PARAM_T, b, (size_t)m * m), m * m, th);
+    bcopy(A.Z, param_ptr(g.Z, g.shared_mask, BKF_PARAM_Z, b, (size_t)p * m), p * m, th);
+    bcopy(A.Hc, param_ptr(g.H, g.shared_mask, BKF_PARAM_H, b, (size_t)p * p), p * p, th);
+    bcopy(A.Qc, param_ptr(g.Q, g.shared_mask, BKF_PARAM_Q, b, (size_t)r * r), r * r, th);
+    bcopy(A.c, param_ptr(g.c, g.shared_mask, BKF_PARAM_C, b, (size_t)m), m, th);
+    bcopy(A.d, param_ptr(g.d, g.shared_mask, BKF_PARAM_D, b, (size_t)p), p, th);
+    int st = 0;
+    bool Hzero = true;
+    for (int i = 0; i < p * p; ++i) Hzero = Hzero && (A.Hc[i] == R(0));
+    __syncthreads();
+    if (!Hzero && !chol_lower(A.Hc, p, th)) st |= BKF_STATUS_NOT_PD;
+    if (!chol_lower(A.Qc, r, th)) st |= BKF_STATUS_NOT_PD;
+    const R* Rg = param_ptr(g.Rm, g.shared_mask, BKF_PARAM_R, b, (size_t)m * r);
+    mm<SET>(A.RQc, r, Rg, r, 1, A.Qc, r, 1, m, r, r, th);
+    *Hzero_out = Hzero;
+    return st;
+}
+
+// One forward step from (A.a, A.Pc) and y_t.  Leaves A0 (QR input), Rf (its R factor), v, sv, inner, af, Pcf,
+// M0, Rp in the arena and returns ll.  flag = all observations missing; partial = some (the reference's
+// cholesky(W H) fails there: NaN is propagated).
+template <typename R>
+__device__ R step(const KArgs<R>& g, Arena<R>& A, const R* yt, bool Hzero, bool* flag_out, Th th) {
+    const int m = g.m, p = g.p, r = g.r, N1 = p + m;
+    for (int o = th.tid; o < p; o += th.nt) {
+        R yv = yt[o];
+        bool miss = is_missing(yv, g.fill, true);
+        A.w[o] = miss ? R(0) : R(1);
+        A.ym[o] = miss ? R(0) : yv;
+    }
+    __syncthreads();
+    R nobs = 0;
+    for (int o = 0; o < p; ++o) nobs += A.w[o];
+    const bool flag = (nobs == R(0));
+    const bool partial = !flag && (nobs != R(p));
+    for (int idx = th.tid; idx < p * m; idx += th.nt) A.Zm[idx] = A.w[idx / m] * A.Z[idx];
+    __syncthreads();
+    for (int o = th.tid; o < p; o += th.nt) {
+        R acc = 0;
+        for (int j = 0; j < m; ++j) acc = fma(A.Zm[o * m + j], A.a[j], acc);
+        A.sv[o] = acc + A.d[o];  // y_hat (kept in sv until the solves overwrite it)
+        A.v[o] = A.ym[o] - (acc + A.d[o]);
+    }
+    for (int idx = th.tid; idx < N1 * N1; idx += th.nt) {
+        int i = idx / N1, j = idx - i * N1;
+        R val;
+        if (i < p) {
+            val = (j < p) ? ((flag || Hzero) ? R(0) : (partial ? R(NAN) : A.Hc[j * p + i])) : R(0);
+        } else if (j < p) {
+            R acc = 0;
+            for (int q = 0; q < m; ++q) acc = fma(A.Zm[j * m + q], A.Pc[q * m + (i - p)], acc);
+            val = acc;
+        } else {
+            val = A.Pc[(j - p) * m + (i - p)];
+        }
+        A.A0[idx] = val;
+        A.Rf[idx] = val;
+    }
+    __syncthreads();
+    householder_r(A.Rf, N1, N1, A.red, th);
+    *flag_out = flag;
+    return R(0);
+}
+
+template <typename R>
+__device__ R finish_update(const KArgs<R>& g, Arena<R>& A, bool flag, Th th) {
+    const int m = g.m, p = g.p, N1 = p + m;
+    R ll = 0;
+    if (!flag) {
+        if (th.tid == 0) {  // s = Fc^{-1} v ; inner = Fc^{-1} s   with Fc[i,q] = Rf[q,i]   (:686-691)
+            for (int i = 0; i < p; ++i) {
+                R tt = A.v[i];
+                for (int q = 0; q < i; ++q) tt -= A.Rf[q * N1 + i] * A.sv[q];
+                A.sv[i] = tt / A.Rf[i * N1 + i];
+            }
+            for (int i = 0; i < p; ++i) {
+                R tt = A.sv[i];
+                for (int q = 0; q < i; ++q) tt -= A.Rf[q * N1 + i] * A.inner[q];
+                A.inner[i] = tt / A.Rf[i * N1 + i];
+            }
+        }
+        __syncthreads();
+        R quad = 0, logdet = 0;
+        for (int o = 0; o < p; ++o) {
+            quad = fma(A.v[o], A.inner[o], quad);
+            logdet += log(fabs(A.Rf[o * N1 + o]));
+        }
+        ll = R(-0.5) * (R(p) * (R(kLog2Pi) + R(2) * logdet) + quad);  // :696 (quirk Q2)
+        for (int i = th.tid; i < m; i += th.nt) {
+            R acc = 0;
+            for (int o = 0; o < p; ++o) acc = fma(A.Rf[o * N1 + (p + i)], A.sv[o], acc);
+            A.af[i] = A.a[i] + acc;
+        }
+        for (int idx = th.tid; idx < m * m; idx += th.nt) {
+            int i = idx / m, j = idx - i * m;
+            A.Pcf[idx] = A.Rf[(p + j) * N1 + (p + i)] + (i == j ? g.jitter : R(0));  // jitter on the factor (Q4)
+        }
+    } else {
+        for (int i = th.tid; i < m; i += th.nt) A.af[i] = A.a[i];
+        for (int idx = th.tid; idx < m * m; idx += th.nt) A.Pcf[idx] = A.Pc[idx] + ((idx / m) == (idx % m) ? g.jitter : R(0));
+    }
+    __syncthreads();
+    return ll;
+}
+
+// predict: M0 = [T Pcf, R Qc]^T ((m+r) x m), Rp = its R factor; next (a, Pc) written to (a_next, Pc_next).
+template <typename R>
+__device__ void predict(const KArgs<R>& g, Arena<R>& A, R* a_next, R* Pc_next, Th th) {
+    const int m = g.m, r = g.r;
+    for (int idx = th.tid; idx < (m + r) * m; idx += th.nt) {
+        int i = idx / m, j = idx - i * m;
+        R val;
+        if (i < m) {
+            R acc = 0;
+            for (int q = 0; q < m; ++q) acc = fma(A.T[j * m + q], A.Pcf[q * m + i], acc);
+            val = acc;
+        } else {
+            val = A.RQc[j * r + (i - m)];
+        }
+        A.M0[idx] = val;
+        A.Rp[idx] = val;
+    }
+    __syncthreads();
+    householder_r(A.Rp, m + r, m, A.red, th);
+    if (a_next) {
+        for (int i = th.tid; i < m; i += th.nt) {
+            R acc = 0;
+            for (int q = 0; q < m; ++q) acc = fma(A.T[i * m + q], A.af[q], acc);
+            a_next[i] = acc + A.c[i];
+        }
+    }
+    if (Pc_next)
+        for (int idx = th.tid; idx < m * m; idx += th.nt) Pc_next[idx] = A.Rp[(idx % m) * m + idx / m];
+    __syncthreads();
+}
+
+template <typename R>
+__global__ void forward_kernel(KArgs<R> g) {
+    extern __shared__ double smem_raw[];
+    R* smem = reinterpret_cast<R*>(smem_raw);
+    const Th th{(int)threadIdx.x, (int)blockDim.x};
+    const int b = blockIdx.x;
+    const int m = g.m, p = g.p, n = g.n, N1 = p + m;
+    Arena<R> A;
+    carve(A, smem, m, p, g.r, false);
+    bool Hzero;
+    int st = setup(g, A, b, &Hzero, th);
+    bcopy(A.a, param_ptr(g.a0, g.shared_mask, BKF_PARAM_A0, b, (size_t)m), m, th);
+    bcopy(A.Pc, param_ptr(g.P0, g.shared_mask, BKF_PARAM_P0, b, (size_t)m * m), m * m, th);
+    const R* yb = g.y_shared ? g.y : g.y + (size_t)b * n * p;
+    const size_t tstride = (size_t)m + (size_t)m * m;
+    auto write_sq = [&](R* dst, const R* L, int k, int ls0, int ls1) {  // dst = L L^T with L(i,q) = L[i*ls0 + q*ls1]
+        for (int idx = th.tid; idx < k * k; idx += th.nt) {
+            int i = idx / k, j = idx - i * k;
+            R acc = 0;
+            for (int q = 0; q < k; ++q) acc = fma(L[i * ls0 + q * ls1], L[j * ls0 + q * ls1], acc);
+            dst[idx] = acc;
+        }
+    };
+    R logp = 0;
+    for (int t = 0; t < n; ++t) {
+        const size_t bt = (size_t)b * n + t;
+        if (g.traj) {
+            bcopy(g.traj + bt * tstride, A.a, m, th);
+            bcopy(g.traj + bt * tstride + m, A.Pc, m * m, th);
+        }
+        if (g.pred_a) bcopy(g.pred_a + bt * m, A.a, m, th);
+        if (g.pred_P) write_sq(g.pred_P + bt * m * m, A.Pc, m, m, 1);
+        bool flag;
+        step(g, A, yb + (size_t)t * p, Hzero, &flag, th);
+        if (g.obs_mu) bcopy(g.obs_mu + bt * p, A.sv, p, th);
+        if (g.obs_cov) write_sq(g.obs_cov + bt * p * p, A.Rf, p, 1, N1);  // F_chol[i,q] = Rf[q,i]
+        __syncthreads();
+        const R ll = finish_update(g, A, flag, th);
+        if (g.filt_a) bcopy(g.filt_a + bt * m, A.af, m, th);
+        if (g.filt_P) write_sq(g.filt_P + bt * m * m, A.Pcf, m, m, 1);
+        if (g.ll && th.tid == 0) g.ll[bt] = ll;
+        logp += ll;
+        predict(g, A, A.a, A.Pc, th);
+    }
+    if (!isfinite(logp)) st |= BKF_STATUS_NONFINITE;
+    if (th.tid == 0) {
+        if (g.logp) g.logp[b] = logp;
+        if (g.status) g.status[b] = st;
+    }
+}
+
+template <typename R>
+__global__ void backward_kernel(KArgs<R> g) {
+    extern __shared__ double smem_raw[];
+    R* smem = reinterpret_cast<R*>(smem_raw);
+    const Th th{(int)threadIdx.x, (int)blockDim.x};
+    const int b = blockIdx.x;
+    const int m = g.m, p = g.p, r = g.r, n = g.n, N1 = p + m;
+    Arena<R> A;
+    carve(A, smem, m, p, r, true);
+    bool Hzero;
+    setup(g, A, b, &Hzero, th);
+    bzero(A.abar, m, th); bzero(A.Pbar, m * m, th); bzero(A.gT, m * m, th); bzero(A.Psum, m * m, th);
+    bzero(A.gZ, p * m, th); bzero(A.gc, m, th); bzero(A.gd, p, th); bzero(A.Hcbar, p * p, th);
+    const R* yb = g.y_shared ? g.y : g.y + (size_t)b * n * p;
+    const size_t tstride = (size_t)m + (size_t)m * m;
+    for (int t = n - 1; t >= 0; --t) {
+        const size_t bt = (size_t)b * n + t;
+        const R gcot = g.ll_cot ? g.ll_cot[bt] : R(1);
+        bcopy(A.a, g.traj + bt * tstride, m, th);
+        bcopy(A.Pc, g.traj + bt * tstride + m, m * m, th);
+        bool flag;
+        step(g, A, yb + (size_t)t * p, Hzero, &flag, th);
+        finish_update(g, A, flag, th);
+        predict(g, A, (R*)nullptr, (R*)nullptr, th);
+        // ================= predict adjoint =================
+        // Rp_bar = triu(Pbar^T): Rbar(i,j) = Pbar[j*m + i]  ->  strides (rs0, rs1) = (1, m)
+        qr_pullback_psi(A.Psi, A.Rp, m, m, A.Pbar, 1, m, A.S1, th);
+        for (int idx = th.tid; idx < m * m; idx += th.nt) A.Psum[idx] += A.Psi[idx];
+        // U1 = Psi (T Pcf), (T Pcf)[k,j] = M0[j*m + k]
+        mm<SET>(A.U1, m, A.Psi, m, 1, A.M0, 1, m, m, m, m, th);
+        // gT += U1 Pcf^T + abar af^T
+        mm<ADD>(A.gT, m, A.U1, m, 1, A.Pcf, 1, m, m, m, m, th);
+        for (int idx = th.tid; idx < m * m; idx += th.nt) A.gT[idx] = fma(A.abar[idx / m], A.af[idx % m], A.gT[idx]);
+        // Pcfbar = T^T U1 ; afbar = T^T abar ; gc += abar
+        mm<SET>(A.Pcfbar, m, A.T, 1, m, A.U1, m, 1, m, m, m, th);
+        for (int i = th.tid; i < m; i += th.nt) {
+            R acc = 0;
+            for (int q = 0; q < m; ++q) acc = fma(A.T[q * m + i], A.abar[q], acc);
+            A.afbar[i] = acc;
+            A.gc[i] += A.abar[i];
+        }
+        __syncthreads();
+        if (flag) {  // degenerate branch (:700-705): (a_f, Pcf0, ll) = (a, Pc, 0)
+            bcopy(A.abar, A.afbar, m, th);
+            bcopy(A.Pbar, A.Pcfbar, m * m, th);
+            continue;
+        }
+        // ================= update adjoint =================
+        // sbar = KF^T afbar, KF[i,o] = Rf[o, p+i];  loss/logdet cotangents;  the two lower solves with Fc = Rf[:p,:p]^T
+        if (th.tid == 0) {
+            const R lossbar = R(-0.5) * gcot, logdetbar = R(-0.5) * gcot * R(p);
+            for (int o = 0; o < p; ++o) {
+                R acc = 0;
+                for (int i = 0; i < m; ++i) acc = fma(A.Rf[o * N1 + (p + i)], A.afbar[i], acc);
+                A.sbar[o] = acc;
+                A.vbar[o] = lossbar * A.inner[o];
+            }
+            // t1 = Fc^{-T} innerbar  (Fc^T = Rf[:p,:p] upper)
+            for (int i = p - 1; i >= 0; --i) {
+                R tt = lossbar * A.v[i];
+                for (int q = i + 1; q < p; ++q) tt -= A.Rf[i * N1 + q] * A.t1[q];
+                A.t1[i] = tt / A.Rf[i * N1 + i];
+            }
+            // Bbar's Fc block goes straight into Abar scratch: Fcbar = tril(-t1 inner^T - t2 s^T) + diag(...)
+            for (int i = 0; i < p; ++i) A.sbar[i] += A.t1[i];
+            for (int i = 0; i < p; ++i)
+                for (int j = 0; j <= i; ++j) A.Abar[i * N1 + j] = -A.t1[i] * A.inner[j];
+            // t2 = Fc^{-T} sbar  (reuse t1)
+            for (int i = p - 1; i >= 0; --i) {
+                R tt = A.sbar[i];
+                for (int q = i + 1; q < p; ++q) tt -= A.Rf[i * N1 + q] * A.t1[q];
+                A.t1[i] = tt / A.Rf[i * N1 + i];
+            }
+            for (int i = 0; i < p; ++i) {
+                A.vbar[i] += A.t1[i];
+                for (int j = 0; j <= i; ++j) A.Abar[i * N1 + j] -= A.t1[i] * A.sv[j];
+                A.Abar[i * N1 + i] += logdetbar * R(2) / A.Rf[i * N1 + i];
+            }
+        }
+        __syncthreads();
+        // Bbar (lower, N1 x N1) assembled in Abar: [Fcbar 0; KFbar tril(Pcfbar)],  KFbar = afbar s^T
+        for (int idx = th.tid; idx < N1 * N1; idx += th.nt) {
+            int i = idx / N1, j = idx - i * N1;
+            if (i < p) {
+                if (j > i) A.Abar[idx] = 0;
+            } else if (j < p) {
+                A.Abar[idx] = A.afbar[i - p] * A.sv[j];
+            } else {
+                A.Abar[idx] = (j <= i) ? A.Pcfbar[(i - p) * m + (j - p)] : R(0);
+            }
+        }
+        __syncthreads();
+        // Rf_bar = Bbar^T: Rbar(i,j) = Bbar[j*N1 + i] -> strides (1, N1); Psi_f into Psi; then Abar = A0 Psi_f
+        qr_pullback_psi(A.Psi, A.Rf, N1, N1, A.Abar, 1, N1, A.S1, th);
+        mm<SET>(A.Abar, N1, A.A0, N1, 1, A.Psi, N1, 1, N1, N1, N1, th);
+        // blocks: Hcbar += tril(Abar11^T); ZPbar = Abar21^T (p x m); Pbar = Abar22^T + Zm^T ZPbar
+        for (int idx = th.tid; idx < p * p; idx += th.nt) {
+            int i = idx / p, j = idx - i * p;
+            if (Hzero) A.Hcbar[idx] += A.w[i] * A.Abar[j * N1 + i];
+            else if (j <= i) A.Hcbar[idx] += A.Abar[j * N1 + i];
+        }
+        for (int idx = th.tid; idx < m * m; idx += th.nt) {
+            int i = idx / m, j = idx - i * m;
+            R acc = A.Abar[(p + j) * N1 + (p + i)];
+            for (int o = 0; o < p; ++o) acc = fma(A.Zm[o * m + i], A.Abar[(p + j) * N1 + o], acc);
+            A.Pbar[idx] = acc;
+        }
+        // Zmbar = ZPbar Pc^T - vbar a^T ; gZ += W Zmbar ; abar = afbar - Zm^T vbar ; gd -= vbar
+        for (int idx = th.tid; idx < p * m; idx += th.nt) {
+            int o = idx / m, j = idx - o * m;
+            R acc = 0;
+            for (int q = 0; q < m; ++q) acc = fma(A.Abar[(p + q) * N1 + o], A.Pc[j * m + q], acc);
+            acc = fma(-A.vbar[o], A.a[j], acc);
+            A.gZ[idx] = fma(A.w[o], acc, A.gZ[idx]);
+        }
+        for (int i = th.tid; i < m; i += th.nt) {
+            R acc = A.afbar[i];
+            for (int o = 0; o < p; ++o) acc = fma(-A.Zm[o * m + i], A.vbar[o], acc);
+            A.abar[i] = acc;
+        }
+        for (int o = th.tid; o < p; o += th.nt) A.gd[o] -= A.vbar[o];
+        __syncthreads();
+    }
+    // ---- gradients out ----
+    auto put = [&](R* dst, const R* src, size_t sz) {
+        if (dst) bcopy(dst + (size_t)b * sz, src, (int)sz, th);
+    };
+    put(g.g_a0, A.abar, m); put(g.g_P0, A.Pbar, (size_t)m * m); put(g.g_c, A.gc, m); put(g.g_d, A.gd, p);
+    put(g.g_T, A.gT, (size_t)m * m); put(g.g_Z, A.gZ, (size_t)p * m);
+    if (g.g_H) {
+        if (Hzero) {
+            put(g.g_H, A.Hcbar, (size_t)p * p);
+        } else {
+            chol_pullback(A.Psi, A.Hc, A.Hcbar, p, A.S1, th);
+            put(g.g_H, A.Psi, (size_t)p * p);
+        }
+    }
+    const R* Rg = param_ptr(g.Rm, g.shared_mask, BKF_PARAM_R, b, (size_t)m * r);
+    // X1 = Psum R (m x r) in U1;  gR = X1 (Qc Qc^T);  Qcbar = tril(R^T X1 Qc)
+    mm<SET>(A.U1, r, A.Psum, m, 1, Rg, r, 1, m, r, m, th);
+    if (g.g_R) {
+        mm<SET>(A.S1, r, A.Qc, r, 1, A.Qc, 1, r, r, r, r, th);  // Qc Qc^T
+        mm<SET>(A.Pcfbar, r, A.U1, r, 1, A.S1, r, 1, m, r, r, th);
+        put(g.g_R, A.Pcfbar, (size_t)m * r);
+    }
+    if (g.g_Q) {
+        mm<SET>(A.Pcfbar, r, A.U1, r, 1, A.Qc, r, 1, m, r, r, th);  // X1 Qc (m x r)
+        mm<SET>(A.Abar, r, Rg, 1, r, A.Pcfbar, r, 1, r, r, m, th);   // R^T X1 Qc (r x r)
+        for (int idx = th.tid; idx < r * r; idx += th.nt)
+            if ((idx % r) > (idx / r)) A.Abar[idx] = 0;
+        __syncthreads();
+        chol_pullback(A.Psi, A.Qc, A.Abar, r, A.S1, th);
+        put(g.g_Q, A.Psi, (size_t)r * r);
+    }
+}
+
+template <typename R>
+static int launch(const KArgs<R>& g, bool bwd, cudaStream_t stream, const char** err) {
+    const size_t bytes = arena_elems(g.m, g.p, g.r, bwd) * sizeof(R);
+    if (bytes > 227 * 1024 || (bwd && g.r > g.m) || (bwd && (size_t)g.r * g.r * 2 > (size_t)(g.p + g.m) * (g.p + g.m)) ||
+        (bwd && (size_t)g.p * g.p * 2 > (size_t)(g.p + g.m) * (g.p + g.m))) {
+        *err = "problem too large for the square-root filter kernels (shared memory)";
+        return BKF_ERR_UNSUPPORTED;
+    }
+    const int N1 = g.p + g.m;
+    const int threads = N1 <= 12 ? 32 : (N1 <= 24 ? 64 : (N1 <= 40 ? 128 : 256));
+    auto kern = bwd ? backward_kernel<R> : forward_kernel<R>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    if (e != cudaSuccess) { *err = cudaGetErrorString(e); return BKF_ERR_CUDA; }
+    kern<<<g.B, threads, bytes, stream>>>(g);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) { *err = cudaGetErrorString(e); return BKF_ERR_CUDA; }
+    return BKF_OK;
+}
+
+template <typename R> int launch_forward(const KArgs<R>& g, cudaStream_t s, const char** err) { return launch<R>(g, false, s, err); }
+template <typename R> int launch_backward(const KArgs<R>& g, cudaStream_t s, const char** err) { return launch<R>(g, true, s, err); }
+template int launch_forward<double>(const KArgs<double>&, cudaStream_t, const char**);
+template int launch_forward<float>(const KArgs<float>&, cudaStream_t, const char**);
+template int launch_backward<double>(const KArgs<double>&, cudaStream_t, const char**);
+template int launch_backward<float>(const KArgs<float>&, cudaStream_t, const char**);
+
+}  // namespace sq
+}  // namespace bkf

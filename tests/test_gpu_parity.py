@@ -57,7 +57,7 @@ def test_forward_outputs_match_reference_golden(eng, name):
         _close(out[n], ref[n], rtol if not _diffuse(name) else 1e-8, f"{name}:{n}")
 
 
-@pytest.mark.parametrize("name", [n for n in golden_names() if "cholesky" not in n])
+@pytest.mark.parametrize("name", golden_names())
 def test_logp_and_gradients_match_reference_golden(eng, name):
     kind, ins, ref = load_golden(name)
     logp, grads, status = eng.logp_grad(kind, *_args(ins))
@@ -177,6 +177,34 @@ def test_subwarp_kernels_all_sizes(eng, m):
         for k in NAMES:
             for b in range(B):
                 _close(grads[k][b], ref_g[k][b], RTOL64, f"{kind} m={m} d/d{k}[{b}]")
+
+
+@pytest.mark.parametrize("shape", [(2, 1, 2), (5, 2, 3), (8, 3, 2), (12, 4, 4), (6, 6, 3)])
+@pytest.mark.parametrize("missing", [0.0, 0.2])
+def test_square_root_filter_batched_logp_grad(eng, shape, missing):
+    """SquareRootFilter forward + QR adjoint (P0 is a factor; H, Q gradients in the lower-triangular convention)."""
+    from oracle import kalman_torch as oth
+    from pymc_experimental_b200 import synth
+
+    m, p, r = shape
+    B, n = 9, 14
+    cfg = synth.random_dense(B, n, m, p, r, seed=300 + m, missing=0.0)
+    if missing:  # only whole-step missingness is defined for this filter (cholesky(W H) fails otherwise)
+        rng = np.random.default_rng(m)
+        cfg["y"][rng.uniform(size=(B, n)) < missing] = np.nan
+    cfg["P0"] = np.linalg.cholesky(cfg["P0"])
+    args = [cfg["y"]] + [cfg[k] for k in NAMES]
+    out = eng.filter("cholesky", *args)
+    assert eng.last_path == "sqrt_cta"
+    ref = oth.kalman_filter("cholesky", *[__import__("torch").as_tensor(a) for a in args])
+    for got, want in zip([out[n_] for n_ in OUT_NAMES], ref):
+        _close(got, want.numpy(), RTOL64, "cholesky forward")
+    logp, grads, status = eng.logp_grad("cholesky", *args)
+    ref_logp, ref_g = oth.logp_and_grad("cholesky", *args)
+    assert_allclose(logp, ref_logp, rtol=RTOL64)
+    for k in NAMES:
+        for b in range(B):
+            _close(grads[k][b], ref_g[k][b], 1e-8, f"cholesky d/d{k}[{b}]")
 
 
 def test_ll_cotangent_is_respected(eng):
