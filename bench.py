@@ -139,6 +139,13 @@ def make_workload(name, B, T, seed_offset=0):
 
 
 # ---- CPU arm (oracle port; also the `--impl reference` arm) ----------------------------------------------
+def cpu_engine(kind, mode):
+    """Which oracle times the CPU arm: the compiled C/OpenMP port where it exists, else the torch / NumPy one."""
+    if mode == "logp_grad" and kind in ("standard", "univariate"):
+        return "c"
+    return "torch" if mode == "logp_grad" else "numpy"
+
+
 def cpu_run(name, kind, mode, cfg, sample_B):
     """One pass of the oracle over the first sample_B series of the workload; returns seconds."""
     import torch
@@ -148,6 +155,13 @@ def cpu_run(name, kind, mode, cfg, sample_B):
 
     sub = {k: cfg[k][:sample_B] for k in NAMES}
     y = cfg["y"] if cfg["y"].ndim == 2 else cfg["y"][:sample_B]
+    if cpu_engine(kind, mode) == "c":
+        from oracle import kalman_c
+
+        kalman_c.lib()
+        t0 = time.perf_counter()
+        kalman_c.logp_and_grad(kind, y, *[sub[k] for k in NAMES])
+        return time.perf_counter() - t0
     t0 = time.perf_counter()
     if mode == "logp_grad":
         oth.logp_and_grad(kind, y, *[sub[k] for k in NAMES])
@@ -160,20 +174,32 @@ def cpu_run(name, kind, mode, cfg, sample_B):
 
 
 def cpu_sample_size(name, mode):
-    return {"C1": 1, "C2": 256, "C3": 16, "C4": 16, "C5": 4096}[name] if mode == "logp_grad" else 16
+    return {"C1": 1, "C2": 2048, "C3": 16, "C4": 16, "C5": 200000}[name] if mode == "logp_grad" else 16
+
+
+def cpu_descr(kind, mode):
+    eng = cpu_engine(kind, mode)
+    if eng == "c":
+        from oracle import kalman_c
+
+        return kalman_c.num_threads(), "oracle/kalman_c.c (C port of the reference formulas + adjoint, gcc -O3 -fopenmp)"
+    if eng == "torch":
+        import torch
+
+        return torch.get_num_threads(), "oracle/kalman_torch.py (batched torch.float64 autograd)"
+    return 1, "oracle/kalman_np.py filter+smoother (NumPy/LAPACK, Python loop)"
 
 
 def cpu_baseline(name, kind, mode, cfg, T, steps=1):
     import torch
 
     sB = min(cpu_sample_size(name, mode), cfg["a0"].shape[0])
+    cpu_run(name, kind, mode, cfg, min(sB, 8))  # warm-up (library load, thread pool)
     best = min(cpu_run(name, kind, mode, cfg, sB) for _ in range(steps))
-    cores = torch.get_num_threads() if mode == "logp_grad" else 1
+    cores, what = cpu_descr(kind, mode)
     return {
         "value": sB * T / best, "unit": UNIT, "cores": cores, "kind": "port",
-        "sample": f"{sB} series x T={T} of the same workload, oracle/kalman_torch.py (batched torch.float64 "
-                  f"autograd)" if mode == "logp_grad" else
-                  f"{sB} series x T={T}, oracle/kalman_np.py filter+smoother (NumPy/LAPACK, Python loop)",
+        "sample": f"{sB} series x T={T} of the same workload through {what}",
         "seconds": best,
     }
 
@@ -193,12 +219,10 @@ def run_reference(args):
     for _ in range(args.steps):
         cpu_run(name, kind, mode, cfg, sB)
     dt = time.perf_counter() - t0
-    import torch
-
-    cores = torch.get_num_threads() if mode == "logp_grad" else 1
+    cores, what = cpu_descr(kind, mode)
     value = sB * T * args.steps / dt
-    sample = f"each step = {sB} series x T={T} of workload {name} through the CPU oracle (restatement of the " \
-             f"reference's PyTensor filter; PyTensor itself is not installable here)"
+    sample = f"each step = {sB} series x T={T} of workload {name} through {what}; a restatement of the " \
+             f"reference's PyTensor filter (PyTensor itself is not installable here)"
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",

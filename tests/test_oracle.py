@@ -182,3 +182,32 @@ def test_last_smoother_is_last_filtered_and_covariances_psd(kind):
     for cov in (outs[3], outs[4], sm_P):  # filtered, predicted, smoothed covariances
         assert (np.linalg.eigvalsh(0.5 * (cov + np.swapaxes(cov, -1, -2))) > 0).all()
         assert_allclose(cov, np.swapaxes(cov, -1, -2), rtol=1e-6, atol=1e-6)
+
+
+@pytest.mark.parametrize("name", [n for n in ALL if "cholesky" not in n])
+def test_c_oracle_matches_reference_logp_and_grad(name):
+    """oracle/kalman_c.c (the compiled CPU baseline) against the vectors produced from the reference's source."""
+    from oracle import kalman_c
+
+    kind, ins, ref = load_golden(name)
+    logp, grads = kalman_c.logp_and_grad(kind, *_args(ins))
+    rtol = 1e-6 if _ill_conditioned(name) else (1e-7 if ("nile" in name or name.startswith("c1_")) else 1e-9)
+    assert_allclose(logp, ref["loglike_obs"].sum(), rtol=rtol)
+    for k in NAMES:
+        g_ref = ref["grad_" + k]
+        scale = max(np.abs(g_ref).max(), 1e-300)
+        assert_allclose(grads[k], g_ref, rtol=0, atol=rtol * scale, err_msg=f"{name}: d/d{k}")
+
+
+def test_c_oracle_batched_and_threaded():
+    from oracle import kalman_c
+    from pymc_experimental_b200 import synth
+
+    cfg = synth.random_dense(13, 12, 5, 2, 3, seed=17, missing=0.0)
+    cot = np.random.default_rng(1).standard_normal((13, 12))
+    for kind in ("standard", "univariate"):
+        logp, grads = kalman_c.logp_and_grad(kind, cfg["y"], *[cfg[k] for k in NAMES], ll_cotangent=cot)
+        ref_logp, ref_g = oth.logp_and_grad(kind, cfg["y"], *[cfg[k] for k in NAMES], ll_cotangent=cot)
+        assert_allclose(logp, ref_logp, rtol=1e-11)
+        for k in NAMES:
+            assert_allclose(grads[k], ref_g[k], rtol=0, atol=1e-9 * np.abs(ref_g[k]).max())
