@@ -228,6 +228,10 @@ static int run_forward(bkf_handle* h, const KArgs<double>& g, const char** err) 
         h->path = "thread_f64";
         return tps::launch_any<double>(g, false, h->stream, err);
     }
+    if (tc::supported(g.kind, g.m, g.p)) {
+        h->path = "dmma_f64";
+        return tc::launch_f64(g, false, h->stream, err);
+    }
     if (sw::supported(g.kind, g.m, g.p)) {
         h->path = "subwarp_f64";
         return sw::launch_f64(g, false, h->stream, err);
@@ -254,6 +258,7 @@ static int run_backward(bkf_handle* h, const KArgs<double>& g, const char** err)
     h->launches += 1;
     if (g.kind == BKF_CHOLESKY) return sq::launch_backward<double>(g, h->stream, err);
     if (tps::supported(g.kind, g.m, g.p)) return tps::launch_any<double>(g, true, h->stream, err);
+    if (tc::supported(g.kind, g.m, g.p)) return tc::launch_f64(g, true, h->stream, err);
     if (sw::supported(g.kind, g.m, g.p)) return sw::launch_f64(g, true, h->stream, err);
     return gen::launch_backward<double>(g, h->stream, err);
 }
@@ -455,7 +460,13 @@ static int logp_grad_impl(bkf_handle* h, const bkf_problem* P, const void* y, co
     R** gdst[BKF_NPARAM] = {&g.g_a0, &g.g_P0, &g.g_c, &g.g_d, &g.g_T, &g.g_Z, &g.g_R, &g.g_H, &g.g_Q};
     for (int i = 0; i < BKF_NPARAM; ++i)
         *gdst[i] = stage_out<R>(h, P, S_GA0 + i, grads[i], B * param_elems(P, i), &rc);
-    if (want_grad) g.traj = (R*)ensure(h, S_TRAJ, B * n * (m + m * m) * sizeof(R), &rc);
+    if (want_grad) {
+        // the trajectory layout is private to a kernel family: dense [a | P] records, or DMMA fragment records
+        const bool frag = sizeof(R) == 8 && P->kind != BKF_CHOLESKY && !tps::supported(P->kind, P->m, P->p) &&
+                          tc::supported(P->kind, P->m, P->p);
+        const size_t rec = frag ? tc::traj_record_elems() : m + m * m;
+        g.traj = (R*)ensure(h, S_TRAJ, B * n * rec * sizeof(R), &rc);
+    }
     int* dstatus = nullptr;
     if (status) dstatus = P->mem == BKF_MEM_DEVICE ? status : (int*)ensure(h, S_STATUS, B * sizeof(int), &rc);
     g.status = dstatus;

@@ -110,7 +110,7 @@ def test_specialised_kernel_path_is_taken_for_m15(eng, kind):
 
     cfg = synth.sarima(B=5, n=12)
     eng.logp_grad(kind, cfg["y"], *[cfg[k] for k in NAMES])
-    assert eng.last_path == "subwarp_f64"
+    assert eng.last_path == "dmma_f64"
 
 
 @pytest.mark.parametrize("kind", ["standard", "univariate"])
@@ -161,7 +161,7 @@ def test_thread_per_series_kernels(eng, kind, m):
             _close(grads[k][b], ref_g[k][b], RTOL64, f"d/d{k}[{b}]")
 
 
-@pytest.mark.parametrize("m", [5, 6, 8, 9, 12, 16])
+@pytest.mark.parametrize("m", [5, 6, 8, 9, 10, 12, 13, 15, 16])
 def test_subwarp_kernels_all_sizes(eng, m):
     from oracle import kalman_torch as oth
     from pymc_experimental_b200 import synth
@@ -171,7 +171,7 @@ def test_subwarp_kernels_all_sizes(eng, m):
     args = [cfg["y"]] + [cfg[k] for k in NAMES]
     for kind in ("standard", "univariate"):
         logp, grads, status = eng.logp_grad(kind, *args)
-        assert eng.last_path == "subwarp_f64"
+        assert eng.last_path == ("dmma_f64" if m >= 9 else "subwarp_f64")
         ref_logp, ref_g = oth.logp_and_grad(kind, *args)
         assert_allclose(logp, ref_logp, rtol=RTOL64)
         for k in NAMES:
