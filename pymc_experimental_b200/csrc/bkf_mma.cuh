@@ -31,6 +31,7 @@ constexpr int SLD = 18;             // leading dimension of the per-warp transpo
 constexpr int SCRATCH = MP * SLD;   // doubles of scratch per warp
 constexpr unsigned FULL = 0xffffffffu;
 
+
 struct Frag { double v[2][2][2]; };  // v[I][J][e] = X[8I+g][8J+2t+e]
 struct RVec { double v[2]; };        // v[I]       = x[8I+g]
 struct CVec { double v[2][2]; };     // v[J][e]    = x[8J+2t+e]
@@ -58,6 +59,33 @@ __device__ __forceinline__ void mm_nt(Frag& D, const Frag& X, const Frag& Y) {
             for (int I = 0; I < 2; ++I)
 #pragma unroll
                 for (int J = 0; J < 2; ++J) dmma(D.v[I][J][0], D.v[I][J][1], X.v[I][K][e], Y.v[J][K][e]);
+}
+
+// Tiles (0,0), (0,1), (1,1) of D += X Y^T (12 DMMAs) for products whose result is symmetric; D is NOT cleared.
+__device__ __forceinline__ void mm_nt_upper(Frag& D, const Frag& X, const Frag& Y) {
+#pragma unroll
+    for (int K = 0; K < 2; ++K)
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+            dmma(D.v[0][0][0], D.v[0][0][1], X.v[0][K][e], Y.v[0][K][e]);
+            dmma(D.v[0][1][0], D.v[0][1][1], X.v[0][K][e], Y.v[1][K][e]);
+            dmma(D.v[1][1][0], D.v[1][1][1], X.v[1][K][e], Y.v[1][K][e]);
+        }
+}
+// Stage tiles (0,0), (0,1), (1,1) of X in the scratch and read back (0,0)^T, (1,1)^T and (0,1)^T:
+// Xt.v[0][0] = X00^T, Xt.v[1][1] = X11^T, Xt.v[1][0] = X01^T  (Xt.v[0][1] is left untouched).
+__device__ __forceinline__ void transpose_upper(Frag& Xt, const Frag& X, double* sc, int g, int t) {
+    *reinterpret_cast<double2*>(sc + g * SLD + 2 * t) = make_double2(X.v[0][0][0], X.v[0][0][1]);
+    *reinterpret_cast<double2*>(sc + g * SLD + 8 + 2 * t) = make_double2(X.v[0][1][0], X.v[0][1][1]);
+    *reinterpret_cast<double2*>(sc + (8 + g) * SLD + 8 + 2 * t) = make_double2(X.v[1][1][0], X.v[1][1][1]);
+    __syncwarp();
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+        Xt.v[0][0][e] = sc[(2 * t + e) * SLD + g];
+        Xt.v[1][1][e] = sc[(8 + 2 * t + e) * SLD + 8 + g];
+        Xt.v[1][0][e] = sc[(2 * t + e) * SLD + 8 + g];
+    }
+    __syncwarp();
 }
 
 __device__ __forceinline__ double red_t(double x) {  // sum over the 4 lanes of a quad (t)
@@ -333,32 +361,63 @@ __device__ __forceinline__ void update(Upd& u, const Frag& P, const Frag& Pt, co
 }
 
 struct FwdConst {
-    Frag Tc, RQR;
+    Frag Tc;   // T
+    Frag C0;   // sym(R Q R^T) + eps sym(T T^T): everything of P+ that does not depend on the step (exactly symmetric)
+    Frag RQR;  // sym(R Q R^T) (first step only)
     RVec z_r, c_r;
     CVec z_c;
     double H0, d0;
 };
 
-template <int KIND, bool ASYM>
-__device__ __forceinline__ void fwd_step(const KArgs<double>& G, const FwdConst& K, Frag& P, const Frag& Pt, RVec& a_r,
-                                         CVec& a_c, double& logp, int b, int ts, double yv, double* sc, int lane) {
+// Log-likelihood terms are deferred: lane (ts mod 32) keeps (F, v) of step ts and every 32 steps all lanes evaluate
+// their log / division at once (one log per 32 steps per lane instead of one per step, replicated 32 times).
+struct LlBuf {
+    double F, v, acc;
+    bool skip;
+};
+__device__ __forceinline__ void ll_capture(LlBuf& L, int lane, int ts, double F, double v, bool skip) {
+    if (lane == (ts & 31)) {
+        L.F = F;
+        L.v = v;
+        L.skip = skip;
+    }
+}
+template <int KIND>
+__device__ __forceinline__ void ll_flush(LlBuf& L, const KArgs<double>& G, int b, int ts, int lane) {
+    const int my = (ts & ~31) + lane;
+    if (my <= ts) {
+        double ll;
+        if (KIND == K_UNI) {
+            const double lli = L.skip ? 0.0 : log(L.F) + L.v * L.v / L.F;  // :787
+            ll = -0.5 * ((lli != 0.0 ? kLog2Pi : 0.0) + lli);             // :818
+        } else {
+            ll = L.skip ? 0.0 : -0.5 * (kLog2Pi + log(L.F) + L.v * (L.v / L.F));  // :611-615
+        }
+        L.acc += ll;
+        if (G.ll) G.ll[(size_t)b * G.n + my] = ll;
+    }
+}
+
+// First step (t = 0): the user's P0 may be asymmetric, so the update is evaluated exactly as the reference writes
+// it (update<KIND, true>) and P_f goes through both products.
+template <int KIND>
+__device__ __forceinline__ void fwd_step_first(const KArgs<double>& G, const FwdConst& K, Frag& P, const Frag& Pt,
+                                               RVec& a_r, CVec& a_c, LlBuf& L, int b, double yv, double* sc, int lane) {
     const int g = lane >> 2, t = lane & 3, m = G.m;
-    const size_t bt = (size_t)b * G.n + ts;
-    // ---- emit the prediction (a, P) of this step: trajectory for the adjoint and/or user outputs ----
+    const size_t bt = (size_t)b * G.n;
     if (G.traj) store_rec(G.traj + bt * REC, P, a_c, lane);
     if (G.pred_a) store_rvec(G.pred_a + bt * m, a_r, m, g, t);
     if (G.pred_P) store_frag(G.pred_P + bt * m * m, P, m, g, t, 1.0);
     Upd u;
-    update<KIND, ASYM>(u, P, Pt, a_r, a_c, yv, G.fill, G.jitter, K.z_r, K.z_c, K.d0, K.H0, g, t);
-    logp += u.ll;
+    update<KIND, true>(u, P, Pt, a_r, a_c, yv, G.fill, G.jitter, K.z_r, K.z_c, K.d0, K.H0, g, t);
+    ll_capture(L, lane, 0, u.F, u.v, KIND == K_UNI ? u.keep == 0.0 : u.flag);
     if (lane == 0) {
-        if (G.ll) G.ll[bt] = u.ll;
         if (G.obs_mu) G.obs_mu[bt] = u.yhat;
         if (G.obs_cov) G.obs_cov[bt] = u.F;
     }
     if (G.filt_a) store_rvec(G.filt_a + bt * m, u.af_r, m, g, t);
     if (G.filt_P) store_frag(G.filt_P + bt * m * m, u.Pf, m, g, t, 1.0);
-    // ---- predict: a+ = T a_f + c ; P+ = sym(T P_f T^T) + sym(R Q R^T) ----
+    // predict: a+ = T a_f + c ; P+ = sym(T P_f T^T) + sym(R Q R^T)
     a_r = mv(K.Tc, u.af_c);
 #pragma unroll
     for (int I = 0; I < 2; ++I) a_r.v[I] += K.c_r.v[I];
@@ -375,8 +434,107 @@ __device__ __forceinline__ void fwd_step(const KArgs<double>& G, const FwdConst&
             for (int e = 0; e < 2; ++e) P.v[I][J][e] = 0.5 * (Y.v[I][J][e] + Yt.v[I][J][e]) + K.RQR.v[I][J][e];
 }
 
-template <int KIND>
-__global__ void __launch_bounds__(64) forward_kernel(KArgs<double> G) {
+// Steps t >= 1: P is symmetric, so P_f = P - coef (P z^T)(P z^T)^T + eps I for both filters
+//   Univariate: coef = 1/F (0 when skipped)                                        (:782-785, :815)
+//   Standard:   coef = (F + eps)/F^2  -- the Joseph form (:601-604) with K = P z^T / F substituted
+// and the prediction is evaluated as
+//   P+ = sym(T P T^T) - coef (T P z^T)(T P z^T)^T + C0 ,   a+ = T a + c + (T P z^T) v / F
+// which takes the two DMMA products off the scalar dependency chain (they only need P, not K or F).
+template <int KIND, bool OUT>
+__device__ __forceinline__ void fwd_step(const KArgs<double>& G, const FwdConst& K, Frag& P, RVec& a_r, CVec& a_c,
+                                         LlBuf& L, int b, int ts, double yv, double* sc, int lane) {
+    const int g = lane >> 2, t = lane & 3, m = G.m;
+    const size_t bt = (size_t)b * G.n + ts;
+    if (G.traj) store_rec(G.traj + bt * REC, P, a_c, lane);
+    if (OUT) {
+        if (G.pred_a) store_rvec(G.pred_a + bt * m, a_r, m, g, t);
+        if (G.pred_P) store_frag(G.pred_P + bt * m * m, P, m, g, t, 1.0);
+    }
+    Frag W;
+    mm_nt<false>(W, K.Tc, P);  // W = T P
+    const bool miss = (KIND == K_UNI) ? isnan(yv) : (isnan(yv) || yv == G.fill);  // :792 vs :352 (quirk Q6)
+    const double ym = miss ? 0.0 : yv;
+    const double Hm = miss ? 0.0 : K.H0;
+    RVec zm_r;
+    CVec zm_c;
+#pragma unroll
+    for (int I = 0; I < 2; ++I) {
+        zm_r.v[I] = miss ? 0.0 : K.z_r.v[I];
+        zm_c.v[I][0] = miss ? 0.0 : K.z_c.v[I][0];
+        zm_c.v[I][1] = miss ? 0.0 : K.z_c.v[I][1];
+    }
+    const double yhat = K.d0 + dot_c(zm_c, a_c);
+    const double v = ym - yhat;
+    const RVec pz_r = mv(P, zm_c);
+    const CVec pz_c = row2col(pz_r, t);
+    const double f0 = dot_r(zm_r, pz_r);
+    double F, rFk, coef;
+    bool skip;
+    if (KIND == K_UNI) {
+        const double F0 = f0 + Hm;
+        skip = (F0 == 0.0) || miss;  // :777
+        F = F0 + G.jitter;
+        rFk = skip ? 0.0 : 1.0 / F;
+        coef = rFk;
+    } else {
+        F = f0 + (Hm + G.jitter);  // :598
+        rFk = 1.0 / F;
+        coef = (F + G.jitter) * rFk * rFk;
+        skip = miss;
+    }
+    ll_capture(L, lane, ts, F, v, skip);
+    const double gain = rFk * v;
+    if (OUT) {
+        if (lane == 0) {
+            if (G.obs_mu) G.obs_mu[bt] = yhat;
+            if (G.obs_cov) G.obs_cov[bt] = F;
+        }
+        if (G.filt_a) {
+            RVec af_r;
+            af_r.v[0] = fma(pz_r.v[0], gain, a_r.v[0]);
+            af_r.v[1] = fma(pz_r.v[1], gain, a_r.v[1]);
+            store_rvec(G.filt_a + bt * m, af_r, m, g, t);
+        }
+        if (G.filt_P) {
+            Frag Pf;
+#pragma unroll
+            for (int I = 0; I < 2; ++I)
+#pragma unroll
+                for (int J = 0; J < 2; ++J)
+#pragma unroll
+                    for (int e = 0; e < 2; ++e) {
+                        double pf = fma(-coef, pz_r.v[I] * pz_c.v[J][e], P.v[I][J][e]);
+                        if (I == J && g == 2 * t + e) pf += G.jitter;
+                        Pf.v[I][J][e] = pf;
+                    }
+            store_frag(G.filt_P + bt * m * m, Pf, m, g, t, 1.0);
+        }
+    }
+    const RVec Ta_r = mv(K.Tc, a_c);
+    const RVec tp_r = mv(K.Tc, pz_c);  // T P z^T
+    const CVec tp_c = row2col(tp_r, t);
+#pragma unroll
+    for (int I = 0; I < 2; ++I) a_r.v[I] = fma(tp_r.v[I], gain, Ta_r.v[I] + K.c_r.v[I]);
+    a_c = row2col(a_r, t);
+    // Y = W T^T, upper tiles; C0 rides in as the accumulator of the off-diagonal tile
+    Frag Y, Yt;
+    Y.v[0][0][0] = Y.v[0][0][1] = Y.v[1][1][0] = Y.v[1][1][1] = 0.0;
+    Y.v[0][1][0] = K.C0.v[0][1][0];
+    Y.v[0][1][1] = K.C0.v[0][1][1];
+    mm_nt_upper(Y, W, K.Tc);
+    transpose_upper(Yt, Y, sc, g, t);
+    const double cr0 = coef * tp_r.v[0], cr1 = coef * tp_r.v[1];
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+        P.v[0][0][e] = fma(-cr0, tp_c.v[0][e], fma(0.5, Y.v[0][0][e] + Yt.v[0][0][e], K.C0.v[0][0][e]));
+        P.v[1][1][e] = fma(-cr1, tp_c.v[1][e], fma(0.5, Y.v[1][1][e] + Yt.v[1][1][e], K.C0.v[1][1][e]));
+        P.v[0][1][e] = fma(-cr0, tp_c.v[1][e], Y.v[0][1][e]);
+        P.v[1][0][e] = fma(-cr1, tp_c.v[0][e], Yt.v[1][0][e]);
+    }
+}
+
+template <int KIND, bool OUT, int OCC>
+__global__ void __launch_bounds__(64, OCC) forward_kernel(KArgs<double> G) {
     extern __shared__ double smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int g = lane >> 2, t = lane & 3;
@@ -386,9 +544,23 @@ __global__ void __launch_bounds__(64) forward_kernel(KArgs<double> G) {
     const int m = G.m, n = G.n;
 
     FwdConst K;
-    load_frag<false>(K.Tc, param_ptr(G.T, G.shared_mask, BKF_PARAM_T, b, (size_t)m * m), m, g, t);
+    const double* Tg = param_ptr(G.T, G.shared_mask, BKF_PARAM_T, b, (size_t)m * m);
+    load_frag<false>(K.Tc, Tg, m, g, t);
     rqr_frag(K.RQR, param_ptr(G.Rm, G.shared_mask, BKF_PARAM_R, b, (size_t)m * G.r),
              param_ptr(G.Q, G.shared_mask, BKF_PARAM_Q, b, (size_t)G.r * G.r), m, G.r, g, t);
+#pragma unroll
+    for (int I = 0; I < 2; ++I)
+#pragma unroll
+        for (int J = 0; J < 2; ++J)
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                // (T T^T)[i][j]: the same products in the same order for (i,j) and (j,i) => exactly symmetric
+                const int i = 8 * I + g, j = 8 * J + 2 * t + e;
+                double s = 0.0;
+                if (i < m && j < m)
+                    for (int k = 0; k < m; ++k) s = fma(Tg[i * m + k], Tg[j * m + k], s);
+                K.C0.v[I][J][e] = fma(G.jitter, s, K.RQR.v[I][J][e]);
+            }
     const double* Zg = param_ptr(G.Z, G.shared_mask, BKF_PARAM_Z, b, (size_t)m);
     K.z_r = load_rvec(Zg, m, g);
     K.z_c = load_cvec(Zg, m, t);
@@ -403,19 +575,26 @@ __global__ void __launch_bounds__(64) forward_kernel(KArgs<double> G) {
     Frag P;
     load_frag<false>(P, P0g, m, g, t);
     const double* yb = G.y_shared ? G.y : G.y + (size_t)b * n;
-    double logp = 0;
+    LlBuf L;
+    L.F = 1.0;
+    L.v = 0.0;
+    L.acc = 0.0;
+    L.skip = true;
     {
         Frag Pt;
         load_frag<true>(Pt, P0g, m, g, t);
-        fwd_step<KIND, true>(G, K, P, Pt, a_r, a_c, logp, b, 0, yb[0], sc, lane);
+        fwd_step_first<KIND>(G, K, P, Pt, a_r, a_c, L, b, yb[0], sc, lane);
+        if (n == 1) ll_flush<KIND>(L, G, b, 0, lane);
     }
     double ynext = n > 1 ? yb[1] : 0.0;
 #pragma unroll 1
     for (int ts = 1; ts < n; ++ts) {
         const double yv = ynext;
         if (ts + 1 < n) ynext = yb[ts + 1];
-        fwd_step<KIND, false>(G, K, P, P, a_r, a_c, logp, b, ts, yv, sc, lane);
+        fwd_step<KIND, OUT>(G, K, P, a_r, a_c, L, b, ts, yv, sc, lane);
+        if ((ts & 31) == 31 || ts == n - 1) ll_flush<KIND>(L, G, b, ts, lane);
     }
+    const double logp = warp_sum(L.acc);
     if (lane == 0) {
         if (G.logp) G.logp[b] = logp;
         if (G.status) G.status[b] = isfinite(logp) ? 0 : BKF_STATUS_NONFINITE;
