@@ -761,6 +761,184 @@ __device__ __forceinline__ void bwd_step(const KArgs<double>& G, const BwdConst&
     S.abar_c = row2col(S.abar_r, t);
 }
 
+// Reverse step for t >= 1 (P symmetric): branch-free, the DMMA chain (W', V, Pbar_f) only needs G, the update is
+// recomputed from (a, P) concurrently, P_f = P - coef (P z^T)(P z^T)^T + eps I (see fwd_step).
+template <int KIND>
+__device__ __forceinline__ void bwd_step_sym(const KArgs<double>& G, const BwdConst& K, BwdState& S, const Frag& P,
+                                             const RVec& a_r, const CVec& a_c, double yv, double gcot, double* sc,
+                                             int lane) {
+    const int g = lane >> 2, t = lane & 3;
+    // ================= predict adjoint: products =================
+    Frag W, V, Pfb;
+#pragma unroll
+    for (int I = 0; I < 2; ++I)
+#pragma unroll
+        for (int J = 0; J < 2; ++J)
+#pragma unroll
+            for (int e = 0; e < 2; ++e) S.Gsum.v[I][J][e] += S.G.v[I][J][e];
+    mm_nt<false>(W, K.TTc, S.G);  // W' = T^T G
+    transpose(V, W, sc, g, t);    // V = G T
+    Pfb.v[0][0][0] = Pfb.v[0][0][1] = Pfb.v[0][1][0] = Pfb.v[0][1][1] = Pfb.v[1][1][0] = Pfb.v[1][1][1] = 0.0;
+    mm_nt_upper(Pfb, W, K.TTc);   // Pbar_f = T^T G T (symmetric): upper tiles, then mirror the off-diagonal one
+    *reinterpret_cast<double2*>(sc + g * SLD + 8 + 2 * t) = make_double2(Pfb.v[0][1][0], Pfb.v[0][1][1]);
+    __syncwarp();
+    Pfb.v[1][0][0] = sc[(2 * t) * SLD + 8 + g];
+    Pfb.v[1][0][1] = sc[(2 * t + 1) * SLD + 8 + g];
+    __syncwarp();
+    // ================= recompute the update =================
+    const bool miss = (KIND == K_UNI) ? isnan(yv) : (isnan(yv) || yv == G.fill);
+    const double ym = miss ? 0.0 : yv;
+    const double Hm = miss ? 0.0 : K.H0;
+    RVec zm_r;
+    CVec zm_c;
+#pragma unroll
+    for (int I = 0; I < 2; ++I) {
+        zm_r.v[I] = miss ? 0.0 : K.z_r.v[I];
+        zm_c.v[I][0] = miss ? 0.0 : K.z_c.v[I][0];
+        zm_c.v[I][1] = miss ? 0.0 : K.z_c.v[I][1];
+    }
+    const double v = ym - (K.d0 + dot_c(zm_c, a_c));
+    const RVec pz_r = mv(P, zm_c);
+    const CVec pz_c = row2col(pz_r, t);
+    const double f0 = dot_r(zm_r, pz_r);
+    double F, rF, rFk, coef, keep;
+    if (KIND == K_UNI) {
+        const double F0 = f0 + Hm;
+        const bool skip = (F0 == 0.0) || miss;
+        F = F0 + G.jitter;
+        rF = 1.0 / F;
+        keep = skip ? 0.0 : 1.0;
+        rFk = skip ? 0.0 : rF;
+        coef = rFk;
+    } else {
+        F = f0 + (Hm + G.jitter);
+        rF = 1.0 / F;
+        rFk = rF;
+        coef = (F + G.jitter) * rF * rF;
+        keep = miss ? 0.0 : 1.0;
+    }
+    RVec K_r;
+    CVec K_c, af_c;
+    Frag Pf;
+#pragma unroll
+    for (int I = 0; I < 2; ++I) {
+        K_r.v[I] = pz_r.v[I] * rFk;
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+            K_c.v[I][e] = pz_c.v[I][e] * rFk;
+            af_c.v[I][e] = fma(K_c.v[I][e], v, a_c.v[I][e]);
+        }
+    }
+#pragma unroll
+    for (int I = 0; I < 2; ++I) {
+        const double cp = coef * pz_r.v[I];
+#pragma unroll
+        for (int J = 0; J < 2; ++J)
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                double pf = fma(-cp, pz_c.v[J][e], P.v[I][J][e]);
+                if (I == J && g == 2 * t + e) pf += G.jitter;
+                Pf.v[I][J][e] = pf;
+            }
+    }
+    // ================= predict adjoint: T, c =================
+    mm_nt<true>(S.Th, V, Pf);  // Tbar/2 += (G T) P_f
+#pragma unroll
+    for (int I = 0; I < 2; ++I) {
+        const double h = 0.5 * S.abar_r.v[I];  // Tbar += abar+ a_f^T
+#pragma unroll
+        for (int J = 0; J < 2; ++J)
+#pragma unroll
+            for (int e = 0; e < 2; ++e) S.Th.v[I][J][e] = fma(h, af_c.v[J][e], S.Th.v[I][J][e]);
+    }
+    const RVec afbar_r = mv(K.TTc, S.abar_c);  // T^T abar+
+#pragma unroll
+    for (int I = 0; I < 2; ++I) S.gc_r.v[I] += S.abar_r.v[I];
+    // ================= update adjoint =================
+    if (KIND == K_UNI) {
+        const double llbar = -0.5 * gcot;
+        const RVec pk_r = mv(Pfb, K_c);  // Pbar_u K, Pbar_u = S(Pbar_f) ~ Pbar_f
+        const double kpk = dot_r(K_r, pk_r);
+        const double ka = dot_r(K_r, afbar_r);
+        const double kk = fma(-2.0 * F, kpk, v * ka);  // Kbar . K
+        const double Fbar = keep * (-kpk + llbar * (rF - v * v * rF * rF) - kk * rF);
+        const double vbar = keep * (ka + llbar * 2.0 * v * rF);
+        RVec hr;  // pzbar / 2
+#pragma unroll
+        for (int I = 0; I < 2; ++I) {
+            const double Kbar = fma(-2.0 * F, pk_r.v[I], afbar_r.v[I] * v);
+            hr.v[I] = 0.5 * fma(Fbar, zm_r.v[I], Kbar * rFk);
+        }
+        const CVec hc = row2col(hr, t);
+        const RVec ppz = mv(P, hc);  // P pzbar / 2
+#pragma unroll
+        for (int I = 0; I < 2; ++I) {
+            S.gz_r.v[I] += fma(Fbar, pz_r.v[I], 2.0 * ppz.v[I]) - vbar * a_r.v[I];
+            S.abar_r.v[I] = fma(-vbar, zm_r.v[I], afbar_r.v[I]);
+#pragma unroll
+            for (int J = 0; J < 2; ++J)
+#pragma unroll
+                for (int e = 0; e < 2; ++e)
+                    S.G.v[I][J][e] = fma(hr.v[I], zm_c.v[J][e], fma(zm_r.v[I], hc.v[J][e], Pfb.v[I][J][e]));
+        }
+        S.gH += Fbar;
+        S.gd -= vbar;
+    } else {
+        const double wv = v * rF;
+        // xz2 = (P + P^T) z - 2 f0 K ;  u1 = G2 xz2 ;  gk = G2 K      (G2 = S(Pbar_f) ~ Pbar_f)
+        CVec xz2_c;
+#pragma unroll
+        for (int J = 0; J < 2; ++J)
+#pragma unroll
+            for (int e = 0; e < 2; ++e) xz2_c.v[J][e] = 2.0 * fma(-f0, K_c.v[J][e], pz_c.v[J][e]);
+        const RVec u1_r = mv(Pfb, xz2_c);
+        const RVec gk_r = mv(Pfb, K_c);
+        const double kgk = dot_r(K_r, gk_r);
+        const CVec gk_c = row2col(gk_r, t);
+        const RVec pg = mv(P, gk_c);  // (P + P^T) gk = 2 P gk
+        double vbar = dot_r(K_r, afbar_r);
+        double Fbar = keep * (-0.5 * gcot * (rF - wv * wv));
+        vbar -= keep * gcot * wv;
+        // Kbar = G2 K (Hm + Hm^T) + afbar v - Lbar z ;  K = PZT / F
+        RVec pztbar_r;
+#pragma unroll
+        for (int I = 0; I < 2; ++I) pztbar_r.v[I] = (fma(2.0 * Hm, gk_r.v[I], afbar_r.v[I] * v) - u1_r.v[I]) * rF;
+        Fbar -= dot_r(K_r, pztbar_r);
+        const double Hmbar = kgk + Fbar;
+        RVec zmbar_r, hr;
+#pragma unroll
+        for (int I = 0; I < 2; ++I) {
+            // Zmbar = -K^T Lbar + Fbar PZT = -(2 P gk - 2 (gk . K) P z^T) + Fbar P z^T
+            zmbar_r.v[I] = fma(Fbar + 2.0 * kgk, pz_r.v[I], -2.0 * pg.v[I]);
+            hr.v[I] = 0.5 * fma(Fbar, zm_r.v[I], pztbar_r.v[I]);  // PZTbar / 2
+        }
+        const CVec hc = row2col(hr, t);
+        const RVec ppz = mv(P, hc);  // PZT = P Zm^T  ->  Zmbar += P^T PZTbar
+        const double hk = 0.5 * kgk;
+        CVec qc;
+#pragma unroll
+        for (int J = 0; J < 2; ++J)
+#pragma unroll
+            for (int e = 0; e < 2; ++e) qc.v[J][e] = fma(hk, zm_c.v[J][e], hc.v[J][e] - gk_c.v[J][e]);
+#pragma unroll
+        for (int I = 0; I < 2; ++I) {
+            zmbar_r.v[I] = fma(-vbar, a_r.v[I], fma(2.0, ppz.v[I], zmbar_r.v[I]));  // v = ym - d - Zm a
+            S.abar_r.v[I] = fma(-vbar, zm_r.v[I], afbar_r.v[I]);
+            S.gz_r.v[I] = fma(keep, zmbar_r.v[I], S.gz_r.v[I]);
+            // S(Pbar) = S(L^T G2 L + PZTbar Zm) = G2 + z q^T + q z^T,  q = PZTbar/2 - gk + (gk . K) z / 2
+            const double qr = fma(hk, zm_r.v[I], hr.v[I] - gk_r.v[I]);
+#pragma unroll
+            for (int J = 0; J < 2; ++J)
+#pragma unroll
+                for (int e = 0; e < 2; ++e)
+                    S.G.v[I][J][e] = fma(qr, zm_c.v[J][e], fma(zm_r.v[I], qc.v[J][e], Pfb.v[I][J][e]));
+        }
+        S.gd -= vbar;
+        S.gH = fma(keep, Hmbar, S.gH);
+    }
+    S.abar_c = row2col(S.abar_r, t);
+}
+
 template <int KIND>
 __global__ void __launch_bounds__(64) backward_kernel(KArgs<double> G) {
     extern __shared__ double smem[];
@@ -806,7 +984,7 @@ __global__ void __launch_bounds__(64) backward_kernel(KArgs<double> G) {
         a_r = an_r;
         a_c = an_c;
         if (ts > 1) load_rec(traj + (size_t)(ts - 1) * REC, Pn, an_r, an_c, lane);  // prefetch one step ahead
-        bwd_step<KIND, false>(G, K, S, P, P, a_r, a_c, yb[ts], cot ? cot[ts] : 1.0, sc, lane);
+        bwd_step_sym<KIND>(G, K, S, P, a_r, a_c, yb[ts], cot ? cot[ts] : 1.0, sc, lane);
     }
     {
         const double* a0g = param_ptr(G.a0, G.shared_mask, BKF_PARAM_A0, b, (size_t)m);
