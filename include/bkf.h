@@ -39,6 +39,8 @@
 #ifndef BKF_H
 #define BKF_H
 
+#include <stddef.h>
+
 #ifdef __cplusplus
 extern "C" {
 #endif
@@ -97,6 +99,12 @@ int bkf_kernel_time_ms(bkf_handle* h, int kernel_class, double* total_ms, long l
 /* DFMA / FFMA issue-rate microbenchmark (register-resident FMA chains on every SM): the measured FP64 / FP32
  * pipe peak in TFLOP/s that roofline fractions are quoted against (MEASURED_PEAKS.json has no such entry). */
 int bkf_measure_fma_peak(bkf_handle* h, int dtype, double* tflops);
+
+/* Page-locked host memory for call outputs / inputs (cudaHostAlloc / cudaFreeHost).  Host-pointer calls work with
+ * any memory; with pinned buffers the H2D / D2H copies inside a call run at full PCIe / C2C rate instead of being
+ * staged through the driver's bounce buffer.  The host side of the PyTensor Op keeps a pool of these. */
+int bkf_host_alloc(size_t bytes, void** out);
+int bkf_host_free(void* p);
 
 int bkf_filter_forward(bkf_handle* h, const bkf_problem* prob, const void* y, const void* a0, const void* P0,
                        const void* c, const void* d, const void* T, const void* Z, const void* R, const void* H,

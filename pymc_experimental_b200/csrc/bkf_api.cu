@@ -209,6 +209,24 @@ extern "C" int bkf_measure_fma_peak(bkf_handle* h, int dtype, double* tflops) {
     return BKF_OK;
 }
 
+extern "C" int bkf_host_alloc(size_t bytes, void** out) {
+    if (!out) return BKF_ERR_ARG;
+    *out = nullptr;
+    cudaError_t e = cudaHostAlloc(out, bytes ? bytes : 1, cudaHostAllocDefault);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return BKF_ERR_NOMEM;
+    }
+    return BKF_OK;
+}
+extern "C" int bkf_host_free(void* p) {
+    if (p && cudaFreeHost(p) != cudaSuccess) {
+        cudaGetLastError();
+        return BKF_ERR_CUDA;
+    }
+    return BKF_OK;
+}
+
 extern "C" int bkf_set_stream(bkf_handle* h, void* s) {
     if (!h) return BKF_ERR_ARG;
     h->stream = reinterpret_cast<cudaStream_t>(s);

@@ -761,21 +761,91 @@ __device__ __forceinline__ void bwd_step(const KArgs<double>& G, const BwdConst&
     S.abar_c = row2col(S.abar_r, t);
 }
 
-// Reverse step for t >= 1 (P symmetric): branch-free, the DMMA chain (W', V, Pbar_f) only needs G, the update is
-// recomputed from (a, P) concurrently, P_f = P - coef (P z^T)(P z^T)^T + eps I (see fwd_step).
-template <int KIND>
-__device__ __forceinline__ void bwd_step_sym(const KArgs<double>& G, const BwdConst& K, BwdState& S, const Frag& P,
-                                             const RVec& a_r, const CVec& a_c, double yv, double gcot, double* sc,
-                                             int lane) {
-    const int g = lane >> 2, t = lane & 3;
-    // ================= predict adjoint: products =================
-    Frag W, V, Pfb;
+constexpr int WS_TH = 0;                 // per-warp workspace of the SM backward variant (doubles)
+constexpr int WS_GS = WS_TH + MP * MP;
+constexpr int WS_ST = WS_GS + MP * MP;   // two trajectory stages of REC doubles
+constexpr int WS_TOTAL = WS_ST + 2 * REC;
+
+__device__ __forceinline__ void load_frag_smem(Frag& X, const double* base, int lane) {
+    const double2* src = reinterpret_cast<const double2*>(base);
 #pragma unroll
     for (int I = 0; I < 2; ++I)
 #pragma unroll
-        for (int J = 0; J < 2; ++J)
+        for (int J = 0; J < 2; ++J) {
+            const double2 d = src[(2 * I + J) * 32 + lane];
+            X.v[I][J][0] = d.x;
+            X.v[I][J][1] = d.y;
+        }
+}
+__device__ __forceinline__ void store_frag_smem(double* base, const Frag& X, int lane) {
+    double2* dst = reinterpret_cast<double2*>(base);
 #pragma unroll
-            for (int e = 0; e < 2; ++e) S.Gsum.v[I][J][e] += S.G.v[I][J][e];
+    for (int I = 0; I < 2; ++I)
+#pragma unroll
+        for (int J = 0; J < 2; ++J) dst[(2 * I + J) * 32 + lane] = make_double2(X.v[I][J][0], X.v[I][J][1]);
+}
+__device__ __forceinline__ void load_rec_smem(const double* base, Frag& P, RVec& a_r, CVec& a_c, int lane) {
+    const int g = lane >> 2, t = lane & 3;
+    load_frag_smem(P, base, lane);
+    const double2* src = reinterpret_cast<const double2*>(base);
+#pragma unroll
+    for (int J = 0; J < 2; ++J) {
+        const double2 d = src[128 + 4 * J + t];
+        a_c.v[J][0] = d.x;
+        a_c.v[J][1] = d.y;
+    }
+#pragma unroll
+    for (int I = 0; I < 2; ++I) a_r.v[I] = base[MP * MP + 8 * I + g];
+}
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+    unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(sa), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::: "memory"); }
+
+// Reverse step for t >= 1 (P symmetric): branch-free, the DMMA chain (W', V, Pbar_f) only needs G, the update is
+// recomputed from (a, P) concurrently, P_f = P - coef (P z^T)(P z^T)^T + eps I (see fwd_step).
+//
+// SM = true: the accumulators Tbar/2 and sum_t G_t live in shared memory (ws + WS_TH, ws + WS_GS, fragment order) and
+// the trajectory record of this step is read from the shared-memory stage `st` (filled by cp.async one step ahead),
+// which frees ~70 registers per thread for a third resident warp per scheduler.
+template <int KIND, bool SM>
+__device__ __forceinline__ void bwd_step_sym(const KArgs<double>& G, const BwdConst& K, BwdState& S, const Frag& Preg,
+                                             const RVec& a_reg, const CVec& ac_reg, const double* st, double* ws,
+                                             double yv, double gcot, double* sc, int lane) {
+    const int g = lane >> 2, t = lane & 3;
+    Frag P;
+    RVec a_r;
+    CVec a_c;
+    if (SM) {
+        load_rec_smem(st, P, a_r, a_c, lane);
+    } else {
+        P = Preg;
+        a_r = a_reg;
+        a_c = ac_reg;
+    }
+    // ================= predict adjoint: products =================
+    Frag W, V, Pfb;
+    if (SM) {
+        double2* gs = reinterpret_cast<double2*>(ws + WS_GS);
+#pragma unroll
+        for (int I = 0; I < 2; ++I)
+#pragma unroll
+            for (int J = 0; J < 2; ++J) {
+                double2 x = gs[(2 * I + J) * 32 + lane];
+                x.x += S.G.v[I][J][0];
+                x.y += S.G.v[I][J][1];
+                gs[(2 * I + J) * 32 + lane] = x;
+            }
+    } else {
+#pragma unroll
+        for (int I = 0; I < 2; ++I)
+#pragma unroll
+            for (int J = 0; J < 2; ++J)
+#pragma unroll
+                for (int e = 0; e < 2; ++e) S.Gsum.v[I][J][e] += S.G.v[I][J][e];
+    }
     mm_nt<false>(W, K.TTc, S.G);  // W' = T^T G
     transpose(V, W, sc, g, t);    // V = G T
     Pfb.v[0][0][0] = Pfb.v[0][0][1] = Pfb.v[0][1][0] = Pfb.v[0][1][1] = Pfb.v[1][1][0] = Pfb.v[1][1][1] = 0.0;
@@ -842,18 +912,25 @@ __device__ __forceinline__ void bwd_step_sym(const KArgs<double>& G, const BwdCo
             }
     }
     // ================= predict adjoint: T, c =================
-    mm_nt<true>(S.Th, V, Pf);  // Tbar/2 += (G T) P_f
+    {
+        Frag ThL;
+        if (SM) load_frag_smem(ThL, ws + WS_TH, lane);
+        Frag& Th = SM ? ThL : S.Th;
+        mm_nt<true>(Th, V, Pf);  // Tbar/2 += (G T) P_f
 #pragma unroll
-    for (int I = 0; I < 2; ++I) {
-        const double h = 0.5 * S.abar_r.v[I];  // Tbar += abar+ a_f^T
+        for (int I = 0; I < 2; ++I) {
+            const double h = 0.5 * S.abar_r.v[I];  // Tbar += abar+ a_f^T
 #pragma unroll
-        for (int J = 0; J < 2; ++J)
+            for (int J = 0; J < 2; ++J)
 #pragma unroll
-            for (int e = 0; e < 2; ++e) S.Th.v[I][J][e] = fma(h, af_c.v[J][e], S.Th.v[I][J][e]);
+                for (int e = 0; e < 2; ++e) Th.v[I][J][e] = fma(h, af_c.v[J][e], Th.v[I][J][e]);
+        }
+        if (SM) store_frag_smem(ws + WS_TH, ThL, lane);
     }
     const RVec afbar_r = mv(K.TTc, S.abar_c);  // T^T abar+
 #pragma unroll
     for (int I = 0; I < 2; ++I) S.gc_r.v[I] += S.abar_r.v[I];
+    if (SM) load_frag_smem(P, st, lane);  // re-read P instead of keeping it live across the products
     // ================= update adjoint =================
     if (KIND == K_UNI) {
         const double llbar = -0.5 * gcot;
@@ -939,14 +1016,15 @@ __device__ __forceinline__ void bwd_step_sym(const KArgs<double>& G, const BwdCo
     S.abar_c = row2col(S.abar_r, t);
 }
 
-template <int KIND>
-__global__ void __launch_bounds__(64) backward_kernel(KArgs<double> G) {
-    extern __shared__ double smem[];
+template <int KIND, bool SM>
+__global__ void __launch_bounds__(64, SM ? 6 : 1) backward_kernel(KArgs<double> G) {
+    extern __shared__ __align__(16) double smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int g = lane >> 2, t = lane & 3;
     const int b = blockIdx.x * (blockDim.x >> 5) + warp;
     if (b >= G.B) return;
-    double* sc = smem + warp * SCRATCH;
+    double* sc = smem + warp * (SCRATCH + (SM ? WS_TOTAL : 0));
+    double* ws = sc + SCRATCH;
     const int m = G.m, n = G.n;
 
     BwdConst K;
@@ -974,17 +1052,43 @@ __global__ void __launch_bounds__(64) backward_kernel(KArgs<double> G) {
     const double* yb = G.y_shared ? G.y : G.y + (size_t)b * n;
     const double* traj = G.traj + (size_t)b * n * REC;
     const double* cot = G.ll_cot ? G.ll_cot + (size_t)b * n : nullptr;
-    Frag P, Pn;
-    RVec a_r, an_r;
-    CVec a_c, an_c;
-    if (n > 1) load_rec(traj + (size_t)(n - 1) * REC, Pn, an_r, an_c, lane);
+    Frag P;
+    RVec a_r;
+    CVec a_c;
+    if (SM) {
+        store_frag_smem(ws + WS_TH, S.Th, lane);
+        store_frag_smem(ws + WS_GS, S.Gsum, lane);
+        auto prefetch = [&](int ts) {
+            const char* src = reinterpret_cast<const char*>(traj + (size_t)ts * REC);
+            char* dst = reinterpret_cast<char*>(ws + WS_ST + (ts & 1) * REC);
+            for (int q = lane; q < REC / 2; q += 32) cp_async16(dst + q * 16, src + q * 16);
+            cp_async_commit();
+        };
+        if (n > 1) prefetch(n - 1);
 #pragma unroll 1
-    for (int ts = n - 1; ts >= 1; --ts) {
-        P = Pn;
-        a_r = an_r;
-        a_c = an_c;
-        if (ts > 1) load_rec(traj + (size_t)(ts - 1) * REC, Pn, an_r, an_c, lane);  // prefetch one step ahead
-        bwd_step_sym<KIND>(G, K, S, P, a_r, a_c, yb[ts], cot ? cot[ts] : 1.0, sc, lane);
+        for (int ts = n - 1; ts >= 1; --ts) {
+            cp_async_wait_all();
+            __syncwarp();
+            if (ts > 1) prefetch(ts - 1);
+            bwd_step_sym<KIND, true>(G, K, S, P, a_r, a_c, ws + WS_ST + (ts & 1) * REC, ws, yb[ts],
+                                     cot ? cot[ts] : 1.0, sc, lane);
+        }
+        __syncwarp();
+        load_frag_smem(S.Th, ws + WS_TH, lane);
+        load_frag_smem(S.Gsum, ws + WS_GS, lane);
+    } else {
+        Frag Pn;
+        RVec an_r;
+        CVec an_c;
+        if (n > 1) load_rec(traj + (size_t)(n - 1) * REC, Pn, an_r, an_c, lane);
+#pragma unroll 1
+        for (int ts = n - 1; ts >= 1; --ts) {
+            P = Pn;
+            a_r = an_r;
+            a_c = an_c;
+            if (ts > 1) load_rec(traj + (size_t)(ts - 1) * REC, Pn, an_r, an_c, lane);  // prefetch one step ahead
+            bwd_step_sym<KIND, false>(G, K, S, P, a_r, a_c, nullptr, nullptr, yb[ts], cot ? cot[ts] : 1.0, sc, lane);
+        }
     }
     {
         const double* a0g = param_ptr(G.a0, G.shared_mask, BKF_PARAM_A0, b, (size_t)m);

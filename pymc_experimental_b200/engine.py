@@ -10,6 +10,7 @@ from __future__ import annotations
 
 import ctypes as C
 import os
+import weakref
 
 import numpy as np
 
@@ -31,7 +32,7 @@ JITTER_F64, JITTER_F32 = 1e-8, 1e-6
 ABI_SYMBOLS = (
     "bkf_version", "bkf_create", "bkf_destroy", "bkf_last_error", "bkf_set_stream", "bkf_launch_count",
     "bkf_last_path", "bkf_enable_timing", "bkf_reset_timing", "bkf_kernel_time_ms", "bkf_measure_fma_peak",
-    "bkf_filter_forward", "bkf_filter_logp_grad", "bkf_smooth", "bkf_filter_smooth",
+    "bkf_filter_forward", "bkf_filter_logp_grad", "bkf_smooth", "bkf_filter_smooth", "bkf_host_alloc", "bkf_host_free",
 )
 
 
@@ -77,6 +78,8 @@ def load_library():
     lib.bkf_reset_timing.argtypes = [vp]
     lib.bkf_kernel_time_ms.argtypes = [vp, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_longlong)]
     lib.bkf_measure_fma_peak.argtypes = [vp, C.c_int, C.POINTER(C.c_double)]
+    lib.bkf_host_alloc.argtypes = [C.c_size_t, C.POINTER(vp)]
+    lib.bkf_host_free.argtypes = [vp]
     pp = C.POINTER(BkfProblem)
     lib.bkf_filter_forward.argtypes = [vp, pp] + [vp] * 10 + [vp] * 7 + [vp]
     lib.bkf_filter_logp_grad.argtypes = [vp, pp] + [vp] * 10 + [vp] + [vp] + [vp] * 9 + [vp]
@@ -88,6 +91,57 @@ def load_library():
 
 def _is_torch(x):
     return type(x).__module__.startswith("torch")
+
+
+class _PinnedPool:
+    """Page-locked host blocks for call outputs (bkf_host_alloc), recycled when the NumPy arrays built on them die.
+
+    D2H copies into pageable ``np.empty`` arrays are staged by the driver at a fraction of the link rate; outputs
+    handed out by this pool are ordinary ndarrays (safe to keep: a block returns to the pool only after every view
+    of it has been garbage-collected)."""
+
+    GRAIN = 1 << 16
+    MAX_FREE_BYTES = 4 << 30
+
+    def __init__(self, lib):
+        self.lib = lib
+        self.free = {}
+        self.free_bytes = 0
+
+    def empty(self, shape, dtype):
+        nbytes = int(np.prod(shape, dtype=np.int64)) * np.dtype(dtype).itemsize
+        if nbytes < self.GRAIN:  # small outputs: pageable memory is fine
+            return np.empty(shape, dtype=dtype)
+        size = -(-nbytes // self.GRAIN) * self.GRAIN
+        blocks = self.free.get(size)
+        if blocks:
+            ptr = blocks.pop()
+            self.free_bytes -= size
+        else:
+            p = C.c_void_p()
+            if self.lib.bkf_host_alloc(size, C.byref(p)) != 0 or not p.value:
+                return np.empty(shape, dtype=dtype)
+            ptr = p.value
+        cbuf = (C.c_char * size).from_address(ptr)
+        weakref.finalize(cbuf, self._release, ptr, size)
+        return np.frombuffer(cbuf, dtype=dtype, count=nbytes // np.dtype(dtype).itemsize).reshape(shape)
+
+    def _release(self, ptr, size):
+        if self.free_bytes + size > self.MAX_FREE_BYTES:
+            self.lib.bkf_host_free(C.c_void_p(ptr))
+            return
+        self.free.setdefault(size, []).append(ptr)
+        self.free_bytes += size
+
+
+_pinned_pool = None
+
+
+def pinned_pool():
+    global _pinned_pool
+    if _pinned_pool is None:
+        _pinned_pool = _PinnedPool(load_library())
+    return _pinned_pool
 
 
 class _Buffers:
@@ -126,7 +180,7 @@ class _Buffers:
         if self.device:
             t = self.torch.empty(shape, dtype=self.tdtype, device=self.dev)
         else:
-            t = np.empty(shape, dtype=self.ndtype)
+            t = pinned_pool().empty(shape, self.ndtype)
         self.keep.append(t)
         return t
 
