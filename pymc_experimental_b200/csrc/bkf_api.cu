@@ -292,7 +292,8 @@ static int run_backward(bkf_handle* h, const KArgs<float>& g, const char** err) 
 // pinv of the generic kernel if any series was flagged ill-conditioned (costs one 4-byte readback).
 static int run_smoother(bkf_handle* h, const KArgs<double>& g, const char** err) {
     const double jitter0 = 1e-8;  // JITTER_DEFAULT (float64), kalman_smoother.py:117
-    if (sw::smoother_supported(g.m)) {
+    const bool use_tc = tc::smoother_supported(g.m);
+    if (use_tc || sw::smoother_supported(g.m)) {
         int rc = BKF_OK;
         int* flag = (int*)ensure(h, S_FLAG, sizeof(int), &rc);
         if (!flag) return rc;
@@ -300,14 +301,15 @@ static int run_smoother(bkf_handle* h, const KArgs<double>& g, const char** err)
         {
             KernelTimer kt(h, BKF_KERNEL_SMOOTHER);
             h->launches += 1;
-            rc = sw::launch_smoother_f64(g, jitter0, flag, h->stream, err);
+            rc = use_tc ? tc::launch_smoother_f64(g, jitter0, flag, h->stream, err)
+                        : sw::launch_smoother_f64(g, jitter0, flag, h->stream, err);
         }
         if (rc != BKF_OK) return rc;
         int host_flag = 0;
         cudaError_t e = cudaMemcpyAsync(&host_flag, flag, sizeof(int), cudaMemcpyDeviceToHost, h->stream);
         if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
         if (e != cudaSuccess) { *err = cudaGetErrorString(e); return BKF_ERR_CUDA; }
-        h->path = "subwarp_f64";
+        h->path = use_tc ? "dmma_f64" : "subwarp_f64";
         if (!host_flag) return BKF_OK;
         h->path = "generic_warp(smoother fallback)";
     }

@@ -24,6 +24,8 @@ namespace tc {  // FP64 tensor-core (DMMA) warp-per-series kernels, 9 <= m <= 16
 bool supported(int kind, int m, int p);
 size_t traj_record_elems();
 int launch_f64(const KArgs<double>& g, bool backward, cudaStream_t stream, const char** err);
+bool smoother_supported(int m);
+int launch_smoother_f64(const KArgs<double>& g, double jitter0, int* any_ill, cudaStream_t stream, const char** err);
 }  // namespace tc
 namespace tps {  // thread-per-series kernels, m <= 4, p = 1 (bkf_thread.cu)
 bool supported(int kind, int m, int p);

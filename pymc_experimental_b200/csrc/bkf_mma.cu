@@ -3,6 +3,7 @@
 #include <cstdlib>
 
 #include "bkf_mma.cuh"
+#include "bkf_mma_smooth.cuh"
 
 #include "bkf_launch.h"
 
@@ -56,6 +57,18 @@ int launch_f64(const KArgs<double>& g, bool backward, cudaStream_t stream, const
         else if (occ8) forward_kernel<K_STD, false, 8><<<grid, 32 * warps, smem, stream>>>(g);
         else forward_kernel<K_STD, false, 1><<<grid, 32 * warps, smem, stream>>>(g);
     }
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) { *err = cudaGetErrorString(e); return BKF_ERR_CUDA; }
+    return BKF_OK;
+}
+
+bool smoother_supported(int m) { return m >= 9 && m <= MP; }
+
+int launch_smoother_f64(const KArgs<double>& g, double jitter0, int* any_ill, cudaStream_t stream, const char** err) {
+    const int warps = 2;
+    const int grid = (g.B + warps - 1) / warps;
+    const size_t smem = (size_t)warps * SCRATCH * sizeof(double);
+    smoother_kernel<<<grid, 32 * warps, smem, stream>>>(g, jitter0, any_ill);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { *err = cudaGetErrorString(e); return BKF_ERR_CUDA; }
     return BKF_OK;

@@ -278,7 +278,7 @@ def test_filter_smooth_fused_call(eng):
         _close(sP[b], rP, 1e-8, "smoothed_covariances")
 
 
-@pytest.mark.parametrize("m", [5, 8, 11, 15, 16])
+@pytest.mark.parametrize("m", [5, 8, 9, 11, 13, 15, 16])
 def test_subwarp_smoother_matches_oracle(eng, m):
     from oracle import kalman_np as onp
     from pymc_experimental_b200 import synth
@@ -286,7 +286,7 @@ def test_subwarp_smoother_matches_oracle(eng, m):
     B, n = 7, 19
     cfg = synth.random_dense(B, n, m, 1, 3, seed=200 + m, missing=0.1)
     ll, sa, sP, status = eng.filter_smooth("standard", cfg["y"], *[cfg[k] for k in NAMES])
-    assert eng.last_path == "subwarp_f64"
+    assert eng.last_path == ("dmma_f64" if m >= 9 else "subwarp_f64")
     for b in range(B):
         outs = onp.kalman_filter("standard", cfg["y"][b], *[cfg[k][b] for k in NAMES])
         ra, rP = onp.kalman_smoother(cfg["T"][b], cfg["R"][b], cfg["Q"][b], outs[0], outs[3])
