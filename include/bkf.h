@@ -73,7 +73,12 @@ typedef struct bkf_problem {
     int m, p, r;           /* k_states, k_endog, k_posdef */
     int y_shared;          /* 1: y is [n,p] and shared by all series */
     unsigned shared_mask;  /* bit BKF_PARAM_x: parameter x has no batch axis */
-    unsigned tv_mask;      /* bit BKF_PARAM_x: parameter x carries a leading time axis (not supported yet) */
+    unsigned tv_mask;      /* bit BKF_PARAM_x: parameter x carries a time axis of length n right after the (optional)
+                              batch axis: c [B,n,m], d [B,n,p], T [B,n,m,m], Z [B,n,p,m], R [B,n,m,r], H [B,n,p,p],
+                              Q [B,n,r,r] (filters/utilities.py:8-47; never a0, P0).  Step t uses x[t]
+                              (kalman_filter.py:110-142); the smoother pairs filtered[t] with x[t+1]
+                              (kalman_smoother.py:84-92).  Gradients of time-varying
+                              parameters have the same time axis.  Standard / univariate filters and smoother. */
     double cov_jitter;     /* JITTER_DEFAULT: 1e-8 (f64) / 1e-6 (f32), utils/constants.py:20 */
     double missing_fill;   /* MISSING_FILL = -9999.0, utils/constants.py:19 */
 } bkf_problem;

@@ -277,7 +277,9 @@ def kalman_smoother(T, R, Q, filtered_states, filtered_covariances, cov_jitter=J
     sm_a[-1], sm_P[-1] = a_s, P_s
     for t in range(n - 2, -1, -1):
         a, P = filtered_states[t], filtered_covariances[t]
-        Tt, Rt, Qt = _at(T, t, 2), _at(R, t, 2), _at(Q, t, 2)
+        # time-varying T/R/Q: scan(go_backwards=True) reverses each sequence and then truncates to the shortest
+        # (filtered[:-1] has n-1 rows), so filtered[t] meets x[t+1] (kalman_smoother.py:84-92; DESIGN quirk Q9)
+        Tt, Rt, Qt = _at(T, t + 1, 2), _at(R, t + 1, 2), _at(Q, t + 1, 2)
         # predict, :121-126 (no state intercept, quirk Q8)
         a_hat = Tt @ a
         P_hat = stabilize(quad_form_sym(Tt, P) + quad_form_sym(Rt, Qt), cov_jitter)

@@ -6,7 +6,8 @@ Same formulas as ``oracle/kalman_np.py`` -- i.e. ``pymc_extras/statespace/filter
 written with torch ops so that ``torch.autograd`` yields d(sum_t ll_t)/d{a0,P0,c,d,T,Z,R,H,Q}: the quantity
 ``pytensor.grad`` derives through ``Scan.L_op`` for NUTS.  Every input may carry
 arbitrary leading batch dimensions (broadcast against each other), which makes this the gradient oracle for
-the batched CUDA engine and a multi-threaded CPU baseline.  Time-invariant matrices only.
+the batched CUDA engine and a multi-threaded CPU baseline.  ``time_varying`` names the inputs that carry a
+time axis right before their static dims (filters/utilities.py:8-47).
 
 Gradient conventions reproduced here (what autodiff of the reference formulas yields):
 * every matrix entry is an independent variable (no symmetrisation of dH, dQ, dP0);
@@ -177,8 +178,12 @@ def sqrt_step(y, a, Pc, c, d, T, Z, R, H, Q, fill, jitter):
 _STEP = {"standard": standard_step, "univariate": univariate_step, "cholesky": sqrt_step}
 
 
+_TV_ORDER = ("c", "d", "T", "Z", "R", "H", "Q")
+_TV_NDIM = {"c": 1, "d": 1, "T": 2, "Z": 2, "R": 2, "H": 2, "Q": 2}
+
+
 def kalman_filter(kind, data, a0, P0, c, d, T, Z, R, H, Q, missing_fill_value=None, cov_jitter=None,
-                  logp_only=False):
+                  logp_only=False, time_varying=()):
     """Batched filter.  ``data``: (..., n, p).  Returns the 7 outputs of ``BaseFilter.build_graph`` with the
     time axis at position -2/-3 (after any batch dims), or only ``loglike_obs`` (..., n) if ``logp_only``."""
     fill = MISSING_FILL if missing_fill_value is None else missing_fill_value
@@ -187,8 +192,16 @@ def kalman_filter(kind, data, a0, P0, c, d, T, Z, R, H, Q, missing_fill_value=No
     n = data.shape[-2]
     a, P = a0, P0
     outs = [[] for _ in range(7)]
+    vals = dict(zip(_TV_ORDER, (c, d, T, Z, R, H, Q)))
+
+    def at(name, t):  # time-varying inputs carry the time axis right before their static dims
+        x = vals[name]
+        if name not in time_varying:
+            return x
+        return x.select(-_TV_NDIM[name] - 1, t)
+
     for t in range(n):
-        res = step(data[..., t, :], a, P, c, d, T, Z, R, H, Q, fill, jitter)
+        res = step(data[..., t, :], a, P, *[at(k, t) for k in _TV_ORDER], fill, jitter)
         a, P = res[1], res[4]
         if logp_only:
             outs[6].append(res[6])

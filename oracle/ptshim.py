@@ -176,8 +176,13 @@ def _scan(fn, sequences=None, outputs_info=None, non_sequences=None, go_backward
     sequences = [s if isinstance(s, Var) else Var(_raw(s)) for s in (sequences or [])]
     non_sequences = list(non_sequences or [])
     n = min(s.shape[0] for s in sequences)
-    order = range(n - 1, -1, -1) if go_backwards else range(n)
-    # go_backwards iterates the (truncated-to-n) sequences from their end
+    # PyTensor's scan() reverses every sequence FIRST when go_backwards is set (nw_seq = nw_seq[::-1]) and only then
+    # levels them to the shortest length (scan_seqs = [seq[:actual_n_steps] ...], pytensor/scan/basic.py -- restated
+    # from memory, PyTensor is not installable here).  For sequences of equal length this is plain reverse iteration;
+    # for the smoother's unequal lengths (filtered[:-1] vs a time-varying T) it pairs filtered[t] with T[t+1].
+    if go_backwards:
+        sequences = [Var(torch.flip(s.v, dims=(0,))[:n]) for s in sequences]
+    order = range(n)
     rec_idx = [i for i, o in enumerate(outputs_info) if o is not None]
     carry = [outputs_info[i] for i in rec_idx]
     collected = [[] for _ in outputs_info]

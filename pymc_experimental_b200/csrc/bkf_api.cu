@@ -242,6 +242,10 @@ static int run_forward(bkf_handle* h, const KArgs<double>& g, const char** err) 
         h->path = "sqrt_cta";
         return sq::launch_forward<double>(g, h->stream, err);
     }
+    if (g.tv_mask) {  // time-varying matrices: the generic kernels stream them per step
+        h->path = "generic_warp";
+        return gen::launch_forward<double>(g, h->stream, err);
+    }
     if (tps::supported(g.kind, g.m, g.p)) {
         h->path = "thread_f64";
         return tps::launch_any<double>(g, false, h->stream, err);
@@ -264,7 +268,7 @@ static int run_forward(bkf_handle* h, const KArgs<float>& g, const char** err) {
         h->path = "sqrt_cta";
         return sq::launch_forward<float>(g, h->stream, err);
     }
-    if (tps::supported(g.kind, g.m, g.p)) {
+    if (!g.tv_mask && tps::supported(g.kind, g.m, g.p)) {
         h->path = "thread_f32";
         return tps::launch_any<float>(g, false, h->stream, err);
     }
@@ -275,6 +279,7 @@ static int run_backward(bkf_handle* h, const KArgs<double>& g, const char** err)
     KernelTimer kt(h, BKF_KERNEL_BACKWARD);
     h->launches += 1;
     if (g.kind == BKF_CHOLESKY) return sq::launch_backward<double>(g, h->stream, err);
+    if (g.tv_mask) return gen::launch_backward<double>(g, h->stream, err);
     if (tps::supported(g.kind, g.m, g.p)) return tps::launch_any<double>(g, true, h->stream, err);
     if (tc::supported(g.kind, g.m, g.p)) return tc::launch_f64(g, true, h->stream, err);
     if (sw::supported(g.kind, g.m, g.p)) return sw::launch_f64(g, true, h->stream, err);
@@ -284,7 +289,7 @@ static int run_backward(bkf_handle* h, const KArgs<float>& g, const char** err) 
     KernelTimer kt(h, BKF_KERNEL_BACKWARD);
     h->launches += 1;
     if (g.kind == BKF_CHOLESKY) return sq::launch_backward<float>(g, h->stream, err);
-    if (tps::supported(g.kind, g.m, g.p)) return tps::launch_any<float>(g, true, h->stream, err);
+    if (!g.tv_mask && tps::supported(g.kind, g.m, g.p)) return tps::launch_any<float>(g, true, h->stream, err);
     return gen::launch_backward<float>(g, h->stream, err);
 }
 
@@ -293,7 +298,7 @@ static int run_backward(bkf_handle* h, const KArgs<float>& g, const char** err) 
 static int run_smoother(bkf_handle* h, const KArgs<double>& g, const char** err) {
     const double jitter0 = 1e-8;  // JITTER_DEFAULT (float64), kalman_smoother.py:117
     const bool use_tc = tc::smoother_supported(g.m);
-    if (use_tc || sw::smoother_supported(g.m)) {
+    if (!g.tv_mask && (use_tc || sw::smoother_supported(g.m))) {
         int rc = BKF_OK;
         int* flag = (int*)ensure(h, S_FLAG, sizeof(int), &rc);
         if (!flag) return rc;
@@ -323,18 +328,19 @@ static int run_smoother(bkf_handle* h, const KArgs<float>& g, const char** err) 
     return gen::launch_smoother<float>(g, h->stream, err);
 }
 
+// elements of parameter `which` for ONE series: the matrix itself, times n when it carries a time axis
 static size_t param_elems(const bkf_problem* P, int which) {
-    size_t m = P->m, p = P->p, r = P->r;
+    size_t m = P->m, p = P->p, r = P->r, e = 0;
     switch (which) {
-        case BKF_PARAM_A0: case BKF_PARAM_C: return m;
-        case BKF_PARAM_P0: case BKF_PARAM_T: return m * m;
-        case BKF_PARAM_D: return p;
-        case BKF_PARAM_Z: return p * m;
-        case BKF_PARAM_R: return m * r;
-        case BKF_PARAM_H: return p * p;
-        case BKF_PARAM_Q: return r * r;
+        case BKF_PARAM_A0: case BKF_PARAM_C: e = m; break;
+        case BKF_PARAM_P0: case BKF_PARAM_T: e = m * m; break;
+        case BKF_PARAM_D: e = p; break;
+        case BKF_PARAM_Z: e = p * m; break;
+        case BKF_PARAM_R: e = m * r; break;
+        case BKF_PARAM_H: e = p * p; break;
+        case BKF_PARAM_Q: e = r * r; break;
     }
-    return 0;
+    return ((P->tv_mask >> which) & 1u) ? e * (size_t)P->n : e;
 }
 
 static int validate(bkf_handle* h, const bkf_problem* P, bool need_obs) {
@@ -345,8 +351,10 @@ static int validate(bkf_handle* h, const bkf_problem* P, bool need_obs) {
     if (P->mem != BKF_MEM_HOST && P->mem != BKF_MEM_DEVICE) return fail(h, BKF_ERR_ARG, "unknown memory space");
     if (P->B < 0 || P->n < 1 || P->m < 1 || P->r < 1 || (need_obs && P->p < 1))
         return fail(h, BKF_ERR_ARG, "non-positive dimension");
-    if (P->tv_mask != 0)
-        return fail(h, BKF_ERR_UNSUPPORTED, "time-varying state-space matrices are not supported yet");
+    if (P->tv_mask & ((1u << BKF_PARAM_A0) | (1u << BKF_PARAM_P0)))
+        return fail(h, BKF_ERR_ARG, "a0 and P0 are never time-varying (utils/constants.py NEVER_TIME_VARYING)");
+    if (P->tv_mask != 0 && P->kind == BKF_CHOLESKY)
+        return fail(h, BKF_ERR_UNSUPPORTED, "time-varying matrices are not supported by the square-root filter kernels yet");
     cudaError_t e = cudaSetDevice(h->device);
     if (e != cudaSuccess) return cuda_fail(h, e, "cudaSetDevice");
     return BKF_OK;
@@ -397,6 +405,7 @@ static void fill_inputs(bkf_handle* h, const bkf_problem* P, KArgs<R>& g, const 
     std::memset(&g, 0, sizeof(g));
     g.kind = P->kind; g.B = P->B; g.n = P->n; g.m = P->m; g.p = P->p; g.r = P->r; g.y_shared = P->y_shared;
     g.shared_mask = P->shared_mask;
+    g.tv_mask = P->tv_mask;
     g.jitter = (R)P->cov_jitter;
     g.fill = (R)P->missing_fill;
     size_t B = P->B;
@@ -482,8 +491,8 @@ static int logp_grad_impl(bkf_handle* h, const bkf_problem* P, const void* y, co
         *gdst[i] = stage_out<R>(h, P, S_GA0 + i, grads[i], B * param_elems(P, i), &rc);
     if (want_grad) {
         // the trajectory layout is private to a kernel family: dense [a | P] records, or DMMA fragment records
-        const bool frag = sizeof(R) == 8 && P->kind != BKF_CHOLESKY && !tps::supported(P->kind, P->m, P->p) &&
-                          tc::supported(P->kind, P->m, P->p);
+        const bool frag = sizeof(R) == 8 && P->kind != BKF_CHOLESKY && !P->tv_mask &&
+                          !tps::supported(P->kind, P->m, P->p) && tc::supported(P->kind, P->m, P->p);
         const size_t rec = frag ? tc::traj_record_elems() : m + m * m;
         g.traj = (R*)ensure(h, S_TRAJ, B * n * rec * sizeof(R), &rc);
     }

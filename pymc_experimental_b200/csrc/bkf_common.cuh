@@ -21,6 +21,7 @@ template <typename R>
 struct KArgs {
     int kind, B, n, m, p, r, y_shared;
     unsigned shared_mask;
+    unsigned tv_mask;  // bit BKF_PARAM_x: parameter x carries a time axis ([B, n, ...] or [n, ...] when shared)
     R jitter, fill;
     // inputs
     const R *y, *a0, *P0, *c, *d, *T, *Z, *Rm, *H, *Q;
@@ -40,6 +41,15 @@ struct KArgs {
 template <typename R>
 __device__ __forceinline__ const R* param_ptr(const R* base, unsigned shared_mask, int which, int b, size_t sz) {
     return (shared_mask >> which) & 1u ? base : base + (size_t)b * sz;
+}
+
+// Pointer to parameter `which` of series b at time step t (t is ignored for time-invariant parameters).
+template <typename R>
+__device__ __forceinline__ const R* param_ptr_t(const R* base, unsigned shared_mask, unsigned tv_mask, int which, int b,
+                                                int t, int n, size_t sz) {
+    const bool tv = (tv_mask >> which) & 1u, sh = (shared_mask >> which) & 1u;
+    const size_t rec = (sh ? 0 : (size_t)b) * (tv ? (size_t)n : 1) + (tv ? (size_t)t : 0);
+    return base + rec * sz;
 }
 
 __device__ __forceinline__ double warp_sum(double v) {

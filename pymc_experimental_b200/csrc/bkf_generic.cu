@@ -173,18 +173,24 @@ __device__ void rqr_sym(R* dst, R* tmp, const R* __restrict__ Rg, const R* __res
     sym_into<R>(dst, tmp, nullptr, R(0), m, lane);
 }
 
-// Load T, Z, H, c, d and RQR = sym(R Q R^T) (kalman_filter.py:408, second term) for series b.
+// Load T, Z, H, c, d and RQR = sym(R Q R^T) (kalman_filter.py:408, second term) for series b at step t.
+// all = true loads everything (first step of a sweep); otherwise only the time-varying parameters are refreshed
+// (kalman_filter.py:110-142: the scan hands matrix[t] of every sequence parameter to kalman_step).
 template <typename R>
-__device__ void load_params(const KArgs<R>& g, Arena<R>& A, int b, int lane) {
-    const int m = g.m, p = g.p, r = g.r;
-    wcopy(A.T, param_ptr(g.T, g.shared_mask, BKF_PARAM_T, b, (size_t)m * m), m * m, lane);
-    wcopy(A.Z, param_ptr(g.Z, g.shared_mask, BKF_PARAM_Z, b, (size_t)p * m), p * m, lane);
-    wcopy(A.H, param_ptr(g.H, g.shared_mask, BKF_PARAM_H, b, (size_t)p * p), p * p, lane);
-    wcopy(A.c, param_ptr(g.c, g.shared_mask, BKF_PARAM_C, b, (size_t)m), m, lane);
-    wcopy(A.d, param_ptr(g.d, g.shared_mask, BKF_PARAM_D, b, (size_t)p), p, lane);
-    const R* Rg = param_ptr(g.Rm, g.shared_mask, BKF_PARAM_R, b, (size_t)m * r);
-    const R* Qg = param_ptr(g.Q, g.shared_mask, BKF_PARAM_Q, b, (size_t)r * r);
-    rqr_sym(A.RQR, A.Y, Rg, Qg, m, r, lane);
+__device__ void load_params(const KArgs<R>& g, Arena<R>& A, int b, int t, bool all, int lane) {
+    const int m = g.m, p = g.p, r = g.r, n = g.n;
+    const unsigned tv = g.tv_mask;
+    auto at = [&](const R* base, int which, size_t sz) {
+        return param_ptr_t(base, g.shared_mask, tv, which, b, t, n, sz);
+    };
+    auto need = [&](int which) { return all || ((tv >> which) & 1u); };
+    if (need(BKF_PARAM_T)) wcopy(A.T, at(g.T, BKF_PARAM_T, (size_t)m * m), m * m, lane);
+    if (need(BKF_PARAM_Z)) wcopy(A.Z, at(g.Z, BKF_PARAM_Z, (size_t)p * m), p * m, lane);
+    if (need(BKF_PARAM_H)) wcopy(A.H, at(g.H, BKF_PARAM_H, (size_t)p * p), p * p, lane);
+    if (need(BKF_PARAM_C)) wcopy(A.c, at(g.c, BKF_PARAM_C, (size_t)m), m, lane);
+    if (need(BKF_PARAM_D)) wcopy(A.d, at(g.d, BKF_PARAM_D, (size_t)p), p, lane);
+    if (need(BKF_PARAM_R) || need(BKF_PARAM_Q))
+        rqr_sym(A.RQR, A.Y, at(g.Rm, BKF_PARAM_R, (size_t)m * r), at(g.Q, BKF_PARAM_Q, (size_t)r * r), m, r, lane);
 }
 
 // a+ = T af + c ; P+ = sym(T Pf T^T) + RQR         (kalman_filter.py:407-408).  Leaves X = T Pf.
@@ -357,7 +363,6 @@ __global__ void forward_kernel(KArgs<R> g, int wpc, size_t arena) {
     const int po = (g.kind == BKF_UNIVARIATE) ? 1 : p;
     Arena<R> A;
     carve(A, smem + (size_t)warp * arena, m, p, g.r, false);
-    load_params(g, A, b, lane);
     wcopy(A.a, param_ptr(g.a0, g.shared_mask, BKF_PARAM_A0, b, (size_t)m), m, lane);
     wcopy(A.P, param_ptr(g.P0, g.shared_mask, BKF_PARAM_P0, b, (size_t)m * m), m * m, lane);
     const R* yb = g.y_shared ? g.y : g.y + (size_t)b * n * p;
@@ -366,6 +371,7 @@ __global__ void forward_kernel(KArgs<R> g, int wpc, size_t arena) {
     int st = 0;
     for (int t = 0; t < n; ++t) {
         const size_t bt = (size_t)b * n + t;
+        if (t == 0 || g.tv_mask) load_params(g, A, b, t, t == 0, lane);
         if (g.traj) {
             wcopy(g.traj + bt * tstride, A.a, m, lane);
             wcopy(g.traj + bt * tstride + m, A.P, m * m, lane);
@@ -408,7 +414,15 @@ __global__ void backward_kernel(KArgs<R> g, int wpc, size_t arena) {
     const int m = g.m, p = g.p, r = g.r, n = g.n;
     Arena<R> A;
     carve(A, smem + (size_t)warp * arena, m, p, r, true);
-    load_params(g, A, b, lane);
+    const unsigned tv = g.tv_mask;
+    const bool tvRQ = ((tv >> BKF_PARAM_R) | (tv >> BKF_PARAM_Q)) & 1u;
+    auto is_tv = [&](int which) { return ((tv >> which) & 1u) != 0; };
+    // gradient of a time-varying parameter has a time axis: element offset of (b, t) in units of one parameter
+    auto grec = [&](int which, int t) { return is_tv(which) ? (size_t)b * n + t : (size_t)b; };
+    if (tvRQ) {  // accumulated in place (one lane owns each element; the sweep over t is sequential)
+        if (g.g_R && !is_tv(BKF_PARAM_R)) wzero(g.g_R + (size_t)b * m * r, m * r, lane);
+        if (g.g_Q && !is_tv(BKF_PARAM_Q)) wzero(g.g_Q + (size_t)b * r * r, r * r, lane);
+    }
     wzero(A.abar, m, lane); wzero(A.Pbar, m * m, lane); wzero(A.gT, m * m, lane); wzero(A.Gsum, m * m, lane);
     wzero(A.gZ, p * m, lane); wzero(A.gH, p * p, lane); wzero(A.gc, m, lane); wzero(A.gd, p, lane);
     const R* yb = g.y_shared ? g.y : g.y + (size_t)b * n * p;
@@ -416,6 +430,7 @@ __global__ void backward_kernel(KArgs<R> g, int wpc, size_t arena) {
     for (int t = n - 1; t >= 0; --t) {
         const size_t bt = (size_t)b * n + t;
         const R gcot = g.ll_cot ? g.ll_cot[bt] : R(1);
+        if (t == n - 1 || tv) load_params(g, A, b, t, t == n - 1, lane);
         wcopy(A.a, g.traj + bt * tstride, m, lane);
         wcopy(A.P, g.traj + bt * tstride + m, m * m, lane);
         bool flag = false, ok = true;
@@ -429,6 +444,38 @@ __global__ void backward_kernel(KArgs<R> g, int wpc, size_t arena) {
             A.Y[idx] = A.Pf[idx] + A.Pf[(idx % m) * m + idx / m];
         }
         __syncwarp();
+        if (tvRQ) {
+            // R or Q varies in time: Rbar_t = G_t R_t (Q_t + Q_t^T), Qbar_t = R_t^T G_t R_t, per step
+            const R* Rg = param_ptr_t(g.Rm, g.shared_mask, tv, BKF_PARAM_R, b, t, n, (size_t)m * r);
+            const R* Qg = param_ptr_t(g.Q, g.shared_mask, tv, BKF_PARAM_Q, b, t, n, (size_t)r * r);
+            if (g.g_R) {
+                R* dst = g.g_R + grec(BKF_PARAM_R, t) * m * r;
+                for (int idx = lane; idx < m * r; idx += 32) {
+                    int i = idx / r, j = idx - i * r;
+                    R acc = 0;
+                    for (int k = 0; k < r; ++k) {
+                        R gr = 0;
+                        for (int l = 0; l < m; ++l) gr = fma(A.G[i * m + l], Rg[l * r + k], gr);
+                        acc = fma(gr, Qg[k * r + j] + Qg[j * r + k], acc);
+                    }
+                    dst[idx] = is_tv(BKF_PARAM_R) ? acc : dst[idx] + acc;
+                }
+            }
+            if (g.g_Q) {
+                R* dst = g.g_Q + grec(BKF_PARAM_Q, t) * r * r;
+                for (int idx = lane; idx < r * r; idx += 32) {
+                    int i = idx / r, j = idx - i * r;
+                    R acc = 0;
+                    for (int k = 0; k < m; ++k) {
+                        R gr = 0;
+                        for (int l = 0; l < m; ++l) gr = fma(A.G[k * m + l], Rg[l * r + j], gr);
+                        acc = fma(Rg[k * r + i], gr, acc);
+                    }
+                    dst[idx] = is_tv(BKF_PARAM_Q) ? acc : dst[idx] + acc;
+                }
+            }
+            __syncwarp();
+        }
         mm<SET>(A.X, A.T, m, 1, A.Y, m, 1, m, m, m, lane);
         mm<ADD>(A.gT, A.G, m, 1, A.X, m, 1, m, m, m, lane);
         for (int idx = lane; idx < m * m; idx += 32) A.gT[idx] = fma(A.abar[idx / m], A.af[idx % m], A.gT[idx]);
@@ -545,13 +592,28 @@ __global__ void backward_kernel(KArgs<R> g, int wpc, size_t arena) {
                 __syncwarp();
             }
         }
+        if (tv) {  // time-varying parameters: this step's contribution IS the gradient of x[t]
+            auto flush = [&](int which, R* dst, R* acc, size_t sz) {
+                if (!is_tv(which)) return;
+                if (dst) wcopy(dst + ((size_t)b * n + t) * sz, acc, (int)sz, lane);
+                wzero(acc, (int)sz, lane);
+            };
+            flush(BKF_PARAM_T, g.g_T, A.gT, (size_t)m * m);
+            flush(BKF_PARAM_C, g.g_c, A.gc, m);
+            flush(BKF_PARAM_Z, g.g_Z, A.gZ, (size_t)p * m);
+            flush(BKF_PARAM_H, g.g_H, A.gH, (size_t)p * p);
+            flush(BKF_PARAM_D, g.g_d, A.gd, p);
+        }
     }
     // ---------------- write gradients ----------------
-    auto put = [&](R* dst, const R* src, size_t sz) {
-        if (dst) wcopy(dst + (size_t)b * sz, src, (int)sz, lane);
+    auto put = [&](int which, R* dst, const R* src, size_t sz) {
+        if (dst && !is_tv(which)) wcopy(dst + (size_t)b * sz, src, (int)sz, lane);
     };
-    put(g.g_a0, A.abar, m); put(g.g_P0, A.Pbar, (size_t)m * m); put(g.g_c, A.gc, m); put(g.g_d, A.gd, p);
-    put(g.g_T, A.gT, (size_t)m * m); put(g.g_Z, A.gZ, (size_t)p * m); put(g.g_H, A.gH, (size_t)p * p);
+    put(BKF_PARAM_A0, g.g_a0, A.abar, m); put(BKF_PARAM_P0, g.g_P0, A.Pbar, (size_t)m * m);
+    put(BKF_PARAM_C, g.g_c, A.gc, m); put(BKF_PARAM_D, g.g_d, A.gd, p);
+    put(BKF_PARAM_T, g.g_T, A.gT, (size_t)m * m); put(BKF_PARAM_Z, g.g_Z, A.gZ, (size_t)p * m);
+    put(BKF_PARAM_H, g.g_H, A.gH, (size_t)p * p);
+    if (tvRQ) return;  // Rbar, Qbar were produced step by step
     // Rbar = Gsum R (Q + Q^T) ; Qbar = R^T Gsum R      (sym(R Q R^T) is time-invariant: sum the cotangents first)
     const R* Rg = param_ptr(g.Rm, g.shared_mask, BKF_PARAM_R, b, (size_t)m * r);
     const R* Qg = param_ptr(g.Q, g.shared_mask, BKF_PARAM_Q, b, (size_t)r * r);
@@ -647,10 +709,18 @@ __global__ void smoother_kernel(KArgs<R> g, int wpc, size_t arena, R jitter0) {
     auto take = [&](size_t k) { R* q = s; s += k; return q; };
     R *T = take(mm_), *RQR = take(mm_), *P = take(mm_), *Ps = take(mm_), *Ph = take(mm_), *X = take(mm_),
       *Y = take(mm_), *V = take(mm_), *G = take(mm_), *a = take(m), *as = take(m), *ah = take(m), *lam = take(m);
-    wcopy(T, param_ptr(g.T, g.shared_mask, BKF_PARAM_T, b, mm_), m * m, lane);
-    const R* Rg = param_ptr(g.Rm, g.shared_mask, BKF_PARAM_R, b, (size_t)m * r);
-    const R* Qg = param_ptr(g.Q, g.shared_mask, BKF_PARAM_Q, b, (size_t)r * r);
-    rqr_sym(RQR, Y, Rg, Qg, m, r, lane);
+    // Time-varying T, R, Q: the reference's scan runs go_backwards over sequences of unequal length
+    // (filtered[:-1] has n-1 rows, T has n): PyTensor reverses each sequence and then truncates to the shortest, so
+    // the smoother step of filtered index t sees T[t+1], R[t+1], Q[t+1] (kalman_smoother.py:84-92; DESIGN quirk Q9).
+    const unsigned tv = g.tv_mask;
+    auto load_trq = [&](int t, bool all) {
+        if (all || ((tv >> BKF_PARAM_T) & 1u))
+            wcopy(T, param_ptr_t(g.T, g.shared_mask, tv, BKF_PARAM_T, b, t, n, mm_), m * m, lane);
+        if (all || (((tv >> BKF_PARAM_R) | (tv >> BKF_PARAM_Q)) & 1u))
+            rqr_sym(RQR, Y, param_ptr_t(g.Rm, g.shared_mask, tv, BKF_PARAM_R, b, t, n, (size_t)m * r),
+                    param_ptr_t(g.Q, g.shared_mask, tv, BKF_PARAM_Q, b, t, n, (size_t)r * r), m, r, lane);
+    };
+    load_trq(n - 1, true);
     const R* fa = g.sm_filt_a + (size_t)b * n * m;
     const R* fP = g.sm_filt_P + (size_t)b * n * mm_;
     R* oa = g.sm_a ? g.sm_a + (size_t)b * n * m : nullptr;
@@ -661,6 +731,7 @@ __global__ void smoother_kernel(KArgs<R> g, int wpc, size_t arena, R jitter0) {
     if (oP) wcopy(oP + (size_t)(n - 1) * mm_, Ps, m * m, lane);
     int st = 0;
     for (int t = n - 2; t >= 0; --t) {
+        if (tv && t != n - 2) load_trq(t + 1, false);
         wcopy(a, fa + (size_t)t * m, m, lane);
         wcopy(P, fP + (size_t)t * mm_, m * m, lane);
         mv<SET>(ah, T, m, 1, a, m, m, lane);  // no state intercept (:122, quirk Q8)

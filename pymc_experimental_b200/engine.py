@@ -269,7 +269,7 @@ class KalmanEngine:
             raise BkfError(f"libbkf error {rc}: {self.lib.bkf_last_error(self.h).decode()}")
 
     # ------------------------------------------------------------------------------------------------
-    def _problem(self, kind, bufs, y, params, B, cov_jitter, missing_fill_value):
+    def _problem(self, kind, bufs, y, params, B, cov_jitter, missing_fill_value, time_varying=()):
         """Shape bookkeeping: returns (BkfProblem, y, [nine parameter arrays])."""
         k = KINDS[kind] if isinstance(kind, str) else int(kind)
         R = params["R"]
@@ -277,19 +277,26 @@ class KalmanEngine:
         m, r = int(R.shape[-2]), int(R.shape[-1])
         p = int(Z.shape[-2])
         n = int(y.shape[-2])
-        shared_mask = 0
+        shared_mask, tv_mask = 0, 0
         arrs = []
         for i, name in enumerate(PARAM_NAMES):
             x = params[name]
-            nd = _STATIC_NDIM[name]
+            tv = name in time_varying
+            if tv and name in ("a0", "P0"):
+                raise BkfError(f"{name} is never time-varying")
+            nd = _STATIC_NDIM[name] + int(tv)
+            if tv:
+                tv_mask |= 1 << i
             if x.ndim == nd:
                 shared_mask |= 1 << i
             elif x.ndim == nd + 1:
                 if x.shape[0] != B:
                     raise BkfError(f"{name}: leading batch dimension {x.shape[0]} != {B}")
             else:
-                raise BkfError(f"{name}: expected {nd} (shared) or {nd + 1} (batched) dims, got {x.ndim}; "
-                               "time-varying matrices are not supported yet")
+                raise BkfError(f"{name}: expected {nd} (shared) or {nd + 1} (batched) dims, got {x.ndim}"
+                               + ("" if tv else "; pass time_varying=(...) for matrices with a time axis"))
+            if tv and x.shape[-_STATIC_NDIM[name] - 1] != n:
+                raise BkfError(f"{name}: time axis has {x.shape[-_STATIC_NDIM[name] - 1]} steps, data has {n}")
             arrs.append(bufs.inp(x))
         y_shared = int(y.ndim == 2)
         if y.ndim == 3 and y.shape[0] != B:
@@ -299,20 +306,20 @@ class KalmanEngine:
         default_jitter = JITTER_F64 if bufs.code == F64 else JITTER_F32
         prob = BkfProblem(
             kind=k, dtype=bufs.code, mem=MEM_DEVICE if bufs.device else MEM_HOST, B=B, n=n, m=m, p=p, r=r,
-            y_shared=y_shared, shared_mask=shared_mask, tv_mask=0,
+            y_shared=y_shared, shared_mask=shared_mask, tv_mask=tv_mask,
             cov_jitter=default_jitter if cov_jitter is None else float(cov_jitter),
             missing_fill=MISSING_FILL if missing_fill_value is None else float(missing_fill_value),
         )
         return prob, bufs.inp(y), arrs
 
     @staticmethod
-    def _batch_size(y, params):
+    def _batch_size(y, params, time_varying=()):
         B = None
         if y.ndim == 3:
             B = y.shape[0]
         for name in PARAM_NAMES:
             x = params[name]
-            if x.ndim == _STATIC_NDIM[name] + 1:
+            if x.ndim == _STATIC_NDIM[name] + 1 + int(name in time_varying):
                 if B is not None and x.shape[0] != B:
                     raise BkfError(f"inconsistent batch sizes ({B} vs {x.shape[0]} for {name})")
                 B = x.shape[0]
@@ -321,17 +328,21 @@ class KalmanEngine:
     # ------------------------------------------------------------------------------------------------
     def filter(self, kind, y, a0, P0, c, d, T, Z, R, H, Q, cov_jitter=None, missing_fill_value=None,
                outputs=("filtered_states", "predicted_states", "observed_states", "filtered_covariances",
-                        "predicted_covariances", "observed_covariances", "loglike_obs"), dtype=None):
+                        "predicted_covariances", "observed_covariances", "loglike_obs"), dtype=None,
+               time_varying=()):
         """Batched ``BaseFilter.build_graph`` (kalman_filter.py:144-308).  Returns a dict of the requested
-        outputs plus ``status``; unbatched inputs (no leading B anywhere) return unbatched outputs."""
+        outputs plus ``status``; unbatched inputs (no leading B anywhere) return unbatched outputs.
+
+        ``time_varying``: names among c, d, T, Z, R, H, Q that carry a time axis of length n right after the optional
+        batch axis (filters/utilities.py:8-47); step t then uses x[t] (standard and univariate filters)."""
         params = dict(zip(PARAM_NAMES, (a0, P0, c, d, T, Z, R, H, Q)))
         bufs = _Buffers([y, *params.values()], dtype)
         params = {k_: (v if _is_torch(v) else np.asarray(v)) for k_, v in params.items()}
         y = y if _is_torch(y) else np.asarray(y)
-        B = self._batch_size(y, params)
+        B = self._batch_size(y, params, time_varying)
         squeeze = B is None
         B = 1 if squeeze else int(B)
-        prob, yb, arrs = self._problem(kind, bufs, y, params, B, cov_jitter, missing_fill_value)
+        prob, yb, arrs = self._problem(kind, bufs, y, params, B, cov_jitter, missing_fill_value, time_varying)
         n, m, p = prob.n, prob.m, prob.p
         po = 1 if prob.kind == UNIVARIATE else p
         shapes = {
@@ -368,7 +379,7 @@ class KalmanEngine:
         return layout, off
 
     def logp_grad(self, kind, y, a0, P0, c, d, T, Z, R, H, Q, ll_cotangent=None, cov_jitter=None,
-                  missing_fill_value=None, grads=PARAM_NAMES, dtype=None, packed_out=None):
+                  missing_fill_value=None, grads=PARAM_NAMES, dtype=None, packed_out=None, time_varying=()):
         """logp[b] = sum_t loglike_obs[b,t] and d(sum_t cot*ll)/d{a0..Q} (reverse-mode adjoint kernels).
 
         ``packed_out``: optional flat preallocated buffer (see :meth:`packed_layout`); logp and the gradients
@@ -377,13 +388,17 @@ class KalmanEngine:
         bufs = _Buffers([y, *params.values()], dtype)
         params = {k_: (v if _is_torch(v) else np.asarray(v)) for k_, v in params.items()}
         y = y if _is_torch(y) else np.asarray(y)
-        B = self._batch_size(y, params)
+        B = self._batch_size(y, params, time_varying)
         squeeze = B is None
         B = 1 if squeeze else int(B)
-        prob, yb, arrs = self._problem(kind, bufs, y, params, B, cov_jitter, missing_fill_value)
+        prob, yb, arrs = self._problem(kind, bufs, y, params, B, cov_jitter, missing_fill_value, time_varying)
         n, m, p, r = prob.n, prob.m, prob.p, prob.r
         gshape = {"a0": (B, m), "P0": (B, m, m), "c": (B, m), "d": (B, p), "T": (B, m, m), "Z": (B, p, m),
                   "R": (B, m, r), "H": (B, p, p), "Q": (B, r, r)}
+        for k_ in time_varying:  # gradients of time-varying parameters keep the time axis
+            gshape[k_] = (B, n) + gshape[k_][1:]
+        if packed_out is not None and time_varying:
+            raise BkfError("packed_out is laid out for time-invariant parameters")
         if packed_out is not None:
             layout, total = self.packed_layout(B, m, p, r)
             flat = packed_out.reshape(-1)
@@ -412,8 +427,9 @@ class KalmanEngine:
             return logp[0], {k_: v[0] for k_, v in g.items()}, status[0]
         return logp, g, status
 
-    def smooth(self, T, R, Q, filtered_states, filtered_covariances, cov_jitter=None, dtype=None):
-        """Batched ``KalmanSmoother.build_graph`` (kalman_smoother.py:66-105)."""
+    def smooth(self, T, R, Q, filtered_states, filtered_covariances, cov_jitter=None, dtype=None, time_varying=()):
+        """Batched ``KalmanSmoother.build_graph`` (kalman_smoother.py:66-105).  Time-varying T / R / Q
+        ([B,] n, ...) follow the reference's pairing filtered[t] <-> x[t+1]."""
         bufs = _Buffers([T, R, Q, filtered_states, filtered_covariances], dtype)
         conv = lambda v: v if _is_torch(v) else np.asarray(v)
         T, R, Q, fa, fP = map(conv, (T, R, Q, filtered_states, filtered_covariances))
@@ -422,15 +438,20 @@ class KalmanEngine:
             fa, fP = fa[None], fP[None]
         B, n, m = (int(s) for s in fa.shape)
         r = int(R.shape[-1])
-        shared_mask = 0
+        shared_mask, tv_mask = 0, 0
         for name, x, bit in (("T", T, 4), ("R", R, 6), ("Q", Q, 8)):
-            if x.ndim == 2:
+            tv = name in time_varying
+            if tv:
+                tv_mask |= 1 << bit
+                if x.shape[-3] != n:
+                    raise BkfError(f"{name}: time axis has {x.shape[-3]} steps, the filtered trajectory has {n}")
+            if x.ndim == 2 + int(tv):
                 shared_mask |= 1 << bit
             elif x.shape[0] != B:
                 raise BkfError(f"{name}: leading batch dimension {x.shape[0]} != {B}")
         default_jitter = JITTER_F64 if bufs.code == F64 else JITTER_F32
         prob = BkfProblem(kind=STANDARD, dtype=bufs.code, mem=MEM_DEVICE if bufs.device else MEM_HOST, B=B, n=n,
-                          m=m, p=1, r=r, y_shared=0, shared_mask=shared_mask, tv_mask=0,
+                          m=m, p=1, r=r, y_shared=0, shared_mask=shared_mask, tv_mask=tv_mask,
                           cov_jitter=default_jitter if cov_jitter is None else float(cov_jitter),
                           missing_fill=MISSING_FILL)
         Tb, Rb, Qb, fab, fPb = map(bufs.inp, (T, R, Q, fa, fP))
@@ -443,17 +464,17 @@ class KalmanEngine:
         return (sa[0], sP[0]) if squeeze else (sa, sP)
 
     def filter_smooth(self, kind, y, a0, P0, c, d, T, Z, R, H, Q, cov_jitter=None, missing_fill_value=None,
-                      dtype=None):
+                      dtype=None, time_varying=()):
         """Filter forward + RTS smoother in one call (core/statespace.py:903-951); the filtered trajectory
         stays in the device workspace.  Returns (loglike_obs, smoothed_states, smoothed_covariances, status)."""
         params = dict(zip(PARAM_NAMES, (a0, P0, c, d, T, Z, R, H, Q)))
         bufs = _Buffers([y, *params.values()], dtype)
         params = {k_: (v if _is_torch(v) else np.asarray(v)) for k_, v in params.items()}
         y = y if _is_torch(y) else np.asarray(y)
-        B = self._batch_size(y, params)
+        B = self._batch_size(y, params, time_varying)
         squeeze = B is None
         B = 1 if squeeze else int(B)
-        prob, yb, arrs = self._problem(kind, bufs, y, params, B, cov_jitter, missing_fill_value)
+        prob, yb, arrs = self._problem(kind, bufs, y, params, B, cov_jitter, missing_fill_value, time_varying)
         n, m = prob.n, prob.m
         ll, sa, sP = bufs.out((B, n)), bufs.out((B, n, m)), bufs.out((B, n, m, m))
         status = bufs.out_int((B,))

@@ -70,7 +70,10 @@ class BaseFilter:
         raise NotImplementedError
 
     def build_graph(self, data, a0, P0, c, d, T, Z, R, H, Q, mode=None, return_updates=False,
-                    missing_fill_value=None, cov_jitter=None):
+                    missing_fill_value=None, cov_jitter=None, time_varying=None):
+        """``time_varying`` (eager mode only, not in the reference signature): names of the inputs among
+        c, d, T, Z, R, H, Q that carry a time axis.  ``None`` = decide by ndim as the reference does
+        (filters/utilities.py:8-29) -- unambiguous only for unbatched inputs, so batched eager callers pass it."""
         if self.kind is None:
             raise NotImplementedError
         if missing_fill_value is None:
@@ -97,21 +100,29 @@ class BaseFilter:
         self.n_states, self.n_shocks = int(R_shape[-2]), int(R_shape[-1])  # kalman_filter.py:206-210
         self.n_posdef = self.n_shocks
         self.n_endog = int(Z_shape[-2])
-        self.seq_names, self.non_seq_names = [], list(PARAM_NAMES)  # time-varying inputs are refused by the engine
+        vals = dict(zip(PARAM_NAMES, (c, d, T, Z, R, H, Q)))
+        if time_varying is None:
+            if np.ndim(data) != 2:
+                time_varying = ()
+            else:  # decide_if_x_time_varies, filters/utilities.py:8-29
+                time_varying = tuple(k for k in PARAM_NAMES if np.ndim(vals[k]) == _STATIC_NDIM[k] + 1)
+        self.seq_names = [k for k in PARAM_NAMES if k in time_varying]  # kalman_filter.py:212-221
+        self.non_seq_names = [k for k in PARAM_NAMES if k not in time_varying]
         eng = default_engine(self.device)
         res = eng.filter(self.kind, data, a0, P0, c, d, T, Z, R, H, Q, cov_jitter=cov_jitter,
-                         missing_fill_value=missing_fill_value)
+                         missing_fill_value=missing_fill_value, time_varying=tuple(self.seq_names))
         outs = [res[k] for k in OUTPUT_NAMES]
         self.status = res["status"]
         return (outs, {}) if return_updates else outs
 
     def logp_and_grad(self, data, a0, P0, c, d, T, Z, R, H, Q, ll_cotangent=None, missing_fill_value=None,
-                      cov_jitter=None):
+                      cov_jitter=None, time_varying=()):
         """Eager ``(sum_t loglike_obs, {name: d/d name})`` -- what ``model.logp_dlogp_function`` needs from the
         filter."""
         eng = default_engine(self.device)
         logp, grads, status = eng.logp_grad(self.kind, data, a0, P0, c, d, T, Z, R, H, Q, ll_cotangent=ll_cotangent,
-                                            cov_jitter=cov_jitter, missing_fill_value=missing_fill_value)
+                                            cov_jitter=cov_jitter, missing_fill_value=missing_fill_value,
+                                            time_varying=tuple(time_varying))
         self.status = status
         return logp, grads
 
@@ -144,7 +155,8 @@ class KalmanSmoother:
         self.non_seq_names: list[str] = []
         self.device = device
 
-    def build_graph(self, T, R, Q, filtered_states, filtered_covariances, mode=None, cov_jitter=JITTER_DEFAULT):
+    def build_graph(self, T, R, Q, filtered_states, filtered_covariances, mode=None, cov_jitter=JITTER_DEFAULT,
+                    time_varying=None):
         self.mode = mode
         self.cov_jitter = cov_jitter
         if _is_symbolic(T, R, Q, filtered_states, filtered_covariances):
@@ -153,9 +165,14 @@ class KalmanSmoother:
             from . import pytensor_ops
 
             return pytensor_ops.build_smoother_graph(self, T, R, Q, filtered_states, filtered_covariances)
-        self.seq_names, self.non_seq_names = [], ["T", "R", "Q"]
+        vals = {"T": T, "R": R, "Q": Q}
+        if time_varying is None:
+            time_varying = () if np.ndim(filtered_states) != 2 else tuple(k for k in vals if np.ndim(vals[k]) == 3)
+        self.seq_names = [k for k in vals if k in time_varying]  # kalman_smoother.py:79-82
+        self.non_seq_names = [k for k in vals if k not in time_varying]
         eng = default_engine(self.device)
-        return eng.smooth(T, R, Q, filtered_states, filtered_covariances, cov_jitter=cov_jitter)
+        return eng.smooth(T, R, Q, filtered_states, filtered_covariances, cov_jitter=cov_jitter,
+                          time_varying=tuple(self.seq_names))
 
 
 # core/statespace.py:51-55

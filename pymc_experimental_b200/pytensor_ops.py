@@ -32,11 +32,12 @@ _ND = {"a0": 1, "P0": 2, "c": 1, "d": 1, "T": 2, "Z": 2, "R": 2, "H": 2, "Q": 2}
 class KalmanFilterOp(Op):
     """data, a0, P0, c, d, T, Z, R, H, Q -> the seven outputs of ``BaseFilter.build_graph``."""
 
-    __props__ = ("kind", "cov_jitter", "missing_fill_value", "device")
+    __props__ = ("kind", "cov_jitter", "missing_fill_value", "device", "time_varying")
 
-    def __init__(self, kind, cov_jitter, missing_fill_value, device=0):
+    def __init__(self, kind, cov_jitter, missing_fill_value, device=0, time_varying=()):
         self.kind, self.cov_jitter, self.missing_fill_value, self.device = kind, float(cov_jitter), float(
             missing_fill_value), int(device)
+        self.time_varying = tuple(time_varying)  # names with a leading time axis (filters/utilities.py:8-47)
 
     def make_node(self, data, *params):
         data = pt.as_tensor_variable(data)
@@ -44,14 +45,12 @@ class KalmanFilterOp(Op):
         if data.ndim != 2:
             raise ValueError("data must be (time, observed_state)")
         for name, x in zip(PARAM_NAMES, params):
-            if x.ndim != _ND[name]:
-                raise NotImplementedError(
-                    f"{name} has {x.ndim} dims: time-varying state-space matrices are not supported by the CUDA "
-                    "engine yet")
+            if x.ndim != _ND[name] + int(name in self.time_varying):
+                raise ValueError(f"{name} has {x.ndim} dims, expected {_ND[name] + int(name in self.time_varying)}")
         dtype = pytensor.config.floatX
         n = data.type.shape[0]
-        m, r = params[6].type.shape  # R
-        p = params[5].type.shape[0]  # Z
+        m, r = params[6].type.shape[-2:]  # R
+        p = params[5].type.shape[-2]  # Z
         po = 1 if self.kind == "univariate" else p
         shapes = [(n, m), (n, m), (n, po), (n, m, m), (n, m, m), (n, po, po), (n,)]
         outs = [pt.tensor(dtype=dtype, shape=s) for s in shapes]
@@ -61,13 +60,13 @@ class KalmanFilterOp(Op):
         data, *prm = inputs
         res = default_engine(self.device).filter(
             self.kind, data, *prm, cov_jitter=self.cov_jitter, missing_fill_value=self.missing_fill_value,
-            dtype=node.outputs[0].dtype)
+            dtype=node.outputs[0].dtype, time_varying=self.time_varying)
         for store, name in zip(output_storage, OUTPUT_NAMES):
             store[0] = res[name]
 
     def infer_shape(self, fgraph, node, ins_shapes):
         (n, p) = ins_shapes[0]
-        m = ins_shapes[1][0]
+        m = ins_shapes[1][0]  # a0
         po = 1 if self.kind == "univariate" else p
         return [(n, m), (n, m), (n, po), (n, m, m), (n, m, m), (n, po, po), (n,)]
 
@@ -83,18 +82,20 @@ class KalmanFilterOp(Op):
         g_ll = output_grads[-1]
         if isinstance(g_ll.type, DisconnectedType):
             return [grad_undefined(self, 0, inputs[0])] + [pt.zeros_like(x) for x in inputs[1:]]
-        grads = KalmanGradOp(self.kind, self.cov_jitter, self.missing_fill_value, self.device)(*inputs, g_ll)
+        grads = KalmanGradOp(self.kind, self.cov_jitter, self.missing_fill_value, self.device,
+                             self.time_varying)(*inputs, g_ll)
         return [grad_undefined(self, 0, inputs[0], "no gradient w.r.t. the observed data"), *grads]
 
 
 class KalmanGradOp(Op):
     """data, a0..Q, ll_cotangent -> d(sum_t cot_t ll_t)/d{a0,P0,c,d,T,Z,R,H,Q}  (bkf_filter_logp_grad)."""
 
-    __props__ = ("kind", "cov_jitter", "missing_fill_value", "device")
+    __props__ = ("kind", "cov_jitter", "missing_fill_value", "device", "time_varying")
 
-    def __init__(self, kind, cov_jitter, missing_fill_value, device=0):
+    def __init__(self, kind, cov_jitter, missing_fill_value, device=0, time_varying=()):
         self.kind, self.cov_jitter, self.missing_fill_value, self.device = kind, float(cov_jitter), float(
             missing_fill_value), int(device)
+        self.time_varying = tuple(time_varying)
 
     def make_node(self, data, *rest):
         ins = [pt.as_tensor_variable(x) for x in (data, *rest)]
@@ -105,7 +106,8 @@ class KalmanGradOp(Op):
         data, *prm, cot = inputs
         _, grads, _ = default_engine(self.device).logp_grad(
             self.kind, data, *prm, ll_cotangent=np.ascontiguousarray(cot), cov_jitter=self.cov_jitter,
-            missing_fill_value=self.missing_fill_value, dtype=node.outputs[0].dtype)
+            missing_fill_value=self.missing_fill_value, dtype=node.outputs[0].dtype,
+            time_varying=self.time_varying)
         for store, name in zip(output_storage, PARAM_NAMES):
             store[0] = grads[name]
 
@@ -116,19 +118,21 @@ class KalmanGradOp(Op):
 class KalmanSmootherOp(Op):
     """T, R, Q, filtered_states, filtered_covariances -> smoothed_states, smoothed_covariances."""
 
-    __props__ = ("cov_jitter", "device")
+    __props__ = ("cov_jitter", "device", "time_varying")
 
-    def __init__(self, cov_jitter, device=0):
-        self.cov_jitter, self.device = float(cov_jitter), int(device)
+    def __init__(self, cov_jitter, device=0, time_varying=()):
+        self.cov_jitter, self.device, self.time_varying = float(cov_jitter), int(device), tuple(time_varying)
 
     def make_node(self, T, R, Q, fa, fP):
         ins = [pt.as_tensor_variable(x) for x in (T, R, Q, fa, fP)]
-        if ins[0].ndim != 2 or ins[1].ndim != 2 or ins[2].ndim != 2:
-            raise NotImplementedError("time-varying T, R, Q are not supported by the CUDA engine yet")
+        for name, x in zip(("T", "R", "Q"), ins[:3]):
+            if x.ndim != 2 + int(name in self.time_varying):
+                raise ValueError(f"{name} has {x.ndim} dims, expected {2 + int(name in self.time_varying)}")
         return Apply(self, ins, [ins[3].type(), ins[4].type()])
 
     def perform(self, node, inputs, output_storage, params=None):
-        sa, sP = default_engine(self.device).smooth(*inputs, cov_jitter=self.cov_jitter, dtype=node.outputs[0].dtype)
+        sa, sP = default_engine(self.device).smooth(*inputs, cov_jitter=self.cov_jitter, dtype=node.outputs[0].dtype,
+                                                    time_varying=self.time_varying)
         output_storage[0][0], output_storage[1][0] = sa, sP
 
     def infer_shape(self, fgraph, node, ins_shapes):
@@ -142,8 +146,11 @@ def build_filter_graph(flt, data, a0, P0, c, d, T, Z, R, H, Q):
     flt.n_states, flt.n_shocks = R_shape[-2:]
     flt.n_posdef = flt.n_shocks
     flt.n_endog = Z_shape[-2]
-    flt.seq_names, flt.non_seq_names = [], ["c", "d", "T", "Z", "R", "H", "Q"]
-    op = KalmanFilterOp(flt.kind, flt.cov_jitter, flt.missing_fill_value, flt.device)
+    names = ["c", "d", "T", "Z", "R", "H", "Q"]
+    nd = dict(zip(names, (c.ndim, d.ndim, T.ndim, Z.ndim, R.ndim, H.ndim, Q.ndim)))
+    flt.seq_names = [k for k in names if nd[k] == _ND[k] + 1]  # decide_if_x_time_varies, filters/utilities.py:8-29
+    flt.non_seq_names = [k for k in names if k not in flt.seq_names]
+    op = KalmanFilterOp(flt.kind, flt.cov_jitter, flt.missing_fill_value, flt.device, tuple(flt.seq_names))
     outs = op(data, a0, P0, c, d, T, Z, R, H, Q)
     for o, name in zip(outs, OUTPUT_NAMES):
         o.name = name
@@ -151,7 +158,10 @@ def build_filter_graph(flt, data, a0, P0, c, d, T, Z, R, H, Q):
 
 
 def build_smoother_graph(sm, T, R, Q, filtered_states, filtered_covariances):
-    sm.seq_names, sm.non_seq_names = [], ["T", "R", "Q"]
-    sa, sP = KalmanSmootherOp(sm.cov_jitter, sm.device)(T, R, Q, filtered_states, filtered_covariances)
+    nd = {"T": T.ndim, "R": R.ndim, "Q": Q.ndim}
+    sm.seq_names = [k for k in nd if nd[k] == 3]
+    sm.non_seq_names = [k for k in nd if nd[k] != 3]
+    sa, sP = KalmanSmootherOp(sm.cov_jitter, sm.device, tuple(sm.seq_names))(
+        T, R, Q, filtered_states, filtered_covariances)
     sa.name, sP.name = "smoothed_states", "smoothed_covariances"
     return sa, sP

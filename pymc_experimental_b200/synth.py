@@ -194,5 +194,28 @@ def random_dense(B, n, m, p, r, seed=0, missing=0.0, per_series_y=True, diag_H=F
                 d=rng.standard_normal((B, p)) * 0.1, T=T_, Z=Z, R=R, H=H, Q=spd(r, 0.5))
 
 
+def random_dense_tv(B, n, m, p, r, time_varying, seed=0, missing=0.0, diag_H=False):
+    """``random_dense`` with a time axis ([B, n, ...]) on the inputs named in ``time_varying`` (c, d, T, Z, R, H, Q):
+    every step gets its own perturbed copy, H_t and Q_t stay SPD.  Mirrors the reference's time-varying tests
+    (tests/statespace/test_kalman_filter.py:151-166) with non-trivial values."""
+    cfg = random_dense(B, n, m, p, r, seed=seed, missing=missing, diag_H=diag_H)
+    rng = np.random.default_rng(seed + 7919)
+    for k in time_varying:
+        x = cfg[k]
+        xt = np.repeat(x[:, None], n, axis=1)
+        if k in ("H", "Q"):
+            kdim = x.shape[-1]
+            L = rng.standard_normal((B, n, kdim, kdim)) * 0.25
+            pert = L @ np.swapaxes(L, -1, -2)
+            if k == "H" and diag_H:
+                pert = pert * np.eye(kdim)
+            xt = xt + pert
+        else:
+            scale = 0.15 * (np.abs(x).mean() + 0.05)
+            xt = xt + rng.standard_normal(xt.shape) * scale
+        cfg[k] = np.ascontiguousarray(xt)
+    return cfg
+
+
 CONFIGS = {"C1": local_level, "C2": sarima, "C3": structural, "C4": varmax, "C5": ets}
 FILTER_OF = {"C1": "standard", "C2": "univariate", "C3": "standard", "C4": "cholesky", "C5": "standard"}

@@ -24,6 +24,14 @@ def golden_names(prefix=None, kind=None):
     return names
 
 
+def golden_tv(name):
+    """Names of the inputs that carry a time axis in this fixture (empty for time-invariant cases)."""
+    import numpy as np
+
+    z = np.load(os.path.join(GOLDEN_DIR, name + ".npz"))
+    return tuple(str(x) for x in z["time_varying"]) if "time_varying" in z.files else ()
+
+
 def load_golden(name):
     import numpy as np
 

@@ -52,9 +52,10 @@ def run_reference(kind, y, params, smoother=True, grad=True):
     return res
 
 
-def save(name, kind, y, params, **kw):
+def save(name, kind, y, params, extra=None, **kw):
     res = run_reference(kind, y, params, **kw)
     payload = {"in_y": y, "kind": np.array(kind)}
+    payload.update(extra or {})
     payload.update({"in_" + k: np.asarray(params[k], dtype=np.float64) for k in NAMES})
     payload.update({"out_" + k: v for k, v in res.items()})
     path = os.path.join(ROOT, "tests", "golden", f"{name}.npz")
@@ -93,7 +94,29 @@ def one(cfg, i=0):
     return y, {k: cfg[k][i] for k in NAMES}
 
 
+TV_CASES = [
+    # name, (m, p, r, n), time-varying inputs, missing fraction
+    ("tv_all_m4p2r2", (4, 2, 2, 18), ("c", "d", "T", "Z", "R", "H", "Q"), 0.0),
+    ("tv_all_m4p2r2_missing", (4, 2, 2, 18), ("c", "d", "T", "Z", "R", "H", "Q"), 0.15),
+    ("tv_regressionZ_m5p1r2", (5, 1, 2, 24), ("Z",), 0.0),        # structural.py:1601-1617 (RegressionComponent)
+    ("tv_TQ_m3p1r1", (3, 1, 1, 20), ("T", "Q"), 0.1),
+]
+
+
+def tv_cases():
+    """Time-varying inputs (leading time axis, filters/utilities.py:8-47), StandardFilter only: the reference's
+    UnivariateFilter.kalman_step (kalman_filter.py:791) takes its arguments positionally without unpack_args, so with
+    any time-varying input the scan hands it (y, *seqs, a, P, *non_seqs) in the wrong slots and it fails -- there is
+    no reference behaviour to record for that combination."""
+    for name, (m, p, r, n), tv, miss in TV_CASES:
+        cfg = synth.random_dense_tv(1, n, m, p, r, tv, seed=31 * m + p + len(tv), missing=miss, diag_H=bool(miss) and p > 1)
+        y, prm = one(cfg)
+        save(f"{name}_standard", "standard", y, prm, extra={"time_varying": np.array(tv)})
+
+
 def main():
+    if "--only-tv" in sys.argv:
+        return tv_cases()
     rng = np.random.default_rng(sum(map(ord, "statespace")))  # tests/statespace/utilities/shared_fixtures.py:4
     for n_missing in (0, 5):
         y, prm = nile_inputs(n_missing, rng)
@@ -131,6 +154,7 @@ def main():
     save("c5_ets_standard", "standard", y, prm)
     y, prm = one(synth.local_level(B=1, n=100), 0)
     save("c1_local_level_standard", "standard", y, prm)
+    tv_cases()
 
 
 if __name__ == "__main__":

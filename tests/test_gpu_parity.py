@@ -9,7 +9,7 @@ Tolerance (BASELINE.json north_star): float64 <= 1e-9 relative on logp and on ev
 
 import numpy as np
 import pytest
-from conftest import golden_names, load_golden
+from conftest import golden_names, golden_tv, load_golden
 from numpy.testing import assert_allclose
 
 pytestmark = pytest.mark.gpu
@@ -50,7 +50,7 @@ def _close(actual, desired, rtol, msg):
 @pytest.mark.parametrize("name", golden_names())
 def test_forward_outputs_match_reference_golden(eng, name):
     kind, ins, ref = load_golden(name)
-    out = eng.filter(kind, *_args(ins))
+    out = eng.filter(kind, *_args(ins), time_varying=golden_tv(name))
     rtol = 1e-6 if _ill(name) else RTOL64
     assert_allclose(out["loglike_obs"].sum(), ref["loglike_obs"].sum(), rtol=rtol)
     for n in OUT_NAMES:
@@ -60,7 +60,7 @@ def test_forward_outputs_match_reference_golden(eng, name):
 @pytest.mark.parametrize("name", golden_names())
 def test_logp_and_gradients_match_reference_golden(eng, name):
     kind, ins, ref = load_golden(name)
-    logp, grads, status = eng.logp_grad(kind, *_args(ins))
+    logp, grads, status = eng.logp_grad(kind, *_args(ins), time_varying=golden_tv(name))
     rtol = 1e-6 if _ill(name) else RTOL64
     assert_allclose(logp, ref["loglike_obs"].sum(), rtol=rtol)
     for k in NAMES:
@@ -70,7 +70,8 @@ def test_logp_and_gradients_match_reference_golden(eng, name):
 @pytest.mark.parametrize("name", golden_names())
 def test_smoother_matches_reference_golden(eng, name):
     kind, ins, ref = load_golden(name)
-    sa, sP = eng.smooth(ins["T"], ins["R"], ins["Q"], ref["filtered_states"], ref["filtered_covariances"])
+    sa, sP = eng.smooth(ins["T"], ins["R"], ins["Q"], ref["filtered_states"], ref["filtered_covariances"],
+                        time_varying=tuple(k for k in golden_tv(name) if k in "TRQ"))
     tol = 1e-4 if (_diffuse(name) or _ill(name)) else 1e-8
     lo = 0
     if _diffuse(name):
@@ -333,3 +334,51 @@ def test_unsupported_configurations_fail_loudly(eng):
     bad = dict(cfg, T=np.broadcast_to(cfg["T"][:, None], (2, 5, 3, 3)))  # time-varying T
     with pytest.raises(BkfError):
         eng.filter("standard", bad["y"], *[bad[k] for k in NAMES])
+
+
+@pytest.mark.parametrize("kind", ["standard", "univariate"])
+@pytest.mark.parametrize("tv", [("Z",), ("T", "Q"), ("c", "d", "T", "Z", "R", "H", "Q")])
+@pytest.mark.parametrize("shape", [(3, 1, 2), (5, 2, 3), (15, 1, 5)])
+def test_time_varying_matrices_batched(eng, kind, tv, shape):
+    """Inputs with a time axis (filters/utilities.py:8-47): batched logp, gradients
+    (which keep the time axis) and filter + smoother against the oracles.  Shared (unbatched) time-varying inputs
+    are covered by the golden cases."""
+    import torch
+
+    from oracle import kalman_np as onp
+    from oracle import kalman_torch as oth
+    from pymc_experimental_b200 import synth
+
+    m, p, r = shape
+    B, n = 9, 14
+    cfg = synth.random_dense_tv(B, n, m, p, r, tv, seed=11 * m + p + len(tv), missing=0.1 if p == 1 else 0.0)
+    args = [cfg["y"]] + [cfg[k] for k in NAMES]
+    logp, grads, status = eng.logp_grad(kind, *args, time_varying=tv)
+    assert eng.last_path == "generic_warp"
+    ref_logp, ref_g = oth.logp_and_grad(kind, *args, time_varying=tv)
+    assert_allclose(logp, ref_logp, rtol=RTOL64)
+    for k in NAMES:
+        assert grads[k].shape == cfg[k].shape
+        for b in range(B):
+            _close(grads[k][b], ref_g[k][b], RTOL64, f"{kind} tv={tv} d/d{k}[{b}]")
+    out = eng.filter(kind, *args, time_varying=tv)
+    ref = oth.kalman_filter(kind, *[torch.as_tensor(a) for a in args], time_varying=tv)
+    for got, want in zip([out[k] for k in OUT_NAMES], ref):
+        _close(got, want.numpy(), RTOL64, f"{kind} tv={tv}")
+    tv_s = tuple(k for k in tv if k in "TRQ")
+    sa, sP = eng.smooth(cfg["T"], cfg["R"], cfg["Q"], out["filtered_states"], out["filtered_covariances"],
+                        time_varying=tv_s)
+    for b in range(0, B, 4):
+        ra, rP = onp.kalman_smoother(cfg["T"][b], cfg["R"][b], cfg["Q"][b], out["filtered_states"][b],
+                                     out["filtered_covariances"][b])
+        _close(sa[b], ra, 1e-8, f"smoothed_states[{b}]")
+        _close(sP[b], rP, 1e-8, f"smoothed_covariances[{b}]")
+
+
+def test_time_varying_square_root_filter_is_refused(eng):
+    from pymc_experimental_b200 import synth
+    from pymc_experimental_b200.engine import BkfError
+
+    cfg = synth.random_dense_tv(2, 6, 3, 2, 2, ("Z",), seed=3)
+    with pytest.raises(BkfError, match="square-root"):
+        eng.filter("cholesky", cfg["y"], *[cfg[k] for k in NAMES], time_varying=("Z",))
