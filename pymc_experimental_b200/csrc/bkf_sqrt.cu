@@ -21,11 +21,65 @@ enum { SET = 0, ADD = 1, SUB = 2 };
 
 struct Th {
     int tid, nt;
+    bool fast;  // float64 and m, p, r multiples of 8: the O(n^3) primitives run on FP64 tensor-core tiles (DMMA)
 };
+
+__device__ __forceinline__ void dmma(double& c0, double& c1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                 : "+d"(c0), "+d"(c1)
+                 : "d"(a), "d"(b));
+}
+
+// DMMA-tiled  C (op)= A B  on shared-memory operands with arbitrary strides: A(i,k) = A[i*as0 + k*as1],
+// B(k,j) = B[k*bs0 + j*bs1], C(i,j) = C[i*cs0 + j*cs1].  M, N multiples of 8, K a multiple of 4.  The warps of the
+// CTA split the 8 x 8 output tiles; two accumulator chains per tile.  BMASK = 1 keeps only B(k,j) with k >= j
+// (the upper-triangular cotangent view of qr_pullback_psi).  In-place use (C aliasing B) is safe when K == 8 and
+// M == 8: a warp loads both k-slices of its own tile column before the warp-synchronous mma and stores after it.
+template <int MODE, int BMASK>
+__device__ void mm_dmma(double* C, int cs0, int cs1, const double* A, int as0, int as1, const double* Bm, int bs0,
+                        int bs1, int M, int N, int K, Th th) {
+    const int warp = th.tid >> 5, nw = th.nt >> 5, lane = th.tid & 31, g = lane >> 2, t = lane & 3;
+    const int tn = N >> 3, tiles = (M >> 3) * tn;
+    for (int tile = warp; tile < tiles; tile += nw) {
+        const int ti = tile / tn, tj = tile - ti * tn;
+        const double* a = A + (8 * ti + g) * as0 + t * as1;
+        const double* b = Bm + t * bs0 + (8 * tj + g) * bs1;
+        const int jcol = 8 * tj + g;
+        double c0 = 0, c1 = 0, e0 = 0, e1 = 0;
+        int k0 = 0;
+        for (; k0 + 8 <= K; k0 += 8) {
+            double b0 = b[k0 * bs0], b1 = b[(k0 + 4) * bs0];
+            if (BMASK) {
+                if (k0 + t < jcol) b0 = 0;
+                if (k0 + 4 + t < jcol) b1 = 0;
+            }
+            dmma(c0, c1, a[k0 * as1], b0);
+            dmma(e0, e1, a[(k0 + 4) * as1], b1);
+        }
+        if (k0 < K) {
+            double b0 = b[k0 * bs0];
+            if (BMASK && k0 + t < jcol) b0 = 0;
+            dmma(c0, c1, a[k0 * as1], b0);
+        }
+        c0 += e0;
+        c1 += e1;
+        double* c = C + (8 * ti + g) * cs0 + (8 * tj + 2 * t) * cs1;
+        if (MODE == SET) { c[0] = c0; c[cs1] = c1; }
+        else if (MODE == ADD) { c[0] += c0; c[cs1] += c1; }
+        else { c[0] -= c0; c[cs1] -= c1; }
+    }
+    __syncthreads();
+}
 
 template <int MODE, typename R>
 __device__ __forceinline__ void mm(R* __restrict__ C, int ldc, const R* __restrict__ A, int as0, int as1,
                                    const R* __restrict__ Bm, int bs0, int bs1, int M, int N, int K, Th th) {
+    if constexpr (sizeof(R) == 8) {
+        if (th.fast && !(M & 7) && !(N & 7) && !(K & 3)) {
+            mm_dmma<MODE, 0>(C, ldc, 1, A, as0, as1, Bm, bs0, bs1, M, N, K, th);
+            return;
+        }
+    }
     for (int idx = th.tid; idx < M * N; idx += th.nt) {
         int i = idx / N, j = idx - i * N;
         const R* a = A + i * as0;
@@ -93,6 +147,158 @@ __device__ void householder_r(R* W, int rows, int cols, R* red, Th th) {
     }
 }
 
+// Blocked Householder R factor (panel width 8, compact-WY trailing updates on DMMA tiles); rows, cols multiples of 8,
+// rows <= 64.  Same reflectors as householder_r (LAPACK dgeqr2/dlarfg sign rules), applied block-wise as dgeqrf does:
+//   panel:    one warp, lane-per-row (rows l and l + 32), the 8 panel columns in registers, warp reductions
+//   T factor: dlarft (forward, columnwise):  T[i][i] = tau_i,  T[0:i, i] = -tau_i T[0:i,0:i] V[:,0:i]^T v_i
+//   trailing: A <- A - V T^T (V^T A)   (three mm_dmma calls)
+// hv: rows*8 (V with unit diagonal), ht: 64 (T), hw: 8*cols (V^T A).
+__device__ void householder_r_fast(double* W, int rows, int cols, double* hv, double* ht, double* hw, Th th) {
+    const int lane = th.tid & 31, warp = th.tid >> 5;
+    const int kmaxp = (rows < cols ? rows : cols) >> 3;
+    for (int jp = 0; jp < kmaxp; ++jp) {
+        const int c0 = jp * 8, prow = rows - c0;
+        if (warp == 0) {
+            // local rows: slot 0 -> lane, slot 1 -> lane + 32 (relative to c0)
+            double a[2][8];
+            const bool has1 = lane + 32 < prow;
+            const bool has0 = lane < prow;
+            {
+                const double2* r0 = reinterpret_cast<const double2*>(W + (c0 + lane) * cols + c0);
+                const double2* r1 = reinterpret_cast<const double2*>(W + (c0 + lane + 32) * cols + c0);
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const double2 u0 = has0 ? r0[q] : make_double2(0.0, 0.0);
+                    const double2 u1 = has1 ? r1[q] : make_double2(0.0, 0.0);
+                    a[0][2 * q] = u0.x; a[0][2 * q + 1] = u0.y;
+                    a[1][2 * q] = u1.x; a[1][2 * q + 1] = u1.y;
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                // x = a[k+1:, k] (unscaled).  ONE window of independent warp reductions per reflector:
+                //   ss = x.x,  d[c] = x . a[k+1:, c] (c > k),  e[i] = x . v_i[k+1:] (i < k, for the T factor)
+                const double x0 = lane > k ? a[0][k] : 0.0, x1 = a[1][k];
+                double ss = warp_sum(fma(x1, x1, x0 * x0));
+                double d[8], e[8];
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {
+                    const double dot = warp_sum(fma(x1, a[1][c], x0 * a[0][c]));
+                    d[c] = dot;  // c > k: trailing panel column;  c < k: column c holds v_c below its diagonal
+                    e[c] = dot;
+                }
+                const double alpha = __shfl_sync(0xffffffffu, a[0][k], k);
+                if (ss == 0.0) {  // dlarfg: tau = 0, H = I
+                    if (lane > k) a[0][k] = 0.0;
+                    a[1][k] = 0.0;
+                    if (lane < 8) ht[lane * 8 + k] = 0.0;
+                    __syncwarp();
+                    continue;
+                }
+                const double nrm = sqrt(fma(alpha, alpha, ss));
+                const double beta = alpha >= 0.0 ? -nrm : nrm;
+                const double tau = (beta - alpha) / beta;
+                const double scal = 1.0 / (alpha - beta);
+                // v (unit at local row k); rows above the pivot do not take part
+                const double v0 = lane > k ? x0 * scal : (lane == k ? 1.0 : 0.0);
+                const double v1 = x1 * scal;
+#pragma unroll
+                for (int c = k + 1; c < 8; ++c) {
+                    const double akc = __shfl_sync(0xffffffffu, a[0][c], k);
+                    const double w = tau * fma(scal, d[c], akc);  // tau v^T a_c
+                    a[0][c] = fma(-w, v0, a[0][c]);
+                    a[1][c] = fma(-w, v1, a[1][c]);
+                }
+                // dlarft column k:  z_i = v_i^T v_k = v_i[k] + scal e_i ;  T[0:k,k] = -tau T[0:k,0:k] z ;  T[k][k] = tau
+                double z[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) z[i] = (i < k) ? fma(scal, e[i], __shfl_sync(0xffffffffu, a[0][i], k)) : 0.0;
+                if (lane < 8) {  // lane i owns row i of T (kept in shared memory: ht)
+                    double acc = 0.0;
+#pragma unroll
+                    for (int l = 0; l < 8; ++l)
+                        if (l < k) acc = fma((l >= lane) ? ht[lane * 8 + l] : 0.0, z[l], acc);
+                    ht[lane * 8 + k] = lane < k ? -tau * acc : (lane == k ? tau : 0.0);
+                }
+                __syncwarp();
+                if (lane == k) a[0][k] = beta;
+                else if (lane > k) a[0][k] = v0;
+                a[1][k] = v1;
+            }
+            // write the panel back: R on and above the diagonal, zeros below; the reflectors go to hv (unit diagonal)
+            {
+                double2* r0 = reinterpret_cast<double2*>(W + (c0 + lane) * cols + c0);
+                double2* r1 = reinterpret_cast<double2*>(W + (c0 + lane + 32) * cols + c0);
+                double2* h0 = reinterpret_cast<double2*>(hv + lane * 8);
+                double2* h1 = reinterpret_cast<double2*>(hv + (lane + 32) * 8);
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const int k0 = 2 * q, k1 = 2 * q + 1;
+                    if (has0) {
+                        r0[q] = make_double2(lane <= k0 ? a[0][k0] : 0.0, lane <= k1 ? a[0][k1] : 0.0);
+                        h0[q] = make_double2(lane > k0 ? a[0][k0] : (lane == k0 ? 1.0 : 0.0),
+                                             lane > k1 ? a[0][k1] : (lane == k1 ? 1.0 : 0.0));
+                    }
+                    if (has1) {
+                        r1[q] = make_double2(0.0, 0.0);
+                        h1[q] = make_double2(a[1][k0], a[1][k1]);
+                    }
+                }
+            }
+        }
+        __syncthreads();
+        const int nt_cols = cols - c0 - 8;
+        if (nt_cols > 0) {
+            double* At = W + c0 * cols + c0 + 8;
+            mm_dmma<SET, 0>(hw, nt_cols, 1, hv, 1, 8, At, cols, 1, 8, nt_cols, prow, th);      // V^T A
+            mm_dmma<SET, 0>(hw, nt_cols, 1, ht, 1, 8, hw, nt_cols, 1, 8, nt_cols, 8, th);     // T^T (V^T A), in place
+            mm_dmma<SUB, 0>(At, cols, 1, hv, 8, 1, hw, nt_cols, 1, prow, nt_cols, 8, th);     // A -= V (...)
+        }
+    }
+}
+
+template <typename R>
+__device__ __forceinline__ void qr_r(R* W, int rows, int cols, R* red, R* hv, R* ht, R* hw, Th th) {
+    if constexpr (sizeof(R) == 8) {
+        if (th.fast && !(rows & 7) && !(cols & 7) && rows <= 64) {
+            householder_r_fast(W, rows, cols, hv, ht, hw, th);
+            return;
+        }
+    }
+    householder_r(W, rows, cols, red, th);
+}
+
+// X <- U^{-1} X on DMMA tiles (n, ncols multiples of 8): the 8 x 8 diagonal tiles are inverted once (one warp each,
+// back-substitution by 8 lanes), then block back-substitution  X_I <- Uinv_I (X_I - sum_{J>I} U_IJ X_J).
+// uinv: (n/8)*64 doubles of scratch.
+__device__ void solve_upper_fast(const double* U, int ldu, int n, double* X, int xs0, int xs1, int ncols, double* uinv,
+                                 Th th) {
+    const int nb = n >> 3, lane = th.tid & 31, warp = th.tid >> 5, nw = th.nt >> 5;
+    for (int I = warp; I < nb; I += nw) {
+        if (lane < 8) {
+            const double* D = U + (8 * I) * ldu + 8 * I;
+            double x[8];
+#pragma unroll
+            for (int i = 7; i >= 0; --i) {
+                double tt = (i == lane) ? 1.0 : 0.0;
+#pragma unroll
+                for (int q = 7; q > i; --q) tt = fma(-D[i * ldu + q], x[q], tt);
+                x[i] = tt / D[i * ldu + i];
+            }
+#pragma unroll
+            for (int i = 0; i < 8; ++i) uinv[I * 64 + i * 8 + lane] = x[i];
+        }
+    }
+    __syncthreads();
+    for (int I = nb - 1; I >= 0; --I) {
+        double* XI = X + (8 * I) * xs0;
+        if (I < nb - 1)
+            mm_dmma<SUB, 0>(XI, xs0, xs1, U + (8 * I) * ldu + 8 * (I + 1), ldu, 1, X + 8 * (I + 1) * xs0, xs0, xs1, 8, ncols,
+                            8 * (nb - 1 - I), th);
+        mm_dmma<SET, 0>(XI, xs0, xs1, uinv + I * 64, 8, 1, XI, xs0, xs1, 8, ncols, 8, th);
+    }
+}
+
 // X <- U^{-1} X for upper-triangular U[n,n] (ld = ldu); X element (i, c) at X[i*xs0 + c*xs1], ncols columns.
 template <typename R>
 __device__ void solve_upper(const R* U, int ldu, int n, R* X, int xs0, int xs1, int ncols, Th th) {
@@ -109,7 +315,22 @@ __device__ void solve_upper(const R* U, int ldu, int n, R* X, int xs0, int xs1, 
 // Psi = U^{-1} copyltu(U Rbar^T) U^{-T}  (n x n, symmetric), with Rbar(i,j) = Rb[i*rs0 + j*rs1] for i <= j, 0 below.
 // tmp: n*n scratch.
 template <typename R>
-__device__ void qr_pullback_psi(R* Psi, const R* U, int ldu, int n, const R* Rb, int rs0, int rs1, R* tmp, Th th) {
+__device__ void qr_pullback_psi(R* Psi, const R* U, int ldu, int n, const R* Rb, int rs0, int rs1, R* tmp, R* uinv,
+                                Th th) {
+    if constexpr (sizeof(R) == 8) {
+        if (th.fast && !(n & 7)) {
+            // U is stored with exact zeros below its diagonal, Rbar is masked to k >= j inside the product
+            mm_dmma<SET, 1>(tmp, n, 1, U, ldu, 1, Rb, rs1, rs0, n, n, n, th);
+            for (int idx = th.tid; idx < n * n; idx += th.nt) {
+                int i = idx / n, j = idx - i * n;
+                Psi[idx] = (i >= j) ? tmp[idx] : tmp[j * n + i];
+            }
+            __syncthreads();
+            solve_upper_fast(U, ldu, n, Psi, n, 1, n, uinv, th);
+            solve_upper_fast(U, ldu, n, Psi, 1, n, n, uinv, th);
+            return;
+        }
+    }
     // tmp = U Rbar^T : tmp[i,j] = sum_{k >= max(i,j)} U[i,k] Rbar[j,k]
     for (int idx = th.tid; idx < n * n; idx += th.nt) {
         int i = idx / n, j = idx - i * n;
@@ -198,6 +419,7 @@ struct Arena {
     R *Zm, *w, *ym, *v, *sv, *inner, *af, *Pcf;
     R *A0, *Rf, *M0, *Rp;                    // update / predict QR inputs and factors
     R *red;                                  // block reduction scratch (32)
+    R *hv, *ht, *hw, *uinv;                  // blocked Householder / tile-solve scratch (fast path)
     // backward only
     R *abar, *Pbar, *S1, *Psi, *Abar, *gT, *gZ, *gc, *gd, *Psum, *Hcbar, *afbar, *Pcfbar, *U1, *vbar, *sbar, *t1;
 };
@@ -209,6 +431,8 @@ __host__ __device__ inline size_t arena_elems(int m, int p, int r, bool bwd) {
                  /*d,w,ym,v,sv,inner*/ 6 * (size_t)p + /*A0,Rf*/ 2 * n1 + /*M0,Rp*/ 2 * n2 + 32;
     size_t bw = /*Pbar,gT,Psum,Pcfbar,U1*/ 5 * mm_ + /*S1,Psi,Abar*/ 3 * n1 + pm + /*abar,gc,afbar*/ 3 * (size_t)m +
                 /*gd,vbar,sbar,t1*/ 4 * (size_t)p + pp;
+    // blocked-QR / tile-solve scratch: the forward kernel never reads A0, so it borrows that region
+    if (bwd) bw += /*hv,hw,uinv*/ 3 * 8 * (size_t)(p + m + r) + /*ht*/ 64;
     size_t tot = fwd + (bwd ? bw : 0);
     return (tot + 1) & ~(size_t)1;
 }
@@ -222,11 +446,16 @@ __device__ void carve(Arena<R>& A, R* s, int m, int p, int r, bool bwd) {
     A.Qc = take(rr); A.RQc = take(mr); A.c = take(m); A.a = take(m); A.af = take(m);
     A.d = take(p); A.w = take(p); A.ym = take(p); A.v = take(p); A.sv = take(p); A.inner = take(p);
     A.A0 = take(n1); A.Rf = take(n1); A.M0 = take(n2); A.Rp = take(n2); A.red = take(32);
+    if (!bwd) {  // (p+m)^2 >= 2*8*(p+m+r) + 64 is checked by the launcher before the fast path is enabled
+        A.hv = A.A0; A.hw = A.A0 + 8 * (size_t)(p + m + r); A.ht = A.hw + 8 * (size_t)(p + m + r); A.uinv = nullptr;
+    }
     if (bwd) {
         A.Pbar = take(mm_); A.gT = take(mm_); A.Psum = take(mm_); A.Pcfbar = take(mm_); A.U1 = take(mm_);
         A.S1 = take(n1); A.Psi = take(n1); A.Abar = take(n1); A.gZ = take(pm);
         A.abar = take(m); A.gc = take(m); A.afbar = take(m);
         A.gd = take(p); A.vbar = take(p); A.sbar = take(p); A.t1 = take(p); A.Hcbar = take(pp);
+        A.hv = take(8 * (size_t)(p + m + r)); A.hw = take(8 * (size_t)(p + m + r)); A.uinv = take(8 * (size_t)(p + m + r));
+        A.ht = take(64);
     }
 }
 
@@ -283,6 +512,7 @@ __device__ R step(const KArgs<R>& g, Arena<R>& A, const R* yt, bool Hzero, bool*
         if (i < p) {
             val = (j < p) ? ((flag || Hzero) ? R(0) : (partial ? R(NAN) : A.Hc[j * p + i])) : R(0);
         } else if (j < p) {
+            if (th.fast) continue;  // (Zm Pc)^T block: DMMA product below
             R acc = 0;
             for (int q = 0; q < m; ++q) acc = fma(A.Zm[j * m + q], A.Pc[q * m + (i - p)], acc);
             val = acc;
@@ -293,7 +523,17 @@ __device__ R step(const KArgs<R>& g, Arena<R>& A, const R* yt, bool Hzero, bool*
         A.Rf[idx] = val;
     }
     __syncthreads();
-    householder_r(A.Rf, N1, N1, A.red, th);
+    if constexpr (sizeof(R) == 8) {
+        if (th.fast) {  // Rf[p+i, j] = sum_q Pc[q, i] Zm[j, q]
+            mm_dmma<SET, 0>(A.Rf + p * N1, N1, 1, A.Pc, 1, m, A.Zm, 1, m, m, p, m, th);
+            for (int idx = th.tid; idx < m * p; idx += th.nt) {
+                int i = idx / p, j = idx - i * p;
+                A.A0[(p + i) * N1 + j] = A.Rf[(p + i) * N1 + j];
+            }
+            __syncthreads();
+        }
+    }
+    qr_r(A.Rf, N1, N1, A.red, A.hv, A.ht, A.hw, th);
     *flag_out = flag;
     return R(0);
 }
@@ -317,10 +557,9 @@ __device__ R finish_update(const KArgs<R>& g, Arena<R>& A, bool flag, Th th) {
         }
         __syncthreads();
         R quad = 0, logdet = 0;
-        for (int o = 0; o < p; ++o) {
-            quad = fma(A.v[o], A.inner[o], quad);
-            logdet += log(fabs(A.Rf[o * N1 + o]));
-        }
+        for (int o = 0; o < p; ++o) quad = fma(A.v[o], A.inner[o], quad);
+        for (int o = th.tid; o < p; o += th.nt) logdet += log(fabs(A.Rf[o * N1 + o]));
+        logdet = block_sum(logdet, A.red, th);
         ll = R(-0.5) * (R(p) * (R(kLog2Pi) + R(2) * logdet) + quad);  // :696 (quirk Q2)
         for (int i = th.tid; i < m; i += th.nt) {
             R acc = 0;
@@ -343,10 +582,21 @@ __device__ R finish_update(const KArgs<R>& g, Arena<R>& A, bool flag, Th th) {
 template <typename R>
 __device__ void predict(const KArgs<R>& g, Arena<R>& A, R* a_next, R* Pc_next, Th th) {
     const int m = g.m, r = g.r;
+    bool tp_done = false;
+    if constexpr (sizeof(R) == 8) {
+        if (th.fast) {  // M0[i, j] = sum_q Pcf[q, i] T[j, q]   (i, j < m)
+            mm_dmma<SET, 0>(A.M0, m, 1, A.Pcf, 1, m, A.T, 1, m, m, m, m, th);
+            tp_done = true;
+        }
+    }
     for (int idx = th.tid; idx < (m + r) * m; idx += th.nt) {
         int i = idx / m, j = idx - i * m;
         R val;
         if (i < m) {
+            if (tp_done) {
+                A.Rp[idx] = A.M0[idx];
+                continue;
+            }
             R acc = 0;
             for (int q = 0; q < m; ++q) acc = fma(A.T[j * m + q], A.Pcf[q * m + i], acc);
             val = acc;
@@ -357,7 +607,7 @@ __device__ void predict(const KArgs<R>& g, Arena<R>& A, R* a_next, R* Pc_next, T
         A.Rp[idx] = val;
     }
     __syncthreads();
-    householder_r(A.Rp, m + r, m, A.red, th);
+    qr_r(A.Rp, m + r, m, A.red, A.hv, A.ht, A.hw, th);
     if (a_next) {
         for (int i = th.tid; i < m; i += th.nt) {
             R acc = 0;
@@ -371,10 +621,11 @@ __device__ void predict(const KArgs<R>& g, Arena<R>& A, R* a_next, R* Pc_next, T
 }
 
 template <typename R>
-__global__ void forward_kernel(KArgs<R> g) {
+__global__ void __launch_bounds__(256, 2) forward_kernel(KArgs<R> g) {
     extern __shared__ double smem_raw[];
     R* smem = reinterpret_cast<R*>(smem_raw);
-    const Th th{(int)threadIdx.x, (int)blockDim.x};
+    const Th th{(int)threadIdx.x, (int)blockDim.x, sizeof(R) == 8 && !((g.m | g.p | g.r) & 7) &&
+                    (g.p + g.m) * (g.p + g.m) >= 16 * (g.p + g.m + g.r) + 64};
     const int b = blockIdx.x;
     const int m = g.m, p = g.p, n = g.n, N1 = p + m;
     Arena<R> A;
@@ -425,7 +676,7 @@ template <typename R>
 __global__ void backward_kernel(KArgs<R> g) {
     extern __shared__ double smem_raw[];
     R* smem = reinterpret_cast<R*>(smem_raw);
-    const Th th{(int)threadIdx.x, (int)blockDim.x};
+    const Th th{(int)threadIdx.x, (int)blockDim.x, sizeof(R) == 8 && !((g.m | g.p | g.r) & 7)};
     const int b = blockIdx.x;
     const int m = g.m, p = g.p, r = g.r, n = g.n, N1 = p + m;
     Arena<R> A;
@@ -447,7 +698,7 @@ __global__ void backward_kernel(KArgs<R> g) {
         predict(g, A, (R*)nullptr, (R*)nullptr, th);
         // ================= predict adjoint =================
         // Rp_bar = triu(Pbar^T): Rbar(i,j) = Pbar[j*m + i]  ->  strides (rs0, rs1) = (1, m)
-        qr_pullback_psi(A.Psi, A.Rp, m, m, A.Pbar, 1, m, A.S1, th);
+        qr_pullback_psi(A.Psi, A.Rp, m, m, A.Pbar, 1, m, A.S1, A.uinv, th);
         for (int idx = th.tid; idx < m * m; idx += th.nt) A.Psum[idx] += A.Psi[idx];
         // U1 = Psi (T Pcf), (T Pcf)[k,j] = M0[j*m + k]
         mm<SET>(A.U1, m, A.Psi, m, 1, A.M0, 1, m, m, m, m, th);
@@ -514,7 +765,7 @@ __global__ void backward_kernel(KArgs<R> g) {
         }
         __syncthreads();
         // Rf_bar = Bbar^T: Rbar(i,j) = Bbar[j*N1 + i] -> strides (1, N1); Psi_f into Psi; then Abar = A0 Psi_f
-        qr_pullback_psi(A.Psi, A.Rf, N1, N1, A.Abar, 1, N1, A.S1, th);
+        qr_pullback_psi(A.Psi, A.Rf, N1, N1, A.Abar, 1, N1, A.S1, A.uinv, th);
         mm<SET>(A.Abar, N1, A.A0, N1, 1, A.Psi, N1, 1, N1, N1, N1, th);
         // blocks: Hcbar += tril(Abar11^T); ZPbar = Abar21^T (p x m); Pbar = Abar22^T + Zm^T ZPbar
         for (int idx = th.tid; idx < p * p; idx += th.nt) {

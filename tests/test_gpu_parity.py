@@ -180,7 +180,8 @@ def test_subwarp_kernels_all_sizes(eng, m):
                 _close(grads[k][b], ref_g[k][b], RTOL64, f"{kind} m={m} d/d{k}[{b}]")
 
 
-@pytest.mark.parametrize("shape", [(2, 1, 2), (5, 2, 3), (8, 3, 2), (12, 4, 4), (6, 6, 3)])
+@pytest.mark.parametrize("shape", [(2, 1, 2), (5, 2, 3), (8, 3, 2), (12, 4, 4), (6, 6, 3), (8, 8, 8), (16, 8, 8),
+                                   (24, 8, 16), (32, 16, 16)])
 @pytest.mark.parametrize("missing", [0.0, 0.2])
 def test_square_root_filter_batched_logp_grad(eng, shape, missing):
     """SquareRootFilter forward + QR adjoint (P0 is a factor; H, Q gradients in the lower-triangular convention)."""
