@@ -493,7 +493,8 @@ static int logp_grad_impl(bkf_handle* h, const bkf_problem* P, const void* y, co
         // the trajectory layout is private to a kernel family: dense [a | P] records, or DMMA fragment records
         const bool frag = sizeof(R) == 8 && P->kind != BKF_CHOLESKY && !P->tv_mask &&
                           !tps::supported(P->kind, P->m, P->p) && tc::supported(P->kind, P->m, P->p);
-        const size_t rec = frag ? tc::traj_record_elems() : m + m * m;
+        const size_t rec = P->kind == BKF_CHOLESKY ? sq::traj_record_elems_host(P->m, P->p)
+                                                   : (frag ? tc::traj_record_elems() : m + m * m);
         g.traj = (R*)ensure(h, S_TRAJ, B * n * rec * sizeof(R), &rc);
     }
     int* dstatus = nullptr;

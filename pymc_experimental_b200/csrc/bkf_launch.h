@@ -11,6 +11,7 @@ template <typename R> int launch_backward(const KArgs<R>& g, cudaStream_t stream
 template <typename R> int launch_smoother(const KArgs<R>& g, cudaStream_t stream, const char** err);
 }  // namespace gen
 namespace sq {  // square-root filter, CTA per series (bkf_sqrt.cu)
+size_t traj_record_elems_host(int m, int p);  // forward-sweep record kept for the adjoint (a, Pc, R factors)
 template <typename R> int launch_forward(const KArgs<R>& g, cudaStream_t stream, const char** err);
 template <typename R> int launch_backward(const KArgs<R>& g, cudaStream_t stream, const char** err);
 }  // namespace sq

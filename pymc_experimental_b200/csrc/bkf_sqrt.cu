@@ -411,6 +411,30 @@ __device__ void chol_pullback(R* out, const R* L, const R* Lbar, int k, R* tmp, 
     __syncthreads();
 }
 
+// Doubles per (series, step) record of the forward sweep kept for the adjoint:
+// [a (m) | Pc (m x m) | upper triangle of Rf ((p+m) x (p+m)) | upper triangle of Rp (m x m)]
+__host__ __device__ inline size_t traj_record_elems(int m, int p) {
+    const size_t N1 = (size_t)p + m;
+    return (size_t)m + (size_t)m * m + N1 * (N1 + 1) / 2 + (size_t)m * (m + 1) / 2;
+}
+
+// Upper triangle of the leading n x n block of W (row-major, ld) <-> packed rows (row i holds n - i entries).
+template <typename R>
+__device__ void store_upper(R* __restrict__ dst, const R* __restrict__ W, int ld, int n, Th th) {
+    for (int idx = th.tid; idx < n * n; idx += th.nt) {
+        int i = idx / n, j = idx - i * n;
+        if (j >= i) dst[i * n - (i * (i - 1)) / 2 + (j - i)] = W[i * ld + j];
+    }
+}
+template <typename R>
+__device__ void load_upper(R* __restrict__ W, int ld, int rows, int n, const R* __restrict__ src, Th th) {
+    for (int idx = th.tid; idx < rows * n; idx += th.nt) {
+        int i = idx / n, j = idx - i * n;
+        W[i * ld + j] = (i < n && j >= i) ? src[i * n - (i * (i - 1)) / 2 + (j - i)] : R(0);
+    }
+    __syncthreads();
+}
+
 // ----------------------------------------------------------------------------------------------------
 template <typename R>
 struct Arena {
@@ -485,7 +509,8 @@ __device__ int setup(const KArgs<R>& g, Arena<R>& A, int b, bool* Hzero_out, Th 
 // M0, Rp in the arena and returns ll.  flag = all observations missing; partial = some (the reference's
 // cholesky(W H) fails there: NaN is propagated).
 template <typename R>
-__device__ R step(const KArgs<R>& g, Arena<R>& A, const R* yt, bool Hzero, bool* flag_out, Th th) {
+__device__ R step(const KArgs<R>& g, Arena<R>& A, const R* yt, bool Hzero, bool* flag_out, const R* Rf_stored,
+                  Th th) {
     const int m = g.m, p = g.p, r = g.r, N1 = p + m;
     for (int o = th.tid; o < p; o += th.nt) {
         R yv = yt[o];
@@ -533,13 +558,14 @@ __device__ R step(const KArgs<R>& g, Arena<R>& A, const R* yt, bool Hzero, bool*
             __syncthreads();
         }
     }
-    qr_r(A.Rf, N1, N1, A.red, A.hv, A.ht, A.hw, th);
+    if (Rf_stored) load_upper(A.Rf, N1, N1, N1, Rf_stored, th);  // the adjoint sweep reuses the forward factor
+    else qr_r(A.Rf, N1, N1, A.red, A.hv, A.ht, A.hw, th);
     *flag_out = flag;
     return R(0);
 }
 
 template <typename R>
-__device__ R finish_update(const KArgs<R>& g, Arena<R>& A, bool flag, Th th) {
+__device__ R finish_update(const KArgs<R>& g, Arena<R>& A, bool flag, bool need_ll, Th th) {
     const int m = g.m, p = g.p, N1 = p + m;
     R ll = 0;
     if (!flag) {
@@ -557,9 +583,11 @@ __device__ R finish_update(const KArgs<R>& g, Arena<R>& A, bool flag, Th th) {
         }
         __syncthreads();
         R quad = 0, logdet = 0;
-        for (int o = 0; o < p; ++o) quad = fma(A.v[o], A.inner[o], quad);
-        for (int o = th.tid; o < p; o += th.nt) logdet += log(fabs(A.Rf[o * N1 + o]));
-        logdet = block_sum(logdet, A.red, th);
+        if (need_ll) {
+            for (int o = 0; o < p; ++o) quad = fma(A.v[o], A.inner[o], quad);
+            for (int o = th.tid; o < p; o += th.nt) logdet += log(fabs(A.Rf[o * N1 + o]));
+            logdet = block_sum(logdet, A.red, th);
+        }
         ll = R(-0.5) * (R(p) * (R(kLog2Pi) + R(2) * logdet) + quad);  // :696 (quirk Q2)
         for (int i = th.tid; i < m; i += th.nt) {
             R acc = 0;
@@ -580,7 +608,7 @@ __device__ R finish_update(const KArgs<R>& g, Arena<R>& A, bool flag, Th th) {
 
 // predict: M0 = [T Pcf, R Qc]^T ((m+r) x m), Rp = its R factor; next (a, Pc) written to (a_next, Pc_next).
 template <typename R>
-__device__ void predict(const KArgs<R>& g, Arena<R>& A, R* a_next, R* Pc_next, Th th) {
+__device__ void predict(const KArgs<R>& g, Arena<R>& A, R* a_next, R* Pc_next, const R* Rp_stored, Th th) {
     const int m = g.m, r = g.r;
     bool tp_done = false;
     if constexpr (sizeof(R) == 8) {
@@ -607,7 +635,8 @@ __device__ void predict(const KArgs<R>& g, Arena<R>& A, R* a_next, R* Pc_next, T
         A.Rp[idx] = val;
     }
     __syncthreads();
-    qr_r(A.Rp, m + r, m, A.red, A.hv, A.ht, A.hw, th);
+    if (Rp_stored) load_upper(A.Rp, m, m + r, m, Rp_stored, th);
+    else qr_r(A.Rp, m + r, m, A.red, A.hv, A.ht, A.hw, th);
     if (a_next) {
         for (int i = th.tid; i < m; i += th.nt) {
             R acc = 0;
@@ -635,7 +664,8 @@ __global__ void __launch_bounds__(256, 2) forward_kernel(KArgs<R> g) {
     bcopy(A.a, param_ptr(g.a0, g.shared_mask, BKF_PARAM_A0, b, (size_t)m), m, th);
     bcopy(A.Pc, param_ptr(g.P0, g.shared_mask, BKF_PARAM_P0, b, (size_t)m * m), m * m, th);
     const R* yb = g.y_shared ? g.y : g.y + (size_t)b * n * p;
-    const size_t tstride = (size_t)m + (size_t)m * m;
+    const size_t tstride = traj_record_elems(m, p);
+    const size_t off_rf = (size_t)m + (size_t)m * m, off_rp = off_rf + (size_t)N1 * (N1 + 1) / 2;
     auto write_sq = [&](R* dst, const R* L, int k, int ls0, int ls1) {  // dst = L L^T with L(i,q) = L[i*ls0 + q*ls1]
         for (int idx = th.tid; idx < k * k; idx += th.nt) {
             int i = idx / k, j = idx - i * k;
@@ -654,16 +684,23 @@ __global__ void __launch_bounds__(256, 2) forward_kernel(KArgs<R> g) {
         if (g.pred_a) bcopy(g.pred_a + bt * m, A.a, m, th);
         if (g.pred_P) write_sq(g.pred_P + bt * m * m, A.Pc, m, m, 1);
         bool flag;
-        step(g, A, yb + (size_t)t * p, Hzero, &flag, th);
+        step(g, A, yb + (size_t)t * p, Hzero, &flag, (const R*)nullptr, th);
+        if (g.traj) store_upper(g.traj + bt * tstride + off_rf, A.Rf, N1, N1, th);
         if (g.obs_mu) bcopy(g.obs_mu + bt * p, A.sv, p, th);
         if (g.obs_cov) write_sq(g.obs_cov + bt * p * p, A.Rf, p, 1, N1);  // F_chol[i,q] = Rf[q,i]
         __syncthreads();
-        const R ll = finish_update(g, A, flag, th);
+        const R ll = finish_update(g, A, flag, true, th);
         if (g.filt_a) bcopy(g.filt_a + bt * m, A.af, m, th);
         if (g.filt_P) write_sq(g.filt_P + bt * m * m, A.Pcf, m, m, 1);
         if (g.ll && th.tid == 0) g.ll[bt] = ll;
         logp += ll;
-        predict(g, A, A.a, A.Pc, th);
+        if (g.traj) {  // Rp is complete once predict() has run; A.Pc (= Rp^T) is only read by the next step
+            predict(g, A, A.a, A.Pc, (const R*)nullptr, th);
+            store_upper(g.traj + bt * tstride + off_rp, A.Rp, m, m, th);
+            __syncthreads();
+        } else {
+            predict(g, A, A.a, A.Pc, (const R*)nullptr, th);
+        }
     }
     if (!isfinite(logp)) st |= BKF_STATUS_NONFINITE;
     if (th.tid == 0) {
@@ -686,16 +723,18 @@ __global__ void backward_kernel(KArgs<R> g) {
     bzero(A.abar, m, th); bzero(A.Pbar, m * m, th); bzero(A.gT, m * m, th); bzero(A.Psum, m * m, th);
     bzero(A.gZ, p * m, th); bzero(A.gc, m, th); bzero(A.gd, p, th); bzero(A.Hcbar, p * p, th);
     const R* yb = g.y_shared ? g.y : g.y + (size_t)b * n * p;
-    const size_t tstride = (size_t)m + (size_t)m * m;
+    const size_t tstride = traj_record_elems(m, p);
+    const size_t off_rf = (size_t)m + (size_t)m * m, off_rp = off_rf + (size_t)N1 * (N1 + 1) / 2;
     for (int t = n - 1; t >= 0; --t) {
         const size_t bt = (size_t)b * n + t;
         const R gcot = g.ll_cot ? g.ll_cot[bt] : R(1);
         bcopy(A.a, g.traj + bt * tstride, m, th);
         bcopy(A.Pc, g.traj + bt * tstride + m, m * m, th);
         bool flag;
-        step(g, A, yb + (size_t)t * p, Hzero, &flag, th);
-        finish_update(g, A, flag, th);
-        predict(g, A, (R*)nullptr, (R*)nullptr, th);
+        // the two R factors come from the forward sweep's record: no Householder QR in the adjoint
+        step(g, A, yb + (size_t)t * p, Hzero, &flag, g.traj + bt * tstride + off_rf, th);
+        finish_update(g, A, flag, false, th);
+        predict(g, A, (R*)nullptr, (R*)nullptr, g.traj + bt * tstride + off_rp, th);
         // ================= predict adjoint =================
         // Rp_bar = triu(Pbar^T): Rbar(i,j) = Pbar[j*m + i]  ->  strides (rs0, rs1) = (1, m)
         qr_pullback_psi(A.Psi, A.Rp, m, m, A.Pbar, 1, m, A.S1, A.uinv, th);
@@ -721,35 +760,46 @@ __global__ void backward_kernel(KArgs<R> g) {
         }
         // ================= update adjoint =================
         // sbar = KF^T afbar, KF[i,o] = Rf[o, p+i];  loss/logdet cotangents;  the two lower solves with Fc = Rf[:p,:p]^T
-        if (th.tid == 0) {
+        if (th.tid < 32) {  // warp 0 (every launch configuration has at least one full warp)
+            const int lane = th.tid;
             const R lossbar = R(-0.5) * gcot, logdetbar = R(-0.5) * gcot * R(p);
-            for (int o = 0; o < p; ++o) {
+            // column-oriented back substitution  x <- U^{-1} x  with U = Fc^T = Rf[:p,:p] (upper), x in shared memory
+            auto solve_fcT = [&](R* x) {
+                for (int i = p - 1; i >= 0; --i) {
+                    __syncwarp();
+                    const R xi = x[i] / A.Rf[i * N1 + i];
+                    __syncwarp();
+                    if (lane == 0) x[i] = xi;
+                    for (int q = lane; q < i; q += 32) x[q] = fma(-A.Rf[q * N1 + i], xi, x[q]);
+                }
+                __syncwarp();
+            };
+            for (int o = lane; o < p; o += 32) {
                 R acc = 0;
                 for (int i = 0; i < m; ++i) acc = fma(A.Rf[o * N1 + (p + i)], A.afbar[i], acc);
                 A.sbar[o] = acc;
                 A.vbar[o] = lossbar * A.inner[o];
+                A.t1[o] = lossbar * A.v[o];
             }
-            // t1 = Fc^{-T} innerbar  (Fc^T = Rf[:p,:p] upper)
-            for (int i = p - 1; i >= 0; --i) {
-                R tt = lossbar * A.v[i];
-                for (int q = i + 1; q < p; ++q) tt -= A.Rf[i * N1 + q] * A.t1[q];
-                A.t1[i] = tt / A.Rf[i * N1 + i];
-            }
+            solve_fcT(A.t1);  // t1 = Fc^{-T} innerbar
             // Bbar's Fc block goes straight into Abar scratch: Fcbar = tril(-t1 inner^T - t2 s^T) + diag(...)
-            for (int i = 0; i < p; ++i) A.sbar[i] += A.t1[i];
-            for (int i = 0; i < p; ++i)
-                for (int j = 0; j <= i; ++j) A.Abar[i * N1 + j] = -A.t1[i] * A.inner[j];
-            // t2 = Fc^{-T} sbar  (reuse t1)
-            for (int i = p - 1; i >= 0; --i) {
-                R tt = A.sbar[i];
-                for (int q = i + 1; q < p; ++q) tt -= A.Rf[i * N1 + q] * A.t1[q];
-                A.t1[i] = tt / A.Rf[i * N1 + i];
+            for (int idx = lane; idx < p * p; idx += 32) {
+                int i = idx / p, j = idx - i * p;
+                if (j <= i) A.Abar[i * N1 + j] = -A.t1[i] * A.inner[j];
             }
-            for (int i = 0; i < p; ++i) {
-                A.vbar[i] += A.t1[i];
-                for (int j = 0; j <= i; ++j) A.Abar[i * N1 + j] -= A.t1[i] * A.sv[j];
-                A.Abar[i * N1 + i] += logdetbar * R(2) / A.Rf[i * N1 + i];
+            for (int i = lane; i < p; i += 32) A.sbar[i] += A.t1[i];
+            __syncwarp();
+            for (int i = lane; i < p; i += 32) A.t1[i] = A.sbar[i];
+            solve_fcT(A.t1);  // t2 = Fc^{-T} sbar  (reuse t1)
+            for (int idx = lane; idx < p * p; idx += 32) {
+                int i = idx / p, j = idx - i * p;
+                if (j <= i) {
+                    R val = A.Abar[i * N1 + j] - A.t1[i] * A.sv[j];
+                    if (i == j) val += logdetbar * R(2) / A.Rf[i * N1 + i];
+                    A.Abar[i * N1 + j] = val;
+                }
             }
+            for (int i = lane; i < p; i += 32) A.vbar[i] += A.t1[i];
         }
         __syncthreads();
         // Bbar (lower, N1 x N1) assembled in Abar: [Fcbar 0; KFbar tril(Pcfbar)],  KFbar = afbar s^T
@@ -773,19 +823,40 @@ __global__ void backward_kernel(KArgs<R> g) {
             if (Hzero) A.Hcbar[idx] += A.w[i] * A.Abar[j * N1 + i];
             else if (j <= i) A.Hcbar[idx] += A.Abar[j * N1 + i];
         }
-        for (int idx = th.tid; idx < m * m; idx += th.nt) {
-            int i = idx / m, j = idx - i * m;
-            R acc = A.Abar[(p + j) * N1 + (p + i)];
-            for (int o = 0; o < p; ++o) acc = fma(A.Zm[o * m + i], A.Abar[(p + j) * N1 + o], acc);
-            A.Pbar[idx] = acc;
+        bool blocks_done = false;
+        if constexpr (sizeof(R) == 8) {
+            if (th.fast) {
+                for (int idx = th.tid; idx < m * m; idx += th.nt) {
+                    int i = idx / m, j = idx - i * m;
+                    A.Pbar[idx] = A.Abar[(p + j) * N1 + (p + i)];
+                }
+                __syncthreads();
+                // Pbar += Zm^T ZPbar,  ZPbar(o, j) = Abar[(p+j), o]
+                mm_dmma<ADD, 0>(A.Pbar, m, 1, A.Zm, 1, m, A.Abar + p * N1, 1, N1, m, m, p, th);
+                // S1[:p*m] = ZPbar Pc^T
+                mm_dmma<SET, 0>(A.S1, m, 1, A.Abar + p * N1, 1, N1, A.Pc, 1, m, p, m, m, th);
+                for (int idx = th.tid; idx < p * m; idx += th.nt) {
+                    int o = idx / m, j = idx - o * m;
+                    A.gZ[idx] = fma(A.w[o], fma(-A.vbar[o], A.a[j], A.S1[idx]), A.gZ[idx]);
+                }
+                blocks_done = true;
+            }
         }
-        // Zmbar = ZPbar Pc^T - vbar a^T ; gZ += W Zmbar ; abar = afbar - Zm^T vbar ; gd -= vbar
-        for (int idx = th.tid; idx < p * m; idx += th.nt) {
-            int o = idx / m, j = idx - o * m;
-            R acc = 0;
-            for (int q = 0; q < m; ++q) acc = fma(A.Abar[(p + q) * N1 + o], A.Pc[j * m + q], acc);
-            acc = fma(-A.vbar[o], A.a[j], acc);
-            A.gZ[idx] = fma(A.w[o], acc, A.gZ[idx]);
+        if (!blocks_done) {
+            for (int idx = th.tid; idx < m * m; idx += th.nt) {
+                int i = idx / m, j = idx - i * m;
+                R acc = A.Abar[(p + j) * N1 + (p + i)];
+                for (int o = 0; o < p; ++o) acc = fma(A.Zm[o * m + i], A.Abar[(p + j) * N1 + o], acc);
+                A.Pbar[idx] = acc;
+            }
+            // Zmbar = ZPbar Pc^T - vbar a^T ; gZ += W Zmbar ; abar = afbar - Zm^T vbar ; gd -= vbar
+            for (int idx = th.tid; idx < p * m; idx += th.nt) {
+                int o = idx / m, j = idx - o * m;
+                R acc = 0;
+                for (int q = 0; q < m; ++q) acc = fma(A.Abar[(p + q) * N1 + o], A.Pc[j * m + q], acc);
+                acc = fma(-A.vbar[o], A.a[j], acc);
+                A.gZ[idx] = fma(A.w[o], acc, A.gZ[idx]);
+            }
         }
         for (int i = th.tid; i < m; i += th.nt) {
             R acc = A.afbar[i];
@@ -847,6 +918,7 @@ static int launch(const KArgs<R>& g, bool bwd, cudaStream_t stream, const char**
     return BKF_OK;
 }
 
+size_t traj_record_elems_host(int m, int p) { return traj_record_elems(m, p); }
 template <typename R> int launch_forward(const KArgs<R>& g, cudaStream_t s, const char** err) { return launch<R>(g, false, s, err); }
 template <typename R> int launch_backward(const KArgs<R>& g, cudaStream_t s, const char** err) { return launch<R>(g, true, s, err); }
 template int launch_forward<double>(const KArgs<double>&, cudaStream_t, const char**);
