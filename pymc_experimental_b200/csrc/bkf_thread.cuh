@@ -170,8 +170,11 @@ __global__ void __launch_bounds__(128) forward_kernel(KArgs<R> g) {
     const R* yb = g.y_shared ? g.y : g.y + (size_t)b * n;
     R logp = 0;
     Step<R, M> s;
+    R ynext = yb[0];
     for (int t = 0; t < n; ++t) {
         const size_t bt = (size_t)b * n + t;
+        const R yt = ynext;
+        if (t + 1 < n) ynext = yb[t + 1];  // one step ahead: the load latency hides behind this step's arithmetic
         if (g.traj && t > 0) {  // batch-innermost SoA record: [t][e][b]
             R* tr = g.traj + (size_t)t * C::REC * B + b;
             int e = 0;
@@ -188,7 +191,7 @@ __global__ void __launch_bounds__(128) forward_kernel(KArgs<R> g) {
         if (g.pred_P)
 #pragma unroll
             for (int i = 0; i < M * M; ++i) g.pred_P[bt * M * M + i] = P[i / M][i % M];
-        update<R, M, KIND>(s, k, a, P, yb[t], g.fill, g.jitter);
+        update<R, M, KIND>(s, k, a, P, yt, g.fill, g.jitter);
         logp += s.ll;
         if (g.ll) g.ll[bt] = s.ll;
         if (g.obs_mu) g.obs_mu[bt] = s.yhat;
@@ -256,22 +259,36 @@ __global__ void __launch_bounds__(128) backward_kernel(KArgs<R> g) {
         for (int j = 0; j < M; ++j) { Pbar[i][j] = 0; gT[i][j] = 0; Gsum[i][j] = 0; }
     }
     Step<R, M> s;
-    for (int t = n - 1; t >= 0; --t) {
-        const R gcot = g.ll_cot ? g.ll_cot[(size_t)b * n + t] : R(1);
-        R a[M], P[M][M];
+    // Software pipeline: the record, observation and cotangent of step t-1 are requested at the top of step t, so
+    // their HBM latency hides behind a full step of arithmetic (the kernel runs at ~8 warps/SM: latency is not hidden
+    // by occupancy).
+    R rec[C::REC], ynext, cnext;
+    auto fetch = [&](int t) {
         if (t > 0) {
             const R* tr = g.traj + (size_t)t * C::REC * B + b;
+#pragma unroll
+            for (int e = 0; e < C::REC; ++e) rec[e] = __ldcs(tr + (size_t)e * B);
+        }
+        ynext = yb[t];
+        cnext = g.ll_cot ? g.ll_cot[(size_t)b * n + t] : R(1);
+    };
+    fetch(n - 1);
+    for (int t = n - 1; t >= 0; --t) {
+        const R gcot = cnext, yt = ynext;
+        R a[M], P[M][M];
+        if (t > 0) {
             int e = 0;
 #pragma unroll
-            for (int i = 0; i < M; ++i) a[i] = tr[(size_t)(e++) * B];
+            for (int i = 0; i < M; ++i) a[i] = rec[e++];
 #pragma unroll
             for (int i = 0; i < M; ++i)
 #pragma unroll
                 for (int j = 0; j <= i; ++j) {
-                    const R v = tr[(size_t)(e++) * B];
+                    const R v = rec[e++];
                     P[i][j] = v;
                     P[j][i] = v;
                 }
+            fetch(t - 1);
         } else {
 #pragma unroll
             for (int i = 0; i < M; ++i) {
@@ -280,7 +297,7 @@ __global__ void __launch_bounds__(128) backward_kernel(KArgs<R> g) {
                 for (int j = 0; j < M; ++j) P[i][j] = P0g[i * M + j];
             }
         }
-        update<R, M, KIND>(s, k, a, P, yb[t], g.fill, g.jitter);
+        update<R, M, KIND>(s, k, a, P, yt, g.fill, g.jitter);
         // ---- predict adjoint ----
         R G[M][M], W[M][M], Pfb[M][M], afbar[M];
 #pragma unroll
