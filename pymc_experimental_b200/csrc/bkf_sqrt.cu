@@ -569,17 +569,23 @@ __device__ R finish_update(const KArgs<R>& g, Arena<R>& A, bool flag, bool need_
     const int m = g.m, p = g.p, N1 = p + m;
     R ll = 0;
     if (!flag) {
-        if (th.tid == 0) {  // s = Fc^{-1} v ; inner = Fc^{-1} s   with Fc[i,q] = Rf[q,i]   (:686-691)
-            for (int i = 0; i < p; ++i) {
-                R tt = A.v[i];
-                for (int q = 0; q < i; ++q) tt -= A.Rf[q * N1 + i] * A.sv[q];
-                A.sv[i] = tt / A.Rf[i * N1 + i];
-            }
-            for (int i = 0; i < p; ++i) {
-                R tt = A.sv[i];
-                for (int q = 0; q < i; ++q) tt -= A.Rf[q * N1 + i] * A.inner[q];
-                A.inner[i] = tt / A.Rf[i * N1 + i];
-            }
+        if (th.tid < 32) {  // s = Fc^{-1} v ; inner = Fc^{-1} s   with Fc[i,q] = Rf[q,i]   (:686-691)
+            // warp 0, column-oriented forward substitution: x_i /= Fc[i,i];  x_q -= Fc[q,i] x_i (q > i) across lanes
+            const int lane = th.tid;
+            auto solve_fc = [&](R* x) {
+                for (int i = 0; i < p; ++i) {
+                    __syncwarp();
+                    const R xi = x[i] / A.Rf[i * N1 + i];
+                    __syncwarp();
+                    if (lane == 0) x[i] = xi;
+                    for (int q = i + 1 + lane; q < p; q += 32) x[q] = fma(-A.Rf[i * N1 + q], xi, x[q]);
+                }
+                __syncwarp();
+            };
+            for (int i = lane; i < p; i += 32) A.sv[i] = A.v[i];
+            solve_fc(A.sv);
+            for (int i = lane; i < p; i += 32) A.inner[i] = A.sv[i];
+            solve_fc(A.inner);
         }
         __syncthreads();
         R quad = 0, logdet = 0;
