@@ -21,38 +21,17 @@ size_t traj_record_elems() { return REC; }
 int launch_f64(const KArgs<double>& g, bool backward, cudaStream_t stream, const char** err) {
     const int warps = 2;
     const int grid = (g.B + warps - 1) / warps;
-    static const bool bwd_regs = getenv("BKF_BWD_SMEM") == nullptr;  // default: register-resident accumulators
-    const bool sm = backward && !bwd_regs;
-    const size_t smem = (size_t)warps * (SCRATCH + (sm ? WS_TOTAL : 0)) * sizeof(double);
-    // OUT: the per-step filter outputs are requested (the logp+grad path only needs logp and the trajectory)
+    const size_t smem = (size_t)warps * SCRATCH * sizeof(double);
     static const bool occ8 = getenv("BKF_FWD_NOCAP") == nullptr;  // default: cap at 128 registers, 8 CTAs/SM
+    // OUT: the per-step filter outputs are requested (the logp+grad path only needs logp and the trajectory)
     const bool out = g.filt_a || g.filt_P || g.pred_a || g.pred_P || g.obs_mu || g.obs_cov;
-    if (sm) {
-        static bool attr_done = false;
-        if (!attr_done) {
-            attr_done = true;
-            cudaFuncSetAttribute(backward_kernel<K_UNI, true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-            cudaFuncSetAttribute(backward_kernel<K_STD, true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-            if (getenv("BKF_DEBUG")) {
-                int nb = 0;
-                cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, backward_kernel<K_UNI, true>, 32 * warps, smem);
-                fprintf(stderr, "[bkf] dmma backward (smem accumulators): %d CTAs/SM, %zu B smem/CTA\n", nb, smem);
-                cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, backward_kernel<K_UNI, false>, 32 * warps, (size_t)warps * SCRATCH * 8);
-                fprintf(stderr, "[bkf] dmma backward (register accumulators): %d CTAs/SM\n", nb);
-                cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, forward_kernel<K_UNI, false, 8>, 32 * warps, (size_t)warps * SCRATCH * 8);
-                fprintf(stderr, "[bkf] dmma forward occ8: %d CTAs/SM\n", nb);
-            }
-        }
-    }
     if (g.kind == BKF_UNIVARIATE) {
-        if (backward && sm) backward_kernel<K_UNI, true><<<grid, 32 * warps, smem, stream>>>(g);
-        else if (backward) backward_kernel<K_UNI, false><<<grid, 32 * warps, smem, stream>>>(g);
+        if (backward) backward_kernel<K_UNI><<<grid, 32 * warps, smem, stream>>>(g);
         else if (out) forward_kernel<K_UNI, true, 1><<<grid, 32 * warps, smem, stream>>>(g);
         else if (occ8) forward_kernel<K_UNI, false, 8><<<grid, 32 * warps, smem, stream>>>(g);
         else forward_kernel<K_UNI, false, 1><<<grid, 32 * warps, smem, stream>>>(g);
     } else {
-        if (backward && sm) backward_kernel<K_STD, true><<<grid, 32 * warps, smem, stream>>>(g);
-        else if (backward) backward_kernel<K_STD, false><<<grid, 32 * warps, smem, stream>>>(g);
+        if (backward) backward_kernel<K_STD><<<grid, 32 * warps, smem, stream>>>(g);
         else if (out) forward_kernel<K_STD, true, 1><<<grid, 32 * warps, smem, stream>>>(g);
         else if (occ8) forward_kernel<K_STD, false, 8><<<grid, 32 * warps, smem, stream>>>(g);
         else forward_kernel<K_STD, false, 1><<<grid, 32 * warps, smem, stream>>>(g);

@@ -14,7 +14,7 @@
 // Vectors live either in "row form" (x[8I+g], replicated over t) or "column form" (x[8J+2t+e], replicated over
 // g); matrix-vector products and rank-1 updates are a handful of FMAs plus quad shuffles.  The prediction
 // trajectory (a_t|t-1, P_t|t-1) that the adjoint needs is spilled in fragment order (perfectly coalesced
-// 16-byte accesses, REC = 272 doubles per state-step).
+// 16-byte accesses, REC = 292 doubles per state-step: P, a, and the update scalars P z^T, v, F the adjoint reuses).
 //
 // Reference formulas: kalman_filter.py:529-539 (step), :594-617 (StandardFilter.update, p = 1),
 // :769-820 (UnivariateFilter, p = 1), :407-408 (predict); adjoint: SURVEY.md Appendix B specialised to p = 1.
@@ -26,7 +26,10 @@ namespace tc {
 
 enum { K_STD = 0, K_UNI = 1 };
 constexpr int MP = 16;              // padded state dimension
-constexpr int REC = MP * MP + MP;   // doubles per trajectory record: P fragments (256) then a (16)
+constexpr int REC_A = MP * MP;      // trajectory record: P fragments (256) | a (16) | P z^T (16) | v, F, 1/F-or-0, pad
+constexpr int REC_PZ = REC_A + MP;
+constexpr int REC_S = REC_PZ + MP;
+constexpr int REC = REC_S + 4;      // 292 doubles per state-step
 constexpr int SLD = 18;             // leading dimension of the per-warp transpose scratch (conflict-free, 16 B rows)
 constexpr int SCRATCH = MP * SLD;   // doubles of scratch per warp
 constexpr unsigned FULL = 0xffffffffu;
@@ -201,9 +204,9 @@ __device__ __forceinline__ void store_rec(double* __restrict__ base, const Frag&
     for (int I = 0; I < 2; ++I)
 #pragma unroll
         for (int J = 0; J < 2; ++J) __stcs(dst + (2 * I + J) * 32 + lane, make_double2(P.v[I][J][0], P.v[I][J][1]));
-    if (lane < 4) {
-#pragma unroll
-        for (int J = 0; J < 2; ++J) __stcs(dst + 128 + 4 * J + lane, make_double2(a_c.v[J][0], a_c.v[J][1]));
+    if (lane < 8) {  // lane L holds chunk L of a in column form: t = L & 3, J = L >> 2
+        const int J = lane >> 2;
+        __stcs(dst + REC_A / 2 + lane, make_double2(J ? a_c.v[1][0] : a_c.v[0][0], J ? a_c.v[1][1] : a_c.v[0][1]));
     }
 }
 __device__ __forceinline__ void load_rec(const double* __restrict__ base, Frag& P, RVec& a_r, CVec& a_c, int lane) {
@@ -225,6 +228,41 @@ __device__ __forceinline__ void load_rec(const double* __restrict__ base, Frag& 
     }
 #pragma unroll
     for (int I = 0; I < 2; ++I) a_r.v[I] = __ldcs(base + MP * MP + 8 * I + g);
+}
+
+// Update quantities of a step that the forward sweep has computed anyway and the adjoint would otherwise recompute
+// (a matrix-vector product, two reductions and a division per step): P z^T in both vector forms, v, F and
+// rFk = 1/F (univariate: 0 when the update is skipped, kalman_filter.py:777-782).
+struct Aux {
+    RVec pz_r;
+    CVec pz_c;
+    double v, F, rFk;
+};
+__device__ __forceinline__ void store_aux(double* __restrict__ base, const CVec& pz_c, double v, double F, double rFk,
+                                          int lane) {
+    // one 16-byte store per lane 8..17: lanes 8..15 write chunk (lane - 8) of P z^T (column form: t = lane & 3,
+    // J = (lane >> 2) & 1), lane 16 writes (v, F), lane 17 writes (rFk, 0)
+    const int J = (lane >> 2) & 1;
+    double2 val = make_double2(J ? pz_c.v[1][0] : pz_c.v[0][0], J ? pz_c.v[1][1] : pz_c.v[0][1]);
+    if (lane == 16) val = make_double2(v, F);
+    if (lane == 17) val = make_double2(rFk, 0.0);
+    if (lane >= 8 && lane < 18) __stcs(reinterpret_cast<double2*>(base + REC_PZ) + (lane - 8), val);
+}
+__device__ __forceinline__ void load_aux(const double* __restrict__ base, Aux& X, int lane) {
+    const int g = lane >> 2, t = lane & 3;
+    const double2* pc = reinterpret_cast<const double2*>(base + REC_PZ);
+#pragma unroll
+    for (int J = 0; J < 2; ++J) {
+        const double2 d = __ldcs(pc + 4 * J + t);
+        X.pz_c.v[J][0] = d.x;
+        X.pz_c.v[J][1] = d.y;
+    }
+    X.pz_r.v[0] = __ldcs(base + REC_PZ + g);
+    X.pz_r.v[1] = __ldcs(base + REC_PZ + 8 + g);
+    const double2 d = __ldcs(reinterpret_cast<const double2*>(base + REC_S));
+    X.v = d.x;
+    X.F = d.y;
+    X.rFk = __ldcs(base + REC_S + 2);
 }
 
 // sym(R Q R^T) in the C layout (once per series)
@@ -483,6 +521,7 @@ __device__ __forceinline__ void fwd_step(const KArgs<double>& G, const FwdConst&
         skip = miss;
     }
     ll_capture(L, lane, ts, F, v, skip);
+    if (G.traj) store_aux(G.traj + bt * REC, pz_c, v, F, rFk, lane);
     const double gain = rFk * v;
     if (OUT) {
         if (lane == 0) {
@@ -761,91 +800,21 @@ __device__ __forceinline__ void bwd_step(const KArgs<double>& G, const BwdConst&
     S.abar_c = row2col(S.abar_r, t);
 }
 
-constexpr int WS_TH = 0;                 // per-warp workspace of the SM backward variant (doubles)
-constexpr int WS_GS = WS_TH + MP * MP;
-constexpr int WS_ST = WS_GS + MP * MP;   // two trajectory stages of REC doubles
-constexpr int WS_TOTAL = WS_ST + 2 * REC;
-
-__device__ __forceinline__ void load_frag_smem(Frag& X, const double* base, int lane) {
-    const double2* src = reinterpret_cast<const double2*>(base);
-#pragma unroll
-    for (int I = 0; I < 2; ++I)
-#pragma unroll
-        for (int J = 0; J < 2; ++J) {
-            const double2 d = src[(2 * I + J) * 32 + lane];
-            X.v[I][J][0] = d.x;
-            X.v[I][J][1] = d.y;
-        }
-}
-__device__ __forceinline__ void store_frag_smem(double* base, const Frag& X, int lane) {
-    double2* dst = reinterpret_cast<double2*>(base);
-#pragma unroll
-    for (int I = 0; I < 2; ++I)
-#pragma unroll
-        for (int J = 0; J < 2; ++J) dst[(2 * I + J) * 32 + lane] = make_double2(X.v[I][J][0], X.v[I][J][1]);
-}
-__device__ __forceinline__ void load_rec_smem(const double* base, Frag& P, RVec& a_r, CVec& a_c, int lane) {
-    const int g = lane >> 2, t = lane & 3;
-    load_frag_smem(P, base, lane);
-    const double2* src = reinterpret_cast<const double2*>(base);
-#pragma unroll
-    for (int J = 0; J < 2; ++J) {
-        const double2 d = src[128 + 4 * J + t];
-        a_c.v[J][0] = d.x;
-        a_c.v[J][1] = d.y;
-    }
-#pragma unroll
-    for (int I = 0; I < 2; ++I) a_r.v[I] = base[MP * MP + 8 * I + g];
-}
-__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
-    unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(sa), "l"(gsrc) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
-__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::: "memory"); }
-
 // Reverse step for t >= 1 (P symmetric): branch-free, the DMMA chain (W', V, Pbar_f) only needs G, the update is
 // recomputed from (a, P) concurrently, P_f = P - coef (P z^T)(P z^T)^T + eps I (see fwd_step).
-//
-// SM = true: the accumulators Tbar/2 and sum_t G_t live in shared memory (ws + WS_TH, ws + WS_GS, fragment order) and
-// the trajectory record of this step is read from the shared-memory stage `st` (filled by cp.async one step ahead),
-// which frees ~70 registers per thread for a third resident warp per scheduler.
-template <int KIND, bool SM>
-__device__ __forceinline__ void bwd_step_sym(const KArgs<double>& G, const BwdConst& K, BwdState& S, const Frag& Preg,
-                                             const RVec& a_reg, const CVec& ac_reg, const double* st, double* ws,
-                                             double yv, double gcot, double* sc, int lane) {
+template <int KIND>
+__device__ __forceinline__ void bwd_step_sym(const KArgs<double>& G, const BwdConst& K, BwdState& S, const Frag& P,
+                                             const RVec& a_r, const CVec& a_c, const Aux& X, double yv, double gcot,
+                                             double* sc, int lane) {
     const int g = lane >> 2, t = lane & 3;
-    Frag P;
-    RVec a_r;
-    CVec a_c;
-    if (SM) {
-        load_rec_smem(st, P, a_r, a_c, lane);
-    } else {
-        P = Preg;
-        a_r = a_reg;
-        a_c = ac_reg;
-    }
     // ================= predict adjoint: products =================
     Frag W, V, Pfb;
-    if (SM) {
-        double2* gs = reinterpret_cast<double2*>(ws + WS_GS);
 #pragma unroll
-        for (int I = 0; I < 2; ++I)
+    for (int I = 0; I < 2; ++I)
 #pragma unroll
-            for (int J = 0; J < 2; ++J) {
-                double2 x = gs[(2 * I + J) * 32 + lane];
-                x.x += S.G.v[I][J][0];
-                x.y += S.G.v[I][J][1];
-                gs[(2 * I + J) * 32 + lane] = x;
-            }
-    } else {
+        for (int J = 0; J < 2; ++J)
 #pragma unroll
-        for (int I = 0; I < 2; ++I)
-#pragma unroll
-            for (int J = 0; J < 2; ++J)
-#pragma unroll
-                for (int e = 0; e < 2; ++e) S.Gsum.v[I][J][e] += S.G.v[I][J][e];
-    }
+            for (int e = 0; e < 2; ++e) S.Gsum.v[I][J][e] += S.G.v[I][J][e];
     mm_nt<false>(W, K.TTc, S.G);  // W' = T^T G
     transpose(V, W, sc, g, t);    // V = G T
     Pfb.v[0][0][0] = Pfb.v[0][0][1] = Pfb.v[0][1][0] = Pfb.v[0][1][1] = Pfb.v[1][1][0] = Pfb.v[1][1][1] = 0.0;
@@ -857,7 +826,6 @@ __device__ __forceinline__ void bwd_step_sym(const KArgs<double>& G, const BwdCo
     __syncwarp();
     // ================= recompute the update =================
     const bool miss = (KIND == K_UNI) ? isnan(yv) : (isnan(yv) || yv == G.fill);
-    const double ym = miss ? 0.0 : yv;
     const double Hm = miss ? 0.0 : K.H0;
     RVec zm_r;
     CVec zm_c;
@@ -867,23 +835,18 @@ __device__ __forceinline__ void bwd_step_sym(const KArgs<double>& G, const BwdCo
         zm_c.v[I][0] = miss ? 0.0 : K.z_c.v[I][0];
         zm_c.v[I][1] = miss ? 0.0 : K.z_c.v[I][1];
     }
-    const double v = ym - (K.d0 + dot_c(zm_c, a_c));
-    const RVec pz_r = mv(P, zm_c);
-    const CVec pz_c = row2col(pz_r, t);
-    const double f0 = dot_r(zm_r, pz_r);
-    double F, rF, rFk, coef, keep;
+    // P z^T, v, F, 1/F come from the forward sweep's record (store_aux)
+    const RVec pz_r = X.pz_r;
+    const CVec pz_c = X.pz_c;
+    const double v = X.v, F = X.F, rFk = X.rFk;
+    const double f0 = F - (Hm + G.jitter);  // only the standard adjoint reads it
+    double rF, coef, keep;
     if (KIND == K_UNI) {
-        const double F0 = f0 + Hm;
-        const bool skip = (F0 == 0.0) || miss;
-        F = F0 + G.jitter;
-        rF = 1.0 / F;
-        keep = skip ? 0.0 : 1.0;
-        rFk = skip ? 0.0 : rF;
+        keep = rFk != 0.0 ? 1.0 : 0.0;
+        rF = rFk;  // a skipped step multiplies every use by keep = 0
         coef = rFk;
     } else {
-        F = f0 + (Hm + G.jitter);
-        rF = 1.0 / F;
-        rFk = rF;
+        rF = rFk;
         coef = (F + G.jitter) * rF * rF;
         keep = miss ? 0.0 : 1.0;
     }
@@ -912,25 +875,18 @@ __device__ __forceinline__ void bwd_step_sym(const KArgs<double>& G, const BwdCo
             }
     }
     // ================= predict adjoint: T, c =================
-    {
-        Frag ThL;
-        if (SM) load_frag_smem(ThL, ws + WS_TH, lane);
-        Frag& Th = SM ? ThL : S.Th;
-        mm_nt<true>(Th, V, Pf);  // Tbar/2 += (G T) P_f
+    mm_nt<true>(S.Th, V, Pf);  // Tbar/2 += (G T) P_f
 #pragma unroll
-        for (int I = 0; I < 2; ++I) {
-            const double h = 0.5 * S.abar_r.v[I];  // Tbar += abar+ a_f^T
+    for (int I = 0; I < 2; ++I) {
+        const double h = 0.5 * S.abar_r.v[I];  // Tbar += abar+ a_f^T
 #pragma unroll
-            for (int J = 0; J < 2; ++J)
+        for (int J = 0; J < 2; ++J)
 #pragma unroll
-                for (int e = 0; e < 2; ++e) Th.v[I][J][e] = fma(h, af_c.v[J][e], Th.v[I][J][e]);
-        }
-        if (SM) store_frag_smem(ws + WS_TH, ThL, lane);
+            for (int e = 0; e < 2; ++e) S.Th.v[I][J][e] = fma(h, af_c.v[J][e], S.Th.v[I][J][e]);
     }
     const RVec afbar_r = mv(K.TTc, S.abar_c);  // T^T abar+
 #pragma unroll
     for (int I = 0; I < 2; ++I) S.gc_r.v[I] += S.abar_r.v[I];
-    if (SM) load_frag_smem(P, st, lane);  // re-read P instead of keeping it live across the products
     // ================= update adjoint =================
     if (KIND == K_UNI) {
         const double llbar = -0.5 * gcot;
@@ -1016,15 +972,14 @@ __device__ __forceinline__ void bwd_step_sym(const KArgs<double>& G, const BwdCo
     S.abar_c = row2col(S.abar_r, t);
 }
 
-template <int KIND, bool SM>
-__global__ void __launch_bounds__(64, SM ? 6 : 1) backward_kernel(KArgs<double> G) {
+template <int KIND>
+__global__ void __launch_bounds__(64) backward_kernel(KArgs<double> G) {
     extern __shared__ __align__(16) double smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int g = lane >> 2, t = lane & 3;
     const int b = blockIdx.x * (blockDim.x >> 5) + warp;
     if (b >= G.B) return;
-    double* sc = smem + warp * (SCRATCH + (SM ? WS_TOTAL : 0));
-    double* ws = sc + SCRATCH;
+    double* sc = smem + warp * SCRATCH;
     const int m = G.m, n = G.n;
 
     BwdConst K;
@@ -1055,39 +1010,26 @@ __global__ void __launch_bounds__(64, SM ? 6 : 1) backward_kernel(KArgs<double> 
     Frag P;
     RVec a_r;
     CVec a_c;
-    if (SM) {
-        store_frag_smem(ws + WS_TH, S.Th, lane);
-        store_frag_smem(ws + WS_GS, S.Gsum, lane);
-        auto prefetch = [&](int ts) {
-            const char* src = reinterpret_cast<const char*>(traj + (size_t)ts * REC);
-            char* dst = reinterpret_cast<char*>(ws + WS_ST + (ts & 1) * REC);
-            for (int q = lane; q < REC / 2; q += 32) cp_async16(dst + q * 16, src + q * 16);
-            cp_async_commit();
-        };
-        if (n > 1) prefetch(n - 1);
-#pragma unroll 1
-        for (int ts = n - 1; ts >= 1; --ts) {
-            cp_async_wait_all();
-            __syncwarp();
-            if (ts > 1) prefetch(ts - 1);
-            bwd_step_sym<KIND, true>(G, K, S, P, a_r, a_c, ws + WS_ST + (ts & 1) * REC, ws, yb[ts],
-                                     cot ? cot[ts] : 1.0, sc, lane);
-        }
-        __syncwarp();
-        load_frag_smem(S.Th, ws + WS_TH, lane);
-        load_frag_smem(S.Gsum, ws + WS_GS, lane);
-    } else {
+    {
         Frag Pn;
         RVec an_r;
         CVec an_c;
-        if (n > 1) load_rec(traj + (size_t)(n - 1) * REC, Pn, an_r, an_c, lane);
+        Aux Xn;
+        if (n > 1) {
+            load_rec(traj + (size_t)(n - 1) * REC, Pn, an_r, an_c, lane);
+            load_aux(traj + (size_t)(n - 1) * REC, Xn, lane);
+        }
 #pragma unroll 1
         for (int ts = n - 1; ts >= 1; --ts) {
             P = Pn;
             a_r = an_r;
             a_c = an_c;
-            if (ts > 1) load_rec(traj + (size_t)(ts - 1) * REC, Pn, an_r, an_c, lane);  // prefetch one step ahead
-            bwd_step_sym<KIND, false>(G, K, S, P, a_r, a_c, nullptr, nullptr, yb[ts], cot ? cot[ts] : 1.0, sc, lane);
+            const Aux X = Xn;
+            if (ts > 1) {  // prefetch one step ahead
+                load_rec(traj + (size_t)(ts - 1) * REC, Pn, an_r, an_c, lane);
+                load_aux(traj + (size_t)(ts - 1) * REC, Xn, lane);
+            }
+            bwd_step_sym<KIND>(G, K, S, P, a_r, a_c, X, yb[ts], cot ? cot[ts] : 1.0, sc, lane);
         }
     }
     {
