@@ -172,6 +172,20 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm), "source": "nvidia-smi"}
 
 
+def ncu_traffic(name, kernel, B, T):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of `kernel` from the committed ncu capture of this
+    exact workload size (profiles/ncu_traffic.json), else None."""
+    path = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    try:
+        with open(path) as f:
+            ent = json.load(f).get(name)
+    except (OSError, ValueError):
+        return None
+    if not ent or ent.get("B") != B or ent.get("T") != T or kernel not in ent:
+        return None
+    return {"bytes_per_launch": ent[kernel], "source": ent["source"]}
+
+
 def load_peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -409,6 +423,7 @@ def run_b200(args):
     else:
         roof = {"bound": "hbm", "achieved": ach_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": ach_gbs / hbm_peak,
                 "traffic": None}
+    roof["traffic"] = ncu_traffic(name, dom, B, T)
     roof.update({
         "kernel": dom, "kernel_ms": dom_ms, "kernel_share_of_step": ktimes[dom][0] / (ms if ms > 0 else 1.0),
         "algorithmic_flops_per_state_step": flops, "algorithmic_bytes_per_state_step": bytes_,

@@ -1,4 +1,5 @@
-// bkf_subwarp.cuh -- register-tiled "sub-warp per series" kernels, 5 <= m <= 16, p = 1, float64.
+// bkf_subwarp.cuh -- register-tiled "sub-warp per series" kernels, p = 1, float64; instantiated for 5 <= m <= 8
+// (9 <= m <= 16 moved to the FP64 tensor-core family, bkf_mma.cuh).
 //
 // Mapping (DESIGN.md "Kernels"): LPS = 8 or 16 lanes own one time-sequential filter; lane j keeps COLUMN j of
 // every m x m state matrix (P, P_f, Pbar, ...) in registers.  A dense product C = A B is evaluated as
