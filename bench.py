@@ -423,7 +423,10 @@ def run_b200(args):
     else:
         roof = {"bound": "hbm", "achieved": ach_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": ach_gbs / hbm_peak,
                 "traffic": None}
-    roof["traffic"] = ncu_traffic(name, dom, B, T)
+    tr = ncu_traffic(name, dom, B, T)
+    if tr is not None:
+        roof["traffic"] = tr["bytes_per_launch"]
+        roof["traffic_source"] = tr["source"]
     roof.update({
         "kernel": dom, "kernel_ms": dom_ms, "kernel_share_of_step": ktimes[dom][0] / (ms if ms > 0 else 1.0),
         "algorithmic_flops_per_state_step": flops, "algorithmic_bytes_per_state_step": bytes_,
