@@ -1,7 +1,4 @@
 // bkf_mma.cu -- launcher of the FP64 tensor-core (DMMA) warp-per-series kernels (see bkf_mma.cuh).
-#include <cstdio>
-#include <cstdlib>
-
 #include "bkf_mma.cuh"
 #include "bkf_mma_smooth.cuh"
 
@@ -22,19 +19,16 @@ int launch_f64(const KArgs<double>& g, bool backward, cudaStream_t stream, const
     const int warps = 2;
     const int grid = (g.B + warps - 1) / warps;
     const size_t smem = (size_t)warps * SCRATCH * sizeof(double);
-    static const bool occ8 = getenv("BKF_FWD_NOCAP") == nullptr;  // default: cap at 128 registers, 8 CTAs/SM
     // OUT: the per-step filter outputs are requested (the logp+grad path only needs logp and the trajectory)
     const bool out = g.filt_a || g.filt_P || g.pred_a || g.pred_P || g.obs_mu || g.obs_cov;
     if (g.kind == BKF_UNIVARIATE) {
         if (backward) backward_kernel<K_UNI><<<grid, 32 * warps, smem, stream>>>(g);
         else if (out) forward_kernel<K_UNI, true, 1><<<grid, 32 * warps, smem, stream>>>(g);
-        else if (occ8) forward_kernel<K_UNI, false, 8><<<grid, 32 * warps, smem, stream>>>(g);
-        else forward_kernel<K_UNI, false, 1><<<grid, 32 * warps, smem, stream>>>(g);
+        else forward_kernel<K_UNI, false, 8><<<grid, 32 * warps, smem, stream>>>(g);  // 128 registers: 8 CTAs/SM
     } else {
         if (backward) backward_kernel<K_STD><<<grid, 32 * warps, smem, stream>>>(g);
         else if (out) forward_kernel<K_STD, true, 1><<<grid, 32 * warps, smem, stream>>>(g);
-        else if (occ8) forward_kernel<K_STD, false, 8><<<grid, 32 * warps, smem, stream>>>(g);
-        else forward_kernel<K_STD, false, 1><<<grid, 32 * warps, smem, stream>>>(g);
+        else forward_kernel<K_STD, false, 8><<<grid, 32 * warps, smem, stream>>>(g);
     }
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { *err = cudaGetErrorString(e); return BKF_ERR_CUDA; }

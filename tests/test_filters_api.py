@@ -152,3 +152,28 @@ def test_eager_batched_build_graph_and_logp_grad(rng):
     assert_allclose(logp, ref_logp, rtol=1e-9)
     for k in names:
         assert_allclose(grads[k], ref_g[k], rtol=0, atol=1e-9 * np.abs(ref_g[k]).max())
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("cls", [StandardFilter, UnivariateFilter], ids=["StandardFilter", "UnivariateFilter"])
+def test_time_varying_inputs_are_detected_by_ndim_like_the_reference(cls, rng):
+    """test_kalman_filter.py:151-166 (time-varying matrices) + filters/utilities.py:8-47: inputs with one extra
+    leading (time) dimension become scan sequences; seq_names / non_seq_names are what PyMCStateSpace reads
+    (core/statespace.py:628, 1267, 2053, 2249)."""
+    from oracle import kalman_np as onp
+
+    p, m, r, n = 1, 5, 2, 10
+    data, a0, P0, c, d, T, Z, R, H, Q = make_test_inputs(p, m, r, n, rng)
+    Zt = np.repeat(Z[None], n, axis=0) * (1.0 + 0.1 * np.arange(n))[:, None, None]  # regression-style Z[t]
+    Qt = np.repeat(Q[None], n, axis=0) * (1.0 + 0.05 * np.arange(n))[:, None, None]
+    kf, ks = cls(), KalmanSmoother()
+    outs = kf.build_graph(data, a0, P0, c, d, T, Zt, R, H, Qt)
+    assert kf.seq_names == ["Z", "Q"] and kf.non_seq_names == ["c", "d", "T", "R", "H"]
+    ref = onp.kalman_filter(KIND[cls], data, a0, P0, c, d, T, Zt, R, H, Qt)
+    for o, e in zip(outs, ref):
+        assert_allclose(o, e.reshape(o.shape), rtol=1e-9, atol=1e-9 * max(1.0, np.abs(e).max()))
+    sa, sP = ks.build_graph(T, R, Qt, outs[0], outs[3])
+    assert ks.seq_names == ["Q"] and ks.non_seq_names == ["T", "R"]
+    ra, rP = onp.kalman_smoother(T, R, Qt, ref[0], ref[3])
+    assert_allclose(sa, ra, rtol=1e-8, atol=1e-8 * max(1.0, np.abs(ra).max()))
+    assert_allclose(sP, rP, rtol=1e-8, atol=1e-8 * max(1.0, np.abs(rP).max()))
