@@ -448,38 +448,39 @@ struct Arena {
     R *abar, *Pbar, *S1, *Psi, *Abar, *gT, *gZ, *gc, *gd, *Psum, *Hcbar, *afbar, *Pcfbar, *U1, *vbar, *sbar, *t1;
 };
 
+// The forward sweep keeps only what it reads again: the update array is factored in place (A0 aliases Rf), so is the
+// predict array (M0 aliases Rp), and Pcf overwrites Pc -- 72 KB at the C4 shape, three CTAs per SM.  The adjoint sweep
+// needs the unfactored arrays next to the factors and its own accumulators (one CTA per SM at C4).
 __host__ __device__ inline size_t arena_elems(int m, int p, int r, bool bwd) {
     size_t mm_ = (size_t)m * m, pm = (size_t)p * m, pp = (size_t)p * p, rr = (size_t)r * r, mr = (size_t)m * r;
-    size_t n1 = (size_t)(p + m) * (p + m), n2 = (size_t)(m + r) * m;
-    size_t fwd = /*T,Pc,Pcf*/ 3 * mm_ + /*Z,Zm*/ 2 * pm + pp + rr + mr + /*c,a,af*/ 3 * (size_t)m +
-                 /*d,w,ym,v,sv,inner*/ 6 * (size_t)p + /*A0,Rf*/ 2 * n1 + /*M0,Rp*/ 2 * n2 + 32;
-    size_t bw = /*Pbar,gT,Psum,Pcfbar,U1*/ 5 * mm_ + /*S1,Psi,Abar*/ 3 * n1 + pm + /*abar,gc,afbar*/ 3 * (size_t)m +
-                /*gd,vbar,sbar,t1*/ 4 * (size_t)p + pp;
-    // blocked-QR / tile-solve scratch: the forward kernel never reads A0, so it borrows that region
-    if (bwd) bw += /*hv,hw,uinv*/ 3 * 8 * (size_t)(p + m + r) + /*ht*/ 64;
-    size_t tot = fwd + (bwd ? bw : 0);
+    size_t n1 = (size_t)(p + m) * (p + m), n2 = (size_t)(m + r) * m, sc = 8 * (size_t)(p + m + r);
+    size_t common = /*T,Pc*/ 2 * mm_ + /*Z,Zm*/ 2 * pm + pp + rr + mr + /*c,a,af*/ 3 * (size_t)m +
+                    /*d,w,ym,v,sv,inner*/ 6 * (size_t)p + /*Rf*/ n1 + /*Rp*/ n2 + 32 + /*hv,hw*/ 2 * sc + /*ht*/ 64;
+    size_t bw = /*Pcf*/ mm_ + /*A0*/ n1 + /*M0*/ n2 + /*Pbar,gT,Psum,Pcfbar,U1*/ 5 * mm_ + /*S1,Psi,Abar*/ 3 * n1 + pm +
+                /*abar,gc,afbar*/ 3 * (size_t)m + /*gd,vbar,sbar,t1*/ 4 * (size_t)p + pp + /*uinv*/ sc;
+    size_t tot = common + (bwd ? bw : 0);
     return (tot + 1) & ~(size_t)1;
 }
 
 template <typename R>
 __device__ void carve(Arena<R>& A, R* s, int m, int p, int r, bool bwd) {
     size_t mm_ = (size_t)m * m, pm = (size_t)p * m, pp = (size_t)p * p, rr = (size_t)r * r, mr = (size_t)m * r;
-    size_t n1 = (size_t)(p + m) * (p + m), n2 = (size_t)(m + r) * m;
+    size_t n1 = (size_t)(p + m) * (p + m), n2 = (size_t)(m + r) * m, sc = 8 * (size_t)(p + m + r);
     auto take = [&](size_t n) { R* q = s; s += n; return q; };
-    A.T = take(mm_); A.Pc = take(mm_); A.Pcf = take(mm_); A.Z = take(pm); A.Zm = take(pm); A.Hc = take(pp);
+    A.T = take(mm_); A.Pc = take(mm_); A.Z = take(pm); A.Zm = take(pm); A.Hc = take(pp);
     A.Qc = take(rr); A.RQc = take(mr); A.c = take(m); A.a = take(m); A.af = take(m);
     A.d = take(p); A.w = take(p); A.ym = take(p); A.v = take(p); A.sv = take(p); A.inner = take(p);
-    A.A0 = take(n1); A.Rf = take(n1); A.M0 = take(n2); A.Rp = take(n2); A.red = take(32);
-    if (!bwd) {  // (p+m)^2 >= 2*8*(p+m+r) + 64 is checked by the launcher before the fast path is enabled
-        A.hv = A.A0; A.hw = A.A0 + 8 * (size_t)(p + m + r); A.ht = A.hw + 8 * (size_t)(p + m + r); A.uinv = nullptr;
-    }
-    if (bwd) {
+    A.Rf = take(n1); A.Rp = take(n2); A.red = take(32);
+    A.hv = take(sc); A.hw = take(sc); A.ht = take(64);
+    if (!bwd) {
+        A.A0 = A.Rf; A.M0 = A.Rp; A.Pcf = A.Pc; A.uinv = nullptr;
+    } else {
+        A.Pcf = take(mm_); A.A0 = take(n1); A.M0 = take(n2);
         A.Pbar = take(mm_); A.gT = take(mm_); A.Psum = take(mm_); A.Pcfbar = take(mm_); A.U1 = take(mm_);
         A.S1 = take(n1); A.Psi = take(n1); A.Abar = take(n1); A.gZ = take(pm);
         A.abar = take(m); A.gc = take(m); A.afbar = take(m);
         A.gd = take(p); A.vbar = take(p); A.sbar = take(p); A.t1 = take(p); A.Hcbar = take(pp);
-        A.hv = take(8 * (size_t)(p + m + r)); A.hw = take(8 * (size_t)(p + m + r)); A.uinv = take(8 * (size_t)(p + m + r));
-        A.ht = take(64);
+        A.uinv = take(sc);
     }
 }
 
@@ -655,12 +656,13 @@ __device__ void predict(const KArgs<R>& g, Arena<R>& A, R* a_next, R* Pc_next, c
     __syncthreads();
 }
 
-template <typename R>
-__global__ void __launch_bounds__(256, 2) forward_kernel(KArgs<R> g) {
+// NT = 128: three CTAs per SM at the C4 shape (72 KB each); NT = 256: two CTAs with twice the warps -- the launcher
+// picks whichever finishes the batch in less (waves x time per wave).
+template <typename R, int NT>
+__global__ void __launch_bounds__(NT, NT == 128 ? 3 : 2) forward_kernel(KArgs<R> g) {
     extern __shared__ double smem_raw[];
     R* smem = reinterpret_cast<R*>(smem_raw);
-    const Th th{(int)threadIdx.x, (int)blockDim.x, sizeof(R) == 8 && !((g.m | g.p | g.r) & 7) &&
-                    (g.p + g.m) * (g.p + g.m) >= 16 * (g.p + g.m + g.r) + 64};
+    const Th th{(int)threadIdx.x, (int)blockDim.x, sizeof(R) == 8 && !((g.m | g.p | g.r) & 7)};
     const int b = blockIdx.x;
     const int m = g.m, p = g.p, n = g.n, N1 = p + m;
     Arena<R> A;
@@ -914,8 +916,17 @@ static int launch(const KArgs<R>& g, bool bwd, cudaStream_t stream, const char**
         return BKF_ERR_UNSUPPORTED;
     }
     const int N1 = g.p + g.m;
-    const int threads = N1 <= 12 ? 32 : (N1 <= 24 ? 64 : (N1 <= 40 ? 128 : 256));
-    auto kern = bwd ? backward_kernel<R> : forward_kernel<R>;
+    int threads = N1 <= 12 ? 32 : (N1 <= 24 ? 64 : (N1 <= 40 ? 128 : 256));
+    if (!bwd && threads == 256) {
+        // forward sweep at large shapes: 3 CTAs x 4 warps per SM sustain ~1.2x the throughput of 2 x 8 warps, but a
+        // batch that is only a little over a whole number of waves loses that to the tail
+        int dev = 0, sms = 148;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        const long w2 = (g.B + 2L * sms - 1) / (2L * sms), w3 = (g.B + 3L * sms - 1) / (3L * sms);
+        if (bytes * 3 <= 225 * 1024 && 5 * w3 < 4 * w2) threads = 128;
+    }
+    auto kern = bwd ? backward_kernel<R> : (threads == 256 ? forward_kernel<R, 256> : forward_kernel<R, 128>);
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
     if (e != cudaSuccess) { *err = cudaGetErrorString(e); return BKF_ERR_CUDA; }
     kern<<<g.B, threads, bytes, stream>>>(g);
