@@ -565,6 +565,30 @@ __device__ R step(const KArgs<R>& g, Arena<R>& A, const R* yt, bool Hzero, bool*
     return R(0);
 }
 
+// Small triangular solves of the update (p <= 32 right-hand-side entries): lane q keeps x[q] in a register, the pivot
+// value travels by shuffle and the reciprocal diagonal is formed once, so an elimination step costs one shuffle and one
+// FMA instead of a division and a shared-memory round trip.  U = Rf[:p,:p] (upper, leading dimension ld); Fc = U^T.
+//   LOWER:  x <- Fc^{-1} x   (forward substitution,  Fc[q,i] = U[i,q])
+//   UPPER:  x <- U^{-1} x    (back substitution)
+template <bool LOWER, typename R>
+__device__ __forceinline__ R warp_trisolve(const R* __restrict__ U, int ld, int p, R x, int lane) {
+    const R rdiag = lane < p ? R(1) / U[lane * ld + lane] : R(0);
+    if (LOWER) {
+        for (int i = 0; i < p; ++i) {
+            const R xi = __shfl_sync(0xffffffffu, x, i) * __shfl_sync(0xffffffffu, rdiag, i);
+            if (lane == i) x = xi;
+            else if (lane > i && lane < p) x = fma(-U[i * ld + lane], xi, x);
+        }
+    } else {
+        for (int i = p - 1; i >= 0; --i) {
+            const R xi = __shfl_sync(0xffffffffu, x, i) * __shfl_sync(0xffffffffu, rdiag, i);
+            if (lane == i) x = xi;
+            else if (lane < i) x = fma(-U[lane * ld + i], xi, x);
+        }
+    }
+    return x;
+}
+
 template <typename R>
 __device__ R finish_update(const KArgs<R>& g, Arena<R>& A, bool flag, bool need_ll, Th th) {
     const int m = g.m, p = g.p, N1 = p + m;
@@ -583,10 +607,18 @@ __device__ R finish_update(const KArgs<R>& g, Arena<R>& A, bool flag, bool need_
                 }
                 __syncwarp();
             };
-            for (int i = lane; i < p; i += 32) A.sv[i] = A.v[i];
-            solve_fc(A.sv);
-            for (int i = lane; i < p; i += 32) A.inner[i] = A.sv[i];
-            solve_fc(A.inner);
+            if (p <= 32) {
+                R x = lane < p ? A.v[lane] : R(0);
+                x = warp_trisolve<true>(A.Rf, N1, p, x, lane);
+                if (lane < p) A.sv[lane] = x;
+                x = warp_trisolve<true>(A.Rf, N1, p, x, lane);
+                if (lane < p) A.inner[lane] = x;
+            } else {
+                for (int i = lane; i < p; i += 32) A.sv[i] = A.v[i];
+                solve_fc(A.sv);
+                for (int i = lane; i < p; i += 32) A.inner[i] = A.sv[i];
+                solve_fc(A.inner);
+            }
         }
         __syncthreads();
         R quad = 0, logdet = 0;
@@ -789,7 +821,15 @@ __global__ void backward_kernel(KArgs<R> g) {
                 A.vbar[o] = lossbar * A.inner[o];
                 A.t1[o] = lossbar * A.v[o];
             }
-            solve_fcT(A.t1);  // t1 = Fc^{-T} innerbar
+            __syncwarp();
+            if (p <= 32) {
+                R x = lane < p ? A.t1[lane] : R(0);
+                x = warp_trisolve<false>(A.Rf, N1, p, x, lane);  // t1 = Fc^{-T} innerbar
+                if (lane < p) A.t1[lane] = x;
+            } else {
+                solve_fcT(A.t1);
+            }
+            __syncwarp();
             // Bbar's Fc block goes straight into Abar scratch: Fcbar = tril(-t1 inner^T - t2 s^T) + diag(...)
             for (int idx = lane; idx < p * p; idx += 32) {
                 int i = idx / p, j = idx - i * p;
@@ -797,8 +837,16 @@ __global__ void backward_kernel(KArgs<R> g) {
             }
             for (int i = lane; i < p; i += 32) A.sbar[i] += A.t1[i];
             __syncwarp();
-            for (int i = lane; i < p; i += 32) A.t1[i] = A.sbar[i];
-            solve_fcT(A.t1);  // t2 = Fc^{-T} sbar  (reuse t1)
+            if (p <= 32) {
+                R x = lane < p ? A.sbar[lane] : R(0);
+                x = warp_trisolve<false>(A.Rf, N1, p, x, lane);  // t2 = Fc^{-T} sbar  (reuse t1)
+                __syncwarp();
+                if (lane < p) A.t1[lane] = x;
+            } else {
+                for (int i = lane; i < p; i += 32) A.t1[i] = A.sbar[i];
+                solve_fcT(A.t1);
+            }
+            __syncwarp();
             for (int idx = lane; idx < p * p; idx += 32) {
                 int i = idx / p, j = idx - i * p;
                 if (j <= i) {
