@@ -111,6 +111,13 @@ int bkf_measure_fma_peak(bkf_handle* h, int dtype, double* tflops);
 int bkf_host_alloc(size_t bytes, void** out);
 int bkf_host_free(void* p);
 
+/* Device workspace (bytes) a bkf_filter_logp_grad call on `prob` needs beyond the caller's own buffers: the forward
+ * sweep's trajectory record (layout private to the kernel family), plus device staging of every input and output
+ * when prob->mem is BKF_MEM_HOST.  With bkf_device_memory it lets the host side split a batch that would not fit
+ * (KalmanEngine.logp_grad does: series are independent, so a batch can be processed in slices). */
+int bkf_logp_grad_workspace_bytes(const bkf_problem* prob, size_t* bytes);
+int bkf_device_memory(bkf_handle* h, size_t* free_bytes, size_t* total_bytes);
+
 int bkf_filter_forward(bkf_handle* h, const bkf_problem* prob, const void* y, const void* a0, const void* P0,
                        const void* c, const void* d, const void* T, const void* Z, const void* R, const void* H,
                        const void* Q, void* filtered_states, void* predicted_states, void* observed_states,

@@ -474,6 +474,39 @@ extern "C" int bkf_filter_forward(bkf_handle* h, const bkf_problem* P, const voi
                                : forward_impl<float>(h, P, y, prm, fa, pa, om, fP, pP, oc, ll, status);
 }
 
+static size_t traj_record_elems(const bkf_problem* P) {
+    // the trajectory layout is private to a kernel family: dense [a | P] records, DMMA fragment records, or the
+    // square-root family's [a | Pc | triu(R_update) | triu(R_predict)]
+    const bool f64 = P->dtype == BKF_F64;
+    if (P->kind == BKF_CHOLESKY) return sq::traj_record_elems_host(P->m, P->p);
+    const bool frag = f64 && !P->tv_mask && !tps::supported(P->kind, P->m, P->p) && tc::supported(P->kind, P->m, P->p);
+    return frag ? tc::traj_record_elems() : (size_t)P->m + (size_t)P->m * P->m;
+}
+
+extern "C" int bkf_logp_grad_workspace_bytes(const bkf_problem* P, size_t* bytes) {
+    if (!P || !bytes) return BKF_ERR_ARG;
+    const size_t es = P->dtype == BKF_F64 ? 8 : 4, B = P->B, n = P->n;
+    size_t tot = B * n * traj_record_elems(P) * es;
+    if (P->mem == BKF_MEM_HOST) {
+        tot += (P->y_shared ? 1 : B) * n * (size_t)P->p * es + B * n * es /* cotangent */ + B * (es + sizeof(int));
+        for (int i = 0; i < BKF_NPARAM; ++i)
+            tot += ((((P->shared_mask >> i) & 1u) ? 1 : B) + B) * param_elems(P, i) * es;  // input + gradient
+    }
+    *bytes = tot;
+    return BKF_OK;
+}
+
+extern "C" int bkf_device_memory(bkf_handle* h, size_t* free_bytes, size_t* total_bytes) {
+    if (!h) return BKF_ERR_ARG;
+    cudaError_t e = cudaSetDevice(h->device);
+    size_t f = 0, t = 0;
+    if (e == cudaSuccess) e = cudaMemGetInfo(&f, &t);
+    if (e != cudaSuccess) return cuda_fail(h, e, "cudaMemGetInfo");
+    if (free_bytes) *free_bytes = f;
+    if (total_bytes) *total_bytes = t;
+    return BKF_OK;
+}
+
 // ----------------------------------------------------------------------------------------------------
 template <typename R>
 static int logp_grad_impl(bkf_handle* h, const bkf_problem* P, const void* y, const void* const* prm,
@@ -490,11 +523,7 @@ static int logp_grad_impl(bkf_handle* h, const bkf_problem* P, const void* y, co
     for (int i = 0; i < BKF_NPARAM; ++i)
         *gdst[i] = stage_out<R>(h, P, S_GA0 + i, grads[i], B * param_elems(P, i), &rc);
     if (want_grad) {
-        // the trajectory layout is private to a kernel family: dense [a | P] records, or DMMA fragment records
-        const bool frag = sizeof(R) == 8 && P->kind != BKF_CHOLESKY && !P->tv_mask &&
-                          !tps::supported(P->kind, P->m, P->p) && tc::supported(P->kind, P->m, P->p);
-        const size_t rec = P->kind == BKF_CHOLESKY ? sq::traj_record_elems_host(P->m, P->p)
-                                                   : (frag ? tc::traj_record_elems() : m + m * m);
+        const size_t rec = traj_record_elems(P);
         g.traj = (R*)ensure(h, S_TRAJ, B * n * rec * sizeof(R), &rc);
     }
     int* dstatus = nullptr;

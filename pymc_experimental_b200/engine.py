@@ -33,6 +33,7 @@ ABI_SYMBOLS = (
     "bkf_version", "bkf_create", "bkf_destroy", "bkf_last_error", "bkf_set_stream", "bkf_launch_count",
     "bkf_last_path", "bkf_enable_timing", "bkf_reset_timing", "bkf_kernel_time_ms", "bkf_measure_fma_peak",
     "bkf_filter_forward", "bkf_filter_logp_grad", "bkf_smooth", "bkf_filter_smooth", "bkf_host_alloc", "bkf_host_free",
+    "bkf_logp_grad_workspace_bytes", "bkf_device_memory",
 )
 
 
@@ -78,6 +79,8 @@ def load_library():
     lib.bkf_reset_timing.argtypes = [vp]
     lib.bkf_kernel_time_ms.argtypes = [vp, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_longlong)]
     lib.bkf_measure_fma_peak.argtypes = [vp, C.c_int, C.POINTER(C.c_double)]
+    lib.bkf_logp_grad_workspace_bytes.argtypes = [C.POINTER(BkfProblem), C.POINTER(C.c_size_t)]
+    lib.bkf_device_memory.argtypes = [vp, C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]
     lib.bkf_host_alloc.argtypes = [C.c_size_t, C.POINTER(vp)]
     lib.bkf_host_free.argtypes = [vp]
     pp = C.POINTER(BkfProblem)
@@ -216,6 +219,15 @@ class KalmanEngine:
                            "(this engine has no CPU fallback)")
         self.h = h
         self.device = int(device)
+        # logp_grad splits a batch whose device workspace (trajectory + staging) would exceed this many bytes;
+        # None = 70 % of the device's memory (B200: ~125 of 180 GB)
+        self.max_workspace_bytes = None
+
+    def device_memory(self):
+        """(free, total) bytes of this engine's device."""
+        f, t = C.c_size_t(0), C.c_size_t(0)
+        self._check(self.lib.bkf_device_memory(self.h, C.byref(f), C.byref(t)))
+        return f.value, t.value
 
     def close(self):
         if getattr(self, "h", None):
@@ -393,6 +405,16 @@ class KalmanEngine:
         B = 1 if squeeze else int(B)
         prob, yb, arrs = self._problem(kind, bufs, y, params, B, cov_jitter, missing_fill_value, time_varying)
         n, m, p, r = prob.n, prob.m, prob.p, prob.r
+        if B > 1 and packed_out is None and grads:
+            need = C.c_size_t(0)
+            self._check(self.lib.bkf_logp_grad_workspace_bytes(C.byref(prob), C.byref(need)))
+            budget = self.max_workspace_bytes
+            if budget is None:
+                budget = int(0.7 * self.device_memory()[1])
+            if need.value > budget:
+                return self._logp_grad_in_slices(kind, y, params, ll_cotangent, B, -(-need.value // budget),
+                                                 dict(cov_jitter=cov_jitter, missing_fill_value=missing_fill_value,
+                                                      grads=grads, dtype=dtype, time_varying=time_varying))
         gshape = {"a0": (B, m), "P0": (B, m, m), "c": (B, m), "d": (B, p), "T": (B, m, m), "Z": (B, p, m),
                   "R": (B, m, r), "H": (B, p, p), "Q": (B, r, r)}
         for k_ in time_varying:  # gradients of time-varying parameters keep the time axis
@@ -426,6 +448,29 @@ class KalmanEngine:
         if squeeze:
             return logp[0], {k_: v[0] for k_, v in g.items()}, status[0]
         return logp, g, status
+
+    def _logp_grad_in_slices(self, kind, y, params, ll_cotangent, B, nslices, kw):
+        """Series are independent: a batch whose trajectory workspace would not fit the device is processed in
+        contiguous slices of the batch axis (shared inputs are passed to every slice) and the results concatenated."""
+        tv = kw["time_varying"]
+        per = -(-B // int(nslices))
+        parts = []
+        for b0 in range(0, B, per):
+            sl = slice(b0, min(B, b0 + per))
+            batched = lambda name, x: x.ndim == _STATIC_NDIM[name] + 1 + int(name in tv)
+            args = [params[k_][sl] if batched(k_, params[k_]) else params[k_] for k_ in PARAM_NAMES]
+            parts.append(self.logp_grad(kind, y[sl] if y.ndim == 3 else y, *args,
+                                        ll_cotangent=None if ll_cotangent is None else ll_cotangent[sl], **kw))
+        if _is_torch(parts[0][0]):
+            import torch
+
+            cat = torch.cat
+        else:
+            cat = np.concatenate
+        logp = cat([q[0] for q in parts])
+        grads = {k_: cat([q[1][k_] for q in parts]) for k_ in parts[0][1]}
+        status = cat([q[2] for q in parts])
+        return logp, grads, status
 
     def smooth(self, T, R, Q, filtered_states, filtered_covariances, cov_jitter=None, dtype=None, time_varying=()):
         """Batched ``KalmanSmoother.build_graph`` (kalman_smoother.py:66-105).  Time-varying T / R / Q

@@ -383,3 +383,36 @@ def test_time_varying_square_root_filter_is_refused(eng):
     cfg = synth.random_dense_tv(2, 6, 3, 2, 2, ("Z",), seed=3)
     with pytest.raises(BkfError, match="square-root"):
         eng.filter("cholesky", cfg["y"], *[cfg[k] for k in NAMES], time_varying=("Z",))
+
+
+@pytest.mark.parametrize("device", [False, True])
+def test_batch_is_sliced_when_the_workspace_would_not_fit(eng, device):
+    """KalmanEngine.logp_grad asks the library how much device workspace a call needs
+    (bkf_logp_grad_workspace_bytes) and processes the batch in slices when that exceeds its budget (70 % of the
+    device by default; forced here).  Series are independent: the sliced result is bit-identical."""
+    import torch
+
+    from pymc_experimental_b200 import synth
+
+    B, n = 37, 11
+    cfg = synth.sarima(B=B, n=n)
+    cot = np.random.default_rng(3).standard_normal((B, n))
+    args = [cfg["y"]] + [cfg[k] for k in NAMES]
+    if device:
+        args = [torch.as_tensor(np.ascontiguousarray(a), device="cuda:0") for a in args]
+        cot = torch.as_tensor(cot, device="cuda:0")
+    to_np = lambda x: x.cpu().numpy() if device else x
+    logp1, g1, st1 = eng.logp_grad("univariate", *args, ll_cotangent=cot)
+    launches = eng.launch_count
+    eng.max_workspace_bytes = 10 * n * 292 * 8  # room for ~10 series of the fragment-order trajectory
+    try:
+        logp2, g2, st2 = eng.logp_grad("univariate", *args, ll_cotangent=cot)
+    finally:
+        eng.max_workspace_bytes = None
+    assert eng.launch_count - launches >= 8  # at least four slices, forward + backward each
+    np.testing.assert_array_equal(to_np(logp1), to_np(logp2))
+    np.testing.assert_array_equal(to_np(st1), to_np(st2))
+    for k in NAMES:
+        np.testing.assert_array_equal(to_np(g1[k]), to_np(g2[k]), err_msg=k)
+    free, total = eng.device_memory()
+    assert 0 < free <= total
