@@ -407,6 +407,34 @@ def run_b200(args):
         dist.all_reduce(t_e, op=dist.ReduceOp.MAX)
     e2e_value = units_per_step * args.steps / float(t_e.item())
 
+    # ---- the same through the compact parameterisation (row f-1): only the draw-dependent entries cross PCIe ----
+    e2e_compact = None
+    if name == "C2" and mode == "logp_grad":
+        from pymc_experimental_b200 import synth
+
+        base, positions, u = synth.sarima_compact(cfg)
+        hu, hy = pinned(u), hargs[0]
+        hbase = {k: np.ascontiguousarray(v, dtype=npdtype) for k, v in base.items()}
+
+        def compact_step():
+            lp, gu, _ = eng.logp_grad_compact(kind, hy, hbase, positions, hu, dtype=npdtype, cov_jitter=jitter)
+            return lp.nbytes + gu.nbytes
+
+        compact_step()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            c_d2h = compact_step()
+        torch.cuda.synchronize()
+        t_c = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t_c, op=dist.ReduceOp.MAX)
+        e2e_compact = {"value": units_per_step * args.steps / float(t_c.item()), "unit": UNIT,
+                       "h2d_bytes_per_step": int(hu.nbytes + hy.nbytes + sum(v.nbytes for v in hbase.values())),
+                       "d2h_bytes_per_step": int(c_d2h),
+                       "note": "bkf_filter_logp_grad_compact: 7 draw-dependent matrix entries per draw in, logp + 7 "
+                               "gradient entries out (SURVEY 8 f-1); extra figure, `e2e` above is the dense call"}
+
     # ---- roofline of the dominant kernel ----
     model = step_model(kind, mode, m, p, r)
     hbm_peak, peak_src = load_peaks()
@@ -454,6 +482,8 @@ def run_b200(args):
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
             "roofline": roof,
         }
+        if e2e_compact is not None:
+            line["e2e_compact"] = e2e_compact
         if cpu is not None:
             line["cpu_baseline"] = cpu
         print(json.dumps(line))

@@ -132,6 +132,21 @@ int bkf_filter_logp_grad(bkf_handle* h, const bkf_problem* prob, const void* y, 
                          void* g_P0, void* g_c, void* g_d, void* g_T, void* g_Z, void* g_R, void* g_H,
                          void* g_Q, int* status);
 
+/* Compact parameterisation: every state-space model of the reference is a constant
+ * pattern with a few parametrised entries (models/SARIMAX.py:383-536, ETS.py:468-670, structural.py components,
+ * VARMAX.py:297-393), so a caller that evaluates many draws ships, per draw, only those entries:
+ *   base[9]     the nine matrices WITHOUT batch axis (shared constants; prob->shared_mask is ignored)
+ *   nnz, which[nnz], index[nnz]   entry k of the compact vector lands in matrix which[k] (BKF_PARAM_x) at flat
+ *               row-major index index[k]; (which, index) pairs must be unique; index arrays are HOST memory
+ *   u   [B, nnz]  the per-draw values;  g_u [B, nnz]  d(sum_t cot * ll)/du  (the matrix gradients gathered at the
+ *               same positions: the caller chains them through its own theta -> u map)
+ * The per-draw matrices are expanded on the device (base broadcast + scatter), the ordinary kernels run, and only
+ * logp, g_u and status travel back: for C2 that is 7 instead of 513 doubles per draw in each direction.  y, u, ll_cot,
+ * logp, g_u, status live where prob->mem says; time-varying inputs are not supported here. */
+int bkf_filter_logp_grad_compact(bkf_handle* h, const bkf_problem* prob, const void* y, const void* const base[9],
+                                 int nnz, const int* which, const int* index, const void* u, const void* ll_cotangent,
+                                 void* logp, void* g_u, int* status);
+
 /* Uses prob->{dtype,mem,B,n,m,r,shared_mask(T,R,Q),cov_jitter}.  filtered_* are [B,n,m] / [B,n,m,m]. */
 int bkf_smooth(bkf_handle* h, const bkf_problem* prob, const void* T, const void* R, const void* Q,
                const void* filtered_states, const void* filtered_covariances, void* smoothed_states,

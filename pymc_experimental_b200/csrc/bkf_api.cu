@@ -2,6 +2,7 @@
 //
 // No torch types, no exceptions across the boundary.  Host pointers (NumPy) are staged through a grow-only
 // device workspace owned by the handle; device pointers are used in place.
+#include <algorithm>
 #include <cstdio>
 #include <cstring>
 #include <string>
@@ -13,10 +14,10 @@
 using namespace bkf;
 
 enum Slot {
-    S_Y = 0, S_A0, S_P0, S_C, S_D, S_T, S_Z, S_R, S_H, S_Q,            // inputs
+    S_Y = 0, S_A0, S_P0, S_C, S_D, S_T, S_Z, S_R, S_H, S_Q,            // inputs (order = BKF_PARAM_* + 1)
     S_FA, S_PA, S_OM, S_FP, S_PP, S_OC, S_LL,                          // forward outputs
     S_TRAJ, S_COT, S_LOGP, S_GA0, S_GP0, S_GC, S_GD, S_GT, S_GZ, S_GR, S_GH, S_GQ, S_STATUS,
-    S_SMA, S_SMP, S_WFA, S_WFP, S_FLAG, S_NSLOT
+    S_SMA, S_SMP, S_WFA, S_WFP, S_FLAG, S_U, S_GU, S_MAP, S_BASE, S_NSLOT
 };
 
 struct bkf_handle {
@@ -514,7 +515,7 @@ static int logp_grad_impl(bkf_handle* h, const bkf_problem* P, const void* y, co
     int rc = BKF_OK;
     KArgs<R> g;
     fill_inputs<R>(h, P, g, y, prm, &rc);
-    const size_t B = P->B, n = P->n, m = P->m;
+    const size_t B = P->B, n = P->n;
     bool want_grad = false;
     for (int i = 0; i < BKF_NPARAM; ++i) want_grad = want_grad || grads[i];
     if (cot) g.ll_cot = stage_in<R>(h, P, S_COT, cot, B * n, &rc);
@@ -559,6 +560,145 @@ extern "C" int bkf_filter_logp_grad(bkf_handle* h, const bkf_problem* P, const v
     void* grads[BKF_NPARAM] = {g_a0, g_P0, g_c, g_d, g_T, g_Z, g_R, g_H, g_Q};
     return P->dtype == BKF_F64 ? logp_grad_impl<double>(h, P, y, prm, ll_cotangent, logp, grads, status)
                                : logp_grad_impl<float>(h, P, y, prm, ll_cotangent, logp, grads, status);
+}
+
+// ----------------------------------------------------------------------------------------------------
+// compact parameterisation (bkf.h: bkf_filter_logp_grad_compact)
+template <typename R>
+__global__ void expand_kernel(R* __restrict__ out, const R* __restrict__ base, size_t elems, size_t B) {
+    const size_t total = elems * B;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x)
+        out[i] = base[i % elems];
+}
+struct MapEntry { int which, index; };
+template <typename R>
+struct ScatterArgs { R* mat[BKF_NPARAM]; size_t elems[BKF_NPARAM]; };
+template <typename R>
+__global__ void scatter_kernel(ScatterArgs<R> a, const MapEntry* __restrict__ map, int nnz, const R* __restrict__ u,
+                               size_t B) {
+    const size_t total = (size_t)nnz * B;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const size_t b = i / nnz;
+        const MapEntry e = map[i - b * nnz];
+        a.mat[e.which][b * a.elems[e.which] + e.index] = u[i];
+    }
+}
+template <typename R>
+__global__ void gather_kernel(R* __restrict__ gu, ScatterArgs<R> a, const MapEntry* __restrict__ map, int nnz, size_t B) {
+    const size_t total = (size_t)nnz * B;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const size_t b = i / nnz;
+        const MapEntry e = map[i - b * nnz];
+        gu[i] = a.mat[e.which][b * a.elems[e.which] + e.index];
+    }
+}
+
+template <typename R>
+static int compact_impl(bkf_handle* h, const bkf_problem* P, const void* y, const void* const* base, int nnz,
+                        const int* which, const int* index, const void* u, const void* cot, void* logp, void* g_u,
+                        int* status) {
+    int rc = BKF_OK;
+    const size_t B = P->B, n = P->n;
+    const bool host = P->mem == BKF_MEM_HOST;
+    bool mapped[BKF_NPARAM] = {false};
+    std::vector<MapEntry> hmap(nnz);
+    for (int k = 0; k < nnz; ++k) {
+        if (which[k] < 0 || which[k] >= BKF_NPARAM || index[k] < 0 || (size_t)index[k] >= param_elems(P, which[k]))
+            return fail(h, BKF_ERR_ARG, "compact map entry out of range");
+        for (int q = 0; q < k; ++q)
+            if (which[q] == which[k] && index[q] == index[k]) return fail(h, BKF_ERR_ARG, "compact map entries must be unique");
+        mapped[which[k]] = true;
+        hmap[k] = {which[k], index[k]};
+    }
+    // ---- inputs: bases are shared; mapped parameters get a per-draw expansion in the staging slots ----
+    KArgs<R> g;
+    std::memset(&g, 0, sizeof(g));
+    g.kind = P->kind; g.B = P->B; g.n = P->n; g.m = P->m; g.p = P->p; g.r = P->r; g.y_shared = P->y_shared;
+    g.jitter = (R)P->cov_jitter; g.fill = (R)P->missing_fill;
+    bkf_problem Pd = *P;  // what the kernels see: device memory, unmapped parameters shared
+    Pd.mem = BKF_MEM_DEVICE;
+    Pd.shared_mask = 0;
+    Pd.tv_mask = 0;
+    g.y = stage_in<R>(h, P, S_Y, y, (P->y_shared ? 1 : B) * n * (size_t)P->p, &rc);
+    const R* du = stage_in<R>(h, P, S_U, u, B * (size_t)nnz, &rc);
+    if (cot) g.ll_cot = stage_in<R>(h, P, S_COT, cot, B * n, &rc);
+    size_t base_off[BKF_NPARAM + 1] = {0};
+    for (int i = 0; i < BKF_NPARAM; ++i) base_off[i + 1] = base_off[i] + param_elems(P, i);
+    R* dbase = nullptr;
+    if (host) {  // one staging buffer for the nine small base matrices
+        dbase = (R*)ensure(h, S_BASE, base_off[BKF_NPARAM] * sizeof(R), &rc);
+        if (!dbase) return rc;
+        for (int i = 0; i < BKF_NPARAM; ++i)
+            cudaMemcpyAsync(dbase + base_off[i], base[i], param_elems(P, i) * sizeof(R), cudaMemcpyHostToDevice, h->stream);
+    }
+    MapEntry* dmap = (MapEntry*)ensure(h, S_MAP, (size_t)(nnz > 0 ? nnz : 1) * sizeof(MapEntry), &rc);
+    if (rc != BKF_OK) return rc;
+    if (nnz) cudaMemcpyAsync(dmap, hmap.data(), (size_t)nnz * sizeof(MapEntry), cudaMemcpyHostToDevice, h->stream);
+    const R** in[BKF_NPARAM] = {&g.a0, &g.P0, &g.c, &g.d, &g.T, &g.Z, &g.Rm, &g.H, &g.Q};
+    R** gd[BKF_NPARAM] = {&g.g_a0, &g.g_P0, &g.g_c, &g.g_d, &g.g_T, &g.g_Z, &g.g_R, &g.g_H, &g.g_Q};
+    ScatterArgs<R> sa, ga;
+    for (int i = 0; i < BKF_NPARAM; ++i) {
+        const size_t e = param_elems(P, i);
+        const R* bsrc = host ? dbase + base_off[i] : (const R*)base[i];
+        sa.elems[i] = ga.elems[i] = e;
+        sa.mat[i] = ga.mat[i] = nullptr;
+        if (mapped[i]) {
+            R* ex = (R*)ensure(h, S_A0 + i, B * e * sizeof(R), &rc);
+            R* gx = (R*)ensure(h, S_GA0 + i, B * e * sizeof(R), &rc);
+            if (rc != BKF_OK) return rc;
+            if (B) expand_kernel<R><<<(unsigned)std::min<size_t>((B * e + 255) / 256, 4096), 256, 0, h->stream>>>(ex, bsrc, e, B);
+            sa.mat[i] = ex;
+            ga.mat[i] = gx;
+            *in[i] = ex;
+            *gd[i] = gx;
+        } else {
+            Pd.shared_mask |= 1u << i;
+            *in[i] = bsrc;
+        }
+    }
+    g.shared_mask = Pd.shared_mask;
+    g.logp = stage_out<R>(h, P, S_LOGP, logp, B, &rc);
+    R* dgu = stage_out<R>(h, P, S_GU, g_u, B * (size_t)nnz, &rc);
+    int* dstatus = nullptr;
+    if (status) dstatus = host ? (int*)ensure(h, S_STATUS, B * sizeof(int), &rc) : status;
+    g.status = dstatus;
+    const bool want_grad = g_u != nullptr && nnz > 0;
+    if (want_grad) g.traj = (R*)ensure(h, S_TRAJ, B * n * traj_record_elems(&Pd) * sizeof(R), &rc);
+    if (rc != BKF_OK) return rc;
+    if (B == 0) return BKF_OK;
+    const unsigned sgrid = (unsigned)std::min<size_t>((B * (size_t)(nnz > 0 ? nnz : 1) + 255) / 256, 4096);
+    if (nnz) scatter_kernel<R><<<sgrid, 256, 0, h->stream>>>(sa, dmap, nnz, du, B);
+    h->launches += 1 + (nnz ? 1 : 0);
+    const char* err = "";
+    rc = run_forward(h, g, &err);
+    if (rc != BKF_OK) return fail(h, rc, err);
+    if (want_grad) {
+        rc = run_backward(h, g, &err);
+        if (rc != BKF_OK) return fail(h, rc, err);
+        gather_kernel<R><<<sgrid, 256, 0, h->stream>>>(dgu, ga, dmap, nnz, B);
+        h->launches += 1;
+    }
+    copy_back<R>(h, P, logp, g.logp, B, &rc);
+    if (want_grad) copy_back<R>(h, P, g_u, dgu, B * (size_t)nnz, &rc);
+    if (status && host && rc == BKF_OK) {
+        cudaError_t e = cudaMemcpyAsync(status, dstatus, B * sizeof(int), cudaMemcpyDeviceToHost, h->stream);
+        if (e != cudaSuccess) rc = cuda_fail(h, e, "D2H copy");
+    }
+    return finish(h, P, rc);
+}
+
+extern "C" int bkf_filter_logp_grad_compact(bkf_handle* h, const bkf_problem* P, const void* y,
+                                            const void* const base[9], int nnz, const int* which, const int* index,
+                                            const void* u, const void* ll_cotangent, void* logp, void* g_u,
+                                            int* status) {
+    int rc = validate(h, P, true);
+    if (rc != BKF_OK) return rc;
+    if (P->tv_mask) return fail(h, BKF_ERR_UNSUPPORTED, "the compact parameterisation does not take time-varying inputs");
+    if (!y || !base || any_null(base, BKF_NPARAM) || nnz < 0 || (nnz > 0 && (!which || !index || !u)))
+        return fail(h, BKF_ERR_ARG, "null input pointer");
+    return P->dtype == BKF_F64
+               ? compact_impl<double>(h, P, y, base, nnz, which, index, u, ll_cotangent, logp, g_u, status)
+               : compact_impl<float>(h, P, y, base, nnz, which, index, u, ll_cotangent, logp, g_u, status);
 }
 
 // ----------------------------------------------------------------------------------------------------

@@ -33,7 +33,7 @@ ABI_SYMBOLS = (
     "bkf_version", "bkf_create", "bkf_destroy", "bkf_last_error", "bkf_set_stream", "bkf_launch_count",
     "bkf_last_path", "bkf_enable_timing", "bkf_reset_timing", "bkf_kernel_time_ms", "bkf_measure_fma_peak",
     "bkf_filter_forward", "bkf_filter_logp_grad", "bkf_smooth", "bkf_filter_smooth", "bkf_host_alloc", "bkf_host_free",
-    "bkf_logp_grad_workspace_bytes", "bkf_device_memory",
+    "bkf_logp_grad_workspace_bytes", "bkf_device_memory", "bkf_filter_logp_grad_compact",
 )
 
 
@@ -86,6 +86,8 @@ def load_library():
     pp = C.POINTER(BkfProblem)
     lib.bkf_filter_forward.argtypes = [vp, pp] + [vp] * 10 + [vp] * 7 + [vp]
     lib.bkf_filter_logp_grad.argtypes = [vp, pp] + [vp] * 10 + [vp] + [vp] + [vp] * 9 + [vp]
+    lib.bkf_filter_logp_grad_compact.argtypes = [vp, pp, vp, C.POINTER(vp), C.c_int, C.POINTER(C.c_int),
+                                                 C.POINTER(C.c_int), vp, vp, vp, vp, vp]
     lib.bkf_smooth.argtypes = [vp, pp] + [vp] * 5 + [vp] * 2 + [vp]
     lib.bkf_filter_smooth.argtypes = [vp, pp] + [vp] * 10 + [vp] * 3 + [vp]
     _lib = lib
@@ -448,6 +450,44 @@ class KalmanEngine:
         if squeeze:
             return logp[0], {k_: v[0] for k_, v in g.items()}, status[0]
         return logp, g, status
+
+    def logp_grad_compact(self, kind, y, base, positions, u, ll_cotangent=None, cov_jitter=None,
+                          missing_fill_value=None, dtype=None, want_grad=True):
+        """logp and gradient for B draws that differ only in a few matrix entries.
+
+        ``base``: dict of the nine matrices without batch axis; ``positions``: list of ``(name, index_tuple)`` -- entry k
+        of ``u[b]`` is written into ``base[name][index_tuple]`` for draw b; ``u``: (B, len(positions)).  Returns
+        ``(logp (B,), g_u (B, nnz), status (B,))`` where ``g_u[b, k] = d logp_b / d u[b, k]``.  Only ``u``, ``logp`` and
+        ``g_u`` cross the host-device boundary (``bkf_filter_logp_grad_compact``)."""
+        bufs = _Buffers([y, u, *base.values()], dtype)
+        conv = lambda v: v if _is_torch(v) else np.asarray(v)
+        y, u = conv(y), conv(u)
+        base = {k_: conv(base[k_]) for k_ in PARAM_NAMES}
+        for k_ in PARAM_NAMES:
+            if base[k_].ndim != _STATIC_NDIM[k_]:
+                raise BkfError(f"base[{k_!r}] must not have a batch axis")
+        B, nnz = int(u.shape[0]), int(u.shape[1])
+        if nnz != len(positions):
+            raise BkfError("u must have one column per position")
+        prob, yb, arrs = self._problem(kind, bufs, y, base, B, cov_jitter, missing_fill_value)
+        which = (C.c_int * max(nnz, 1))()
+        index = (C.c_int * max(nnz, 1))()
+        for k, (name, idx) in enumerate(positions):
+            which[k] = PARAM_NAMES.index(name)
+            index[k] = int(np.ravel_multi_index(tuple(np.atleast_1d(idx)), base[name].shape))
+        ub = bufs.inp(u)
+        cot = None if ll_cotangent is None else bufs.inp(ll_cotangent)
+        logp = bufs.out((B,))
+        g_u = bufs.out((B, nnz)) if want_grad else None
+        status = bufs.out_int((B,))
+        base_ptrs = (C.c_void_p * 9)(*[bufs.ptr(a).value for a in arrs])
+        if bufs.device:
+            self.use_torch_stream()
+        rc = self.lib.bkf_filter_logp_grad_compact(
+            self.h, C.byref(prob), bufs.ptr(yb), base_ptrs, nnz, which, index, bufs.ptr(ub), bufs.ptr(cot),
+            bufs.ptr(logp), bufs.ptr(g_u), bufs.ptr(status))
+        self._check(rc)
+        return logp, g_u, status
 
     def _logp_grad_in_slices(self, kind, y, params, ll_cotangent, B, nslices, kw):
         """Series are independent: a batch whose trajectory workspace would not fit the device is processed in

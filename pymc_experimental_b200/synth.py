@@ -87,6 +87,20 @@ def sarima(B=16384, n=500, seed=SEED_BASE + 2):
                 Q=np.ascontiguousarray(Q))
 
 
+# (matrix, index) of every entry of the C2 model that depends on the draw (models/SARIMAX.py:383-536): phi, Phi and
+# -Phi*phi in the transition matrix, theta, Theta and Theta*theta in the selection matrix, sigma^2 in the state covariance
+SARIMA_POSITIONS = [("T", (1, 1)), ("T", (12, 1)), ("T", (13, 1)), ("R", (2, 0)), ("R", (13, 0)), ("R", (14, 0)),
+                    ("Q", (0, 0))]
+
+
+def sarima_compact(cfg):
+    """(base, positions, u) of a ``sarima`` config for ``KalmanEngine.logp_grad_compact``."""
+    names = ("a0", "P0", "c", "d", "T", "Z", "R", "H", "Q")
+    base = {k: np.array(cfg[k][0]) for k in names}
+    u = np.stack([cfg[name][(slice(None), *idx)] for name, idx in SARIMA_POSITIONS], axis=1)
+    return base, SARIMA_POSITIONS, np.ascontiguousarray(u)
+
+
 def structural(B=65536, n=240, seed=SEED_BASE + 3):
     """C3: LevelTrend(2) + TimeSeasonality(12) + Cycle, m=15, r=5, with MeasurementError."""
     rng = np.random.default_rng(seed)

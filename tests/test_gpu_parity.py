@@ -416,3 +416,40 @@ def test_batch_is_sliced_when_the_workspace_would_not_fit(eng, device):
         np.testing.assert_array_equal(to_np(g1[k]), to_np(g2[k]), err_msg=k)
     free, total = eng.device_memory()
     assert 0 < free <= total
+
+
+@pytest.mark.parametrize("device", [False, True])
+def test_compact_parameterisation_equals_the_dense_call(eng, device):
+    """draws that differ in a few matrix entries ship only those entries
+    (bkf_filter_logp_grad_compact).  The expanded matrices are the dense call's inputs, so logp is bit-identical and
+    g_u is the dense gradient gathered at the mapped positions."""
+    import torch
+
+    from pymc_experimental_b200 import synth
+
+    B, n = 29, 40
+    cfg = synth.sarima(B=B, n=n)
+    # SARIMA(1,1,1)x(1,0,1,12): phi, Phi, -Phi*phi in T; theta, Theta, Theta*theta in R; sigma^2 in Q (SARIMAX.py:383-536)
+    positions = [("T", (1, 1)), ("T", (12, 1)), ("T", (13, 1)), ("R", (2, 0)), ("R", (13, 0)), ("R", (14, 0)),
+                 ("Q", (0, 0))]
+    base = {k: np.array(cfg[k][0]) for k in NAMES}
+    u = np.stack([cfg[name][(slice(None), *idx)] for name, idx in positions], axis=1)
+    cot = np.random.default_rng(9).standard_normal((B, n))
+    dense = [cfg["y"]] + [cfg[k] for k in NAMES]
+    y, uu, cc, bb = cfg["y"], u, cot, base
+    if device:
+        t = lambda a: torch.as_tensor(np.ascontiguousarray(a), device="cuda:0")
+        dense, y, uu, cc, bb = [t(a) for a in dense], t(y), t(u), t(cot), {k: t(v) for k, v in base.items()}
+    to_np = lambda x: x.cpu().numpy() if device else x
+    logp_d, g_d, st_d = eng.logp_grad("univariate", *dense, ll_cotangent=cc)
+    logp_c, g_u, st_c = eng.logp_grad_compact("univariate", y, bb, positions, uu, ll_cotangent=cc)
+    assert eng.last_path == "dmma_f64"
+    np.testing.assert_array_equal(to_np(logp_c), to_np(logp_d))
+    np.testing.assert_array_equal(to_np(st_c), to_np(st_d))
+    for k, (name, idx) in enumerate(positions):
+        np.testing.assert_array_equal(to_np(g_u)[:, k], to_np(g_d[name])[(slice(None), *idx)], err_msg=f"{name}{idx}")
+    from pymc_experimental_b200.engine import BkfError
+
+    with pytest.raises(BkfError, match="unique"):
+        eng.logp_grad_compact("univariate", y, bb, positions + [("T", (1, 1))],
+                              np.concatenate([u, u[:, :1]], axis=1) if not device else torch.cat([uu, uu[:, :1]], 1))
