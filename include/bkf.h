@@ -60,7 +60,8 @@ enum { BKF_OK = 0, BKF_ERR_ARG = -1, BKF_ERR_UNSUPPORTED = -2, BKF_ERR_CUDA = -3
 /* per-series status bits */
 enum { BKF_STATUS_OK = 0, BKF_STATUS_NOT_PD = 1, BKF_STATUS_NONFINITE = 2,
        BKF_STATUS_SMOOTHER_ILL = 4 /* P_hat too ill-conditioned for the Cholesky smoother: series was re-run with the
-                                      eigen-decomposition pinv (informational) */ };
+                                      eigen-decomposition pinv (informational) */,
+       BKF_STATUS_NOT_STATIONARY = 8 /* bkf_stationary_init: the powers of T do not decay (spectral radius >= 1) */ };
 
 typedef struct bkf_handle bkf_handle;
 
@@ -146,6 +147,20 @@ int bkf_filter_logp_grad(bkf_handle* h, const bkf_problem* prob, const void* y, 
 int bkf_filter_logp_grad_compact(bkf_handle* h, const bkf_problem* prob, const void* y, const void* const base[9],
                                  int nnz, const int* which, const int* index, const void* u, const void* ll_cotangent,
                                  void* logp, void* g_u, int* status);
+
+/* Stationary initialisation, the step right before the filter in the reference's SARIMA /
+ * VARMA / ETS models (models/SARIMAX.py:369-381, VARMAX.py:379-393, ETS.py:453-466):
+ *     a0 = (I - T)^{-1} c          P0 = solve_discrete_lyapunov(T, R Q R^T)      (P0 = T P0 T^T + R Q R^T)
+ * Uses prob->{dtype,mem,B,m,r,shared_mask(c,T,R,Q)}.  a0 [B,m], P0 [B,m,m].  status[b] gets
+ * BKF_STATUS_NOT_STATIONARY when the series in T does not converge. */
+int bkf_stationary_init(bkf_handle* h, const bkf_problem* prob, const void* c, const void* T, const void* R,
+                        const void* Q, void* a0, void* P0, int* status);
+/* Pull-back of bkf_stationary_init: given its results a0, P0 and their cotangents a0_bar [B,m] (may be NULL),
+ * P0_bar [B,m,m] (may be NULL), writes g_c [B,m], g_T [B,m,m], g_R [B,m,r], g_Q [B,r,r] (any may be NULL) -- what
+ * PyTensor's SolveDiscreteLyapunov / Solve L_ops yield. */
+int bkf_stationary_init_grad(bkf_handle* h, const bkf_problem* prob, const void* T, const void* R, const void* Q,
+                             const void* a0, const void* P0, const void* a0_bar, const void* P0_bar, void* g_c,
+                             void* g_T, void* g_R, void* g_Q);
 
 /* Uses prob->{dtype,mem,B,n,m,r,shared_mask(T,R,Q),cov_jitter}.  filtered_* are [B,n,m] / [B,n,m,m]. */
 int bkf_smooth(bkf_handle* h, const bkf_problem* prob, const void* T, const void* R, const void* Q,

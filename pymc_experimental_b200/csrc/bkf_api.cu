@@ -702,6 +702,107 @@ extern "C" int bkf_filter_logp_grad_compact(bkf_handle* h, const bkf_problem* P,
 }
 
 // ----------------------------------------------------------------------------------------------------
+// stationary initialisation (bkf.h: bkf_stationary_init, bkf_stationary_init_grad)
+template <typename R>
+static int stationary_impl(bkf_handle* h, const bkf_problem* P, const void* c, const void* T, const void* Rm,
+                           const void* Q, void* a0, void* P0, int* status) {
+    int rc = BKF_OK;
+    KArgs<R> g;
+    const void* prm[BKF_NPARAM] = {nullptr, nullptr, c, nullptr, T, nullptr, Rm, nullptr, Q};
+    bkf_problem P2 = *P;
+    P2.p = P2.p > 0 ? P2.p : 1;
+    P2.n = P2.n > 0 ? P2.n : 1;
+    fill_inputs<R>(h, &P2, g, nullptr, prm, &rc);
+    const size_t B = P->B, m = P->m;
+    g.sm_a = stage_out<R>(h, P, S_SMA, a0, B * m, &rc);
+    g.sm_P = stage_out<R>(h, P, S_SMP, P0, B * m * m, &rc);
+    int* dstatus = nullptr;
+    if (status) dstatus = P->mem == BKF_MEM_DEVICE ? status : (int*)ensure(h, S_STATUS, B * sizeof(int), &rc);
+    g.status = dstatus;
+    if (rc != BKF_OK) return rc;
+    if (!g.sm_a || !g.sm_P) return fail(h, BKF_ERR_ARG, "null output pointer");
+    if (B == 0) return BKF_OK;
+    const char* err = "";
+    h->launches += 1;
+    h->path = "stationary_warp";
+    rc = stat::launch<R>(g, false, h->stream, &err);
+    if (rc != BKF_OK) return fail(h, rc, err);
+    copy_back<R>(h, P, a0, g.sm_a, B * m, &rc);
+    copy_back<R>(h, P, P0, g.sm_P, B * m * m, &rc);
+    if (status && P->mem == BKF_MEM_HOST && rc == BKF_OK) {
+        cudaError_t e = cudaMemcpyAsync(status, dstatus, B * sizeof(int), cudaMemcpyDeviceToHost, h->stream);
+        if (e != cudaSuccess) rc = cuda_fail(h, e, "D2H copy");
+    }
+    return finish(h, P, rc);
+}
+
+template <typename R>
+static int stationary_grad_impl(bkf_handle* h, const bkf_problem* P, const void* T, const void* Rm, const void* Q,
+                                const void* a0, const void* P0, const void* a0b, const void* P0b, void* g_c, void* g_T,
+                                void* g_R, void* g_Q) {
+    int rc = BKF_OK;
+    KArgs<R> g;
+    const void* prm[BKF_NPARAM] = {nullptr, nullptr, nullptr, nullptr, T, nullptr, Rm, nullptr, Q};
+    bkf_problem P2 = *P;
+    P2.p = P2.p > 0 ? P2.p : 1;
+    P2.n = P2.n > 0 ? P2.n : 1;
+    fill_inputs<R>(h, &P2, g, nullptr, prm, &rc);
+    const size_t B = P->B, m = P->m, r = P->r;
+    g.sm_filt_a = stage_in<R>(h, P, S_WFA, a0, B * m, &rc);
+    g.sm_filt_P = stage_in<R>(h, P, S_WFP, P0, B * m * m, &rc);
+    g.a0 = stage_in<R>(h, P, S_A0, a0b, B * m, &rc);   // cotangents travel in the a0 / P0 input slots
+    g.P0 = stage_in<R>(h, P, S_P0, P0b, B * m * m, &rc);
+    g.g_c = stage_out<R>(h, P, S_GC, g_c, B * m, &rc);
+    g.g_T = stage_out<R>(h, P, S_GT, g_T, B * m * m, &rc);
+    g.g_R = stage_out<R>(h, P, S_GR, g_R, B * m * r, &rc);
+    g.g_Q = stage_out<R>(h, P, S_GQ, g_Q, B * r * r, &rc);
+    if (rc != BKF_OK) return rc;
+    if (B == 0) return BKF_OK;
+    const char* err = "";
+    h->launches += 1;
+    h->path = "stationary_warp";
+    rc = stat::launch<R>(g, true, h->stream, &err);
+    if (rc != BKF_OK) return fail(h, rc, err);
+    copy_back<R>(h, P, g_c, g.g_c, B * m, &rc);
+    copy_back<R>(h, P, g_T, g.g_T, B * m * m, &rc);
+    copy_back<R>(h, P, g_R, g.g_R, B * m * r, &rc);
+    copy_back<R>(h, P, g_Q, g.g_Q, B * r * r, &rc);
+    return finish(h, P, rc);
+}
+
+static int validate_stationary(bkf_handle* h, const bkf_problem* P) {
+    if (!h) return BKF_ERR_ARG;
+    if (!P) return fail(h, BKF_ERR_ARG, "null problem");
+    if (P->dtype != BKF_F64 && P->dtype != BKF_F32) return fail(h, BKF_ERR_ARG, "unknown dtype");
+    if (P->mem != BKF_MEM_HOST && P->mem != BKF_MEM_DEVICE) return fail(h, BKF_ERR_ARG, "unknown memory space");
+    if (P->B < 0 || P->m < 1 || P->r < 1) return fail(h, BKF_ERR_ARG, "non-positive dimension");
+    if (P->tv_mask) return fail(h, BKF_ERR_UNSUPPORTED, "a time-varying model has no stationary initialisation");
+    cudaError_t e = cudaSetDevice(h->device);
+    if (e != cudaSuccess) return cuda_fail(h, e, "cudaSetDevice");
+    return BKF_OK;
+}
+
+extern "C" int bkf_stationary_init(bkf_handle* h, const bkf_problem* P, const void* c, const void* T, const void* R,
+                                   const void* Q, void* a0, void* P0, int* status) {
+    int rc = validate_stationary(h, P);
+    if (rc != BKF_OK) return rc;
+    if (!c || !T || !R || !Q) return fail(h, BKF_ERR_ARG, "null input pointer");
+    return P->dtype == BKF_F64 ? stationary_impl<double>(h, P, c, T, R, Q, a0, P0, status)
+                               : stationary_impl<float>(h, P, c, T, R, Q, a0, P0, status);
+}
+
+extern "C" int bkf_stationary_init_grad(bkf_handle* h, const bkf_problem* P, const void* T, const void* R,
+                                        const void* Q, const void* a0, const void* P0, const void* a0_bar,
+                                        const void* P0_bar, void* g_c, void* g_T, void* g_R, void* g_Q) {
+    int rc = validate_stationary(h, P);
+    if (rc != BKF_OK) return rc;
+    if (!T || !R || !Q || !a0 || !P0) return fail(h, BKF_ERR_ARG, "null input pointer");
+    return P->dtype == BKF_F64
+               ? stationary_grad_impl<double>(h, P, T, R, Q, a0, P0, a0_bar, P0_bar, g_c, g_T, g_R, g_Q)
+               : stationary_grad_impl<float>(h, P, T, R, Q, a0, P0, a0_bar, P0_bar, g_c, g_T, g_R, g_Q);
+}
+
+// ----------------------------------------------------------------------------------------------------
 template <typename R>
 static int smooth_impl(bkf_handle* h, const bkf_problem* P, const void* T, const void* Rm, const void* Q,
                        const void* fa, const void* fP, void* sa, void* sP, int* status) {

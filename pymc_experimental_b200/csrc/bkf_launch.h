@@ -28,6 +28,9 @@ int launch_f64(const KArgs<double>& g, bool backward, cudaStream_t stream, const
 bool smoother_supported(int m);
 int launch_smoother_f64(const KArgs<double>& g, double jitter0, int* any_ill, cudaStream_t stream, const char** err);
 }  // namespace tc
+namespace stat {  // stationary initialisation: Lyapunov / (I - T)^{-1} c by doubling (bkf_stationary.cu)
+template <typename R> int launch(const KArgs<R>& g, bool backward, cudaStream_t stream, const char** err);
+}  // namespace stat
 namespace tps {  // thread-per-series kernels, m <= 4, p = 1 (bkf_thread.cu)
 bool supported(int kind, int m, int p);
 template <typename R> int launch_any(const KArgs<R>& g, bool backward, cudaStream_t stream, const char** err);

@@ -22,7 +22,7 @@ KINDS = {"standard": STANDARD, "univariate": UNIVARIATE, "cholesky": CHOLESKY}
 F64, F32 = 0, 1
 MEM_HOST, MEM_DEVICE = 0, 1
 PARAM_NAMES = ("a0", "P0", "c", "d", "T", "Z", "R", "H", "Q")  # utils/constants.py:24 (x0 == a0)
-STATUS_NOT_PD, STATUS_NONFINITE, STATUS_SMOOTHER_ILL = 1, 2, 4
+STATUS_NOT_PD, STATUS_NONFINITE, STATUS_SMOOTHER_ILL, STATUS_NOT_STATIONARY = 1, 2, 4, 8
 
 # pymc_extras/statespace/utils/constants.py:19-20
 MISSING_FILL = -9999.0
@@ -33,7 +33,8 @@ ABI_SYMBOLS = (
     "bkf_version", "bkf_create", "bkf_destroy", "bkf_last_error", "bkf_set_stream", "bkf_launch_count",
     "bkf_last_path", "bkf_enable_timing", "bkf_reset_timing", "bkf_kernel_time_ms", "bkf_measure_fma_peak",
     "bkf_filter_forward", "bkf_filter_logp_grad", "bkf_smooth", "bkf_filter_smooth", "bkf_host_alloc", "bkf_host_free",
-    "bkf_logp_grad_workspace_bytes", "bkf_device_memory", "bkf_filter_logp_grad_compact",
+    "bkf_logp_grad_workspace_bytes", "bkf_device_memory", "bkf_filter_logp_grad_compact", "bkf_stationary_init",
+    "bkf_stationary_init_grad",
 )
 
 
@@ -88,6 +89,8 @@ def load_library():
     lib.bkf_filter_logp_grad.argtypes = [vp, pp] + [vp] * 10 + [vp] + [vp] + [vp] * 9 + [vp]
     lib.bkf_filter_logp_grad_compact.argtypes = [vp, pp, vp, C.POINTER(vp), C.c_int, C.POINTER(C.c_int),
                                                  C.POINTER(C.c_int), vp, vp, vp, vp, vp]
+    lib.bkf_stationary_init.argtypes = [vp, pp] + [vp] * 4 + [vp] * 2 + [vp]
+    lib.bkf_stationary_init_grad.argtypes = [vp, pp] + [vp] * 7 + [vp] * 4
     lib.bkf_smooth.argtypes = [vp, pp] + [vp] * 5 + [vp] * 2 + [vp]
     lib.bkf_filter_smooth.argtypes = [vp, pp] + [vp] * 10 + [vp] * 3 + [vp]
     _lib = lib
@@ -488,6 +491,55 @@ class KalmanEngine:
             bufs.ptr(logp), bufs.ptr(g_u), bufs.ptr(status))
         self._check(rc)
         return logp, g_u, status
+
+    # ------------------------------------------------------------------------------------------------
+    def _stationary_problem(self, bufs, c, T, R, Q):
+        conv = lambda v: v if _is_torch(v) else np.asarray(v)
+        vals = {"c": conv(c), "T": conv(T), "R": conv(R), "Q": conv(Q)}
+        B = None
+        for name, x in vals.items():
+            if x.ndim == _STATIC_NDIM[name] + 1:
+                if B is not None and x.shape[0] != B:
+                    raise BkfError(f"inconsistent batch sizes ({B} vs {x.shape[0]} for {name})")
+                B = int(x.shape[0])
+            elif x.ndim != _STATIC_NDIM[name]:
+                raise BkfError(f"{name}: expected {_STATIC_NDIM[name]} or {_STATIC_NDIM[name] + 1} dims")
+        squeeze = B is None
+        B = 1 if squeeze else B
+        m, r = int(vals["R"].shape[-2]), int(vals["R"].shape[-1])
+        shared = 0
+        for name in ("c", "T", "R", "Q"):
+            if vals[name].ndim == _STATIC_NDIM[name]:
+                shared |= 1 << PARAM_NAMES.index(name)
+        prob = BkfProblem(kind=STANDARD, dtype=bufs.code, mem=MEM_DEVICE if bufs.device else MEM_HOST, B=B, n=1, m=m,
+                          p=1, r=r, y_shared=0, shared_mask=shared, tv_mask=0, cov_jitter=0.0, missing_fill=MISSING_FILL)
+        return prob, {k_: bufs.inp(v) for k_, v in vals.items()}, B, m, r, squeeze
+
+    def stationary_init(self, c, T, R, Q, dtype=None):
+        """``a0 = (I - T)^-1 c`` and ``P0 = solve_discrete_lyapunov(T, R Q R^T)`` for a batch of models
+        (models/SARIMAX.py:369-381, VARMAX.py:379-393).  Returns ``(a0, P0, status)``."""
+        bufs = _Buffers([c, T, R, Q], dtype)
+        prob, v, B, m, r, squeeze = self._stationary_problem(bufs, c, T, R, Q)
+        a0, P0, status = bufs.out((B, m)), bufs.out((B, m, m)), bufs.out_int((B,))
+        if bufs.device:
+            self.use_torch_stream()
+        self._check(self.lib.bkf_stationary_init(self.h, C.byref(prob), *[bufs.ptr(v[k_]) for k_ in ("c", "T", "R", "Q")],
+                                                 bufs.ptr(a0), bufs.ptr(P0), bufs.ptr(status)))
+        return (a0[0], P0[0], status[0]) if squeeze else (a0, P0, status)
+
+    def stationary_init_grad(self, T, R, Q, a0, P0, a0_bar, P0_bar, dtype=None):
+        """Pull-back of :meth:`stationary_init`: ``{c, T, R, Q: gradient}`` of ``<a0_bar, a0> + <P0_bar, P0>``."""
+        bufs = _Buffers([T, R, Q, a0, P0], dtype)
+        prob, v, B, m, r, squeeze = self._stationary_problem(bufs, np.zeros(int(np.shape(T)[-1])), T, R, Q)
+        fix = lambda x, nd: None if x is None else bufs.inp(x if not squeeze else x[None])
+        a0b, P0b, ab, Pb = fix(a0, 1), fix(P0, 2), fix(a0_bar, 1), fix(P0_bar, 2)
+        g = {"c": bufs.out((B, m)), "T": bufs.out((B, m, m)), "R": bufs.out((B, m, r)), "Q": bufs.out((B, r, r))}
+        if bufs.device:
+            self.use_torch_stream()
+        self._check(self.lib.bkf_stationary_init_grad(
+            self.h, C.byref(prob), bufs.ptr(v["T"]), bufs.ptr(v["R"]), bufs.ptr(v["Q"]), bufs.ptr(a0b), bufs.ptr(P0b),
+            bufs.ptr(ab), bufs.ptr(Pb), *[bufs.ptr(g[k_]) for k_ in ("c", "T", "R", "Q")]))
+        return {k_: x[0] for k_, x in g.items()} if squeeze else g
 
     def _logp_grad_in_slices(self, kind, y, params, ll_cotangent, B, nslices, kw):
         """Series are independent: a batch whose trajectory workspace would not fit the device is processed in

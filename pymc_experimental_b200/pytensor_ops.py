@@ -139,6 +139,58 @@ class KalmanSmootherOp(Op):
         return [ins_shapes[3], ins_shapes[4]]
 
 
+class StationaryInitOp(Op):
+    """c, T, R, Q -> x0 = (I - T)^-1 c, P0 = solve_discrete_lyapunov(T, R Q R^T)  (bkf_stationary_init; models/SARIMAX.py:
+    369-381).  ``L_op`` applies :class:`StationaryInitGradOp` (bkf_stationary_init_grad), i.e. the pull-backs of
+    PyTensor's ``Solve`` and ``SolveDiscreteLyapunov`` Ops."""
+
+    __props__ = ("device",)
+
+    def __init__(self, device=0):
+        self.device = int(device)
+
+    def make_node(self, c, T, R, Q):
+        ins = [pt.as_tensor_variable(x) for x in (c, T, R, Q)]
+        if [x.ndim for x in ins] != [1, 2, 2, 2]:
+            raise ValueError("c, T, R, Q must be a vector and three matrices")
+        return Apply(self, ins, [ins[0].type(), ins[1].type()])
+
+    def perform(self, node, inputs, output_storage, params=None):
+        a0, P0, status = default_engine(self.device).stationary_init(*inputs, dtype=node.outputs[0].dtype)
+        if int(status) & 8:
+            raise np.linalg.LinAlgError("stationary initialisation: the transition matrix is not stationary")
+        output_storage[0][0], output_storage[1][0] = a0, P0
+
+    def infer_shape(self, fgraph, node, ins_shapes):
+        return [ins_shapes[0], ins_shapes[1]]
+
+    def L_op(self, inputs, outputs, output_grads):
+        c, T, R, Q = inputs
+        gb = [pt.zeros_like(o) if isinstance(g.type, DisconnectedType) else g for o, g in zip(outputs, output_grads)]
+        return StationaryInitGradOp(self.device)(T, R, Q, outputs[0], outputs[1], *gb)
+
+
+class StationaryInitGradOp(Op):
+    """T, R, Q, x0, P0, x0_bar, P0_bar -> c_bar, T_bar, R_bar, Q_bar."""
+
+    __props__ = ("device",)
+
+    def __init__(self, device=0):
+        self.device = int(device)
+
+    def make_node(self, T, R, Q, a0, P0, a0_bar, P0_bar):
+        ins = [pt.as_tensor_variable(x) for x in (T, R, Q, a0, P0, a0_bar, P0_bar)]
+        return Apply(self, ins, [ins[3].type(), ins[0].type(), ins[1].type(), ins[2].type()])
+
+    def perform(self, node, inputs, output_storage, params=None):
+        g = default_engine(self.device).stationary_init_grad(*inputs, dtype=node.outputs[0].dtype)
+        for store, name in zip(output_storage, ("c", "T", "R", "Q")):
+            store[0] = g[name]
+
+    def infer_shape(self, fgraph, node, ins_shapes):
+        return [ins_shapes[3], ins_shapes[0], ins_shapes[1], ins_shapes[2]]
+
+
 def build_filter_graph(flt, data, a0, P0, c, d, T, Z, R, H, Q):
     """Symbolic branch of ``BaseFilter.build_graph``: one Op node, outputs named / shaped as the reference does
     (kalman_filter.py:271-296)."""

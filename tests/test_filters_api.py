@@ -177,3 +177,27 @@ def test_time_varying_inputs_are_detected_by_ndim_like_the_reference(cls, rng):
     ra, rP = onp.kalman_smoother(T, R, Qt, ref[0], ref[3])
     assert_allclose(sa, ra, rtol=1e-8, atol=1e-8 * max(1.0, np.abs(ra).max()))
     assert_allclose(sP, rP, rtol=1e-8, atol=1e-8 * max(1.0, np.abs(rP).max()))
+
+
+@pytest.mark.gpu
+def test_solve_discrete_lyapunov_mirror(rng):
+    """pymc_experimental_b200.stationary.solve_discrete_lyapunov against scipy (what the reference's "bilinear" method
+    calls), unbatched and batched, and the non-stationary error."""
+    import scipy.linalg
+
+    from pymc_experimental_b200.stationary import solve_discrete_lyapunov, stationary_initialization
+
+    m = 5
+    A = rng.standard_normal((m, m))
+    A *= 0.8 / np.abs(np.linalg.eigvals(A)).max()
+    L = rng.standard_normal((m, m))
+    Q = L @ L.T
+    X = solve_discrete_lyapunov(A, Q)
+    assert_allclose(X, scipy.linalg.solve_discrete_lyapunov(A, Q), rtol=1e-9, atol=1e-11)
+    Xb = solve_discrete_lyapunov(np.stack([A, 0.5 * A]), np.stack([Q, Q]))
+    assert_allclose(Xb[1], scipy.linalg.solve_discrete_lyapunov(0.5 * A, Q), rtol=1e-9, atol=1e-11)
+    c = rng.standard_normal(m)
+    x0, P0 = stationary_initialization(c, A, np.eye(m), Q)
+    assert_allclose(x0, np.linalg.solve(np.eye(m) - A, c), rtol=1e-9)
+    with pytest.raises(np.linalg.LinAlgError):
+        solve_discrete_lyapunov(np.eye(m), Q)

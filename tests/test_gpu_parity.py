@@ -453,3 +453,40 @@ def test_compact_parameterisation_equals_the_dense_call(eng, device):
     with pytest.raises(BkfError, match="unique"):
         eng.logp_grad_compact("univariate", y, bb, positions + [("T", (1, 1))],
                               np.concatenate([u, u[:, :1]], axis=1) if not device else torch.cat([uu, uu[:, :1]], 1))
+
+
+@pytest.mark.parametrize("shape", [(3, 1), (6, 3), (15, 1), (16, 4), (32, 16)])
+@pytest.mark.parametrize("device", [False, True])
+def test_stationary_initialisation_matches_the_oracle(eng, shape, device):
+    """a0 = (I - T)^-1 c and P0 = solve_discrete_lyapunov(T, R Q R^T)
+    (models/SARIMAX.py:369-381, VARMAX.py:379-393) for a batch, and their pull-back, against oracle/stationary.py."""
+    import torch
+
+    from oracle import stationary as ost
+
+    m, r = shape
+    B = 7
+    rng = np.random.default_rng(50 + m)
+    T = rng.standard_normal((B, m, m))
+    rho = np.array([0.5, 0.9, 0.97, 0.2, 0.8, 0.99, 0.6])
+    T *= (rho / np.abs(np.linalg.eigvals(T)).max(axis=1))[:, None, None]
+    R, c = rng.standard_normal((B, m, r)), rng.standard_normal((B, m))
+    L = rng.standard_normal((B, r, r))
+    Q = L @ np.swapaxes(L, -1, -2) + 0.1 * np.eye(r)
+    ab, Pb = rng.standard_normal((B, m)), rng.standard_normal((B, m, m))
+    wrap = (lambda a: torch.as_tensor(a, device="cuda:0")) if device else (lambda a: a)
+    to_np = lambda x: x.cpu().numpy() if device else x
+    a0, P0, status = eng.stationary_init(wrap(c), wrap(T), wrap(R), wrap(Q))
+    assert eng.last_path == "stationary_warp"
+    assert (to_np(status) == 0).all()
+    g = eng.stationary_init_grad(wrap(T), wrap(R), wrap(Q), a0, P0, wrap(ab), wrap(Pb))
+    for b in range(B):
+        ra, rP, rg = ost.stationary_init_grad(c[b], T[b], R[b], Q[b], ab[b], Pb[b])
+        _close(to_np(a0)[b], ra, 1e-9, f"a0[{b}]")
+        _close(to_np(P0)[b], rP, 1e-9, f"P0[{b}]")
+        for k in ("c", "T", "R", "Q"):
+            _close(to_np(g[k])[b], rg[k], 1e-8, f"d/d{k}[{b}]")
+    # a unit root is not stationary: flagged, not silently wrong
+    Tu = np.eye(m)[None]
+    _, _, st = eng.stationary_init(c[:1], Tu, R[:1], Q[:1])
+    assert st[0] == 8

@@ -228,3 +228,36 @@ def test_univariate_time_varying_oracles_agree(tv):
     assert_allclose(ll_np, ll_th, rtol=1e-11)
     ll_std = onp.kalman_filter("standard", *args)[-1]
     assert_allclose(ll_np, ll_std, rtol=1e-6)
+
+
+def test_stationary_init_oracle_direct_equals_bilinear_and_gradient_matches_finite_differences():
+    """oracle/stationary.py: the two solve_discrete_lyapunov methods the reference selects between agree, the result
+    satisfies P0 = T P0 T^T + R Q R^T, and the torch gradient matches central differences."""
+    from oracle import stationary as ost
+
+    rng = np.random.default_rng(21)
+    m, r = 6, 3
+    T = rng.standard_normal((m, m))
+    T *= 0.9 / np.abs(np.linalg.eigvals(T)).max()
+    R, c = rng.standard_normal((m, r)), rng.standard_normal(m)
+    L = rng.standard_normal((r, r))
+    Q = L @ L.T + 0.1 * np.eye(r)
+    a0, P0 = ost.stationary_init_np(c, T, R, Q, "direct")
+    _, P0b = ost.stationary_init_np(c, T, R, Q, "bilinear")
+    assert_allclose(P0, P0b, rtol=1e-10, atol=1e-12)
+    assert_allclose(P0, T @ P0 @ T.T + R @ Q @ R.T, rtol=1e-10, atol=1e-12)
+    assert_allclose(a0, T @ a0 + c, rtol=1e-10, atol=1e-12)
+    ab, Pb = rng.standard_normal(m), rng.standard_normal((m, m))
+    _, _, g = ost.stationary_init_grad(c, T, R, Q, ab, Pb)
+    def f(c, T, R, Q):
+        a, P = ost.stationary_init_np(c, T, R, Q)
+        return (a * ab).sum() + (P * Pb).sum()
+
+    args = {"c": c, "T": T, "R": R, "Q": Q}
+    for k, x in args.items():
+        for idx in [tuple(rng.integers(0, s) for s in x.shape) for _ in range(4)]:
+            xp, xm = x.copy(), x.copy()
+            xp[idx] += 1e-6
+            xm[idx] -= 1e-6
+            fd = (f(**{**args, k: xp}) - f(**{**args, k: xm})) / 2e-6
+            assert_allclose(g[k][idx], fd, rtol=1e-6, atol=1e-7)
