@@ -272,6 +272,9 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    # torchrun pins OMP_NUM_THREADS=1 in every worker; the CPU arm runs alone on rank 0 and may use the whole host
+    if int(os.environ.get("WORLD_SIZE", "1")) > 1 or "OMP_NUM_THREADS" not in os.environ:
+        os.environ["OMP_NUM_THREADS"] = os.environ.get("BKF_CPU_THREADS", str(os.cpu_count() or 1))
     name = args.workload
     _, kind, dB, dT, mode = WORKLOADS[name]
     T = args.T or dT
