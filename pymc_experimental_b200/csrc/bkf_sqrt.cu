@@ -147,6 +147,30 @@ __device__ void householder_r(R* W, int rows, int cols, R* red, Th th) {
     }
 }
 
+// Sums of eight per-lane values over the warp, all eight totals returned in every lane.  Instead of eight 5-stage
+// butterflies (40 double shuffles) the first three stages exchange HALF of the values each (4 + 2 + 1 shuffles), two more
+// finish the one value a lane is left with, and eight broadcasts hand the totals out: 17 double shuffles, 9 adds.
+__device__ __forceinline__ void warp_sum8(double (&v)[8], int lane) {
+    const bool h4 = lane & 16, h3 = lane & 8, h2 = lane & 4;
+    double w[4], x[2];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const double send = h4 ? v[j] : v[j + 4], keep = h4 ? v[j + 4] : v[j];
+        w[j] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+    }
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+        const double send = h3 ? w[j] : w[j + 2], keep = h3 ? w[j + 2] : w[j];
+        x[j] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+    }
+    double y = (h2 ? x[1] : x[0]) + __shfl_xor_sync(0xffffffffu, h2 ? x[0] : x[1], 4);
+    y += __shfl_xor_sync(0xffffffffu, y, 2);
+    y += __shfl_xor_sync(0xffffffffu, y, 1);
+    // lane holds the total of value 4*bit4 + 2*bit3 + bit2 = (lane >> 2) & 7
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = __shfl_sync(0xffffffffu, y, 4 * j);
+}
+
 // Blocked Householder R factor (panel width 8, compact-WY trailing updates on DMMA tiles); rows, cols multiples of 8,
 // rows <= 64.  Same reflectors as householder_r (LAPACK dgeqr2/dlarfg sign rules), applied block-wise as dgeqrf does:
 //   panel:    one warp, lane-per-row (rows l and l + 32), the 8 panel columns in registers, warp reductions
@@ -179,14 +203,12 @@ __device__ void householder_r_fast(double* W, int rows, int cols, double* hv, do
                 // x = a[k+1:, k] (unscaled).  ONE window of independent warp reductions per reflector:
                 //   ss = x.x,  d[c] = x . a[k+1:, c] (c > k),  e[i] = x . v_i[k+1:] (i < k, for the T factor)
                 const double x0 = lane > k ? a[0][k] : 0.0, x1 = a[1][k];
-                double ss = warp_sum(fma(x1, x1, x0 * x0));
-                double d[8], e[8];
+                double d[8];  // c > k: trailing panel column;  c == k: ss;  c < k: column c holds v_c below its diagonal
 #pragma unroll
-                for (int c = 0; c < 8; ++c) {
-                    const double dot = warp_sum(fma(x1, a[1][c], x0 * a[0][c]));
-                    d[c] = dot;  // c > k: trailing panel column;  c < k: column c holds v_c below its diagonal
-                    e[c] = dot;
-                }
+                for (int c = 0; c < 8; ++c) d[c] = fma(x1, a[1][c], x0 * a[0][c]);
+                warp_sum8(d, lane);
+                const double ss = d[k];
+                const double(&e)[8] = d;
                 const double alpha = __shfl_sync(0xffffffffu, a[0][k], k);
                 if (ss == 0.0) {  // dlarfg: tau = 0, H = I
                     if (lane > k) a[0][k] = 0.0;
