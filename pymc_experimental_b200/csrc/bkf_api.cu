@@ -240,6 +240,10 @@ static int run_forward(bkf_handle* h, const KArgs<double>& g, const char** err) 
     KernelTimer kt(h, BKF_KERNEL_FORWARD);
     h->launches += 1;
     if (g.kind == BKF_CHOLESKY) {
+        if (sqw::supported(g, false)) {
+            h->path = "sqrt_warp_dmma";
+            return sqw::launch_f64(g, false, h->stream, err);
+        }
         h->path = "sqrt_cta";
         return sq::launch_forward<double>(g, h->stream, err);
     }
@@ -279,7 +283,9 @@ static int run_forward(bkf_handle* h, const KArgs<float>& g, const char** err) {
 static int run_backward(bkf_handle* h, const KArgs<double>& g, const char** err) {
     KernelTimer kt(h, BKF_KERNEL_BACKWARD);
     h->launches += 1;
-    if (g.kind == BKF_CHOLESKY) return sq::launch_backward<double>(g, h->stream, err);
+    if (g.kind == BKF_CHOLESKY)
+        return sqw::supported(g, true) ? sqw::launch_f64(g, true, h->stream, err)
+                                       : sq::launch_backward<double>(g, h->stream, err);
     if (g.tv_mask) return gen::launch_backward<double>(g, h->stream, err);
     if (tps::supported(g.kind, g.m, g.p)) return tps::launch_any<double>(g, true, h->stream, err);
     if (tc::supported(g.kind, g.m, g.p)) return tc::launch_f64(g, true, h->stream, err);

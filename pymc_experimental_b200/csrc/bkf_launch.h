@@ -15,6 +15,10 @@ size_t traj_record_elems_host(int m, int p);  // forward-sweep record kept for t
 template <typename R> int launch_forward(const KArgs<R>& g, cudaStream_t stream, const char** err);
 template <typename R> int launch_backward(const KArgs<R>& g, cudaStream_t stream, const char** err);
 }  // namespace sq
+namespace sqw {  // square-root filter, warp per series on DMMA tiles, float64, selected shapes (bkf_sqrt_warp.cu)
+bool supported(const KArgs<double>& g, bool backward);
+int launch_f64(const KArgs<double>& g, bool backward, cudaStream_t stream, const char** err);
+}  // namespace sqw
 namespace sw {  // register-tiled sub-warp-per-series kernels, float64, p = 1 (bkf_subwarp.cu)
 bool supported(int kind, int m, int p);
 int launch_f64(const KArgs<double>& g, bool backward, cudaStream_t stream, const char** err);

@@ -1,0 +1,526 @@
+// bkf_sqrt_warp.cuh -- SquareRootFilter (kalman_filter.py:620-750) on FP64 tensor-core tiles, ONE WARP PER SERIES.
+//
+// Same arithmetic as bkf_sqrt.cu (CTA per series) -- Householder QR with LAPACK's dgeqr2/dlarfg sign rules, the Q-free
+// QR pull-back -- but organised so that a warp never waits for another one:
+//
+//   * every matrix lives in the warp's shared-memory arena as 8 x 8 tiles in DMMA accumulator order ("C layout":
+//     lane 4g+t owns elements [g][2t], [g][2t+1] of a tile, one 16-byte word), so a tile load/store is one conflict-free
+//     512-byte access and a loaded tile is directly an operand of   D += X Y^T   (mma_nt: two DMMA.8x8x4 whose A / B
+//     operands are the accumulator registers of X / Y, see bkf_mma.cuh);
+//   * the arrays that are factored are stored TRANSPOSED (tile row = column block of the array): the 8-column panel of
+//     a Householder sweep is then one tile row, a lane group g owns column g of the panel, the reflector is broadcast
+//     with one shuffle per element and all inner products of a reflector step are formed in one reduction window; the
+//     compact-WY factor T is built on the fly from the same window (dlarft), and the trailing update
+//     A^T <- A^T - (A^T V) T V^T  is three chains of mma_nt per column block;
+//   * the update array [[Hc, Zm Pc], [0, Pc]] and the predict array [T Pcf, R Qc] share one tile array: the factor of
+//     one is written where the next one reads it (Pc never moves).
+//
+// Shapes: float64, m, p, r multiples of 8 with r <= p (instantiated for the shapes in bkf_sqrt_warp.cu).  Everything else
+// takes the CTA-per-series kernels.  The forward record kept for the adjoint is the one of bkf_sqrt.cu
+// ([a | Pc | triu(Rf) | triu(Rp)]), so either family's adjoint can read either family's forward sweep.
+#pragma once
+#include "bkf_common.cuh"
+
+namespace bkf {
+namespace sqw {
+
+constexpr unsigned FULL = 0xffffffffu;
+
+__device__ __forceinline__ void dmma(double& c0, double& c1, double a, double b) {
+    asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+        : "+d"(c0), "+d"(c1)
+        : "d"(a), "d"(b));
+}
+// D += X Y^T on 8 x 8 tiles in C layout
+__device__ __forceinline__ void mma_nt(double2& d, const double2 x, const double2 y) {
+    dmma(d.x, d.y, x.x, y.x);
+    dmma(d.x, d.y, x.y, y.y);
+}
+__device__ __forceinline__ double2 ldt(const double* S, int tile, int lane) {
+    return reinterpret_cast<const double2*>(S)[tile * 32 + lane];
+}
+__device__ __forceinline__ void stt(double* S, int tile, int lane, double2 v) {
+    reinterpret_cast<double2*>(S)[tile * 32 + lane] = v;
+}
+__device__ __forceinline__ double2 neg(double2 v) { return make_double2(-v.x, -v.y); }
+__device__ __forceinline__ double2 zero2() { return make_double2(0.0, 0.0); }
+
+// transpose of a tile in C layout: two shuffles (each lane sends one of its two values per round)
+__device__ __forceinline__ double2 ttrans(double2 v, int lane) {
+    const int g = lane >> 2, t = lane & 3;
+    const bool odd = g & 1;
+    const int s1 = 4 * (2 * t + (odd ? 1 : 0)) + (g >> 1);
+    const int s2 = 4 * (2 * t + (odd ? 0 : 1)) + (g >> 1);
+    const double r1 = __shfl_sync(FULL, odd ? v.y : v.x, s1);
+    const double r2 = __shfl_sync(FULL, odd ? v.x : v.y, s2);
+    return odd ? make_double2(r2, r1) : make_double2(r1, r2);
+}
+// sum over the four lanes of a group (same g)
+__device__ __forceinline__ double red_t(double x) {
+    x += __shfl_xor_sync(FULL, x, 1);
+    x += __shfl_xor_sync(FULL, x, 2);
+    return x;
+}
+// sum over the eight groups (same t)
+__device__ __forceinline__ double red_g(double x) {
+    x += __shfl_xor_sync(FULL, x, 4);
+    x += __shfl_xor_sync(FULL, x, 8);
+    x += __shfl_xor_sync(FULL, x, 16);
+    return x;
+}
+__device__ __forceinline__ double warp_sum_d(double x) { return red_g(red_t(x)); }
+
+// tile (I, J) of a row-major global matrix (leading dimension ld, even) in C layout, and of its transpose
+__device__ __forceinline__ double2 ldg_tile(const double* __restrict__ M, int ld, int I, int J, int lane) {
+    const int g = lane >> 2, t = lane & 3;
+    return *reinterpret_cast<const double2*>(M + (size_t)(8 * I + g) * ld + 8 * J + 2 * t);
+}
+__device__ __forceinline__ double2 ldg_tile_t(const double* __restrict__ M, int ld, int I, int J, int lane) {
+    const int g = lane >> 2, t = lane & 3;  // out[g][2t+e] = M[8J + 2t + e][8I + g]
+    const double* q = M + (size_t)(8 * J + 2 * t) * ld + 8 * I + g;
+    return make_double2(q[0], q[ld]);
+}
+__device__ __forceinline__ void stg_tile(double* __restrict__ M, int ld, int I, int J, int lane, double2 v) {
+    const int g = lane >> 2, t = lane & 3;
+    *reinterpret_cast<double2*>(M + (size_t)(8 * I + g) * ld + 8 * J + 2 * t) = v;
+}
+// address of element (i, j) of a tile matrix with WT tile columns
+__device__ __forceinline__ int elem_addr(int i, int j, int WT) {
+    return ((i >> 3) * WT + (j >> 3)) * 64 + ((i & 7) * 4 + ((j & 7) >> 1)) * 2 + (j & 1);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Householder R factor of an array stored transposed in tiles.  Map::tile(jt, rt) is the tile holding columns
+// 8jt..8jt+7 and rows 8rt..8rt+7 of the array (element [col][row] in C layout).  NP column blocks, NR row blocks.
+// On return the tiles hold R^T (lower triangular in storage order), zeros elsewhere.
+template <int NP, int NR, class Map>
+__device__ __forceinline__ void qr_tiles(double* __restrict__ S, const int lane) {
+    const int g = lane >> 2, t = lane & 3;
+#pragma unroll
+    for (int jt = 0; jt < NP; ++jt) {
+        double2 pa[NR];
+#pragma unroll
+        for (int rt = 0; rt < NR; ++rt)
+            if (rt >= jt) pa[rt] = ldt(S, Map::tile(jt, rt), lane);
+        double2 tt = zero2();  // T^T in C layout: lane (g = j, t) holds T[2t][j], T[2t+1][j]
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            // x = column k of the panel below its diagonal, handed to every group (lane (k, t) -> lanes (*, t))
+            double2 xb[NR];
+#pragma unroll
+            for (int rt = 0; rt < NR; ++rt)
+                if (rt >= jt) {
+                    xb[rt].x = __shfl_sync(FULL, pa[rt].x, 4 * k + t);
+                    xb[rt].y = __shfl_sync(FULL, pa[rt].y, 4 * k + t);
+                }
+            double2 xm = xb[jt];
+            if (2 * t <= k) xm.x = 0.0;
+            if (2 * t + 1 <= k) xm.y = 0.0;
+            double d0 = xm.x * pa[jt].x, d1 = xm.y * pa[jt].y;
+#pragma unroll
+            for (int rt = 0; rt < NR; ++rt)
+                if (rt > jt) {
+                    d0 = fma(xb[rt].x, pa[rt].x, d0);
+                    d1 = fma(xb[rt].y, pa[rt].y, d1);
+                }
+            // one reduction window: group k -> ss = x.x; group c > k -> x.a_c; group i < k -> x.v_i (for T)
+            const double dot = red_t(d0 + d1);
+            const double ss = __shfl_sync(FULL, dot, 4 * k);
+            const double akc = __shfl_sync(FULL, (k & 1) ? pa[jt].y : pa[jt].x, 4 * g + (k >> 1));  // [row k][col g]
+            const double alpha = __shfl_sync(FULL, akc, 4 * k);
+            if (ss == 0.0) continue;  // dlarfg: tau = 0, H = I (column k of T stays zero)
+            const double nrm = sqrt(fma(alpha, alpha, ss));
+            const double beta = alpha >= 0.0 ? -nrm : nrm;
+            const double tau = (beta - alpha) / beta;
+            const double scal = 1.0 / (alpha - beta);
+            const double zz = fma(scal, dot, akc);  // v_k . a_c  (c > k)   or   v_i . v_k  (i < k)
+            const double w = g > k ? tau * zz : 0.0;
+            double2 vd = make_double2(xm.x * scal, xm.y * scal);  // v on my rows (unit at row k)
+            if (2 * t == k) vd.x = 1.0;
+            if (2 * t + 1 == k) vd.y = 1.0;
+            pa[jt].x = fma(-w, vd.x, pa[jt].x);
+            pa[jt].y = fma(-w, vd.y, pa[jt].y);
+            if (g == k) {
+                if (2 * t > k) pa[jt].x = vd.x;
+                else if (2 * t == k) pa[jt].x = beta;
+                if (2 * t + 1 > k) pa[jt].y = vd.y;
+                else if (2 * t + 1 == k) pa[jt].y = beta;
+            }
+#pragma unroll
+            for (int rt = 0; rt < NR; ++rt)
+                if (rt > jt) {
+                    const double vx = xb[rt].x * scal, vy = xb[rt].y * scal;
+                    pa[rt].x = g == k ? vx : fma(-w, vx, pa[rt].x);
+                    pa[rt].y = g == k ? vy : fma(-w, vy, pa[rt].y);
+                }
+            // dlarft, column k:  T[0:k, k] = -tau T[0:k, 0:k] z,  z_i = v_i . v_k ;  T[k][k] = tau
+            const double cz = g < k ? zz : 0.0;
+            const double s0 = red_g(tt.x * cz), s1 = red_g(tt.y * cz);
+            if (g == k) {
+                tt.x = 2 * t < k ? -tau * s0 : (2 * t == k ? tau : 0.0);
+                tt.y = 2 * t + 1 < k ? -tau * s1 : (2 * t + 1 == k ? tau : 0.0);
+            }
+        }
+        // R goes back to the array (zeros below the diagonal); V^T (unit diagonal) stays in registers
+        double2 vt[NR], vv[NR];
+        {
+            const double2 r = pa[jt];
+            stt(S, Map::tile(jt, jt), lane, make_double2(2 * t <= g ? r.x : 0.0, 2 * t + 1 <= g ? r.y : 0.0));
+            vt[jt].x = 2 * t > g ? r.x : (2 * t == g ? 1.0 : 0.0);
+            vt[jt].y = 2 * t + 1 > g ? r.y : (2 * t + 1 == g ? 1.0 : 0.0);
+        }
+#pragma unroll
+        for (int rt = 0; rt < NR; ++rt)
+            if (rt > jt) {
+                vt[rt] = pa[rt];
+                stt(S, Map::tile(jt, rt), lane, zero2());
+            }
+        if (jt + 1 < NP) {
+#pragma unroll
+            for (int rt = 0; rt < NR; ++rt)
+                if (rt >= jt) vv[rt] = ttrans(vt[rt], lane);
+#pragma unroll
+            for (int j2 = 0; j2 < NP; ++j2)
+                if (j2 > jt) {
+                    double2 c[NR];
+                    double2 w0 = zero2(), w1 = zero2();
+#pragma unroll
+                    for (int rt = 0; rt < NR; ++rt)
+                        if (rt >= jt) {
+                            c[rt] = ldt(S, Map::tile(j2, rt), lane);
+                            if ((rt - jt) & 1) mma_nt(w1, c[rt], vt[rt]);
+                            else mma_nt(w0, c[rt], vt[rt]);
+                        }
+                    const double2 wt = make_double2(w0.x + w1.x, w0.y + w1.y);  // (A^T V) block
+                    double2 ut = zero2();
+                    mma_nt(ut, wt, tt);  // (A^T V) T
+                    ut = neg(ut);
+#pragma unroll
+                    for (int rt = 0; rt < NR; ++rt)
+                        if (rt >= jt) {
+                            mma_nt(c[rt], ut, vv[rt]);  // A^T -= (A^T V T) V^T
+                            stt(S, Map::tile(j2, rt), lane, c[rt]);
+                        }
+                }
+        }
+        __syncwarp();
+    }
+}
+
+// Doubles per (series, step) record: identical to sq::traj_record_elems (bkf_sqrt.cu)
+__host__ __device__ inline size_t traj_record_elems(int m, int p) {
+    const size_t N1 = (size_t)p + m;
+    return (size_t)m + (size_t)m * m + N1 * (N1 + 1) / 2 + (size_t)m * (m + 1) / 2;
+}
+
+template <int MT, int PT, int RT>
+struct Dims {
+    static constexpr int mt = MT, pt = PT, rt = RT;
+    static constexpr int m = 8 * MT, p = 8 * PT, r = 8 * RT, N1 = m + p;
+    static constexpr int NT1 = MT + PT;  // tile rows / columns of the shared array
+    static constexpr int WT = NT1;       // tile columns (RT <= PT so that the predict array fits)
+    static_assert(RT <= PT, "predict array [T Pcf, R Qc] must fit in the update array");
+    // update array A^T = [[Hc, Zm Pc], [0, Pc]]: column block jt -> tile row jt, row block rt -> tile column rt
+    struct MapU {
+        __host__ __device__ static constexpr int tile(int jt, int rt) { return jt * WT + rt; }
+    };
+    // predict array M^T = [T Pcf, R Qc]: its R^T (= next Pc) must land on the Pc block -> tile rows PT + jt,
+    // row blocks 0..MT-1 on tile columns PT.., row blocks MT.. (the R Qc part) on tile columns 0..RT-1
+    struct MapP {
+        __host__ __device__ static constexpr int tile(int jt, int rt) {
+            return (PT + jt) * WT + (rt < MT ? PT + rt : rt - MT);
+        }
+    };
+    static constexpr int pc_tile(int I, int J) { return (PT + I) * WT + PT + J; }
+    // forward arena (doubles)
+    static constexpr int SA = 0;
+    static constexpr int RQ = SA + NT1 * WT * 64;   // R Qc, MT x RT tiles
+    static constexpr int HC = RQ + MT * RT * 64;    // Hc, PT x PT tiles
+    static constexpr int VA = HC + PT * PT * 64;    // vectors
+    static constexpr int V_a = VA, V_af = V_a + m, V_c = V_af + m, V_d = V_c + m, V_v = V_d + p, V_sv = V_v + p,
+                         V_in = V_sv + p, V_w = V_in + p, V_ym = V_w + p;
+    static constexpr int FWD_ELEMS = V_ym + p;
+};
+
+// In-place lower Cholesky of a k x k row-major matrix in shared memory by one warp; the upper triangle is zeroed.
+__device__ inline bool chol_lower_warp(double* A, int k, int lane) {
+    bool ok = true;
+    for (int j = 0; j < k; ++j) {
+        double s = A[j * k + j];
+        for (int q = 0; q < j; ++q) s -= A[j * k + q] * A[j * k + q];
+        if (!(s > 0)) { ok = false; s = NAN; }
+        const double ljj = sqrt(s);
+        __syncwarp();
+        for (int i = j + 1 + lane; i < k; i += 32) {
+            double tv = A[i * k + j];
+            for (int q = 0; q < j; ++q) tv -= A[i * k + q] * A[j * k + q];
+            A[i * k + j] = tv / ljj;
+        }
+        if (lane == 0) A[j * k + j] = ljj;
+        for (int i = lane; i < j; i += 32) A[i * k + j] = 0.0;
+        __syncwarp();
+    }
+    return ok;
+}
+
+// Per-series constants: Hc = chol(H) (or H when all zero, :666) and R Qc as tiles.  scratch: >= p*p + r*r + m*r doubles.
+template <class D>
+__device__ inline int setup_consts(const KArgs<double>& G, int b, double* HCt, double* RQt, double* Qc_rowmajor,
+                                   double* scratch, bool* Hzero_out, int lane) {
+    constexpr int m = D::m, p = D::p, r = D::r;
+    const double* Hg = param_ptr(G.H, G.shared_mask, BKF_PARAM_H, b, (size_t)p * p);
+    const double* Qg = param_ptr(G.Q, G.shared_mask, BKF_PARAM_Q, b, (size_t)r * r);
+    const double* Rg = param_ptr(G.Rm, G.shared_mask, BKF_PARAM_R, b, (size_t)m * r);
+    double* Hc = scratch;
+    double* Qc = Qc_rowmajor ? Qc_rowmajor : scratch + p * p;
+    bool nz = false;
+    for (int i = lane; i < p * p; i += 32) {
+        const double h = Hg[i];
+        Hc[i] = h;
+        nz = nz || !(h == 0.0);
+    }
+    for (int i = lane; i < r * r; i += 32) Qc[i] = Qg[i];
+    const bool Hzero = !__any_sync(FULL, nz);
+    __syncwarp();
+    int st = 0;
+    if (!Hzero && !chol_lower_warp(Hc, p, lane)) st |= BKF_STATUS_NOT_PD;
+    if (!chol_lower_warp(Qc, r, lane)) st |= BKF_STATUS_NOT_PD;
+    for (int idx = lane; idx < p * p; idx += 32) HCt[elem_addr(idx / p, idx % p, D::pt)] = Hc[idx];
+    for (int idx = lane; idx < m * r; idx += 32) {
+        const int i = idx / r, k = idx - i * r;
+        double acc = 0;
+        for (int l = k; l < r; ++l) acc = fma(Rg[i * r + l], Qc[l * r + k], acc);  // Qc lower: l >= k
+        RQt[elem_addr(i, k, D::rt)] = acc;
+    }
+    __syncwarp();
+    *Hzero_out = Hzero;
+    return st;
+}
+
+// Packed upper triangle (row i holds n - i entries) <- R, where the tiles hold R^T: tile (I, J), I >= J, element
+// [g][2t+e] = R[8J + 2t + e][8I + g].
+template <int NT, class TileOf>
+__device__ __forceinline__ void store_packed_upper(double* __restrict__ dst, const double* __restrict__ S, int lane,
+                                                   TileOf tile_of) {
+    const int g = lane >> 2, t = lane & 3;
+    constexpr int n = 8 * NT;
+#pragma unroll
+    for (int I = 0; I < NT; ++I)
+#pragma unroll
+        for (int J = 0; J <= I; ++J) {
+            const double2 v = ldt(S, tile_of(I, J), lane);
+            const int j = 8 * I + g;
+            int i = 8 * J + 2 * t;
+            if (j >= i) dst[i * n - (i * (i - 1)) / 2 + (j - i)] = v.x;
+            ++i;
+            if (j >= i) dst[i * n - (i * (i - 1)) / 2 + (j - i)] = v.y;
+        }
+}
+
+template <int MT, int PT, int RT>
+__global__ void __launch_bounds__(32) forward_kernel(KArgs<double> G) {
+    using D = Dims<MT, PT, RT>;
+    constexpr int m = D::m, p = D::p, N1 = D::N1, WT = D::WT;
+    extern __shared__ double smem[];
+    const int lane = threadIdx.x, g = lane >> 2, t = lane & 3;
+    const int b = blockIdx.x;
+    const int n = G.n;
+    double* SA = smem + D::SA;
+    double* RQ = smem + D::RQ;
+    double* HC = smem + D::HC;
+    double *va = smem + D::V_a, *vaf = smem + D::V_af, *vc = smem + D::V_c, *vd = smem + D::V_d, *vv = smem + D::V_v,
+           *vsv = smem + D::V_sv, *vin = smem + D::V_in, *vw = smem + D::V_w, *vym = smem + D::V_ym;
+
+    bool Hzero;
+    int st = setup_consts<D>(G, b, HC, RQ, nullptr, SA, &Hzero, lane);
+    const double* Tg = param_ptr(G.T, G.shared_mask, BKF_PARAM_T, b, (size_t)m * m);
+    const double* Zg = param_ptr(G.Z, G.shared_mask, BKF_PARAM_Z, b, (size_t)p * m);
+    {
+        const double* a0 = param_ptr(G.a0, G.shared_mask, BKF_PARAM_A0, b, (size_t)m);
+        const double* P0 = param_ptr(G.P0, G.shared_mask, BKF_PARAM_P0, b, (size_t)m * m);
+        const double* cg = param_ptr(G.c, G.shared_mask, BKF_PARAM_C, b, (size_t)m);
+        const double* dg = param_ptr(G.d, G.shared_mask, BKF_PARAM_D, b, (size_t)p);
+        for (int i = lane; i < m; i += 32) { va[i] = a0[i]; vc[i] = cg[i]; }
+        for (int i = lane; i < p; i += 32) vd[i] = dg[i];
+        __syncwarp();  // the Cholesky scratch in SA is dead from here on
+#pragma unroll
+        for (int I = 0; I < MT; ++I)
+#pragma unroll
+            for (int J = 0; J < MT; ++J) stt(SA, D::pc_tile(I, J), lane, ldg_tile(P0, m, I, J, lane));
+        __syncwarp();
+    }
+    const double* yb = G.y_shared ? G.y : G.y + (size_t)b * n * p;
+    const size_t tstride = traj_record_elems(m, p);
+    const size_t off_rf = (size_t)m + (size_t)m * m, off_rp = off_rf + (size_t)N1 * (N1 + 1) / 2;
+    double logp = 0.0;
+    for (int ts = 0; ts < n; ++ts) {
+        const size_t bt = (size_t)b * n + ts;
+        double* rec = G.traj ? G.traj + bt * tstride : nullptr;
+        // ---- mask, innovation ----
+        bool miss = true;
+        if (lane < p) {
+            const double yv = yb[(size_t)ts * p + lane];
+            miss = is_missing(yv, G.fill, true);
+            vw[lane] = miss ? 0.0 : 1.0;
+            vym[lane] = miss ? 0.0 : yv;
+        }
+        const int nobs = __popc(__ballot_sync(FULL, !miss));
+        const bool flag = nobs == 0, partial = !flag && nobs != p;
+        __syncwarp();
+        if (rec) {
+            for (int i = lane; i < m; i += 32) rec[i] = va[i];
+#pragma unroll
+            for (int I = 0; I < MT; ++I)
+#pragma unroll
+                for (int J = 0; J < MT; ++J) stg_tile(rec + m, m, I, J, lane, ldt(SA, D::pc_tile(I, J), lane));
+        }
+        double2 zf[PT][MT];
+#pragma unroll
+        for (int I = 0; I < PT; ++I) {
+            const double wI = vw[8 * I + g];
+            double acc = 0.0;
+#pragma unroll
+            for (int J = 0; J < MT; ++J) {
+                double2 z = ldg_tile(Zg, m, I, J, lane);
+                z.x *= wI;
+                z.y *= wI;
+                zf[I][J] = z;
+                acc = fma(z.x, va[8 * J + 2 * t], acc);
+                acc = fma(z.y, va[8 * J + 2 * t + 1], acc);
+            }
+            acc = red_t(acc) + vd[8 * I + g];
+            if (t == 0) {
+                vsv[8 * I + g] = acc;                  // y_hat
+                vv[8 * I + g] = vym[8 * I + g] - acc;  // v
+            }
+        }
+        __syncwarp();
+        double ll = 0.0;
+        if (!flag) {
+            // ---- update array (transposed): [[Hc, Zm Pc], [0, Pc]] ----
+#pragma unroll
+            for (int I = 0; I < PT; ++I)
+#pragma unroll
+                for (int J = 0; J < PT; ++J) {
+                    double2 h = ldt(HC, I * PT + J, lane);
+                    if (Hzero) h = zero2();
+                    else if (partial) h = make_double2(NAN, NAN);  // the reference's cholesky(W H) fails here
+                    stt(SA, I * WT + J, lane, h);
+                }
+#pragma unroll
+            for (int J = 0; J < MT; ++J) {
+                double2 acc[PT];
+#pragma unroll
+                for (int I = 0; I < PT; ++I) acc[I] = zero2();
+#pragma unroll
+                for (int K = 0; K < MT; ++K) {
+                    const double2 pt = ttrans(ldt(SA, D::pc_tile(K, J), lane), lane);  // (Pc[K][J])^T
+#pragma unroll
+                    for (int I = 0; I < PT; ++I) mma_nt(acc[I], zf[I][K], pt);
+                }
+#pragma unroll
+                for (int I = 0; I < PT; ++I) stt(SA, I * WT + PT + J, lane, acc[I]);
+            }
+#pragma unroll
+            for (int I = 0; I < MT; ++I)
+#pragma unroll
+                for (int J = 0; J < PT; ++J) stt(SA, (PT + I) * WT + J, lane, zero2());
+            __syncwarp();
+            qr_tiles<D::NT1, D::NT1, typename D::MapU>(SA, lane);
+            if (rec)
+                store_packed_upper<D::NT1>(rec + off_rf, SA, lane, [](int I, int J) { return I * WT + J; });
+            // ---- s = Fc^{-1} v, inner = Fc^{-1} s  (Fc = B[:p,:p], lower), lane q owns x[q] ----
+            {
+                const int q = lane < p ? lane : p - 1;
+                double frow[p];
+#pragma unroll
+                for (int i = 0; i < p; ++i) frow[i] = SA[elem_addr(q, i, WT)];
+                const double dq = SA[elem_addr(q, q, WT)];
+                const double rdiag = 1.0 / dq;
+                double x = lane < p ? vv[lane] : 0.0;
+#pragma unroll
+                for (int rep = 0; rep < 2; ++rep) {
+#pragma unroll
+                    for (int i = 0; i < p; ++i) {
+                        const double xi = __shfl_sync(FULL, x, i) * __shfl_sync(FULL, rdiag, i);
+                        if (lane == i) x = xi;
+                        else if (lane > i) x = fma(-frow[i], xi, x);
+                    }
+                    if (lane < p) (rep == 0 ? vsv : vin)[lane] = x;
+                }
+                const double quad = warp_sum_d(lane < p ? vv[lane] * x : 0.0);
+                const double logdet = warp_sum_d(lane < p ? log(fabs(dq)) : 0.0);
+                ll = -0.5 * ((double)p * (kLog2Pi + 2.0 * logdet) + quad);  // :696 (quirk Q2)
+            }
+            __syncwarp();
+            // ---- a_f = a + KF s ;  jitter on the factor (Q4) ----
+#pragma unroll
+            for (int I = 0; I < MT; ++I) {
+                double acc = 0.0;
+#pragma unroll
+                for (int J = 0; J < PT; ++J) {
+                    const double2 kf = ldt(SA, (PT + I) * WT + J, lane);
+                    acc = fma(kf.x, vsv[8 * J + 2 * t], acc);
+                    acc = fma(kf.y, vsv[8 * J + 2 * t + 1], acc);
+                }
+                acc = red_t(acc);
+                if (t == 0) vaf[8 * I + g] = va[8 * I + g] + acc;
+            }
+        } else {
+            for (int i = lane; i < m; i += 32) vaf[i] = va[i];
+        }
+        if ((g >> 1) == t) {  // lanes holding a diagonal element: [g][2t+e] with 2t+e == g
+#pragma unroll
+            for (int I = 0; I < MT; ++I) SA[D::pc_tile(I, I) * 64 + lane * 2 + (g & 1)] += G.jitter;
+        }
+        __syncwarp();
+        if (G.ll && lane == 0) G.ll[bt] = ll;
+        logp += ll;
+        // ---- predict array (transposed) [T Pcf, R Qc]; a+ = T a_f + c ----
+        {
+            double2 tp[MT][MT];
+            double an[MT];
+#pragma unroll
+            for (int I = 0; I < MT; ++I) {
+                an[I] = 0.0;
+#pragma unroll
+                for (int J = 0; J < MT; ++J) tp[I][J] = zero2();
+            }
+#pragma unroll
+            for (int K = 0; K < MT; ++K) {
+                double2 pt[MT];
+#pragma unroll
+                for (int J = 0; J < MT; ++J) pt[J] = ttrans(ldt(SA, D::pc_tile(K, J), lane), lane);
+#pragma unroll
+                for (int I = 0; I < MT; ++I) {
+                    const double2 tf = ldg_tile(Tg, m, I, K, lane);
+                    an[I] = fma(tf.x, vaf[8 * K + 2 * t], an[I]);
+                    an[I] = fma(tf.y, vaf[8 * K + 2 * t + 1], an[I]);
+#pragma unroll
+                    for (int J = 0; J < MT; ++J) mma_nt(tp[I][J], tf, pt[J]);
+                }
+            }
+            __syncwarp();
+#pragma unroll
+            for (int I = 0; I < MT; ++I) {
+                const double s = red_t(an[I]) + vc[8 * I + g];
+                if (t == 0) va[8 * I + g] = s;
+#pragma unroll
+                for (int J = 0; J < MT; ++J) stt(SA, D::pc_tile(I, J), lane, tp[I][J]);
+#pragma unroll
+                for (int J = 0; J < RT; ++J) stt(SA, (PT + I) * WT + J, lane, ldt(RQ, I * RT + J, lane));
+            }
+            __syncwarp();
+        }
+        qr_tiles<MT, MT + RT, typename D::MapP>(SA, lane);
+        if (rec) store_packed_upper<MT>(rec + off_rp, SA, lane, [](int I, int J) { return D::pc_tile(I, J); });
+    }
+    if (lane == 0) {
+        if (!isfinite(logp)) st |= BKF_STATUS_NONFINITE;
+        if (G.logp) G.logp[b] = logp;
+        if (G.status) G.status[b] = st;
+    }
+}
+
+}  // namespace sqw
+}  // namespace bkf
