@@ -490,10 +490,17 @@ static size_t traj_record_elems(const bkf_problem* P) {
     return frag ? tc::traj_record_elems() : (size_t)P->m + (size_t)P->m * P->m;
 }
 
+// Elements of the whole trajectory workspace.  The square-root family appends one record per series: scratch for the
+// adjoint's add-only accumulators (bkf_sqrt_warp.cuh).
+static size_t traj_elems(const bkf_problem* P) {
+    const size_t B = P->B, n = P->n;
+    return B * (n + (P->kind == BKF_CHOLESKY ? 1 : 0)) * traj_record_elems(P);
+}
+
 extern "C" int bkf_logp_grad_workspace_bytes(const bkf_problem* P, size_t* bytes) {
     if (!P || !bytes) return BKF_ERR_ARG;
     const size_t es = P->dtype == BKF_F64 ? 8 : 4, B = P->B, n = P->n;
-    size_t tot = B * n * traj_record_elems(P) * es;
+    size_t tot = traj_elems(P) * es;
     if (P->mem == BKF_MEM_HOST) {
         tot += (P->y_shared ? 1 : B) * n * (size_t)P->p * es + B * n * es /* cotangent */ + B * (es + sizeof(int));
         for (int i = 0; i < BKF_NPARAM; ++i)
@@ -530,8 +537,7 @@ static int logp_grad_impl(bkf_handle* h, const bkf_problem* P, const void* y, co
     for (int i = 0; i < BKF_NPARAM; ++i)
         *gdst[i] = stage_out<R>(h, P, S_GA0 + i, grads[i], B * param_elems(P, i), &rc);
     if (want_grad) {
-        const size_t rec = traj_record_elems(P);
-        g.traj = (R*)ensure(h, S_TRAJ, B * n * rec * sizeof(R), &rc);
+        g.traj = (R*)ensure(h, S_TRAJ, traj_elems(P) * sizeof(R), &rc);
     }
     int* dstatus = nullptr;
     if (status) dstatus = P->mem == BKF_MEM_DEVICE ? status : (int*)ensure(h, S_STATUS, B * sizeof(int), &rc);
@@ -669,7 +675,7 @@ static int compact_impl(bkf_handle* h, const bkf_problem* P, const void* y, cons
     if (status) dstatus = host ? (int*)ensure(h, S_STATUS, B * sizeof(int), &rc) : status;
     g.status = dstatus;
     const bool want_grad = g_u != nullptr && nnz > 0;
-    if (want_grad) g.traj = (R*)ensure(h, S_TRAJ, B * n * traj_record_elems(&Pd) * sizeof(R), &rc);
+    if (want_grad) g.traj = (R*)ensure(h, S_TRAJ, traj_elems(&Pd) * sizeof(R), &rc);
     if (rc != BKF_OK) return rc;
     if (B == 0) return BKF_OK;
     const unsigned sgrid = (unsigned)std::min<size_t>((B * (size_t)(nnz > 0 ? nnz : 1) + 255) / 256, 4096);

@@ -23,7 +23,7 @@ static bool shape_ok(int m, int p, int r) {
 bool supported(const KArgs<double>& g, bool backward) {
     if (g.kind != BKF_CHOLESKY || g.tv_mask || !shape_ok(g.m, g.p, g.r)) return false;
     if (!((enabled_mask() >> (backward ? 1 : 0)) & 1)) return false;
-    if (backward) return false;  // adjoint: not yet
+    if (backward) return g.traj != nullptr;
     // the forward sweep of this family only produces the log-likelihood and the adjoint's record
     return !(g.filt_a || g.pred_a || g.obs_mu || g.filt_P || g.pred_P || g.obs_cov);
 }
@@ -31,8 +31,9 @@ bool supported(const KArgs<double>& g, bool backward) {
 template <int MT, int PT, int RT>
 static int launch_t(const KArgs<double>& g, bool backward, cudaStream_t stream, const char** err) {
     using D = Dims<MT, PT, RT>;
-    const size_t bytes = (size_t)D::FWD_ELEMS * sizeof(double);
-    auto kern = forward_kernel<MT, PT, RT>;
+    using BD = BDims<MT, PT, RT>;
+    const size_t bytes = (size_t)(backward ? BD::ELEMS : D::FWD_ELEMS) * sizeof(double);
+    auto kern = backward ? backward_kernel<MT, PT, RT> : forward_kernel<MT, PT, RT>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
     if (e != cudaSuccess) { *err = cudaGetErrorString(e); return BKF_ERR_CUDA; }
     kern<<<g.B, 32, bytes, stream>>>(g);

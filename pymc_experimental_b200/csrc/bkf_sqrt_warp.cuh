@@ -80,6 +80,13 @@ __device__ __forceinline__ double2 ldg_tile_t(const double* __restrict__ M, int 
     const double* q = M + (size_t)(8 * J + 2 * t) * ld + 8 * I + g;
     return make_double2(q[0], q[ld]);
 }
+// the same for a buffer this kernel also writes (no read-only-cache path)
+__device__ __forceinline__ double2 ldrw_tile(double* M, int ld, int I, int J, int lane) {
+    const int g = lane >> 2, t = lane & 3;
+    double2 v;
+    asm volatile("ld.global.v2.f64 {%0,%1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(M + (size_t)(8 * I + g) * ld + 8 * J + 2 * t));
+    return v;
+}
 __device__ __forceinline__ void stg_tile(double* __restrict__ M, int ld, int I, int J, int lane, double2 v) {
     const int g = lane >> 2, t = lane & 3;
     *reinterpret_cast<double2*>(M + (size_t)(8 * I + g) * ld + 8 * J + 2 * t) = v;
@@ -286,12 +293,13 @@ __device__ inline int setup_consts(const KArgs<double>& G, int b, double* HCt, d
     if (!Hzero && !chol_lower_warp(Hc, p, lane)) st |= BKF_STATUS_NOT_PD;
     if (!chol_lower_warp(Qc, r, lane)) st |= BKF_STATUS_NOT_PD;
     for (int idx = lane; idx < p * p; idx += 32) HCt[elem_addr(idx / p, idx % p, D::pt)] = Hc[idx];
-    for (int idx = lane; idx < m * r; idx += 32) {
-        const int i = idx / r, k = idx - i * r;
-        double acc = 0;
-        for (int l = k; l < r; ++l) acc = fma(Rg[i * r + l], Qc[l * r + k], acc);  // Qc lower: l >= k
-        RQt[elem_addr(i, k, D::rt)] = acc;
-    }
+    if (RQt)
+        for (int idx = lane; idx < m * r; idx += 32) {
+            const int i = idx / r, k = idx - i * r;
+            double acc = 0;
+            for (int l = k; l < r; ++l) acc = fma(Rg[i * r + l], Qc[l * r + k], acc);  // Qc lower: l >= k
+            RQt[elem_addr(i, k, D::rt)] = acc;
+        }
     __syncwarp();
     *Hzero_out = Hzero;
     return st;
@@ -519,6 +527,706 @@ __global__ void __launch_bounds__(32) forward_kernel(KArgs<double> G) {
         if (!isfinite(logp)) st |= BKF_STATUS_NONFINITE;
         if (G.logp) G.logp[b] = logp;
         if (G.status) G.status[b] = st;
+    }
+}
+
+// ===============================================================================================================
+// Adjoint sweep.
+//
+// For A = Q R and an upper-triangular cotangent Rbar:  Abar = A Psi,  Psi = R^{-1} copyltu(R Rbar^T) R^{-T}  (symmetric).
+// On tiles:   S0 = R Rbar^T = mma_nt(R, Rbar)  (lower tiles only), S = copyltu(S0),
+//             G = S R^{-T}   (right-solve by tile columns, diagonal tiles inverted once),
+//             Psi = G^T R^{-T}  (same right-solve after an in-place transposition).
+// The R factors come from the forward record (no QR here).  Cotangents of the factor are carried TRANSPOSED
+// (PBT = Pbar^T) because that is what both the pull-back (Rbar_p = triu(Pbar^T)) and the products below produce.
+
+template <int NT>
+__host__ __device__ constexpr int tri(int I, int K) { return I * NT - (I * (I - 1)) / 2 + (K - I); }  // I <= K
+
+// tiles of the upper triangle of an n x n factor (n = 8 NT) from its packed rows (row i holds n - i entries)
+template <int NT>
+__device__ __forceinline__ void load_packed_upper(double* __restrict__ RF, const double* __restrict__ src, int lane) {
+    const int g = lane >> 2, t = lane & 3;
+    constexpr int n = 8 * NT;
+#pragma unroll
+    for (int I = 0; I < NT; ++I)
+#pragma unroll
+        for (int K = I; K < NT; ++K) {
+            const int i = 8 * I + g, j = 8 * K + 2 * t;
+            const double* q = src + (i * n - (i * (i - 1)) / 2 - i + j);
+            double2 v;
+            v.x = j >= i ? q[0] : 0.0;
+            v.y = j + 1 >= i ? q[1] : 0.0;
+            stt(RF, tri<NT>(I, K), lane, v);
+        }
+}
+
+// Psi (NT x NT tiles, row stride NT, in W) from the factor tiles RF (upper, tri<NT> order) and a provider of the
+// cotangent tiles rbar(J, K), K >= J, with exact zeros below the diagonal.  RINV: NT tiles of scratch.
+template <int NT, class RbF>
+__device__ __forceinline__ void psi_tiles(double* __restrict__ W, const double* __restrict__ RF, double* __restrict__ RINV,
+                                          RbF rbar, const int lane) {
+    const int g = lane >> 2, t = lane & 3;
+    // S = copyltu(R Rbar^T)
+#pragma unroll
+    for (int I = 0; I < NT; ++I) {
+        double2 acc[NT];
+#pragma unroll
+        for (int J = 0; J < NT; ++J) acc[J] = zero2();
+#pragma unroll
+        for (int K = I; K < NT; ++K) {
+            const double2 rk = ldt(RF, tri<NT>(I, K), lane);
+#pragma unroll
+            for (int J = 0; J <= I; ++J) mma_nt(acc[J], rk, rbar(J, K));
+        }
+#pragma unroll
+        for (int J = 0; J < I; ++J) {
+            stt(W, I * NT + J, lane, acc[J]);
+            stt(W, J * NT + I, lane, ttrans(acc[J], lane));
+        }
+        const double2 dt = ttrans(acc[I], lane);
+        stt(W, I * NT + I, lane, make_double2(g >= 2 * t ? acc[I].x : dt.x, g >= 2 * t + 1 ? acc[I].y : dt.y));
+    }
+    __syncwarp();
+    // inverses of the diagonal tiles: lane 8q + c solves column c of tile q (four tiles per round)
+#pragma unroll
+    for (int base = 0; base < NT; base += 4) {
+        const int I = base + (lane >> 3), c = lane & 7;
+        if (I < NT) {
+            const double* Dg = RF + (I * NT - (I * (I - 1)) / 2) * 64;
+            double x[8];
+#pragma unroll
+            for (int i = 7; i >= 0; --i) {
+                double tv = i == c ? 1.0 : 0.0;
+#pragma unroll
+                for (int q = 7; q > i; --q) tv = fma(-Dg[i * 8 + q], x[q], tv);
+                x[i] = tv / Dg[i * 8 + i];
+            }
+#pragma unroll
+            for (int i = 0; i < 8; ++i) RINV[I * 64 + i * 8 + c] = x[i];
+        }
+    }
+    __syncwarp();
+#pragma unroll
+    for (int pass = 0; pass < 2; ++pass) {
+        // X <- X R^{-T}, tile column by tile column (all tile rows at once)
+#pragma unroll
+        for (int I = NT - 1; I >= 0; --I) {
+            double2 acc[NT];
+#pragma unroll
+            for (int J = 0; J < NT; ++J) acc[J] = ldt(W, J * NT + I, lane);
+#pragma unroll
+            for (int K = I + 1; K < NT; ++K) {
+                const double2 rk = neg(ldt(RF, tri<NT>(I, K), lane));
+#pragma unroll
+                for (int J = 0; J < NT; ++J) mma_nt(acc[J], ldt(W, J * NT + K, lane), rk);
+            }
+            const double2 ri = ldt(RINV, I, lane);
+#pragma unroll
+            for (int J = 0; J < NT; ++J) {
+                double2 o = zero2();
+                mma_nt(o, acc[J], ri);
+                stt(W, J * NT + I, lane, o);
+            }
+            __syncwarp();
+        }
+        if (pass == 0) {
+#pragma unroll
+            for (int I = 0; I < NT; ++I) {
+#pragma unroll
+                for (int J = 0; J < I; ++J) {
+                    const double2 lo = ldt(W, I * NT + J, lane), up = ldt(W, J * NT + I, lane);
+                    stt(W, I * NT + J, lane, ttrans(up, lane));
+                    stt(W, J * NT + I, lane, ttrans(lo, lane));
+                }
+                stt(W, I * NT + I, lane, ttrans(ldt(W, I * NT + I, lane), lane));
+            }
+            __syncwarp();
+        }
+    }
+}
+
+// C[M,N] (row-major, ldc) (op)= A B with strided operands, one warp (epilogue only)
+template <bool ADD>
+__device__ inline void wmm(double* C, int ldc, const double* A, int as0, int as1, const double* Bm, int bs0, int bs1,
+                           int M, int N, int K, int lane) {
+    for (int idx = lane; idx < M * N; idx += 32) {
+        const int i = idx / N, j = idx - i * N;
+        double acc = 0;
+        for (int k = 0; k < K; ++k) acc = fma(A[i * as0 + k * as1], Bm[k * bs0 + j * bs1], acc);
+        C[i * ldc + j] = ADD ? C[i * ldc + j] + acc : acc;
+    }
+    __syncwarp();
+}
+
+// Pull a lower-triangular factor cotangent Lbar back through S = L L^T (PyTensor lower convention, as
+// sq::chol_pullback):  Sbar = tril(2 X) - diag(X),  X = 0.5 L^{-T} (P + P^T) L^{-1},  P = Phi(L^T Lbar).  tmp: 2 k k.
+__device__ inline void chol_pullback_warp(double* out, const double* L, const double* Lbar, int k, double* tmp, int lane) {
+    double* P = tmp;
+    double* X = tmp + k * k;
+    for (int idx = lane; idx < k * k; idx += 32) {
+        const int i = idx / k, j = idx - i * k;
+        double acc = 0;
+        for (int q = (i > j ? i : j); q < k; ++q) acc = fma(L[q * k + i], Lbar[q * k + j], acc);
+        P[idx] = (i > j) ? acc : (i == j ? 0.5 * acc : 0.0);
+    }
+    __syncwarp();
+    for (int idx = lane; idx < k * k; idx += 32) X[idx] = P[idx] + P[(idx % k) * k + idx / k];
+    __syncwarp();
+    for (int c = lane; c < k; c += 32)  // X <- L^{-T} X, column c
+        for (int i = k - 1; i >= 0; --i) {
+            double tv = X[i * k + c];
+            for (int q = i + 1; q < k; ++q) tv -= L[q * k + i] * X[q * k + c];
+            X[i * k + c] = tv / L[i * k + i];
+        }
+    __syncwarp();
+    for (int rw = lane; rw < k; rw += 32)  // X <- X L^{-1}, row rw
+        for (int j = k - 1; j >= 0; --j) {
+            double tv = X[rw * k + j];
+            for (int q = j + 1; q < k; ++q) tv -= X[rw * k + q] * L[q * k + j];
+            X[rw * k + j] = tv / L[j * k + j];
+        }
+    __syncwarp();
+    for (int idx = lane; idx < k * k; idx += 32) {
+        const int i = idx / k, j = idx - i * k;
+        const double sv = 0.5 * X[idx];
+        out[idx] = (i > j) ? 2.0 * sv : (i == j ? sv : 0.0);
+    }
+    __syncwarp();
+}
+
+template <int MT, int PT, int RT>
+struct BDims {
+    using D = Dims<MT, PT, RT>;
+    static constexpr int m = D::m, p = D::p, NT1 = D::NT1;
+    static constexpr int NTRI = NT1 * (NT1 + 1) / 2;
+    static constexpr int W = 0;                           // NT1 x NT1 tiles: Psi work array
+    static constexpr int RF = W + NT1 * NT1 * 64;         // factor tiles (upper)
+    static constexpr int RB = RF + NTRI * 64;             // cotangent tiles (upper); also RINV / scratch
+    static constexpr int PBT = RB + NTRI * 64;            // carried Pbar^T, MT x MT tiles
+    static constexpr int HC = PBT + MT * MT * 64;         // Hc tiles
+    static constexpr int HBT = HC + PT * PT * 64;         // sum of Abar11 (= Hcbar^T)
+    static constexpr int VA = HBT + PT * PT * 64;
+    static constexpr int V_a = VA, V_af = V_a + m, V_ab = V_af + m, V_afb = V_ab + m, V_gc = V_afb + m, V_v = V_gc + m,
+                         V_s = V_v + p, V_in = V_s + p, V_w = V_in + p, V_ym = V_w + p, V_vb = V_ym + p, V_sb = V_vb + p,
+                         V_t1 = V_sb + p, V_t2 = V_t1 + p, V_gd = V_t2 + p, V_d = V_gd + p;
+    static constexpr int ELEMS = V_d + p;
+    static_assert(MT * MT <= NTRI && MT * PT <= NTRI, "scratch tiles must fit the factor arrays");
+    static_assert(2 * MT * MT <= NT1 * NT1, "predict adjoint scratch must fit the Psi work array");
+};
+
+template <int MT, int PT, int RT>
+__global__ void __launch_bounds__(32) backward_kernel(KArgs<double> G) {
+    using D = Dims<MT, PT, RT>;
+    using BD = BDims<MT, PT, RT>;
+    constexpr int m = D::m, p = D::p, r = D::r, N1 = D::N1, NT1 = D::NT1;
+    extern __shared__ double smem[];
+    const int lane = threadIdx.x, g = lane >> 2, t = lane & 3;
+    const int b = blockIdx.x;
+    const int n = G.n;
+    double *W = smem + BD::W, *RF = smem + BD::RF, *RB = smem + BD::RB, *PBT = smem + BD::PBT, *HC = smem + BD::HC,
+           *HBT = smem + BD::HBT;
+    double *va = smem + BD::V_a, *vaf = smem + BD::V_af, *vab = smem + BD::V_ab, *vafb = smem + BD::V_afb,
+           *vgc = smem + BD::V_gc, *vv = smem + BD::V_v, *vs = smem + BD::V_s, *vin = smem + BD::V_in, *vw = smem + BD::V_w,
+           *vym = smem + BD::V_ym, *vvb = smem + BD::V_vb, *vsb = smem + BD::V_sb, *vt1 = smem + BD::V_t1,
+           *vt2 = smem + BD::V_t2, *vgd = smem + BD::V_gd, *vd = smem + BD::V_d;
+
+    bool Hzero;
+    setup_consts<D>(G, b, HC, nullptr, nullptr, W, &Hzero, lane);
+    const double* Tg = param_ptr(G.T, G.shared_mask, BKF_PARAM_T, b, (size_t)m * m);
+    const double* Zg = param_ptr(G.Z, G.shared_mask, BKF_PARAM_Z, b, (size_t)p * m);
+    {
+        const double* dg = param_ptr(G.d, G.shared_mask, BKF_PARAM_D, b, (size_t)p);
+        for (int i = lane; i < p; i += 32) { vd[i] = dg[i]; vgd[i] = 0.0; }
+        for (int i = lane; i < m; i += 32) { vab[i] = 0.0; vgc[i] = 0.0; }
+        for (int i = lane; i < MT * MT * 32; i += 32) reinterpret_cast<double2*>(PBT)[i] = zero2();
+        for (int i = lane; i < PT * PT * 32; i += 32) reinterpret_cast<double2*>(HBT)[i] = zero2();
+    }
+    const double* yb = G.y_shared ? G.y : G.y + (size_t)b * n * p;
+    const size_t tstride = traj_record_elems(m, p);
+    const size_t off_rf = (size_t)m + (size_t)m * m, off_rp = off_rf + (size_t)N1 * (N1 + 1) / 2;
+    // accumulators that are only added to live in global memory (L2): the gradient buffers themselves when requested,
+    // else the scratch record behind the trajectory
+    double* scr = G.traj + (size_t)G.B * n * tstride + (size_t)b * tstride;
+    double* gT = G.g_T ? G.g_T + (size_t)b * m * m : scr;
+    double* gZ = G.g_Z ? G.g_Z + (size_t)b * p * m : scr + m * m;
+    double* PS = scr + m * m + p * m;
+    const bool want_ps = G.g_R || G.g_Q;
+    for (int i = lane; i < m * m; i += 32) { gT[i] = 0.0; PS[i] = 0.0; }
+    for (int i = lane; i < p * m; i += 32) gZ[i] = 0.0;
+    __syncwarp();
+
+    for (int ts = n - 1; ts >= 0; --ts) {
+        const size_t bt = (size_t)b * n + ts;
+        const double* rec = G.traj + bt * tstride;
+        const double* Pcg = rec + m;
+        const double gcot = G.ll_cot ? G.ll_cot[bt] : 1.0;
+        const bool dense_pc = ts == 0;  // P0 is whatever the caller passed; later factors are lower triangular
+        // ---- mask, innovation (as the forward sweep) ----
+        bool miss = true;
+        if (lane < p) {
+            const double yv = yb[(size_t)ts * p + lane];
+            miss = is_missing(yv, G.fill, true);
+            vw[lane] = miss ? 0.0 : 1.0;
+            vym[lane] = miss ? 0.0 : yv;
+        }
+        const int nobs = __popc(__ballot_sync(FULL, !miss));
+        const bool flag = nobs == 0, partial = !flag && nobs != p;
+        for (int i = lane; i < m; i += 32) va[i] = rec[i];
+        load_packed_upper<MT>(RF, rec + off_rp, lane);
+        __syncwarp();
+#pragma unroll
+        for (int I = 0; I < PT; ++I) {
+            const double wI = vw[8 * I + g];
+            double acc = 0.0;
+#pragma unroll
+            for (int J = 0; J < MT; ++J) {
+                const double2 z = ldg_tile(Zg, m, I, J, lane);
+                acc = fma(z.x * wI, va[8 * J + 2 * t], acc);
+                acc = fma(z.y * wI, va[8 * J + 2 * t + 1], acc);
+            }
+            acc = red_t(acc) + vd[8 * I + g];
+            if (t == 0) vv[8 * I + g] = vym[8 * I + g] - acc;
+        }
+        // ================= predict adjoint =================
+        psi_tiles<MT>(W, RF, RB, [&](int J, int K) {
+            double2 v = ldt(PBT, J * MT + K, lane);
+            if (J == K) {
+                if (2 * t < g) v.x = 0.0;
+                if (2 * t + 1 < g) v.y = 0.0;
+            }
+            return v;
+        }, lane);
+        if (want_ps) {
+#pragma unroll
+            for (int I = 0; I < MT; ++I)
+#pragma unroll
+                for (int J = 0; J < MT; ++J) {
+                    double2 a = ldrw_tile(PS, m, I, J, lane);
+                    const double2 ps = ldt(W, I * MT + J, lane);
+                    a.x += ps.x;
+                    a.y += ps.y;
+                    stg_tile(PS, m, I, J, lane, a);
+                }
+        }
+        // ---- forward quantities of this step from the record: s, inner, a_f, Pcf ----
+        if (!flag) {
+            load_packed_upper<NT1>(RF, rec + off_rf, lane);
+            __syncwarp();
+            const int q = lane < p ? lane : p - 1;
+            double frow[p];
+#pragma unroll
+            for (int i = 0; i < p; ++i)  // Fc[q][i] = Rf[i][q], i <= q
+                frow[i] = (i >> 3) <= (q >> 3) ? RF[((i >> 3) * NT1 - ((i >> 3) * ((i >> 3) - 1)) / 2 + ((q >> 3) - (i >> 3))) * 64 +
+                                                    (i & 7) * 8 + (q & 7)]
+                                               : 0.0;
+            const double rdiag = 1.0 / RF[((q >> 3) * NT1 - ((q >> 3) * ((q >> 3) - 1)) / 2) * 64 + (q & 7) * 9];
+            double x = lane < p ? vv[lane] : 0.0;
+#pragma unroll
+            for (int rep = 0; rep < 2; ++rep) {
+#pragma unroll
+                for (int i = 0; i < p; ++i) {
+                    const double xi = __shfl_sync(FULL, x, i) * __shfl_sync(FULL, rdiag, i);
+                    if (lane == i) x = xi;
+                    else if (lane > i) x = fma(-frow[i], xi, x);
+                }
+                if (lane < p) (rep == 0 ? vs : vin)[lane] = x;
+            }
+            __syncwarp();
+            // a_f = a + KF s,  KF[i][o] = Rf[o][p + i]
+#pragma unroll
+            for (int J = 0; J < MT; ++J) {
+                double c0 = 0.0, c1 = 0.0;
+#pragma unroll
+                for (int I = 0; I < PT; ++I) {
+                    const double2 rk = ldt(RF, tri<NT1>(I, PT + J), lane);
+                    const double sI = vs[8 * I + g];
+                    c0 = fma(rk.x, sI, c0);
+                    c1 = fma(rk.y, sI, c1);
+                }
+                c0 = red_g(c0);
+                c1 = red_g(c1);
+                if (g == 0) {
+                    vaf[8 * J + 2 * t] = va[8 * J + 2 * t] + c0;
+                    vaf[8 * J + 2 * t + 1] = va[8 * J + 2 * t + 1] + c1;
+                }
+            }
+        } else {
+            for (int i = lane; i < m; i += 32) vaf[i] = va[i];
+        }
+        __syncwarp();
+        // (Pcf + jitter I)^T tile (I, K): upper triangular from the record's factor, or Pc^T when the step was skipped
+        auto pft = [&](int I, int K) {
+            double2 v;
+            if (flag) v = ldg_tile_t(Pcg, m, I, K, lane);
+            else v = K >= I ? ldt(RF, tri<NT1>(PT + I, PT + (K >= I ? K : I)), lane) : zero2();
+            if (I == K) {
+                if (2 * t == g) v.x += G.jitter;
+                if (2 * t + 1 == g) v.y += G.jitter;
+            }
+            return v;
+        };
+        const bool dense_pf = flag && dense_pc;  // (a skipped step keeps Pc, which is dense only at t = 0)
+        constexpr int TPT = MT * MT;  // tile offset of the second scratch block inside W
+        // TP^T = (T Pcf)^T = Pcf^T T^T :  [I][J] = sum_K pft(I,K) (T[J][K])^T
+#pragma unroll
+        for (int I = 0; I < MT; ++I) {
+            double2 acc[MT];
+#pragma unroll
+            for (int J = 0; J < MT; ++J) acc[J] = zero2();
+#pragma unroll
+            for (int K = 0; K < MT; ++K)
+                if (dense_pf || K >= I) {
+                    const double2 pf = pft(I, K);
+#pragma unroll
+                    for (int J = 0; J < MT; ++J) mma_nt(acc[J], pf, ldg_tile(Tg, m, J, K, lane));
+                }
+#pragma unroll
+            for (int J = 0; J < MT; ++J) stt(W, TPT + I * MT + J, lane, acc[J]);
+        }
+        __syncwarp();
+        // U1^T = TP^T Psi_p  -> RB[0 .. MT*MT)
+#pragma unroll
+        for (int I = 0; I < MT; ++I) {
+            double2 acc[MT];
+#pragma unroll
+            for (int J = 0; J < MT; ++J) acc[J] = zero2();
+#pragma unroll
+            for (int K = 0; K < MT; ++K) {
+                const double2 tpk = ldt(W, TPT + I * MT + K, lane);
+#pragma unroll
+                for (int J = 0; J < MT; ++J) mma_nt(acc[J], tpk, ldt(W, J * MT + K, lane));
+            }
+#pragma unroll
+            for (int J = 0; J < MT; ++J) stt(RB, I * MT + J, lane, acc[J]);
+        }
+        __syncwarp();
+        // U1 -> W[TPT ..)
+#pragma unroll
+        for (int I = 0; I < MT; ++I)
+#pragma unroll
+            for (int J = 0; J < MT; ++J) stt(W, TPT + I * MT + J, lane, ttrans(ldt(RB, J * MT + I, lane), lane));
+        __syncwarp();
+        // gT += U1 Pcf^T + abar af^T ;  Pcf[J][K] = (pft(K, J))^T
+        if (G.g_T) {
+#pragma unroll
+            for (int J = 0; J < MT; ++J) {
+                double2 acc[MT];
+#pragma unroll
+                for (int I = 0; I < MT; ++I) {
+                    acc[I] = ldrw_tile(gT, m, I, J, lane);
+                    const double ab = vab[8 * I + g];
+                    acc[I].x = fma(ab, vaf[8 * J + 2 * t], acc[I].x);
+                    acc[I].y = fma(ab, vaf[8 * J + 2 * t + 1], acc[I].y);
+                }
+#pragma unroll
+                for (int K = 0; K < MT; ++K)
+                    if (dense_pf || K <= J) {
+                        const double2 pk = ttrans(pft(K, J), lane);
+#pragma unroll
+                        for (int I = 0; I < MT; ++I) mma_nt(acc[I], ldt(W, TPT + I * MT + K, lane), pk);
+                    }
+#pragma unroll
+                for (int I = 0; I < MT; ++I) stg_tile(gT, m, I, J, lane, acc[I]);
+            }
+        }
+        // Pcfbar^T = U1^T T :  [I][J] = sum_K U1T[I][K] ((T^T)[J][K])^T  -> W[0 .. MT*MT)   (Psi_p is dead)
+#pragma unroll
+        for (int I = 0; I < MT; ++I) {
+            double2 acc[MT];
+#pragma unroll
+            for (int J = 0; J < MT; ++J) acc[J] = zero2();
+#pragma unroll
+            for (int K = 0; K < MT; ++K) {
+                const double2 uk = ldt(RB, I * MT + K, lane);
+#pragma unroll
+                for (int J = 0; J < MT; ++J) mma_nt(acc[J], uk, ldg_tile_t(Tg, m, J, K, lane));
+            }
+#pragma unroll
+            for (int J = 0; J < MT; ++J) stt(W, I * MT + J, lane, acc[J]);
+        }
+        // afbar = T^T abar ; gc += abar
+#pragma unroll
+        for (int J = 0; J < MT; ++J) {
+            double c0 = 0.0, c1 = 0.0;
+#pragma unroll
+            for (int I = 0; I < MT; ++I) {
+                const double2 tf = ldg_tile(Tg, m, I, J, lane);
+                const double ab = vab[8 * I + g];
+                c0 = fma(tf.x, ab, c0);
+                c1 = fma(tf.y, ab, c1);
+            }
+            c0 = red_g(c0);
+            c1 = red_g(c1);
+            if (g == 0) {
+                vafb[8 * J + 2 * t] = c0;
+                vafb[8 * J + 2 * t + 1] = c1;
+            }
+        }
+        for (int i = lane; i < m; i += 32) vgc[i] += vab[i];
+        __syncwarp();
+        if (flag) {  // degenerate branch (:700-705): (a_f, Pcf, ll) = (a, Pc, 0)
+            for (int i = lane; i < m; i += 32) vab[i] = vafb[i];
+#pragma unroll
+            for (int i = 0; i < MT * MT; ++i) stt(PBT, i, lane, ldt(W, i, lane));
+            __syncwarp();
+            continue;
+        }
+        // ================= update adjoint =================
+        {
+            const double lossbar = -0.5 * gcot, logdetbar = -0.5 * gcot * (double)p;
+            // sbar = KF^T afbar
+#pragma unroll
+            for (int I = 0; I < PT; ++I) {
+                double acc = 0.0;
+#pragma unroll
+                for (int J = 0; J < MT; ++J) {
+                    const double2 rk = ldt(RF, tri<NT1>(I, PT + J), lane);
+                    acc = fma(rk.x, vafb[8 * J + 2 * t], acc);
+                    acc = fma(rk.y, vafb[8 * J + 2 * t + 1], acc);
+                }
+                acc = red_t(acc);
+                if (t == 0) vsb[8 * I + g] = acc;
+            }
+            __syncwarp();
+            // back substitution with U = Rf[:p,:p] = Fc^T : lane q owns x[q] and row q of U
+            const int q = lane < p ? lane : p - 1;
+            double urow[p];
+#pragma unroll
+            for (int i = 0; i < p; ++i)
+                urow[i] = (i >> 3) >= (q >> 3) ? RF[((q >> 3) * NT1 - ((q >> 3) * ((q >> 3) - 1)) / 2 + ((i >> 3) - (q >> 3))) * 64 +
+                                                    (q & 7) * 8 + (i & 7)]
+                                               : 0.0;
+            const double dq = RF[((q >> 3) * NT1 - ((q >> 3) * ((q >> 3) - 1)) / 2) * 64 + (q & 7) * 9];
+            const double rdiag = 1.0 / dq;
+            auto usolve = [&](double x) {
+#pragma unroll
+                for (int i = p - 1; i >= 0; --i) {
+                    const double xi = __shfl_sync(FULL, x, i) * __shfl_sync(FULL, rdiag, i);
+                    if (lane == i) x = xi;
+                    else if (lane < i) x = fma(-urow[i], xi, x);
+                }
+                return x;
+            };
+            double vbar = lane < p ? lossbar * vin[lane] : 0.0;
+            const double t1 = usolve(lane < p ? lossbar * vv[lane] : 0.0);          // Fc^{-T} innerbar
+            const double t2 = usolve(lane < p ? vsb[lane] + t1 : 0.0);              // Fc^{-T} (sbar + t1)
+            vbar += t2;
+            if (lane < p) {
+                vt1[lane] = t1;
+                vt2[lane] = t2;
+                vvb[lane] = vbar;
+                vsb[lane] = logdetbar * 2.0 * rdiag;  // diagonal term of Fcbar
+            }
+            __syncwarp();
+            // Rbar = Bbar^T (upper):  [Fcbar^T, KFbar^T; 0, triu(Pcfbar^T)]
+#pragma unroll
+            for (int I = 0; I < PT; ++I) {
+                const int i = 8 * I + g;
+                const double ini = vin[i], si = vs[i];
+#pragma unroll
+                for (int K = I; K < PT; ++K) {
+                    const int k = 8 * K + 2 * t;
+                    double2 v;
+                    v.x = k >= i ? fma(-vt1[k], ini, -vt2[k] * si) + (k == i ? vsb[i] : 0.0) : 0.0;
+                    v.y = k + 1 >= i ? fma(-vt1[k + 1], ini, -vt2[k + 1] * si) + (k + 1 == i ? vsb[i] : 0.0) : 0.0;
+                    stt(RB, tri<NT1>(I, K), lane, v);
+                }
+#pragma unroll
+                for (int K = 0; K < MT; ++K)
+                    stt(RB, tri<NT1>(I, PT + K), lane,
+                        make_double2(vafb[8 * K + 2 * t] * si, vafb[8 * K + 2 * t + 1] * si));
+            }
+#pragma unroll
+            for (int I = 0; I < MT; ++I)
+#pragma unroll
+                for (int K = I; K < MT; ++K) {
+                    double2 v = ldt(W, I * MT + K, lane);
+                    if (I == K) {
+                        if (2 * t < g) v.x = 0.0;
+                        if (2 * t + 1 < g) v.y = 0.0;
+                    }
+                    stt(RB, tri<NT1>(PT + I, PT + K), lane, v);
+                }
+            __syncwarp();
+        }
+        // RINV must not overlap the cotangent tiles while S0 is formed: psi_tiles reads rbar only in its first phase
+        psi_tiles<NT1>(W, RF, RB, [&](int J, int K) { return ldt(RB, tri<NT1>(J, K), lane); }, lane);
+        // ---- Abar = A Psi, A = [[Hc^T, 0], [A21, Pc^T]],  A21 = (Zm Pc)^T = Pc^T Zm^T -> RB[NT1 ..) ----
+        constexpr int A21T = NT1;  // behind RINV
+        static_assert(NT1 + MT * PT <= BD::NTRI, "A21 scratch");
+#pragma unroll
+        for (int I = 0; I < MT; ++I) {
+            double2 acc[PT];
+#pragma unroll
+            for (int J = 0; J < PT; ++J) acc[J] = zero2();
+#pragma unroll
+            for (int K = 0; K < MT; ++K)
+                if (dense_pc || K >= I) {
+                    const double2 pk = ldg_tile_t(Pcg, m, I, K, lane);
+#pragma unroll
+                    for (int J = 0; J < PT; ++J) {
+                        double2 z = ldg_tile(Zg, m, J, K, lane);
+                        const double wJ = vw[8 * J + g];
+                        z.x *= wJ;
+                        z.y *= wJ;
+                        mma_nt(acc[J], pk, z);
+                    }
+                }
+#pragma unroll
+            for (int J = 0; J < PT; ++J) stt(RB, A21T + I * PT + J, lane, acc[J]);
+        }
+        __syncwarp();
+        // Abar11 = Hc^T Psi11  (accumulated: Hcbar^T)
+#pragma unroll
+        for (int I = 0; I < PT; ++I) {
+            double2 acc[PT];
+#pragma unroll
+            for (int J = 0; J < PT; ++J) acc[J] = ldt(HBT, I * PT + J, lane);
+#pragma unroll
+            for (int K = I; K < PT; ++K) {
+                double2 h = ttrans(ldt(HC, K * PT + I, lane), lane);  // (Hc^T)[I][K]
+                if (Hzero) h = zero2();
+                else if (partial) h = make_double2(NAN, NAN);
+#pragma unroll
+                for (int J = 0; J < PT; ++J) mma_nt(acc[J], h, ldt(W, J * NT1 + K, lane));
+            }
+#pragma unroll
+            for (int J = 0; J < PT; ++J) stt(HBT, I * PT + J, lane, acc[J]);
+        }
+        // rows of [Abar21, Abar22]; Abar21 -> RF[0 ..) (the factor is dead), Pbar^T = Abar22 + Abar21 Zm -> PBT
+#pragma unroll
+        for (int I = 0; I < MT; ++I) {
+            double2 acc[NT1];
+#pragma unroll
+            for (int J = 0; J < NT1; ++J) acc[J] = zero2();
+#pragma unroll
+            for (int K = 0; K < NT1; ++K)
+                if (K < PT || dense_pc || K - PT >= I) {
+                    const double2 ak = K < PT ? ldt(RB, A21T + I * PT + (K < PT ? K : 0), lane)
+                                              : ldg_tile_t(Pcg, m, I, K >= PT ? K - PT : 0, lane);
+#pragma unroll
+                    for (int J = 0; J < NT1; ++J) mma_nt(acc[J], ak, ldt(W, J * NT1 + K, lane));
+                }
+#pragma unroll
+            for (int J = 0; J < PT; ++J) stt(RF, I * PT + J, lane, acc[J]);
+#pragma unroll
+            for (int J = 0; J < MT; ++J) {
+                double2 pb = acc[PT + J];
+#pragma unroll
+                for (int K = 0; K < PT; ++K) {
+                    double2 zt = ldg_tile_t(Zg, m, J, K, lane);  // (Zm^T)[J][K]: [g][2t+e] = Zm[8K+2t+e][8J+g]
+                    zt.x *= vw[8 * K + 2 * t];
+                    zt.y *= vw[8 * K + 2 * t + 1];
+                    mma_nt(pb, acc[K], zt);
+                }
+                stt(PBT, I * MT + J, lane, pb);
+            }
+        }
+        __syncwarp();
+        // gZ += W (ZPbar Pc^T - vbar a^T),  ZPbar = Abar21^T
+        if (G.g_Z) {
+#pragma unroll
+            for (int Io = 0; Io < PT; ++Io) {
+                double2 zp[MT];
+#pragma unroll
+                for (int K = 0; K < MT; ++K) zp[K] = ttrans(ldt(RF, K * PT + Io, lane), lane);
+                const double wo = vw[8 * Io + g], vb = vvb[8 * Io + g];
+#pragma unroll
+                for (int J = 0; J < MT; ++J) {
+                    double2 acc = zero2();
+#pragma unroll
+                    for (int K = 0; K < MT; ++K)
+                        if (dense_pc || K <= J) mma_nt(acc, zp[K], ldg_tile(Pcg, m, J, K, lane));
+                    double2 gz = ldrw_tile(gZ, m, Io, J, lane);
+                    gz.x = fma(wo, fma(-vb, va[8 * J + 2 * t], acc.x), gz.x);
+                    gz.y = fma(wo, fma(-vb, va[8 * J + 2 * t + 1], acc.y), gz.y);
+                    stg_tile(gZ, m, Io, J, lane, gz);
+                }
+            }
+        }
+        // abar = afbar - Zm^T vbar ; gd -= vbar
+#pragma unroll
+        for (int J = 0; J < MT; ++J) {
+            double c0 = 0.0, c1 = 0.0;
+#pragma unroll
+            for (int I = 0; I < PT; ++I) {
+                const double2 z = ldg_tile(Zg, m, I, J, lane);
+                const double f = vw[8 * I + g] * vvb[8 * I + g];
+                c0 = fma(z.x, f, c0);
+                c1 = fma(z.y, f, c1);
+            }
+            c0 = red_g(c0);
+            c1 = red_g(c1);
+            if (g == 0) {
+                vab[8 * J + 2 * t] = vafb[8 * J + 2 * t] - c0;
+                vab[8 * J + 2 * t + 1] = vafb[8 * J + 2 * t + 1] - c1;
+            }
+        }
+        if (lane < p) vgd[lane] -= vvb[lane];
+        __syncwarp();
+    }
+    // ---- gradients out ----
+    for (int i = lane; i < m; i += 32) {
+        if (G.g_a0) G.g_a0[(size_t)b * m + i] = vab[i];
+        if (G.g_c) G.g_c[(size_t)b * m + i] = vgc[i];
+    }
+    if (G.g_d && lane < p) G.g_d[(size_t)b * p + lane] = vgd[lane];
+    if (G.g_P0) {
+        double* dst = G.g_P0 + (size_t)b * m * m;
+#pragma unroll
+        for (int I = 0; I < MT; ++I)
+#pragma unroll
+            for (int J = 0; J < MT; ++J) {
+                const double2 v = ldt(PBT, I * MT + J, lane);  // Pbar[8J+2t+e][8I+g]
+                dst[(8 * J + 2 * t) * m + 8 * I + g] = v.x;
+                dst[(8 * J + 2 * t + 1) * m + 8 * I + g] = v.y;
+            }
+    }
+    __syncwarp();
+    double* E = smem + BD::W;  // W, RF, RB are dead: one row-major scratch block
+    if (G.g_H) {
+        double* dst = G.g_H + (size_t)b * p * p;
+        if (Hzero) {
+            for (int idx = lane; idx < p * p; idx += 32) dst[idx] = HBT[elem_addr(idx % p, idx / p, PT)];
+        } else {
+            double *L = E, *Lb = E + p * p, *out = E + 2 * p * p, *tmp = E + 3 * p * p;
+            for (int idx = lane; idx < p * p; idx += 32) {
+                const int i = idx / p, j = idx - i * p;
+                L[idx] = HC[elem_addr(i, j, PT)];
+                Lb[idx] = j <= i ? HBT[elem_addr(j, i, PT)] : 0.0;
+            }
+            __syncwarp();
+            chol_pullback_warp(out, L, Lb, p, tmp, lane);
+            for (int idx = lane; idx < p * p; idx += 32) dst[idx] = out[idx];
+            __syncwarp();
+        }
+    }
+    if (want_ps) {
+        const double* Rg = param_ptr(G.Rm, G.shared_mask, BKF_PARAM_R, b, (size_t)m * r);
+        const double* Qg = param_ptr(G.Q, G.shared_mask, BKF_PARAM_Q, b, (size_t)r * r);
+        double *Qc = E, *X1 = Qc + r * r, *QQ = X1 + m * r, *Y = QQ + r * r, *Qb = Y + m * r, *out = Qb + r * r,
+               *tmp = out + r * r;
+        for (int i = lane; i < r * r; i += 32) Qc[i] = Qg[i];
+        __syncwarp();
+        chol_lower_warp(Qc, r, lane);
+        __threadfence_block();
+        wmm<false>(X1, r, PS, m, 1, Rg, r, 1, m, r, m, lane);  // X1 = Psum R
+        if (G.g_R) {
+            wmm<false>(QQ, r, Qc, r, 1, Qc, 1, r, r, r, r, lane);  // Qc Qc^T
+            wmm<false>(Y, r, X1, r, 1, QQ, r, 1, m, r, r, lane);
+            for (int i = lane; i < m * r; i += 32) G.g_R[(size_t)b * m * r + i] = Y[i];
+            __syncwarp();
+        }
+        if (G.g_Q) {
+            wmm<false>(Y, r, X1, r, 1, Qc, r, 1, m, r, r, lane);   // X1 Qc
+            wmm<false>(Qb, r, Rg, 1, r, Y, r, 1, r, r, m, lane);   // R^T X1 Qc
+            for (int idx = lane; idx < r * r; idx += 32)
+                if ((idx % r) > (idx / r)) Qb[idx] = 0.0;
+            __syncwarp();
+            chol_pullback_warp(out, Qc, Qb, r, tmp, lane);
+            for (int i = lane; i < r * r; i += 32) G.g_Q[(size_t)b * r * r + i] = out[i];
+        }
     }
 }
 

@@ -181,7 +181,7 @@ def test_subwarp_kernels_all_sizes(eng, m):
 
 
 @pytest.mark.parametrize("shape", [(2, 1, 2), (5, 2, 3), (8, 3, 2), (12, 4, 4), (6, 6, 3), (8, 8, 8), (16, 8, 8),
-                                   (24, 8, 16), (32, 16, 16)])
+                                   (16, 16, 8), (24, 8, 16), (32, 16, 16)])
 @pytest.mark.parametrize("missing", [0.0, 0.2])
 def test_square_root_filter_batched_logp_grad(eng, shape, missing):
     """SquareRootFilter forward + QR adjoint (P0 is a factor; H, Q gradients in the lower-triangular convention)."""
@@ -202,6 +202,8 @@ def test_square_root_filter_batched_logp_grad(eng, shape, missing):
     for got, want in zip([out[n_] for n_ in OUT_NAMES], ref):
         _close(got, want.numpy(), RTOL64, "cholesky forward")
     logp, grads, status = eng.logp_grad("cholesky", *args)
+    # float64 shapes made of whole 8 x 8 tiles run the warp-per-series DMMA kernels, everything else the CTA ones
+    assert eng.last_path == ("sqrt_warp_dmma" if shape in ((16, 8, 8), (16, 16, 8), (32, 16, 16)) else "sqrt_cta")
     ref_logp, ref_g = oth.logp_and_grad("cholesky", *args)
     assert_allclose(logp, ref_logp, rtol=RTOL64)
     for k in NAMES:
