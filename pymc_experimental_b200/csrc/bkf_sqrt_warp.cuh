@@ -36,6 +36,18 @@ __device__ __forceinline__ void mma_nt(double2& d, const double2 x, const double
     dmma(d.x, d.y, x.x, y.x);
     dmma(d.x, d.y, x.y, y.y);
 }
+// Accumulator tile of the adjoint's product chains.  (Splitting it into one accumulator per k-half -- two independent
+// DMMAs instead of a dependent pair -- was measured: no gain at one warp per scheduler, more spills.)
+struct Acc2 {
+    double2 a;
+};
+__device__ __forceinline__ Acc2 acc2_zero() { return Acc2{make_double2(0.0, 0.0)}; }
+__device__ __forceinline__ Acc2 acc2_from(double2 v) { return Acc2{v}; }
+__device__ __forceinline__ void mma_nt(Acc2& d, const double2 x, const double2 y) {
+    dmma(d.a.x, d.a.y, x.x, y.x);
+    dmma(d.a.x, d.a.y, x.y, y.y);
+}
+__device__ __forceinline__ double2 fin(const Acc2& d) { return d.a; }
 __device__ __forceinline__ double2 ldt(const double* S, int tile, int lane) {
     return reinterpret_cast<const double2*>(S)[tile * 32 + lane];
 }
@@ -97,120 +109,172 @@ __device__ __forceinline__ int elem_addr(int i, int j, int WT) {
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// Householder R factor of an array stored transposed in tiles.  Map::tile(jt, rt) is the tile holding columns
-// 8jt..8jt+7 and rows 8rt..8rt+7 of the array (element [col][row] in C layout).  NP column blocks, NR row blocks.
-// On return the tiles hold R^T (lower triangular in storage order), zeros elsewhere.
-template <int NP, int NR, class Map>
-__device__ __forceinline__ void qr_tiles(double* __restrict__ S, const int lane) {
+// 1 / sqrt(x) and 1 / x from the 20-bit hardware seeds and two Newton steps (normal, positive-magnitude arguments: the
+// pivot norms of a Householder sweep) -- a quarter of the instructions and half the latency of the IEEE sequences, which
+// sit on the serial chain of every reflector.
+__device__ __forceinline__ double rsqrt_nr(double x) {
+    double r;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    const double hx = 0.5 * x;
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+        const double e = fma(-hx * r, r, 0.5);
+        r = fma(r, e, r);
+    }
+    return r;
+}
+__device__ __forceinline__ double rcp_nr(double x) {
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+        const double e = fma(-x, r, 1.0);
+        r = fma(r, e, r);
+    }
+    return r;
+}
+
+// One panel (8 columns, NQ active row blocks, the diagonal block first) of the Householder sweep and its trailing update.
+// tile(jt, rt) -> tile index.  The reflector loop is rolled (runtime k): see qr_tiles.
+template <int NQ, class TileF>
+__device__ __forceinline__ void qr_panel(double* __restrict__ S, const int jt, const int np, TileF tile, const int lane) {
     const int g = lane >> 2, t = lane & 3;
+    double2 pa[NQ];
 #pragma unroll
-    for (int jt = 0; jt < NP; ++jt) {
-        double2 pa[NR];
+    for (int q = 0; q < NQ; ++q) pa[q] = ldt(S, tile(jt, jt + q), lane);
+    double2 tt = zero2();  // T^T in C layout: lane (g = j, t) holds T[2t][j], T[2t+1][j]
+#pragma unroll 1
+    for (int k = 0; k < 8; ++k) {
+        // x = column k of the panel below its diagonal, handed to every group (lane (k, t) -> lanes (*, t))
+        double2 xb[NQ];
 #pragma unroll
-        for (int rt = 0; rt < NR; ++rt)
-            if (rt >= jt) pa[rt] = ldt(S, Map::tile(jt, rt), lane);
-        double2 tt = zero2();  // T^T in C layout: lane (g = j, t) holds T[2t][j], T[2t+1][j]
-#pragma unroll
-        for (int k = 0; k < 8; ++k) {
-            // x = column k of the panel below its diagonal, handed to every group (lane (k, t) -> lanes (*, t))
-            double2 xb[NR];
-#pragma unroll
-            for (int rt = 0; rt < NR; ++rt)
-                if (rt >= jt) {
-                    xb[rt].x = __shfl_sync(FULL, pa[rt].x, 4 * k + t);
-                    xb[rt].y = __shfl_sync(FULL, pa[rt].y, 4 * k + t);
-                }
-            double2 xm = xb[jt];
-            if (2 * t <= k) xm.x = 0.0;
-            if (2 * t + 1 <= k) xm.y = 0.0;
-            double d0 = xm.x * pa[jt].x, d1 = xm.y * pa[jt].y;
-#pragma unroll
-            for (int rt = 0; rt < NR; ++rt)
-                if (rt > jt) {
-                    d0 = fma(xb[rt].x, pa[rt].x, d0);
-                    d1 = fma(xb[rt].y, pa[rt].y, d1);
-                }
-            // one reduction window: group k -> ss = x.x; group c > k -> x.a_c; group i < k -> x.v_i (for T)
-            const double dot = red_t(d0 + d1);
-            const double ss = __shfl_sync(FULL, dot, 4 * k);
-            const double akc = __shfl_sync(FULL, (k & 1) ? pa[jt].y : pa[jt].x, 4 * g + (k >> 1));  // [row k][col g]
-            const double alpha = __shfl_sync(FULL, akc, 4 * k);
-            if (ss == 0.0) continue;  // dlarfg: tau = 0, H = I (column k of T stays zero)
-            const double nrm = sqrt(fma(alpha, alpha, ss));
-            const double beta = alpha >= 0.0 ? -nrm : nrm;
-            const double tau = (beta - alpha) / beta;
-            const double scal = 1.0 / (alpha - beta);
-            const double zz = fma(scal, dot, akc);  // v_k . a_c  (c > k)   or   v_i . v_k  (i < k)
-            const double w = g > k ? tau * zz : 0.0;
-            double2 vd = make_double2(xm.x * scal, xm.y * scal);  // v on my rows (unit at row k)
-            if (2 * t == k) vd.x = 1.0;
-            if (2 * t + 1 == k) vd.y = 1.0;
-            pa[jt].x = fma(-w, vd.x, pa[jt].x);
-            pa[jt].y = fma(-w, vd.y, pa[jt].y);
-            if (g == k) {
-                if (2 * t > k) pa[jt].x = vd.x;
-                else if (2 * t == k) pa[jt].x = beta;
-                if (2 * t + 1 > k) pa[jt].y = vd.y;
-                else if (2 * t + 1 == k) pa[jt].y = beta;
-            }
-#pragma unroll
-            for (int rt = 0; rt < NR; ++rt)
-                if (rt > jt) {
-                    const double vx = xb[rt].x * scal, vy = xb[rt].y * scal;
-                    pa[rt].x = g == k ? vx : fma(-w, vx, pa[rt].x);
-                    pa[rt].y = g == k ? vy : fma(-w, vy, pa[rt].y);
-                }
-            // dlarft, column k:  T[0:k, k] = -tau T[0:k, 0:k] z,  z_i = v_i . v_k ;  T[k][k] = tau
-            const double cz = g < k ? zz : 0.0;
-            const double s0 = red_g(tt.x * cz), s1 = red_g(tt.y * cz);
-            if (g == k) {
-                tt.x = 2 * t < k ? -tau * s0 : (2 * t == k ? tau : 0.0);
-                tt.y = 2 * t + 1 < k ? -tau * s1 : (2 * t + 1 == k ? tau : 0.0);
-            }
+        for (int q = 0; q < NQ; ++q) {
+            xb[q].x = __shfl_sync(FULL, pa[q].x, 4 * k + t);
+            xb[q].y = __shfl_sync(FULL, pa[q].y, 4 * k + t);
         }
-        // R goes back to the array (zeros below the diagonal); V^T (unit diagonal) stays in registers
-        double2 vt[NR], vv[NR];
+        double2 xm = xb[0];
+        if (2 * t <= k) xm.x = 0.0;
+        if (2 * t + 1 <= k) xm.y = 0.0;
+        double d0 = xm.x * pa[0].x, d1 = xm.y * pa[0].y;
+#pragma unroll
+        for (int q = 1; q < NQ; ++q) {
+            d0 = fma(xb[q].x, pa[q].x, d0);
+            d1 = fma(xb[q].y, pa[q].y, d1);
+        }
+        // one reduction window: group k -> ss = x.x; group c > k -> x.a_c; group i < k -> x.v_i (for T)
+        const double dot = red_t(d0 + d1);
+        const double ss = __shfl_sync(FULL, dot, 4 * k);
+        const double akc = __shfl_sync(FULL, (k & 1) ? pa[0].y : pa[0].x, 4 * g + (k >> 1));  // [row k][col g]
+        const double alpha = __shfl_sync(FULL, akc, 4 * k);
+        if (ss == 0.0) continue;  // dlarfg: tau = 0, H = I (column k of T stays zero)
+        // beta = -sign(alpha) nrm,  tau = (beta - alpha) / beta = (|alpha| + nrm) / nrm,  scal = 1 / (alpha - beta)
+        const double x2 = fma(alpha, alpha, ss);
+        const double rn = rsqrt_nr(x2);
+        double nrm = x2 * rn;
+        nrm = fma(fma(-nrm, nrm, x2), 0.5 * rn, nrm);
+        const double den = fabs(alpha) + nrm;
+        const double rden = rcp_nr(den);
+        const double beta = alpha >= 0.0 ? -nrm : nrm;
+        const double tau = den * rn;
+        const double scal = alpha >= 0.0 ? rden : -rden;
+        const double zz = fma(scal, dot, akc);  // v_k . a_c  (c > k)   or   v_i . v_k  (i < k)
+        // column update a_c -= w v (c > k); the pivot column itself becomes v = x scal, written as x - w_k v with
+        // w_k = 1 / scal - 1 = (alpha - beta) - 1 so that every lane runs the same FMA
+        const double w = g > k ? tau * zz : (g == k ? (alpha - beta) - 1.0 : 0.0);
+        double2 vd = make_double2(xm.x * scal, xm.y * scal);  // v on my rows (unit at row k)
+        if (2 * t == k) vd.x = 1.0;
+        if (2 * t + 1 == k) vd.y = 1.0;
         {
-            const double2 r = pa[jt];
-            stt(S, Map::tile(jt, jt), lane, make_double2(2 * t <= g ? r.x : 0.0, 2 * t + 1 <= g ? r.y : 0.0));
-            vt[jt].x = 2 * t > g ? r.x : (2 * t == g ? 1.0 : 0.0);
-            vt[jt].y = 2 * t + 1 > g ? r.y : (2 * t + 1 == g ? 1.0 : 0.0);
+            const double nx = fma(-w, vd.x, pa[0].x), ny = fma(-w, vd.y, pa[0].y);
+            const bool piv = g == k;
+            pa[0].x = piv ? (2 * t > k ? vd.x : (2 * t == k ? beta : pa[0].x)) : nx;
+            pa[0].y = piv ? (2 * t + 1 > k ? vd.y : (2 * t + 1 == k ? beta : pa[0].y)) : ny;
         }
 #pragma unroll
-        for (int rt = 0; rt < NR; ++rt)
-            if (rt > jt) {
-                vt[rt] = pa[rt];
-                stt(S, Map::tile(jt, rt), lane, zero2());
+        for (int q = 1; q < NQ; ++q) {
+            pa[q].x = fma(-w, xb[q].x * scal, pa[q].x);
+            pa[q].y = fma(-w, xb[q].y * scal, pa[q].y);
+        }
+        // dlarft, column k:  T[0:k, k] = -tau T[0:k, 0:k] z,  z_i = v_i . v_k ;  T[k][k] = tau
+        const double cz = g < k ? zz : 0.0;
+        const double s0 = red_g(tt.x * cz), s1 = red_g(tt.y * cz);
+        if (g == k) {
+            tt.x = 2 * t < k ? -tau * s0 : (2 * t == k ? tau : 0.0);
+            tt.y = 2 * t + 1 < k ? -tau * s1 : (2 * t + 1 == k ? tau : 0.0);
+        }
+    }
+    // R goes back to the array (zeros below the diagonal); V^T (unit diagonal) stays in registers (in pa)
+    {
+        const double2 r = pa[0];
+        stt(S, tile(jt, jt), lane, make_double2(2 * t <= g ? r.x : 0.0, 2 * t + 1 <= g ? r.y : 0.0));
+        pa[0].x = 2 * t > g ? r.x : (2 * t == g ? 1.0 : 0.0);
+        pa[0].y = 2 * t + 1 > g ? r.y : (2 * t + 1 == g ? 1.0 : 0.0);
+    }
+#pragma unroll
+    for (int q = 1; q < NQ; ++q) stt(S, tile(jt, jt + q), lane, zero2());
+    if (jt + 1 < np) {
+        double2 vv[NQ];
+#pragma unroll
+        for (int q = 0; q < NQ; ++q) vv[q] = ttrans(pa[q], lane);
+#pragma unroll 1
+        for (int j2 = jt + 1; j2 < np; ++j2) {
+            double2 c[NQ];
+#pragma unroll
+            for (int q = 0; q < NQ; ++q) c[q] = ldt(S, tile(j2, jt + q), lane);
+            // (A^T V) block: independent accumulator chains (even / odd q, first / second k-half)
+            double2 wa = zero2(), wb = zero2(), wc = zero2(), wd = zero2();
+#pragma unroll
+            for (int q = 0; q < NQ; q += 2) {
+                dmma(wa.x, wa.y, c[q].x, pa[q].x);
+                if (q + 1 < NQ) dmma(wc.x, wc.y, c[q + 1 < NQ ? q + 1 : q].x, pa[q + 1 < NQ ? q + 1 : q].x);
+                dmma(wb.x, wb.y, c[q].y, pa[q].y);
+                if (q + 1 < NQ) dmma(wd.x, wd.y, c[q + 1 < NQ ? q + 1 : q].y, pa[q + 1 < NQ ? q + 1 : q].y);
             }
-        if (jt + 1 < NP) {
+            const double2 wt = make_double2((wa.x + wb.x) + (wc.x + wd.x), (wa.y + wb.y) + (wc.y + wd.y));
+            double2 u0 = zero2(), u1 = zero2();  // (A^T V) T
+            dmma(u0.x, u0.y, wt.x, tt.x);
+            dmma(u1.x, u1.y, wt.y, tt.y);
+            const double2 ut = make_double2(-(u0.x + u1.x), -(u0.y + u1.y));
+            // A^T -= (A^T V T) V^T : first k-halves of every tile, then the second halves
 #pragma unroll
-            for (int rt = 0; rt < NR; ++rt)
-                if (rt >= jt) vv[rt] = ttrans(vt[rt], lane);
+            for (int q = 0; q < NQ; ++q) dmma(c[q].x, c[q].y, ut.x, vv[q].x);
 #pragma unroll
-            for (int j2 = 0; j2 < NP; ++j2)
-                if (j2 > jt) {
-                    double2 c[NR];
-                    double2 w0 = zero2(), w1 = zero2();
-#pragma unroll
-                    for (int rt = 0; rt < NR; ++rt)
-                        if (rt >= jt) {
-                            c[rt] = ldt(S, Map::tile(j2, rt), lane);
-                            if ((rt - jt) & 1) mma_nt(w1, c[rt], vt[rt]);
-                            else mma_nt(w0, c[rt], vt[rt]);
-                        }
-                    const double2 wt = make_double2(w0.x + w1.x, w0.y + w1.y);  // (A^T V) block
-                    double2 ut = zero2();
-                    mma_nt(ut, wt, tt);  // (A^T V) T
-                    ut = neg(ut);
-#pragma unroll
-                    for (int rt = 0; rt < NR; ++rt)
-                        if (rt >= jt) {
-                            mma_nt(c[rt], ut, vv[rt]);  // A^T -= (A^T V T) V^T
-                            stt(S, Map::tile(j2, rt), lane, c[rt]);
-                        }
-                }
+            for (int q = 0; q < NQ; ++q) {
+                dmma(c[q].x, c[q].y, ut.y, vv[q].y);
+                stt(S, tile(j2, jt + q), lane, c[q]);
+            }
         }
-        __syncwarp();
+    }
+    __syncwarp();
+}
+
+// Householder R factor of an array stored transposed in tiles (element [col][row] in C layout).  Two arrays share the
+// tile grid (WT tile columns):
+//   update  (predict = false): column block jt -> tile row jt,      row block rt -> tile column rt
+//   predict (predict = true ): column block jt -> tile row PT + jt, row block rt -> tile column PT + rt (rt < MT),
+//                              rt - MT (the R Qc rows) -- so that R^T (= the next Pc) lands on the Pc block.
+// np column blocks, nr row blocks (nr <= NRMAX).  On return the tiles hold R^T, zeros elsewhere.
+// One copy of the code per number of active row blocks, panel and reflector loops rolled: a fully unrolled sweep is
+// ~200 KB of SASS, which the 32 KB instruction cache cannot hold with one warp per scheduler.
+template <int NRMAX, int MT, int PT, int WT>
+__device__ __noinline__ void qr_tiles(double* __restrict__ S, const int np, const int nr, const bool predict,
+                                      const int lane) {
+    auto tile = [&](int jt, int rt) {
+        return predict ? (PT + jt) * WT + (rt < MT ? PT + rt : rt - MT) : jt * WT + rt;
+    };
+#pragma unroll 1
+    for (int jt = 0; jt < np; ++jt) {
+        switch (nr - jt) {
+            case 1: qr_panel<1>(S, jt, np, tile, lane); break;
+            case 2: if constexpr (NRMAX >= 2) qr_panel<2>(S, jt, np, tile, lane); break;
+            case 3: if constexpr (NRMAX >= 3) qr_panel<3>(S, jt, np, tile, lane); break;
+            case 4: if constexpr (NRMAX >= 4) qr_panel<4>(S, jt, np, tile, lane); break;
+            case 5: if constexpr (NRMAX >= 5) qr_panel<5>(S, jt, np, tile, lane); break;
+            case 6: if constexpr (NRMAX >= 6) qr_panel<6>(S, jt, np, tile, lane); break;
+            case 7: if constexpr (NRMAX >= 7) qr_panel<7>(S, jt, np, tile, lane); break;
+            case 8: if constexpr (NRMAX >= 8) qr_panel<8>(S, jt, np, tile, lane); break;
+            default: break;
+        }
     }
 }
 
@@ -434,7 +498,7 @@ __global__ void __launch_bounds__(32) forward_kernel(KArgs<double> G) {
 #pragma unroll
                 for (int J = 0; J < PT; ++J) stt(SA, (PT + I) * WT + J, lane, zero2());
             __syncwarp();
-            qr_tiles<D::NT1, D::NT1, typename D::MapU>(SA, lane);
+            qr_tiles<D::NT1, MT, PT, WT>(SA, D::NT1, D::NT1, false, lane);
             if (rec)
                 store_packed_upper<D::NT1>(rec + off_rf, SA, lane, [](int I, int J) { return I * WT + J; });
             // ---- s = Fc^{-1} v, inner = Fc^{-1} s  (Fc = B[:p,:p], lower), lane q owns x[q] ----
@@ -520,7 +584,7 @@ __global__ void __launch_bounds__(32) forward_kernel(KArgs<double> G) {
             }
             __syncwarp();
         }
-        qr_tiles<MT, MT + RT, typename D::MapP>(SA, lane);
+        qr_tiles<D::NT1, MT, PT, WT>(SA, MT, MT + RT, true, lane);
         if (rec) store_packed_upper<MT>(rec + off_rp, SA, lane, [](int I, int J) { return D::pc_tile(I, J); });
     }
     if (lane == 0) {
@@ -570,9 +634,9 @@ __device__ __forceinline__ void psi_tiles(double* __restrict__ W, const double* 
     // S = copyltu(R Rbar^T)
 #pragma unroll
     for (int I = 0; I < NT; ++I) {
-        double2 acc[NT];
+        Acc2 acc[NT];
 #pragma unroll
-        for (int J = 0; J < NT; ++J) acc[J] = zero2();
+        for (int J = 0; J < NT; ++J) acc[J] = acc2_zero();
 #pragma unroll
         for (int K = I; K < NT; ++K) {
             const double2 rk = ldt(RF, tri<NT>(I, K), lane);
@@ -581,11 +645,13 @@ __device__ __forceinline__ void psi_tiles(double* __restrict__ W, const double* 
         }
 #pragma unroll
         for (int J = 0; J < I; ++J) {
-            stt(W, I * NT + J, lane, acc[J]);
-            stt(W, J * NT + I, lane, ttrans(acc[J], lane));
+            const double2 v = fin(acc[J]);
+            stt(W, I * NT + J, lane, v);
+            stt(W, J * NT + I, lane, ttrans(v, lane));
         }
-        const double2 dt = ttrans(acc[I], lane);
-        stt(W, I * NT + I, lane, make_double2(g >= 2 * t ? acc[I].x : dt.x, g >= 2 * t + 1 ? acc[I].y : dt.y));
+        const double2 dv = fin(acc[I]);
+        const double2 dt = ttrans(dv, lane);
+        stt(W, I * NT + I, lane, make_double2(g >= 2 * t ? dv.x : dt.x, g >= 2 * t + 1 ? dv.y : dt.y));
     }
     __syncwarp();
     // inverses of the diagonal tiles: lane 8q + c solves column c of tile q (four tiles per round)
@@ -594,13 +660,15 @@ __device__ __forceinline__ void psi_tiles(double* __restrict__ W, const double* 
         const int I = base + (lane >> 3), c = lane & 7;
         if (I < NT) {
             const double* Dg = RF + (I * NT - (I * (I - 1)) / 2) * 64;
-            double x[8];
+            double x[8], rd[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) rd[i] = 1.0 / Dg[i * 9];
 #pragma unroll
             for (int i = 7; i >= 0; --i) {
                 double tv = i == c ? 1.0 : 0.0;
 #pragma unroll
                 for (int q = 7; q > i; --q) tv = fma(-Dg[i * 8 + q], x[q], tv);
-                x[i] = tv / Dg[i * 8 + i];
+                x[i] = tv * rd[i];
             }
 #pragma unroll
             for (int i = 0; i < 8; ++i) RINV[I * 64 + i * 8 + c] = x[i];
@@ -612,9 +680,9 @@ __device__ __forceinline__ void psi_tiles(double* __restrict__ W, const double* 
         // X <- X R^{-T}, tile column by tile column (all tile rows at once)
 #pragma unroll
         for (int I = NT - 1; I >= 0; --I) {
-            double2 acc[NT];
+            Acc2 acc[NT];
 #pragma unroll
-            for (int J = 0; J < NT; ++J) acc[J] = ldt(W, J * NT + I, lane);
+            for (int J = 0; J < NT; ++J) acc[J] = acc2_from(ldt(W, J * NT + I, lane));
 #pragma unroll
             for (int K = I + 1; K < NT; ++K) {
                 const double2 rk = neg(ldt(RF, tri<NT>(I, K), lane));
@@ -622,12 +690,14 @@ __device__ __forceinline__ void psi_tiles(double* __restrict__ W, const double* 
                 for (int J = 0; J < NT; ++J) mma_nt(acc[J], ldt(W, J * NT + K, lane), rk);
             }
             const double2 ri = ldt(RINV, I, lane);
+            Acc2 o[NT];
 #pragma unroll
             for (int J = 0; J < NT; ++J) {
-                double2 o = zero2();
-                mma_nt(o, acc[J], ri);
-                stt(W, J * NT + I, lane, o);
+                o[J] = acc2_zero();
+                mma_nt(o[J], fin(acc[J]), ri);
             }
+#pragma unroll
+            for (int J = 0; J < NT; ++J) stt(W, J * NT + I, lane, fin(o[J]));
             __syncwarp();
         }
         if (pass == 0) {
@@ -762,6 +832,11 @@ __global__ void __launch_bounds__(32) backward_kernel(KArgs<double> G) {
         const double* Pcg = rec + m;
         const double gcot = G.ll_cot ? G.ll_cot[bt] : 1.0;
         const bool dense_pc = ts == 0;  // P0 is whatever the caller passed; later factors are lower triangular
+        if (ts > 0) {  // the next record this warp will read: pull it towards L2 while this step computes
+            const char* nxt = reinterpret_cast<const char*>(rec - tstride);
+            for (int off = lane * 128; off < (int)(tstride * sizeof(double)); off += 32 * 128)
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(nxt + off));
+        }
         // ---- mask, innovation (as the forward sweep) ----
         bool miss = true;
         if (lane < p) {
@@ -868,29 +943,38 @@ __global__ void __launch_bounds__(32) backward_kernel(KArgs<double> G) {
         };
         const bool dense_pf = flag && dense_pc;  // (a skipped step keeps Pc, which is dense only at t = 0)
         constexpr int TPT = MT * MT;  // tile offset of the second scratch block inside W
-        // TP^T = (T Pcf)^T = Pcf^T T^T :  [I][J] = sum_K pft(I,K) (T[J][K])^T
+        // TP^T = (T Pcf)^T = Pcf^T T^T :  [I][J] = sum_K pft(I,K) (T[J][K])^T   (each T tile is fetched once)
+        {
+            double2 acc[MT][MT];
 #pragma unroll
-        for (int I = 0; I < MT; ++I) {
-            double2 acc[MT];
+            for (int I = 0; I < MT; ++I)
 #pragma unroll
-            for (int J = 0; J < MT; ++J) acc[J] = zero2();
+                for (int J = 0; J < MT; ++J) acc[I][J] = zero2();
 #pragma unroll
-            for (int K = 0; K < MT; ++K)
-                if (dense_pf || K >= I) {
-                    const double2 pf = pft(I, K);
+            for (int K = 0; K < MT; ++K) {
+                double2 tk[MT];
 #pragma unroll
-                    for (int J = 0; J < MT; ++J) mma_nt(acc[J], pf, ldg_tile(Tg, m, J, K, lane));
-                }
+                for (int J = 0; J < MT; ++J) tk[J] = ldg_tile(Tg, m, J, K, lane);
 #pragma unroll
-            for (int J = 0; J < MT; ++J) stt(W, TPT + I * MT + J, lane, acc[J]);
+                for (int I = 0; I < MT; ++I)
+                    if (dense_pf || K >= I) {
+                        const double2 pf = pft(I, K);
+#pragma unroll
+                        for (int J = 0; J < MT; ++J) mma_nt(acc[I][J], pf, tk[J]);
+                    }
+            }
+#pragma unroll
+            for (int I = 0; I < MT; ++I)
+#pragma unroll
+                for (int J = 0; J < MT; ++J) stt(W, TPT + I * MT + J, lane, acc[I][J]);
         }
         __syncwarp();
         // U1^T = TP^T Psi_p  -> RB[0 .. MT*MT)
 #pragma unroll
         for (int I = 0; I < MT; ++I) {
-            double2 acc[MT];
+            Acc2 acc[MT];
 #pragma unroll
-            for (int J = 0; J < MT; ++J) acc[J] = zero2();
+            for (int J = 0; J < MT; ++J) acc[J] = acc2_zero();
 #pragma unroll
             for (int K = 0; K < MT; ++K) {
                 const double2 tpk = ldt(W, TPT + I * MT + K, lane);
@@ -898,7 +982,7 @@ __global__ void __launch_bounds__(32) backward_kernel(KArgs<double> G) {
                 for (int J = 0; J < MT; ++J) mma_nt(acc[J], tpk, ldt(W, J * MT + K, lane));
             }
 #pragma unroll
-            for (int J = 0; J < MT; ++J) stt(RB, I * MT + J, lane, acc[J]);
+            for (int J = 0; J < MT; ++J) stt(RB, I * MT + J, lane, fin(acc[J]));
         }
         __syncwarp();
         // U1 -> W[TPT ..)
@@ -911,13 +995,14 @@ __global__ void __launch_bounds__(32) backward_kernel(KArgs<double> G) {
         if (G.g_T) {
 #pragma unroll
             for (int J = 0; J < MT; ++J) {
-                double2 acc[MT];
+                Acc2 acc[MT];
 #pragma unroll
                 for (int I = 0; I < MT; ++I) {
-                    acc[I] = ldrw_tile(gT, m, I, J, lane);
+                    double2 v0 = ldrw_tile(gT, m, I, J, lane);
                     const double ab = vab[8 * I + g];
-                    acc[I].x = fma(ab, vaf[8 * J + 2 * t], acc[I].x);
-                    acc[I].y = fma(ab, vaf[8 * J + 2 * t + 1], acc[I].y);
+                    v0.x = fma(ab, vaf[8 * J + 2 * t], v0.x);
+                    v0.y = fma(ab, vaf[8 * J + 2 * t + 1], v0.y);
+                    acc[I] = acc2_from(v0);
                 }
 #pragma unroll
                 for (int K = 0; K < MT; ++K)
@@ -927,42 +1012,47 @@ __global__ void __launch_bounds__(32) backward_kernel(KArgs<double> G) {
                         for (int I = 0; I < MT; ++I) mma_nt(acc[I], ldt(W, TPT + I * MT + K, lane), pk);
                     }
 #pragma unroll
-                for (int I = 0; I < MT; ++I) stg_tile(gT, m, I, J, lane, acc[I]);
+                for (int I = 0; I < MT; ++I) stg_tile(gT, m, I, J, lane, fin(acc[I]));
             }
         }
         // Pcfbar^T = U1^T T :  [I][J] = sum_K U1T[I][K] ((T^T)[J][K])^T  -> W[0 .. MT*MT)   (Psi_p is dead)
+        // and, from the same tiles of T^T,  afbar = T^T abar
+        {
+            double afp[MT];
 #pragma unroll
-        for (int I = 0; I < MT; ++I) {
-            double2 acc[MT];
+            for (int J = 0; J < MT; ++J) afp[J] = 0.0;
+            double2 acc[MT][MT];
 #pragma unroll
-            for (int J = 0; J < MT; ++J) acc[J] = zero2();
+            for (int I = 0; I < MT; ++I)
+#pragma unroll
+                for (int J = 0; J < MT; ++J) acc[I][J] = zero2();
 #pragma unroll
             for (int K = 0; K < MT; ++K) {
-                const double2 uk = ldt(RB, I * MT + K, lane);
+                double2 tk[MT];
+                const double ab0 = vab[8 * K + 2 * t], ab1 = vab[8 * K + 2 * t + 1];
 #pragma unroll
-                for (int J = 0; J < MT; ++J) mma_nt(acc[J], uk, ldg_tile_t(Tg, m, J, K, lane));
+                for (int J = 0; J < MT; ++J) {
+                    tk[J] = ldg_tile_t(Tg, m, J, K, lane);  // [g][2t+e] = T[8K + 2t + e][8J + g]
+                    afp[J] = fma(tk[J].x, ab0, fma(tk[J].y, ab1, afp[J]));
+                }
+#pragma unroll
+                for (int I = 0; I < MT; ++I) {
+                    const double2 uk = ldt(RB, I * MT + K, lane);
+#pragma unroll
+                    for (int J = 0; J < MT; ++J) mma_nt(acc[I][J], uk, tk[J]);
+                }
             }
 #pragma unroll
-            for (int J = 0; J < MT; ++J) stt(W, I * MT + J, lane, acc[J]);
+            for (int I = 0; I < MT; ++I)
+#pragma unroll
+                for (int J = 0; J < MT; ++J) stt(W, I * MT + J, lane, acc[I][J]);
+#pragma unroll
+            for (int J = 0; J < MT; ++J) {
+                const double v = red_t(afp[J]);
+                if (t == 0) vafb[8 * J + g] = v;
+            }
         }
-        // afbar = T^T abar ; gc += abar
-#pragma unroll
-        for (int J = 0; J < MT; ++J) {
-            double c0 = 0.0, c1 = 0.0;
-#pragma unroll
-            for (int I = 0; I < MT; ++I) {
-                const double2 tf = ldg_tile(Tg, m, I, J, lane);
-                const double ab = vab[8 * I + g];
-                c0 = fma(tf.x, ab, c0);
-                c1 = fma(tf.y, ab, c1);
-            }
-            c0 = red_g(c0);
-            c1 = red_g(c1);
-            if (g == 0) {
-                vafb[8 * J + 2 * t] = c0;
-                vafb[8 * J + 2 * t + 1] = c1;
-            }
-        }
+        // gc += abar
         for (int i = lane; i < m; i += 32) vgc[i] += vab[i];
         __syncwarp();
         if (flag) {  // degenerate branch (:700-705): (a_f, Pcf, ll) = (a, Pc, 0)
@@ -1057,9 +1147,9 @@ __global__ void __launch_bounds__(32) backward_kernel(KArgs<double> G) {
         static_assert(NT1 + MT * PT <= BD::NTRI, "A21 scratch");
 #pragma unroll
         for (int I = 0; I < MT; ++I) {
-            double2 acc[PT];
+            Acc2 acc[PT];
 #pragma unroll
-            for (int J = 0; J < PT; ++J) acc[J] = zero2();
+            for (int J = 0; J < PT; ++J) acc[J] = acc2_zero();
 #pragma unroll
             for (int K = 0; K < MT; ++K)
                 if (dense_pc || K >= I) {
@@ -1074,15 +1164,15 @@ __global__ void __launch_bounds__(32) backward_kernel(KArgs<double> G) {
                     }
                 }
 #pragma unroll
-            for (int J = 0; J < PT; ++J) stt(RB, A21T + I * PT + J, lane, acc[J]);
+            for (int J = 0; J < PT; ++J) stt(RB, A21T + I * PT + J, lane, fin(acc[J]));
         }
         __syncwarp();
         // Abar11 = Hc^T Psi11  (accumulated: Hcbar^T)
 #pragma unroll
         for (int I = 0; I < PT; ++I) {
-            double2 acc[PT];
+            Acc2 acc[PT];
 #pragma unroll
-            for (int J = 0; J < PT; ++J) acc[J] = ldt(HBT, I * PT + J, lane);
+            for (int J = 0; J < PT; ++J) acc[J] = acc2_from(ldt(HBT, I * PT + J, lane));
 #pragma unroll
             for (int K = I; K < PT; ++K) {
                 double2 h = ttrans(ldt(HC, K * PT + I, lane), lane);  // (Hc^T)[I][K]
@@ -1092,27 +1182,30 @@ __global__ void __launch_bounds__(32) backward_kernel(KArgs<double> G) {
                 for (int J = 0; J < PT; ++J) mma_nt(acc[J], h, ldt(W, J * NT1 + K, lane));
             }
 #pragma unroll
-            for (int J = 0; J < PT; ++J) stt(HBT, I * PT + J, lane, acc[J]);
+            for (int J = 0; J < PT; ++J) stt(HBT, I * PT + J, lane, fin(acc[J]));
         }
         // rows of [Abar21, Abar22]; Abar21 -> RF[0 ..) (the factor is dead), Pbar^T = Abar22 + Abar21 Zm -> PBT
 #pragma unroll
         for (int I = 0; I < MT; ++I) {
-            double2 acc[NT1];
+            Acc2 acc2[NT1];
 #pragma unroll
-            for (int J = 0; J < NT1; ++J) acc[J] = zero2();
+            for (int J = 0; J < NT1; ++J) acc2[J] = acc2_zero();
 #pragma unroll
             for (int K = 0; K < NT1; ++K)
                 if (K < PT || dense_pc || K - PT >= I) {
                     const double2 ak = K < PT ? ldt(RB, A21T + I * PT + (K < PT ? K : 0), lane)
                                               : ldg_tile_t(Pcg, m, I, K >= PT ? K - PT : 0, lane);
 #pragma unroll
-                    for (int J = 0; J < NT1; ++J) mma_nt(acc[J], ak, ldt(W, J * NT1 + K, lane));
+                    for (int J = 0; J < NT1; ++J) mma_nt(acc2[J], ak, ldt(W, J * NT1 + K, lane));
                 }
+            double2 acc[NT1];
+#pragma unroll
+            for (int J = 0; J < NT1; ++J) acc[J] = fin(acc2[J]);
 #pragma unroll
             for (int J = 0; J < PT; ++J) stt(RF, I * PT + J, lane, acc[J]);
 #pragma unroll
             for (int J = 0; J < MT; ++J) {
-                double2 pb = acc[PT + J];
+                Acc2 pb = acc2_from(acc[PT + J]);
 #pragma unroll
                 for (int K = 0; K < PT; ++K) {
                     double2 zt = ldg_tile_t(Zg, m, J, K, lane);  // (Zm^T)[J][K]: [g][2t+e] = Zm[8K+2t+e][8J+g]
@@ -1120,27 +1213,35 @@ __global__ void __launch_bounds__(32) backward_kernel(KArgs<double> G) {
                     zt.y *= vw[8 * K + 2 * t + 1];
                     mma_nt(pb, acc[K], zt);
                 }
-                stt(PBT, I * MT + J, lane, pb);
+                stt(PBT, I * MT + J, lane, fin(pb));
             }
         }
         __syncwarp();
         // gZ += W (ZPbar Pc^T - vbar a^T),  ZPbar = Abar21^T
         if (G.g_Z) {
+            double2 zp[PT][MT];
 #pragma unroll
-            for (int Io = 0; Io < PT; ++Io) {
-                double2 zp[MT];
+            for (int Io = 0; Io < PT; ++Io)
 #pragma unroll
-                for (int K = 0; K < MT; ++K) zp[K] = ttrans(ldt(RF, K * PT + Io, lane), lane);
-                const double wo = vw[8 * Io + g], vb = vvb[8 * Io + g];
+                for (int K = 0; K < MT; ++K) zp[Io][K] = ttrans(ldt(RF, K * PT + Io, lane), lane);
 #pragma unroll
-                for (int J = 0; J < MT; ++J) {
-                    double2 acc = zero2();
+            for (int J = 0; J < MT; ++J) {
+                double2 acc[PT];
 #pragma unroll
-                    for (int K = 0; K < MT; ++K)
-                        if (dense_pc || K <= J) mma_nt(acc, zp[K], ldg_tile(Pcg, m, J, K, lane));
+                for (int Io = 0; Io < PT; ++Io) acc[Io] = zero2();
+#pragma unroll
+                for (int K = 0; K < MT; ++K)
+                    if (dense_pc || K <= J) {
+                        const double2 pc = ldg_tile(Pcg, m, J, K, lane);
+#pragma unroll
+                        for (int Io = 0; Io < PT; ++Io) mma_nt(acc[Io], zp[Io][K], pc);
+                    }
+#pragma unroll
+                for (int Io = 0; Io < PT; ++Io) {
+                    const double wo = vw[8 * Io + g], vb = vvb[8 * Io + g];
                     double2 gz = ldrw_tile(gZ, m, Io, J, lane);
-                    gz.x = fma(wo, fma(-vb, va[8 * J + 2 * t], acc.x), gz.x);
-                    gz.y = fma(wo, fma(-vb, va[8 * J + 2 * t + 1], acc.y), gz.y);
+                    gz.x = fma(wo, fma(-vb, va[8 * J + 2 * t], acc[Io].x), gz.x);
+                    gz.y = fma(wo, fma(-vb, va[8 * J + 2 * t + 1], acc[Io].y), gz.y);
                     stg_tile(gZ, m, Io, J, lane, gz);
                 }
             }
