@@ -1,8 +1,9 @@
-// bkf_sqrt_warp.cu -- launchers of the warp-per-series SquareRootFilter kernels (bkf_sqrt_warp.cuh).
+// bkf_sqrt_warp.cu -- dispatch of the warp-per-series SquareRootFilter kernels (bkf_sqrt_warp.cuh).  The kernels are
+// instantiated per shape (m/8, p/8, r/8) in bkf_sqrt_warp_inst_*.cu so that the shapes compile in parallel.
 #include <cstdlib>
 
 #include "bkf_launch.h"
-#include "bkf_sqrt_warp.cuh"
+#include "bkf_sqrt_warp_launch.cuh"
 
 namespace bkf {
 namespace sqw {
@@ -16,8 +17,13 @@ static int enabled_mask() {
     return mask;
 }
 
+#define BKF_SQW_SHAPES(X) X(1, 1, 1) X(2, 1, 1) X(3, 1, 1) X(4, 1, 1) X(2, 2, 1) X(2, 2, 2) X(4, 2, 2)
+
 static bool shape_ok(int m, int p, int r) {
-    return (m == 32 && p == 16 && r == 16) || (m == 16 && p == 8 && r == 8) || (m == 16 && p == 16 && r == 8);
+#define X(MT, PT, RT) if (m == 8 * MT && p == 8 * PT && r == 8 * RT) return true;
+    BKF_SQW_SHAPES(X)
+#undef X
+    return false;
 }
 
 bool supported(const KArgs<double>& g, bool backward) {
@@ -28,24 +34,10 @@ bool supported(const KArgs<double>& g, bool backward) {
     return !(g.filt_a || g.pred_a || g.obs_mu || g.filt_P || g.pred_P || g.obs_cov);
 }
 
-template <int MT, int PT, int RT>
-static int launch_t(const KArgs<double>& g, bool backward, cudaStream_t stream, const char** err) {
-    using D = Dims<MT, PT, RT>;
-    using BD = BDims<MT, PT, RT>;
-    const size_t bytes = (size_t)(backward ? BD::ELEMS : D::FWD_ELEMS) * sizeof(double);
-    auto kern = backward ? backward_kernel<MT, PT, RT> : forward_kernel<MT, PT, RT>;
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
-    if (e != cudaSuccess) { *err = cudaGetErrorString(e); return BKF_ERR_CUDA; }
-    kern<<<g.B, 32, bytes, stream>>>(g);
-    e = cudaGetLastError();
-    if (e != cudaSuccess) { *err = cudaGetErrorString(e); return BKF_ERR_CUDA; }
-    return BKF_OK;
-}
-
 int launch_f64(const KArgs<double>& g, bool backward, cudaStream_t stream, const char** err) {
-    if (g.m == 32 && g.p == 16 && g.r == 16) return launch_t<4, 2, 2>(g, backward, stream, err);
-    if (g.m == 16 && g.p == 8 && g.r == 8) return launch_t<2, 1, 1>(g, backward, stream, err);
-    if (g.m == 16 && g.p == 16 && g.r == 8) return launch_t<2, 2, 1>(g, backward, stream, err);
+#define X(MT, PT, RT) if (g.m == 8 * MT && g.p == 8 * PT && g.r == 8 * RT) return launch_t<MT, PT, RT>(g, backward, stream, err);
+    BKF_SQW_SHAPES(X)
+#undef X
     *err = "shape not instantiated for the warp-per-series square-root kernels";
     return BKF_ERR_UNSUPPORTED;
 }

@@ -770,10 +770,15 @@ struct BDims {
     using D = Dims<MT, PT, RT>;
     static constexpr int m = D::m, p = D::p, NT1 = D::NT1;
     static constexpr int NTRI = NT1 * (NT1 + 1) / 2;
-    static constexpr int W = 0;                           // NT1 x NT1 tiles: Psi work array
-    static constexpr int RF = W + NT1 * NT1 * 64;         // factor tiles (upper)
-    static constexpr int RB = RF + NTRI * 64;             // cotangent tiles (upper); also RINV / scratch
-    static constexpr int PBT = RB + NTRI * 64;            // carried Pbar^T, MT x MT tiles
+    static constexpr int cmax(int a, int b) { return a > b ? a : b; }
+    // tile counts: the arrays double as scratch for the products of the predict / update adjoints (see the kernel)
+    static constexpr int WTILES = cmax(NT1 * NT1, 2 * MT * MT);                       // Psi | Psi_p + TP^T / U1
+    static constexpr int RFTILES = cmax(NTRI, MT * PT);                               // factor | Abar21
+    static constexpr int RBTILES = cmax(cmax(NTRI, MT * MT), NT1 + MT * PT);          // Rbar | RINV + A21 | U1^T
+    static constexpr int W = 0;                           // Psi work array
+    static constexpr int RF = W + WTILES * 64;            // factor tiles (upper)
+    static constexpr int RB = RF + RFTILES * 64;          // cotangent tiles (upper); also RINV / scratch
+    static constexpr int PBT = RB + RBTILES * 64;         // carried Pbar^T, MT x MT tiles
     static constexpr int HC = PBT + MT * MT * 64;         // Hc tiles
     static constexpr int HBT = HC + PT * PT * 64;         // sum of Abar11 (= Hcbar^T)
     static constexpr int VA = HBT + PT * PT * 64;
@@ -781,8 +786,8 @@ struct BDims {
                          V_s = V_v + p, V_in = V_s + p, V_w = V_in + p, V_ym = V_w + p, V_vb = V_ym + p, V_sb = V_vb + p,
                          V_t1 = V_sb + p, V_t2 = V_t1 + p, V_gd = V_t2 + p, V_d = V_gd + p;
     static constexpr int ELEMS = V_d + p;
-    static_assert(MT * MT <= NTRI && MT * PT <= NTRI, "scratch tiles must fit the factor arrays");
-    static_assert(2 * MT * MT <= NT1 * NT1, "predict adjoint scratch must fit the Psi work array");
+    // epilogue scratch (row-major) laid over W, RF, RB
+    static_assert((WTILES + RFTILES + RBTILES) * 64 >= cmax(5 * p * p, 6 * D::r * D::r + 2 * m * D::r), "epilogue scratch");
 };
 
 template <int MT, int PT, int RT>
@@ -1144,7 +1149,6 @@ __global__ void __launch_bounds__(32) backward_kernel(KArgs<double> G) {
         psi_tiles<NT1>(W, RF, RB, [&](int J, int K) { return ldt(RB, tri<NT1>(J, K), lane); }, lane);
         // ---- Abar = A Psi, A = [[Hc^T, 0], [A21, Pc^T]],  A21 = (Zm Pc)^T = Pc^T Zm^T -> RB[NT1 ..) ----
         constexpr int A21T = NT1;  // behind RINV
-        static_assert(NT1 + MT * PT <= BD::NTRI, "A21 scratch");
 #pragma unroll
         for (int I = 0; I < MT; ++I) {
             Acc2 acc[PT];

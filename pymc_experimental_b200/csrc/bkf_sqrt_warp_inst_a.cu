@@ -1,0 +1,9 @@
+// bkf_sqrt_warp_inst_a.cu -- instantiations of the warp-per-series SquareRootFilter kernels (m/8, p/8, r/8).
+#define BKF_SQW_DEFINE_LAUNCH
+#include "bkf_sqrt_warp_launch.cuh"
+
+namespace bkf {
+namespace sqw {
+template int launch_t<4, 2, 2>(const KArgs<double>&, bool, cudaStream_t, const char**);
+}  // namespace sqw
+}  // namespace bkf

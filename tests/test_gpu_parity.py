@@ -180,8 +180,12 @@ def test_subwarp_kernels_all_sizes(eng, m):
                 _close(grads[k][b], ref_g[k][b], RTOL64, f"{kind} m={m} d/d{k}[{b}]")
 
 
+# shapes (m, p, r) instantiated for the warp-per-series DMMA square-root kernels (bkf_sqrt_warp.cu)
+SQRT_WARP_SHAPES = ((8, 8, 8), (16, 8, 8), (24, 8, 8), (32, 8, 8), (16, 16, 8), (16, 16, 16), (32, 16, 16))
+
+
 @pytest.mark.parametrize("shape", [(2, 1, 2), (5, 2, 3), (8, 3, 2), (12, 4, 4), (6, 6, 3), (8, 8, 8), (16, 8, 8),
-                                   (16, 16, 8), (24, 8, 16), (32, 16, 16)])
+                                   (24, 8, 8), (32, 8, 8), (16, 16, 8), (16, 16, 16), (24, 8, 16), (32, 16, 16)])
 @pytest.mark.parametrize("missing", [0.0, 0.2])
 def test_square_root_filter_batched_logp_grad(eng, shape, missing):
     """SquareRootFilter forward + QR adjoint (P0 is a factor; H, Q gradients in the lower-triangular convention)."""
@@ -203,12 +207,57 @@ def test_square_root_filter_batched_logp_grad(eng, shape, missing):
         _close(got, want.numpy(), RTOL64, "cholesky forward")
     logp, grads, status = eng.logp_grad("cholesky", *args)
     # float64 shapes made of whole 8 x 8 tiles run the warp-per-series DMMA kernels, everything else the CTA ones
-    assert eng.last_path == ("sqrt_warp_dmma" if shape in ((16, 8, 8), (16, 16, 8), (32, 16, 16)) else "sqrt_cta")
+    assert eng.last_path == ("sqrt_warp_dmma" if shape in SQRT_WARP_SHAPES else "sqrt_cta")
     ref_logp, ref_g = oth.logp_and_grad("cholesky", *args)
     assert_allclose(logp, ref_logp, rtol=RTOL64)
     for k in NAMES:
         for b in range(B):
             _close(grads[k][b], ref_g[k][b], 1e-8, f"cholesky d/d{k}[{b}]")
+
+
+@pytest.mark.parametrize("case", ["dense_P0", "H_zero", "cotangent", "shared_params"])
+def test_square_root_warp_kernels_corner_cases(eng, case):
+    """Branches of the warp-per-series square-root kernels the main sweep does not reach: a factor P0 that is not
+    triangular (only the first step sees it), H == 0 (the reference then skips cholesky(H), kalman_filter.py:666),
+    a non-trivial log-likelihood cotangent, and parameters shared across the batch."""
+    from oracle import kalman_torch as oth
+    from pymc_experimental_b200 import synth
+
+    m, p, r = 16, 8, 8
+    B, n = 5, 9
+    cfg = synth.random_dense(B, n, m, p, r, seed=77, missing=0.0)
+    cfg["y"][1, 3] = np.nan  # one skipped step
+    cfg["P0"] = np.linalg.cholesky(cfg["P0"])
+    kw = {}
+    if case == "dense_P0":
+        cfg["P0"] = cfg["P0"] + 0.1 * np.random.default_rng(5).normal(size=cfg["P0"].shape)
+    elif case == "H_zero":
+        cfg["H"] = np.zeros_like(cfg["H"])
+    elif case == "cotangent":
+        kw["ll_cotangent"] = np.random.default_rng(6).normal(size=(B, n))
+    full = {k: cfg[k] for k in NAMES}
+    if case == "shared_params":  # the engine returns per-series gradients also for a parameter passed once
+        for k in ("Z", "R", "c", "d"):
+            cfg[k] = cfg[k][0]
+            full[k] = np.ascontiguousarray(np.broadcast_to(cfg[k], (B,) + cfg[k].shape))
+    args = [cfg["y"]] + [cfg[k] for k in NAMES]
+    logp, grads, status = eng.logp_grad("cholesky", *args, **kw)
+    assert eng.last_path == "sqrt_warp_dmma"
+    ref_logp, ref_g = oth.logp_and_grad("cholesky", cfg["y"], *[full[k] for k in NAMES], **kw)
+    assert_allclose(logp, ref_logp, rtol=RTOL64)
+    # H == 0 with p observed series makes the filtered covariance exactly singular: its factor is jitter-sized (1e-8) in p
+    # directions, and the QR pull-back (R^{-1} ... R^{-T}) amplifies rounding by that ratio in BOTH implementations
+    # (measured: up to 3e-6 relative between this kernel and autograd through the oracle, 2e-5 for the CTA kernels).
+    # d logp / dH is exactly zero there -- the rows of the QR input that hold H are zero, so R^T R = A^T A does not
+    # move at first order -- and the oracle's value is rounding noise (1e-9 of the other gradients' scale).
+    tol = 1e-4 if case == "H_zero" else 1e-8
+    for k in NAMES:
+        if case == "H_zero" and k == "H":
+            assert np.all(grads[k] == 0.0)
+            assert np.abs(ref_g[k]).max() < 1e-6 * max(np.abs(ref_g[j]).max() for j in NAMES)
+            continue
+        for b in range(B):
+            _close(grads[k][b], ref_g[k][b], tol, f"{case} d/d{k}[{b}]")
 
 
 def test_ll_cotangent_is_respected(eng):

@@ -25,7 +25,7 @@ if __name__ == "__main__":
         run(tuple(json.loads(sys.argv[2])), float(sys.argv[3]), sys.argv[4])
         sys.exit(0)
     modes = sys.argv[1:] or ["1"]
-    for shape in [(16, 8, 8), (16, 16, 8), (32, 16, 16)]:
+    for shape in [(8, 8, 8), (16, 8, 8), (24, 8, 8), (32, 8, 8), (16, 16, 8), (16, 16, 16), (32, 16, 16)]:
         for missing in (0.0, 0.2):
             res = {}
             for mode in ["0"] + modes:
