@@ -174,21 +174,21 @@ __device__ __forceinline__ void qr_panel(double* __restrict__ S, const int jt, c
         nrm = fma(fma(-nrm, nrm, x2), 0.5 * rn, nrm);
         const double den = fabs(alpha) + nrm;
         const double rden = rcp_nr(den);
-        const double beta = alpha >= 0.0 ? -nrm : nrm;
+        const double beta = copysign(nrm, -alpha);
         const double tau = den * rn;
-        const double scal = alpha >= 0.0 ? rden : -rden;
+        const double scal = copysign(rden, alpha);
         const double zz = fma(scal, dot, akc);  // v_k . a_c  (c > k)   or   v_i . v_k  (i < k)
         // column update a_c -= w v (c > k); the pivot column itself becomes v = x scal, written as x - w_k v with
-        // w_k = 1 / scal - 1 = (alpha - beta) - 1 so that every lane runs the same FMA
-        const double w = g > k ? tau * zz : (g == k ? (alpha - beta) - 1.0 : 0.0);
+        // w_k = 1 / scal - 1 = (alpha - beta) - 1 so that every lane runs the same FMA (rows above the pivot see v = 0)
+        const bool piv = g == k;
+        const double w = g > k ? tau * zz : (piv ? (alpha - beta) - 1.0 : 0.0);
         double2 vd = make_double2(xm.x * scal, xm.y * scal);  // v on my rows (unit at row k)
         if (2 * t == k) vd.x = 1.0;
         if (2 * t + 1 == k) vd.y = 1.0;
         {
             const double nx = fma(-w, vd.x, pa[0].x), ny = fma(-w, vd.y, pa[0].y);
-            const bool piv = g == k;
-            pa[0].x = piv ? (2 * t > k ? vd.x : (2 * t == k ? beta : pa[0].x)) : nx;
-            pa[0].y = piv ? (2 * t + 1 > k ? vd.y : (2 * t + 1 == k ? beta : pa[0].y)) : ny;
+            pa[0].x = (piv && 2 * t == k) ? beta : nx;
+            pa[0].y = (piv && 2 * t + 1 == k) ? beta : ny;
         }
 #pragma unroll
         for (int q = 1; q < NQ; ++q) {
