@@ -136,9 +136,15 @@ __device__ __forceinline__ double rcp_nr(double x) {
 
 // One panel (8 columns, NQ active row blocks, the diagonal block first) of the Householder sweep and its trailing update.
 // tile(jt, rt) -> tile index.  The reflector loop is rolled (runtime k): see qr_tiles.
-template <int NQ, class TileF>
-__device__ __forceinline__ void qr_panel(double* __restrict__ S, const int jt, const int np, TileF tile, const int lane) {
+template <int NQ, int WT, class ColF>
+__device__ __forceinline__ void qr_panel(double* __restrict__ S, const int jt, const int np, const int row0, ColF colf,
+                                         const int lane) {
     const int g = lane >> 2, t = lane & 3;
+    // tile (column block j, active row block q) = (row0 + j) * WT + col[q]: the column part is fixed for the panel
+    int col[NQ];
+#pragma unroll
+    for (int q = 0; q < NQ; ++q) col[q] = colf(jt + q);
+    auto tile = [&](int j, int rt) { return (row0 + j) * WT + col[rt - jt]; };
     double2 pa[NQ];
 #pragma unroll
     for (int q = 0; q < NQ; ++q) pa[q] = ldt(S, tile(jt, jt + q), lane);
@@ -259,20 +265,19 @@ __device__ __forceinline__ void qr_panel(double* __restrict__ S, const int jt, c
 template <int NRMAX, int MT, int PT, int WT>
 __device__ __noinline__ void qr_tiles(double* __restrict__ S, const int np, const int nr, const bool predict,
                                       const int lane) {
-    auto tile = [&](int jt, int rt) {
-        return predict ? (PT + jt) * WT + (rt < MT ? PT + rt : rt - MT) : jt * WT + rt;
-    };
+    const int row0 = predict ? PT : 0;
+    auto colf = [&](int rt) { return predict ? (rt < MT ? PT + rt : rt - MT) : rt; };
 #pragma unroll 1
     for (int jt = 0; jt < np; ++jt) {
         switch (nr - jt) {
-            case 1: qr_panel<1>(S, jt, np, tile, lane); break;
-            case 2: if constexpr (NRMAX >= 2) qr_panel<2>(S, jt, np, tile, lane); break;
-            case 3: if constexpr (NRMAX >= 3) qr_panel<3>(S, jt, np, tile, lane); break;
-            case 4: if constexpr (NRMAX >= 4) qr_panel<4>(S, jt, np, tile, lane); break;
-            case 5: if constexpr (NRMAX >= 5) qr_panel<5>(S, jt, np, tile, lane); break;
-            case 6: if constexpr (NRMAX >= 6) qr_panel<6>(S, jt, np, tile, lane); break;
-            case 7: if constexpr (NRMAX >= 7) qr_panel<7>(S, jt, np, tile, lane); break;
-            case 8: if constexpr (NRMAX >= 8) qr_panel<8>(S, jt, np, tile, lane); break;
+            case 1: qr_panel<1, WT>(S, jt, np, row0, colf, lane); break;
+            case 2: if constexpr (NRMAX >= 2) qr_panel<2, WT>(S, jt, np, row0, colf, lane); break;
+            case 3: if constexpr (NRMAX >= 3) qr_panel<3, WT>(S, jt, np, row0, colf, lane); break;
+            case 4: if constexpr (NRMAX >= 4) qr_panel<4, WT>(S, jt, np, row0, colf, lane); break;
+            case 5: if constexpr (NRMAX >= 5) qr_panel<5, WT>(S, jt, np, row0, colf, lane); break;
+            case 6: if constexpr (NRMAX >= 6) qr_panel<6, WT>(S, jt, np, row0, colf, lane); break;
+            case 7: if constexpr (NRMAX >= 7) qr_panel<7, WT>(S, jt, np, row0, colf, lane); break;
+            case 8: if constexpr (NRMAX >= 8) qr_panel<8, WT>(S, jt, np, row0, colf, lane); break;
             default: break;
         }
     }
