@@ -29,9 +29,7 @@ static bool shape_ok(int m, int p, int r) {
 bool supported(const KArgs<double>& g, bool backward) {
     if (g.kind != BKF_CHOLESKY || g.tv_mask || !shape_ok(g.m, g.p, g.r)) return false;
     if (!((enabled_mask() >> (backward ? 1 : 0)) & 1)) return false;
-    if (backward) return g.traj != nullptr;
-    // the forward sweep of this family only produces the log-likelihood and the adjoint's record
-    return !(g.filt_a || g.pred_a || g.obs_mu || g.filt_P || g.pred_P || g.obs_cov);
+    return backward ? g.traj != nullptr : true;
 }
 
 int launch_f64(const KArgs<double>& g, bool backward, cudaStream_t stream, const char** err) {

@@ -394,6 +394,24 @@ __device__ __forceinline__ void store_packed_upper(double* __restrict__ dst, con
         }
 }
 
+// dst (row-major n x n, n = 8 NT) = L L^T for a factor given as tiles L(I, K)  (_postprocess_scan_results, :733-740)
+template <int NT, class TileF>
+__device__ __forceinline__ void store_square(double* __restrict__ dst, TileF L, int lane) {
+#pragma unroll
+    for (int I = 0; I < NT; ++I) {
+        double2 li[NT];
+#pragma unroll
+        for (int K = 0; K < NT; ++K) li[K] = L(I, K);
+#pragma unroll
+        for (int J = 0; J < NT; ++J) {
+            double2 acc = zero2();
+#pragma unroll
+            for (int K = 0; K < NT; ++K) mma_nt(acc, li[K], L(J, K));
+            stg_tile(dst, 8 * NT, I, J, lane, acc);
+        }
+    }
+}
+
 template <int MT, int PT, int RT>
 __global__ void __launch_bounds__(32) forward_kernel(KArgs<double> G) {
     using D = Dims<MT, PT, RT>;
@@ -451,6 +469,10 @@ __global__ void __launch_bounds__(32) forward_kernel(KArgs<double> G) {
 #pragma unroll
                 for (int J = 0; J < MT; ++J) stg_tile(rec + m, m, I, J, lane, ldt(SA, D::pc_tile(I, J), lane));
         }
+        if (G.pred_a)
+            for (int i = lane; i < m; i += 32) G.pred_a[bt * m + i] = va[i];
+        if (G.pred_P)
+            store_square<MT>(G.pred_P + bt * m * m, [&](int I, int K) { return ldt(SA, D::pc_tile(I, K), lane); }, lane);
         double2 zf[PT][MT];
 #pragma unroll
         for (int I = 0; I < PT; ++I) {
@@ -472,6 +494,9 @@ __global__ void __launch_bounds__(32) forward_kernel(KArgs<double> G) {
             }
         }
         __syncwarp();
+        if (G.obs_mu && lane < p) G.obs_mu[bt * p + lane] = vsv[lane];
+        if (G.obs_cov && flag)  // every observation missing: the masked array has zero columns there, F_chol = 0
+            for (int i = lane; i < p * p; i += 32) G.obs_cov[bt * p * p + i] = 0.0;
         double ll = 0.0;
         if (!flag) {
             // ---- update array (transposed): [[Hc, Zm Pc], [0, Pc]] ----
@@ -506,6 +531,8 @@ __global__ void __launch_bounds__(32) forward_kernel(KArgs<double> G) {
             qr_tiles<D::NT1, MT, PT, WT>(SA, D::NT1, D::NT1, false, lane);
             if (rec)
                 store_packed_upper<D::NT1>(rec + off_rf, SA, lane, [](int I, int J) { return I * WT + J; });
+            if (G.obs_cov)  // F = Fc Fc^T, Fc = B[:p,:p]
+                store_square<PT>(G.obs_cov + bt * p * p, [&](int I, int K) { return ldt(SA, I * WT + K, lane); }, lane);
             // ---- s = Fc^{-1} v, inner = Fc^{-1} s  (Fc = B[:p,:p], lower), lane q owns x[q] ----
             {
                 const int q = lane < p ? lane : p - 1;
@@ -551,6 +578,10 @@ __global__ void __launch_bounds__(32) forward_kernel(KArgs<double> G) {
             for (int I = 0; I < MT; ++I) SA[D::pc_tile(I, I) * 64 + lane * 2 + (g & 1)] += G.jitter;
         }
         __syncwarp();
+        if (G.filt_a)
+            for (int i = lane; i < m; i += 32) G.filt_a[bt * m + i] = vaf[i];
+        if (G.filt_P)
+            store_square<MT>(G.filt_P + bt * m * m, [&](int I, int K) { return ldt(SA, D::pc_tile(I, K), lane); }, lane);
         if (G.ll && lane == 0) G.ll[bt] = ll;
         logp += ll;
         // ---- predict array (transposed) [T Pcf, R Qc]; a+ = T a_f + c ----
