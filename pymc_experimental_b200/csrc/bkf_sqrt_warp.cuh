@@ -137,8 +137,8 @@ __device__ __forceinline__ double rcp_nr(double x) {
 // One panel (8 columns, NQ active row blocks, the diagonal block first) of the Householder sweep and its trailing update.
 // tile(jt, rt) -> tile index.  The reflector loop is rolled (runtime k): see qr_tiles.
 template <int NQ, int WT, class ColF>
-__device__ __forceinline__ void qr_panel(double* __restrict__ S, const int jt, const int np, const int row0, ColF colf,
-                                         const int lane) {
+__device__ __forceinline__ void qr_panel(double* __restrict__ S, double* __restrict__ tq, const int jt, const int np,
+                                         const int row0, ColF colf, const int lane) {
     const int g = lane >> 2, t = lane & 3;
     // tile (column block j, active row block q) = (row0 + j) * WT + col[q]: the column part is fixed for the panel
     int col[NQ];
@@ -148,7 +148,7 @@ __device__ __forceinline__ void qr_panel(double* __restrict__ S, const int jt, c
     double2 pa[NQ];
 #pragma unroll
     for (int q = 0; q < NQ; ++q) pa[q] = ldt(S, tile(jt, jt + q), lane);
-    double2 tt = zero2();  // T^T in C layout: lane (g = j, t) holds T[2t][j], T[2t+1][j]
+    double tauv = 0.0;  // tau of the reflector of column g (0: H = I)
 #pragma unroll 1
     for (int k = 0; k < 8; ++k) {
         // x = column k of the panel below its diagonal, handed to every group (lane (k, t) -> lanes (*, t))
@@ -167,12 +167,12 @@ __device__ __forceinline__ void qr_panel(double* __restrict__ S, const int jt, c
             d0 = fma(xb[q].x, pa[q].x, d0);
             d1 = fma(xb[q].y, pa[q].y, d1);
         }
-        // one reduction window: group k -> ss = x.x; group c > k -> x.a_c; group i < k -> x.v_i (for T)
+        // one reduction window: group k -> ss = x.x; group c > k -> x.a_c
         const double dot = red_t(d0 + d1);
         const double ss = __shfl_sync(FULL, dot, 4 * k);
         const double akc = __shfl_sync(FULL, (k & 1) ? pa[0].y : pa[0].x, 4 * g + (k >> 1));  // [row k][col g]
         const double alpha = __shfl_sync(FULL, akc, 4 * k);
-        if (ss == 0.0) continue;  // dlarfg: tau = 0, H = I (column k of T stays zero)
+        if (ss == 0.0) continue;  // dlarfg: tau = 0, H = I
         // beta = -sign(alpha) nrm,  tau = (beta - alpha) / beta = (|alpha| + nrm) / nrm,  scal = 1 / (alpha - beta)
         const double x2 = fma(alpha, alpha, ss);
         const double rn = rsqrt_nr(x2);
@@ -183,7 +183,7 @@ __device__ __forceinline__ void qr_panel(double* __restrict__ S, const int jt, c
         const double beta = copysign(nrm, -alpha);
         const double tau = den * rn;
         const double scal = copysign(rden, alpha);
-        const double zz = fma(scal, dot, akc);  // v_k . a_c  (c > k)   or   v_i . v_k  (i < k)
+        const double zz = fma(scal, dot, akc);  // v_k . a_c  (c > k)
         // column update a_c -= w v (c > k); the pivot column itself becomes v = x scal, written as x - w_k v with
         // w_k = 1 / scal - 1 = (alpha - beta) - 1 so that every lane runs the same FMA (rows above the pivot see v = 0)
         const bool piv = g == k;
@@ -201,13 +201,7 @@ __device__ __forceinline__ void qr_panel(double* __restrict__ S, const int jt, c
             pa[q].x = fma(-w, xb[q].x * scal, pa[q].x);
             pa[q].y = fma(-w, xb[q].y * scal, pa[q].y);
         }
-        // dlarft, column k:  T[0:k, k] = -tau T[0:k, 0:k] z,  z_i = v_i . v_k ;  T[k][k] = tau
-        const double cz = g < k ? zz : 0.0;
-        const double s0 = red_g(tt.x * cz), s1 = red_g(tt.y * cz);
-        if (g == k) {
-            tt.x = 2 * t < k ? -tau * s0 : (2 * t == k ? tau : 0.0);
-            tt.y = 2 * t + 1 < k ? -tau * s1 : (2 * t + 1 == k ? tau : 0.0);
-        }
+        if (piv) tauv = tau;
     }
     // R goes back to the array (zeros below the diagonal); V^T (unit diagonal) stays in registers (in pa)
     {
@@ -219,6 +213,35 @@ __device__ __forceinline__ void qr_panel(double* __restrict__ S, const int jt, c
 #pragma unroll
     for (int q = 1; q < NQ; ++q) stt(S, tile(jt, jt + q), lane, zero2());
     if (jt + 1 < np) {
+        // Compact-WY factor (dlarft) from the Gram matrix of the reflectors:  T^{-1} = striu(V^T V) + diag(1 / tau), so
+        // column j of T solves  x_i = tau_i (delta_ij - sum_{l > i} G_il x_l)  by back substitution -- no division, a
+        // reflector with tau = 0 gives a zero row and column.  G = V^T V is two short DMMA chains; group j solves column j
+        // with broadcast reads of G (all lanes read the same word).  Doing this once per panel instead of one
+        // three-stage shuffle reduction per reflector takes the T factor off the serial reflector chain.
+        double2 tt;  // T^T in C layout: lane (g = j, t) holds T[2t][j], T[2t+1][j]
+        {
+            double2 ga = zero2(), gb = zero2();
+#pragma unroll
+            for (int q = 0; q < NQ; ++q) {
+                dmma(ga.x, ga.y, pa[q].x, pa[q].x);
+                dmma(gb.x, gb.y, pa[q].y, pa[q].y);
+            }
+            reinterpret_cast<double2*>(tq)[lane] = make_double2(ga.x + gb.x, ga.y + gb.y);  // G, row-major 8 x 8
+            if (t == 0) tq[64 + g] = tauv;
+            __syncwarp();
+            double x[8];
+#pragma unroll
+            for (int i = 7; i >= 0; --i) {
+                double acc = 0.0;
+#pragma unroll
+                for (int l = 7; l > i; --l) acc = fma(tq[i * 8 + l], x[l], acc);
+                const double ti = tq[64 + i];
+                x[i] = i == g ? ti : (i < g ? -ti * acc : 0.0);
+            }
+            tt.x = t == 0 ? x[0] : (t == 1 ? x[2] : (t == 2 ? x[4] : x[6]));
+            tt.y = t == 0 ? x[1] : (t == 1 ? x[3] : (t == 2 ? x[5] : x[7]));
+            __syncwarp();
+        }
         double2 vv[NQ];
 #pragma unroll
         for (int q = 0; q < NQ; ++q) vv[q] = ttrans(pa[q], lane);
@@ -263,21 +286,21 @@ __device__ __forceinline__ void qr_panel(double* __restrict__ S, const int jt, c
 // One copy of the code per number of active row blocks, panel and reflector loops rolled: a fully unrolled sweep is
 // ~200 KB of SASS, which the 32 KB instruction cache cannot hold with one warp per scheduler.
 template <int NRMAX, int MT, int PT, int WT>
-__device__ __noinline__ void qr_tiles(double* __restrict__ S, const int np, const int nr, const bool predict,
-                                      const int lane) {
+__device__ __noinline__ void qr_tiles(double* __restrict__ S, double* __restrict__ tq, const int np, const int nr,
+                                      const bool predict, const int lane) {
     const int row0 = predict ? PT : 0;
     auto colf = [&](int rt) { return predict ? (rt < MT ? PT + rt : rt - MT) : rt; };
 #pragma unroll 1
     for (int jt = 0; jt < np; ++jt) {
         switch (nr - jt) {
-            case 1: qr_panel<1, WT>(S, jt, np, row0, colf, lane); break;
-            case 2: if constexpr (NRMAX >= 2) qr_panel<2, WT>(S, jt, np, row0, colf, lane); break;
-            case 3: if constexpr (NRMAX >= 3) qr_panel<3, WT>(S, jt, np, row0, colf, lane); break;
-            case 4: if constexpr (NRMAX >= 4) qr_panel<4, WT>(S, jt, np, row0, colf, lane); break;
-            case 5: if constexpr (NRMAX >= 5) qr_panel<5, WT>(S, jt, np, row0, colf, lane); break;
-            case 6: if constexpr (NRMAX >= 6) qr_panel<6, WT>(S, jt, np, row0, colf, lane); break;
-            case 7: if constexpr (NRMAX >= 7) qr_panel<7, WT>(S, jt, np, row0, colf, lane); break;
-            case 8: if constexpr (NRMAX >= 8) qr_panel<8, WT>(S, jt, np, row0, colf, lane); break;
+            case 1: qr_panel<1, WT>(S, tq, jt, np, row0, colf, lane); break;
+            case 2: if constexpr (NRMAX >= 2) qr_panel<2, WT>(S, tq, jt, np, row0, colf, lane); break;
+            case 3: if constexpr (NRMAX >= 3) qr_panel<3, WT>(S, tq, jt, np, row0, colf, lane); break;
+            case 4: if constexpr (NRMAX >= 4) qr_panel<4, WT>(S, tq, jt, np, row0, colf, lane); break;
+            case 5: if constexpr (NRMAX >= 5) qr_panel<5, WT>(S, tq, jt, np, row0, colf, lane); break;
+            case 6: if constexpr (NRMAX >= 6) qr_panel<6, WT>(S, tq, jt, np, row0, colf, lane); break;
+            case 7: if constexpr (NRMAX >= 7) qr_panel<7, WT>(S, tq, jt, np, row0, colf, lane); break;
+            case 8: if constexpr (NRMAX >= 8) qr_panel<8, WT>(S, tq, jt, np, row0, colf, lane); break;
             default: break;
         }
     }
@@ -314,8 +337,8 @@ struct Dims {
     static constexpr int HC = RQ + MT * RT * 64;    // Hc, PT x PT tiles
     static constexpr int VA = HC + PT * PT * 64;    // vectors
     static constexpr int V_a = VA, V_af = V_a + m, V_c = V_af + m, V_d = V_c + m, V_v = V_d + p, V_sv = V_v + p,
-                         V_in = V_sv + p, V_w = V_in + p, V_ym = V_w + p;
-    static constexpr int FWD_ELEMS = V_ym + p;
+                         V_in = V_sv + p, V_w = V_in + p, V_ym = V_w + p, V_tq = V_ym + p;  // V_tq: Gram tile + taus (72)
+    static constexpr int FWD_ELEMS = V_tq + 72;
 };
 
 // In-place lower Cholesky of a k x k row-major matrix in shared memory by one warp; the upper triangle is zeroed.
@@ -528,7 +551,7 @@ __global__ void __launch_bounds__(32) forward_kernel(KArgs<double> G) {
 #pragma unroll
                 for (int J = 0; J < PT; ++J) stt(SA, (PT + I) * WT + J, lane, zero2());
             __syncwarp();
-            qr_tiles<D::NT1, MT, PT, WT>(SA, D::NT1, D::NT1, false, lane);
+            qr_tiles<D::NT1, MT, PT, WT>(SA, smem + D::V_tq, D::NT1, D::NT1, false, lane);
             if (rec)
                 store_packed_upper<D::NT1>(rec + off_rf, SA, lane, [](int I, int J) { return I * WT + J; });
             if (G.obs_cov)  // F = Fc Fc^T, Fc = B[:p,:p]
@@ -620,7 +643,7 @@ __global__ void __launch_bounds__(32) forward_kernel(KArgs<double> G) {
             }
             __syncwarp();
         }
-        qr_tiles<D::NT1, MT, PT, WT>(SA, MT, MT + RT, true, lane);
+        qr_tiles<D::NT1, MT, PT, WT>(SA, smem + D::V_tq, MT, MT + RT, true, lane);
         if (rec) store_packed_upper<MT>(rec + off_rp, SA, lane, [](int I, int J) { return D::pc_tile(I, J); });
     }
     if (lane == 0) {
