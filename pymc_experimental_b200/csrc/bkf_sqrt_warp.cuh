@@ -148,7 +148,7 @@ __device__ __forceinline__ void qr_panel(double* __restrict__ S, double* __restr
     double2 pa[NQ];
 #pragma unroll
     for (int q = 0; q < NQ; ++q) pa[q] = ldt(S, tile(jt, jt + q), lane);
-    double tauv = 0.0;  // tau of the reflector of column g (0: H = I)
+    double tauv = 0.0, scalv = 1.0;  // tau and 1 / (alpha - beta) of the reflector of column g (tau = 0: H = I)
 #pragma unroll 1
     for (int k = 0; k < 8; ++k) {
         // x = column k of the panel below its diagonal, handed to every group (lane (k, t) -> lanes (*, t))
@@ -184,34 +184,41 @@ __device__ __forceinline__ void qr_panel(double* __restrict__ S, double* __restr
         const double tau = den * rn;
         const double scal = copysign(rden, alpha);
         const double zz = fma(scal, dot, akc);  // v_k . a_c  (c > k)
-        // column update a_c -= w v (c > k); the pivot column itself becomes v = x scal, written as x - w_k v with
-        // w_k = 1 / scal - 1 = (alpha - beta) - 1 so that every lane runs the same FMA (rows above the pivot see v = 0)
+        // Update with the UNSCALED reflector u = [alpha - beta; x] (v = u scal):  a_c -= (tau zz scal) u  for c > k.
+        // The pivot column keeps x until the sweep of the panel is over (nothing reads v before) and is scaled once.
         const bool piv = g == k;
-        const double w = g > k ? tau * zz : (piv ? (alpha - beta) - 1.0 : 0.0);
-        double2 vd = make_double2(xm.x * scal, xm.y * scal);  // v on my rows (unit at row k)
-        if (2 * t == k) vd.x = 1.0;
-        if (2 * t + 1 == k) vd.y = 1.0;
+        const double w = g > k ? tau * zz * scal : 0.0;
+        double2 ud = xm;  // u on my rows of the diagonal block
+        if (2 * t == k) ud.x = alpha - beta;
+        if (2 * t + 1 == k) ud.y = alpha - beta;
         {
-            const double nx = fma(-w, vd.x, pa[0].x), ny = fma(-w, vd.y, pa[0].y);
+            const double nx = fma(-w, ud.x, pa[0].x), ny = fma(-w, ud.y, pa[0].y);
             pa[0].x = (piv && 2 * t == k) ? beta : nx;
             pa[0].y = (piv && 2 * t + 1 == k) ? beta : ny;
         }
 #pragma unroll
         for (int q = 1; q < NQ; ++q) {
-            pa[q].x = fma(-w, xb[q].x * scal, pa[q].x);
-            pa[q].y = fma(-w, xb[q].y * scal, pa[q].y);
+            pa[q].x = fma(-w, xb[q].x, pa[q].x);
+            pa[q].y = fma(-w, xb[q].y, pa[q].y);
         }
-        if (piv) tauv = tau;
+        if (piv) {
+            tauv = tau;
+            scalv = scal;
+        }
     }
-    // R goes back to the array (zeros below the diagonal); V^T (unit diagonal) stays in registers (in pa)
+    // R goes back to the array (zeros below the diagonal); V^T = (x scal)^T with unit diagonal stays in registers (in pa)
     {
         const double2 r = pa[0];
         stt(S, tile(jt, jt), lane, make_double2(2 * t <= g ? r.x : 0.0, 2 * t + 1 <= g ? r.y : 0.0));
-        pa[0].x = 2 * t > g ? r.x : (2 * t == g ? 1.0 : 0.0);
-        pa[0].y = 2 * t + 1 > g ? r.y : (2 * t + 1 == g ? 1.0 : 0.0);
+        pa[0].x = 2 * t > g ? r.x * scalv : (2 * t == g ? 1.0 : 0.0);
+        pa[0].y = 2 * t + 1 > g ? r.y * scalv : (2 * t + 1 == g ? 1.0 : 0.0);
     }
 #pragma unroll
-    for (int q = 1; q < NQ; ++q) stt(S, tile(jt, jt + q), lane, zero2());
+    for (int q = 1; q < NQ; ++q) {
+        pa[q].x *= scalv;
+        pa[q].y *= scalv;
+        stt(S, tile(jt, jt + q), lane, zero2());
+    }
     if (jt + 1 < np) {
         // Compact-WY factor (dlarft) from the Gram matrix of the reflectors:  T^{-1} = striu(V^T V) + diag(1 / tau), so
         // column j of T solves  x_i = tau_i (delta_ij - sum_{l > i} G_il x_l)  by back substitution -- no division, a
