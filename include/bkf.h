@@ -173,6 +173,19 @@ int bkf_filter_smooth(bkf_handle* h, const bkf_problem* prob, const void* y, con
                       const void* Q, void* loglike_obs, void* smoothed_states, void* smoothed_covariances,
                       int* status);
 
+/* Row f-3 of SURVEY.md section 8: one multivariate-normal draw per (series, step),
+ *     x[b,t] = mu[b,t] + L[b,t] z[b,t],   L L^T = cov[b,t],
+ * the batched form of SequenceMvNormal.rv_op (pymc_extras/statespace/filters/distributions.py:411-443), which scans
+ * MvNormalSVD (:52-87) over time to sample the conditional posterior from the smoother's output
+ * (core/statespace.py:1119-1150).  L is the lower Cholesky factor with semidefinite pivots dropped (a pivot below
+ * 64 m eps max(diag) zeroes its column): like the reference's SVD square root it accepts rank-deficient covariances, and
+ * the distribution of x is the same for every square root.  z: standard normal variates drawn by the caller, so the call
+ * itself is deterministic.  Uses prob->B, n, m, dtype, mem; mu, z, x: [B, n, m]; cov: [B, n, m, m] (lower triangle
+ * read); m <= 32.  status[B] (nullable): BKF_STATUS_NOT_PD if some cov[b,t] has a pivot below -1e-8 max(diag)
+ * (-1e-4 in float32), numpy's check_valid tolerance. */
+int bkf_mvn_sample(bkf_handle* h, const bkf_problem* prob, const void* mu, const void* cov, const void* z, void* x,
+                   int* status);
+
 #ifdef __cplusplus
 }
 #endif

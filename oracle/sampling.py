@@ -1,0 +1,45 @@
+"""TEST INFRASTRUCTURE ONLY -- CPU restatement of the draw the reference makes from the smoother's output.
+
+Reference: ``SequenceMvNormal.rv_op`` (pymc_extras/statespace/filters/distributions.py:411-443) scans
+``MvNormalSVD.dist(mu=mu, cov=cov)`` (:52-87) over time; on the default backend that is NumPy's
+``Generator.multivariate_normal(mean, cov, method="svd")``:  ``x = mean + z @ (sqrt(s)[:, None] * vh)``  with
+``u, s, vh = svd(cov)`` and ``z`` standard normal.
+
+``svd_factor`` restates that square root; ``chol_psd`` is the square root the CUDA kernel uses (lower Cholesky with
+semidefinite pivots dropped, same tolerance).  Both satisfy ``A^T A = cov`` / ``L L^T = cov`` for a PSD matrix, so the
+draws ``mean + z @ A`` and ``mean + L z`` have the same distribution; the tests pin the kernel to ``chol_psd`` exactly
+and both factors to ``cov``.  Parity with the reference's NUMBERS is not defined for a random draw (its own stream is not
+reproducible across generators); this is stated in DESIGN.md.
+"""
+
+import numpy as np
+
+
+def svd_factor(cov):
+    """A with x = mean + z @ A as numpy.random.Generator.multivariate_normal(method="svd") forms it."""
+    u, s, vh = np.linalg.svd(cov)
+    return np.sqrt(s)[:, None] * vh
+
+
+def chol_psd(cov):
+    """Lower factor L, L L^T = cov for PSD cov; a pivot <= 64 m eps max(diag) zeroes its column."""
+    cov = np.asarray(cov, dtype=np.float64)
+    m = cov.shape[-1]
+    tol = 64 * m * np.finfo(np.float64).eps * np.max(np.diag(cov))
+    L = np.zeros((m, m))
+    for j in range(m):
+        acc = cov[j:, j] - L[j:, :j] @ L[j, :j]
+        d = acc[0]
+        if d > tol:
+            L[j, j] = np.sqrt(d)
+            L[j + 1:, j] = acc[1:] / L[j, j]
+    return L
+
+
+def sample(mu, cov, z):
+    """x[..., t, :] = mu + L z with L = chol_psd(cov[..., t, :, :]) (loops: small cases only)."""
+    mu, cov, z = np.asarray(mu, float), np.asarray(cov, float), np.asarray(z, float)
+    x = np.empty_like(mu)
+    for idx in np.ndindex(mu.shape[:-1]):
+        x[idx] = mu[idx] + chol_psd(cov[idx]) @ z[idx]
+    return x

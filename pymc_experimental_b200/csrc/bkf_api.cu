@@ -815,6 +815,51 @@ extern "C" int bkf_stationary_init_grad(bkf_handle* h, const bkf_problem* P, con
 }
 
 // ----------------------------------------------------------------------------------------------------
+// multivariate-normal draws (bkf.h: bkf_mvn_sample)
+template <typename R>
+static int sample_impl(bkf_handle* h, const bkf_problem* P, const void* mu, const void* cov, const void* z, void* x,
+                       int* status) {
+    int rc = BKF_OK;
+    const size_t B = P->B, n = P->n, m = P->m;
+    const R* dmu = stage_in<R>(h, P, S_WFA, mu, B * n * m, &rc);
+    const R* dcov = stage_in<R>(h, P, S_WFP, cov, B * n * m * m, &rc);
+    const R* dz = stage_in<R>(h, P, S_Y, z, B * n * m, &rc);
+    R* dx = stage_out<R>(h, P, S_SMA, x, B * n * m, &rc);
+    int* dstatus = nullptr;
+    if (status) {
+        dstatus = P->mem == BKF_MEM_DEVICE ? status : (int*)ensure(h, S_STATUS, B * sizeof(int), &rc);
+        if (dstatus && rc == BKF_OK) cudaMemsetAsync(dstatus, 0, B * sizeof(int), h->stream);
+    }
+    if (rc != BKF_OK) return rc;
+    if (B * n == 0) return BKF_OK;
+    const char* err = "";
+    h->launches += 1;
+    h->path = "mvn_chol_subwarp";
+    rc = smp::launch<R>(dmu, dcov, dz, dx, dstatus, (long long)(B * n), (int)n, (int)m, h->stream, &err);
+    if (rc != BKF_OK) return fail(h, rc, err);
+    copy_back<R>(h, P, x, dx, B * n * m, &rc);
+    if (status && P->mem == BKF_MEM_HOST && rc == BKF_OK) {
+        cudaError_t e = cudaMemcpyAsync(status, dstatus, B * sizeof(int), cudaMemcpyDeviceToHost, h->stream);
+        if (e != cudaSuccess) rc = cuda_fail(h, e, "D2H copy");
+    }
+    return finish(h, P, rc);
+}
+
+extern "C" int bkf_mvn_sample(bkf_handle* h, const bkf_problem* P, const void* mu, const void* cov, const void* z,
+                              void* x, int* status) {
+    if (!h) return BKF_ERR_ARG;
+    if (!P) return fail(h, BKF_ERR_ARG, "null problem");
+    if (P->dtype != BKF_F64 && P->dtype != BKF_F32) return fail(h, BKF_ERR_ARG, "unknown dtype");
+    if (P->mem != BKF_MEM_HOST && P->mem != BKF_MEM_DEVICE) return fail(h, BKF_ERR_ARG, "unknown memory space");
+    if (P->B < 0 || P->n < 0 || P->m < 1) return fail(h, BKF_ERR_ARG, "non-positive dimension");
+    if (!mu || !cov || !z || !x) return fail(h, BKF_ERR_ARG, "null pointer");
+    cudaError_t e = cudaSetDevice(h->device);
+    if (e != cudaSuccess) return cuda_fail(h, e, "cudaSetDevice");
+    return P->dtype == BKF_F64 ? sample_impl<double>(h, P, mu, cov, z, x, status)
+                               : sample_impl<float>(h, P, mu, cov, z, x, status);
+}
+
+// ----------------------------------------------------------------------------------------------------
 template <typename R>
 static int smooth_impl(bkf_handle* h, const bkf_problem* P, const void* T, const void* Rm, const void* Q,
                        const void* fa, const void* fP, void* sa, void* sP, int* status) {

@@ -35,6 +35,11 @@ int launch_smoother_f64(const KArgs<double>& g, double jitter0, int* any_ill, cu
 namespace stat {  // stationary initialisation: Lyapunov / (I - T)^{-1} c by doubling (bkf_stationary.cu)
 template <typename R> int launch(const KArgs<R>& g, bool backward, cudaStream_t stream, const char** err);
 }  // namespace stat
+namespace smp {  // multivariate-normal draws from (mu, cov) sequences (bkf_sample.cu)
+template <typename R>
+int launch(const R* mu, const R* cov, const R* z, R* x, int* status, long long N, int n, int m, cudaStream_t stream,
+           const char** err);
+}  // namespace smp
 namespace tps {  // thread-per-series kernels, m <= 4, p = 1 (bkf_thread.cu)
 bool supported(int kind, int m, int p);
 template <typename R> int launch_any(const KArgs<R>& g, bool backward, cudaStream_t stream, const char** err);

@@ -34,7 +34,7 @@ ABI_SYMBOLS = (
     "bkf_last_path", "bkf_enable_timing", "bkf_reset_timing", "bkf_kernel_time_ms", "bkf_measure_fma_peak",
     "bkf_filter_forward", "bkf_filter_logp_grad", "bkf_smooth", "bkf_filter_smooth", "bkf_host_alloc", "bkf_host_free",
     "bkf_logp_grad_workspace_bytes", "bkf_device_memory", "bkf_filter_logp_grad_compact", "bkf_stationary_init",
-    "bkf_stationary_init_grad",
+    "bkf_stationary_init_grad", "bkf_mvn_sample",
 )
 
 
@@ -91,6 +91,7 @@ def load_library():
                                                  C.POINTER(C.c_int), vp, vp, vp, vp, vp]
     lib.bkf_stationary_init.argtypes = [vp, pp] + [vp] * 4 + [vp] * 2 + [vp]
     lib.bkf_stationary_init_grad.argtypes = [vp, pp] + [vp] * 7 + [vp] * 4
+    lib.bkf_mvn_sample.argtypes = [vp, pp] + [vp] * 3 + [vp] + [vp]
     lib.bkf_smooth.argtypes = [vp, pp] + [vp] * 5 + [vp] * 2 + [vp]
     lib.bkf_filter_smooth.argtypes = [vp, pp] + [vp] * 10 + [vp] * 3 + [vp]
     _lib = lib
@@ -540,6 +541,31 @@ class KalmanEngine:
             self.h, C.byref(prob), bufs.ptr(v["T"]), bufs.ptr(v["R"]), bufs.ptr(v["Q"]), bufs.ptr(a0b), bufs.ptr(P0b),
             bufs.ptr(ab), bufs.ptr(Pb), *[bufs.ptr(g[k_]) for k_ in ("c", "T", "R", "Q")]))
         return {k_: x[0] for k_, x in g.items()} if squeeze else g
+
+    def sample_mvn(self, mu, cov, z, dtype=None):
+        """One draw from ``N(mu[..., t, :], cov[..., t, :, :])`` per (series, step): ``x = mu + L z`` with ``L L^T = cov``
+        (``bkf_mvn_sample``; SURVEY section 8 row f-3 -- the batched form of ``SequenceMvNormal.rv_op`` /
+        ``MvNormalSVD``, filters/distributions.py:52-87, 411-443).  ``mu, z``: (B, n, m) or (n, m); ``cov``: (B, n, m, m)
+        or (n, m, m); ``z`` standard normal variates.  Returns ``(x, status)``."""
+        bufs = _Buffers([mu, cov, z], dtype)
+        conv = lambda v: v if _is_torch(v) else np.asarray(v)
+        mu, cov, z = conv(mu), conv(cov), conv(z)
+        squeeze = mu.ndim == 2
+        if squeeze:
+            mu, cov, z = mu[None], cov[None], z[None]
+        if mu.ndim != 3 or cov.ndim != 4 or tuple(z.shape) != tuple(mu.shape) or \
+                tuple(cov.shape) != tuple(mu.shape) + (mu.shape[-1],):
+            raise BkfError("sample_mvn: expected mu, z (B, n, m) and cov (B, n, m, m)")
+        B, n, m = (int(v) for v in mu.shape)
+        prob = BkfProblem(kind=STANDARD, dtype=bufs.code, mem=MEM_DEVICE if bufs.device else MEM_HOST, B=B, n=n, m=m,
+                          p=1, r=1, y_shared=0, shared_mask=0, tv_mask=0, cov_jitter=0.0, missing_fill=MISSING_FILL)
+        dmu, dcov, dz = bufs.inp(mu), bufs.inp(cov), bufs.inp(z)
+        x, status = bufs.out((B, n, m)), bufs.out_int((B,))
+        if bufs.device:
+            self.use_torch_stream()
+        self._check(self.lib.bkf_mvn_sample(self.h, C.byref(prob), bufs.ptr(dmu), bufs.ptr(dcov), bufs.ptr(dz),
+                                            bufs.ptr(x), bufs.ptr(status)))
+        return (x[0], status[0]) if squeeze else (x, status)
 
     def _logp_grad_in_slices(self, kind, y, params, ll_cotangent, B, nslices, kw):
         """Series are independent: a batch whose trajectory workspace would not fit the device is processed in

@@ -1,0 +1,46 @@
+"""Conditional-posterior draws from the smoother's output.
+
+Host-side mirror of ``SequenceMvNormal`` (pymc_extras/statespace/filters/distributions.py:411-443): the reference scans
+``MvNormalSVD(mu=mu[t], cov=cov[t])`` over the time axis to sample hidden states given the smoothed moments
+(``core/statespace.py:1119-1150``).  Here every (series, step) is drawn in one kernel launch: the standard normal
+variates come from the caller's generator (NumPy ``Generator`` on the host, ``torch.Generator`` on the device), the
+square root of each covariance and the affine map run on the GPU (``bkf_mvn_sample``).
+
+The draws have the reference's DISTRIBUTION, not its numbers: NumPy's SVD method uses the square root
+``sqrt(s) V^T``, the kernel a Cholesky factor with semidefinite pivots dropped, and the two differ by an orthogonal
+transformation of the variates (a different random stream gives different numbers in the reference as well).
+"""
+
+from __future__ import annotations
+
+import numpy as np
+
+from .engine import KalmanEngine, _is_torch
+
+
+def sample_sequence_mvnormal(mus, covs, rng=None, engine: KalmanEngine | None = None, return_status=False):
+    """One draw per (batch..., time) from ``N(mus[..., t, :], covs[..., t, :, :])``.
+
+    ``mus``: (..., T, m), ``covs``: (..., T, m, m), NumPy arrays or CUDA tensors (the result lives where the inputs do).
+    ``rng``: ``numpy.random.Generator`` (host inputs) or ``torch.Generator`` (device inputs); a fresh default one if None.
+    """
+    eng = engine if engine is not None else KalmanEngine(0)
+    if _is_torch(mus):
+        import torch
+
+        z = torch.randn(mus.shape, dtype=mus.dtype, device=mus.device, generator=rng)
+        lead = tuple(mus.shape[:-2])
+        x, status = eng.sample_mvn(mus.reshape((-1,) + tuple(mus.shape[-2:])),
+                                   covs.reshape((-1,) + tuple(covs.shape[-3:])), z.reshape((-1,) + tuple(mus.shape[-2:])))
+        x = x.reshape(tuple(mus.shape))
+        status = status.reshape(lead) if lead else status[0]
+    else:
+        mus, covs = np.asarray(mus), np.asarray(covs)
+        gen = rng if rng is not None else np.random.default_rng()
+        z = gen.standard_normal(mus.shape).astype(mus.dtype, copy=False)
+        lead = mus.shape[:-2]
+        x, status = eng.sample_mvn(mus.reshape((-1,) + mus.shape[-2:]), covs.reshape((-1,) + covs.shape[-3:]),
+                                   z.reshape((-1,) + mus.shape[-2:]))
+        x = np.array(x).reshape(mus.shape)
+        status = np.array(status).reshape(lead) if lead else int(status[0])
+    return (x, status) if return_status else x

@@ -144,3 +144,26 @@ def test_c4_varmax_square_root_spot_check(eng):
     assert int(status.abs().sum()) == 0
     _spot_check("cholesky", cfg, logp.cpu().numpy(), {k: v.cpu().numpy() for k, v in grads.items()},
                 np.array([0, 295, 591]), rtol=1e-8)
+
+
+def test_c3_conditional_posterior_draw_full_size(eng):
+    """Row f-3 at the C3 size (8 192 draws x T=240, m=15): one draw per (draw, step) from the smoother's output; the
+    Mahalanobis norm of every draw equals the norm of its variates, (x - mu)^T cov^-1 (x - mu) == |z|^2 -- an identity
+    that holds for any square root of cov -- and the empirical moments over the batch are those of a standard normal."""
+    import torch
+
+    from pymc_experimental_b200 import synth
+
+    cfg = synth.structural(B=8192, n=240)
+    dcfg = _dev(cfg)
+    ll, sa, sP, status = eng.filter_smooth("standard", dcfg["y"], *[dcfg[k] for k in NAMES])
+    gen = torch.Generator(device="cuda:0").manual_seed(11)
+    z = torch.randn(sa.shape, dtype=torch.float64, device="cuda:0", generator=gen)
+    x, st = eng.sample_mvn(sa, sP, z)
+    assert eng.last_path == "mvn_chol_subwarp"
+    assert int(st.abs().sum()) == 0
+    dx = (x - sa).unsqueeze(-1)
+    maha = (dx * torch.linalg.solve(sP, dx)).sum((-1, -2))
+    z2 = (z * z).sum(-1)
+    assert float(((maha - z2).abs() / z2).max()) < 1e-6  # cond(P_s) ~ 1e5 on these draws
+    assert abs(float(z.mean())) < 1e-3 and abs(float(z.var()) - 1.0) < 1e-3

@@ -541,3 +541,58 @@ def test_stationary_initialisation_matches_the_oracle(eng, shape, device):
     Tu = np.eye(m)[None]
     _, _, st = eng.stationary_init(c[:1], Tu, R[:1], Q[:1])
     assert st[0] == 8
+
+
+@pytest.mark.parametrize("m", [3, 8, 15, 16, 32])
+def test_mvn_sample_matches_oracle_and_reproduces_covariance(eng, m):
+    """Row f-3 (SequenceMvNormal / MvNormalSVD draw): the kernel's x = mu + L z equals the oracle's Cholesky-with-dropped-
+    pivots restatement, L L^T reproduces cov (recovered by feeding unit vectors as z), for full-rank and rank-deficient
+    covariances, host and device pointers."""
+    import torch
+
+    from oracle import sampling as osm
+
+    rng = np.random.default_rng(100 + m)
+    B, n = 5, 7
+    A = rng.normal(size=(B, n, m, m))
+    cov = A @ A.transpose(0, 1, 3, 2) + 0.05 * np.eye(m)
+    rk = max(1, m // 3)
+    cov[1] = A[1][..., :rk] @ A[1][..., :rk].transpose(0, 2, 1)  # one series with rank-deficient covariances
+    mu = rng.normal(size=(B, n, m))
+    z = rng.standard_normal((B, n, m))
+    x, status = eng.sample_mvn(mu, cov, z)
+    assert eng.last_path == "mvn_chol_subwarp"
+    assert int(np.abs(status).sum()) == 0
+    ref = osm.sample(mu, cov, z)
+    scale = np.abs(ref).max()
+    assert_allclose(x, ref, rtol=0, atol=1e-10 * scale)
+    xd, _ = eng.sample_mvn(*[torch.as_tensor(a, device="cuda") for a in (mu, cov, z)])
+    assert_allclose(xd.cpu().numpy(), np.asarray(x), rtol=0, atol=0)
+    # columns of L from unit variates: L L^T == cov
+    L = np.empty((B, n, m, m))
+    for k in range(m):
+        e = np.zeros((B, n, m))
+        e[..., k] = 1.0
+        L[..., k] = np.asarray(eng.sample_mvn(np.zeros_like(mu), cov, e)[0])
+    assert_allclose(L @ L.transpose(0, 1, 3, 2), cov, rtol=0, atol=1e-11 * np.abs(cov).max())
+    # an indefinite matrix is flagged, not silently accepted
+    bad = cov.copy()
+    bad[2, 3] = -np.eye(m)
+    _, st = eng.sample_mvn(mu, bad, z)
+    assert st[2] != 0 and st[0] == 0
+
+
+def test_sample_sequence_mvnormal_host_mirror(eng):
+    """sampling.sample_sequence_mvnormal: draws live where the inputs do, shape (..., T, m), reproducible from the rng."""
+    from pymc_experimental_b200.sampling import sample_sequence_mvnormal
+
+    rng = np.random.default_rng(4)
+    A = rng.normal(size=(2, 3, 6, 4, 4))
+    covs = A @ A.transpose(0, 1, 2, 4, 3) + 0.1 * np.eye(4)
+    mus = rng.normal(size=(2, 3, 6, 4))
+    x1 = sample_sequence_mvnormal(mus, covs, rng=np.random.default_rng(9), engine=eng)
+    x2 = sample_sequence_mvnormal(mus, covs, rng=np.random.default_rng(9), engine=eng)
+    assert x1.shape == mus.shape and np.array_equal(x1, x2)
+    z = np.random.default_rng(9).standard_normal(mus.shape)
+    L = np.linalg.cholesky(covs)
+    assert_allclose(x1, mus + np.einsum("...ij,...j->...i", L, z), rtol=0, atol=1e-11 * np.abs(x1).max())

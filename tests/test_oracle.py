@@ -261,3 +261,33 @@ def test_stationary_init_oracle_direct_equals_bilinear_and_gradient_matches_fini
             xm[idx] -= 1e-6
             fd = (f(**{**args, k: xp}) - f(**{**args, k: xm})) / 2e-6
             assert_allclose(g[k][idx], fd, rtol=1e-6, atol=1e-7)
+
+
+def test_sampling_oracle_factors_reproduce_the_covariance():
+    """Row f-3: the reference's SVD square root (numpy multivariate_normal, method="svd") and the Cholesky-with-dropped-
+    pivots square root of the CUDA kernel both reproduce cov -- full rank and rank deficient -- so the two draws have the
+    same distribution; and a Monte-Carlo check of the oracle's draw against numpy's own sampler."""
+    from oracle import sampling as osm
+
+    rng = np.random.default_rng(12)
+    m = 7
+    A = rng.normal(size=(m, m))
+    full = A @ A.T + 0.1 * np.eye(m)
+    low = A[:, :3] @ A[:, :3].T  # rank 3
+    for cov in (full, low):
+        S = osm.svd_factor(cov)
+        L = osm.chol_psd(cov)
+        np.testing.assert_allclose(S.T @ S, cov, rtol=0, atol=1e-12 * np.abs(cov).max())
+        np.testing.assert_allclose(L @ L.T, cov, rtol=0, atol=1e-12 * np.abs(cov).max())
+        assert np.all(np.triu(L, 1) == 0)
+    assert (np.abs(np.diag(osm.chol_psd(low))) > 0).sum() == 3
+    # the oracle's draws and numpy's SVD-method draws agree in mean and covariance (50 000 draws, 4 sigma bounds)
+    n = 50_000
+    mu = rng.normal(size=m)
+    z = rng.standard_normal((n, m))
+    ours = mu + z @ osm.chol_psd(full).T
+    ref = np.random.default_rng(3).multivariate_normal(mu, full, size=n, method="svd")
+    se = np.sqrt(np.diag(full) / n)
+    assert np.all(np.abs(ours.mean(0) - ref.mean(0)) < 6 * se)
+    c1, c2 = np.cov(ours.T), np.cov(ref.T)
+    assert np.abs(c1 - c2).max() < 0.05 * np.abs(full).max()
