@@ -186,6 +186,19 @@ int bkf_filter_smooth(bkf_handle* h, const bkf_problem* prob, const void* y, con
 int bkf_mvn_sample(bkf_handle* h, const bkf_problem* prob, const void* mu, const void* cov, const void* z, void* x,
                    int* status);
 
+/* Row f-3, second part: unconditional simulation of B state-space models for prob->n steps -- the batched form of
+ * LinearGaussianStateSpace.rv_op (filters/distributions.py:181-293; prior / forecast / IRF draws):
+ *     x_0 ~ N(a0, P0),  y_0 ~ N(Z x_0, H)                      (:262-263: no d in the first observation mean)
+ *     x_t = c + T x_{t-1} + R eps_t,  eps_t ~ N(0, Q) ;  y_t = d + Z x_t + eta_t,  eta_t ~ N(0, H)       (:247-254)
+ * Every normal draw is (Cholesky factor with dropped semidefinite pivots, as bkf_mvn_sample) x (standard normal variates
+ * supplied by the caller): z_x0 [B,m], z_y0 [B,p], z_state [B,n,r], z_obs [B,n,p].  Outputs: states [B,n+1,m],
+ * obs [B,n+1,p] (row 0 = the initial draw; the reference concatenates the two along the last axis, append_x0=True).
+ * Parameters follow prob->shared_mask; time-varying matrices are refused (BKF_ERR_UNSUPPORTED).  status[B] (nullable):
+ * BKF_STATUS_NOT_PD if P0, H or Q is not positive semidefinite. */
+int bkf_simulate(bkf_handle* h, const bkf_problem* prob, const void* a0, const void* P0, const void* c, const void* d,
+                 const void* T, const void* Z, const void* R, const void* H, const void* Q, const void* z_x0,
+                 const void* z_y0, const void* z_state, const void* z_obs, void* states, void* obs, int* status);
+
 #ifdef __cplusplus
 }
 #endif

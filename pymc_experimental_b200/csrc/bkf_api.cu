@@ -859,6 +859,52 @@ extern "C" int bkf_mvn_sample(bkf_handle* h, const bkf_problem* P, const void* m
                                : sample_impl<float>(h, P, mu, cov, z, x, status);
 }
 
+template <typename R>
+static int simulate_impl(bkf_handle* h, const bkf_problem* P, const void* const* prm, const void* z_x0, const void* z_y0,
+                         const void* z_state, const void* z_obs, void* states, void* obs, int* status) {
+    int rc = BKF_OK;
+    KArgs<R> g;
+    fill_inputs<R>(h, P, g, nullptr, prm, &rc);
+    const size_t B = P->B, n = P->n, m = P->m, p = P->p, r = P->r;
+    const R* dzx = stage_in<R>(h, P, S_WFA, z_x0, B * m, &rc);
+    const R* dzy = stage_in<R>(h, P, S_COT, z_y0, B * p, &rc);
+    const R* dzs = stage_in<R>(h, P, S_WFP, z_state, B * n * r, &rc);
+    const R* dzo = stage_in<R>(h, P, S_Y, z_obs, B * n * p, &rc);
+    R* dxs = stage_out<R>(h, P, S_SMA, states, B * (n + 1) * m, &rc);
+    R* dys = stage_out<R>(h, P, S_SMP, obs, B * (n + 1) * p, &rc);
+    int* dstatus = nullptr;
+    if (status) dstatus = P->mem == BKF_MEM_DEVICE ? status : (int*)ensure(h, S_STATUS, B * sizeof(int), &rc);
+    g.status = dstatus;
+    if (rc != BKF_OK) return rc;
+    if (B == 0) return BKF_OK;
+    const char* err = "";
+    h->launches += 1;
+    h->path = "simulate_warp";
+    rc = smp::launch_simulate<R>(g, dzx, dzy, dzs, dzo, dxs, dys, h->stream, &err);
+    if (rc != BKF_OK) return fail(h, rc, err);
+    copy_back<R>(h, P, states, dxs, B * (n + 1) * m, &rc);
+    copy_back<R>(h, P, obs, dys, B * (n + 1) * p, &rc);
+    if (status && P->mem == BKF_MEM_HOST && rc == BKF_OK) {
+        cudaError_t e = cudaMemcpyAsync(status, dstatus, B * sizeof(int), cudaMemcpyDeviceToHost, h->stream);
+        if (e != cudaSuccess) rc = cuda_fail(h, e, "D2H copy");
+    }
+    return finish(h, P, rc);
+}
+
+extern "C" int bkf_simulate(bkf_handle* h, const bkf_problem* P, const void* a0, const void* P0, const void* c,
+                            const void* d, const void* T, const void* Z, const void* R, const void* H, const void* Q,
+                            const void* z_x0, const void* z_y0, const void* z_state, const void* z_obs, void* states,
+                            void* obs, int* status) {
+    int rc = validate(h, P, true);
+    if (rc != BKF_OK) return rc;
+    if (P->tv_mask) return fail(h, BKF_ERR_UNSUPPORTED, "bkf_simulate does not take time-varying matrices yet");
+    const void* prm[BKF_NPARAM] = {a0, P0, c, d, T, Z, R, H, Q};
+    if (any_null(prm, BKF_NPARAM) || !z_x0 || !z_y0 || !z_state || !z_obs || !states || !obs)
+        return fail(h, BKF_ERR_ARG, "null pointer");
+    return P->dtype == BKF_F64 ? simulate_impl<double>(h, P, prm, z_x0, z_y0, z_state, z_obs, states, obs, status)
+                               : simulate_impl<float>(h, P, prm, z_x0, z_y0, z_state, z_obs, states, obs, status);
+}
+
 // ----------------------------------------------------------------------------------------------------
 template <typename R>
 static int smooth_impl(bkf_handle* h, const bkf_problem* P, const void* T, const void* Rm, const void* Q,

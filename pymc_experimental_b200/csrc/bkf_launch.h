@@ -39,6 +39,9 @@ namespace smp {  // multivariate-normal draws from (mu, cov) sequences (bkf_samp
 template <typename R>
 int launch(const R* mu, const R* cov, const R* z, R* x, int* status, long long N, int n, int m, cudaStream_t stream,
            const char** err);
+template <typename R>
+int launch_simulate(const KArgs<R>& g, const R* z_x0, const R* z_y0, const R* z_state, const R* z_obs, R* xs, R* ys,
+                    cudaStream_t stream, const char** err);
 }  // namespace smp
 namespace tps {  // thread-per-series kernels, m <= 4, p = 1 (bkf_thread.cu)
 bool supported(int kind, int m, int p);

@@ -84,6 +84,144 @@ int launch(const R* mu, const R* cov, const R* z, R* x, int* status, long long N
     return BKF_OK;
 }
 
+// ----------------------------------------------------------------------------------------------------
+// Unconditional simulation of the state-space model: LinearGaussianStateSpace.rv_op (filters/distributions.py:181-293).
+//     x_0 ~ N(a0, P0),  y_0 ~ N(Z x_0, H)           (:262-263 -- no d in the first observation mean, as the reference)
+//     x_t = c + T x_{t-1} + R eps_t,  eps_t ~ N(0, Q);   y_t = d + Z x_t + eta_t,  eta_t ~ N(0, H)      (:247-254)
+// with every normal draw written as (factor) x (caller-supplied standard normal variates), factors = Cholesky with
+// dropped semidefinite pivots as above.  One warp per series, matrices in the warp's shared-memory arena, lane i owns
+// row i of the matrix-vector products.
+template <typename R>
+__device__ int chol_psd_warp(R* A, int k, int lane) {
+    R dmax = 0;
+    for (int i = 0; i < k; ++i) dmax = fmax(dmax, A[i * k + i]);
+    const R eps = sizeof(R) == 8 ? R(2.220446049250313e-16) : R(1.1920929e-7f);
+    const R tol = R(64 * k) * eps * dmax, neg = (sizeof(R) == 8 ? R(1e-8) : R(1e-4)) * dmax;
+    int bad = 0;
+    for (int j = 0; j < k; ++j) {
+        R d = A[j * k + j];
+        for (int q = 0; q < j; ++q) d = fma(-A[j * k + q], A[j * k + q], d);
+        const bool ok = d > tol;
+        if (d < -neg) bad = BKF_STATUS_NOT_PD;
+        const R ljj = ok ? sqrt(d) : R(0), inv = ok ? R(1) / ljj : R(0);
+        __syncwarp();
+        for (int i = j + 1 + lane; i < k; i += 32) {
+            R tv = A[i * k + j];
+            for (int q = 0; q < j; ++q) tv = fma(-A[i * k + q], A[j * k + q], tv);
+            A[i * k + j] = tv * inv;
+        }
+        if (lane == 0) A[j * k + j] = ljj;
+        for (int i = lane; i < j; i += 32) A[i * k + j] = 0;
+        __syncwarp();
+    }
+    return bad;
+}
+
+__host__ __device__ inline size_t sim_arena_elems(int m, int p, int r) {
+    size_t tot = /*L0,T*/ 2 * (size_t)m * m + /*Z*/ (size_t)p * m + /*RL*/ (size_t)m * r + /*LH*/ (size_t)p * p +
+                 /*LQ*/ (size_t)r * r + /*a,an,c*/ 3 * (size_t)m + /*d*/ (size_t)p + /*zs*/ (size_t)r + /*zo*/ (size_t)p;
+    return (tot + 1) & ~(size_t)1;
+}
+
+template <typename R>
+__global__ void simulate_kernel(KArgs<R> g, const R* __restrict__ z_x0, const R* __restrict__ z_y0,
+                                const R* __restrict__ z_state, const R* __restrict__ z_obs, R* __restrict__ xs,
+                                R* __restrict__ ys, int wpc, size_t arena) {
+    extern __shared__ double smem_raw[];
+    R* s_ = reinterpret_cast<R*>(smem_raw);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int b = blockIdx.x * wpc + warp;
+    if (b >= g.B) return;
+    const int m = g.m, p = g.p, r = g.r, n = g.n;
+    R* L0 = s_ + (size_t)warp * arena;
+    R *Tm = L0 + m * m, *Zm = Tm + m * m, *RL = Zm + p * m, *LH = RL + m * r, *LQ = LH + p * p, *a = LQ + r * r,
+      *an = a + m, *cv = an + m, *dv = cv + m, *zs = dv + p, *zo = zs + r;
+    auto ld = [&](R* dst, const R* src, int which, size_t sz) {
+        const R* q = param_ptr(src, g.shared_mask, which, b, sz);
+        for (int i = lane; i < (int)sz; i += 32) dst[i] = q[i];
+    };
+    ld(L0, g.P0, BKF_PARAM_P0, (size_t)m * m);
+    ld(Tm, g.T, BKF_PARAM_T, (size_t)m * m);
+    ld(Zm, g.Z, BKF_PARAM_Z, (size_t)p * m);
+    ld(LH, g.H, BKF_PARAM_H, (size_t)p * p);
+    ld(LQ, g.Q, BKF_PARAM_Q, (size_t)r * r);
+    ld(cv, g.c, BKF_PARAM_C, (size_t)m);
+    ld(dv, g.d, BKF_PARAM_D, (size_t)p);
+    __syncwarp();
+    int st = chol_psd_warp(L0, m, lane) | chol_psd_warp(LH, p, lane) | chol_psd_warp(LQ, r, lane);
+    const R* Rg = param_ptr(g.Rm, g.shared_mask, BKF_PARAM_R, b, (size_t)m * r);
+    for (int idx = lane; idx < m * r; idx += 32) {
+        const int i = idx / r, k = idx - i * r;
+        R acc = 0;
+        for (int l = k; l < r; ++l) acc = fma(Rg[i * r + l], LQ[l * r + k], acc);
+        RL[idx] = acc;
+    }
+    const R* a0 = param_ptr(g.a0, g.shared_mask, BKF_PARAM_A0, b, (size_t)m);
+    R* xb = xs + (size_t)b * (n + 1) * m;
+    R* yb = ys + (size_t)b * (n + 1) * p;
+    // x_0 = a0 + L0 z ;  y_0 = Z x_0 + LH z'
+    for (int i = lane; i < m; i += 32) an[i] = z_x0[(size_t)b * m + i];
+    for (int i = lane; i < p; i += 32) zo[i] = z_y0[(size_t)b * p + i];
+    __syncwarp();
+    for (int i = lane; i < m; i += 32) {
+        R acc = a0[i];
+        for (int k = 0; k <= i; ++k) acc = fma(L0[i * m + k], an[k], acc);
+        a[i] = acc;
+        xb[i] = acc;
+    }
+    __syncwarp();
+    for (int o = lane; o < p; o += 32) {
+        R acc = 0;
+        for (int j = 0; j < m; ++j) acc = fma(Zm[o * m + j], a[j], acc);
+        for (int k = 0; k <= o; ++k) acc = fma(LH[o * p + k], zo[k], acc);
+        yb[o] = acc;
+    }
+    for (int t = 0; t < n; ++t) {
+        __syncwarp();
+        for (int i = lane; i < r; i += 32) zs[i] = z_state[((size_t)b * n + t) * r + i];
+        for (int i = lane; i < p; i += 32) zo[i] = z_obs[((size_t)b * n + t) * p + i];
+        __syncwarp();
+        for (int i = lane; i < m; i += 32) {
+            R acc = cv[i];
+            for (int j = 0; j < m; ++j) acc = fma(Tm[i * m + j], a[j], acc);
+            for (int k = 0; k < r; ++k) acc = fma(RL[i * r + k], zs[k], acc);
+            an[i] = acc;
+            xb[(size_t)(t + 1) * m + i] = acc;
+        }
+        __syncwarp();
+        for (int o = lane; o < p; o += 32) {
+            R acc = dv[o];
+            for (int j = 0; j < m; ++j) acc = fma(Zm[o * m + j], an[j], acc);
+            for (int k = 0; k <= o; ++k) acc = fma(LH[o * p + k], zo[k], acc);
+            yb[(size_t)(t + 1) * p + o] = acc;
+        }
+        for (int i = lane; i < m; i += 32) a[i] = an[i];
+    }
+    if (lane == 0 && g.status) g.status[b] = st;
+}
+
+template <typename R>
+int launch_simulate(const KArgs<R>& g, const R* z_x0, const R* z_y0, const R* z_state, const R* z_obs, R* xs, R* ys,
+                    cudaStream_t stream, const char** err) {
+    const size_t arena = sim_arena_elems(g.m, g.p, g.r), arena_bytes = arena * sizeof(R);
+    if (arena_bytes > 227 * 1024) { *err = "problem too large for the simulation kernel (m, p, r)"; return BKF_ERR_UNSUPPORTED; }
+    int wpc = 4;
+    while (wpc > 1 && arena_bytes * wpc > 96 * 1024) wpc >>= 1;
+    const size_t smem = arena_bytes * wpc;
+    auto kern = simulate_kernel<R>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) { *err = cudaGetErrorString(e); return BKF_ERR_CUDA; }
+    kern<<<(g.B + wpc - 1) / wpc, 32 * wpc, smem, stream>>>(g, z_x0, z_y0, z_state, z_obs, xs, ys, wpc, arena);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) { *err = cudaGetErrorString(e); return BKF_ERR_CUDA; }
+    return BKF_OK;
+}
+
+template int launch_simulate<double>(const KArgs<double>&, const double*, const double*, const double*, const double*,
+                                     double*, double*, cudaStream_t, const char**);
+template int launch_simulate<float>(const KArgs<float>&, const float*, const float*, const float*, const float*, float*,
+                                    float*, cudaStream_t, const char**);
+
 template int launch<double>(const double*, const double*, const double*, double*, int*, long long, int, int, cudaStream_t,
                             const char**);
 template int launch<float>(const float*, const float*, const float*, float*, int*, long long, int, int, cudaStream_t,

@@ -34,7 +34,7 @@ ABI_SYMBOLS = (
     "bkf_last_path", "bkf_enable_timing", "bkf_reset_timing", "bkf_kernel_time_ms", "bkf_measure_fma_peak",
     "bkf_filter_forward", "bkf_filter_logp_grad", "bkf_smooth", "bkf_filter_smooth", "bkf_host_alloc", "bkf_host_free",
     "bkf_logp_grad_workspace_bytes", "bkf_device_memory", "bkf_filter_logp_grad_compact", "bkf_stationary_init",
-    "bkf_stationary_init_grad", "bkf_mvn_sample",
+    "bkf_stationary_init_grad", "bkf_mvn_sample", "bkf_simulate",
 )
 
 
@@ -92,6 +92,7 @@ def load_library():
     lib.bkf_stationary_init.argtypes = [vp, pp] + [vp] * 4 + [vp] * 2 + [vp]
     lib.bkf_stationary_init_grad.argtypes = [vp, pp] + [vp] * 7 + [vp] * 4
     lib.bkf_mvn_sample.argtypes = [vp, pp] + [vp] * 3 + [vp] + [vp]
+    lib.bkf_simulate.argtypes = [vp, pp] + [vp] * 9 + [vp] * 4 + [vp] * 2 + [vp]
     lib.bkf_smooth.argtypes = [vp, pp] + [vp] * 5 + [vp] * 2 + [vp]
     lib.bkf_filter_smooth.argtypes = [vp, pp] + [vp] * 10 + [vp] * 3 + [vp]
     _lib = lib
@@ -566,6 +567,32 @@ class KalmanEngine:
         self._check(self.lib.bkf_mvn_sample(self.h, C.byref(prob), bufs.ptr(dmu), bufs.ptr(dcov), bufs.ptr(dz),
                                             bufs.ptr(x), bufs.ptr(status)))
         return (x[0], status[0]) if squeeze else (x, status)
+
+    def simulate(self, a0, P0, c, d, T, Z, R, H, Q, z_x0, z_y0, z_state, z_obs, dtype=None):
+        """Unconditional simulation of B models (``bkf_simulate``; ``LinearGaussianStateSpace.rv_op``,
+        filters/distributions.py:181-293).  ``z_x0`` (B, m), ``z_y0`` (B, p), ``z_state`` (B, n, r), ``z_obs`` (B, n, p):
+        standard normal variates (they define B and the number of steps n).  Parameters may be batched or shared.
+        Returns ``(states (B, n+1, m), obs (B, n+1, p), status)``; row 0 is the initial draw."""
+        params = dict(zip(PARAM_NAMES, (a0, P0, c, d, T, Z, R, H, Q)))
+        bufs = _Buffers([z_x0, z_y0, z_state, z_obs, *params.values()], dtype)
+        conv = lambda v: v if _is_torch(v) else np.asarray(v)
+        params = {k_: conv(v) for k_, v in params.items()}
+        z_x0, z_y0, z_state, z_obs = conv(z_x0), conv(z_y0), conv(z_state), conv(z_obs)
+        if z_state.ndim != 3 or z_obs.ndim != 3 or z_x0.ndim != 2 or z_y0.ndim != 2:
+            raise BkfError("simulate: expected z_x0 (B, m), z_y0 (B, p), z_state (B, n, r), z_obs (B, n, p)")
+        B, n = int(z_state.shape[0]), int(z_state.shape[1])
+        prob, _, arrs = self._problem(STANDARD, bufs, z_obs, params, B, None, None)
+        m, p, r = prob.m, prob.p, prob.r
+        if tuple(z_x0.shape) != (B, m) or tuple(z_y0.shape) != (B, p) or tuple(z_state.shape) != (B, n, r) or \
+                tuple(z_obs.shape) != (B, n, p):
+            raise BkfError("simulate: variate shapes do not match the model (m, p, r) / batch / steps")
+        zs = [bufs.inp(v) for v in (z_x0, z_y0, z_state, z_obs)]
+        states, obs, status = bufs.out((B, n + 1, m)), bufs.out((B, n + 1, p)), bufs.out_int((B,))
+        if bufs.device:
+            self.use_torch_stream()
+        self._check(self.lib.bkf_simulate(self.h, C.byref(prob), *[bufs.ptr(x) for x in arrs], *[bufs.ptr(x) for x in zs],
+                                          bufs.ptr(states), bufs.ptr(obs), bufs.ptr(status)))
+        return states, obs, status
 
     def _logp_grad_in_slices(self, kind, y, params, ll_cotangent, B, nslices, kw):
         """Series are independent: a batch whose trajectory workspace would not fit the device is processed in

@@ -596,3 +596,57 @@ def test_sample_sequence_mvnormal_host_mirror(eng):
     z = np.random.default_rng(9).standard_normal(mus.shape)
     L = np.linalg.cholesky(covs)
     assert_allclose(x1, mus + np.einsum("...ij,...j->...i", L, z), rtol=0, atol=1e-11 * np.abs(x1).max())
+
+
+@pytest.mark.parametrize("shape", [(3, 1, 1), (15, 1, 5), (8, 3, 2), (32, 16, 16)])
+def test_simulate_matches_oracle(eng, shape):
+    """Row f-3: LinearGaussianStateSpace.rv_op (unconditional simulation) against its restatement, batched and shared
+    parameters, a rank-deficient Q, host and device pointers."""
+    import torch
+
+    from oracle import sampling as osm
+    from pymc_experimental_b200 import synth
+
+    m, p, r = shape
+    B, n = 6, 11
+    cfg = synth.random_dense(B, n, m, p, r, seed=40 + m)
+    cfg["Q"][2] = cfg["Q"][2][:, :1] @ cfg["Q"][2][:, :1].T  # rank one
+    rng = np.random.default_rng(m)
+    zs = [rng.standard_normal(sh) for sh in ((B, m), (B, p), (B, n, r), (B, n, p))]
+    xs, ys, status = eng.simulate(*[cfg[k] for k in NAMES], *zs)
+    assert eng.last_path == "simulate_warp" and int(np.abs(status).sum()) == 0
+    for b in range(B):
+        rx, ry = osm.simulate(*[cfg[k][b] for k in NAMES], *[z[b] for z in zs])
+        assert_allclose(xs[b], rx, rtol=0, atol=1e-10 * np.abs(rx).max())
+        assert_allclose(ys[b], ry, rtol=0, atol=1e-10 * np.abs(ry).max())
+    shared = dict(cfg, T=cfg["T"][0], Z=cfg["Z"][0], R=cfg["R"][0], Q=cfg["Q"][0])
+    xs2, ys2, _ = eng.simulate(*[torch.as_tensor(shared[k], device="cuda") for k in NAMES],
+                               *[torch.as_tensor(z, device="cuda") for z in zs])
+    rx, ry = osm.simulate(*[(shared[k] if shared[k].ndim < cfg[k].ndim else shared[k][1]) for k in NAMES],
+                          *[z[1] for z in zs])
+    assert_allclose(xs2[1].cpu().numpy(), rx, rtol=0, atol=1e-10 * np.abs(rx).max())
+    assert_allclose(ys2[1].cpu().numpy(), ry, rtol=0, atol=1e-10 * np.abs(ry).max())
+
+
+def test_simulate_then_filter_is_calibrated(eng):
+    """Size-independent property tying the simulator to the filter: for data simulated from the model, the standardised
+    one-step innovations of the Kalman filter are white with unit variance, so sum_t v_t^2 / F_t ~ chi2(T) per series."""
+    from pymc_experimental_b200 import synth
+    from pymc_experimental_b200.sampling import simulate_statespace
+
+    cfg = synth.structural(B=2048, n=5)
+    steps = 200
+    out = simulate_statespace(*[cfg[k] for k in NAMES], steps=steps, rng=np.random.default_rng(2), engine=eng,
+                              append_x0=False)
+    assert out.shape == (2048, steps, 16)
+    y = out[..., 15:]
+    # y_1.. are generated from x_0 ~ N(a0, P0) one transition earlier: the matching prior for y_1 is the prediction of x_1
+    a1 = np.einsum("bij,bj->bi", cfg["T"], cfg["a0"]) + cfg["c"]
+    RQR = cfg["R"] @ cfg["Q"] @ cfg["R"].transpose(0, 2, 1)
+    P1 = cfg["T"] @ cfg["P0"] @ cfg["T"].transpose(0, 2, 1) + RQR
+    f = eng.filter("standard", y, a1, P1, *[cfg[k] for k in NAMES[2:]],
+                   outputs=("observed_states", "observed_covariances"))
+    v = y - f["observed_states"]
+    q = (v[..., 0] ** 2 / f["observed_covariances"][..., 0, 0]).sum(-1)  # chi2(steps): mean steps, var 2 steps
+    assert abs(q.mean() - steps) < 5 * np.sqrt(2 * steps / 2048)
+    assert abs(q.var() / (2 * steps) - 1.0) < 0.2

@@ -33,3 +33,19 @@ bytes_ = B * T * (m * m + 3 * m) * 8  # cov + mu + z read, x written
 print(json.dumps({"workload": f"C3 smoother output, {B} x {T}, m={m}: one MvNormal draw per (draw, step)", "ms": ms,
                   "draws_per_s": B * T / ms * 1e3, "algorithmic_bytes": bytes_, "achieved_GBs": bytes_ / ms / 1e6,
                   "hbm_peak_GBs": 6538.9, "frac": bytes_ / ms / 1e6 / 6538.9, "path": eng.last_path}))
+
+# unconditional simulation (bkf_simulate) of the same models: B series x T steps
+g = torch.Generator(device="cuda:0").manual_seed(3)
+r, p = d["R"].shape[-1], d["Z"].shape[-2]
+zs = [torch.randn(sh, dtype=torch.float64, device="cuda:0", generator=g) for sh in ((B, m), (B, p), (B, T, r), (B, T, p))]
+for _ in range(3):
+    xs, ys, _ = eng.simulate(*[d[k] for k in PARAM_NAMES], *zs)
+torch.cuda.synchronize()
+e0.record()
+for _ in range(steps):
+    xs, ys, _ = eng.simulate(*[d[k] for k in PARAM_NAMES], *zs)
+e1.record()
+torch.cuda.synchronize()
+ms = e0.elapsed_time(e1) / steps
+print(json.dumps({"workload": f"C3 model, {B} series x {T} steps: unconditional simulation (states + observations)",
+                  "ms": ms, "state_steps_per_s": B * T / ms * 1e3, "path": eng.last_path}))
