@@ -18,6 +18,17 @@
 namespace bkf {
 namespace smp {
 
+// 1 / sqrt(d) for a positive, normal pivot: hardware seed + two Newton steps (a third of the IEEE sqrt + divide sequence)
+__device__ __forceinline__ double pivot_rsqrt(double x) {
+    double r;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    const double hx = 0.5 * x;
+#pragma unroll
+    for (int i = 0; i < 2; ++i) r = fma(r, fma(-hx * r, r, 0.5), r);
+    return r;
+}
+__device__ __forceinline__ float pivot_rsqrt(float x) { return rsqrtf(x); }
+
 template <typename R, int G>
 __global__ void __launch_bounds__(128) sample_kernel(const R* __restrict__ mu, const R* __restrict__ cov,
                                                     const R* __restrict__ z, R* __restrict__ x, int* __restrict__ status,
@@ -54,9 +65,8 @@ __global__ void __launch_bounds__(128) sample_kernel(const R* __restrict__ mu, c
             const R d = __shfl_sync(gmask, acc, base + j);
             const bool ok = d > tol;
             if (d < -neg) bad = BKF_STATUS_NOT_PD;
-            const R ljj = ok ? sqrt(d) : R(0);
-            const R inv = ok ? R(1) / ljj : R(0);
-            l[j] = i == j ? ljj : (i > j ? acc * inv : R(0));
+            const R inv = ok ? pivot_rsqrt(d) : R(0);
+            l[j] = i >= j ? acc * inv : R(0);  // the diagonal: d / sqrt(d)
         }
     }
     const R zi = (live && i < m) ? z[mm * m + i] : R(0);
