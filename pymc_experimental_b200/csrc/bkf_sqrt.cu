@@ -506,25 +506,36 @@ __device__ void carve(Arena<R>& A, R* s, int m, int p, int r, bool bwd) {
     }
 }
 
-// Per-series setup shared by forward and backward.  Returns status bits; *Hzero_out = all(H == 0) (:666).
+// Per-series parameters shared by forward and backward.  first: load everything (step t of the time-varying ones) and
+// hoist the time-invariant factors; otherwise only what carries a time axis is refreshed for step t (c, d, T, Z, H --
+// filters/utilities.py:8-47; R and Q are refused upstream for this family).  Returns status bits;
+// *Hzero_io = all(H_t == 0) (:666).
 template <typename R>
-__device__ int setup(const KArgs<R>& g, Arena<R>& A, int b, bool* Hzero_out, Th th) {
-    const int m = g.m, p = g.p, r = g.r;
-    bcopy(A.T, param_ptr(g.T, g.shared_mask, BKF_PARAM_T, b, (size_t)m * m), m * m, th);
-    bcopy(A.Z, param_ptr(g.Z, g.shared_mask, BKF_PARAM_Z, b, (size_t)p * m), p * m, th);
-    bcopy(A.Hc, param_ptr(g.H, g.shared_mask, BKF_PARAM_H, b, (size_t)p * p), p * p, th);
-    bcopy(A.Qc, param_ptr(g.Q, g.shared_mask, BKF_PARAM_Q, b, (size_t)r * r), r * r, th);
-    bcopy(A.c, param_ptr(g.c, g.shared_mask, BKF_PARAM_C, b, (size_t)m), m, th);
-    bcopy(A.d, param_ptr(g.d, g.shared_mask, BKF_PARAM_D, b, (size_t)p), p, th);
+__device__ int load_params(const KArgs<R>& g, Arena<R>& A, int b, int t, bool first, bool* Hzero_io, Th th) {
+    const int m = g.m, p = g.p, r = g.r, n = g.n;
+    auto want = [&](int which) { return first || ((g.tv_mask >> which) & 1u); };
+    auto src = [&](const R* base, int which, size_t sz) {
+        return param_ptr_t(base, g.shared_mask, g.tv_mask, which, b, t, n, sz);
+    };
+    if (want(BKF_PARAM_T)) bcopy(A.T, src(g.T, BKF_PARAM_T, (size_t)m * m), m * m, th);
+    if (want(BKF_PARAM_Z)) bcopy(A.Z, src(g.Z, BKF_PARAM_Z, (size_t)p * m), p * m, th);
+    if (want(BKF_PARAM_C)) bcopy(A.c, src(g.c, BKF_PARAM_C, (size_t)m), m, th);
+    if (want(BKF_PARAM_D)) bcopy(A.d, src(g.d, BKF_PARAM_D, (size_t)p), p, th);
     int st = 0;
-    bool Hzero = true;
-    for (int i = 0; i < p * p; ++i) Hzero = Hzero && (A.Hc[i] == R(0));
-    __syncthreads();
-    if (!Hzero && !chol_lower(A.Hc, p, th)) st |= BKF_STATUS_NOT_PD;
-    if (!chol_lower(A.Qc, r, th)) st |= BKF_STATUS_NOT_PD;
-    const R* Rg = param_ptr(g.Rm, g.shared_mask, BKF_PARAM_R, b, (size_t)m * r);
-    mm<SET>(A.RQc, r, Rg, r, 1, A.Qc, r, 1, m, r, r, th);
-    *Hzero_out = Hzero;
+    if (want(BKF_PARAM_H)) {
+        bcopy(A.Hc, src(g.H, BKF_PARAM_H, (size_t)p * p), p * p, th);
+        bool Hzero = true;
+        for (int i = 0; i < p * p; ++i) Hzero = Hzero && (A.Hc[i] == R(0));
+        __syncthreads();
+        if (!Hzero && !chol_lower(A.Hc, p, th)) st |= BKF_STATUS_NOT_PD;
+        *Hzero_io = Hzero;
+    }
+    if (first) {
+        bcopy(A.Qc, param_ptr(g.Q, g.shared_mask, BKF_PARAM_Q, b, (size_t)r * r), r * r, th);
+        if (!chol_lower(A.Qc, r, th)) st |= BKF_STATUS_NOT_PD;
+        const R* Rg = param_ptr(g.Rm, g.shared_mask, BKF_PARAM_R, b, (size_t)m * r);
+        mm<SET>(A.RQc, r, Rg, r, 1, A.Qc, r, 1, m, r, r, th);
+    }
     return st;
 }
 
@@ -722,7 +733,7 @@ __global__ void __launch_bounds__(NT, NT == 128 ? 3 : 2) forward_kernel(KArgs<R>
     Arena<R> A;
     carve(A, smem, m, p, g.r, false);
     bool Hzero;
-    int st = setup(g, A, b, &Hzero, th);
+    int st = load_params(g, A, b, 0, true, &Hzero, th);
     bcopy(A.a, param_ptr(g.a0, g.shared_mask, BKF_PARAM_A0, b, (size_t)m), m, th);
     bcopy(A.Pc, param_ptr(g.P0, g.shared_mask, BKF_PARAM_P0, b, (size_t)m * m), m * m, th);
     const R* yb = g.y_shared ? g.y : g.y + (size_t)b * n * p;
@@ -739,6 +750,7 @@ __global__ void __launch_bounds__(NT, NT == 128 ? 3 : 2) forward_kernel(KArgs<R>
     R logp = 0;
     for (int t = 0; t < n; ++t) {
         const size_t bt = (size_t)b * n + t;
+        if (g.tv_mask && t > 0) st |= load_params(g, A, b, t, false, &Hzero, th);
         if (g.traj) {
             bcopy(g.traj + bt * tstride, A.a, m, th);
             bcopy(g.traj + bt * tstride + m, A.Pc, m * m, th);
@@ -781,14 +793,49 @@ __global__ void backward_kernel(KArgs<R> g) {
     Arena<R> A;
     carve(A, smem, m, p, r, true);
     bool Hzero;
-    setup(g, A, b, &Hzero, th);
+    load_params(g, A, b, n - 1, true, &Hzero, th);
     bzero(A.abar, m, th); bzero(A.Pbar, m * m, th); bzero(A.gT, m * m, th); bzero(A.Psum, m * m, th);
     bzero(A.gZ, p * m, th); bzero(A.gc, m, th); bzero(A.gd, p, th); bzero(A.Hcbar, p * p, th);
     const R* yb = g.y_shared ? g.y : g.y + (size_t)b * n * p;
     const size_t tstride = traj_record_elems(m, p);
     const size_t off_rf = (size_t)m + (size_t)m * m, off_rp = off_rf + (size_t)N1 * (N1 + 1) / 2;
+    // a time-varying parameter receives one gradient record per step: hand the step's contribution out and restart
+    // the accumulator (the Cholesky pull-back of H_t runs per step as well)
+    auto tv = [&](int which) { return (g.tv_mask >> which) & 1u; };
+    auto flush_tv = [&](int t) {
+        if (!g.tv_mask) return;
+        const size_t bt = (size_t)b * n + t;
+        if (tv(BKF_PARAM_T)) {
+            if (g.g_T) bcopy(g.g_T + bt * m * m, A.gT, m * m, th);
+            bzero(A.gT, m * m, th);
+        }
+        if (tv(BKF_PARAM_Z)) {
+            if (g.g_Z) bcopy(g.g_Z + bt * p * m, A.gZ, p * m, th);
+            bzero(A.gZ, p * m, th);
+        }
+        if (tv(BKF_PARAM_C)) {
+            if (g.g_c) bcopy(g.g_c + bt * m, A.gc, m, th);
+            bzero(A.gc, m, th);
+        }
+        if (tv(BKF_PARAM_D)) {
+            if (g.g_d) bcopy(g.g_d + bt * p, A.gd, p, th);
+            bzero(A.gd, p, th);
+        }
+        if (tv(BKF_PARAM_H)) {
+            if (g.g_H) {
+                if (Hzero) {
+                    bcopy(g.g_H + bt * p * p, A.Hcbar, p * p, th);
+                } else {
+                    chol_pullback(A.Psi, A.Hc, A.Hcbar, p, A.S1, th);
+                    bcopy(g.g_H + bt * p * p, A.Psi, p * p, th);
+                }
+            }
+            bzero(A.Hcbar, p * p, th);
+        }
+    };
     for (int t = n - 1; t >= 0; --t) {
         const size_t bt = (size_t)b * n + t;
+        if (g.tv_mask && t < n - 1) load_params(g, A, b, t, false, &Hzero, th);
         const R gcot = g.ll_cot ? g.ll_cot[bt] : R(1);
         bcopy(A.a, g.traj + bt * tstride, m, th);
         bcopy(A.Pc, g.traj + bt * tstride + m, m * m, th);
@@ -818,6 +865,7 @@ __global__ void backward_kernel(KArgs<R> g) {
         if (flag) {  // degenerate branch (:700-705): (a_f, Pcf0, ll) = (a, Pc, 0)
             bcopy(A.abar, A.afbar, m, th);
             bcopy(A.Pbar, A.Pcfbar, m * m, th);
+            flush_tv(t);
             continue;
         }
         // ================= update adjoint =================
@@ -943,14 +991,18 @@ __global__ void backward_kernel(KArgs<R> g) {
         }
         for (int o = th.tid; o < p; o += th.nt) A.gd[o] -= A.vbar[o];
         __syncthreads();
+        flush_tv(t);
     }
     // ---- gradients out ----
     auto put = [&](R* dst, const R* src, size_t sz) {
         if (dst) bcopy(dst + (size_t)b * sz, src, (int)sz, th);
     };
-    put(g.g_a0, A.abar, m); put(g.g_P0, A.Pbar, (size_t)m * m); put(g.g_c, A.gc, m); put(g.g_d, A.gd, p);
-    put(g.g_T, A.gT, (size_t)m * m); put(g.g_Z, A.gZ, (size_t)p * m);
-    if (g.g_H) {
+    put(g.g_a0, A.abar, m); put(g.g_P0, A.Pbar, (size_t)m * m);
+    if (!tv(BKF_PARAM_C)) put(g.g_c, A.gc, m);
+    if (!tv(BKF_PARAM_D)) put(g.g_d, A.gd, p);
+    if (!tv(BKF_PARAM_T)) put(g.g_T, A.gT, (size_t)m * m);
+    if (!tv(BKF_PARAM_Z)) put(g.g_Z, A.gZ, (size_t)p * m);
+    if (g.g_H && !tv(BKF_PARAM_H)) {
         if (Hzero) {
             put(g.g_H, A.Hcbar, (size_t)p * p);
         } else {

@@ -427,13 +427,44 @@ def test_time_varying_matrices_batched(eng, kind, tv, shape):
         _close(sP[b], rP, 1e-8, f"smoothed_covariances[{b}]")
 
 
-def test_time_varying_square_root_filter_is_refused(eng):
+@pytest.mark.parametrize("shape", [(5, 2, 3), (16, 8, 8)])
+@pytest.mark.parametrize("tv", [("Z",), ("c", "d"), ("T", "H"), ("c", "d", "T", "Z", "H")])
+def test_time_varying_square_root_filter(eng, tv, shape):
+    """SquareRootFilter with a time axis on c, d, T, Z, H (exogenous intercepts, regression loadings: the cases the
+    reference's models produce): filter outputs, logp and gradients (per-step records for the time-varying inputs, the
+    Cholesky pull-back of H_t per step) against autograd through the oracle; one whole-step missing observation."""
+    import torch
+
+    from oracle import kalman_torch as oth
+    from pymc_experimental_b200 import synth
+
+    m, p, r = shape
+    B, n = 5, 9
+    cfg = synth.random_dense_tv(B, n, m, p, r, tv, seed=13 * m + len(tv))
+    cfg["y"][1, 4] = np.nan
+    cfg["P0"] = np.linalg.cholesky(cfg["P0"])
+    args = [cfg["y"]] + [cfg[k] for k in NAMES]
+    out = eng.filter("cholesky", *args, time_varying=tv)
+    assert eng.last_path == "sqrt_cta"
+    ref = oth.kalman_filter("cholesky", *[torch.as_tensor(a) for a in args], time_varying=tv)
+    for got, want in zip([out[k] for k in OUT_NAMES], ref):
+        _close(got, want.numpy(), RTOL64, f"cholesky tv={tv}")
+    logp, grads, status = eng.logp_grad("cholesky", *args, time_varying=tv)
+    ref_logp, ref_g = oth.logp_and_grad("cholesky", *args, time_varying=tv)
+    assert_allclose(logp, ref_logp, rtol=RTOL64)
+    for k in NAMES:
+        assert grads[k].shape == cfg[k].shape
+        for b in range(B):
+            _close(grads[k][b], ref_g[k][b], 1e-8, f"cholesky tv={tv} d/d{k}[{b}]")
+
+
+def test_time_varying_R_or_Q_with_the_square_root_filter_is_refused(eng):
     from pymc_experimental_b200 import synth
     from pymc_experimental_b200.engine import BkfError
 
-    cfg = synth.random_dense_tv(2, 6, 3, 2, 2, ("Z",), seed=3)
+    cfg = synth.random_dense_tv(2, 6, 3, 2, 2, ("Q",), seed=3)
     with pytest.raises(BkfError, match="square-root"):
-        eng.filter("cholesky", cfg["y"], *[cfg[k] for k in NAMES], time_varying=("Z",))
+        eng.filter("cholesky", cfg["y"], *[cfg[k] for k in NAMES], time_varying=("Q",))
 
 
 @pytest.mark.parametrize("device", [False, True])
