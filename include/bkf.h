@@ -79,7 +79,7 @@ typedef struct bkf_problem {
                               Q [B,n,r,r] (filters/utilities.py:8-47; never a0, P0).  Step t uses x[t]
                               (kalman_filter.py:110-142); the smoother pairs filtered[t] with x[t+1]
                               (kalman_smoother.py:84-92).  Gradients of time-varying
-                              parameters have the same time axis.  Standard / univariate filters and smoother. */
+                              parameters have the same time axis.  All three filters and the smoother. */
     double cov_jitter;     /* JITTER_DEFAULT: 1e-8 (f64) / 1e-6 (f32), utils/constants.py:20 */
     double missing_fill;   /* MISSING_FILL = -9999.0, utils/constants.py:19 */
 } bkf_problem;

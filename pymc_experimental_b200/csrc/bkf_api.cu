@@ -360,9 +360,6 @@ static int validate(bkf_handle* h, const bkf_problem* P, bool need_obs) {
         return fail(h, BKF_ERR_ARG, "non-positive dimension");
     if (P->tv_mask & ((1u << BKF_PARAM_A0) | (1u << BKF_PARAM_P0)))
         return fail(h, BKF_ERR_ARG, "a0 and P0 are never time-varying (utils/constants.py NEVER_TIME_VARYING)");
-    if (P->kind == BKF_CHOLESKY && (P->tv_mask & ((1u << BKF_PARAM_R) | (1u << BKF_PARAM_Q))))
-        return fail(h, BKF_ERR_UNSUPPORTED,
-                    "time-varying R or Q are not supported by the square-root filter kernels yet (c, d, T, Z, H are)");
     cudaError_t e = cudaSetDevice(h->device);
     if (e != cudaSuccess) return cuda_fail(h, e, "cudaSetDevice");
     return BKF_OK;

@@ -507,8 +507,8 @@ __device__ void carve(Arena<R>& A, R* s, int m, int p, int r, bool bwd) {
 }
 
 // Per-series parameters shared by forward and backward.  first: load everything (step t of the time-varying ones) and
-// hoist the time-invariant factors; otherwise only what carries a time axis is refreshed for step t (c, d, T, Z, H --
-// filters/utilities.py:8-47; R and Q are refused upstream for this family).  Returns status bits;
+// hoist the time-invariant factors; otherwise only what carries a time axis is refreshed for step t
+// (filters/utilities.py:8-47).  Returns status bits;
 // *Hzero_io = all(H_t == 0) (:666).
 template <typename R>
 __device__ int load_params(const KArgs<R>& g, Arena<R>& A, int b, int t, bool first, bool* Hzero_io, Th th) {
@@ -530,12 +530,12 @@ __device__ int load_params(const KArgs<R>& g, Arena<R>& A, int b, int t, bool fi
         if (!Hzero && !chol_lower(A.Hc, p, th)) st |= BKF_STATUS_NOT_PD;
         *Hzero_io = Hzero;
     }
-    if (first) {
-        bcopy(A.Qc, param_ptr(g.Q, g.shared_mask, BKF_PARAM_Q, b, (size_t)r * r), r * r, th);
+    if (want(BKF_PARAM_Q)) {
+        bcopy(A.Qc, src(g.Q, BKF_PARAM_Q, (size_t)r * r), r * r, th);
         if (!chol_lower(A.Qc, r, th)) st |= BKF_STATUS_NOT_PD;
-        const R* Rg = param_ptr(g.Rm, g.shared_mask, BKF_PARAM_R, b, (size_t)m * r);
-        mm<SET>(A.RQc, r, Rg, r, 1, A.Qc, r, 1, m, r, r, th);
     }
+    if (want(BKF_PARAM_Q) || want(BKF_PARAM_R))
+        mm<SET>(A.RQc, r, src(g.Rm, BKF_PARAM_R, (size_t)m * r), r, 1, A.Qc, r, 1, m, r, r, th);
     return st;
 }
 
@@ -783,6 +783,20 @@ __global__ void __launch_bounds__(NT, NT == 128 ? 3 : 2) forward_kernel(KArgs<R>
     }
 }
 
+// Cotangents of R and of the factor Qc from P = sum of Psi_p (or one step's Psi_p):
+//   X1 = P R,  gR = X1 (Qc Qc^T) -> A.Pcfbar[:m*r],  Qcbar = tril(R^T X1 Qc) -> A.S1[:r*r].   Scratch: U1, S1, Abar.
+template <typename R>
+__device__ void rq_cotangents(Arena<R>& A, const R* P, const R* Rg, int m, int r, Th th) {
+    mm<SET>(A.U1, r, P, m, 1, Rg, r, 1, m, r, m, th);            // X1
+    mm<SET>(A.S1, r, A.Qc, r, 1, A.Qc, 1, r, r, r, r, th);        // Qc Qc^T
+    mm<SET>(A.Pcfbar, r, A.U1, r, 1, A.S1, r, 1, m, r, r, th);    // gR
+    mm<SET>(A.Abar, r, A.U1, r, 1, A.Qc, r, 1, m, r, r, th);      // X1 Qc (m x r)
+    mm<SET>(A.S1, r, Rg, 1, r, A.Abar, r, 1, r, r, m, th);        // R^T X1 Qc (r x r)
+    for (int idx = th.tid; idx < r * r; idx += th.nt)
+        if ((idx % r) > (idx / r)) A.S1[idx] = 0;
+    __syncthreads();
+}
+
 template <typename R>
 __global__ void backward_kernel(KArgs<R> g) {
     extern __shared__ double smem_raw[];
@@ -802,6 +816,7 @@ __global__ void backward_kernel(KArgs<R> g) {
     // a time-varying parameter receives one gradient record per step: hand the step's contribution out and restart
     // the accumulator (the Cholesky pull-back of H_t runs per step as well)
     auto tv = [&](int which) { return (g.tv_mask >> which) & 1u; };
+    const bool tv_rq = tv(BKF_PARAM_R) || tv(BKF_PARAM_Q);
     auto flush_tv = [&](int t) {
         if (!g.tv_mask) return;
         const size_t bt = (size_t)b * n + t;
@@ -847,7 +862,27 @@ __global__ void backward_kernel(KArgs<R> g) {
         // ================= predict adjoint =================
         // Rp_bar = triu(Pbar^T): Rbar(i,j) = Pbar[j*m + i]  ->  strides (rs0, rs1) = (1, m)
         qr_pullback_psi(A.Psi, A.Rp, m, m, A.Pbar, 1, m, A.S1, A.uinv, th);
-        for (int idx = th.tid; idx < m * m; idx += th.nt) A.Psum[idx] += A.Psi[idx];
+        if (!tv_rq) {
+            for (int idx = th.tid; idx < m * m; idx += th.nt) A.Psum[idx] += A.Psi[idx];
+        } else {
+            // R_t or Q_t carries a time axis: this step's Psi is pulled back through this step's R and Qc at once.
+            // The record goes out for the time-varying one; the other one accumulates in (the unused) Psum.
+            rq_cotangents(A, A.Psi, param_ptr_t(g.Rm, g.shared_mask, g.tv_mask, BKF_PARAM_R, b, t, n, (size_t)m * r), m, r, th);
+            if (tv(BKF_PARAM_R)) {
+                if (g.g_R) bcopy(g.g_R + bt * m * r, A.Pcfbar, m * r, th);
+            } else {
+                for (int idx = th.tid; idx < m * r; idx += th.nt) A.Psum[idx] += A.Pcfbar[idx];
+            }
+            if (tv(BKF_PARAM_Q)) {
+                if (g.g_Q) {
+                    chol_pullback(A.U1, A.Qc, A.S1, r, A.Abar, th);
+                    bcopy(g.g_Q + bt * r * r, A.U1, r * r, th);
+                }
+            } else {
+                for (int idx = th.tid; idx < r * r; idx += th.nt) A.Psum[idx] += A.S1[idx];
+            }
+            __syncthreads();
+        }
         // U1 = Psi (T Pcf), (T Pcf)[k,j] = M0[j*m + k]
         mm<SET>(A.U1, m, A.Psi, m, 1, A.M0, 1, m, m, m, m, th);
         // gT += U1 Pcf^T + abar af^T
@@ -1010,22 +1045,20 @@ __global__ void backward_kernel(KArgs<R> g) {
             put(g.g_H, A.Psi, (size_t)p * p);
         }
     }
-    const R* Rg = param_ptr(g.Rm, g.shared_mask, BKF_PARAM_R, b, (size_t)m * r);
-    // X1 = Psum R (m x r) in U1;  gR = X1 (Qc Qc^T);  Qcbar = tril(R^T X1 Qc)
-    mm<SET>(A.U1, r, A.Psum, m, 1, Rg, r, 1, m, r, m, th);
-    if (g.g_R) {
-        mm<SET>(A.S1, r, A.Qc, r, 1, A.Qc, 1, r, r, r, r, th);  // Qc Qc^T
-        mm<SET>(A.Pcfbar, r, A.U1, r, 1, A.S1, r, 1, m, r, r, th);
+    if (!tv_rq) {
+        rq_cotangents(A, A.Psum, param_ptr(g.Rm, g.shared_mask, BKF_PARAM_R, b, (size_t)m * r), m, r, th);
         put(g.g_R, A.Pcfbar, (size_t)m * r);
-    }
-    if (g.g_Q) {
-        mm<SET>(A.Pcfbar, r, A.U1, r, 1, A.Qc, r, 1, m, r, r, th);  // X1 Qc (m x r)
-        mm<SET>(A.Abar, r, Rg, 1, r, A.Pcfbar, r, 1, r, r, m, th);   // R^T X1 Qc (r x r)
-        for (int idx = th.tid; idx < r * r; idx += th.nt)
-            if ((idx % r) > (idx / r)) A.Abar[idx] = 0;
-        __syncthreads();
-        chol_pullback(A.Psi, A.Qc, A.Abar, r, A.S1, th);
-        put(g.g_Q, A.Psi, (size_t)r * r);
+        if (g.g_Q) {
+            chol_pullback(A.Psi, A.Qc, A.S1, r, A.Abar, th);
+            put(g.g_Q, A.Psi, (size_t)r * r);
+        }
+    } else if (!tv(BKF_PARAM_R)) {
+        put(g.g_R, A.Psum, (size_t)m * r);  // accumulated over the steps, Q_t time-varying
+    } else if (!tv(BKF_PARAM_Q)) {
+        if (g.g_Q) {  // factor cotangent accumulated over the steps, pulled back once through the constant Qc
+            chol_pullback(A.Psi, A.Qc, A.Psum, r, A.Abar, th);
+            put(g.g_Q, A.Psi, (size_t)r * r);
+        }
     }
 }
 

@@ -428,11 +428,12 @@ def test_time_varying_matrices_batched(eng, kind, tv, shape):
 
 
 @pytest.mark.parametrize("shape", [(5, 2, 3), (16, 8, 8)])
-@pytest.mark.parametrize("tv", [("Z",), ("c", "d"), ("T", "H"), ("c", "d", "T", "Z", "H")])
+@pytest.mark.parametrize("tv", [("Z",), ("c", "d"), ("T", "H"), ("R",), ("Q",), ("R", "Q"),
+                                ("c", "d", "T", "Z", "R", "H", "Q")])
 def test_time_varying_square_root_filter(eng, tv, shape):
-    """SquareRootFilter with a time axis on c, d, T, Z, H (exogenous intercepts, regression loadings: the cases the
-    reference's models produce): filter outputs, logp and gradients (per-step records for the time-varying inputs, the
-    Cholesky pull-back of H_t per step) against autograd through the oracle; one whole-step missing observation."""
+    """SquareRootFilter with a time axis on any of c, d, T, Z, R, H, Q (filters/utilities.py:8-47): filter outputs, logp
+    and gradients (per-step records for the time-varying inputs, the Cholesky pull-backs of H_t and Q_t per step, the
+    other of R / Q accumulated) against autograd through the oracle; one whole-step missing observation."""
     import torch
 
     from oracle import kalman_torch as oth
@@ -456,15 +457,6 @@ def test_time_varying_square_root_filter(eng, tv, shape):
         assert grads[k].shape == cfg[k].shape
         for b in range(B):
             _close(grads[k][b], ref_g[k][b], 1e-8, f"cholesky tv={tv} d/d{k}[{b}]")
-
-
-def test_time_varying_R_or_Q_with_the_square_root_filter_is_refused(eng):
-    from pymc_experimental_b200 import synth
-    from pymc_experimental_b200.engine import BkfError
-
-    cfg = synth.random_dense_tv(2, 6, 3, 2, 2, ("Q",), seed=3)
-    with pytest.raises(BkfError, match="square-root"):
-        eng.filter("cholesky", cfg["y"], *[cfg[k] for k in NAMES], time_varying=("Q",))
 
 
 @pytest.mark.parametrize("device", [False, True])
