@@ -193,7 +193,8 @@ int bkf_mvn_sample(bkf_handle* h, const bkf_problem* prob, const void* mu, const
  * Every normal draw is (Cholesky factor with dropped semidefinite pivots, as bkf_mvn_sample) x (standard normal variates
  * supplied by the caller): z_x0 [B,m], z_y0 [B,p], z_state [B,n,r], z_obs [B,n,p].  Outputs: states [B,n+1,m],
  * obs [B,n+1,p] (row 0 = the initial draw; the reference concatenates the two along the last axis, append_x0=True).
- * Parameters follow prob->shared_mask; time-varying matrices are refused (BKF_ERR_UNSUPPORTED).  status[B] (nullable):
+ * Parameters follow prob->shared_mask and prob->tv_mask (sequences of length n: step t uses x[t], the initial
+ * observation Z[0] and H[0], :259-260).  status[B] (nullable):
  * BKF_STATUS_NOT_PD if P0, H or Q is not positive semidefinite. */
 int bkf_simulate(bkf_handle* h, const bkf_problem* prob, const void* a0, const void* P0, const void* c, const void* d,
                  const void* T, const void* Z, const void* R, const void* H, const void* Q, const void* z_x0,

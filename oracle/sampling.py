@@ -45,16 +45,18 @@ def sample(mu, cov, z):
     return x
 
 
-def simulate(a0, P0, c, d, T, Z, R, H, Q, z_x0, z_y0, z_state, z_obs):
+def simulate(a0, P0, c, d, T, Z, R, H, Q, z_x0, z_y0, z_state, z_obs, time_varying=()):
     """One model: restatement of LinearGaussianStateSpace.rv_op's step_fn / initial draw (distributions.py:239-263) with
-    the normal draws written as chol_psd(cov) @ z.  Returns (states (n+1, m), obs (n+1, p))."""
-    L0, LH, LQ = chol_psd(P0), chol_psd(H), chol_psd(Q)
+    the normal draws written as chol_psd(cov) @ z.  ``time_varying``: names of the inputs that are sequences of length n
+    (``sequence_names``; the initial observation uses Z[0], H[0], :259-260).  Returns (states (n+1, m), obs (n+1, p))."""
+    vals = dict(c=c, d=d, T=T, Z=Z, R=R, H=H, Q=Q)
+    at = lambda k, t: vals[k][t] if k in time_varying else vals[k]
     n = z_state.shape[0]
     xs = np.empty((n + 1, a0.shape[0]))
-    ys = np.empty((n + 1, d.shape[0]))
-    xs[0] = a0 + L0 @ z_x0                  # init_x_ = MvNormalSVD(a0, P0)
-    ys[0] = Z @ xs[0] + LH @ z_y0           # init_y_ = MvNormalSVD(Z @ init_x_, H): no d (:263)
+    ys = np.empty((n + 1, z_y0.shape[0]))
+    xs[0] = a0 + chol_psd(P0) @ z_x0                                  # init_x_ = MvNormalSVD(a0, P0)
+    ys[0] = at("Z", 0) @ xs[0] + chol_psd(at("H", 0)) @ z_y0          # init_y_ = MvNormalSVD(Z @ init_x_, H): no d
     for t in range(n):
-        xs[t + 1] = c + T @ xs[t] + R @ (LQ @ z_state[t])     # a_next = c + T a + R a_innovation
-        ys[t + 1] = d + Z @ xs[t + 1] + LH @ z_obs[t]         # y_next = d + Z a_next + y_innovation
+        xs[t + 1] = at("c", t) + at("T", t) @ xs[t] + at("R", t) @ (chol_psd(at("Q", t)) @ z_state[t])
+        ys[t + 1] = at("d", t) + at("Z", t) @ xs[t + 1] + chol_psd(at("H", t)) @ z_obs[t]
     return xs, ys

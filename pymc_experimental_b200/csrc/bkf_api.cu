@@ -895,7 +895,6 @@ extern "C" int bkf_simulate(bkf_handle* h, const bkf_problem* P, const void* a0,
                             void* obs, int* status) {
     int rc = validate(h, P, true);
     if (rc != BKF_OK) return rc;
-    if (P->tv_mask) return fail(h, BKF_ERR_UNSUPPORTED, "bkf_simulate does not take time-varying matrices yet");
     const void* prm[BKF_NPARAM] = {a0, P0, c, d, T, Z, R, H, Q};
     if (any_null(prm, BKF_NPARAM) || !z_x0 || !z_y0 || !z_state || !z_obs || !states || !obs)
         return fail(h, BKF_ERR_ARG, "null pointer");

@@ -146,26 +146,42 @@ __global__ void simulate_kernel(KArgs<R> g, const R* __restrict__ z_x0, const R*
     R* L0 = s_ + (size_t)warp * arena;
     R *Tm = L0 + m * m, *Zm = Tm + m * m, *RL = Zm + p * m, *LH = RL + m * r, *LQ = LH + p * p, *a = LQ + r * r,
       *an = a + m, *cv = an + m, *dv = cv + m, *zs = dv + p, *zo = zs + r;
-    auto ld = [&](R* dst, const R* src, int which, size_t sz) {
-        const R* q = param_ptr(src, g.shared_mask, which, b, sz);
-        for (int i = lane; i < (int)sz; i += 32) dst[i] = q[i];
+    int st = 0;
+    // parameters of step t (sequences of length n, distributions.py:213-218); first: everything, else only what carries
+    // a time axis -- with the factors of H_t, Q_t and R_t L_Q,t redone
+    auto load_step = [&](int t, bool first) {
+        auto want = [&](int which) { return first || ((g.tv_mask >> which) & 1u); };
+        auto ld = [&](R* dst, const R* src, int which, size_t sz) {
+            const R* q = param_ptr_t(src, g.shared_mask, g.tv_mask, which, b, t, n, sz);
+            for (int i = lane; i < (int)sz; i += 32) dst[i] = q[i];
+        };
+        if (want(BKF_PARAM_T)) ld(Tm, g.T, BKF_PARAM_T, (size_t)m * m);
+        if (want(BKF_PARAM_Z)) ld(Zm, g.Z, BKF_PARAM_Z, (size_t)p * m);
+        if (want(BKF_PARAM_C)) ld(cv, g.c, BKF_PARAM_C, (size_t)m);
+        if (want(BKF_PARAM_D)) ld(dv, g.d, BKF_PARAM_D, (size_t)p);
+        if (want(BKF_PARAM_H)) ld(LH, g.H, BKF_PARAM_H, (size_t)p * p);
+        if (want(BKF_PARAM_Q)) ld(LQ, g.Q, BKF_PARAM_Q, (size_t)r * r);
+        __syncwarp();
+        if (want(BKF_PARAM_H)) st |= chol_psd_warp(LH, p, lane);
+        if (want(BKF_PARAM_Q)) st |= chol_psd_warp(LQ, r, lane);
+        if (want(BKF_PARAM_Q) || want(BKF_PARAM_R)) {
+            const R* Rg = param_ptr_t(g.Rm, g.shared_mask, g.tv_mask, BKF_PARAM_R, b, t, n, (size_t)m * r);
+            for (int idx = lane; idx < m * r; idx += 32) {
+                const int i = idx / r, k = idx - i * r;
+                R acc = 0;
+                for (int l = k; l < r; ++l) acc = fma(Rg[i * r + l], LQ[l * r + k], acc);
+                RL[idx] = acc;
+            }
+        }
+        __syncwarp();
     };
-    ld(L0, g.P0, BKF_PARAM_P0, (size_t)m * m);
-    ld(Tm, g.T, BKF_PARAM_T, (size_t)m * m);
-    ld(Zm, g.Z, BKF_PARAM_Z, (size_t)p * m);
-    ld(LH, g.H, BKF_PARAM_H, (size_t)p * p);
-    ld(LQ, g.Q, BKF_PARAM_Q, (size_t)r * r);
-    ld(cv, g.c, BKF_PARAM_C, (size_t)m);
-    ld(dv, g.d, BKF_PARAM_D, (size_t)p);
-    __syncwarp();
-    int st = chol_psd_warp(L0, m, lane) | chol_psd_warp(LH, p, lane) | chol_psd_warp(LQ, r, lane);
-    const R* Rg = param_ptr(g.Rm, g.shared_mask, BKF_PARAM_R, b, (size_t)m * r);
-    for (int idx = lane; idx < m * r; idx += 32) {
-        const int i = idx / r, k = idx - i * r;
-        R acc = 0;
-        for (int l = k; l < r; ++l) acc = fma(Rg[i * r + l], LQ[l * r + k], acc);
-        RL[idx] = acc;
+    {
+        const R* q = param_ptr(g.P0, g.shared_mask, BKF_PARAM_P0, b, (size_t)m * m);
+        for (int i = lane; i < m * m; i += 32) L0[i] = q[i];
+        __syncwarp();
+        st |= chol_psd_warp(L0, m, lane);
     }
+    load_step(0, true);
     const R* a0 = param_ptr(g.a0, g.shared_mask, BKF_PARAM_A0, b, (size_t)m);
     R* xb = xs + (size_t)b * (n + 1) * m;
     R* yb = ys + (size_t)b * (n + 1) * p;
@@ -188,6 +204,7 @@ __global__ void simulate_kernel(KArgs<R> g, const R* __restrict__ z_x0, const R*
     }
     for (int t = 0; t < n; ++t) {
         __syncwarp();
+        if (g.tv_mask && t > 0) load_step(t, false);
         for (int i = lane; i < r; i += 32) zs[i] = z_state[((size_t)b * n + t) * r + i];
         for (int i = lane; i < p; i += 32) zo[i] = z_obs[((size_t)b * n + t) * p + i];
         __syncwarp();

@@ -568,10 +568,11 @@ class KalmanEngine:
                                             bufs.ptr(x), bufs.ptr(status)))
         return (x[0], status[0]) if squeeze else (x, status)
 
-    def simulate(self, a0, P0, c, d, T, Z, R, H, Q, z_x0, z_y0, z_state, z_obs, dtype=None):
+    def simulate(self, a0, P0, c, d, T, Z, R, H, Q, z_x0, z_y0, z_state, z_obs, dtype=None, time_varying=()):
         """Unconditional simulation of B models (``bkf_simulate``; ``LinearGaussianStateSpace.rv_op``,
         filters/distributions.py:181-293).  ``z_x0`` (B, m), ``z_y0`` (B, p), ``z_state`` (B, n, r), ``z_obs`` (B, n, p):
-        standard normal variates (they define B and the number of steps n).  Parameters may be batched or shared.
+        standard normal variates (they define B and the number of steps n).  Parameters may be batched or shared;
+        ``time_varying`` names those with a time axis of length n (the reference's ``sequence_names``).
         Returns ``(states (B, n+1, m), obs (B, n+1, p), status)``; row 0 is the initial draw."""
         params = dict(zip(PARAM_NAMES, (a0, P0, c, d, T, Z, R, H, Q)))
         bufs = _Buffers([z_x0, z_y0, z_state, z_obs, *params.values()], dtype)
@@ -581,7 +582,7 @@ class KalmanEngine:
         if z_state.ndim != 3 or z_obs.ndim != 3 or z_x0.ndim != 2 or z_y0.ndim != 2:
             raise BkfError("simulate: expected z_x0 (B, m), z_y0 (B, p), z_state (B, n, r), z_obs (B, n, p)")
         B, n = int(z_state.shape[0]), int(z_state.shape[1])
-        prob, _, arrs = self._problem(STANDARD, bufs, z_obs, params, B, None, None)
+        prob, _, arrs = self._problem(STANDARD, bufs, z_obs, params, B, None, None, time_varying)
         m, p, r = prob.m, prob.p, prob.r
         if tuple(z_x0.shape) != (B, m) or tuple(z_y0.shape) != (B, p) or tuple(z_state.shape) != (B, n, r) or \
                 tuple(z_obs.shape) != (B, n, p):

@@ -47,18 +47,19 @@ def sample_sequence_mvnormal(mus, covs, rng=None, engine: KalmanEngine | None = 
 
 
 def simulate_statespace(a0, P0, c, d, T, Z, R, H, Q, steps, draws=None, rng=None, engine: KalmanEngine | None = None,
-                        append_x0=True):
+                        append_x0=True, sequence_names=()):
     """Unconditional draws of the hidden states and observations: the batched ``LinearGaussianStateSpace.rv_op``
     (filters/distributions.py:181-293).  Any of the nine matrices may carry a leading batch axis (one model per draw);
     ``draws`` gives the batch size when none does.  Returns an array (B, steps + 1, m + p) -- states and observations
     concatenated along the last axis as the reference does (``steps`` rows without the initial draw if not ``append_x0``).
+    ``sequence_names``: matrices that carry a time axis of length ``steps`` right after the optional batch axis.
     """
     eng = engine if engine is not None else KalmanEngine(0)
     mats = dict(zip(("a0", "P0", "c", "d", "T", "Z", "R", "H", "Q"), (a0, P0, c, d, T, Z, R, H, Q)))
     static = {"a0": 1, "P0": 2, "c": 1, "d": 1, "T": 2, "Z": 2, "R": 2, "H": 2, "Q": 2}
     B = None
     for k, v in mats.items():
-        if v.ndim == static[k] + 1:
+        if v.ndim == static[k] + 1 + int(k in sequence_names):
             B = int(v.shape[0])
     if B is None:
         B = 1 if draws is None else int(draws)
@@ -68,11 +69,11 @@ def simulate_statespace(a0, P0, c, d, T, Z, R, H, Q, steps, draws=None, rng=None
 
         kw = dict(dtype=mats["T"].dtype, device=mats["T"].device, generator=rng)
         zs = [torch.randn(sh, **kw) for sh in ((B, m), (B, p), (B, steps, r), (B, steps, p))]
-        xs, ys, _ = eng.simulate(*mats.values(), *zs)
+        xs, ys, _ = eng.simulate(*mats.values(), *zs, time_varying=tuple(sequence_names))
         out = torch.cat([xs, ys], dim=-1)
     else:
         gen = rng if rng is not None else np.random.default_rng()
         zs = [gen.standard_normal(sh) for sh in ((B, m), (B, p), (B, steps, r), (B, steps, p))]
-        xs, ys, _ = eng.simulate(*[np.asarray(v) for v in mats.values()], *zs)
+        xs, ys, _ = eng.simulate(*[np.asarray(v) for v in mats.values()], *zs, time_varying=tuple(sequence_names))
         out = np.concatenate([np.array(xs), np.array(ys)], axis=-1)
     return out if append_x0 else out[:, 1:]

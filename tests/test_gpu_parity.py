@@ -651,6 +651,25 @@ def test_simulate_matches_oracle(eng, shape):
     assert_allclose(ys2[1].cpu().numpy(), ry, rtol=0, atol=1e-10 * np.abs(ry).max())
 
 
+@pytest.mark.parametrize("tv", [("Z",), ("c", "d", "T", "Z", "R", "H", "Q")])
+def test_simulate_with_time_varying_matrices(eng, tv):
+    """sequence_names of LinearGaussianStateSpace.rv_op: step t uses x[t], the initial observation Z[0] and H[0]."""
+    from oracle import sampling as osm
+    from pymc_experimental_b200 import synth
+
+    m, p, r = 6, 2, 3
+    B, n = 4, 8
+    cfg = synth.random_dense_tv(B, n, m, p, r, tv, seed=71)
+    rng = np.random.default_rng(8)
+    zs = [rng.standard_normal(sh) for sh in ((B, m), (B, p), (B, n, r), (B, n, p))]
+    xs, ys, status = eng.simulate(*[cfg[k] for k in NAMES], *zs, time_varying=tv)
+    assert int(np.abs(status).sum()) == 0
+    for b in range(B):
+        rx, ry = osm.simulate(*[cfg[k][b] for k in NAMES], *[z[b] for z in zs], time_varying=tv)
+        assert_allclose(xs[b], rx, rtol=0, atol=1e-10 * np.abs(rx).max())
+        assert_allclose(ys[b], ry, rtol=0, atol=1e-10 * np.abs(ry).max())
+
+
 def test_simulate_then_filter_is_calibrated(eng):
     """Size-independent property tying the simulator to the filter: for data simulated from the model, the standardised
     one-step innovations of the Kalman filter are white with unit variance, so sum_t v_t^2 / F_t ~ chi2(T) per series."""
