@@ -438,6 +438,31 @@ def run_b200(args):
                        "note": "bkf_filter_logp_grad_compact: 7 draw-dependent matrix entries per draw in, logp + 7 "
                                "gradient entries out (SURVEY 8 f-1); extra figure, `e2e` above is the dense call"}
 
+    # ---- filter + smoother + one draw per (draw, step), smoothed moments kept on the device (row f-3) ----
+    e2e_sample = None
+    if mode == "filter_smooth" and m <= 32:
+        hz = pinned(np.random.default_rng(5).standard_normal((B, T, m)).astype(npdtype))
+
+        def sample_step():
+            x, ll, _ = eng.sample_conditional_posterior(kind, *hargs, hz, dtype=npdtype, cov_jitter=jitter)
+            return x.nbytes + ll.nbytes
+
+        sample_step()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            s_d2h = sample_step()
+        torch.cuda.synchronize()
+        t_s = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t_s, op=dist.ReduceOp.MAX)
+        e2e_sample = {"value": units_per_step * args.steps / float(t_s.item()), "unit": UNIT,
+                      "h2d_bytes_per_step": int(sum(a.nbytes for a in hargs) + hz.nbytes),
+                      "d2h_bytes_per_step": int(s_d2h),
+                      "note": "bkf_filter_smooth_sample: filter + smoother + one conditional-posterior draw per (draw, "
+                              "step) through host buffers; the smoothed covariances stay on the device (SURVEY 8 f-3); "
+                              "extra figure, `e2e` above returns the smoothed moments themselves"}
+
     # ---- roofline of the dominant kernel ----
     model = step_model(kind, mode, m, p, r)
     hbm_peak, peak_src = load_peaks()
@@ -487,6 +512,8 @@ def run_b200(args):
         }
         if e2e_compact is not None:
             line["e2e_compact"] = e2e_compact
+        if e2e_sample is not None:
+            line["e2e_sample"] = e2e_sample
         if cpu is not None:
             line["cpu_baseline"] = cpu
         print(json.dumps(line))

@@ -173,6 +173,14 @@ int bkf_filter_smooth(bkf_handle* h, const bkf_problem* prob, const void* y, con
                       const void* Q, void* loglike_obs, void* smoothed_states, void* smoothed_covariances,
                       int* status);
 
+/* The whole of sample_conditional_posterior (core/statespace.py:1061-1171) for a batch of posterior draws in one call:
+ * filter forward, smoother, then one draw x[b,t] ~ N(smoothed_state[b,t], smoothed_cov[b,t]) (bkf_mvn_sample below) --
+ * the smoothed moments never leave the device; only x [B,n,m] (and loglike_obs [B,n], nullable) come back.
+ * z: standard normal variates [B,n,m] supplied by the caller.  m <= 32. */
+int bkf_filter_smooth_sample(bkf_handle* h, const bkf_problem* prob, const void* y, const void* a0, const void* P0,
+                             const void* c, const void* d, const void* T, const void* Z, const void* R, const void* H,
+                             const void* Q, const void* z, void* loglike_obs, void* x, int* status);
+
 /* Row f-3 of SURVEY.md section 8: one multivariate-normal draw per (series, step),
  *     x[b,t] = mu[b,t] + L[b,t] z[b,t],   L L^T = cov[b,t],
  * the batched form of SequenceMvNormal.rv_op (pymc_extras/statespace/filters/distributions.py:411-443), which scans

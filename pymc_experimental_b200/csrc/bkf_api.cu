@@ -981,6 +981,58 @@ static int filter_smooth_impl(bkf_handle* h, const bkf_problem* P, const void* y
     return finish(h, P, rc);
 }
 
+// filter -> smoother -> one draw per (series, step), all on the device: only the draws (and the log-likelihood) go back
+template <typename R>
+static int filter_smooth_sample_impl(bkf_handle* h, const bkf_problem* P, const void* y, const void* const* prm,
+                                     const void* z, void* ll, void* x, int* status) {
+    int rc = BKF_OK;
+    KArgs<R> g;
+    fill_inputs<R>(h, P, g, y, prm, &rc);
+    const size_t B = P->B, n = P->n, m = P->m;
+    g.ll = stage_out<R>(h, P, S_LL, ll, B * n, &rc);
+    g.filt_a = (R*)ensure(h, S_WFA, B * n * m * sizeof(R), &rc);
+    g.filt_P = (R*)ensure(h, S_WFP, B * n * m * m * sizeof(R), &rc);
+    int* dstatus = nullptr;
+    if (status) dstatus = P->mem == BKF_MEM_DEVICE ? status : (int*)ensure(h, S_STATUS, B * sizeof(int), &rc);
+    g.status = dstatus;
+    g.sm_filt_a = g.filt_a;
+    g.sm_filt_P = g.filt_P;
+    g.sm_a = (R*)ensure(h, S_SMA, B * n * m * sizeof(R), &rc);
+    g.sm_P = (R*)ensure(h, S_SMP, B * n * m * m * sizeof(R), &rc);
+    const R* dz = stage_in<R>(h, P, S_COT, z, B * n * m, &rc);
+    R* dx = stage_out<R>(h, P, S_GU, x, B * n * m, &rc);
+    if (rc != BKF_OK) return rc;
+    if (B == 0) return BKF_OK;
+    const char* err = "";
+    rc = run_forward(h, g, &err);
+    if (rc != BKF_OK) return fail(h, rc, err);
+    rc = run_smoother(h, g, &err);
+    if (rc != BKF_OK) return fail(h, rc, err);
+    h->launches += 1;
+    rc = smp::launch<R>(g.sm_a, g.sm_P, dz, dx, dstatus, (long long)(B * n), (int)n, (int)m, h->stream, &err);
+    if (rc != BKF_OK) return fail(h, rc, err);
+    copy_back<R>(h, P, ll, g.ll, B * n, &rc);
+    copy_back<R>(h, P, x, dx, B * n * m, &rc);
+    if (status && P->mem == BKF_MEM_HOST && rc == BKF_OK) {
+        cudaError_t e = cudaMemcpyAsync(status, dstatus, B * sizeof(int), cudaMemcpyDeviceToHost, h->stream);
+        if (e != cudaSuccess) rc = cuda_fail(h, e, "D2H copy");
+    }
+    return finish(h, P, rc);
+}
+
+extern "C" int bkf_filter_smooth_sample(bkf_handle* h, const bkf_problem* P, const void* y, const void* a0,
+                                        const void* P0, const void* c, const void* d, const void* T, const void* Z,
+                                        const void* R, const void* H, const void* Q, const void* z, void* ll, void* x,
+                                        int* status) {
+    int rc = validate(h, P, true);
+    if (rc != BKF_OK) return rc;
+    if (P->m > 32) return fail(h, BKF_ERR_UNSUPPORTED, "bkf_filter_smooth_sample: m > 32 is not supported");
+    const void* prm[BKF_NPARAM] = {a0, P0, c, d, T, Z, R, H, Q};
+    if (!y || any_null(prm, BKF_NPARAM) || !z || !x) return fail(h, BKF_ERR_ARG, "null pointer");
+    return P->dtype == BKF_F64 ? filter_smooth_sample_impl<double>(h, P, y, prm, z, ll, x, status)
+                               : filter_smooth_sample_impl<float>(h, P, y, prm, z, ll, x, status);
+}
+
 extern "C" int bkf_filter_smooth(bkf_handle* h, const bkf_problem* P, const void* y, const void* a0, const void* P0,
                                  const void* c, const void* d, const void* T, const void* Z, const void* R,
                                  const void* H, const void* Q, void* ll, void* sa, void* sP, int* status) {

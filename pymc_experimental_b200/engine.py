@@ -35,6 +35,7 @@ ABI_SYMBOLS = (
     "bkf_filter_forward", "bkf_filter_logp_grad", "bkf_smooth", "bkf_filter_smooth", "bkf_host_alloc", "bkf_host_free",
     "bkf_logp_grad_workspace_bytes", "bkf_device_memory", "bkf_filter_logp_grad_compact", "bkf_stationary_init",
     "bkf_stationary_init_grad", "bkf_mvn_sample", "bkf_simulate",
+    "bkf_filter_smooth_sample",
 )
 
 
@@ -93,6 +94,7 @@ def load_library():
     lib.bkf_stationary_init_grad.argtypes = [vp, pp] + [vp] * 7 + [vp] * 4
     lib.bkf_mvn_sample.argtypes = [vp, pp] + [vp] * 3 + [vp] + [vp]
     lib.bkf_simulate.argtypes = [vp, pp] + [vp] * 9 + [vp] * 4 + [vp] * 2 + [vp]
+    lib.bkf_filter_smooth_sample.argtypes = [vp, pp] + [vp] * 10 + [vp] + [vp] * 2 + [vp]
     lib.bkf_smooth.argtypes = [vp, pp] + [vp] * 5 + [vp] * 2 + [vp]
     lib.bkf_filter_smooth.argtypes = [vp, pp] + [vp] * 10 + [vp] * 3 + [vp]
     _lib = lib
@@ -567,6 +569,33 @@ class KalmanEngine:
         self._check(self.lib.bkf_mvn_sample(self.h, C.byref(prob), bufs.ptr(dmu), bufs.ptr(dcov), bufs.ptr(dz),
                                             bufs.ptr(x), bufs.ptr(status)))
         return (x[0], status[0]) if squeeze else (x, status)
+
+    def sample_conditional_posterior(self, kind, y, a0, P0, c, d, T, Z, R, H, Q, z, cov_jitter=None,
+                                     missing_fill_value=None, dtype=None, time_varying=()):
+        """Filter, smoother and one draw of the hidden states per (series, step) from the smoothed moments in ONE call
+        (``bkf_filter_smooth_sample``; ``sample_conditional_posterior``, core/statespace.py:1061-1171): the smoothed
+        covariances stay on the device.  ``z``: standard normal variates (B, n, m).  Returns ``(x, loglike_obs, status)``."""
+        params = dict(zip(PARAM_NAMES, (a0, P0, c, d, T, Z, R, H, Q)))
+        bufs = _Buffers([y, z, *params.values()], dtype)
+        params = {k_: (v if _is_torch(v) else np.asarray(v)) for k_, v in params.items()}
+        y = y if _is_torch(y) else np.asarray(y)
+        z = z if _is_torch(z) else np.asarray(z)
+        B = self._batch_size(y, params, time_varying)
+        squeeze = B is None
+        B = 1 if squeeze else int(B)
+        prob, yb, arrs = self._problem(kind, bufs, y, params, B, cov_jitter, missing_fill_value, time_varying)
+        n, m = prob.n, prob.m
+        if squeeze:
+            z = z[None]
+        if tuple(z.shape) != (B, n, m):
+            raise BkfError(f"z: expected shape {(B, n, m)}, got {tuple(z.shape)}")
+        dz = bufs.inp(z)
+        x, ll, status = bufs.out((B, n, m)), bufs.out((B, n)), bufs.out_int((B,))
+        if bufs.device:
+            self.use_torch_stream()
+        self._check(self.lib.bkf_filter_smooth_sample(self.h, C.byref(prob), bufs.ptr(yb), *[bufs.ptr(a) for a in arrs],
+                                                      bufs.ptr(dz), bufs.ptr(ll), bufs.ptr(x), bufs.ptr(status)))
+        return (x[0], ll[0], status[0]) if squeeze else (x, ll, status)
 
     def simulate(self, a0, P0, c, d, T, Z, R, H, Q, z_x0, z_y0, z_state, z_obs, dtype=None, time_varying=()):
         """Unconditional simulation of B models (``bkf_simulate``; ``LinearGaussianStateSpace.rv_op``,

@@ -692,3 +692,24 @@ def test_simulate_then_filter_is_calibrated(eng):
     q = (v[..., 0] ** 2 / f["observed_covariances"][..., 0, 0]).sum(-1)  # chi2(steps): mean steps, var 2 steps
     assert abs(q.mean() - steps) < 5 * np.sqrt(2 * steps / 2048)
     assert abs(q.var() / (2 * steps) - 1.0) < 0.2
+
+
+@pytest.mark.parametrize("kind,shape", [("standard", (15, 1, 5)), ("univariate", (6, 3, 2)), ("cholesky", (16, 8, 8))])
+def test_fused_filter_smooth_sample_equals_the_three_calls(eng, kind, shape):
+    """bkf_filter_smooth_sample (sample_conditional_posterior in one call) is bit-identical to filter_smooth followed by
+    sample_mvn on its outputs; only the draws and the log-likelihood come back."""
+    from pymc_experimental_b200 import synth
+
+    m, p, r = shape
+    B, n = 7, 12
+    cfg = synth.random_dense(B, n, m, p, r, seed=5 + m, missing=0.1 if p == 1 else 0.0)
+    if kind == "cholesky":
+        cfg["P0"] = np.linalg.cholesky(cfg["P0"])
+    args = [cfg["y"]] + [cfg[k] for k in NAMES]
+    z = np.random.default_rng(1).standard_normal((B, n, m))
+    x, ll, status = eng.sample_conditional_posterior(kind, *args, z)
+    ll2, sa, sP, _ = eng.filter_smooth(kind, *args)
+    x2, _ = eng.sample_mvn(sa, sP, z)
+    np.testing.assert_array_equal(np.asarray(x), np.asarray(x2))
+    np.testing.assert_array_equal(np.asarray(ll), np.asarray(ll2))
+    assert int(np.abs(status).sum()) == 0
