@@ -175,7 +175,7 @@ __device__ __forceinline__ void qr_panel(double* __restrict__ S, double* __restr
         if (ss == 0.0) continue;  // dlarfg: tau = 0, H = I
         // beta = -sign(alpha) nrm,  tau = (beta - alpha) / beta = (|alpha| + nrm) / nrm,  scal = 1 / (alpha - beta)
         const double x2 = fma(alpha, alpha, ss);
-        const double rn = rsqrt_nr(x2);
+        const double rn = rsqrt_nr(x2);  // (x2 subnormal, i.e. a column of magnitude < 1e-154, is outside the supported range)
         double nrm = x2 * rn;
         nrm = fma(fma(-nrm, nrm, x2), 0.5 * rn, nrm);
         const double den = fabs(alpha) + nrm;
