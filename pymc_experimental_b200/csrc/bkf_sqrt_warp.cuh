@@ -109,31 +109,6 @@ __device__ __forceinline__ int elem_addr(int i, int j, int WT) {
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// 1 / sqrt(x) and 1 / x from the 20-bit hardware seeds and two Newton steps (normal, positive-magnitude arguments: the
-// pivot norms of a Householder sweep) -- a quarter of the instructions and half the latency of the IEEE sequences, which
-// sit on the serial chain of every reflector.
-__device__ __forceinline__ double rsqrt_nr(double x) {
-    double r;
-    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
-    const double hx = 0.5 * x;
-#pragma unroll
-    for (int i = 0; i < 2; ++i) {
-        const double e = fma(-hx * r, r, 0.5);
-        r = fma(r, e, r);
-    }
-    return r;
-}
-__device__ __forceinline__ double rcp_nr(double x) {
-    double r;
-    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
-#pragma unroll
-    for (int i = 0; i < 2; ++i) {
-        const double e = fma(-x, r, 1.0);
-        r = fma(r, e, r);
-    }
-    return r;
-}
-
 // One panel (8 columns, NQ active row blocks, the diagonal block first) of the Householder sweep and its trailing update.
 // tile(jt, rt) -> tile index.  The reflector loop is rolled (runtime k): see qr_tiles.
 template <int NQ, int WT, class ColF>
@@ -173,21 +148,33 @@ __device__ __forceinline__ void qr_panel(double* __restrict__ S, double* __restr
         const double akc = __shfl_sync(FULL, (k & 1) ? pa[0].y : pa[0].x, 4 * g + (k >> 1));  // [row k][col g]
         const double alpha = __shfl_sync(FULL, akc, 4 * k);
         if (ss == 0.0) continue;  // dlarfg: tau = 0, H = I
-        // beta = -sign(alpha) nrm,  tau = (beta - alpha) / beta = (|alpha| + nrm) / nrm,  scal = 1 / (alpha - beta)
-        const double x2 = fma(alpha, alpha, ss);
-        const double rn = rsqrt_nr(x2);  // (x2 subnormal, i.e. a column of magnitude < 1e-154, is outside the supported range)
-        double nrm = x2 * rn;
-        nrm = fma(fma(-nrm, nrm, x2), 0.5 * rn, nrm);
-        const double den = fabs(alpha) + nrm;
-        const double rden = rcp_nr(den);
+        // beta = -sign(alpha) nrm,  tau = (beta - alpha) / beta = (|alpha| + nrm) / nrm,  scal = 1 / (alpha - beta).
+        // 1 / sqrt and 1 / x come from the 20-bit hardware seeds and two Newton steps each (a quarter of the instructions
+        // and half the latency of the IEEE sequences: measured dependent latencies sqrt 91, div 71 cycles).
+        // Serial chain of the reflector, kept as short as it goes: the reciprocal of |alpha| + nrm starts from a seed
+        // taken at the rsqrt SEED's accuracy (both seeds carry ~20 bits, two Newton steps each reach full precision), so
+        // the second hardware approximation overlaps the Newton steps of the first instead of waiting for nrm.
+        const double x2 = fma(alpha, alpha, ss);  // (x2 subnormal, a column of magnitude < 1e-154, is out of range)
+        const double aa = fabs(alpha);
+        double rn, r0;
+        asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(rn) : "d"(x2));
+        asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r0) : "d"(fma(x2, rn, aa)));
+        const double hx = 0.5 * x2;
+        rn = fma(rn, fma(-hx * rn, rn, 0.5), rn);
+        rn = fma(rn, fma(-hx * rn, rn, 0.5), rn);
+        const double nrm = x2 * rn;
+        const double den = aa + nrm;
+        r0 = fma(r0, fma(-den, r0, 1.0), r0);
+        const double rden = fma(r0, fma(-den, r0, 1.0), r0);
         const double beta = copysign(nrm, -alpha);
         const double tau = den * rn;
         const double scal = copysign(rden, alpha);
+        const double ts = tau * scal;
         const double zz = fma(scal, dot, akc);  // v_k . a_c  (c > k)
         // Update with the UNSCALED reflector u = [alpha - beta; x] (v = u scal):  a_c -= (tau zz scal) u  for c > k.
         // The pivot column keeps x until the sweep of the panel is over (nothing reads v before) and is scaled once.
         const bool piv = g == k;
-        const double w = g > k ? tau * zz * scal : 0.0;
+        const double w = g > k ? ts * zz : 0.0;
         double2 ud = xm;  // u on my rows of the diagonal block
         if (2 * t == k) ud.x = alpha - beta;
         if (2 * t + 1 == k) ud.y = alpha - beta;
