@@ -215,11 +215,13 @@ def test_square_root_filter_batched_logp_grad(eng, shape, missing):
             _close(grads[k][b], ref_g[k][b], 1e-8, f"cholesky d/d{k}[{b}]")
 
 
-@pytest.mark.parametrize("case", ["dense_P0", "H_zero", "cotangent", "shared_params"])
+@pytest.mark.parametrize("case", ["dense_P0", "H_zero", "cotangent", "shared_params", "zero_Z_row"])
 def test_square_root_warp_kernels_corner_cases(eng, case):
     """Branches of the warp-per-series square-root kernels the main sweep does not reach: a factor P0 that is not
     triangular (only the first step sees it), H == 0 (the reference then skips cholesky(H), kalman_filter.py:666),
-    a non-trivial log-likelihood cotangent, and parameters shared across the batch."""
+    a non-trivial log-likelihood cotangent, parameters shared across the batch, and an observed series that loads on no
+    state (a zero row of Z with diagonal H: that column of the update array has nothing below its diagonal, so its
+    Householder reflector is the identity -- dlarfg's tau = 0 branch)."""
     from oracle import kalman_torch as oth
     from pymc_experimental_b200 import synth
 
@@ -235,6 +237,9 @@ def test_square_root_warp_kernels_corner_cases(eng, case):
         cfg["H"] = np.zeros_like(cfg["H"])
     elif case == "cotangent":
         kw["ll_cotangent"] = np.random.default_rng(6).normal(size=(B, n))
+    elif case == "zero_Z_row":
+        cfg["Z"][:, 2, :] = 0.0
+        cfg["H"] = cfg["H"] * np.eye(p)
     full = {k: cfg[k] for k in NAMES}
     if case == "shared_params":  # the engine returns per-series gradients also for a parameter passed once
         for k in ("Z", "R", "c", "d"):
