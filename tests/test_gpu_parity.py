@@ -718,3 +718,28 @@ def test_fused_filter_smooth_sample_equals_the_three_calls(eng, kind, shape):
     np.testing.assert_array_equal(np.asarray(x), np.asarray(x2))
     np.testing.assert_array_equal(np.asarray(ll), np.asarray(ll2))
     assert int(np.abs(status).sum()) == 0
+
+
+def test_sampling_entry_points_in_float32(eng):
+    """The float32 instantiations of bkf_mvn_sample / bkf_simulate against the float64 oracle (single-precision bound)."""
+    from oracle import sampling as osm
+    from pymc_experimental_b200 import synth
+
+    rng = np.random.default_rng(21)
+    B, n, m, p, r = 4, 6, 8, 2, 3
+    A = rng.normal(size=(B, n, m, m))
+    cov = A @ A.transpose(0, 1, 3, 2) + 0.5 * np.eye(m)
+    mu = rng.normal(size=(B, n, m))
+    z = rng.standard_normal((B, n, m))
+    x, status = eng.sample_mvn(mu, cov, z, dtype=np.float32)
+    assert x.dtype == np.float32 and int(np.abs(status).sum()) == 0
+    ref = osm.sample(mu, cov, z)
+    assert_allclose(x, ref, rtol=0, atol=2e-5 * np.abs(ref).max())
+    cfg = synth.random_dense(B, n, m, p, r, seed=3)
+    zs = [rng.standard_normal(sh) for sh in ((B, m), (B, p), (B, n, r), (B, n, p))]
+    xs, ys, status = eng.simulate(*[cfg[k] for k in NAMES], *zs, dtype=np.float32)
+    assert xs.dtype == np.float32 and int(np.abs(status).sum()) == 0
+    for b in range(B):
+        rx, ry = osm.simulate(*[cfg[k][b] for k in NAMES], *[zz[b] for zz in zs])
+        assert_allclose(xs[b], rx, rtol=0, atol=1e-4 * np.abs(rx).max())
+        assert_allclose(ys[b], ry, rtol=0, atol=1e-4 * np.abs(ry).max())
