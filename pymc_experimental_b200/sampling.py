@@ -77,3 +77,29 @@ def simulate_statespace(a0, P0, c, d, T, Z, R, H, Q, steps, draws=None, rng=None
         xs, ys, _ = eng.simulate(*[np.asarray(v) for v in mats.values()], *zs, time_varying=tuple(sequence_names))
         out = np.concatenate([np.array(xs), np.array(ys)], axis=-1)
     return out if append_x0 else out[:, 1:]
+
+
+def sample_conditional_posterior(kind, data, a0, P0, c, d, T, Z, R, H, Q, rng=None, engine: KalmanEngine | None = None,
+                                 time_varying=()):
+    """Hidden-state draws given the data for a batch of parameter draws: filter, smoother and one
+    ``N(smoothed_state, smoothed_cov)`` draw per (draw, step) in one library call (``bkf_filter_smooth_sample``) -- what
+    ``PyMCStateSpace.sample_conditional_posterior`` (core/statespace.py:1061-1171) evaluates draw by draw.  Returns
+    ``(x (B, T, m), loglike_obs (B, T))``; only those cross the host-device boundary."""
+    eng = engine if engine is not None else KalmanEngine(0)
+    m = int(R.shape[-2])
+    n = int(data.shape[-2])
+    static = {"a0": 1, "P0": 2, "c": 1, "d": 1, "T": 2, "Z": 2, "R": 2, "H": 2, "Q": 2}
+    mats = dict(zip(static, (a0, P0, c, d, T, Z, R, H, Q)))
+    B = int(data.shape[0]) if data.ndim == 3 else None
+    for k, v in mats.items():
+        if v.ndim == static[k] + 1 + int(k in time_varying):
+            B = int(v.shape[0])
+    shape = (n, m) if B is None else (B, n, m)
+    if _is_torch(data):
+        import torch
+
+        z = torch.randn(shape, dtype=data.dtype, device=data.device, generator=rng)
+    else:
+        z = (rng if rng is not None else np.random.default_rng()).standard_normal(shape)
+    x, ll, _ = eng.sample_conditional_posterior(kind, data, *mats.values(), z, time_varying=tuple(time_varying))
+    return x, ll

@@ -718,6 +718,10 @@ def test_fused_filter_smooth_sample_equals_the_three_calls(eng, kind, shape):
     np.testing.assert_array_equal(np.asarray(x), np.asarray(x2))
     np.testing.assert_array_equal(np.asarray(ll), np.asarray(ll2))
     assert int(np.abs(status).sum()) == 0
+    from pymc_experimental_b200.sampling import sample_conditional_posterior
+
+    x3, ll3 = sample_conditional_posterior(kind, *args, rng=np.random.default_rng(1), engine=eng)
+    np.testing.assert_array_equal(np.asarray(x3), np.asarray(x))  # same generator state -> same variates -> same draws
 
 
 def test_sampling_entry_points_in_float32(eng):
