@@ -92,12 +92,12 @@ __device__ __forceinline__ double2 ldg_tile_t(const double* __restrict__ M, int 
     const double* q = M + (size_t)(8 * J + 2 * t) * ld + 8 * I + g;
     return make_double2(q[0], q[ld]);
 }
-// the same for a buffer this kernel also writes (no read-only-cache path)
-__device__ __forceinline__ double2 ldrw_tile(double* M, int ld, int I, int J, int lane) {
+// M[tile] += v without reading it back (RED: the add happens in L2, nothing waits for it; every element has one owner)
+__device__ __forceinline__ void red_tile(double* M, int ld, int I, int J, int lane, double2 v) {
     const int g = lane >> 2, t = lane & 3;
-    double2 v;
-    asm volatile("ld.global.v2.f64 {%0,%1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(M + (size_t)(8 * I + g) * ld + 8 * J + 2 * t));
-    return v;
+    double* q = M + (size_t)(8 * I + g) * ld + 8 * J + 2 * t;
+    atomicAdd(q, v.x);
+    atomicAdd(q + 1, v.y);
 }
 __device__ __forceinline__ void stg_tile(double* __restrict__ M, int ld, int I, int J, int lane, double2 v) {
     const int g = lane >> 2, t = lane & 3;
@@ -873,8 +873,9 @@ __global__ void __launch_bounds__(32) backward_kernel(KArgs<double> G) {
     const double* yb = G.y_shared ? G.y : G.y + (size_t)b * n * p;
     const size_t tstride = traj_record_elems(m, p);
     const size_t off_rf = (size_t)m + (size_t)m * m, off_rp = off_rf + (size_t)N1 * (N1 + 1) / 2;
-    // accumulators that are only added to live in global memory (L2): the gradient buffers themselves when requested,
-    // else the scratch record behind the trajectory
+    // accumulators that are only added to live in global memory (L2), updated with fire-and-forget reductions (RED.ADD:
+    // no load on the step's critical path): the gradient buffers themselves when requested, else the scratch record
+    // behind the trajectory
     double* scr = G.traj + (size_t)G.B * n * tstride + (size_t)b * tstride;
     double* gT = G.g_T ? G.g_T + (size_t)b * m * m : scr;
     double* gZ = G.g_Z ? G.g_Z + (size_t)b * p * m : scr + m * m;
@@ -935,11 +936,7 @@ __global__ void __launch_bounds__(32) backward_kernel(KArgs<double> G) {
             for (int I = 0; I < MT; ++I)
 #pragma unroll
                 for (int J = 0; J < MT; ++J) {
-                    double2 a = ldrw_tile(PS, m, I, J, lane);
-                    const double2 ps = ldt(W, I * MT + J, lane);
-                    a.x += ps.x;
-                    a.y += ps.y;
-                    stg_tile(PS, m, I, J, lane, a);
+                    red_tile(PS, m, I, J, lane, ldt(W, I * MT + J, lane));
                 }
         }
         // ---- forward quantities of this step from the record: s, inner, a_f, Pcf ----
@@ -1056,11 +1053,8 @@ __global__ void __launch_bounds__(32) backward_kernel(KArgs<double> G) {
                 Acc2 acc[MT];
 #pragma unroll
                 for (int I = 0; I < MT; ++I) {
-                    double2 v0 = ldrw_tile(gT, m, I, J, lane);
                     const double ab = vab[8 * I + g];
-                    v0.x = fma(ab, vaf[8 * J + 2 * t], v0.x);
-                    v0.y = fma(ab, vaf[8 * J + 2 * t + 1], v0.y);
-                    acc[I] = acc2_from(v0);
+                    acc[I] = acc2_from(make_double2(ab * vaf[8 * J + 2 * t], ab * vaf[8 * J + 2 * t + 1]));
                 }
 #pragma unroll
                 for (int K = 0; K < MT; ++K)
@@ -1070,7 +1064,7 @@ __global__ void __launch_bounds__(32) backward_kernel(KArgs<double> G) {
                         for (int I = 0; I < MT; ++I) mma_nt(acc[I], ldt(W, TPT + I * MT + K, lane), pk);
                     }
 #pragma unroll
-                for (int I = 0; I < MT; ++I) stg_tile(gT, m, I, J, lane, fin(acc[I]));
+                for (int I = 0; I < MT; ++I) red_tile(gT, m, I, J, lane, fin(acc[I]));
             }
         }
         // Pcfbar^T = U1^T T :  [I][J] = sum_K U1T[I][K] ((T^T)[J][K])^T  -> W[0 .. MT*MT)   (Psi_p is dead)
@@ -1296,10 +1290,8 @@ __global__ void __launch_bounds__(32) backward_kernel(KArgs<double> G) {
 #pragma unroll
                 for (int Io = 0; Io < PT; ++Io) {
                     const double wo = vw[8 * Io + g], vb = vvb[8 * Io + g];
-                    double2 gz = ldrw_tile(gZ, m, Io, J, lane);
-                    gz.x = fma(wo, fma(-vb, va[8 * J + 2 * t], acc[Io].x), gz.x);
-                    gz.y = fma(wo, fma(-vb, va[8 * J + 2 * t + 1], acc[Io].y), gz.y);
-                    stg_tile(gZ, m, Io, J, lane, gz);
+                    red_tile(gZ, m, Io, J, lane, make_double2(wo * fma(-vb, va[8 * J + 2 * t], acc[Io].x),
+                                                              wo * fma(-vb, va[8 * J + 2 * t + 1], acc[Io].y)));
                 }
             }
         }
@@ -1368,7 +1360,8 @@ __global__ void __launch_bounds__(32) backward_kernel(KArgs<double> G) {
         for (int i = lane; i < r * r; i += 32) Qc[i] = Qg[i];
         __syncwarp();
         chol_lower_warp(Qc, r, lane);
-        __threadfence_block();
+        __threadfence();  // the reductions into PS were issued by other lanes of this warp
+        __syncwarp();
         wmm<false>(X1, r, PS, m, 1, Rg, r, 1, m, r, m, lane);  // X1 = Psum R
         if (G.g_R) {
             wmm<false>(QQ, r, Qc, r, 1, Qc, 1, r, r, r, r, lane);  // Qc Qc^T
