@@ -291,3 +291,38 @@ def test_sampling_oracle_factors_reproduce_the_covariance():
     assert np.all(np.abs(ours.mean(0) - ref.mean(0)) < 6 * se)
     c1, c2 = np.cov(ours.T), np.cov(ref.T)
     assert np.abs(c1 - c2).max() < 0.05 * np.abs(full).max()
+
+
+def test_simulation_oracle_follows_the_reference_recursion():
+    """oracle/sampling.simulate against an independent plain-NumPy transcription of LinearGaussianStateSpace.rv_op's
+    step_fn (distributions.py:239-263): Cholesky factors of PD matrices, no d in the first observation mean, and the
+    time-varying selection (step t uses x[t], the initial observation Z[0], H[0])."""
+    from oracle import sampling as osm
+
+    rng = np.random.default_rng(31)
+    m, p, r, n = 5, 2, 3, 7
+
+    def spd(k):
+        A = rng.normal(size=(k, k))
+        return A @ A.T + 0.3 * np.eye(k)
+
+    a0, P0 = rng.normal(size=m), spd(m)
+    c, d = rng.normal(size=(n, m)), rng.normal(size=(n, p))
+    T, Z, R = 0.4 * rng.normal(size=(n, m, m)), rng.normal(size=(n, p, m)), rng.normal(size=(n, m, r))
+    H, Q = np.stack([spd(p) for _ in range(n)]), np.stack([spd(r) for _ in range(n)])
+    z0, zy0 = rng.standard_normal(m), rng.standard_normal(p)
+    zs, zo = rng.standard_normal((n, r)), rng.standard_normal((n, p))
+    for tv in ((), ("c", "d", "T", "Z", "R", "H", "Q")):
+        sel = lambda name, x, t: x[t] if name in tv else x[0]
+        args = [a0, P0] + [x if name in tv else x[0] for name, x in zip("cdTZRHQ", (c, d, T, Z, R, H, Q))]
+        xs, ys = osm.simulate(*args, z0, zy0, zs, zo, time_varying=tv)
+        chol = np.linalg.cholesky
+        x = a0 + chol(P0) @ z0
+        y = sel("Z", Z, 0) @ x + chol(sel("H", H, 0)) @ zy0
+        np.testing.assert_allclose(xs[0], x, rtol=1e-12)
+        np.testing.assert_allclose(ys[0], y, rtol=1e-12)
+        for t in range(n):
+            x = sel("c", c, t) + sel("T", T, t) @ x + sel("R", R, t) @ (chol(sel("Q", Q, t)) @ zs[t])
+            y = sel("d", d, t) + sel("Z", Z, t) @ x + chol(sel("H", H, t)) @ zo[t]
+            np.testing.assert_allclose(xs[t + 1], x, rtol=1e-11, atol=1e-12)
+            np.testing.assert_allclose(ys[t + 1], y, rtol=1e-11, atol=1e-12)
