@@ -124,7 +124,7 @@ __device__ __forceinline__ void qr_panel(double* __restrict__ S, double* __restr
 #pragma unroll
     for (int q = 0; q < NQ; ++q) pa[q] = ldt(S, tile(jt, jt + q), lane);
     double tauv = 0.0, scalv = 1.0;  // tau and 1 / (alpha - beta) of the reflector of column g (tau = 0: H = I)
-#pragma unroll 1
+#pragma unroll 2
     for (int k = 0; k < 8; ++k) {
         // x = column k of the panel below its diagonal, handed to every group (lane (k, t) -> lanes (*, t))
         double2 xb[NQ];
