@@ -240,7 +240,7 @@ static int run_forward(bkf_handle* h, const KArgs<double>& g, const char** err) 
     KernelTimer kt(h, BKF_KERNEL_FORWARD);
     h->launches += 1;
     if (g.kind == BKF_CHOLESKY) {
-        if (sqc::supported(g)) {
+        if (sqc::supported(g, false)) {
             h->path = "sqrt_cta4_lookahead";
             return sqc::launch_f64(g, false, h->stream, err);
         }
@@ -287,7 +287,10 @@ static int run_forward(bkf_handle* h, const KArgs<float>& g, const char** err) {
 static int run_backward(bkf_handle* h, const KArgs<double>& g, const char** err) {
     KernelTimer kt(h, BKF_KERNEL_BACKWARD);
     h->launches += 1;
-    if (g.kind == BKF_CHOLESKY && sqc::supported(g)) return sqc::launch_f64(g, true, h->stream, err);
+    if (g.kind == BKF_CHOLESKY && sqc::supported(g, true)) {
+        h->path += "+adjoint_cta4";
+        return sqc::launch_f64(g, true, h->stream, err);
+    }
     if (g.kind == BKF_CHOLESKY)
         return sqw::supported(g, true) ? sqw::launch_f64(g, true, h->stream, err)
                                        : sq::launch_backward<double>(g, h->stream, err);

@@ -20,7 +20,7 @@ bool supported(const KArgs<double>& g, bool backward);
 int launch_f64(const KArgs<double>& g, bool backward, cudaStream_t stream, const char** err);
 }  // namespace sqw
 namespace sqc {  // square-root filter, four warps per series with a look-ahead Householder chain (bkf_sqrt_cta.cu)
-bool supported(const KArgs<double>& g);
+bool supported(const KArgs<double>& g, bool backward);
 int launch_f64(const KArgs<double>& g, bool backward, cudaStream_t stream, const char** err);
 }  // namespace sqc
 namespace sw {  // register-tiled sub-warp-per-series kernels, float64, p = 1 (bkf_subwarp.cu)

@@ -7,8 +7,8 @@
 namespace bkf {
 namespace sqc {
 
-// BKF_SQRT_CTA (debugging aid): bit 0 = filter-only calls, bit 1 = logp + gradient calls (both sweeps: the record of
-// the forward sweep is private to the family) on the four-warp kernels
+// BKF_SQRT_CTA (debugging aid): bit 0 = forward sweep of filter-only calls (its record is not read by any adjoint yet),
+// bit 1 = adjoint sweep (reads the record of either warp-per-series / CTA-per-series forward family)
 static int enabled_mask() {
     static const int mask = [] {
         const char* e = std::getenv("BKF_SQRT_CTA");
@@ -26,9 +26,10 @@ static bool shape_ok(int m, int p, int r) {
     return false;
 }
 
-bool supported(const KArgs<double>& g) {
+bool supported(const KArgs<double>& g, bool backward) {
     if (g.kind != BKF_CHOLESKY || g.tv_mask || !shape_ok(g.m, g.p, g.r)) return false;
-    return (enabled_mask() >> (g.traj ? 1 : 0)) & 1;
+    if (backward) return g.traj != nullptr && ((enabled_mask() >> 1) & 1);
+    return g.traj == nullptr && (enabled_mask() & 1);
 }
 
 int launch_f64(const KArgs<double>& g, bool backward, cudaStream_t stream, const char** err) {

@@ -679,5 +679,674 @@ __global__ void __launch_bounds__(NTHR, 4) forward_kernel(KArgs<double> G) {
     }
 }
 
+
+// ===============================================================================================================
+// Adjoint sweep, four warps per series.  Same mathematics and the same record as sqw::backward_kernel
+// (bkf_sqrt_warp.cuh: Abar = A Psi, Psi = R^{-1} copyltu(R Rbar^T) R^{-T}; [a | Pc | triu(R_update) | triu(R_predict)]
+// from either forward family); every tile phase is split over the warps by tile ROWS (warp (row + b) mod 4, so that
+// co-resident series load different sub-partitions), with a CTA barrier between phases.  The right-solves of Psi are
+// independent per tile row, so a pass needs no barrier inside.
+
+template <int NT, class RbF>
+__device__ __forceinline__ void psi_tiles_cta(double* __restrict__ W, const double* __restrict__ RF,
+                                              double* __restrict__ RINV, RbF rbar, const int warp, const int rot,
+                                              const int lane) {
+    const int g = lane >> 2, t = lane & 3;
+    auto own = [&](int I) { return ((I + rot) & (NWARP - 1)) == warp; };
+    // S = copyltu(R Rbar^T), row by row; the inverse of the row's diagonal tile of R on lanes 0..7
+#pragma unroll
+    for (int I = 0; I < NT; ++I) {
+        if (!own(I)) continue;
+        Acc2 acc[NT];
+#pragma unroll
+        for (int J = 0; J < NT; ++J) acc[J] = acc2_zero();
+#pragma unroll
+        for (int K = I; K < NT; ++K) {
+            const double2 rk = ldt(RF, tri<NT>(I, K), lane);
+#pragma unroll
+            for (int J = 0; J <= I; ++J) mma_nt(acc[J], rk, rbar(J, K));
+        }
+#pragma unroll
+        for (int J = 0; J < I; ++J) {
+            const double2 v = fin(acc[J]);
+            stt(W, I * NT + J, lane, v);
+            stt(W, J * NT + I, lane, ttrans(v, lane));
+        }
+        const double2 dv = fin(acc[I]);
+        const double2 dt = ttrans(dv, lane);
+        stt(W, I * NT + I, lane, make_double2(g >= 2 * t ? dv.x : dt.x, g >= 2 * t + 1 ? dv.y : dt.y));
+        if (lane < 8) {
+            const int c = lane;
+            const double* Dg = RF + (I * NT - (I * (I - 1)) / 2) * 64;
+            double x[8], rd[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) rd[i] = 1.0 / Dg[i * 9];
+#pragma unroll
+            for (int i = 7; i >= 0; --i) {
+                double tv = i == c ? 1.0 : 0.0;
+#pragma unroll
+                for (int q = 7; q > i; --q) tv = fma(-Dg[i * 8 + q], x[q], tv);
+                x[i] = tv * rd[i];
+            }
+#pragma unroll
+            for (int i = 0; i < 8; ++i) RINV[I * 64 + i * 8 + c] = x[i];
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int pass = 0; pass < 2; ++pass) {
+        // X <- X R^{-T}: tile row J, tile column by tile column (the rows are independent)
+#pragma unroll
+        for (int J = 0; J < NT; ++J) {
+            if (!own(J)) continue;
+#pragma unroll
+            for (int I = NT - 1; I >= 0; --I) {
+                Acc2 acc = acc2_from(ldt(W, J * NT + I, lane));
+#pragma unroll
+                for (int K = I + 1; K < NT; ++K) mma_nt(acc, ldt(W, J * NT + K, lane), neg(ldt(RF, tri<NT>(I, K), lane)));
+                Acc2 o = acc2_zero();
+                mma_nt(o, fin(acc), ldt(RINV, I, lane));
+                stt(W, J * NT + I, lane, fin(o));
+                __syncwarp();
+            }
+        }
+        __syncthreads();
+        if (pass == 0) {
+#pragma unroll
+            for (int I = 0; I < NT; ++I) {
+                if (!own(I)) continue;
+#pragma unroll
+                for (int J = 0; J < I; ++J) {
+                    const double2 lo = ldt(W, I * NT + J, lane), up = ldt(W, J * NT + I, lane);
+                    stt(W, I * NT + J, lane, ttrans(up, lane));
+                    stt(W, J * NT + I, lane, ttrans(lo, lane));
+                }
+                stt(W, I * NT + I, lane, ttrans(ldt(W, I * NT + I, lane), lane));
+            }
+            __syncthreads();
+        }
+    }
+}
+
+// tiles of the upper triangle of an n x n factor from its packed rows, split over the warps (see load_packed_upper)
+template <int NT>
+__device__ __forceinline__ void load_packed_upper_cta(double* __restrict__ RF, const double* __restrict__ src,
+                                                      const int warp, const int lane) {
+    const int g = lane >> 2, t = lane & 3;
+    constexpr int n = 8 * NT;
+    int idx = 0;
+#pragma unroll
+    for (int I = 0; I < NT; ++I)
+#pragma unroll
+        for (int K = I; K < NT; ++K, ++idx) {
+            if ((idx & (NWARP - 1)) != warp) continue;
+            const int i = 8 * I + g, j = 8 * K + 2 * t;
+            const double* q = src + (i * n - (i * (i - 1)) / 2 - i + j);
+            double2 v;
+            v.x = j >= i ? q[0] : 0.0;
+            v.y = j + 1 >= i ? q[1] : 0.0;
+            stt(RF, tri<NT>(I, K), lane, v);
+        }
+}
+
+template <int MT, int PT, int RT>
+struct BDimsC : sqw::BDims<MT, PT, RT> {
+    using B0 = sqw::BDims<MT, PT, RT>;
+    static constexpr int SI = B0::ELEMS;      // 4 ints: flag, partial, Hzero
+    static constexpr int ELEMS = B0::ELEMS + 2;
+    static constexpr int RINV2 = B0::PBT;     // inverses of the diagonal tiles of the update factor: Pbar^T is dead then
+    static constexpr int AB21 = B0::RF;       // Abar21: the factor is dead then
+    static_assert(B0::NT1 <= MT * MT && MT * PT <= B0::RFTILES && MT * PT <= B0::RBTILES, "scratch blocks fit");
+};
+
+template <int MT, int PT, int RT>
+__global__ void __launch_bounds__(NTHR, 4) backward_kernel(KArgs<double> G) {
+    using D = sqw::Dims<MT, PT, RT>;
+    using BD = BDimsC<MT, PT, RT>;
+    constexpr int m = D::m, p = D::p, r = D::r, N1 = D::N1, NT1 = D::NT1;
+    extern __shared__ double smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+    const int b = blockIdx.x;
+    const int n = G.n;
+    const int rot = b & (NWARP - 1);
+    auto own = [&](int I) { return ((I + rot) & (NWARP - 1)) == warp; };
+    double *W = smem + BD::W, *RF = smem + BD::RF, *RB = smem + BD::RB, *PBT = smem + BD::PBT, *HC = smem + BD::HC,
+           *HBT = smem + BD::HBT;
+    double *va = smem + BD::V_a, *vaf = smem + BD::V_af, *vab = smem + BD::V_ab, *vafb = smem + BD::V_afb,
+           *vgc = smem + BD::V_gc, *vv = smem + BD::V_v, *vs = smem + BD::V_s, *vin = smem + BD::V_in, *vw = smem + BD::V_w,
+           *vym = smem + BD::V_ym, *vvb = smem + BD::V_vb, *vsb = smem + BD::V_sb, *vt1 = smem + BD::V_t1,
+           *vt2 = smem + BD::V_t2, *vgd = smem + BD::V_gd, *vd = smem + BD::V_d;
+    volatile int* si = reinterpret_cast<volatile int*>(smem + BD::SI);
+
+    const double* Tg = param_ptr(G.T, G.shared_mask, BKF_PARAM_T, b, (size_t)m * m);
+    const double* Zg = param_ptr(G.Z, G.shared_mask, BKF_PARAM_Z, b, (size_t)p * m);
+    const double* yb = G.y_shared ? G.y : G.y + (size_t)b * n * p;
+    const size_t tstride = sqw::traj_record_elems(m, p);
+    const size_t off_rf = (size_t)m + (size_t)m * m, off_rp = off_rf + (size_t)N1 * (N1 + 1) / 2;
+    // add-only accumulators in global memory (L2), as in sqw::backward_kernel
+    double* scr = G.traj + (size_t)G.B * n * tstride + (size_t)b * tstride;
+    double* gT = G.g_T ? G.g_T + (size_t)b * m * m : scr;
+    double* gZ = G.g_Z ? G.g_Z + (size_t)b * p * m : scr + m * m;
+    double* PS = scr + m * m + p * m;
+    const bool want_ps = G.g_R || G.g_Q;
+
+    if (warp == 0) {
+        bool Hz;
+        setup_consts<D>(G, b, HC, nullptr, nullptr, W, &Hz, lane);
+        if (lane == 0) si[2] = Hz ? 1 : 0;
+    } else {
+        const int tid = threadIdx.x - 32;
+        const double* dg = param_ptr(G.d, G.shared_mask, BKF_PARAM_D, b, (size_t)p);
+        for (int i = tid; i < p; i += NTHR - 32) { vd[i] = dg[i]; vgd[i] = 0.0; }
+        for (int i = tid; i < m; i += NTHR - 32) { vab[i] = 0.0; vgc[i] = 0.0; }
+        for (int i = tid; i < MT * MT * 32; i += NTHR - 32) reinterpret_cast<double2*>(PBT)[i] = zero2();
+        for (int i = tid; i < PT * PT * 32; i += NTHR - 32) reinterpret_cast<double2*>(HBT)[i] = zero2();
+        for (int i = tid; i < m * m; i += NTHR - 32) { gT[i] = 0.0; PS[i] = 0.0; }
+        for (int i = tid; i < p * m; i += NTHR - 32) gZ[i] = 0.0;
+    }
+    __syncthreads();
+    const bool Hzero = si[2] != 0;
+
+#ifdef BKF_SQC_PROFILE
+    long long tb[16], tcb = clock64();
+    for (int i = 0; i < 16; ++i) tb[i] = 0;
+#define BKF_TOCK(i) { const long long tc1 = clock64(); tb[i] += tc1 - tcb; tcb = tc1; }
+#else
+#define BKF_TOCK(i)
+#endif
+    for (int ts = n - 1; ts >= 0; --ts) {
+        const size_t bt = (size_t)b * n + ts;
+        const double* rec = G.traj + bt * tstride;
+        const double* Pcg = rec + m;
+        const double gcot = G.ll_cot ? G.ll_cot[bt] : 1.0;
+        const bool dense_pc = ts == 0;  // P0 is whatever the caller passed; later factors are lower triangular
+        if (ts > 0) {  // the next record: pull it towards L2 while this step computes
+            const char* nxt = reinterpret_cast<const char*>(rec - tstride);
+            for (int off = threadIdx.x * 128; off < (int)(tstride * sizeof(double)); off += NTHR * 128)
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(nxt + off));
+        }
+        // ---- mask (warp 0), a, predict factor ----
+        if (warp == 0) {
+            bool miss = true;
+            if (lane < p) {
+                const double yv = yb[(size_t)ts * p + lane];
+                miss = is_missing(yv, G.fill, true);
+                vw[lane] = miss ? 0.0 : 1.0;
+                vym[lane] = miss ? 0.0 : yv;
+            }
+            const int nobs = __popc(__ballot_sync(FULL, !miss));
+            if (lane == 0) {
+                si[0] = nobs == 0 ? 1 : 0;
+                si[1] = (nobs != 0 && nobs != p) ? 1 : 0;
+            }
+        } else if (warp == 1) {
+            for (int i = lane; i < m; i += 32) va[i] = rec[i];
+        }
+        load_packed_upper_cta<MT>(RF, rec + off_rp, warp, lane);
+        __syncthreads(); BKF_TOCK(0)
+        const bool flag = si[0] != 0, partial = si[1] != 0;
+        if (warp == NWARP - 1) {  // innovation v = y - (Zm a + d): needed by the solves further down
+#pragma unroll
+            for (int I = 0; I < PT; ++I) {
+                const double wI = vw[8 * I + g];
+                double acc = 0.0;
+#pragma unroll
+                for (int J = 0; J < MT; ++J) {
+                    const double2 z = ldg_tile(Zg, m, I, J, lane);
+                    acc = fma(z.x * wI, va[8 * J + 2 * t], acc);
+                    acc = fma(z.y * wI, va[8 * J + 2 * t + 1], acc);
+                }
+                acc = red_t(acc) + vd[8 * I + g];
+                if (t == 0) vv[8 * I + g] = vym[8 * I + g] - acc;
+            }
+        }
+        // ================= predict adjoint =================
+        psi_tiles_cta<MT>(W, RF, RB, [&](int J, int K) {
+            double2 v = ldt(PBT, J * MT + K, lane);
+            if (J == K) {
+                if (2 * t < g) v.x = 0.0;
+                if (2 * t + 1 < g) v.y = 0.0;
+            }
+            return v;
+        }, warp, rot, lane);
+        BKF_TOCK(14)
+        if (want_ps) {
+#pragma unroll
+            for (int I = 0; I < MT; ++I)
+                if (own(I))
+#pragma unroll
+                    for (int J = 0; J < MT; ++J) red_tile(PS, m, I, J, lane, ldt(W, I * MT + J, lane));
+        }
+        // ---- forward quantities of this step from the record: s, inner, a_f, Pcf ----
+        if (!flag) load_packed_upper_cta<NT1>(RF, rec + off_rf, warp, lane);  // (the predict factor is dead)
+        __syncthreads(); BKF_TOCK(1)
+        if (warp == NWARP - 1) {
+            if (!flag) {
+                const int q = lane < p ? lane : p - 1;
+                double frow[p];
+#pragma unroll
+                for (int i = 0; i < p; ++i)  // Fc[q][i] = Rf[i][q], i <= q
+                    frow[i] = (i >> 3) <= (q >> 3) ? RF[((i >> 3) * NT1 - ((i >> 3) * ((i >> 3) - 1)) / 2 + ((q >> 3) - (i >> 3))) * 64 +
+                                                        (i & 7) * 8 + (q & 7)]
+                                                   : 0.0;
+                const double rdiag = 1.0 / RF[((q >> 3) * NT1 - ((q >> 3) * ((q >> 3) - 1)) / 2) * 64 + (q & 7) * 9];
+                double x = lane < p ? vv[lane] : 0.0;
+#pragma unroll
+                for (int rep = 0; rep < 2; ++rep) {
+#pragma unroll
+                    for (int i = 0; i < p; ++i) {
+                        const double xi = __shfl_sync(FULL, x, i) * __shfl_sync(FULL, rdiag, i);
+                        if (lane == i) x = xi;
+                        else if (lane > i) x = fma(-frow[i], xi, x);
+                    }
+                    if (lane < p) (rep == 0 ? vs : vin)[lane] = x;
+                }
+                __syncwarp();
+                // a_f = a + KF s,  KF[i][o] = Rf[o][p + i]
+#pragma unroll
+                for (int J = 0; J < MT; ++J) {
+                    double c0 = 0.0, c1 = 0.0;
+#pragma unroll
+                    for (int I = 0; I < PT; ++I) {
+                        const double2 rk = ldt(RF, tri<NT1>(I, PT + J), lane);
+                        const double sI = vs[8 * I + g];
+                        c0 = fma(rk.x, sI, c0);
+                        c1 = fma(rk.y, sI, c1);
+                    }
+                    c0 = red_g(c0);
+                    c1 = red_g(c1);
+                    if (g == 0) {
+                        vaf[8 * J + 2 * t] = va[8 * J + 2 * t] + c0;
+                        vaf[8 * J + 2 * t + 1] = va[8 * J + 2 * t + 1] + c1;
+                    }
+                }
+            } else {
+                for (int i = lane; i < m; i += 32) vaf[i] = va[i];
+            }
+        }
+        // (Pcf + jitter I)^T tile (I, K): upper triangular from the record's factor, or Pc^T when the step was skipped
+        auto pft = [&](int I, int K) {
+            double2 v;
+            if (flag) v = ldg_tile_t(Pcg, m, I, K, lane);
+            else v = K >= I ? ldt(RF, tri<NT1>(PT + I, PT + (K >= I ? K : I)), lane) : zero2();
+            if (I == K) {
+                if (2 * t == g) v.x += G.jitter;
+                if (2 * t + 1 == g) v.y += G.jitter;
+            }
+            return v;
+        };
+        const bool dense_pf = flag && dense_pc;  // (a skipped step keeps Pc, which is dense only at t = 0)
+        constexpr int TPT = MT * MT;             // tile offset of the second scratch block inside W
+        // TP^T = (T Pcf)^T = Pcf^T T^T :  [I][J] = sum_K pft(I,K) (T[J][K])^T, tile column J by warp own(J)
+#pragma unroll
+        for (int J = 0; J < MT; ++J) {
+            if (!own(J)) continue;
+            double2 acc[MT];
+#pragma unroll
+            for (int I = 0; I < MT; ++I) acc[I] = zero2();
+#pragma unroll
+            for (int K = 0; K < MT; ++K) {
+                const double2 tk = ldg_tile(Tg, m, J, K, lane);
+#pragma unroll
+                for (int I = 0; I < MT; ++I)
+                    if (dense_pf || K >= I) mma_nt(acc[I], pft(I, K), tk);
+            }
+#pragma unroll
+            for (int I = 0; I < MT; ++I) stt(W, TPT + I * MT + J, lane, acc[I]);
+        }
+        __syncthreads(); BKF_TOCK(2)
+        // U1^T = TP^T Psi_p  -> RB[0 .. MT*MT), tile row I by warp own(I); then U1 -> W[TPT ..)
+#pragma unroll
+        for (int I = 0; I < MT; ++I) {
+            if (!own(I)) continue;
+            Acc2 acc[MT];
+#pragma unroll
+            for (int J = 0; J < MT; ++J) acc[J] = acc2_zero();
+#pragma unroll
+            for (int K = 0; K < MT; ++K) {
+                const double2 tpk = ldt(W, TPT + I * MT + K, lane);
+#pragma unroll
+                for (int J = 0; J < MT; ++J) mma_nt(acc[J], tpk, ldt(W, J * MT + K, lane));
+            }
+#pragma unroll
+            for (int J = 0; J < MT; ++J) stt(RB, I * MT + J, lane, fin(acc[J]));
+        }
+        __syncthreads(); BKF_TOCK(3)
+#pragma unroll
+        for (int I = 0; I < MT; ++I) {
+            if (!own(I)) continue;
+#pragma unroll
+            for (int J = 0; J < MT; ++J) stt(W, TPT + I * MT + J, lane, ttrans(ldt(RB, J * MT + I, lane), lane));
+        }
+        __syncthreads(); BKF_TOCK(4)
+        // gT += U1 Pcf^T + abar af^T (tile row I by warp own(I));  Pcf[J][K] = (pft(K, J))^T
+        if (G.g_T) {
+#pragma unroll
+            for (int I = 0; I < MT; ++I) {
+                if (!own(I)) continue;
+                const double ab = vab[8 * I + g];
+#pragma unroll
+                for (int J = 0; J < MT; ++J) {
+                    Acc2 acc = acc2_from(make_double2(ab * vaf[8 * J + 2 * t], ab * vaf[8 * J + 2 * t + 1]));
+#pragma unroll
+                    for (int K = 0; K < MT; ++K)
+                        if (dense_pf || K <= J) mma_nt(acc, ldt(W, TPT + I * MT + K, lane), ttrans(pft(K, J), lane));
+                    red_tile(gT, m, I, J, lane, fin(acc));
+                }
+            }
+        }
+        // Pcfbar^T = U1^T T :  [I][J] = sum_K U1T[I][K] ((T^T)[J][K])^T  -> W[0 .. MT*MT)   (Psi_p is dead), row I by own(I)
+#pragma unroll
+        for (int I = 0; I < MT; ++I) {
+            if (!own(I)) continue;
+            Acc2 acc[MT];
+#pragma unroll
+            for (int J = 0; J < MT; ++J) acc[J] = acc2_zero();
+#pragma unroll
+            for (int K = 0; K < MT; ++K) {
+                const double2 uk = ldt(RB, I * MT + K, lane);
+#pragma unroll
+                for (int J = 0; J < MT; ++J) mma_nt(acc[J], uk, ldg_tile_t(Tg, m, J, K, lane));
+            }
+#pragma unroll
+            for (int J = 0; J < MT; ++J) stt(W, I * MT + J, lane, fin(acc[J]));
+        }
+        // afbar = T^T abar (tile column J of T by warp own(J)); gc += abar afterwards
+#pragma unroll
+        for (int J = 0; J < MT; ++J) {
+            if (!own(J)) continue;
+            double afp = 0.0;
+#pragma unroll
+            for (int K = 0; K < MT; ++K) {
+                const double2 tk = ldg_tile_t(Tg, m, J, K, lane);  // [g][2t+e] = T[8K + 2t + e][8J + g]
+                afp = fma(tk.x, vab[8 * K + 2 * t], fma(tk.y, vab[8 * K + 2 * t + 1], afp));
+            }
+            afp = red_t(afp);
+            if (t == 0) vafb[8 * J + g] = afp;
+        }
+        __syncthreads(); BKF_TOCK(5)
+        for (int i = threadIdx.x; i < m; i += NTHR) vgc[i] += vab[i];
+        if (flag) {  // degenerate branch (:700-705): (a_f, Pcf, ll) = (a, Pc, 0)
+            for (int i = threadIdx.x; i < m; i += NTHR) vab[i] = vafb[i];
+            for (int i = warp; i < MT * MT; i += NWARP) stt(PBT, i, lane, ldt(W, i, lane));
+            __syncthreads(); BKF_TOCK(6)
+            continue;
+        }
+        // ================= update adjoint =================
+        if (warp == NWARP - 1) {
+            const double lossbar = -0.5 * gcot, logdetbar = -0.5 * gcot * (double)p;
+            // sbar = KF^T afbar
+#pragma unroll
+            for (int I = 0; I < PT; ++I) {
+                double acc = 0.0;
+#pragma unroll
+                for (int J = 0; J < MT; ++J) {
+                    const double2 rk = ldt(RF, tri<NT1>(I, PT + J), lane);
+                    acc = fma(rk.x, vafb[8 * J + 2 * t], acc);
+                    acc = fma(rk.y, vafb[8 * J + 2 * t + 1], acc);
+                }
+                acc = red_t(acc);
+                if (t == 0) vsb[8 * I + g] = acc;
+            }
+            __syncwarp();
+            // back substitution with U = Rf[:p,:p] = Fc^T : lane q owns x[q] and row q of U
+            const int q = lane < p ? lane : p - 1;
+            double urow[p];
+#pragma unroll
+            for (int i = 0; i < p; ++i)
+                urow[i] = (i >> 3) >= (q >> 3) ? RF[((q >> 3) * NT1 - ((q >> 3) * ((q >> 3) - 1)) / 2 + ((i >> 3) - (q >> 3))) * 64 +
+                                                    (q & 7) * 8 + (i & 7)]
+                                               : 0.0;
+            const double dq = RF[((q >> 3) * NT1 - ((q >> 3) * ((q >> 3) - 1)) / 2) * 64 + (q & 7) * 9];
+            const double rdiag = 1.0 / dq;
+            auto usolve = [&](double x) {
+#pragma unroll
+                for (int i = p - 1; i >= 0; --i) {
+                    const double xi = __shfl_sync(FULL, x, i) * __shfl_sync(FULL, rdiag, i);
+                    if (lane == i) x = xi;
+                    else if (lane < i) x = fma(-urow[i], xi, x);
+                }
+                return x;
+            };
+            double vbar = lane < p ? lossbar * vin[lane] : 0.0;
+            const double t1 = usolve(lane < p ? lossbar * vv[lane] : 0.0);  // Fc^{-T} innerbar
+            const double t2 = usolve(lane < p ? vsb[lane] + t1 : 0.0);      // Fc^{-T} (sbar + t1)
+            vbar += t2;
+            if (lane < p) {
+                vt1[lane] = t1;
+                vt2[lane] = t2;
+                vvb[lane] = vbar;
+                vsb[lane] = logdetbar * 2.0 * rdiag;  // diagonal term of Fcbar
+            }
+        }
+        __syncthreads(); BKF_TOCK(7)
+        // Rbar = Bbar^T (upper):  [Fcbar^T, KFbar^T; 0, triu(Pcfbar^T)], tile row by warp own(row)
+#pragma unroll
+        for (int I = 0; I < PT; ++I) {
+            if (!own(I)) continue;
+            const int i = 8 * I + g;
+            const double ini = vin[i], sv = vs[i];
+#pragma unroll
+            for (int K = I; K < PT; ++K) {
+                const int k = 8 * K + 2 * t;
+                double2 v;
+                v.x = k >= i ? fma(-vt1[k], ini, -vt2[k] * sv) + (k == i ? vsb[i] : 0.0) : 0.0;
+                v.y = k + 1 >= i ? fma(-vt1[k + 1], ini, -vt2[k + 1] * sv) + (k + 1 == i ? vsb[i] : 0.0) : 0.0;
+                stt(RB, tri<NT1>(I, K), lane, v);
+            }
+#pragma unroll
+            for (int K = 0; K < MT; ++K)
+                stt(RB, tri<NT1>(I, PT + K), lane, make_double2(vafb[8 * K + 2 * t] * sv, vafb[8 * K + 2 * t + 1] * sv));
+        }
+#pragma unroll
+        for (int I = 0; I < MT; ++I) {
+            if (!own(PT + I)) continue;
+#pragma unroll
+            for (int K = I; K < MT; ++K) {
+                double2 v = ldt(W, I * MT + K, lane);
+                if (I == K) {
+                    if (2 * t < g) v.x = 0.0;
+                    if (2 * t + 1 < g) v.y = 0.0;
+                }
+                stt(RB, tri<NT1>(PT + I, PT + K), lane, v);
+            }
+        }
+        __syncthreads(); BKF_TOCK(8)
+        // Psi of the update array.  RINV must not overlap the cotangent tiles while S0 is formed: psi_tiles reads rbar only
+        // in its first phase, and RINV sits in a block of its own here (behind the vectors would be too small): W2 below.
+        psi_tiles_cta<NT1>(W, RF, smem + BD::RINV2, [&](int J, int K) { return ldt(RB, tri<NT1>(J, K), lane); }, warp, rot, lane);
+        BKF_TOCK(15)
+        // ---- Abar = A Psi, A = [[Hc^T, 0], [A21, Pc^T]],  A21 = (Zm Pc)^T = Pc^T Zm^T -> RB[0 ..), row I by own(I) ----
+        constexpr int A21T = 0;  // the cotangent tiles are dead
+#pragma unroll
+        for (int I = 0; I < MT; ++I) {
+            if (!own(I)) continue;
+            Acc2 acc[PT];
+#pragma unroll
+            for (int J = 0; J < PT; ++J) acc[J] = acc2_zero();
+#pragma unroll
+            for (int K = 0; K < MT; ++K)
+                if (dense_pc || K >= I) {
+                    const double2 pk = ldg_tile_t(Pcg, m, I, K, lane);
+#pragma unroll
+                    for (int J = 0; J < PT; ++J) {
+                        double2 z = ldg_tile(Zg, m, J, K, lane);
+                        const double wJ = vw[8 * J + g];
+                        z.x *= wJ;
+                        z.y *= wJ;
+                        mma_nt(acc[J], pk, z);
+                    }
+                }
+#pragma unroll
+            for (int J = 0; J < PT; ++J) stt(RB, A21T + I * PT + J, lane, fin(acc[J]));
+        }
+        // Abar11 = Hc^T Psi11  (accumulated: Hcbar^T), row I by own(I)
+#pragma unroll
+        for (int I = 0; I < PT; ++I) {
+            if (!own(I)) continue;
+            Acc2 acc[PT];
+#pragma unroll
+            for (int J = 0; J < PT; ++J) acc[J] = acc2_from(ldt(HBT, I * PT + J, lane));
+#pragma unroll
+            for (int K = I; K < PT; ++K) {
+                double2 h = ttrans(ldt(HC, K * PT + I, lane), lane);  // (Hc^T)[I][K]
+                if (Hzero) h = zero2();
+                else if (partial) h = make_double2(NAN, NAN);
+#pragma unroll
+                for (int J = 0; J < PT; ++J) mma_nt(acc[J], h, ldt(W, J * NT1 + K, lane));
+            }
+#pragma unroll
+            for (int J = 0; J < PT; ++J) stt(HBT, I * PT + J, lane, fin(acc[J]));
+        }
+        __syncthreads();  // (a row of [Abar21, Abar22] needs its own row of A21 only, but RF is overwritten below)
+        // rows of [Abar21, Abar22]; Abar21 -> RF[0 ..) (the factor is dead), Pbar^T = Abar22 + Abar21 Zm -> PBT
+#pragma unroll
+        for (int I = 0; I < MT; ++I) {
+            if (!own(I)) continue;
+            Acc2 acc2[NT1];
+#pragma unroll
+            for (int J = 0; J < NT1; ++J) acc2[J] = acc2_zero();
+#pragma unroll
+            for (int K = 0; K < NT1; ++K)
+                if (K < PT || dense_pc || K - PT >= I) {
+                    const double2 ak = K < PT ? ldt(RB, A21T + I * PT + (K < PT ? K : 0), lane)
+                                              : ldg_tile_t(Pcg, m, I, K >= PT ? K - PT : 0, lane);
+#pragma unroll
+                    for (int J = 0; J < NT1; ++J) mma_nt(acc2[J], ak, ldt(W, J * NT1 + K, lane));
+                }
+            double2 acc[NT1];
+#pragma unroll
+            for (int J = 0; J < NT1; ++J) acc[J] = fin(acc2[J]);
+#pragma unroll
+            for (int J = 0; J < PT; ++J) stt(smem + BD::AB21, I * PT + J, lane, acc[J]);
+#pragma unroll
+            for (int J = 0; J < MT; ++J) {
+                Acc2 pb = acc2_from(acc[PT + J]);
+#pragma unroll
+                for (int K = 0; K < PT; ++K) {
+                    double2 zt = ldg_tile_t(Zg, m, J, K, lane);  // (Zm^T)[J][K]: [g][2t+e] = Zm[8K+2t+e][8J+g]
+                    zt.x *= vw[8 * K + 2 * t];
+                    zt.y *= vw[8 * K + 2 * t + 1];
+                    mma_nt(pb, acc[K], zt);
+                }
+                stt(PBT, I * MT + J, lane, fin(pb));
+            }
+        }
+        __syncthreads(); BKF_TOCK(9)
+        // gZ += W (ZPbar Pc^T - vbar a^T),  ZPbar = Abar21^T, tile column J by own(J)
+        if (G.g_Z) {
+#pragma unroll
+            for (int J = 0; J < MT; ++J) {
+                if (!own(J)) continue;
+                double2 acc[PT];
+#pragma unroll
+                for (int Io = 0; Io < PT; ++Io) acc[Io] = zero2();
+#pragma unroll
+                for (int K = 0; K < MT; ++K)
+                    if (dense_pc || K <= J) {
+                        const double2 pc = ldg_tile(Pcg, m, J, K, lane);
+#pragma unroll
+                        for (int Io = 0; Io < PT; ++Io)
+                            mma_nt(acc[Io], ttrans(ldt(smem + BD::AB21, K * PT + Io, lane), lane), pc);
+                    }
+#pragma unroll
+                for (int Io = 0; Io < PT; ++Io) {
+                    const double wo = vw[8 * Io + g], vb = vvb[8 * Io + g];
+                    red_tile(gZ, m, Io, J, lane, make_double2(wo * fma(-vb, va[8 * J + 2 * t], acc[Io].x),
+                                                              wo * fma(-vb, va[8 * J + 2 * t + 1], acc[Io].y)));
+                }
+            }
+        }
+        // abar = afbar - Zm^T vbar (tile column J by own(J)); gd -= vbar
+#pragma unroll
+        for (int J = 0; J < MT; ++J) {
+            if (!own(J)) continue;
+            double c0 = 0.0, c1 = 0.0;
+#pragma unroll
+            for (int I = 0; I < PT; ++I) {
+                const double2 z = ldg_tile(Zg, m, I, J, lane);
+                const double f = vw[8 * I + g] * vvb[8 * I + g];
+                c0 = fma(z.x, f, c0);
+                c1 = fma(z.y, f, c1);
+            }
+            c0 = red_g(c0);
+            c1 = red_g(c1);
+            if (g == 0) {
+                vab[8 * J + 2 * t] = vafb[8 * J + 2 * t] - c0;
+                vab[8 * J + 2 * t + 1] = vafb[8 * J + 2 * t + 1] - c1;
+            }
+        }
+        if (warp == 0 && lane < p) vgd[lane] -= vvb[lane];
+        __syncthreads(); BKF_TOCK(10)
+    }
+    // ---- gradients out ----
+    for (int i = threadIdx.x; i < m; i += NTHR) {
+        if (G.g_a0) G.g_a0[(size_t)b * m + i] = vab[i];
+        if (G.g_c) G.g_c[(size_t)b * m + i] = vgc[i];
+    }
+    if (G.g_d && threadIdx.x < p) G.g_d[(size_t)b * p + threadIdx.x] = vgd[threadIdx.x];
+    if (G.g_P0) {
+        double* dst = G.g_P0 + (size_t)b * m * m;
+        for (int idx = warp; idx < MT * MT; idx += NWARP) {
+            const int I = idx / MT, J = idx % MT;
+            const double2 v = ldt(PBT, I * MT + J, lane);  // Pbar[8J+2t+e][8I+g]
+            dst[(8 * J + 2 * t) * m + 8 * I + g] = v.x;
+            dst[(8 * J + 2 * t + 1) * m + 8 * I + g] = v.y;
+        }
+    }
+    __threadfence();  // the reductions into PS / gT / gZ were issued by all warps; the epilogue below reads PS
+    __syncthreads();
+#ifdef BKF_SQC_PROFILE
+    if (b == 0 && lane == 0 && G.g_T)
+        for (int i = 0; i < 16; ++i) G.g_T[(size_t)b * m * m + 64 + warp * 16 + i] = (double)tb[i];
+    __syncthreads();
+#endif
+    if (warp != 0) return;
+    double* E = smem + BD::W;  // W, RF, RB are dead: one row-major scratch block
+    if (G.g_H) {
+        double* dst = G.g_H + (size_t)b * p * p;
+        if (Hzero) {
+            for (int idx = lane; idx < p * p; idx += 32) dst[idx] = HBT[elem_addr(idx % p, idx / p, PT)];
+        } else {
+            double *L = E, *Lb = E + p * p, *out = E + 2 * p * p, *tmp = E + 3 * p * p;
+            for (int idx = lane; idx < p * p; idx += 32) {
+                const int i = idx / p, j = idx - i * p;
+                L[idx] = HC[elem_addr(i, j, PT)];
+                Lb[idx] = j <= i ? HBT[elem_addr(j, i, PT)] : 0.0;
+            }
+            __syncwarp();
+            chol_pullback_warp(out, L, Lb, p, tmp, lane);
+            for (int idx = lane; idx < p * p; idx += 32) dst[idx] = out[idx];
+            __syncwarp();
+        }
+    }
+    if (want_ps) {
+        const double* Rg = param_ptr(G.Rm, G.shared_mask, BKF_PARAM_R, b, (size_t)m * r);
+        const double* Qg = param_ptr(G.Q, G.shared_mask, BKF_PARAM_Q, b, (size_t)r * r);
+        double *Qc = E, *X1 = Qc + r * r, *QQ = X1 + m * r, *Y = QQ + r * r, *Qb = Y + m * r, *out = Qb + r * r,
+               *tmp = out + r * r;
+        for (int i = lane; i < r * r; i += 32) Qc[i] = Qg[i];
+        __syncwarp();
+        chol_lower_warp(Qc, r, lane);
+        __syncwarp();
+        wmm<false>(X1, r, PS, m, 1, Rg, r, 1, m, r, m, lane);  // X1 = Psum R
+        if (G.g_R) {
+            wmm<false>(QQ, r, Qc, r, 1, Qc, 1, r, r, r, r, lane);  // Qc Qc^T
+            wmm<false>(Y, r, X1, r, 1, QQ, r, 1, m, r, r, lane);
+            for (int i = lane; i < m * r; i += 32) G.g_R[(size_t)b * m * r + i] = Y[i];
+            __syncwarp();
+        }
+        if (G.g_Q) {
+            wmm<false>(Y, r, X1, r, 1, Qc, r, 1, m, r, r, lane);   // X1 Qc
+            wmm<false>(Qb, r, Rg, 1, r, Y, r, 1, r, r, m, lane);   // R^T X1 Qc
+            for (int idx = lane; idx < r * r; idx += 32)
+                if ((idx % r) > (idx / r)) Qb[idx] = 0.0;
+            __syncwarp();
+            chol_pullback_warp(out, Qc, Qb, r, tmp, lane);
+            for (int i = lane; i < r * r; i += 32) G.g_Q[(size_t)b * r * r + i] = out[i];
+        }
+    }
+}
+
 }  // namespace sqc
 }  // namespace bkf

@@ -28,10 +28,10 @@ size_t record_elems_t() {
 template <int MT, int PT, int RT>
 int launch_t(const KArgs<double>& g, bool backward, cudaStream_t stream, const char** err) {
     using D = Dims<MT, PT, RT>;
-    if (backward) { *err = "sqc backward not built"; return BKF_ERR_UNSUPPORTED; }
-    const size_t bytes = (size_t)D::FWD_ELEMS * sizeof(double);
+    using BD = BDimsC<MT, PT, RT>;
+    const size_t bytes = (size_t)(backward ? BD::ELEMS : D::FWD_ELEMS) * sizeof(double);
     if (bytes > 227 * 1024) { *err = "shape too large for the four-warp square-root kernels"; return BKF_ERR_UNSUPPORTED; }
-    auto kern = forward_kernel<MT, PT, RT>;
+    auto kern = backward ? backward_kernel<MT, PT, RT> : forward_kernel<MT, PT, RT>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
     if (e != cudaSuccess) { *err = cudaGetErrorString(e); return BKF_ERR_CUDA; }
     kern<<<g.B, NTHR, bytes, stream>>>(g);

@@ -97,7 +97,33 @@ def profile():
           {q: int(t[34 + q] / (8 * npan[q])) for q in range(1, 7)}, "panels total/step", int(t[35:41].sum()))
 
 
+def profile_bwd():
+    """BKF_SQC_PROFILE build: phase timers of the adjoint sweep of series 0 (cycles per step, per warp)."""
+    sys.path.insert(0, ROOT)
+    from pymc_experimental_b200 import engine as _eng
+    from pymc_experimental_b200 import synth
+    from pymc_experimental_b200.engine import KalmanEngine
+
+    if os.environ.get("DBG_LIB"):
+        _eng.LIB_PATH = os.path.join(os.path.dirname(_eng.LIB_PATH), os.environ["DBG_LIB"])
+    eng = KalmanEngine(0)
+    B, n = int(os.environ.get("DBG_B", 512)), 100
+    cfg = synth.varmax(B, n)
+    args = [cfg["y"]] + [cfg[k] for k in NAMES]
+    for _ in range(2):
+        logp, grads, status = eng.logp_grad("cholesky", *args)
+    t = grads["T"][0].reshape(-1)[64:128] / n
+    names = ["load", "PS+ldRf", "solve|TPt", "U1t", "U1", "gT,Pcfb", "flag", "vec solves", "Rbar", "A21..rows", "gZ,abar",
+             "-", "-", "-", "psi4", "psi6"]
+    print("B", B, eng.last_path)
+    for w in range(4):
+        print("warp", w, {k: int(v) for k, v in zip(names, t[16 * w:16 * w + 16]) if k != "-"}, "sum", int(t[16 * w:16 * w + 16].sum()))
+
+
 if __name__ == "__main__":
+    if sys.argv[1] == "profile_bwd":
+        profile_bwd()
+        sys.exit(0)
     if sys.argv[1] == "profile":
         profile()
         sys.exit(0)
@@ -108,7 +134,7 @@ if __name__ == "__main__":
     if what == "time":
         timing()
         sys.exit(0)
-    bit = "1" if what == "fwd" else "3"
+    bit = "1" if what == "fwd" else "2"
     bad = 0
     for shape in SHAPES:
         for missing in (0.0, 0.2):
