@@ -275,7 +275,7 @@ def run_reference(args):
     # torchrun pins OMP_NUM_THREADS=1 in every worker; the CPU arm runs alone on rank 0 and may use the whole host
     if int(os.environ.get("WORLD_SIZE", "1")) > 1 or "OMP_NUM_THREADS" not in os.environ:
         os.environ["OMP_NUM_THREADS"] = os.environ.get("BKF_CPU_THREADS", str(os.cpu_count() or 1))
-    name = args.workload
+    name = args.workload or "C2"
     _, kind, dB, dT, mode = WORKLOADS[name]
     T = args.T or dT
     sB = cpu_sample_size(name, mode)
@@ -303,10 +303,12 @@ def run_reference(args):
 
 # ---- GPU arm ------------------------------------------------------------------------------------------------
 def run_b200(args):
+    """Headline line = the workload asked for (default C2).  With no --workload the line also carries, under "also",
+    one record each for C3, C4 and C5 at their BASELINE sizes (single GPU only), measured the same way."""
     import torch
     import torch.distributed as dist
 
-    from pymc_experimental_b200.engine import F32, F64, KalmanEngine
+    from pymc_experimental_b200.engine import KalmanEngine
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -318,17 +320,45 @@ def run_b200(args):
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
+    eng = KalmanEngine(local_rank)
+    ctx = {"world": world, "rank": rank, "local_rank": local_rank, "dev": dev, "eng": eng}
 
-    name = args.workload
+    name = args.workload or "C2"
+    line = measure_workload(args, ctx, name, args.batch, args.T, args.steps, with_cpu=world == 1 and not args.no_cpu)
+    if rank == 0 and args.workload is None and world == 1 and not args.no_also:
+        line["also"] = {}
+    if args.workload is None and world == 1 and not args.no_also:
+        for extra in ("C3", "C4", "C5"):
+            rec = measure_workload(args, ctx, extra, 0, 0, max(2, min(args.steps, 3)), with_cpu=False)
+            if rank == 0:
+                line["also"][extra] = {k: rec[k] for k in ("value", "unit", "ms_per_step", "steps", "warmup", "dtype", "config",
+                                                           "clocks", "gpu_launches", "e2e", "roofline") if k in rec}
+                for k in ("e2e_sample",):
+                    if k in rec:
+                        line["also"][extra][k] = rec[k]
+    if rank == 0:
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return line
+
+
+def measure_workload(args, ctx, name, batch, T_arg, steps, with_cpu):
+    import torch
+    import torch.distributed as dist
+
+    from pymc_experimental_b200.engine import F32, F64
+
+    world, rank, local_rank, dev, eng = ctx["world"], ctx["rank"], ctx["local_rank"], ctx["dev"], ctx["eng"]
     _, kind, dB, dT, mode = WORKLOADS[name]
-    B = args.batch or dB
-    T = args.T or dT
+    B = batch or dB
+    T = T_arg or dT
     dtype = torch.float64 if args.dtype == "f64" else torch.float32
     npdtype = np.float64 if args.dtype == "f64" else np.float32
     cfg, kind, mode = make_workload(name, B, T, seed_offset=rank)
     m, r = cfg["R"].shape[-2:]
     p = cfg["Z"].shape[-2]
-    eng = KalmanEngine(local_rank)
     jitter = 1e-8 if args.dtype == "f64" else 1e-6
 
     # device-resident inputs
@@ -380,7 +410,7 @@ def run_b200(args):
     barrier()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
-    for _ in range(args.steps):
+    for _ in range(steps):
         device_step()
     ev1.record()
     barrier()
@@ -394,21 +424,21 @@ def run_b200(args):
         dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
     ms = float(t_ms.item())
     units_per_step = B * T * world
-    value = units_per_step * args.steps / (ms * 1e-3)
+    value = units_per_step * steps / (ms * 1e-3)
 
     # ---- timed region: end to end through host buffers ----
     host_step()
     barrier()
     t0 = time.perf_counter()
     d2h = 0
-    for _ in range(args.steps):
+    for _ in range(steps):
         d2h = host_step()
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
     t_e = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t_e, op=dist.ReduceOp.MAX)
-    e2e_value = units_per_step * args.steps / float(t_e.item())
+    e2e_value = units_per_step * steps / float(t_e.item())
 
     # ---- the same through the compact parameterisation (row f-1): only the draw-dependent entries cross PCIe ----
     e2e_compact = None
@@ -426,13 +456,13 @@ def run_b200(args):
         compact_step()
         barrier()
         t0 = time.perf_counter()
-        for _ in range(args.steps):
+        for _ in range(steps):
             c_d2h = compact_step()
         torch.cuda.synchronize()
         t_c = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(t_c, op=dist.ReduceOp.MAX)
-        e2e_compact = {"value": units_per_step * args.steps / float(t_c.item()), "unit": UNIT,
+        e2e_compact = {"value": units_per_step * steps / float(t_c.item()), "unit": UNIT,
                        "h2d_bytes_per_step": int(hu.nbytes + hy.nbytes + sum(v.nbytes for v in hbase.values())),
                        "d2h_bytes_per_step": int(c_d2h),
                        "note": "bkf_filter_logp_grad_compact: 7 draw-dependent matrix entries per draw in, logp + 7 "
@@ -450,13 +480,13 @@ def run_b200(args):
         sample_step()
         barrier()
         t0 = time.perf_counter()
-        for _ in range(args.steps):
+        for _ in range(steps):
             s_d2h = sample_step()
         torch.cuda.synchronize()
         t_s = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(t_s, op=dist.ReduceOp.MAX)
-        e2e_sample = {"value": units_per_step * args.steps / float(t_s.item()), "unit": UNIT,
+        e2e_sample = {"value": units_per_step * steps / float(t_s.item()), "unit": UNIT,
                       "h2d_bytes_per_step": int(sum(a.nbytes for a in hargs) + hz.nbytes),
                       "d2h_bytes_per_step": int(s_d2h),
                       "note": "bkf_filter_smooth_sample: filter + smoother + one conditional-posterior draw per (draw, "
@@ -490,6 +520,12 @@ def run_b200(args):
         "achieved_hbm_gbs": ach_gbs, "hbm_peak_gbs": hbm_peak, "hbm_peak_source": peak_src,
         "all_kernels_ms": {k: (v[0] / v[1] if v[1] else None) for k, v in ktimes.items()},
     })
+    # every kernel of the step against the same peak: the whole step (device-timed, collectives included) and each kernel
+    step_flops = sum(f for f, _ in model.values()) * B * T
+    roof["whole_step"] = {"achieved_tflops": step_flops / (ms / steps * 1e-3) / 1e12,
+                          "frac_of_fma_peak": step_flops / (ms / steps * 1e-3) / 1e12 / fp64_peak}
+    roof["per_kernel_frac_of_fma_peak"] = {
+        k: (model[k][0] * B * T / (ktimes[k][0] / ktimes[k][1] * 1e-3) / 1e12 / fp64_peak) for k in model if ktimes[k][1] > 0}
     if dom == "smoother":
         roof["flops_note"] = ("smoother charged 14 m^3 + (7/3) m^3 (pinv as factor-and-solve) + O(m^2); SURVEY 8d's "
                               "figure with the reference's SVD pinv (22 m^3) is in achieved_tflops_survey_formula")
@@ -497,10 +533,10 @@ def run_b200(args):
 
     line = None
     if rank == 0:
-        cpu = cpu_baseline(name, kind, mode, cfg, T) if world == 1 and not args.no_cpu else None
+        cpu = cpu_baseline(name, kind, mode, cfg, T) if with_cpu else None
         line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms / steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
             "config": {"workload": f"{name}: {DESCR[name]}", "series_per_gpu": B, "T": T, "m": int(m), "p": int(p),
                        "r": int(r), "mode": mode, "kernel_path": eng.last_path,
@@ -516,10 +552,8 @@ def run_b200(args):
             line["e2e_sample"] = e2e_sample
         if cpu is not None:
             line["cpu_baseline"] = cpu
-        print(json.dumps(line))
-    if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
+    del dargs, packed, gathered, hargs
+    torch.cuda.empty_cache()
     return line
 
 
@@ -529,7 +563,9 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="C2", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default=None, choices=sorted(WORKLOADS),
+                    help="one workload only (default: C2 as the headline plus C3, C4, C5 under \"also\")")
+    ap.add_argument("--no-also", action="store_true", help="headline workload only")
     ap.add_argument("--batch", type=int, default=0, help="series per GPU (default: the workload's)")
     ap.add_argument("--T", type=int, default=0, help="time steps (default: the workload's)")
     ap.add_argument("--dtype", default="f64", choices=["f64", "f32"])

@@ -177,12 +177,15 @@ def ets(B=1_000_000, n=100, seed=SEED_BASE + 5):
     a0[:, 1:] = rng.standard_normal((B, 2))
     P0 = _bcast(np.eye(3), B)
     # vectorised simulation: one series per parameter set
-    x = a0.copy()
-    y = np.empty((B, n, 1))
-    for t in range(n):
-        y[:, t, 0] = x[:, 0] + x[:, 1]
-        e = sigma * rng.standard_normal(B)
-        x = np.einsum("bij,bj->bi", T_, x) + R[:, :, 0] * e[:, None]
+    x0, x1, x2 = a0[:, 0].copy(), a0[:, 1].copy(), a0[:, 2].copy()
+    Y = np.empty((n, B))
+    E = rng.standard_normal((n, B))
+    r0, r1, r2 = R[:, 0, 0] * sigma, R[:, 1, 0] * sigma, R[:, 2, 0] * sigma
+    for t in range(n):  # x <- T x + R e with T = [[0,0,0],[0,1,phi],[0,0,phi]] written out (a million 3 x 3 einsums are slow)
+        Y[t] = x0 + x1
+        e = E[t]
+        x0, x1, x2 = r0 * e, x1 + phi * x2 + r1 * e, phi * x2 + r2 * e
+    y = np.ascontiguousarray(Y.T)[:, :, None]
     return dict(y=y, a0=a0, P0=P0, c=np.zeros((B, 3)), d=np.zeros((B, 1)), T=T_, Z=Z,
                 R=np.ascontiguousarray(R), H=H, Q=np.ascontiguousarray(Q))
 
