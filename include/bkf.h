@@ -56,7 +56,8 @@ enum { BKF_PARAM_A0 = 0, BKF_PARAM_P0, BKF_PARAM_C, BKF_PARAM_D, BKF_PARAM_T, BK
        BKF_PARAM_H, BKF_PARAM_Q, BKF_NPARAM };
 
 /* call-level error codes */
-enum { BKF_OK = 0, BKF_ERR_ARG = -1, BKF_ERR_UNSUPPORTED = -2, BKF_ERR_CUDA = -3, BKF_ERR_NOMEM = -4 };
+enum { BKF_OK = 0, BKF_ERR_ARG = -1, BKF_ERR_UNSUPPORTED = -2, BKF_ERR_CUDA = -3, BKF_ERR_NOMEM = -4,
+       BKF_ERR_STALE = -5 /* bkf_filter_backward_saved: the saved forward sweep is gone, call bkf_filter_logp_grad */ };
 /* per-series status bits */
 enum { BKF_STATUS_OK = 0, BKF_STATUS_NOT_PD = 1, BKF_STATUS_NONFINITE = 2,
        BKF_STATUS_SMOOTHER_ILL = 4 /* P_hat too ill-conditioned for the Cholesky smoother: series was re-run with the
@@ -124,6 +125,21 @@ int bkf_filter_forward(bkf_handle* h, const bkf_problem* prob, const void* y, co
                        const void* Q, void* filtered_states, void* predicted_states, void* observed_states,
                        void* filtered_covariances, void* predicted_covariances, void* observed_covariances,
                        void* loglike_obs, int* status);
+
+/* The two halves of bkf_filter_logp_grad as separate calls, for a host framework whose forward and gradient are
+ * separate graph nodes (PyTensor: Op.perform of the log-likelihood node, then Op.perform of its L_op node; reference:
+ * pytensor.grad through Scan.L_op of kalman_filter.py:144-308).  bkf_filter_forward_saved runs the forward sweep ONCE,
+ * returns loglike_obs [B, n] and / or logp [B] (either may be NULL) and keeps the sweep's record in the handle;
+ * *ticket names it.  bkf_filter_backward_saved runs only the adjoint sweep on that record (same semantics of
+ * ll_cotangent and of the g_* pointers as bkf_filter_logp_grad).  The record lives until the next call on the handle
+ * that uses its workspace: after that, or with another ticket, bkf_filter_backward_saved returns BKF_ERR_STALE and has
+ * done nothing (the caller falls back to bkf_filter_logp_grad).  With BKF_MEM_DEVICE the caller's input buffers must
+ * stay unchanged between the two calls (with BKF_MEM_HOST the staged copies are used).  One ticket, one adjoint. */
+int bkf_filter_forward_saved(bkf_handle* h, const bkf_problem* prob, const void* y, const void* a0, const void* P0,
+                             const void* c, const void* d, const void* T, const void* Z, const void* R, const void* H,
+                             const void* Q, void* loglike_obs, void* logp, int* status, unsigned long long* ticket);
+int bkf_filter_backward_saved(bkf_handle* h, unsigned long long ticket, const void* ll_cotangent, void* g_a0,
+                              void* g_P0, void* g_c, void* g_d, void* g_T, void* g_Z, void* g_R, void* g_H, void* g_Q);
 
 /* logp[b] = sum_t loglike_obs[b,t];  g_x = d(sum_t ll_cotangent[b,t] * loglike_obs[b,t]) / dx
  * (ll_cotangent == NULL means all ones, the NUTS case).  Any g_* pointer may be NULL. */

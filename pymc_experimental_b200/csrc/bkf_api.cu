@@ -34,6 +34,15 @@ struct bkf_handle {
     size_t ev_used[BKF_NKERNEL] = {0, 0, 0};
     double ms_total[BKF_NKERNEL] = {0, 0, 0};
     long long ms_launches[BKF_NKERNEL] = {0, 0, 0};
+    // bkf_filter_forward_saved / bkf_filter_backward_saved: `gen` counts the times a workspace slot was handed out
+    unsigned long long gen = 0, tickets = 0;
+    struct Saved {
+        bool valid = false;
+        unsigned long long ticket = 0, gen = 0;
+        bkf_problem P;
+        KArgs<double> gd;
+        KArgs<float> gf;
+    } saved;
 };
 
 // RAII bracket: records start/stop events around one kernel launch when timing is on.
@@ -84,6 +93,7 @@ static int cuda_fail(bkf_handle* h, cudaError_t e, const char* what) {
 
 static void* ensure(bkf_handle* h, int slot, size_t bytes, int* rc) {
     auto& b = h->slots[slot];
+    h->gen += 1;
     if (bytes == 0) bytes = 8;
     if (b.cap < bytes) {
         if (b.p) cudaFree(b.p);
@@ -578,6 +588,95 @@ extern "C" int bkf_filter_logp_grad(bkf_handle* h, const bkf_problem* P, const v
     void* grads[BKF_NPARAM] = {g_a0, g_P0, g_c, g_d, g_T, g_Z, g_R, g_H, g_Q};
     return P->dtype == BKF_F64 ? logp_grad_impl<double>(h, P, y, prm, ll_cotangent, logp, grads, status)
                                : logp_grad_impl<float>(h, P, y, prm, ll_cotangent, logp, grads, status);
+}
+
+// ----------------------------------------------------------------------------------------------------
+// forward sweep now, adjoint sweep later (bkf.h: bkf_filter_forward_saved / bkf_filter_backward_saved)
+static KArgs<double>& saved_args(bkf_handle* h, double) { return h->saved.gd; }
+static KArgs<float>& saved_args(bkf_handle* h, float) { return h->saved.gf; }
+
+template <typename R>
+static int forward_saved_impl(bkf_handle* h, const bkf_problem* P, const void* y, const void* const* prm, void* ll,
+                              void* logp, int* status, unsigned long long* ticket) {
+    int rc = BKF_OK;
+    h->saved.valid = false;
+    KArgs<R> g;
+    fill_inputs<R>(h, P, g, y, prm, &rc);
+    const size_t B = P->B, n = P->n;
+    g.ll = stage_out<R>(h, P, S_LL, ll, B * n, &rc);
+    g.logp = stage_out<R>(h, P, S_LOGP, logp, B, &rc);
+    g.traj = (R*)ensure(h, S_TRAJ, traj_elems(P) * sizeof(R), &rc);
+    int* dstatus = nullptr;
+    if (status) dstatus = P->mem == BKF_MEM_DEVICE ? status : (int*)ensure(h, S_STATUS, B * sizeof(int), &rc);
+    g.status = dstatus;
+    if (rc != BKF_OK) return rc;
+    if (B > 0) {
+        const char* err = "";
+        rc = run_forward(h, g, &err);
+        if (rc != BKF_OK) return fail(h, rc, err);
+        copy_back<R>(h, P, ll, g.ll, B * n, &rc);
+        copy_back<R>(h, P, logp, g.logp, B, &rc);
+        if (status && P->mem == BKF_MEM_HOST && rc == BKF_OK) {
+            cudaError_t e = cudaMemcpyAsync(status, dstatus, B * sizeof(int), cudaMemcpyDeviceToHost, h->stream);
+            if (e != cudaSuccess) rc = cuda_fail(h, e, "D2H copy");
+        }
+    }
+    rc = finish(h, P, rc);
+    if (rc != BKF_OK) return rc;
+    g.ll = nullptr;  // (the adjoint sweep reads the record, not the outputs)
+    g.logp = nullptr;
+    g.status = nullptr;
+    h->saved.P = *P;
+    saved_args(h, R(0)) = g;
+    h->saved.ticket = ++h->tickets;
+    h->saved.gen = h->gen;
+    h->saved.valid = true;
+    *ticket = h->saved.ticket;
+    return BKF_OK;
+}
+
+template <typename R>
+static int backward_saved_impl(bkf_handle* h, const void* cot, void* const* grads) {
+    const bkf_problem* P = &h->saved.P;
+    KArgs<R> g = saved_args(h, R(0));
+    h->saved.valid = false;  // one ticket, one adjoint
+    int rc = BKF_OK;
+    const size_t B = P->B, n = P->n;
+    if (cot) g.ll_cot = stage_in<R>(h, P, S_COT, cot, B * n, &rc);
+    R** gdst[BKF_NPARAM] = {&g.g_a0, &g.g_P0, &g.g_c, &g.g_d, &g.g_T, &g.g_Z, &g.g_R, &g.g_H, &g.g_Q};
+    for (int i = 0; i < BKF_NPARAM; ++i)
+        *gdst[i] = stage_out<R>(h, P, S_GA0 + i, grads[i], B * param_elems(P, i), &rc);
+    if (rc != BKF_OK) return rc;
+    if (B == 0) return BKF_OK;
+    const char* err = "";
+    rc = run_backward(h, g, &err);
+    if (rc != BKF_OK) return fail(h, rc, err);
+    for (int i = 0; i < BKF_NPARAM; ++i) copy_back<R>(h, P, grads[i], *gdst[i], B * param_elems(P, i), &rc);
+    return finish(h, P, rc);
+}
+
+extern "C" int bkf_filter_forward_saved(bkf_handle* h, const bkf_problem* P, const void* y, const void* a0,
+                                        const void* P0, const void* c, const void* d, const void* T, const void* Z,
+                                        const void* R, const void* H, const void* Q, void* ll, void* logp, int* status,
+                                        unsigned long long* ticket) {
+    int rc = validate(h, P, true);
+    if (rc != BKF_OK) return rc;
+    const void* prm[BKF_NPARAM] = {a0, P0, c, d, T, Z, R, H, Q};
+    if (!y || !ticket || any_null(prm, BKF_NPARAM)) return fail(h, BKF_ERR_ARG, "null input pointer");
+    return P->dtype == BKF_F64 ? forward_saved_impl<double>(h, P, y, prm, ll, logp, status, ticket)
+                               : forward_saved_impl<float>(h, P, y, prm, ll, logp, status, ticket);
+}
+
+extern "C" int bkf_filter_backward_saved(bkf_handle* h, unsigned long long ticket, const void* cot, void* g_a0,
+                                         void* g_P0, void* g_c, void* g_d, void* g_T, void* g_Z, void* g_R, void* g_H,
+                                         void* g_Q) {
+    if (!h) return BKF_ERR_ARG;
+    if (!h->saved.valid || h->saved.ticket != ticket || h->saved.gen != h->gen)
+        return fail(h, BKF_ERR_STALE, "the saved forward sweep is gone (another call used the workspace)");
+    cudaError_t e = cudaSetDevice(h->device);
+    if (e != cudaSuccess) return cuda_fail(h, e, "cudaSetDevice");
+    void* grads[BKF_NPARAM] = {g_a0, g_P0, g_c, g_d, g_T, g_Z, g_R, g_H, g_Q};
+    return h->saved.P.dtype == BKF_F64 ? backward_saved_impl<double>(h, cot, grads) : backward_saved_impl<float>(h, cot, grads);
 }
 
 // ----------------------------------------------------------------------------------------------------

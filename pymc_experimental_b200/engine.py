@@ -35,8 +35,9 @@ ABI_SYMBOLS = (
     "bkf_filter_forward", "bkf_filter_logp_grad", "bkf_smooth", "bkf_filter_smooth", "bkf_host_alloc", "bkf_host_free",
     "bkf_logp_grad_workspace_bytes", "bkf_device_memory", "bkf_filter_logp_grad_compact", "bkf_stationary_init",
     "bkf_stationary_init_grad", "bkf_mvn_sample", "bkf_simulate",
-    "bkf_filter_smooth_sample",
+    "bkf_filter_smooth_sample", "bkf_filter_forward_saved", "bkf_filter_backward_saved",
 )
+ERR_STALE = -5
 
 
 class BkfProblem(C.Structure):
@@ -88,6 +89,8 @@ def load_library():
     pp = C.POINTER(BkfProblem)
     lib.bkf_filter_forward.argtypes = [vp, pp] + [vp] * 10 + [vp] * 7 + [vp]
     lib.bkf_filter_logp_grad.argtypes = [vp, pp] + [vp] * 10 + [vp] + [vp] + [vp] * 9 + [vp]
+    lib.bkf_filter_forward_saved.argtypes = [vp, pp] + [vp] * 10 + [vp, vp, vp, C.POINTER(C.c_ulonglong)]
+    lib.bkf_filter_backward_saved.argtypes = [vp, C.c_ulonglong, vp] + [vp] * 9
     lib.bkf_filter_logp_grad_compact.argtypes = [vp, pp, vp, C.POINTER(vp), C.c_int, C.POINTER(C.c_int),
                                                  C.POINTER(C.c_int), vp, vp, vp, vp, vp]
     lib.bkf_stationary_init.argtypes = [vp, pp] + [vp] * 4 + [vp] * 2 + [vp]
@@ -228,6 +231,8 @@ class KalmanEngine:
                            "(this engine has no CPU fallback)")
         self.h = h
         self.device = int(device)
+        self._stream = 0
+        self._saved = None  # (ticket, buffers kept alive, shapes) of the last forward_saved
         # logp_grad splits a batch whose device workspace (trajectory + staging) would exceed this many bytes;
         # None = 70 % of the device's memory (B200: ~125 of 180 GB)
         self.max_workspace_bytes = None
@@ -253,10 +258,28 @@ class KalmanEngine:
     def set_stream(self, cuda_stream_ptr: int | None):
         self.lib.bkf_set_stream(self.h, C.c_void_p(cuda_stream_ptr or 0))
 
-    def use_torch_stream(self):
+    def use_torch_stream(self, bufs=None):
+        """Device-pointer calls run on torch's current stream of this engine's device.  The workspace of the handle is
+        shared by every call, so when the stream changes the old one is drained first; tensors of another device are
+        refused (the kernels would run on the wrong GPU)."""
         import torch
 
-        self.set_stream(torch.cuda.current_stream(self.device).cuda_stream)
+        if bufs is not None and bufs.dev.index is not None and bufs.dev.index != self.device:
+            raise BkfError(f"tensors live on cuda:{bufs.dev.index} but this engine drives cuda:{self.device}")
+        s = torch.cuda.current_stream(self.device).cuda_stream
+        if s != self._stream:
+            torch.cuda.synchronize(self.device)
+            self.set_stream(s)
+            self._stream = s
+
+    def use_default_stream(self):
+        """Host-pointer calls run on the legacy default stream (a torch stream set earlier may be gone by now)."""
+        if self._stream != 0:
+            import torch
+
+            torch.cuda.synchronize(self.device)
+            self.set_stream(0)
+            self._stream = 0
 
     @property
     def launch_count(self) -> int:
@@ -374,7 +397,9 @@ class KalmanEngine:
         outs = {k_: (bufs.out(shapes[k_]) if k_ in outputs else None) for k_ in shapes}
         status = bufs.out_int((B,))
         if bufs.device:
-            self.use_torch_stream()
+            self.use_torch_stream(bufs)
+        else:
+            self.use_default_stream()
         rc = self.lib.bkf_filter_forward(
             self.h, C.byref(prob), bufs.ptr(yb), *[bufs.ptr(a) for a in arrs],
             *[bufs.ptr(outs[k_]) for k_ in shapes], bufs.ptr(status))
@@ -448,7 +473,9 @@ class KalmanEngine:
             if tuple(cot.shape) != (B, n) and not (squeeze and tuple(cot.shape) == (n,)):
                 raise BkfError("ll_cotangent must have shape (B, n)")
         if bufs.device:
-            self.use_torch_stream()
+            self.use_torch_stream(bufs)
+        else:
+            self.use_default_stream()
         rc = self.lib.bkf_filter_logp_grad(
             self.h, C.byref(prob), bufs.ptr(yb), *[bufs.ptr(a) for a in arrs], bufs.ptr(cot), bufs.ptr(logp),
             *[bufs.ptr(gouts[k_]) for k_ in PARAM_NAMES], bufs.ptr(status))
@@ -457,6 +484,60 @@ class KalmanEngine:
         if squeeze:
             return logp[0], {k_: v[0] for k_, v in g.items()}, status[0]
         return logp, g, status
+
+    def forward_saved(self, kind, y, a0, P0, c, d, T, Z, R, H, Q, cov_jitter=None, missing_fill_value=None, dtype=None,
+                      time_varying=(), want_ll=True):
+        """Forward sweep only (``bkf_filter_forward_saved``): returns ``(loglike_obs or None, logp, status, ticket)`` and
+        keeps the sweep's record on the device for ONE later :meth:`backward_saved` with that ticket."""
+        params = dict(zip(PARAM_NAMES, (a0, P0, c, d, T, Z, R, H, Q)))
+        bufs = _Buffers([y, *params.values()], dtype)
+        params = {k_: (v if _is_torch(v) else np.asarray(v)) for k_, v in params.items()}
+        y = y if _is_torch(y) else np.asarray(y)
+        B = self._batch_size(y, params, time_varying)
+        squeeze = B is None
+        B = 1 if squeeze else int(B)
+        prob, yb, arrs = self._problem(kind, bufs, y, params, B, cov_jitter, missing_fill_value, time_varying)
+        ll = bufs.out((B, prob.n)) if want_ll else None
+        logp = bufs.out((B,))
+        status = bufs.out_int((B,))
+        if bufs.device:
+            self.use_torch_stream(bufs)
+        else:
+            self.use_default_stream()
+        ticket = C.c_ulonglong(0)
+        self._check(self.lib.bkf_filter_forward_saved(
+            self.h, C.byref(prob), bufs.ptr(yb), *[bufs.ptr(a) for a in arrs], bufs.ptr(ll), bufs.ptr(logp),
+            bufs.ptr(status), C.byref(ticket)))
+        gshape = {"a0": (B, prob.m), "P0": (B, prob.m, prob.m), "c": (B, prob.m), "d": (B, prob.p),
+                  "T": (B, prob.m, prob.m), "Z": (B, prob.p, prob.m), "R": (B, prob.m, prob.r),
+                  "H": (B, prob.p, prob.p), "Q": (B, prob.r, prob.r)}
+        for k_ in time_varying:
+            gshape[k_] = (B, prob.n) + gshape[k_][1:]
+        self._saved = (ticket.value, bufs, gshape, squeeze, (B, prob.n))
+        if squeeze:
+            return (None if ll is None else ll[0]), logp[0], status[0], ticket.value
+        return ll, logp, status, ticket.value
+
+    def backward_saved(self, ticket, ll_cotangent=None, grads=PARAM_NAMES):
+        """Adjoint sweep on the record of :meth:`forward_saved` (``bkf_filter_backward_saved``).  Returns the dict of
+        gradients, or ``None`` when the record is gone (the caller then runs :meth:`logp_grad`)."""
+        saved, self._saved = self._saved, None
+        if saved is None or saved[0] != int(ticket):
+            return None
+        _, bufs, gshape, squeeze, (B, n) = saved
+        gouts = {k_: (bufs.out(gshape[k_]) if k_ in grads else None) for k_ in PARAM_NAMES}
+        cot = None
+        if ll_cotangent is not None:
+            cot = bufs.inp(ll_cotangent)
+            if tuple(cot.shape) != (B, n) and not (squeeze and tuple(cot.shape) == (n,)):
+                raise BkfError("ll_cotangent must have shape (B, n)")
+        rc = self.lib.bkf_filter_backward_saved(self.h, C.c_ulonglong(int(ticket)), bufs.ptr(cot),
+                                                *[bufs.ptr(gouts[k_]) for k_ in PARAM_NAMES])
+        if rc == ERR_STALE:
+            return None
+        self._check(rc)
+        g = {k_: v for k_, v in gouts.items() if v is not None}
+        return {k_: v[0] for k_, v in g.items()} if squeeze else g
 
     def logp_grad_compact(self, kind, y, base, positions, u, ll_cotangent=None, cov_jitter=None,
                           missing_fill_value=None, dtype=None, want_grad=True):
@@ -489,7 +570,9 @@ class KalmanEngine:
         status = bufs.out_int((B,))
         base_ptrs = (C.c_void_p * 9)(*[bufs.ptr(a).value for a in arrs])
         if bufs.device:
-            self.use_torch_stream()
+            self.use_torch_stream(bufs)
+        else:
+            self.use_default_stream()
         rc = self.lib.bkf_filter_logp_grad_compact(
             self.h, C.byref(prob), bufs.ptr(yb), base_ptrs, nnz, which, index, bufs.ptr(ub), bufs.ptr(cot),
             bufs.ptr(logp), bufs.ptr(g_u), bufs.ptr(status))
@@ -526,7 +609,9 @@ class KalmanEngine:
         prob, v, B, m, r, squeeze = self._stationary_problem(bufs, c, T, R, Q)
         a0, P0, status = bufs.out((B, m)), bufs.out((B, m, m)), bufs.out_int((B,))
         if bufs.device:
-            self.use_torch_stream()
+            self.use_torch_stream(bufs)
+        else:
+            self.use_default_stream()
         self._check(self.lib.bkf_stationary_init(self.h, C.byref(prob), *[bufs.ptr(v[k_]) for k_ in ("c", "T", "R", "Q")],
                                                  bufs.ptr(a0), bufs.ptr(P0), bufs.ptr(status)))
         return (a0[0], P0[0], status[0]) if squeeze else (a0, P0, status)
@@ -539,7 +624,9 @@ class KalmanEngine:
         a0b, P0b, ab, Pb = fix(a0, 1), fix(P0, 2), fix(a0_bar, 1), fix(P0_bar, 2)
         g = {"c": bufs.out((B, m)), "T": bufs.out((B, m, m)), "R": bufs.out((B, m, r)), "Q": bufs.out((B, r, r))}
         if bufs.device:
-            self.use_torch_stream()
+            self.use_torch_stream(bufs)
+        else:
+            self.use_default_stream()
         self._check(self.lib.bkf_stationary_init_grad(
             self.h, C.byref(prob), bufs.ptr(v["T"]), bufs.ptr(v["R"]), bufs.ptr(v["Q"]), bufs.ptr(a0b), bufs.ptr(P0b),
             bufs.ptr(ab), bufs.ptr(Pb), *[bufs.ptr(g[k_]) for k_ in ("c", "T", "R", "Q")]))
@@ -565,7 +652,9 @@ class KalmanEngine:
         dmu, dcov, dz = bufs.inp(mu), bufs.inp(cov), bufs.inp(z)
         x, status = bufs.out((B, n, m)), bufs.out_int((B,))
         if bufs.device:
-            self.use_torch_stream()
+            self.use_torch_stream(bufs)
+        else:
+            self.use_default_stream()
         self._check(self.lib.bkf_mvn_sample(self.h, C.byref(prob), bufs.ptr(dmu), bufs.ptr(dcov), bufs.ptr(dz),
                                             bufs.ptr(x), bufs.ptr(status)))
         return (x[0], status[0]) if squeeze else (x, status)
@@ -592,7 +681,9 @@ class KalmanEngine:
         dz = bufs.inp(z)
         x, ll, status = bufs.out((B, n, m)), bufs.out((B, n)), bufs.out_int((B,))
         if bufs.device:
-            self.use_torch_stream()
+            self.use_torch_stream(bufs)
+        else:
+            self.use_default_stream()
         self._check(self.lib.bkf_filter_smooth_sample(self.h, C.byref(prob), bufs.ptr(yb), *[bufs.ptr(a) for a in arrs],
                                                       bufs.ptr(dz), bufs.ptr(ll), bufs.ptr(x), bufs.ptr(status)))
         return (x[0], ll[0], status[0]) if squeeze else (x, ll, status)
@@ -619,7 +710,9 @@ class KalmanEngine:
         zs = [bufs.inp(v) for v in (z_x0, z_y0, z_state, z_obs)]
         states, obs, status = bufs.out((B, n + 1, m)), bufs.out((B, n + 1, p)), bufs.out_int((B,))
         if bufs.device:
-            self.use_torch_stream()
+            self.use_torch_stream(bufs)
+        else:
+            self.use_default_stream()
         self._check(self.lib.bkf_simulate(self.h, C.byref(prob), *[bufs.ptr(x) for x in arrs], *[bufs.ptr(x) for x in zs],
                                           bufs.ptr(states), bufs.ptr(obs), bufs.ptr(status)))
         return states, obs, status
@@ -677,7 +770,9 @@ class KalmanEngine:
         Tb, Rb, Qb, fab, fPb = map(bufs.inp, (T, R, Q, fa, fP))
         sa, sP = bufs.out((B, n, m)), bufs.out((B, n, m, m))
         if bufs.device:
-            self.use_torch_stream()
+            self.use_torch_stream(bufs)
+        else:
+            self.use_default_stream()
         rc = self.lib.bkf_smooth(self.h, C.byref(prob), *[bufs.ptr(x) for x in (Tb, Rb, Qb, fab, fPb, sa, sP)],
                                  None)
         self._check(rc)
@@ -699,7 +794,9 @@ class KalmanEngine:
         ll, sa, sP = bufs.out((B, n)), bufs.out((B, n, m)), bufs.out((B, n, m, m))
         status = bufs.out_int((B,))
         if bufs.device:
-            self.use_torch_stream()
+            self.use_torch_stream(bufs)
+        else:
+            self.use_default_stream()
         rc = self.lib.bkf_filter_smooth(self.h, C.byref(prob), bufs.ptr(yb), *[bufs.ptr(a) for a in arrs],
                                         bufs.ptr(ll), bufs.ptr(sa), bufs.ptr(sP), bufs.ptr(status))
         self._check(rc)
@@ -708,12 +805,39 @@ class KalmanEngine:
         return ll, sa, sP, status
 
 
-_default_engines: dict[tuple[int, int], KalmanEngine] = {}
+_default_engines: dict[int, KalmanEngine] = {}
+_cuda_pid: int | None = None  # the process that created the first engine (and with it a CUDA context)
+
+
+def _after_fork_in_child():
+    """A forked child inherits handles and pinned buffers that belong to the parent's CUDA context: drop them (without
+    calling into the driver) so that nothing dangling is ever used."""
+    global _pinned_pool
+    for eng in _default_engines.values():
+        eng.h = None
+    _default_engines.clear()
+    _pinned_pool = None
+
+
+if hasattr(os, "register_at_fork"):
+    os.register_at_fork(after_in_child=_after_fork_in_child)
 
 
 def default_engine(device: int = 0) -> KalmanEngine:
-    """Per-process (fork-safe: keyed by pid) lazily created engine, as a PyTensor Op.perform needs it."""
-    key = (os.getpid(), device)
-    if key not in _default_engines:
-        _default_engines[key] = KalmanEngine(device)
-    return _default_engines[key]
+    """Lazily created per-process engine, as a PyTensor ``Op.perform`` needs it.
+
+    NOT fork-safe, and says so: CUDA cannot be initialised in a child forked from a process that already holds a CUDA
+    context, and ``pm.sample`` evaluates the model in the parent (start-value check) before it forks its chain
+    workers.  Use ``pm.sample(..., mp_ctx="spawn")`` (or ``"forkserver"``, or ``cores=1``): a spawned worker imports this
+    module afresh and gets an engine of its own here."""
+    global _cuda_pid
+    pid = os.getpid()
+    if _cuda_pid is not None and _cuda_pid != pid:
+        raise BkfError(
+            f"this process (pid {pid}) was forked from pid {_cuda_pid}, which had already initialised CUDA: the Kalman "
+            "engine cannot run here.  Start the workers with the 'spawn' or 'forkserver' context "
+            "(pm.sample(..., mp_ctx='spawn')) or sample with cores=1")
+    if device not in _default_engines:
+        _default_engines[device] = KalmanEngine(device)
+        _cuda_pid = pid
+    return _default_engines[device]

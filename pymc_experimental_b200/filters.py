@@ -27,13 +27,29 @@ from __future__ import annotations
 
 import numpy as np
 
-from .engine import JITTER_F64, MISSING_FILL, default_engine
+from .engine import JITTER_F32, JITTER_F64, MISSING_FILL, default_engine
 
-JITTER_DEFAULT = JITTER_F64  # utils/constants.py:20 for floatX == float64
+JITTER_DEFAULT = JITTER_F64  # utils/constants.py:20 for floatX == float64 (float32: 1e-6, see _resolve_jitter)
 PARAM_NAMES = ["c", "d", "T", "Z", "R", "H", "Q"]  # kalman_filter.py:22
 _STATIC_NDIM = {"c": 1, "d": 1, "T": 2, "Z": 2, "R": 2, "H": 2, "Q": 2}
 OUTPUT_NAMES = ["filtered_states", "predicted_states", "observed_states", "filtered_covariances",
                 "predicted_covariances", "observed_covariances", "loglike_obs"]
+
+
+def _resolve_jitter(cov_jitter, symbolic, arrays):
+    """``cov_jitter=None`` means the reference's dtype-dependent default (utils/constants.py:20): 1e-8 in float64,
+    1e-6 in float32 -- floatX for a PyTensor graph, the dtype the engine will compute in for eager inputs (float64 for
+    NumPy arrays, the tensors' own dtype for torch CUDA tensors)."""
+    if cov_jitter is not None:
+        return cov_jitter
+    if symbolic:
+        from . import pytensor_ops
+
+        return pytensor_ops.default_jitter()
+    for a in arrays:
+        if type(a).__module__.startswith("torch") and getattr(a, "is_cuda", False):
+            return JITTER_F32 if str(a.dtype) == "torch.float32" else JITTER_F64
+    return JITTER_F64
 
 
 def _is_symbolic(*xs):
@@ -78,14 +94,14 @@ class BaseFilter:
             raise NotImplementedError
         if missing_fill_value is None:
             missing_fill_value = MISSING_FILL  # kalman_filter.py:197-200
-        if cov_jitter is None:
-            cov_jitter = JITTER_DEFAULT
+        data, a0, P0, c, d, T, Z, R, H, Q = self.check_params(data, a0, P0, c, d, T, Z, R, H, Q)
+        symbolic = _is_symbolic(data, a0, P0, c, d, T, Z, R, H, Q)
+        cov_jitter = _resolve_jitter(cov_jitter, symbolic, (data, a0, P0, c, d, T, Z, R, H, Q))
         self.mode = mode
         self.missing_fill_value = missing_fill_value
         self.cov_jitter = cov_jitter
-        data, a0, P0, c, d, T, Z, R, H, Q = self.check_params(data, a0, P0, c, d, T, Z, R, H, Q)
 
-        if _is_symbolic(data, a0, P0, c, d, T, Z, R, H, Q):
+        if symbolic:
             if mode not in (None, "FAST_RUN", "FAST_COMPILE"):
                 raise NotImplementedError(
                     f"mode={mode!r}: the B200 Kalman Ops only run under PyTensor's default C/Python linker "
@@ -155,11 +171,13 @@ class KalmanSmoother:
         self.non_seq_names: list[str] = []
         self.device = device
 
-    def build_graph(self, T, R, Q, filtered_states, filtered_covariances, mode=None, cov_jitter=JITTER_DEFAULT,
+    def build_graph(self, T, R, Q, filtered_states, filtered_covariances, mode=None, cov_jitter=None,
                     time_varying=None):
+        symbolic = _is_symbolic(T, R, Q, filtered_states, filtered_covariances)
+        cov_jitter = _resolve_jitter(cov_jitter, symbolic, (T, R, Q, filtered_states, filtered_covariances))
         self.mode = mode
         self.cov_jitter = cov_jitter
-        if _is_symbolic(T, R, Q, filtered_states, filtered_covariances):
+        if symbolic:
             if mode not in (None, "FAST_RUN", "FAST_COMPILE"):
                 raise NotImplementedError(f"mode={mode!r} is not supported by the B200 Kalman Ops")
             from . import pytensor_ops

@@ -18,16 +18,33 @@ def shard_bounds(B: int, world: int, rank: int) -> tuple[int, int]:
     return lo, lo + base + (1 if rank < extra else 0)
 
 
-def shard_inputs(arrays: dict, B: int, world: int, rank: int, shared=()):
-    """Slice every batched array to this rank's block; arrays named in ``shared`` (or without a batch axis of
-    length B) are replicated."""
+_STATIC_NDIM = {"y": 2, "a0": 1, "P0": 2, "c": 1, "d": 1, "T": 2, "Z": 2, "R": 2, "H": 2, "Q": 2}
+
+
+def shard_inputs(arrays: dict, B: int, world: int, rank: int, shared=(), time_varying=(), batched=()):
+    """Slice every batched array to this rank's block; the others are replicated.
+
+    Whether an array carries the batch axis is decided by its RANK against the static rank of its name (``y`` [n, p],
+    ``a0`` [m], ``P0`` [m, m] ... plus one for the names in ``time_varying``), as ``KalmanEngine`` does -- never by
+    ``shape[0] == B``, which would silently slice a shared array whose leading dimension happens to equal B.  Arrays
+    with other names are sliced only when listed in ``batched``; names in ``shared`` are never sliced."""
     lo, hi = shard_bounds(B, world, rank)
     out = {}
     for k, v in arrays.items():
-        if k in shared or v.shape[0] != B:
-            out[k] = v
+        if k in shared:
+            is_batched = False
+        elif k in batched:
+            is_batched = True
+        elif k in _STATIC_NDIM:
+            nd = _STATIC_NDIM[k] + int(k in time_varying)
+            if v.ndim not in (nd, nd + 1):
+                raise ValueError(f"{k}: expected {nd} (shared) or {nd + 1} (batched) dims, got {v.ndim}")
+            is_batched = v.ndim == nd + 1
         else:
-            out[k] = v[lo:hi]
+            raise ValueError(f"{k}: not a state-space input; list it in `batched` or `shared`")
+        if is_batched and v.shape[0] != B:
+            raise ValueError(f"{k}: leading batch dimension {v.shape[0]} != {B}")
+        out[k] = v[lo:hi] if is_batched else v
     return out
 
 

@@ -143,7 +143,7 @@ def test_c4_varmax_square_root_spot_check(eng):
     assert eng.last_path == "sqrt_warp_dmma"
     assert int(status.abs().sum()) == 0
     _spot_check("cholesky", cfg, logp.cpu().numpy(), {k: v.cpu().numpy() for k, v in grads.items()},
-                np.array([0, 295, 591]), rtol=1e-8)
+                np.array([0, 295, 591]), rtol=1e-9)
 
 
 def test_c3_conditional_posterior_draw_full_size(eng):
