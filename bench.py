@@ -34,6 +34,7 @@ sys.path.insert(0, ROOT)
 METRIC = "kalman_logp_grad_state_steps_per_sec"
 UNIT = "state-steps/s"
 NAMES = ("a0", "P0", "c", "d", "T", "Z", "R", "H", "Q")
+STATIC_NDIM = {"a0": 1, "P0": 2, "c": 1, "d": 1, "T": 2, "Z": 2, "R": 2, "H": 2, "Q": 2}
 
 WORKLOADS = {
     # name: (synth fn name, filter kind, default B per GPU, default T, mode)
@@ -336,6 +337,15 @@ def run_b200(args):
                 for k in ("e2e_sample",):
                     if k in rec:
                         line["also"][extra][k] = rec[k]
+    if world > 1 and not args.no_also and not args.batch:
+        # strong scaling beside the (default) weak figure: the workload's BASELINE total split over the ranks
+        _, _, dB, _, _ = WORKLOADS[name]
+        total = {"C4": 4096}.get(name, dB)  # C4's BASELINE total is 4 096 draws (512 per GPU on 8 GPUs)
+        rec = measure_workload(args, ctx, name, max(total // world, 1), args.T, args.steps, with_cpu=False)
+        if rank == 0:
+            line["strong_scaling"] = {"total_series": total, "series_per_gpu": max(total // world, 1), "value": rec["value"],
+                                      "unit": rec["unit"], "ms_per_step": rec["ms_per_step"], "e2e": rec["e2e"],
+                                      "note": "same workload, the BASELINE total split over the ranks (fixed total work)"}
     if rank == 0:
         print(json.dumps(line))
     if world > 1:
@@ -366,11 +376,29 @@ def measure_workload(args, ctx, name, batch, T_arg, steps, with_cpu):
     layout, total = eng.packed_layout(B, m, p, r)
     packed = torch.empty(total, dtype=dtype, device=dev)
     gathered = torch.empty(total * world, dtype=dtype, device=dev) if world > 1 else None
+    # N > 1: the batch goes through the kernels in two halves, each with its own packed [logp | grads] buffer; the
+    # all-gather of the first half (NCCL's own stream, async_op) runs under the kernels of the second half, so only half of
+    # the one collective of the path is exposed.  (Series are independent: halves give bit-identical results.)
+    halves = []
+    if world > 1 and mode == "logp_grad" and B >= 2:
+        for lo, hi in ((0, B // 2), (B // 2, B)):
+            _, tot_h = eng.packed_layout(hi - lo, m, p, r)
+            sl = [dargs[0][lo:hi] if cfg["y"].ndim == 3 else dargs[0]]
+            sl += [a[lo:hi] if a.ndim == STATIC_NDIM[k] + 1 else a for k, a in zip(NAMES, dargs[1:])]
+            halves.append((sl, torch.empty(tot_h, dtype=dtype, device=dev), torch.empty(tot_h * world, dtype=dtype, device=dev)))
 
     def device_step():
         if mode == "logp_grad":
+            if halves:  # the only inter-GPU traffic: one all-gather of [logp | grads] over NVLink, in two overlapped parts
+                works = []
+                for sl, pk, gt in halves:
+                    eng.logp_grad(kind, *sl, packed_out=pk, cov_jitter=jitter)
+                    works.append(dist.all_gather_into_tensor(gt, pk, async_op=True))
+                for w in works:
+                    w.wait()
+                return None
             out = eng.logp_grad(kind, *dargs, packed_out=packed, cov_jitter=jitter)
-            if world > 1:  # the only inter-GPU traffic: one all-gather of [logp | grads] over NVLink
+            if world > 1:
                 dist.all_gather_into_tensor(gathered, packed)
             return out
         return eng.filter_smooth(kind, *dargs, cov_jitter=jitter)
@@ -499,8 +527,9 @@ def measure_workload(args, ctx, name, batch, T_arg, steps, with_cpu):
     dom = max((k for k in model if ktimes[k][1] > 0), key=lambda k: ktimes[k][0])
     dom_ms = ktimes[dom][0] / ktimes[dom][1]
     flops, bytes_ = model[dom]
-    ach_tf = flops * B * T / (dom_ms * 1e-3) / 1e12
-    ach_gbs = bytes_ * B * T / (dom_ms * 1e-3) / 1e9
+    Bl = B / (len(halves) or 1)  # series per kernel launch (N > 1 runs the batch as two launches per kernel)
+    ach_tf = flops * Bl * T / (dom_ms * 1e-3) / 1e12
+    ach_gbs = bytes_ * Bl * T / (dom_ms * 1e-3) / 1e9
     t_fp = flops / (fp64_peak * 1e12)
     t_hbm = bytes_ / (hbm_peak * 1e9)
     if t_fp >= t_hbm:
@@ -525,11 +554,11 @@ def measure_workload(args, ctx, name, batch, T_arg, steps, with_cpu):
     roof["whole_step"] = {"achieved_tflops": step_flops / (ms / steps * 1e-3) / 1e12,
                           "frac_of_fma_peak": step_flops / (ms / steps * 1e-3) / 1e12 / fp64_peak}
     roof["per_kernel_frac_of_fma_peak"] = {
-        k: (model[k][0] * B * T / (ktimes[k][0] / ktimes[k][1] * 1e-3) / 1e12 / fp64_peak) for k in model if ktimes[k][1] > 0}
+        k: (model[k][0] * Bl * T / (ktimes[k][0] / ktimes[k][1] * 1e-3) / 1e12 / fp64_peak) for k in model if ktimes[k][1] > 0}
     if dom == "smoother":
         roof["flops_note"] = ("smoother charged 14 m^3 + (7/3) m^3 (pinv as factor-and-solve) + O(m^2); SURVEY 8d's "
                               "figure with the reference's SVD pinv (22 m^3) is in achieved_tflops_survey_formula")
-        roof["achieved_tflops_survey_formula"] = smoother_flops(m, r, True) * B * T / (dom_ms * 1e-3) / 1e12
+        roof["achieved_tflops_survey_formula"] = smoother_flops(m, r, True) * Bl * T / (dom_ms * 1e-3) / 1e12
 
     line = None
     if rank == 0:
@@ -541,7 +570,8 @@ def measure_workload(args, ctx, name, batch, T_arg, steps, with_cpu):
             "config": {"workload": f"{name}: {DESCR[name]}", "series_per_gpu": B, "T": T, "m": int(m), "p": int(p),
                        "r": int(r), "mode": mode, "kernel_path": eng.last_path,
                        "l2": "working set (trajectory workspace + parameters) exceeds the 126 MB L2; no explicit flush",
-                       "parallelism": f"independent series sharded over {world} GPU(s); one final NCCL all-gather"},
+                       "parallelism": f"independent series sharded over {world} GPU(s); one final NCCL all-gather of [logp | "
+                                      "grads]" + (", issued in two halves: the first under the second half's kernels" if halves else "")},
             "clocks": clocks, "gpu_launches": int(launches),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
             "roofline": roof,
