@@ -83,6 +83,11 @@ typedef struct bkf_problem {
                               parameters have the same time axis.  All three filters and the smoother. */
     double cov_jitter;     /* JITTER_DEFAULT: 1e-8 (f64) / 1e-6 (f32), utils/constants.py:20 */
     double missing_fill;   /* MISSING_FILL = -9999.0, utils/constants.py:19 */
+    unsigned long long rng_seed;   /* sampling calls with a NULL variate pointer draw their standard normals in the kernel: */
+    unsigned long long rng_offset; /* Philox4x32-10 keyed by rng_seed, Box-Muller; variate i of variate array s of the call is
+                                      a pure function of (rng_seed, rng_offset, s, i) -- independent of the launch geometry
+                                      and of B (see bkf_mvn_sample).  Advance rng_offset between calls (any stride >= the
+                                      largest variate array of a call), as a counter-based generator is used. */
 } bkf_problem;
 
 int bkf_version(void);
@@ -164,6 +169,25 @@ int bkf_filter_logp_grad_compact(bkf_handle* h, const bkf_problem* prob, const v
                                  int nnz, const int* which, const int* index, const void* u, const void* ll_cotangent,
                                  void* logp, void* g_u, int* status);
 
+/* theta -> matrices on the device (the rest of row f-1): the entries of the compact vector are themselves simple
+ * functions of a model's free parameters -- SARIMA: phi_i, Phi_j, -phi_i Phi_j, theta, Theta, theta Theta, sigma^2
+ * (models/SARIMAX.py:404-458); ETS: alpha, alpha beta, 1 - alpha, phi ... (models/ETS.py:499-555); VARMAX: the AR / MA
+ * coefficients themselves and Q = L L^T (models/VARMAX.py:297-393); structural components: rho cos(lambda),
+ * rho sin(lambda), sigma^2 (models/structural.py:858-875, 1220-1237, 1489-1514) -- all of the form
+ *     u_k(theta) = sum over the terms of entry k of   coef * prod_{f < nfac} fn_f(theta[idx_f]),   nfac <= 3,
+ * with fn one of BKF_FN_*.  The caller ships theta [B, ntheta] only; the library evaluates u on the device, expands the
+ * matrices, runs the filter and its adjoint, and applies the chain rule: g_theta [B, ntheta] = d(sum_t cot ll)/dtheta.
+ * Term q: entry term_entry[q] in [0, nnz), coefficient term_coef[q], term_nfac[q] factors with parameter indices
+ * term_theta[3q + f] and function codes term_fn[3q + f] (HOST arrays, like which / index; any order).  An entry without
+ * terms is 0; a constant is a term with nfac = 0.  base, which, index as in bkf_filter_logp_grad_compact; y, theta, ll_cot,
+ * logp, g_theta (nullable), status live where prob->mem says. */
+enum { BKF_FN_ID = 0, BKF_FN_COS = 1, BKF_FN_SIN = 2, BKF_FN_EXP = 3, BKF_FN_ONE_MINUS = 4, BKF_FN_SQUARE = 5 };
+int bkf_filter_logp_grad_theta(bkf_handle* h, const bkf_problem* prob, const void* y, const void* const base[9], int nnz,
+                               const int* which, const int* index, int nterms, const int* term_entry,
+                               const double* term_coef, const int* term_nfac, const int* term_theta, const int* term_fn,
+                               int ntheta, const void* theta, const void* ll_cotangent, void* logp, void* g_theta,
+                               int* status);
+
 /* Stationary initialisation, the step right before the filter in the reference's SARIMA /
  * VARMA / ETS models (models/SARIMAX.py:369-381, VARMAX.py:379-393, ETS.py:453-466):
  *     a0 = (I - T)^{-1} c          P0 = solve_discrete_lyapunov(T, R Q R^T)      (P0 = T P0 T^T + R Q R^T)
@@ -192,7 +216,8 @@ int bkf_filter_smooth(bkf_handle* h, const bkf_problem* prob, const void* y, con
 /* The whole of sample_conditional_posterior (core/statespace.py:1061-1171) for a batch of posterior draws in one call:
  * filter forward, smoother, then one draw x[b,t] ~ N(smoothed_state[b,t], smoothed_cov[b,t]) (bkf_mvn_sample below) --
  * the smoothed moments never leave the device; only x [B,n,m] (and loglike_obs [B,n], nullable) come back.
- * z: standard normal variates [B,n,m] supplied by the caller.  m <= 32. */
+ * z: standard normal variates [B,n,m] supplied by the caller, or NULL: drawn in the kernel (prob->rng_seed / rng_offset,
+ * variate array 0) -- then nothing but y and the parameters goes in and only x comes out.  m <= 32. */
 int bkf_filter_smooth_sample(bkf_handle* h, const bkf_problem* prob, const void* y, const void* a0, const void* P0,
                              const void* c, const void* d, const void* T, const void* Z, const void* R, const void* H,
                              const void* Q, const void* z, void* loglike_obs, void* x, int* status);
@@ -203,8 +228,11 @@ int bkf_filter_smooth_sample(bkf_handle* h, const bkf_problem* prob, const void*
  * MvNormalSVD (:52-87) over time to sample the conditional posterior from the smoother's output
  * (core/statespace.py:1119-1150).  L is the lower Cholesky factor with semidefinite pivots dropped (a pivot below
  * 64 m eps max(diag) zeroes its column): like the reference's SVD square root it accepts rank-deficient covariances, and
- * the distribution of x is the same for every square root.  z: standard normal variates drawn by the caller, so the call
- * itself is deterministic.  Uses prob->B, n, m, dtype, mem; mu, z, x: [B, n, m]; cov: [B, n, m, m] (lower triangle
+ * the distribution of x is the same for every square root.  z: standard normal variates drawn by the caller, or NULL:
+ * generated in the kernel by the counter-based generator of prob->rng_seed / rng_offset (variate array 0, variate
+ * i = flat index into [B, n, m]: counter rng_offset + i / 2 -> 128 Philox bits -> two uniforms in (0, 1) -> one
+ * Box-Muller pair, variate i takes element i & 1) -- either way the call is deterministic.
+ * Uses prob->B, n, m, dtype, mem; mu, z, x: [B, n, m]; cov: [B, n, m, m] (lower triangle
  * read); m <= 32.  status[B] (nullable): BKF_STATUS_NOT_PD if some cov[b,t] has a pivot below -1e-8 max(diag)
  * (-1e-4 in float32), numpy's check_valid tolerance. */
 int bkf_mvn_sample(bkf_handle* h, const bkf_problem* prob, const void* mu, const void* cov, const void* z, void* x,
@@ -215,7 +243,8 @@ int bkf_mvn_sample(bkf_handle* h, const bkf_problem* prob, const void* mu, const
  *     x_0 ~ N(a0, P0),  y_0 ~ N(Z x_0, H)                      (:262-263: no d in the first observation mean)
  *     x_t = c + T x_{t-1} + R eps_t,  eps_t ~ N(0, Q) ;  y_t = d + Z x_t + eta_t,  eta_t ~ N(0, H)       (:247-254)
  * Every normal draw is (Cholesky factor with dropped semidefinite pivots, as bkf_mvn_sample) x (standard normal variates
- * supplied by the caller): z_x0 [B,m], z_y0 [B,p], z_state [B,n,r], z_obs [B,n,p].  Outputs: states [B,n+1,m],
+ * supplied by the caller): z_x0 [B,m], z_y0 [B,p], z_state [B,n,r], z_obs [B,n,p] -- or all four NULL: generated in the
+ * kernel (prob->rng_seed / rng_offset; variate arrays 1, 2, 3, 4 in that order).  Outputs: states [B,n+1,m],
  * obs [B,n+1,p] (row 0 = the initial draw; the reference concatenates the two along the last axis, append_x0=True).
  * Parameters follow prob->shared_mask and prob->tv_mask (sequences of length n: step t uses x[t], the initial
  * observation Z[0] and H[0], :259-260).  status[B] (nullable):

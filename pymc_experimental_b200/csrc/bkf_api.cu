@@ -17,7 +17,7 @@ enum Slot {
     S_Y = 0, S_A0, S_P0, S_C, S_D, S_T, S_Z, S_R, S_H, S_Q,            // inputs (order = BKF_PARAM_* + 1)
     S_FA, S_PA, S_OM, S_FP, S_PP, S_OC, S_LL,                          // forward outputs
     S_TRAJ, S_COT, S_LOGP, S_GA0, S_GP0, S_GC, S_GD, S_GT, S_GZ, S_GR, S_GH, S_GQ, S_STATUS,
-    S_SMA, S_SMP, S_WFA, S_WFP, S_FLAG, S_U, S_GU, S_MAP, S_BASE, S_NSLOT
+    S_SMA, S_SMP, S_WFA, S_WFP, S_FLAG, S_U, S_GU, S_MAP, S_BASE, S_THETA, S_GTHETA, S_PROG, S_NSLOT
 };
 
 struct bkf_handle {
@@ -250,13 +250,9 @@ static int run_forward(bkf_handle* h, const KArgs<double>& g, const char** err) 
     KernelTimer kt(h, BKF_KERNEL_FORWARD);
     h->launches += 1;
     if (g.kind == BKF_CHOLESKY) {
-        if (sqc::supported(g, false)) {
-            h->path = "sqrt_cta4_lookahead";
-            return sqc::launch_f64(g, false, h->stream, err);
-        }
-        if (sqw::supported(g, false)) {
+        if (sqw::supported(g)) {  // (with a trajectory it writes the tile record the four-warp adjoint reads)
             h->path = "sqrt_warp_dmma";
-            return sqw::launch_f64(g, false, h->stream, err);
+            return sqw::launch_f64(g, h->stream, err);
         }
         h->path = "sqrt_cta";
         return sq::launch_forward<double>(g, h->stream, err);
@@ -297,13 +293,11 @@ static int run_forward(bkf_handle* h, const KArgs<float>& g, const char** err) {
 static int run_backward(bkf_handle* h, const KArgs<double>& g, const char** err) {
     KernelTimer kt(h, BKF_KERNEL_BACKWARD);
     h->launches += 1;
-    if (g.kind == BKF_CHOLESKY && sqc::supported(g, true)) {
-        h->path += "+adjoint_cta4";
-        return sqc::launch_f64(g, true, h->stream, err);
+    if (g.kind == BKF_CHOLESKY && g.rec_tiles) {
+        h->path += "+adjoint_4warp";
+        return sqb::launch_f64(g, h->stream, err);
     }
-    if (g.kind == BKF_CHOLESKY)
-        return sqw::supported(g, true) ? sqw::launch_f64(g, true, h->stream, err)
-                                       : sq::launch_backward<double>(g, h->stream, err);
+    if (g.kind == BKF_CHOLESKY) return sq::launch_backward<double>(g, h->stream, err);
     if (g.tv_mask) return gen::launch_backward<double>(g, h->stream, err);
     if (tps::supported(g.kind, g.m, g.p)) return tps::launch_any<double>(g, true, h->stream, err);
     if (tc::supported(g.kind, g.m, g.p)) return tc::launch_f64(g, true, h->stream, err);
@@ -318,39 +312,39 @@ static int run_backward(bkf_handle* h, const KArgs<float>& g, const char** err) 
     return gen::launch_backward<float>(g, h->stream, err);
 }
 
-// Smoother dispatch: Cholesky sub-warp kernel when available; whole-call fallback to the eigen-decomposition
-// pinv of the generic kernel if any series was flagged ill-conditioned (costs one 4-byte readback).
+// Smoother dispatch: the DMMA / sub-warp kernels when available, with a per-series fallback to the eigen-decomposition
+// pinv of the generic kernel for the series they flag as ill-conditioned.
 static int run_smoother(bkf_handle* h, const KArgs<double>& g, const char** err) {
     const double jitter0 = 1e-8;  // JITTER_DEFAULT (float64), kalman_smoother.py:117
     const bool use_tc = tc::smoother_supported(g.m);
     if (!g.tv_mask && (use_tc || sw::smoother_supported(g.m))) {
+        // The fast kernels invert P_hat directly and list the series where that is not safe (pivot <= 0 or spanning
+        // > 1e13); the generic kernel then redoes exactly those with the eigen-decomposition pinv.  The list lives on
+        // the device and the second launch strides over it (it returns at once when the list is empty): no host round
+        // trip, the flagged series are reported through status (BKF_STATUS_SMOOTHER_ILL).
         int rc = BKF_OK;
-        int* flag = (int*)ensure(h, S_FLAG, sizeof(int), &rc);
-        if (!flag) return rc;
-        cudaMemsetAsync(flag, 0, sizeof(int), h->stream);
+        int* ill = (int*)ensure(h, S_FLAG, ((size_t)g.B + 1) * sizeof(int), &rc);
+        if (!ill) return rc;
+        cudaMemsetAsync(ill, 0, sizeof(int), h->stream);
         {
             KernelTimer kt(h, BKF_KERNEL_SMOOTHER);
             h->launches += 1;
-            rc = use_tc ? tc::launch_smoother_f64(g, jitter0, flag, h->stream, err)
-                        : sw::launch_smoother_f64(g, jitter0, flag, h->stream, err);
+            rc = use_tc ? tc::launch_smoother_f64(g, jitter0, ill, h->stream, err)
+                        : sw::launch_smoother_f64(g, jitter0, ill, h->stream, err);
         }
         if (rc != BKF_OK) return rc;
-        int host_flag = 0;
-        cudaError_t e = cudaMemcpyAsync(&host_flag, flag, sizeof(int), cudaMemcpyDeviceToHost, h->stream);
-        if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
-        if (e != cudaSuccess) { *err = cudaGetErrorString(e); return BKF_ERR_CUDA; }
         h->path = use_tc ? "dmma_f64" : "subwarp_f64";
-        if (!host_flag) return BKF_OK;
-        h->path = "generic_warp(smoother fallback)";
+        h->launches += 1;
+        return gen::launch_smoother<double>(g, ill + 1, ill, h->stream, err);
     }
     KernelTimer kt(h, BKF_KERNEL_SMOOTHER);
     h->launches += 1;
-    return gen::launch_smoother<double>(g, h->stream, err);
+    return gen::launch_smoother<double>(g, nullptr, nullptr, h->stream, err);
 }
 static int run_smoother(bkf_handle* h, const KArgs<float>& g, const char** err) {
     KernelTimer kt(h, BKF_KERNEL_SMOOTHER);
     h->launches += 1;
-    return gen::launch_smoother<float>(g, h->stream, err);
+    return gen::launch_smoother<float>(g, nullptr, nullptr, h->stream, err);
 }
 
 // elements of parameter `which` for ONE series: the matrix itself, times n when it carries a time axis
@@ -431,6 +425,7 @@ static void fill_inputs(bkf_handle* h, const bkf_problem* P, KArgs<R>& g, const 
     g.tv_mask = P->tv_mask;
     g.jitter = (R)P->cov_jitter;
     g.fill = (R)P->missing_fill;
+    g.rec_tiles = P->dtype == BKF_F64 && sqb::tile_record(P->kind, P->m, P->p, P->r, P->tv_mask);
     size_t B = P->B;
     if (y) g.y = stage_in<R>(h, P, S_Y, y, (P->y_shared ? 1 : B) * (size_t)P->n * P->p, rc);
     const R** dst[BKF_NPARAM] = {&g.a0, &g.P0, &g.c, &g.d, &g.T, &g.Z, &g.Rm, &g.H, &g.Q};
@@ -510,6 +505,11 @@ static size_t traj_record_elems(const bkf_problem* P) {
 // adjoint's add-only accumulators (bkf_sqrt_warp.cuh).
 static size_t traj_elems(const bkf_problem* P) {
     const size_t B = P->B, n = P->n;
+    if (P->dtype == BKF_F64 && sqb::tile_record(P->kind, P->m, P->p, P->r, P->tv_mask)) {
+        size_t rec, scr;
+        sqb::sizes(P->m, P->p, P->r, &rec, &scr);
+        return B * n * rec + B * scr;
+    }
     return B * (n + (P->kind == BKF_CHOLESKY ? 1 : 0)) * traj_record_elems(P);
 }
 
@@ -710,10 +710,71 @@ __global__ void gather_kernel(R* __restrict__ gu, ScatterArgs<R> a, const MapEnt
     }
 }
 
+// theta -> entries program (bkf.h: bkf_filter_logp_grad_theta).  Entry k of the compact vector is
+//     u_k(theta) = sum over its terms  coef * prod_{f < nfac} fn_f(theta[idx_f]),   nfac <= 3.
+// Device layout of the table (ints, then doubles): start[nnz + 1] | nfac[nterms] | idx[3 nterms] | fn[3 nterms] ; coef[nterms].
+struct ThetaProg {
+    int nterms, ntheta;
+    const int *start, *nfac, *idx, *fn;  // device
+    const double* coef;                  // device
+    const void* theta;                   // caller's theta [B, ntheta] (prob->mem)
+    void* g_theta;                       // caller's output [B, ntheta] (nullable)
+};
+__device__ __forceinline__ double theta_fn(int fn, double x, double* dx) {
+    switch (fn) {
+        case BKF_FN_COS: *dx = -sin(x); return cos(x);
+        case BKF_FN_SIN: *dx = cos(x); return sin(x);
+        case BKF_FN_EXP: { const double e = exp(x); *dx = e; return e; }
+        case BKF_FN_ONE_MINUS: *dx = -1.0; return 1.0 - x;
+        case BKF_FN_SQUARE: *dx = 2.0 * x; return x * x;
+        default: *dx = 1.0; return x;
+    }
+}
+template <typename R>
+__global__ void theta_eval_kernel(R* __restrict__ u, const R* __restrict__ theta, ThetaProg pg, int nnz, size_t B) {
+    const size_t total = (size_t)nnz * B;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const size_t b = i / nnz;
+        const int k = (int)(i - b * nnz);
+        const R* th = theta + b * pg.ntheta;
+        double acc = 0.0;
+        for (int q = pg.start[k]; q < pg.start[k + 1]; ++q) {
+            double v = pg.coef[q], dx;
+            for (int f = 0; f < pg.nfac[q]; ++f) v *= theta_fn(pg.fn[3 * q + f], (double)th[pg.idx[3 * q + f]], &dx);
+            acc += v;
+        }
+        u[i] = (R)acc;
+    }
+}
+// chain rule: g_theta[b, i] = sum_k g_u[b, k] du_k / dtheta_i; one thread per draw walks the table in order (deterministic)
+template <typename R>
+__global__ void theta_chain_kernel(R* __restrict__ gth, const R* __restrict__ gu, const R* __restrict__ theta, ThetaProg pg,
+                                   int nnz, size_t B) {
+    for (size_t b = blockIdx.x * (size_t)blockDim.x + threadIdx.x; b < B; b += (size_t)gridDim.x * blockDim.x) {
+        const R* th = theta + b * pg.ntheta;
+        R* g = gth + b * pg.ntheta;
+        for (int i = 0; i < pg.ntheta; ++i) g[i] = R(0);
+        for (int k = 0; k < nnz; ++k) {
+            const double gk = (double)gu[b * nnz + k];
+            for (int q = pg.start[k]; q < pg.start[k + 1]; ++q) {
+                double val[3], der[3];
+                const int nf = pg.nfac[q];
+                for (int f = 0; f < nf; ++f) val[f] = theta_fn(pg.fn[3 * q + f], (double)th[pg.idx[3 * q + f]], &der[f]);
+                for (int f = 0; f < nf; ++f) {
+                    double v = gk * pg.coef[q] * der[f];
+                    for (int f2 = 0; f2 < nf; ++f2)
+                        if (f2 != f) v *= val[f2];
+                    g[pg.idx[3 * q + f]] += (R)v;
+                }
+            }
+        }
+    }
+}
+
 template <typename R>
 static int compact_impl(bkf_handle* h, const bkf_problem* P, const void* y, const void* const* base, int nnz,
                         const int* which, const int* index, const void* u, const void* cot, void* logp, void* g_u,
-                        int* status) {
+                        int* status, const ThetaProg* prog = nullptr) {
     int rc = BKF_OK;
     const size_t B = P->B, n = P->n;
     const bool host = P->mem == BKF_MEM_HOST;
@@ -737,7 +798,14 @@ static int compact_impl(bkf_handle* h, const bkf_problem* P, const void* y, cons
     Pd.shared_mask = 0;
     Pd.tv_mask = 0;
     g.y = stage_in<R>(h, P, S_Y, y, (P->y_shared ? 1 : B) * n * (size_t)P->p, &rc);
-    const R* du = stage_in<R>(h, P, S_U, u, B * (size_t)nnz, &rc);
+    const R* du = nullptr;
+    const R* dtheta = nullptr;
+    if (prog) {  // u is evaluated on the device from theta
+        dtheta = stage_in<R>(h, P, S_THETA, prog->theta, B * (size_t)prog->ntheta, &rc);
+        du = (const R*)ensure(h, S_U, (B * (size_t)nnz + 1) * sizeof(R), &rc);
+    } else {
+        du = stage_in<R>(h, P, S_U, u, B * (size_t)nnz, &rc);
+    }
     if (cot) g.ll_cot = stage_in<R>(h, P, S_COT, cot, B * n, &rc);
     size_t base_off[BKF_NPARAM + 1] = {0};
     for (int i = 0; i < BKF_NPARAM; ++i) base_off[i + 1] = base_off[i] + param_elems(P, i);
@@ -775,15 +843,21 @@ static int compact_impl(bkf_handle* h, const bkf_problem* P, const void* y, cons
     }
     g.shared_mask = Pd.shared_mask;
     g.logp = stage_out<R>(h, P, S_LOGP, logp, B, &rc);
-    R* dgu = stage_out<R>(h, P, S_GU, g_u, B * (size_t)nnz, &rc);
+    R* dgu = prog ? (prog->g_theta ? (R*)ensure(h, S_GU, (B * (size_t)nnz + 1) * sizeof(R), &rc) : nullptr)
+                  : stage_out<R>(h, P, S_GU, g_u, B * (size_t)nnz, &rc);
+    R* dgth = prog ? stage_out<R>(h, P, S_GTHETA, prog->g_theta, B * (size_t)prog->ntheta, &rc) : nullptr;
     int* dstatus = nullptr;
     if (status) dstatus = host ? (int*)ensure(h, S_STATUS, B * sizeof(int), &rc) : status;
     g.status = dstatus;
-    const bool want_grad = g_u != nullptr && nnz > 0;
+    const bool want_grad = (prog ? prog->g_theta != nullptr : g_u != nullptr) && nnz > 0;
     if (want_grad) g.traj = (R*)ensure(h, S_TRAJ, traj_elems(&Pd) * sizeof(R), &rc);
     if (rc != BKF_OK) return rc;
     if (B == 0) return BKF_OK;
     const unsigned sgrid = (unsigned)std::min<size_t>((B * (size_t)(nnz > 0 ? nnz : 1) + 255) / 256, 4096);
+    if (prog && nnz) {
+        theta_eval_kernel<R><<<sgrid, 256, 0, h->stream>>>(const_cast<R*>(du), dtheta, *prog, nnz, B);
+        h->launches += 1;
+    }
     if (nnz) scatter_kernel<R><<<sgrid, 256, 0, h->stream>>>(sa, dmap, nnz, du, B);
     h->launches += 1 + (nnz ? 1 : 0);
     const char* err = "";
@@ -794,9 +868,14 @@ static int compact_impl(bkf_handle* h, const bkf_problem* P, const void* y, cons
         if (rc != BKF_OK) return fail(h, rc, err);
         gather_kernel<R><<<sgrid, 256, 0, h->stream>>>(dgu, ga, dmap, nnz, B);
         h->launches += 1;
+        if (prog) {
+            theta_chain_kernel<R><<<(unsigned)std::min<size_t>((B + 127) / 128, 4096), 128, 0, h->stream>>>(dgth, dgu, dtheta, *prog, nnz, B);
+            h->launches += 1;
+        }
     }
     copy_back<R>(h, P, logp, g.logp, B, &rc);
-    if (want_grad) copy_back<R>(h, P, g_u, dgu, B * (size_t)nnz, &rc);
+    if (want_grad && !prog) copy_back<R>(h, P, g_u, dgu, B * (size_t)nnz, &rc);
+    if (want_grad && prog) copy_back<R>(h, P, prog->g_theta, dgth, B * (size_t)prog->ntheta, &rc);
     if (status && host && rc == BKF_OK) {
         cudaError_t e = cudaMemcpyAsync(status, dstatus, B * sizeof(int), cudaMemcpyDeviceToHost, h->stream);
         if (e != cudaSuccess) rc = cuda_fail(h, e, "D2H copy");
@@ -816,6 +895,68 @@ extern "C" int bkf_filter_logp_grad_compact(bkf_handle* h, const bkf_problem* P,
     return P->dtype == BKF_F64
                ? compact_impl<double>(h, P, y, base, nnz, which, index, u, ll_cotangent, logp, g_u, status)
                : compact_impl<float>(h, P, y, base, nnz, which, index, u, ll_cotangent, logp, g_u, status);
+}
+
+extern "C" int bkf_filter_logp_grad_theta(bkf_handle* h, const bkf_problem* P, const void* y, const void* const base[9],
+                                          int nnz, const int* which, const int* index, int nterms, const int* term_entry,
+                                          const double* term_coef, const int* term_nfac, const int* term_theta,
+                                          const int* term_fn, int ntheta, const void* theta, const void* ll_cotangent,
+                                          void* logp, void* g_theta, int* status) {
+    int rc = validate(h, P, true);
+    if (rc != BKF_OK) return rc;
+    if (P->tv_mask) return fail(h, BKF_ERR_UNSUPPORTED, "the theta parameterisation does not take time-varying inputs");
+    if (!y || !base || any_null(base, BKF_NPARAM) || nnz < 0 || nterms < 0 || ntheta < 0 ||
+        (nnz > 0 && (!which || !index)) || (nterms > 0 && (!term_entry || !term_coef || !term_nfac || !term_theta || !term_fn)) ||
+        (ntheta > 0 && !theta))
+        return fail(h, BKF_ERR_ARG, "null input pointer");
+    // table: terms grouped by entry (CSR), validated on the host, shipped once per call (a few hundred bytes)
+    std::vector<int> start(nnz + 1, 0), order(nterms);
+    for (int q = 0; q < nterms; ++q) {
+        if (term_entry[q] < 0 || term_entry[q] >= nnz || term_nfac[q] < 0 || term_nfac[q] > 3)
+            return fail(h, BKF_ERR_ARG, "theta program: term entry / factor count out of range");
+        for (int f = 0; f < term_nfac[q]; ++f)
+            if (term_theta[3 * q + f] < 0 || term_theta[3 * q + f] >= ntheta || term_fn[3 * q + f] < 0 ||
+                term_fn[3 * q + f] > BKF_FN_SQUARE)
+                return fail(h, BKF_ERR_ARG, "theta program: parameter index / function code out of range");
+        start[term_entry[q] + 1] += 1;
+    }
+    for (int k = 0; k < nnz; ++k) start[k + 1] += start[k];
+    {
+        std::vector<int> fill(start.begin(), start.end() - 1);
+        for (int q = 0; q < nterms; ++q) order[fill[term_entry[q]]++] = q;  // stable: the caller's order within an entry
+    }
+    const size_t nint = (size_t)(nnz + 1) + 7 * (size_t)nterms, nint_pad = (nint + 1) & ~(size_t)1;
+    std::vector<int> ints(nint_pad, 0);
+    std::vector<double> coef(nterms > 0 ? nterms : 1, 0.0);
+    int* pstart = ints.data();
+    int* pnfac = pstart + nnz + 1;
+    int* pidx = pnfac + nterms;
+    int* pfn = pidx + 3 * (size_t)nterms;
+    for (int k = 0; k <= nnz; ++k) pstart[k] = start[k];
+    for (int j = 0; j < nterms; ++j) {
+        const int q = order[j];
+        pnfac[j] = term_nfac[q];
+        coef[j] = term_coef[q];
+        for (int f = 0; f < 3; ++f) {
+            pidx[3 * j + f] = f < term_nfac[q] ? term_theta[3 * q + f] : 0;
+            pfn[3 * j + f] = f < term_nfac[q] ? term_fn[3 * q + f] : 0;
+        }
+    }
+    char* dtab = (char*)ensure(h, S_PROG, nint_pad * sizeof(int) + coef.size() * sizeof(double), &rc);
+    if (!dtab) return rc;
+    cudaError_t e = cudaMemcpyAsync(dtab, ints.data(), nint_pad * sizeof(int), cudaMemcpyHostToDevice, h->stream);
+    if (e == cudaSuccess)
+        e = cudaMemcpyAsync(dtab + nint_pad * sizeof(int), coef.data(), coef.size() * sizeof(double), cudaMemcpyHostToDevice, h->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);  // (the host vectors die with this frame)
+    if (e != cudaSuccess) return cuda_fail(h, e, "theta program upload");
+    ThetaProg pg;
+    pg.nterms = nterms; pg.ntheta = ntheta;
+    pg.start = (const int*)dtab; pg.nfac = pg.start + nnz + 1; pg.idx = pg.nfac + nterms; pg.fn = pg.idx + 3 * (size_t)nterms;
+    pg.coef = (const double*)(dtab + nint_pad * sizeof(int));
+    pg.theta = theta; pg.g_theta = g_theta;
+    return P->dtype == BKF_F64
+               ? compact_impl<double>(h, P, y, base, nnz, which, index, nullptr, ll_cotangent, logp, nullptr, status, &pg)
+               : compact_impl<float>(h, P, y, base, nnz, which, index, nullptr, ll_cotangent, logp, nullptr, status, &pg);
 }
 
 // ----------------------------------------------------------------------------------------------------
@@ -940,7 +1081,7 @@ static int sample_impl(bkf_handle* h, const bkf_problem* P, const void* mu, cons
     const char* err = "";
     h->launches += 1;
     h->path = "mvn_chol_subwarp";
-    rc = smp::launch<R>(dmu, dcov, dz, dx, dstatus, (long long)(B * n), (int)n, (int)m, h->stream, &err);
+    rc = smp::launch<R>(dmu, dcov, dz, smp::Rng{P->rng_seed, P->rng_offset}, dx, dstatus, (long long)(B * n), (int)n, (int)m, h->stream, &err);
     if (rc != BKF_OK) return fail(h, rc, err);
     copy_back<R>(h, P, x, dx, B * n * m, &rc);
     if (status && P->mem == BKF_MEM_HOST && rc == BKF_OK) {
@@ -957,7 +1098,7 @@ extern "C" int bkf_mvn_sample(bkf_handle* h, const bkf_problem* P, const void* m
     if (P->dtype != BKF_F64 && P->dtype != BKF_F32) return fail(h, BKF_ERR_ARG, "unknown dtype");
     if (P->mem != BKF_MEM_HOST && P->mem != BKF_MEM_DEVICE) return fail(h, BKF_ERR_ARG, "unknown memory space");
     if (P->B < 0 || P->n < 0 || P->m < 1) return fail(h, BKF_ERR_ARG, "non-positive dimension");
-    if (!mu || !cov || !z || !x) return fail(h, BKF_ERR_ARG, "null pointer");
+    if (!mu || !cov || !x) return fail(h, BKF_ERR_ARG, "null pointer");  // (z == NULL: variates drawn in the kernel)
     cudaError_t e = cudaSetDevice(h->device);
     if (e != cudaSuccess) return cuda_fail(h, e, "cudaSetDevice");
     return P->dtype == BKF_F64 ? sample_impl<double>(h, P, mu, cov, z, x, status)
@@ -985,7 +1126,7 @@ static int simulate_impl(bkf_handle* h, const bkf_problem* P, const void* const*
     const char* err = "";
     h->launches += 1;
     h->path = "simulate_warp";
-    rc = smp::launch_simulate<R>(g, dzx, dzy, dzs, dzo, dxs, dys, h->stream, &err);
+    rc = smp::launch_simulate<R>(g, dzx, dzy, dzs, dzo, smp::Rng{P->rng_seed, P->rng_offset}, dxs, dys, h->stream, &err);
     if (rc != BKF_OK) return fail(h, rc, err);
     copy_back<R>(h, P, states, dxs, B * (n + 1) * m, &rc);
     copy_back<R>(h, P, obs, dys, B * (n + 1) * p, &rc);
@@ -1003,7 +1144,9 @@ extern "C" int bkf_simulate(bkf_handle* h, const bkf_problem* P, const void* a0,
     int rc = validate(h, P, true);
     if (rc != BKF_OK) return rc;
     const void* prm[BKF_NPARAM] = {a0, P0, c, d, T, Z, R, H, Q};
-    if (any_null(prm, BKF_NPARAM) || !z_x0 || !z_y0 || !z_state || !z_obs || !states || !obs)
+    const int nz = (z_x0 != nullptr) + (z_y0 != nullptr) + (z_state != nullptr) + (z_obs != nullptr);
+    if (nz != 0 && nz != 4) return fail(h, BKF_ERR_ARG, "pass all four variate arrays, or none (in-kernel generator)");
+    if (any_null(prm, BKF_NPARAM) || !states || !obs)
         return fail(h, BKF_ERR_ARG, "null pointer");
     return P->dtype == BKF_F64 ? simulate_impl<double>(h, P, prm, z_x0, z_y0, z_state, z_obs, states, obs, status)
                                : simulate_impl<float>(h, P, prm, z_x0, z_y0, z_state, z_obs, states, obs, status);
@@ -1116,7 +1259,7 @@ static int filter_smooth_sample_impl(bkf_handle* h, const bkf_problem* P, const 
     rc = run_smoother(h, g, &err);
     if (rc != BKF_OK) return fail(h, rc, err);
     h->launches += 1;
-    rc = smp::launch<R>(g.sm_a, g.sm_P, dz, dx, dstatus, (long long)(B * n), (int)n, (int)m, h->stream, &err);
+    rc = smp::launch<R>(g.sm_a, g.sm_P, dz, smp::Rng{P->rng_seed, P->rng_offset}, dx, dstatus, (long long)(B * n), (int)n, (int)m, h->stream, &err);
     if (rc != BKF_OK) return fail(h, rc, err);
     copy_back<R>(h, P, ll, g.ll, B * n, &rc);
     copy_back<R>(h, P, x, dx, B * n * m, &rc);
@@ -1135,7 +1278,7 @@ extern "C" int bkf_filter_smooth_sample(bkf_handle* h, const bkf_problem* P, con
     if (rc != BKF_OK) return rc;
     if (P->m > 32) return fail(h, BKF_ERR_UNSUPPORTED, "bkf_filter_smooth_sample: m > 32 is not supported");
     const void* prm[BKF_NPARAM] = {a0, P0, c, d, T, Z, R, H, Q};
-    if (!y || any_null(prm, BKF_NPARAM) || !z || !x) return fail(h, BKF_ERR_ARG, "null pointer");
+    if (!y || any_null(prm, BKF_NPARAM) || !x) return fail(h, BKF_ERR_ARG, "null pointer");  // (z == NULL: in-kernel variates)
     return P->dtype == BKF_F64 ? filter_smooth_sample_impl<double>(h, P, y, prm, z, ll, x, status)
                                : filter_smooth_sample_impl<float>(h, P, y, prm, z, ll, x, status);
 }

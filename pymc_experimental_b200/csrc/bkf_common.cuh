@@ -29,6 +29,7 @@ struct KArgs {
     R *filt_a, *pred_a, *obs_mu, *filt_P, *pred_P, *obs_cov, *ll;
     // forward -> backward trajectory of predictions: [B, n, m + m*m] (nullable)
     R* traj;
+    int rec_tiles;  // square-root family: the record holds the factors as 8 x 8 tiles (bkf_sqrt_bwd4.cuh)
     // logp + gradients (nullable)
     const R* ll_cot;
     R *logp, *g_a0, *g_P0, *g_c, *g_d, *g_T, *g_Z, *g_R, *g_H, *g_Q;

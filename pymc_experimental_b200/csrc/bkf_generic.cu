@@ -696,15 +696,10 @@ __device__ void jacobi_eig(R* A, R* V, int m, int lane) {
     }
 }
 
+// One series of the smoother sweep by one warp (s: the warp's arena).
 template <typename R>
-__global__ void smoother_kernel(KArgs<R> g, int wpc, size_t arena, R jitter0) {
-    extern __shared__ double smem_raw[];
-    R* s = reinterpret_cast<R*>(smem_raw);
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int b = blockIdx.x * wpc + warp;
-    if (b >= g.B) return;
+__device__ void smooth_series(const KArgs<R>& g, const int b, R* s, const R jitter0, const int lane) {
     const int m = g.m, r = g.r, n = g.n;
-    s += (size_t)warp * arena;
     const size_t mm_ = (size_t)m * m;
     auto take = [&](size_t k) { R* q = s; s += k; return q; };
     R *T = take(mm_), *RQR = take(mm_), *P = take(mm_), *Ps = take(mm_), *Ph = take(mm_), *X = take(mm_),
@@ -784,6 +779,27 @@ __global__ void smoother_kernel(KArgs<R> g, int wpc, size_t arena, R jitter0) {
     if (lane == 0 && g.status) g.status[b] |= st;
 }
 
+// list == nullptr: warp w of the grid takes series w.  Otherwise the series are list[0 .. *count) (the ones a fast
+// smoother flagged as ill-conditioned, bkf_api.cu::run_smoother): the grid strides over them and a launch with
+// *count == 0 returns at once -- no host round trip decides whether this kernel has work.
+template <typename R>
+__global__ void smoother_kernel(KArgs<R> g, int wpc, size_t arena, R jitter0, const int* list, const int* count) {
+    extern __shared__ double smem_raw[];
+    R* s = reinterpret_cast<R*>(smem_raw);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    s += (size_t)warp * arena;
+    if (!list) {
+        const int b = blockIdx.x * wpc + warp;
+        if (b < g.B) smooth_series<R>(g, b, s, jitter0, lane);
+        return;
+    }
+    const int cnt = *count;
+    for (int i = blockIdx.x * wpc + warp; i < cnt; i += gridDim.x * wpc) {
+        smooth_series<R>(g, list[i], s, jitter0, lane);
+        __syncwarp();
+    }
+}
+
 // ----------------------------------------------------------------------------------------------------
 // host launchers
 // ----------------------------------------------------------------------------------------------------
@@ -824,7 +840,7 @@ int launch_backward(const KArgs<R>& g, cudaStream_t stream, const char** err) {
 }
 
 template <typename R>
-int launch_smoother(const KArgs<R>& g, cudaStream_t stream, const char** err) {
+int launch_smoother(const KArgs<R>& g, const int* list, const int* count, cudaStream_t stream, const char** err) {
     size_t arena = smooth_arena_elems(g.m, g.r);
     size_t arena_bytes = arena * sizeof(R);
     if (arena_bytes > 227 * 1024) { *err = "problem too large for the generic smoother kernel"; return BKF_ERR_UNSUPPORTED; }
@@ -834,8 +850,9 @@ int launch_smoother(const KArgs<R>& g, cudaStream_t stream, const char** err) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) { *err = cudaGetErrorString(e); return BKF_ERR_CUDA; }
     int grid = (g.B + wpc - 1) / wpc;
+    if (list && grid > 148) grid = 148;  // flagged series only: a small strided grid (usually there are none)
     R jitter0 = sizeof(R) == 8 ? R(1e-8) : R(1e-6);  // JITTER_DEFAULT, utils/constants.py:20
-    kern<<<grid, 32 * wpc, smem, stream>>>(g, wpc, arena, jitter0);
+    kern<<<grid, 32 * wpc, smem, stream>>>(g, wpc, arena, jitter0, list, count);
     e = cudaGetLastError();
     if (e != cudaSuccess) { *err = cudaGetErrorString(e); return BKF_ERR_CUDA; }
     return BKF_OK;
@@ -845,8 +862,8 @@ template int launch_forward<double>(const KArgs<double>&, cudaStream_t, const ch
 template int launch_forward<float>(const KArgs<float>&, cudaStream_t, const char**);
 template int launch_backward<double>(const KArgs<double>&, cudaStream_t, const char**);
 template int launch_backward<float>(const KArgs<float>&, cudaStream_t, const char**);
-template int launch_smoother<double>(const KArgs<double>&, cudaStream_t, const char**);
-template int launch_smoother<float>(const KArgs<float>&, cudaStream_t, const char**);
+template int launch_smoother<double>(const KArgs<double>&, const int*, const int*, cudaStream_t, const char**);
+template int launch_smoother<float>(const KArgs<float>&, const int*, const int*, cudaStream_t, const char**);
 
 }  // namespace gen
 }  // namespace bkf

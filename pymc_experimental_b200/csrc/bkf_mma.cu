@@ -37,11 +37,11 @@ int launch_f64(const KArgs<double>& g, bool backward, cudaStream_t stream, const
 
 bool smoother_supported(int m) { return m >= 9 && m <= MP; }
 
-int launch_smoother_f64(const KArgs<double>& g, double jitter0, int* any_ill, cudaStream_t stream, const char** err) {
+int launch_smoother_f64(const KArgs<double>& g, double jitter0, int* ill_list, cudaStream_t stream, const char** err) {
     const int warps = 2;
     const int grid = (g.B + warps - 1) / warps;
     const size_t smem = (size_t)warps * SCRATCH * sizeof(double);
-    smoother_kernel<<<grid, 32 * warps, smem, stream>>>(g, jitter0, any_ill);
+    smoother_kernel<<<grid, 32 * warps, smem, stream>>>(g, jitter0, ill_list);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { *err = cudaGetErrorString(e); return BKF_ERR_CUDA; }
     return BKF_OK;

@@ -49,7 +49,7 @@ __device__ __forceinline__ void inv8(double (&a)[2], int g, int t, int nreal, do
     }
 }
 
-__global__ void __launch_bounds__(64) smoother_kernel(KArgs<double> G, double jitter0, int* any_ill) {
+__global__ void __launch_bounds__(64) smoother_kernel(KArgs<double> G, double jitter0, int* ill_list) {
     extern __shared__ __align__(16) double smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int g = lane >> 2, t = lane & 3;
@@ -199,7 +199,7 @@ __global__ void __launch_bounds__(64) smoother_kernel(KArgs<double> G, double ji
     }
     if (ill && lane == 0) {
         if (G.status) G.status[b] |= BKF_STATUS_SMOOTHER_ILL;
-        atomicOr(any_ill, 1);
+        ill_list[1 + atomicAdd(ill_list, 1)] = b;  // ill_list[0]: how many, then which
     }
 }
 

@@ -29,10 +29,41 @@ __device__ __forceinline__ double pivot_rsqrt(double x) {
 }
 __device__ __forceinline__ float pivot_rsqrt(float x) { return rsqrtf(x); }
 
+// Counter-based standard normals (Philox4x32-10 + Box-Muller): variate i of variate array `stream` of a call is a pure
+// function of (seed, offset, stream, i).  Counter = [lo, hi of offset + i / 2, stream, 0], key = [lo, hi of seed]; the four
+// 32-bit outputs give two uniforms in (0, 1) with 53 random bits each; variate i is element i & 1 of the Box-Muller pair.
+// Restated for the parity tests in oracle/philox.py.
+__device__ __forceinline__ double philox_normal(const Rng rng, const unsigned stream, const unsigned long long i) {
+    const unsigned long long ctr = rng.offset + (i >> 1);
+    unsigned c0 = (unsigned)ctr, c1 = (unsigned)(ctr >> 32), c2 = stream, c3 = 0u;
+    unsigned k0 = (unsigned)rng.seed, k1 = (unsigned)(rng.seed >> 32);
+#pragma unroll
+    for (int round = 0; round < 10; ++round) {
+        const unsigned hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+        const unsigned hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+        c0 = hi1 ^ c1 ^ k0;
+        c1 = lo1;
+        c2 = hi0 ^ c3 ^ k1;
+        c3 = lo0;
+        k0 += 0x9E3779B9u;
+        k1 += 0xBB67AE85u;
+    }
+    const double u1 = ((double)((((unsigned long long)c0 << 32) | c1) >> 11) + 0.5) * 0x1.0p-53;
+    const double u2 = ((double)((((unsigned long long)c2 << 32) | c3) >> 11) + 0.5) * 0x1.0p-53;
+    const double rad = sqrt(-2.0 * log(u1));
+    double sn, cs;
+    sincospi(2.0 * u2, &sn, &cs);
+    return rad * ((i & 1) ? sn : cs);
+}
+template <typename R>
+__device__ __forceinline__ R variate(const R* __restrict__ z, const Rng rng, const unsigned stream, const unsigned long long i) {
+    return z ? z[i] : (R)philox_normal(rng, stream, i);
+}
+
 template <typename R, int G>
 __global__ void __launch_bounds__(128) sample_kernel(const R* __restrict__ mu, const R* __restrict__ cov,
-                                                    const R* __restrict__ z, R* __restrict__ x, int* __restrict__ status,
-                                                    long long N, int n, int m) {
+                                                    const R* __restrict__ z, const Rng rng, R* __restrict__ x,
+                                                    int* __restrict__ status, long long N, int n, int m) {
     constexpr int GPW = 32 / G;  // matrices per warp
     const int lane = threadIdx.x & 31, i = lane % G, sub = lane / G;
     const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -69,7 +100,7 @@ __global__ void __launch_bounds__(128) sample_kernel(const R* __restrict__ mu, c
             l[j] = i >= j ? acc * inv : R(0);  // the diagonal: d / sqrt(d)
         }
     }
-    const R zi = (live && i < m) ? z[mm * m + i] : R(0);
+    const R zi = (live && i < m) ? variate<R>(z, rng, 0u, (unsigned long long)(mm * m + i)) : R(0);
     R acc = (live && i < m) ? mu[mm * m + i] : R(0);
 #pragma unroll
     for (int k = 0; k < G; ++k)
@@ -79,16 +110,16 @@ __global__ void __launch_bounds__(128) sample_kernel(const R* __restrict__ mu, c
 }
 
 template <typename R>
-int launch(const R* mu, const R* cov, const R* z, R* x, int* status, long long N, int n, int m, cudaStream_t stream,
-           const char** err) {
+int launch(const R* mu, const R* cov, const R* z, Rng rng, R* x, int* status, long long N, int n, int m,
+           cudaStream_t stream, const char** err) {
     if (m > 32) { *err = "bkf_mvn_sample: m > 32 is not supported"; return BKF_ERR_UNSUPPORTED; }
     const int G = m <= 8 ? 8 : (m <= 16 ? 16 : 32);
     const long long warps = (N + (32 / G) - 1) / (32 / G);
     const long long blocks = (warps + 3) / 4;
     if (blocks == 0) return BKF_OK;
-    if (G == 8) sample_kernel<R, 8><<<(unsigned)blocks, 128, 0, stream>>>(mu, cov, z, x, status, N, n, m);
-    else if (G == 16) sample_kernel<R, 16><<<(unsigned)blocks, 128, 0, stream>>>(mu, cov, z, x, status, N, n, m);
-    else sample_kernel<R, 32><<<(unsigned)blocks, 128, 0, stream>>>(mu, cov, z, x, status, N, n, m);
+    if (G == 8) sample_kernel<R, 8><<<(unsigned)blocks, 128, 0, stream>>>(mu, cov, z, rng, x, status, N, n, m);
+    else if (G == 16) sample_kernel<R, 16><<<(unsigned)blocks, 128, 0, stream>>>(mu, cov, z, rng, x, status, N, n, m);
+    else sample_kernel<R, 32><<<(unsigned)blocks, 128, 0, stream>>>(mu, cov, z, rng, x, status, N, n, m);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { *err = cudaGetErrorString(e); return BKF_ERR_CUDA; }
     return BKF_OK;
@@ -135,7 +166,8 @@ __host__ __device__ inline size_t sim_arena_elems(int m, int p, int r) {
 
 template <typename R>
 __global__ void simulate_kernel(KArgs<R> g, const R* __restrict__ z_x0, const R* __restrict__ z_y0,
-                                const R* __restrict__ z_state, const R* __restrict__ z_obs, R* __restrict__ xs,
+                                const R* __restrict__ z_state, const R* __restrict__ z_obs, const Rng rng,
+                                R* __restrict__ xs,
                                 R* __restrict__ ys, int wpc, size_t arena) {
     extern __shared__ double smem_raw[];
     R* s_ = reinterpret_cast<R*>(smem_raw);
@@ -186,8 +218,8 @@ __global__ void simulate_kernel(KArgs<R> g, const R* __restrict__ z_x0, const R*
     R* xb = xs + (size_t)b * (n + 1) * m;
     R* yb = ys + (size_t)b * (n + 1) * p;
     // x_0 = a0 + L0 z ;  y_0 = Z x_0 + LH z'
-    for (int i = lane; i < m; i += 32) an[i] = z_x0[(size_t)b * m + i];
-    for (int i = lane; i < p; i += 32) zo[i] = z_y0[(size_t)b * p + i];
+    for (int i = lane; i < m; i += 32) an[i] = variate<R>(z_x0, rng, 1u, (unsigned long long)b * m + i);
+    for (int i = lane; i < p; i += 32) zo[i] = variate<R>(z_y0, rng, 2u, (unsigned long long)b * p + i);
     __syncwarp();
     for (int i = lane; i < m; i += 32) {
         R acc = a0[i];
@@ -205,8 +237,8 @@ __global__ void simulate_kernel(KArgs<R> g, const R* __restrict__ z_x0, const R*
     for (int t = 0; t < n; ++t) {
         __syncwarp();
         if (g.tv_mask && t > 0) load_step(t, false);
-        for (int i = lane; i < r; i += 32) zs[i] = z_state[((size_t)b * n + t) * r + i];
-        for (int i = lane; i < p; i += 32) zo[i] = z_obs[((size_t)b * n + t) * p + i];
+        for (int i = lane; i < r; i += 32) zs[i] = variate<R>(z_state, rng, 3u, ((unsigned long long)b * n + t) * r + i);
+        for (int i = lane; i < p; i += 32) zo[i] = variate<R>(z_obs, rng, 4u, ((unsigned long long)b * n + t) * p + i);
         __syncwarp();
         for (int i = lane; i < m; i += 32) {
             R acc = cv[i];
@@ -228,8 +260,8 @@ __global__ void simulate_kernel(KArgs<R> g, const R* __restrict__ z_x0, const R*
 }
 
 template <typename R>
-int launch_simulate(const KArgs<R>& g, const R* z_x0, const R* z_y0, const R* z_state, const R* z_obs, R* xs, R* ys,
-                    cudaStream_t stream, const char** err) {
+int launch_simulate(const KArgs<R>& g, const R* z_x0, const R* z_y0, const R* z_state, const R* z_obs, Rng rng, R* xs,
+                    R* ys, cudaStream_t stream, const char** err) {
     const size_t arena = sim_arena_elems(g.m, g.p, g.r), arena_bytes = arena * sizeof(R);
     if (arena_bytes > 227 * 1024) { *err = "problem too large for the simulation kernel (m, p, r)"; return BKF_ERR_UNSUPPORTED; }
     int wpc = 4;
@@ -238,20 +270,20 @@ int launch_simulate(const KArgs<R>& g, const R* z_x0, const R* z_y0, const R* z_
     auto kern = simulate_kernel<R>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) { *err = cudaGetErrorString(e); return BKF_ERR_CUDA; }
-    kern<<<(g.B + wpc - 1) / wpc, 32 * wpc, smem, stream>>>(g, z_x0, z_y0, z_state, z_obs, xs, ys, wpc, arena);
+    kern<<<(g.B + wpc - 1) / wpc, 32 * wpc, smem, stream>>>(g, z_x0, z_y0, z_state, z_obs, rng, xs, ys, wpc, arena);
     e = cudaGetLastError();
     if (e != cudaSuccess) { *err = cudaGetErrorString(e); return BKF_ERR_CUDA; }
     return BKF_OK;
 }
 
 template int launch_simulate<double>(const KArgs<double>&, const double*, const double*, const double*, const double*,
-                                     double*, double*, cudaStream_t, const char**);
-template int launch_simulate<float>(const KArgs<float>&, const float*, const float*, const float*, const float*, float*,
-                                    float*, cudaStream_t, const char**);
+                                     Rng, double*, double*, cudaStream_t, const char**);
+template int launch_simulate<float>(const KArgs<float>&, const float*, const float*, const float*, const float*, Rng,
+                                    float*, float*, cudaStream_t, const char**);
 
-template int launch<double>(const double*, const double*, const double*, double*, int*, long long, int, int, cudaStream_t,
-                            const char**);
-template int launch<float>(const float*, const float*, const float*, float*, int*, long long, int, int, cudaStream_t,
+template int launch<double>(const double*, const double*, const double*, Rng, double*, int*, long long, int, int,
+                            cudaStream_t, const char**);
+template int launch<float>(const float*, const float*, const float*, Rng, float*, int*, long long, int, int, cudaStream_t,
                            const char**);
 
 }  // namespace smp

@@ -1,0 +1,14 @@
+// bkf_sqrt_bwd4_inst_c.cu -- instantiations of the four-warps-per-series SquareRootFilter adjoint (m/8, p/8, r/8).
+#define BKF_SQB_DEFINE_LAUNCH
+#include "bkf_sqrt_bwd4_launch.cuh"
+
+namespace bkf {
+namespace sqb {
+template int launch_t<1, 1, 1>(const KArgs<double>&, cudaStream_t, const char**);
+template void sizes_t<1, 1, 1>(size_t*, size_t*);
+template int launch_t<2, 1, 1>(const KArgs<double>&, cudaStream_t, const char**);
+template void sizes_t<2, 1, 1>(size_t*, size_t*);
+template int launch_t<3, 1, 1>(const KArgs<double>&, cudaStream_t, const char**);
+template void sizes_t<3, 1, 1>(size_t*, size_t*);
+}  // namespace sqb
+}  // namespace bkf

@@ -1,21 +1,11 @@
 // bkf_sqrt_warp.cu -- dispatch of the warp-per-series SquareRootFilter kernels (bkf_sqrt_warp.cuh).  The kernels are
 // instantiated per shape (m/8, p/8, r/8) in bkf_sqrt_warp_inst_*.cu so that the shapes compile in parallel.
-#include <cstdlib>
-
 #include "bkf_launch.h"
 #include "bkf_sqrt_warp_launch.cuh"
 
 namespace bkf {
 namespace sqw {
 
-// BKF_SQRT_WARP (debugging aid): bit 0 = forward sweep, bit 1 = adjoint sweep on the warp-per-series kernels (default 3)
-static int enabled_mask() {
-    static const int mask = [] {
-        const char* e = std::getenv("BKF_SQRT_WARP");
-        return e ? std::atoi(e) : 3;
-    }();
-    return mask;
-}
 
 #define BKF_SQW_SHAPES(X) X(1, 1, 1) X(2, 1, 1) X(3, 1, 1) X(4, 1, 1) X(2, 2, 1) X(2, 2, 2) X(4, 2, 2)
 
@@ -26,14 +16,10 @@ static bool shape_ok(int m, int p, int r) {
     return false;
 }
 
-bool supported(const KArgs<double>& g, bool backward) {
-    if (g.kind != BKF_CHOLESKY || g.tv_mask || !shape_ok(g.m, g.p, g.r)) return false;
-    if (!((enabled_mask() >> (backward ? 1 : 0)) & 1)) return false;
-    return backward ? g.traj != nullptr : true;
-}
+bool supported(const KArgs<double>& g) { return g.kind == BKF_CHOLESKY && !g.tv_mask && shape_ok(g.m, g.p, g.r); }
 
-int launch_f64(const KArgs<double>& g, bool backward, cudaStream_t stream, const char** err) {
-#define X(MT, PT, RT) if (g.m == 8 * MT && g.p == 8 * PT && g.r == 8 * RT) return launch_t<MT, PT, RT>(g, backward, stream, err);
+int launch_f64(const KArgs<double>& g, cudaStream_t stream, const char** err) {
+#define X(MT, PT, RT) if (g.m == 8 * MT && g.p == 8 * PT && g.r == 8 * RT) return launch_t<MT, PT, RT>(g, stream, err);
     BKF_SQW_SHAPES(X)
 #undef X
     *err = "shape not instantiated for the warp-per-series square-root kernels";

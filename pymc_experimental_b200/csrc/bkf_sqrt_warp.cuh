@@ -16,8 +16,9 @@
 //     one is written where the next one reads it (Pc never moves).
 //
 // Shapes: float64, m, p, r multiples of 8 with r <= p (instantiated for the shapes in bkf_sqrt_warp.cu).  Everything else
-// takes the CTA-per-series kernels.  The forward record kept for the adjoint is the one of bkf_sqrt.cu
-// ([a | Pc | triu(Rf) | triu(Rp)]), so either family's adjoint can read either family's forward sweep.
+// takes the CTA-per-series kernels.  This file holds the forward sweep and the device helpers shared with its adjoint,
+// the four-warps-per-series kernel of bkf_sqrt_bwd4.cuh, which reads the record the sweep leaves: per (series, step)
+// [a | a_f | v | s | inner | tiles of Rf^T | tiles of Rp^T] with the tiles exactly as they lie in the arena.
 #pragma once
 #include "bkf_common.cuh"
 
@@ -300,12 +301,6 @@ __device__ __noinline__ void qr_tiles(double* __restrict__ S, double* __restrict
     }
 }
 
-// Doubles per (series, step) record: identical to sq::traj_record_elems (bkf_sqrt.cu)
-__host__ __device__ inline size_t traj_record_elems(int m, int p) {
-    const size_t N1 = (size_t)p + m;
-    return (size_t)m + (size_t)m * m + N1 * (N1 + 1) / 2 + (size_t)m * (m + 1) / 2;
-}
-
 template <int MT, int PT, int RT>
 struct Dims {
     static constexpr int mt = MT, pt = PT, rt = RT;
@@ -391,26 +386,6 @@ __device__ inline int setup_consts(const KArgs<double>& G, int b, double* HCt, d
     return st;
 }
 
-// Packed upper triangle (row i holds n - i entries) <- R, where the tiles hold R^T: tile (I, J), I >= J, element
-// [g][2t+e] = R[8J + 2t + e][8I + g].
-template <int NT, class TileOf>
-__device__ __forceinline__ void store_packed_upper(double* __restrict__ dst, const double* __restrict__ S, int lane,
-                                                   TileOf tile_of) {
-    const int g = lane >> 2, t = lane & 3;
-    constexpr int n = 8 * NT;
-#pragma unroll
-    for (int I = 0; I < NT; ++I)
-#pragma unroll
-        for (int J = 0; J <= I; ++J) {
-            const double2 v = ldt(S, tile_of(I, J), lane);
-            const int j = 8 * I + g;
-            int i = 8 * J + 2 * t;
-            if (j >= i) dst[i * n - (i * (i - 1)) / 2 + (j - i)] = v.x;
-            ++i;
-            if (j >= i) dst[i * n - (i * (i - 1)) / 2 + (j - i)] = v.y;
-        }
-}
-
 // dst (row-major n x n, n = 8 NT) = L L^T for a factor given as tiles L(I, K)  (_postprocess_scan_results, :733-740)
 template <int NT, class TileF>
 __device__ __forceinline__ void store_square(double* __restrict__ dst, TileF L, int lane) {
@@ -462,8 +437,11 @@ __global__ void __launch_bounds__(32) forward_kernel(KArgs<double> G) {
         __syncwarp();
     }
     const double* yb = G.y_shared ? G.y : G.y + (size_t)b * n * p;
-    const size_t tstride = traj_record_elems(m, p);
-    const size_t off_rf = (size_t)m + (size_t)m * m, off_rp = off_rf + (size_t)N1 * (N1 + 1) / 2;
+    // record for the adjoint (bkf_sqrt_bwd4.cuh): [a | a_f | v | s = Fc^{-1} v | inner = Fc^{-1} s | tiles of Rf^T | tiles of
+    // Rp^T], the tiles exactly as they lie in the arena (upper tile (I, K) at tri(I, K), 512-byte coalesced stores); Pc is
+    // not stored (it is the previous step's Rp^T, or P0)
+    constexpr int NTRI1 = D::NT1 * (D::NT1 + 1) / 2, NTRIP = MT * (MT + 1) / 2;
+    constexpr size_t off_rf = (size_t)(2 * m + 3 * p), off_rp = off_rf + (size_t)NTRI1 * 64, tstride = off_rp + (size_t)NTRIP * 64;
     double logp = 0.0;
     for (int ts = 0; ts < n; ++ts) {
         const size_t bt = (size_t)b * n + ts;
@@ -481,10 +459,6 @@ __global__ void __launch_bounds__(32) forward_kernel(KArgs<double> G) {
         __syncwarp();
         if (rec) {
             for (int i = lane; i < m; i += 32) rec[i] = va[i];
-#pragma unroll
-            for (int I = 0; I < MT; ++I)
-#pragma unroll
-                for (int J = 0; J < MT; ++J) stg_tile(rec + m, m, I, J, lane, ldt(SA, D::pc_tile(I, J), lane));
         }
         if (G.pred_a)
             for (int i = lane; i < m; i += 32) G.pred_a[bt * m + i] = va[i];
@@ -546,8 +520,14 @@ __global__ void __launch_bounds__(32) forward_kernel(KArgs<double> G) {
                 for (int J = 0; J < PT; ++J) stt(SA, (PT + I) * WT + J, lane, zero2());
             __syncwarp();
             qr_tiles<D::NT1, MT, PT, WT>(SA, smem + D::V_tq, D::NT1, D::NT1, false, lane);
-            if (rec)
-                store_packed_upper<D::NT1>(rec + off_rf, SA, lane, [](int I, int J) { return I * WT + J; });
+            if (rec) {
+                int idx = 0;
+#pragma unroll
+                for (int I = 0; I < D::NT1; ++I)
+#pragma unroll
+                    for (int K = I; K < D::NT1; ++K, ++idx)
+                        reinterpret_cast<double2*>(rec + off_rf)[idx * 32 + lane] = ldt(SA, K * WT + I, lane);
+            }
             if (G.obs_cov)  // F = Fc Fc^T, Fc = B[:p,:p]
                 store_square<PT>(G.obs_cov + bt * p * p, [&](int I, int K) { return ldt(SA, I * WT + K, lane); }, lane);
             // ---- s = Fc^{-1} v, inner = Fc^{-1} s  (Fc = B[:p,:p], lower), lane q owns x[q] ----
@@ -595,6 +575,14 @@ __global__ void __launch_bounds__(32) forward_kernel(KArgs<double> G) {
             for (int I = 0; I < MT; ++I) SA[D::pc_tile(I, I) * 64 + lane * 2 + (g & 1)] += G.jitter;
         }
         __syncwarp();
+        if (rec) {
+            for (int i = lane; i < m; i += 32) rec[m + i] = vaf[i];
+            if (lane < p) {
+                rec[2 * m + lane] = vv[lane];
+                rec[2 * m + p + lane] = vsv[lane];
+                rec[2 * m + 2 * p + lane] = vin[lane];
+            }
+        }
         if (G.filt_a)
             for (int i = lane; i < m; i += 32) G.filt_a[bt * m + i] = vaf[i];
         if (G.filt_P)
@@ -638,7 +626,14 @@ __global__ void __launch_bounds__(32) forward_kernel(KArgs<double> G) {
             __syncwarp();
         }
         qr_tiles<D::NT1, MT, PT, WT>(SA, smem + D::V_tq, MT, MT + RT, true, lane);
-        if (rec) store_packed_upper<MT>(rec + off_rp, SA, lane, [](int I, int J) { return D::pc_tile(I, J); });
+        if (rec) {
+            int idx = 0;
+#pragma unroll
+            for (int I = 0; I < MT; ++I)
+#pragma unroll
+                for (int K = I; K < MT; ++K, ++idx)
+                    reinterpret_cast<double2*>(rec + off_rp)[idx * 32 + lane] = ldt(SA, D::pc_tile(K, I), lane);
+        }
     }
     if (lane == 0) {
         if (!isfinite(logp)) st |= BKF_STATUS_NONFINITE;
@@ -648,126 +643,10 @@ __global__ void __launch_bounds__(32) forward_kernel(KArgs<double> G) {
 }
 
 // ===============================================================================================================
-// Adjoint sweep.
-//
-// For A = Q R and an upper-triangular cotangent Rbar:  Abar = A Psi,  Psi = R^{-1} copyltu(R Rbar^T) R^{-T}  (symmetric).
-// On tiles:   S0 = R Rbar^T = mma_nt(R, Rbar)  (lower tiles only), S = copyltu(S0),
-//             G = S R^{-T}   (right-solve by tile columns, diagonal tiles inverted once),
-//             Psi = G^T R^{-T}  (same right-solve after an in-place transposition).
-// The R factors come from the forward record (no QR here).  Cotangents of the factor are carried TRANSPOSED
-// (PBT = Pbar^T) because that is what both the pull-back (Rbar_p = triu(Pbar^T)) and the products below produce.
+// Helpers of the adjoint sweep (bkf_sqrt_bwd4.cuh).
 
 template <int NT>
 __host__ __device__ constexpr int tri(int I, int K) { return I * NT - (I * (I - 1)) / 2 + (K - I); }  // I <= K
-
-// tiles of the upper triangle of an n x n factor (n = 8 NT) from its packed rows (row i holds n - i entries)
-template <int NT>
-__device__ __forceinline__ void load_packed_upper(double* __restrict__ RF, const double* __restrict__ src, int lane) {
-    const int g = lane >> 2, t = lane & 3;
-    constexpr int n = 8 * NT;
-#pragma unroll
-    for (int I = 0; I < NT; ++I)
-#pragma unroll
-        for (int K = I; K < NT; ++K) {
-            const int i = 8 * I + g, j = 8 * K + 2 * t;
-            const double* q = src + (i * n - (i * (i - 1)) / 2 - i + j);
-            double2 v;
-            v.x = j >= i ? q[0] : 0.0;
-            v.y = j + 1 >= i ? q[1] : 0.0;
-            stt(RF, tri<NT>(I, K), lane, v);
-        }
-}
-
-// Psi (NT x NT tiles, row stride NT, in W) from the factor tiles RF (upper, tri<NT> order) and a provider of the
-// cotangent tiles rbar(J, K), K >= J, with exact zeros below the diagonal.  RINV: NT tiles of scratch.
-template <int NT, class RbF>
-__device__ __forceinline__ void psi_tiles(double* __restrict__ W, const double* __restrict__ RF, double* __restrict__ RINV,
-                                          RbF rbar, const int lane) {
-    const int g = lane >> 2, t = lane & 3;
-    // S = copyltu(R Rbar^T)
-#pragma unroll
-    for (int I = 0; I < NT; ++I) {
-        Acc2 acc[NT];
-#pragma unroll
-        for (int J = 0; J < NT; ++J) acc[J] = acc2_zero();
-#pragma unroll
-        for (int K = I; K < NT; ++K) {
-            const double2 rk = ldt(RF, tri<NT>(I, K), lane);
-#pragma unroll
-            for (int J = 0; J <= I; ++J) mma_nt(acc[J], rk, rbar(J, K));
-        }
-#pragma unroll
-        for (int J = 0; J < I; ++J) {
-            const double2 v = fin(acc[J]);
-            stt(W, I * NT + J, lane, v);
-            stt(W, J * NT + I, lane, ttrans(v, lane));
-        }
-        const double2 dv = fin(acc[I]);
-        const double2 dt = ttrans(dv, lane);
-        stt(W, I * NT + I, lane, make_double2(g >= 2 * t ? dv.x : dt.x, g >= 2 * t + 1 ? dv.y : dt.y));
-    }
-    __syncwarp();
-    // inverses of the diagonal tiles: lane 8q + c solves column c of tile q (four tiles per round)
-#pragma unroll
-    for (int base = 0; base < NT; base += 4) {
-        const int I = base + (lane >> 3), c = lane & 7;
-        if (I < NT) {
-            const double* Dg = RF + (I * NT - (I * (I - 1)) / 2) * 64;
-            double x[8], rd[8];
-#pragma unroll
-            for (int i = 0; i < 8; ++i) rd[i] = 1.0 / Dg[i * 9];
-#pragma unroll
-            for (int i = 7; i >= 0; --i) {
-                double tv = i == c ? 1.0 : 0.0;
-#pragma unroll
-                for (int q = 7; q > i; --q) tv = fma(-Dg[i * 8 + q], x[q], tv);
-                x[i] = tv * rd[i];
-            }
-#pragma unroll
-            for (int i = 0; i < 8; ++i) RINV[I * 64 + i * 8 + c] = x[i];
-        }
-    }
-    __syncwarp();
-#pragma unroll
-    for (int pass = 0; pass < 2; ++pass) {
-        // X <- X R^{-T}, tile column by tile column (all tile rows at once)
-#pragma unroll
-        for (int I = NT - 1; I >= 0; --I) {
-            Acc2 acc[NT];
-#pragma unroll
-            for (int J = 0; J < NT; ++J) acc[J] = acc2_from(ldt(W, J * NT + I, lane));
-#pragma unroll
-            for (int K = I + 1; K < NT; ++K) {
-                const double2 rk = neg(ldt(RF, tri<NT>(I, K), lane));
-#pragma unroll
-                for (int J = 0; J < NT; ++J) mma_nt(acc[J], ldt(W, J * NT + K, lane), rk);
-            }
-            const double2 ri = ldt(RINV, I, lane);
-            Acc2 o[NT];
-#pragma unroll
-            for (int J = 0; J < NT; ++J) {
-                o[J] = acc2_zero();
-                mma_nt(o[J], fin(acc[J]), ri);
-            }
-#pragma unroll
-            for (int J = 0; J < NT; ++J) stt(W, J * NT + I, lane, fin(o[J]));
-            __syncwarp();
-        }
-        if (pass == 0) {
-#pragma unroll
-            for (int I = 0; I < NT; ++I) {
-#pragma unroll
-                for (int J = 0; J < I; ++J) {
-                    const double2 lo = ldt(W, I * NT + J, lane), up = ldt(W, J * NT + I, lane);
-                    stt(W, I * NT + J, lane, ttrans(up, lane));
-                    stt(W, J * NT + I, lane, ttrans(lo, lane));
-                }
-                stt(W, I * NT + I, lane, ttrans(ldt(W, I * NT + I, lane), lane));
-            }
-            __syncwarp();
-        }
-    }
-}
 
 // C[M,N] (row-major, ldc) (op)= A B with strided operands, one warp (epilogue only)
 template <bool ADD>
@@ -816,569 +695,6 @@ __device__ inline void chol_pullback_warp(double* out, const double* L, const do
         out[idx] = (i > j) ? 2.0 * sv : (i == j ? sv : 0.0);
     }
     __syncwarp();
-}
-
-template <int MT, int PT, int RT>
-struct BDims {
-    using D = Dims<MT, PT, RT>;
-    static constexpr int m = D::m, p = D::p, NT1 = D::NT1;
-    static constexpr int NTRI = NT1 * (NT1 + 1) / 2;
-    static constexpr int cmax(int a, int b) { return a > b ? a : b; }
-    // tile counts: the arrays double as scratch for the products of the predict / update adjoints (see the kernel)
-    static constexpr int WTILES = cmax(NT1 * NT1, 2 * MT * MT);                       // Psi | Psi_p + TP^T / U1
-    static constexpr int RFTILES = cmax(NTRI, MT * PT);                               // factor | Abar21
-    static constexpr int RBTILES = cmax(cmax(NTRI, MT * MT), NT1 + MT * PT);          // Rbar | RINV + A21 | U1^T
-    static constexpr int W = 0;                           // Psi work array
-    static constexpr int RF = W + WTILES * 64;            // factor tiles (upper)
-    static constexpr int RB = RF + RFTILES * 64;          // cotangent tiles (upper); also RINV / scratch
-    static constexpr int PBT = RB + RBTILES * 64;         // carried Pbar^T, MT x MT tiles
-    static constexpr int HC = PBT + MT * MT * 64;         // Hc tiles
-    static constexpr int HBT = HC + PT * PT * 64;         // sum of Abar11 (= Hcbar^T)
-    static constexpr int VA = HBT + PT * PT * 64;
-    static constexpr int V_a = VA, V_af = V_a + m, V_ab = V_af + m, V_afb = V_ab + m, V_gc = V_afb + m, V_v = V_gc + m,
-                         V_s = V_v + p, V_in = V_s + p, V_w = V_in + p, V_ym = V_w + p, V_vb = V_ym + p, V_sb = V_vb + p,
-                         V_t1 = V_sb + p, V_t2 = V_t1 + p, V_gd = V_t2 + p, V_d = V_gd + p;
-    static constexpr int ELEMS = V_d + p;
-    // epilogue scratch (row-major) laid over W, RF, RB
-    static_assert((WTILES + RFTILES + RBTILES) * 64 >= cmax(5 * p * p, 6 * D::r * D::r + 2 * m * D::r), "epilogue scratch");
-};
-
-template <int MT, int PT, int RT>
-__global__ void __launch_bounds__(32) backward_kernel(KArgs<double> G) {
-    using D = Dims<MT, PT, RT>;
-    using BD = BDims<MT, PT, RT>;
-    constexpr int m = D::m, p = D::p, r = D::r, N1 = D::N1, NT1 = D::NT1;
-    extern __shared__ double smem[];
-    const int lane = threadIdx.x, g = lane >> 2, t = lane & 3;
-    const int b = blockIdx.x;
-    const int n = G.n;
-    double *W = smem + BD::W, *RF = smem + BD::RF, *RB = smem + BD::RB, *PBT = smem + BD::PBT, *HC = smem + BD::HC,
-           *HBT = smem + BD::HBT;
-    double *va = smem + BD::V_a, *vaf = smem + BD::V_af, *vab = smem + BD::V_ab, *vafb = smem + BD::V_afb,
-           *vgc = smem + BD::V_gc, *vv = smem + BD::V_v, *vs = smem + BD::V_s, *vin = smem + BD::V_in, *vw = smem + BD::V_w,
-           *vym = smem + BD::V_ym, *vvb = smem + BD::V_vb, *vsb = smem + BD::V_sb, *vt1 = smem + BD::V_t1,
-           *vt2 = smem + BD::V_t2, *vgd = smem + BD::V_gd, *vd = smem + BD::V_d;
-
-    bool Hzero;
-    setup_consts<D>(G, b, HC, nullptr, nullptr, W, &Hzero, lane);
-    const double* Tg = param_ptr(G.T, G.shared_mask, BKF_PARAM_T, b, (size_t)m * m);
-    const double* Zg = param_ptr(G.Z, G.shared_mask, BKF_PARAM_Z, b, (size_t)p * m);
-    {
-        const double* dg = param_ptr(G.d, G.shared_mask, BKF_PARAM_D, b, (size_t)p);
-        for (int i = lane; i < p; i += 32) { vd[i] = dg[i]; vgd[i] = 0.0; }
-        for (int i = lane; i < m; i += 32) { vab[i] = 0.0; vgc[i] = 0.0; }
-        for (int i = lane; i < MT * MT * 32; i += 32) reinterpret_cast<double2*>(PBT)[i] = zero2();
-        for (int i = lane; i < PT * PT * 32; i += 32) reinterpret_cast<double2*>(HBT)[i] = zero2();
-    }
-    const double* yb = G.y_shared ? G.y : G.y + (size_t)b * n * p;
-    const size_t tstride = traj_record_elems(m, p);
-    const size_t off_rf = (size_t)m + (size_t)m * m, off_rp = off_rf + (size_t)N1 * (N1 + 1) / 2;
-    // accumulators that are only added to live in global memory (L2), updated with fire-and-forget reductions (RED.ADD:
-    // no load on the step's critical path): the gradient buffers themselves when requested, else the scratch record
-    // behind the trajectory
-    double* scr = G.traj + (size_t)G.B * n * tstride + (size_t)b * tstride;
-    double* gT = G.g_T ? G.g_T + (size_t)b * m * m : scr;
-    double* gZ = G.g_Z ? G.g_Z + (size_t)b * p * m : scr + m * m;
-    double* PS = scr + m * m + p * m;
-    const bool want_ps = G.g_R || G.g_Q;
-    for (int i = lane; i < m * m; i += 32) { gT[i] = 0.0; PS[i] = 0.0; }
-    for (int i = lane; i < p * m; i += 32) gZ[i] = 0.0;
-    __syncwarp();
-
-    for (int ts = n - 1; ts >= 0; --ts) {
-        const size_t bt = (size_t)b * n + ts;
-        const double* rec = G.traj + bt * tstride;
-        const double* Pcg = rec + m;
-        const double gcot = G.ll_cot ? G.ll_cot[bt] : 1.0;
-        const bool dense_pc = ts == 0;  // P0 is whatever the caller passed; later factors are lower triangular
-        if (ts > 0) {  // the next record this warp will read: pull it towards L2 while this step computes
-            const char* nxt = reinterpret_cast<const char*>(rec - tstride);
-            for (int off = lane * 128; off < (int)(tstride * sizeof(double)); off += 32 * 128)
-                asm volatile("prefetch.global.L2 [%0];" ::"l"(nxt + off));
-        }
-        // ---- mask, innovation (as the forward sweep) ----
-        bool miss = true;
-        if (lane < p) {
-            const double yv = yb[(size_t)ts * p + lane];
-            miss = is_missing(yv, G.fill, true);
-            vw[lane] = miss ? 0.0 : 1.0;
-            vym[lane] = miss ? 0.0 : yv;
-        }
-        const int nobs = __popc(__ballot_sync(FULL, !miss));
-        const bool flag = nobs == 0, partial = !flag && nobs != p;
-        for (int i = lane; i < m; i += 32) va[i] = rec[i];
-        load_packed_upper<MT>(RF, rec + off_rp, lane);
-        __syncwarp();
-#pragma unroll
-        for (int I = 0; I < PT; ++I) {
-            const double wI = vw[8 * I + g];
-            double acc = 0.0;
-#pragma unroll
-            for (int J = 0; J < MT; ++J) {
-                const double2 z = ldg_tile(Zg, m, I, J, lane);
-                acc = fma(z.x * wI, va[8 * J + 2 * t], acc);
-                acc = fma(z.y * wI, va[8 * J + 2 * t + 1], acc);
-            }
-            acc = red_t(acc) + vd[8 * I + g];
-            if (t == 0) vv[8 * I + g] = vym[8 * I + g] - acc;
-        }
-        // ================= predict adjoint =================
-        psi_tiles<MT>(W, RF, RB, [&](int J, int K) {
-            double2 v = ldt(PBT, J * MT + K, lane);
-            if (J == K) {
-                if (2 * t < g) v.x = 0.0;
-                if (2 * t + 1 < g) v.y = 0.0;
-            }
-            return v;
-        }, lane);
-        if (want_ps) {
-#pragma unroll
-            for (int I = 0; I < MT; ++I)
-#pragma unroll
-                for (int J = 0; J < MT; ++J) {
-                    red_tile(PS, m, I, J, lane, ldt(W, I * MT + J, lane));
-                }
-        }
-        // ---- forward quantities of this step from the record: s, inner, a_f, Pcf ----
-        if (!flag) {
-            load_packed_upper<NT1>(RF, rec + off_rf, lane);
-            __syncwarp();
-            const int q = lane < p ? lane : p - 1;
-            double frow[p];
-#pragma unroll
-            for (int i = 0; i < p; ++i)  // Fc[q][i] = Rf[i][q], i <= q
-                frow[i] = (i >> 3) <= (q >> 3) ? RF[((i >> 3) * NT1 - ((i >> 3) * ((i >> 3) - 1)) / 2 + ((q >> 3) - (i >> 3))) * 64 +
-                                                    (i & 7) * 8 + (q & 7)]
-                                               : 0.0;
-            const double rdiag = 1.0 / RF[((q >> 3) * NT1 - ((q >> 3) * ((q >> 3) - 1)) / 2) * 64 + (q & 7) * 9];
-            double x = lane < p ? vv[lane] : 0.0;
-#pragma unroll
-            for (int rep = 0; rep < 2; ++rep) {
-#pragma unroll
-                for (int i = 0; i < p; ++i) {
-                    const double xi = __shfl_sync(FULL, x, i) * __shfl_sync(FULL, rdiag, i);
-                    if (lane == i) x = xi;
-                    else if (lane > i) x = fma(-frow[i], xi, x);
-                }
-                if (lane < p) (rep == 0 ? vs : vin)[lane] = x;
-            }
-            __syncwarp();
-            // a_f = a + KF s,  KF[i][o] = Rf[o][p + i]
-#pragma unroll
-            for (int J = 0; J < MT; ++J) {
-                double c0 = 0.0, c1 = 0.0;
-#pragma unroll
-                for (int I = 0; I < PT; ++I) {
-                    const double2 rk = ldt(RF, tri<NT1>(I, PT + J), lane);
-                    const double sI = vs[8 * I + g];
-                    c0 = fma(rk.x, sI, c0);
-                    c1 = fma(rk.y, sI, c1);
-                }
-                c0 = red_g(c0);
-                c1 = red_g(c1);
-                if (g == 0) {
-                    vaf[8 * J + 2 * t] = va[8 * J + 2 * t] + c0;
-                    vaf[8 * J + 2 * t + 1] = va[8 * J + 2 * t + 1] + c1;
-                }
-            }
-        } else {
-            for (int i = lane; i < m; i += 32) vaf[i] = va[i];
-        }
-        __syncwarp();
-        // (Pcf + jitter I)^T tile (I, K): upper triangular from the record's factor, or Pc^T when the step was skipped
-        auto pft = [&](int I, int K) {
-            double2 v;
-            if (flag) v = ldg_tile_t(Pcg, m, I, K, lane);
-            else v = K >= I ? ldt(RF, tri<NT1>(PT + I, PT + (K >= I ? K : I)), lane) : zero2();
-            if (I == K) {
-                if (2 * t == g) v.x += G.jitter;
-                if (2 * t + 1 == g) v.y += G.jitter;
-            }
-            return v;
-        };
-        const bool dense_pf = flag && dense_pc;  // (a skipped step keeps Pc, which is dense only at t = 0)
-        constexpr int TPT = MT * MT;  // tile offset of the second scratch block inside W
-        // TP^T = (T Pcf)^T = Pcf^T T^T :  [I][J] = sum_K pft(I,K) (T[J][K])^T   (each T tile is fetched once)
-        {
-            double2 acc[MT][MT];
-#pragma unroll
-            for (int I = 0; I < MT; ++I)
-#pragma unroll
-                for (int J = 0; J < MT; ++J) acc[I][J] = zero2();
-#pragma unroll
-            for (int K = 0; K < MT; ++K) {
-                double2 tk[MT];
-#pragma unroll
-                for (int J = 0; J < MT; ++J) tk[J] = ldg_tile(Tg, m, J, K, lane);
-#pragma unroll
-                for (int I = 0; I < MT; ++I)
-                    if (dense_pf || K >= I) {
-                        const double2 pf = pft(I, K);
-#pragma unroll
-                        for (int J = 0; J < MT; ++J) mma_nt(acc[I][J], pf, tk[J]);
-                    }
-            }
-#pragma unroll
-            for (int I = 0; I < MT; ++I)
-#pragma unroll
-                for (int J = 0; J < MT; ++J) stt(W, TPT + I * MT + J, lane, acc[I][J]);
-        }
-        __syncwarp();
-        // U1^T = TP^T Psi_p  -> RB[0 .. MT*MT)
-#pragma unroll
-        for (int I = 0; I < MT; ++I) {
-            Acc2 acc[MT];
-#pragma unroll
-            for (int J = 0; J < MT; ++J) acc[J] = acc2_zero();
-#pragma unroll
-            for (int K = 0; K < MT; ++K) {
-                const double2 tpk = ldt(W, TPT + I * MT + K, lane);
-#pragma unroll
-                for (int J = 0; J < MT; ++J) mma_nt(acc[J], tpk, ldt(W, J * MT + K, lane));
-            }
-#pragma unroll
-            for (int J = 0; J < MT; ++J) stt(RB, I * MT + J, lane, fin(acc[J]));
-        }
-        __syncwarp();
-        // U1 -> W[TPT ..)
-#pragma unroll
-        for (int I = 0; I < MT; ++I)
-#pragma unroll
-            for (int J = 0; J < MT; ++J) stt(W, TPT + I * MT + J, lane, ttrans(ldt(RB, J * MT + I, lane), lane));
-        __syncwarp();
-        // gT += U1 Pcf^T + abar af^T ;  Pcf[J][K] = (pft(K, J))^T
-        if (G.g_T) {
-#pragma unroll
-            for (int J = 0; J < MT; ++J) {
-                Acc2 acc[MT];
-#pragma unroll
-                for (int I = 0; I < MT; ++I) {
-                    const double ab = vab[8 * I + g];
-                    acc[I] = acc2_from(make_double2(ab * vaf[8 * J + 2 * t], ab * vaf[8 * J + 2 * t + 1]));
-                }
-#pragma unroll
-                for (int K = 0; K < MT; ++K)
-                    if (dense_pf || K <= J) {
-                        const double2 pk = ttrans(pft(K, J), lane);
-#pragma unroll
-                        for (int I = 0; I < MT; ++I) mma_nt(acc[I], ldt(W, TPT + I * MT + K, lane), pk);
-                    }
-#pragma unroll
-                for (int I = 0; I < MT; ++I) red_tile(gT, m, I, J, lane, fin(acc[I]));
-            }
-        }
-        // Pcfbar^T = U1^T T :  [I][J] = sum_K U1T[I][K] ((T^T)[J][K])^T  -> W[0 .. MT*MT)   (Psi_p is dead)
-        // and, from the same tiles of T^T,  afbar = T^T abar
-        {
-            double afp[MT];
-#pragma unroll
-            for (int J = 0; J < MT; ++J) afp[J] = 0.0;
-            double2 acc[MT][MT];
-#pragma unroll
-            for (int I = 0; I < MT; ++I)
-#pragma unroll
-                for (int J = 0; J < MT; ++J) acc[I][J] = zero2();
-#pragma unroll
-            for (int K = 0; K < MT; ++K) {
-                double2 tk[MT];
-                const double ab0 = vab[8 * K + 2 * t], ab1 = vab[8 * K + 2 * t + 1];
-#pragma unroll
-                for (int J = 0; J < MT; ++J) {
-                    tk[J] = ldg_tile_t(Tg, m, J, K, lane);  // [g][2t+e] = T[8K + 2t + e][8J + g]
-                    afp[J] = fma(tk[J].x, ab0, fma(tk[J].y, ab1, afp[J]));
-                }
-#pragma unroll
-                for (int I = 0; I < MT; ++I) {
-                    const double2 uk = ldt(RB, I * MT + K, lane);
-#pragma unroll
-                    for (int J = 0; J < MT; ++J) mma_nt(acc[I][J], uk, tk[J]);
-                }
-            }
-#pragma unroll
-            for (int I = 0; I < MT; ++I)
-#pragma unroll
-                for (int J = 0; J < MT; ++J) stt(W, I * MT + J, lane, acc[I][J]);
-#pragma unroll
-            for (int J = 0; J < MT; ++J) {
-                const double v = red_t(afp[J]);
-                if (t == 0) vafb[8 * J + g] = v;
-            }
-        }
-        // gc += abar
-        for (int i = lane; i < m; i += 32) vgc[i] += vab[i];
-        __syncwarp();
-        if (flag) {  // degenerate branch (:700-705): (a_f, Pcf, ll) = (a, Pc, 0)
-            for (int i = lane; i < m; i += 32) vab[i] = vafb[i];
-#pragma unroll
-            for (int i = 0; i < MT * MT; ++i) stt(PBT, i, lane, ldt(W, i, lane));
-            __syncwarp();
-            continue;
-        }
-        // ================= update adjoint =================
-        {
-            const double lossbar = -0.5 * gcot, logdetbar = -0.5 * gcot * (double)p;
-            // sbar = KF^T afbar
-#pragma unroll
-            for (int I = 0; I < PT; ++I) {
-                double acc = 0.0;
-#pragma unroll
-                for (int J = 0; J < MT; ++J) {
-                    const double2 rk = ldt(RF, tri<NT1>(I, PT + J), lane);
-                    acc = fma(rk.x, vafb[8 * J + 2 * t], acc);
-                    acc = fma(rk.y, vafb[8 * J + 2 * t + 1], acc);
-                }
-                acc = red_t(acc);
-                if (t == 0) vsb[8 * I + g] = acc;
-            }
-            __syncwarp();
-            // back substitution with U = Rf[:p,:p] = Fc^T : lane q owns x[q] and row q of U
-            const int q = lane < p ? lane : p - 1;
-            double urow[p];
-#pragma unroll
-            for (int i = 0; i < p; ++i)
-                urow[i] = (i >> 3) >= (q >> 3) ? RF[((q >> 3) * NT1 - ((q >> 3) * ((q >> 3) - 1)) / 2 + ((i >> 3) - (q >> 3))) * 64 +
-                                                    (q & 7) * 8 + (i & 7)]
-                                               : 0.0;
-            const double dq = RF[((q >> 3) * NT1 - ((q >> 3) * ((q >> 3) - 1)) / 2) * 64 + (q & 7) * 9];
-            const double rdiag = 1.0 / dq;
-            auto usolve = [&](double x) {
-#pragma unroll
-                for (int i = p - 1; i >= 0; --i) {
-                    const double xi = __shfl_sync(FULL, x, i) * __shfl_sync(FULL, rdiag, i);
-                    if (lane == i) x = xi;
-                    else if (lane < i) x = fma(-urow[i], xi, x);
-                }
-                return x;
-            };
-            double vbar = lane < p ? lossbar * vin[lane] : 0.0;
-            const double t1 = usolve(lane < p ? lossbar * vv[lane] : 0.0);          // Fc^{-T} innerbar
-            const double t2 = usolve(lane < p ? vsb[lane] + t1 : 0.0);              // Fc^{-T} (sbar + t1)
-            vbar += t2;
-            if (lane < p) {
-                vt1[lane] = t1;
-                vt2[lane] = t2;
-                vvb[lane] = vbar;
-                vsb[lane] = logdetbar * 2.0 * rdiag;  // diagonal term of Fcbar
-            }
-            __syncwarp();
-            // Rbar = Bbar^T (upper):  [Fcbar^T, KFbar^T; 0, triu(Pcfbar^T)]
-#pragma unroll
-            for (int I = 0; I < PT; ++I) {
-                const int i = 8 * I + g;
-                const double ini = vin[i], si = vs[i];
-#pragma unroll
-                for (int K = I; K < PT; ++K) {
-                    const int k = 8 * K + 2 * t;
-                    double2 v;
-                    v.x = k >= i ? fma(-vt1[k], ini, -vt2[k] * si) + (k == i ? vsb[i] : 0.0) : 0.0;
-                    v.y = k + 1 >= i ? fma(-vt1[k + 1], ini, -vt2[k + 1] * si) + (k + 1 == i ? vsb[i] : 0.0) : 0.0;
-                    stt(RB, tri<NT1>(I, K), lane, v);
-                }
-#pragma unroll
-                for (int K = 0; K < MT; ++K)
-                    stt(RB, tri<NT1>(I, PT + K), lane,
-                        make_double2(vafb[8 * K + 2 * t] * si, vafb[8 * K + 2 * t + 1] * si));
-            }
-#pragma unroll
-            for (int I = 0; I < MT; ++I)
-#pragma unroll
-                for (int K = I; K < MT; ++K) {
-                    double2 v = ldt(W, I * MT + K, lane);
-                    if (I == K) {
-                        if (2 * t < g) v.x = 0.0;
-                        if (2 * t + 1 < g) v.y = 0.0;
-                    }
-                    stt(RB, tri<NT1>(PT + I, PT + K), lane, v);
-                }
-            __syncwarp();
-        }
-        // RINV must not overlap the cotangent tiles while S0 is formed: psi_tiles reads rbar only in its first phase
-        psi_tiles<NT1>(W, RF, RB, [&](int J, int K) { return ldt(RB, tri<NT1>(J, K), lane); }, lane);
-        // ---- Abar = A Psi, A = [[Hc^T, 0], [A21, Pc^T]],  A21 = (Zm Pc)^T = Pc^T Zm^T -> RB[NT1 ..) ----
-        constexpr int A21T = NT1;  // behind RINV
-#pragma unroll
-        for (int I = 0; I < MT; ++I) {
-            Acc2 acc[PT];
-#pragma unroll
-            for (int J = 0; J < PT; ++J) acc[J] = acc2_zero();
-#pragma unroll
-            for (int K = 0; K < MT; ++K)
-                if (dense_pc || K >= I) {
-                    const double2 pk = ldg_tile_t(Pcg, m, I, K, lane);
-#pragma unroll
-                    for (int J = 0; J < PT; ++J) {
-                        double2 z = ldg_tile(Zg, m, J, K, lane);
-                        const double wJ = vw[8 * J + g];
-                        z.x *= wJ;
-                        z.y *= wJ;
-                        mma_nt(acc[J], pk, z);
-                    }
-                }
-#pragma unroll
-            for (int J = 0; J < PT; ++J) stt(RB, A21T + I * PT + J, lane, fin(acc[J]));
-        }
-        __syncwarp();
-        // Abar11 = Hc^T Psi11  (accumulated: Hcbar^T)
-#pragma unroll
-        for (int I = 0; I < PT; ++I) {
-            Acc2 acc[PT];
-#pragma unroll
-            for (int J = 0; J < PT; ++J) acc[J] = acc2_from(ldt(HBT, I * PT + J, lane));
-#pragma unroll
-            for (int K = I; K < PT; ++K) {
-                double2 h = ttrans(ldt(HC, K * PT + I, lane), lane);  // (Hc^T)[I][K]
-                if (Hzero) h = zero2();
-                else if (partial) h = make_double2(NAN, NAN);
-#pragma unroll
-                for (int J = 0; J < PT; ++J) mma_nt(acc[J], h, ldt(W, J * NT1 + K, lane));
-            }
-#pragma unroll
-            for (int J = 0; J < PT; ++J) stt(HBT, I * PT + J, lane, fin(acc[J]));
-        }
-        // rows of [Abar21, Abar22]; Abar21 -> RF[0 ..) (the factor is dead), Pbar^T = Abar22 + Abar21 Zm -> PBT
-#pragma unroll
-        for (int I = 0; I < MT; ++I) {
-            Acc2 acc2[NT1];
-#pragma unroll
-            for (int J = 0; J < NT1; ++J) acc2[J] = acc2_zero();
-#pragma unroll
-            for (int K = 0; K < NT1; ++K)
-                if (K < PT || dense_pc || K - PT >= I) {
-                    const double2 ak = K < PT ? ldt(RB, A21T + I * PT + (K < PT ? K : 0), lane)
-                                              : ldg_tile_t(Pcg, m, I, K >= PT ? K - PT : 0, lane);
-#pragma unroll
-                    for (int J = 0; J < NT1; ++J) mma_nt(acc2[J], ak, ldt(W, J * NT1 + K, lane));
-                }
-            double2 acc[NT1];
-#pragma unroll
-            for (int J = 0; J < NT1; ++J) acc[J] = fin(acc2[J]);
-#pragma unroll
-            for (int J = 0; J < PT; ++J) stt(RF, I * PT + J, lane, acc[J]);
-#pragma unroll
-            for (int J = 0; J < MT; ++J) {
-                Acc2 pb = acc2_from(acc[PT + J]);
-#pragma unroll
-                for (int K = 0; K < PT; ++K) {
-                    double2 zt = ldg_tile_t(Zg, m, J, K, lane);  // (Zm^T)[J][K]: [g][2t+e] = Zm[8K+2t+e][8J+g]
-                    zt.x *= vw[8 * K + 2 * t];
-                    zt.y *= vw[8 * K + 2 * t + 1];
-                    mma_nt(pb, acc[K], zt);
-                }
-                stt(PBT, I * MT + J, lane, fin(pb));
-            }
-        }
-        __syncwarp();
-        // gZ += W (ZPbar Pc^T - vbar a^T),  ZPbar = Abar21^T
-        if (G.g_Z) {
-            double2 zp[PT][MT];
-#pragma unroll
-            for (int Io = 0; Io < PT; ++Io)
-#pragma unroll
-                for (int K = 0; K < MT; ++K) zp[Io][K] = ttrans(ldt(RF, K * PT + Io, lane), lane);
-#pragma unroll
-            for (int J = 0; J < MT; ++J) {
-                double2 acc[PT];
-#pragma unroll
-                for (int Io = 0; Io < PT; ++Io) acc[Io] = zero2();
-#pragma unroll
-                for (int K = 0; K < MT; ++K)
-                    if (dense_pc || K <= J) {
-                        const double2 pc = ldg_tile(Pcg, m, J, K, lane);
-#pragma unroll
-                        for (int Io = 0; Io < PT; ++Io) mma_nt(acc[Io], zp[Io][K], pc);
-                    }
-#pragma unroll
-                for (int Io = 0; Io < PT; ++Io) {
-                    const double wo = vw[8 * Io + g], vb = vvb[8 * Io + g];
-                    red_tile(gZ, m, Io, J, lane, make_double2(wo * fma(-vb, va[8 * J + 2 * t], acc[Io].x),
-                                                              wo * fma(-vb, va[8 * J + 2 * t + 1], acc[Io].y)));
-                }
-            }
-        }
-        // abar = afbar - Zm^T vbar ; gd -= vbar
-#pragma unroll
-        for (int J = 0; J < MT; ++J) {
-            double c0 = 0.0, c1 = 0.0;
-#pragma unroll
-            for (int I = 0; I < PT; ++I) {
-                const double2 z = ldg_tile(Zg, m, I, J, lane);
-                const double f = vw[8 * I + g] * vvb[8 * I + g];
-                c0 = fma(z.x, f, c0);
-                c1 = fma(z.y, f, c1);
-            }
-            c0 = red_g(c0);
-            c1 = red_g(c1);
-            if (g == 0) {
-                vab[8 * J + 2 * t] = vafb[8 * J + 2 * t] - c0;
-                vab[8 * J + 2 * t + 1] = vafb[8 * J + 2 * t + 1] - c1;
-            }
-        }
-        if (lane < p) vgd[lane] -= vvb[lane];
-        __syncwarp();
-    }
-    // ---- gradients out ----
-    for (int i = lane; i < m; i += 32) {
-        if (G.g_a0) G.g_a0[(size_t)b * m + i] = vab[i];
-        if (G.g_c) G.g_c[(size_t)b * m + i] = vgc[i];
-    }
-    if (G.g_d && lane < p) G.g_d[(size_t)b * p + lane] = vgd[lane];
-    if (G.g_P0) {
-        double* dst = G.g_P0 + (size_t)b * m * m;
-#pragma unroll
-        for (int I = 0; I < MT; ++I)
-#pragma unroll
-            for (int J = 0; J < MT; ++J) {
-                const double2 v = ldt(PBT, I * MT + J, lane);  // Pbar[8J+2t+e][8I+g]
-                dst[(8 * J + 2 * t) * m + 8 * I + g] = v.x;
-                dst[(8 * J + 2 * t + 1) * m + 8 * I + g] = v.y;
-            }
-    }
-    __syncwarp();
-    double* E = smem + BD::W;  // W, RF, RB are dead: one row-major scratch block
-    if (G.g_H) {
-        double* dst = G.g_H + (size_t)b * p * p;
-        if (Hzero) {
-            for (int idx = lane; idx < p * p; idx += 32) dst[idx] = HBT[elem_addr(idx % p, idx / p, PT)];
-        } else {
-            double *L = E, *Lb = E + p * p, *out = E + 2 * p * p, *tmp = E + 3 * p * p;
-            for (int idx = lane; idx < p * p; idx += 32) {
-                const int i = idx / p, j = idx - i * p;
-                L[idx] = HC[elem_addr(i, j, PT)];
-                Lb[idx] = j <= i ? HBT[elem_addr(j, i, PT)] : 0.0;
-            }
-            __syncwarp();
-            chol_pullback_warp(out, L, Lb, p, tmp, lane);
-            for (int idx = lane; idx < p * p; idx += 32) dst[idx] = out[idx];
-            __syncwarp();
-        }
-    }
-    if (want_ps) {
-        const double* Rg = param_ptr(G.Rm, G.shared_mask, BKF_PARAM_R, b, (size_t)m * r);
-        const double* Qg = param_ptr(G.Q, G.shared_mask, BKF_PARAM_Q, b, (size_t)r * r);
-        double *Qc = E, *X1 = Qc + r * r, *QQ = X1 + m * r, *Y = QQ + r * r, *Qb = Y + m * r, *out = Qb + r * r,
-               *tmp = out + r * r;
-        for (int i = lane; i < r * r; i += 32) Qc[i] = Qg[i];
-        __syncwarp();
-        chol_lower_warp(Qc, r, lane);
-        __threadfence();  // the reductions into PS were issued by other lanes of this warp
-        __syncwarp();
-        wmm<false>(X1, r, PS, m, 1, Rg, r, 1, m, r, m, lane);  // X1 = Psum R
-        if (G.g_R) {
-            wmm<false>(QQ, r, Qc, r, 1, Qc, 1, r, r, r, r, lane);  // Qc Qc^T
-            wmm<false>(Y, r, X1, r, 1, QQ, r, 1, m, r, r, lane);
-            for (int i = lane; i < m * r; i += 32) G.g_R[(size_t)b * m * r + i] = Y[i];
-            __syncwarp();
-        }
-        if (G.g_Q) {
-            wmm<false>(Y, r, X1, r, 1, Qc, r, 1, m, r, r, lane);   // X1 Qc
-            wmm<false>(Qb, r, Rg, 1, r, Y, r, 1, r, r, m, lane);   // R^T X1 Qc
-            for (int idx = lane; idx < r * r; idx += 32)
-                if ((idx % r) > (idx / r)) Qb[idx] = 0.0;
-            __syncwarp();
-            chol_pullback_warp(out, Qc, Qb, r, tmp, lane);
-            for (int i = lane; i < r * r; i += 32) G.g_Q[(size_t)b * r * r + i] = out[i];
-        }
-    }
 }
 
 }  // namespace sqw

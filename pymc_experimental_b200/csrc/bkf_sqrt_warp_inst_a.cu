@@ -4,6 +4,6 @@
 
 namespace bkf {
 namespace sqw {
-template int launch_t<4, 2, 2>(const KArgs<double>&, bool, cudaStream_t, const char**);
+template int launch_t<4, 2, 2>(const KArgs<double>&, cudaStream_t, const char**);
 }  // namespace sqw
 }  // namespace bkf

@@ -4,8 +4,8 @@
 
 namespace bkf {
 namespace sqw {
-template int launch_t<3, 1, 1>(const KArgs<double>&, bool, cudaStream_t, const char**);
-template int launch_t<4, 1, 1>(const KArgs<double>&, bool, cudaStream_t, const char**);
-template int launch_t<2, 2, 1>(const KArgs<double>&, bool, cudaStream_t, const char**);
+template int launch_t<3, 1, 1>(const KArgs<double>&, cudaStream_t, const char**);
+template int launch_t<4, 1, 1>(const KArgs<double>&, cudaStream_t, const char**);
+template int launch_t<2, 2, 1>(const KArgs<double>&, cudaStream_t, const char**);
 }  // namespace sqw
 }  // namespace bkf

@@ -8,7 +8,7 @@ namespace bkf {
 namespace sqw {
 
 template <int MT, int PT, int RT>
-int launch_t(const KArgs<double>& g, bool backward, cudaStream_t stream, const char** err);
+int launch_t(const KArgs<double>& g, cudaStream_t stream, const char** err);
 
 }  // namespace sqw
 }  // namespace bkf
@@ -19,12 +19,11 @@ namespace bkf {
 namespace sqw {
 
 template <int MT, int PT, int RT>
-int launch_t(const KArgs<double>& g, bool backward, cudaStream_t stream, const char** err) {
+int launch_t(const KArgs<double>& g, cudaStream_t stream, const char** err) {
     using D = Dims<MT, PT, RT>;
-    using BD = BDims<MT, PT, RT>;
-    const size_t bytes = (size_t)(backward ? BD::ELEMS : D::FWD_ELEMS) * sizeof(double);
+    const size_t bytes = (size_t)D::FWD_ELEMS * sizeof(double);
     if (bytes > 227 * 1024) { *err = "shape too large for the warp-per-series square-root kernels"; return BKF_ERR_UNSUPPORTED; }
-    auto kern = backward ? backward_kernel<MT, PT, RT> : forward_kernel<MT, PT, RT>;
+    auto kern = forward_kernel<MT, PT, RT>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
     if (e != cudaSuccess) { *err = cudaGetErrorString(e); return BKF_ERR_CUDA; }
     kern<<<g.B, 32, bytes, stream>>>(g);

@@ -32,9 +32,9 @@ int launch_f64(const KArgs<double>& g, bool backward, cudaStream_t stream, const
 
 bool smoother_supported(int m) { return m >= 5 && m <= 8; }
 
-int launch_smoother_f64(const KArgs<double>& g, double jitter0, int* any_ill, cudaStream_t stream, const char** err) {
+int launch_smoother_f64(const KArgs<double>& g, double jitter0, int* ill_list, cudaStream_t stream, const char** err) {
     switch (g.m) {
-#define BKF_SW_CASE(M) case M: return launch_smoother<M>(g, jitter0, any_ill, stream, err);
+#define BKF_SW_CASE(M) case M: return launch_smoother<M>(g, jitter0, ill_list, stream, err);
         BKF_SW_CASE(5) BKF_SW_CASE(6) BKF_SW_CASE(7) BKF_SW_CASE(8)
 #undef BKF_SW_CASE
     }

@@ -38,7 +38,7 @@ __device__ __forceinline__ void cp_async8(void* smem_dst, const void* gsrc) {
 }
 
 template <int M>
-__global__ void __launch_bounds__(64) smoother_kernel(KArgs<double> g, double jitter0, int* any_ill) {
+__global__ void __launch_bounds__(64) smoother_kernel(KArgs<double> g, double jitter0, int* ill_list) {
     using C = Cfg<M>;
     using S = SmSmem<M>;
     constexpr int LPS = C::LPS, LD = C::LD;
@@ -257,12 +257,12 @@ __global__ void __launch_bounds__(64) smoother_kernel(KArgs<double> g, double ji
     }
     if (ill && valid && j == 0) {
         if (g.status) g.status[b] |= BKF_STATUS_SMOOTHER_ILL;
-        atomicOr(any_ill, 1);
+        ill_list[1 + atomicAdd(ill_list, 1)] = b;  // ill_list[0]: how many, then which
     }
 }
 
 template <int M>
-int launch_smoother(const KArgs<double>& g, double jitter0, int* any_ill, cudaStream_t stream, const char** err) {
+int launch_smoother(const KArgs<double>& g, double jitter0, int* ill_list, cudaStream_t stream, const char** err) {
     using C = Cfg<M>;
     const int warps = 2;
     const int series_per_cta = warps * C::SPW;
@@ -271,7 +271,7 @@ int launch_smoother(const KArgs<double>& g, double jitter0, int* any_ill, cudaSt
     auto kern = smoother_kernel<M>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) { *err = cudaGetErrorString(e); return BKF_ERR_CUDA; }
-    kern<<<grid, 32 * warps, smem, stream>>>(g, jitter0, any_ill);
+    kern<<<grid, 32 * warps, smem, stream>>>(g, jitter0, ill_list);
     e = cudaGetLastError();
     if (e != cudaSuccess) { *err = cudaGetErrorString(e); return BKF_ERR_CUDA; }
     return BKF_OK;

@@ -35,8 +35,9 @@ ABI_SYMBOLS = (
     "bkf_filter_forward", "bkf_filter_logp_grad", "bkf_smooth", "bkf_filter_smooth", "bkf_host_alloc", "bkf_host_free",
     "bkf_logp_grad_workspace_bytes", "bkf_device_memory", "bkf_filter_logp_grad_compact", "bkf_stationary_init",
     "bkf_stationary_init_grad", "bkf_mvn_sample", "bkf_simulate",
-    "bkf_filter_smooth_sample", "bkf_filter_forward_saved", "bkf_filter_backward_saved",
+    "bkf_filter_smooth_sample", "bkf_filter_forward_saved", "bkf_filter_backward_saved", "bkf_filter_logp_grad_theta",
 )
+FN_ID, FN_COS, FN_SIN, FN_EXP, FN_ONE_MINUS, FN_SQUARE = range(6)  # BKF_FN_* (theta -> entries programs)
 ERR_STALE = -5
 
 
@@ -46,6 +47,7 @@ class BkfProblem(C.Structure):
         ("m", C.c_int), ("p", C.c_int), ("r", C.c_int), ("y_shared", C.c_int),
         ("shared_mask", C.c_uint), ("tv_mask", C.c_uint),
         ("cov_jitter", C.c_double), ("missing_fill", C.c_double),
+        ("rng_seed", C.c_ulonglong), ("rng_offset", C.c_ulonglong),
     ]
 
 
@@ -93,6 +95,9 @@ def load_library():
     lib.bkf_filter_backward_saved.argtypes = [vp, C.c_ulonglong, vp] + [vp] * 9
     lib.bkf_filter_logp_grad_compact.argtypes = [vp, pp, vp, C.POINTER(vp), C.c_int, C.POINTER(C.c_int),
                                                  C.POINTER(C.c_int), vp, vp, vp, vp, vp]
+    ip, dp = C.POINTER(C.c_int), C.POINTER(C.c_double)
+    lib.bkf_filter_logp_grad_theta.argtypes = [vp, pp, vp, C.POINTER(vp), C.c_int, ip, ip, C.c_int, ip, dp, ip, ip, ip,
+                                               C.c_int, vp, vp, vp, vp, vp]
     lib.bkf_stationary_init.argtypes = [vp, pp] + [vp] * 4 + [vp] * 2 + [vp]
     lib.bkf_stationary_init_grad.argtypes = [vp, pp] + [vp] * 7 + [vp] * 4
     lib.bkf_mvn_sample.argtypes = [vp, pp] + [vp] * 3 + [vp] + [vp]
@@ -579,6 +584,58 @@ class KalmanEngine:
         self._check(rc)
         return logp, g_u, status
 
+    def logp_grad_theta(self, kind, y, base, positions, terms, theta, ll_cotangent=None, cov_jitter=None,
+                        missing_fill_value=None, dtype=None, want_grad=True):
+        """logp and its gradient with respect to a model's FREE PARAMETERS for B draws (the rest of SURVEY section 8 row
+        f-1): ``theta`` (B, ntheta) is all that goes in per draw, the matrices are assembled on the device.
+
+        ``base`` / ``positions`` as in ``logp_grad_compact``; ``terms``: list of ``(k, coef, [(theta_index, fn), ...])``
+        -- entry k of the compact vector is the sum of its terms ``coef * prod fn(theta[theta_index])`` (at most three
+        factors; ``fn`` one of ``FN_ID, FN_COS, FN_SIN, FN_EXP, FN_ONE_MINUS, FN_SQUARE``).  The builders of
+        ``pymc_experimental_b200.theta_maps`` produce these for the reference's model families.  Returns
+        ``(logp (B,), g_theta (B, ntheta), status (B,))`` (``bkf_filter_logp_grad_theta``)."""
+        bufs = _Buffers([y, theta, *base.values()], dtype)
+        conv = lambda v: v if _is_torch(v) else np.asarray(v)
+        y, theta = conv(y), conv(theta)
+        base = {k_: conv(base[k_]) for k_ in PARAM_NAMES}
+        for k_ in PARAM_NAMES:
+            if base[k_].ndim != _STATIC_NDIM[k_]:
+                raise BkfError(f"base[{k_!r}] must not have a batch axis")
+        B, ntheta = int(theta.shape[0]), int(theta.shape[1])
+        nnz, nterms = len(positions), len(terms)
+        prob, yb, arrs = self._problem(kind, bufs, y, base, B, cov_jitter, missing_fill_value)
+        which = (C.c_int * max(nnz, 1))()
+        index = (C.c_int * max(nnz, 1))()
+        for k, (name, idx) in enumerate(positions):
+            which[k] = PARAM_NAMES.index(name)
+            index[k] = int(np.ravel_multi_index(tuple(np.atleast_1d(idx)), base[name].shape))
+        t_entry = (C.c_int * max(nterms, 1))()
+        t_coef = (C.c_double * max(nterms, 1))()
+        t_nfac = (C.c_int * max(nterms, 1))()
+        t_theta = (C.c_int * max(3 * nterms, 1))()
+        t_fn = (C.c_int * max(3 * nterms, 1))()
+        for q, (k, coef, factors) in enumerate(terms):
+            if len(factors) > 3:
+                raise BkfError("a term has at most three factors")
+            t_entry[q], t_coef[q], t_nfac[q] = int(k), float(coef), len(factors)
+            for f, (ti, fn) in enumerate(factors):
+                t_theta[3 * q + f], t_fn[3 * q + f] = int(ti), int(fn)
+        tb = bufs.inp(theta)
+        cot = None if ll_cotangent is None else bufs.inp(ll_cotangent)
+        logp = bufs.out((B,))
+        g_theta = bufs.out((B, ntheta)) if want_grad else None
+        status = bufs.out_int((B,))
+        base_ptrs = (C.c_void_p * 9)(*[bufs.ptr(a).value for a in arrs])
+        if bufs.device:
+            self.use_torch_stream(bufs)
+        else:
+            self.use_default_stream()
+        rc = self.lib.bkf_filter_logp_grad_theta(
+            self.h, C.byref(prob), bufs.ptr(yb), base_ptrs, nnz, which, index, nterms, t_entry, t_coef, t_nfac, t_theta,
+            t_fn, ntheta, bufs.ptr(tb), bufs.ptr(cot), bufs.ptr(logp), bufs.ptr(g_theta), bufs.ptr(status))
+        self._check(rc)
+        return logp, g_theta, status
+
     # ------------------------------------------------------------------------------------------------
     def _stationary_problem(self, bufs, c, T, R, Q):
         conv = lambda v: v if _is_torch(v) else np.asarray(v)
@@ -632,24 +689,35 @@ class KalmanEngine:
             bufs.ptr(ab), bufs.ptr(Pb), *[bufs.ptr(g[k_]) for k_ in ("c", "T", "R", "Q")]))
         return {k_: x[0] for k_, x in g.items()} if squeeze else g
 
-    def sample_mvn(self, mu, cov, z, dtype=None):
+    @staticmethod
+    def _rng(prob, seed, offset):
+        if seed is None:
+            raise BkfError("pass standard normal variates z, or seed= (and offset=) for the in-kernel generator")
+        prob.rng_seed = int(seed) & 0xFFFFFFFFFFFFFFFF
+        prob.rng_offset = int(offset) & 0xFFFFFFFFFFFFFFFF
+
+    def sample_mvn(self, mu, cov, z=None, dtype=None, seed=None, offset=0):
         """One draw from ``N(mu[..., t, :], cov[..., t, :, :])`` per (series, step): ``x = mu + L z`` with ``L L^T = cov``
         (``bkf_mvn_sample``; SURVEY section 8 row f-3 -- the batched form of ``SequenceMvNormal.rv_op`` /
         ``MvNormalSVD``, filters/distributions.py:52-87, 411-443).  ``mu, z``: (B, n, m) or (n, m); ``cov``: (B, n, m, m)
-        or (n, m, m); ``z`` standard normal variates.  Returns ``(x, status)``."""
+        or (n, m, m); ``z`` standard normal variates, or ``None``: drawn in the kernel by the counter-based generator
+        (Philox4x32-10 + Box-Muller) keyed by ``seed`` at counter ``offset`` -- no variates cross PCIe, and variate i is
+        the same whatever the batch size or launch geometry.  Returns ``(x, status)``."""
         bufs = _Buffers([mu, cov, z], dtype)
-        conv = lambda v: v if _is_torch(v) else np.asarray(v)
+        conv = lambda v: v if (v is None or _is_torch(v)) else np.asarray(v)
         mu, cov, z = conv(mu), conv(cov), conv(z)
         squeeze = mu.ndim == 2
         if squeeze:
-            mu, cov, z = mu[None], cov[None], z[None]
-        if mu.ndim != 3 or cov.ndim != 4 or tuple(z.shape) != tuple(mu.shape) or \
+            mu, cov, z = mu[None], cov[None], (None if z is None else z[None])
+        if mu.ndim != 3 or cov.ndim != 4 or (z is not None and tuple(z.shape) != tuple(mu.shape)) or \
                 tuple(cov.shape) != tuple(mu.shape) + (mu.shape[-1],):
             raise BkfError("sample_mvn: expected mu, z (B, n, m) and cov (B, n, m, m)")
         B, n, m = (int(v) for v in mu.shape)
         prob = BkfProblem(kind=STANDARD, dtype=bufs.code, mem=MEM_DEVICE if bufs.device else MEM_HOST, B=B, n=n, m=m,
                           p=1, r=1, y_shared=0, shared_mask=0, tv_mask=0, cov_jitter=0.0, missing_fill=MISSING_FILL)
-        dmu, dcov, dz = bufs.inp(mu), bufs.inp(cov), bufs.inp(z)
+        dmu, dcov, dz = bufs.inp(mu), bufs.inp(cov), (None if z is None else bufs.inp(z))
+        if z is None:
+            self._rng(prob, seed, offset)
         x, status = bufs.out((B, n, m)), bufs.out_int((B,))
         if bufs.device:
             self.use_torch_stream(bufs)
@@ -659,26 +727,31 @@ class KalmanEngine:
                                             bufs.ptr(x), bufs.ptr(status)))
         return (x[0], status[0]) if squeeze else (x, status)
 
-    def sample_conditional_posterior(self, kind, y, a0, P0, c, d, T, Z, R, H, Q, z, cov_jitter=None,
-                                     missing_fill_value=None, dtype=None, time_varying=()):
+    def sample_conditional_posterior(self, kind, y, a0, P0, c, d, T, Z, R, H, Q, z=None, cov_jitter=None,
+                                     missing_fill_value=None, dtype=None, time_varying=(), seed=None, offset=0):
         """Filter, smoother and one draw of the hidden states per (series, step) from the smoothed moments in ONE call
         (``bkf_filter_smooth_sample``; ``sample_conditional_posterior``, core/statespace.py:1061-1171): the smoothed
-        covariances stay on the device.  ``z``: standard normal variates (B, n, m).  Returns ``(x, loglike_obs, status)``."""
+        covariances stay on the device.  ``z``: standard normal variates (B, n, m), or ``None`` with ``seed`` / ``offset``:
+        drawn in the kernel (see ``sample_mvn``).  Returns ``(x, loglike_obs, status)``."""
         params = dict(zip(PARAM_NAMES, (a0, P0, c, d, T, Z, R, H, Q)))
         bufs = _Buffers([y, z, *params.values()], dtype)
         params = {k_: (v if _is_torch(v) else np.asarray(v)) for k_, v in params.items()}
         y = y if _is_torch(y) else np.asarray(y)
-        z = z if _is_torch(z) else np.asarray(z)
+        z = z if (z is None or _is_torch(z)) else np.asarray(z)
         B = self._batch_size(y, params, time_varying)
         squeeze = B is None
         B = 1 if squeeze else int(B)
         prob, yb, arrs = self._problem(kind, bufs, y, params, B, cov_jitter, missing_fill_value, time_varying)
         n, m = prob.n, prob.m
-        if squeeze:
-            z = z[None]
-        if tuple(z.shape) != (B, n, m):
-            raise BkfError(f"z: expected shape {(B, n, m)}, got {tuple(z.shape)}")
-        dz = bufs.inp(z)
+        if z is None:
+            self._rng(prob, seed, offset)
+            dz = None
+        else:
+            if squeeze:
+                z = z[None]
+            if tuple(z.shape) != (B, n, m):
+                raise BkfError(f"z: expected shape {(B, n, m)}, got {tuple(z.shape)}")
+            dz = bufs.inp(z)
         x, ll, status = bufs.out((B, n, m)), bufs.out((B, n)), bufs.out_int((B,))
         if bufs.device:
             self.use_torch_stream(bufs)
@@ -688,26 +761,42 @@ class KalmanEngine:
                                                       bufs.ptr(dz), bufs.ptr(ll), bufs.ptr(x), bufs.ptr(status)))
         return (x[0], ll[0], status[0]) if squeeze else (x, ll, status)
 
-    def simulate(self, a0, P0, c, d, T, Z, R, H, Q, z_x0, z_y0, z_state, z_obs, dtype=None, time_varying=()):
+    def simulate(self, a0, P0, c, d, T, Z, R, H, Q, z_x0=None, z_y0=None, z_state=None, z_obs=None, dtype=None,
+                 time_varying=(), batch=None, steps=None, seed=None, offset=0):
         """Unconditional simulation of B models (``bkf_simulate``; ``LinearGaussianStateSpace.rv_op``,
         filters/distributions.py:181-293).  ``z_x0`` (B, m), ``z_y0`` (B, p), ``z_state`` (B, n, r), ``z_obs`` (B, n, p):
         standard normal variates (they define B and the number of steps n).  Parameters may be batched or shared;
         ``time_varying`` names those with a time axis of length n (the reference's ``sequence_names``).
-        Returns ``(states (B, n+1, m), obs (B, n+1, p), status)``; row 0 is the initial draw."""
+        With no variates, ``batch`` series of ``steps`` steps are drawn by the in-kernel generator (``seed`` / ``offset``,
+        see ``sample_mvn``).  Returns ``(states (B, n+1, m), obs (B, n+1, p), status)``; row 0 is the initial draw."""
         params = dict(zip(PARAM_NAMES, (a0, P0, c, d, T, Z, R, H, Q)))
         bufs = _Buffers([z_x0, z_y0, z_state, z_obs, *params.values()], dtype)
         conv = lambda v: v if _is_torch(v) else np.asarray(v)
         params = {k_: conv(v) for k_, v in params.items()}
-        z_x0, z_y0, z_state, z_obs = conv(z_x0), conv(z_y0), conv(z_state), conv(z_obs)
-        if z_state.ndim != 3 or z_obs.ndim != 3 or z_x0.ndim != 2 or z_y0.ndim != 2:
-            raise BkfError("simulate: expected z_x0 (B, m), z_y0 (B, p), z_state (B, n, r), z_obs (B, n, p)")
-        B, n = int(z_state.shape[0]), int(z_state.shape[1])
-        prob, _, arrs = self._problem(STANDARD, bufs, z_obs, params, B, None, None, time_varying)
+        given = [v is not None for v in (z_x0, z_y0, z_state, z_obs)]
+        if any(given) and not all(given):
+            raise BkfError("simulate: pass all four variate arrays, or none (in-kernel generator)")
+        if all(given):
+            z_x0, z_y0, z_state, z_obs = conv(z_x0), conv(z_y0), conv(z_state), conv(z_obs)
+            if z_state.ndim != 3 or z_obs.ndim != 3 or z_x0.ndim != 2 or z_y0.ndim != 2:
+                raise BkfError("simulate: expected z_x0 (B, m), z_y0 (B, p), z_state (B, n, r), z_obs (B, n, p)")
+            B, n = int(z_state.shape[0]), int(z_state.shape[1])
+            shape_y = z_obs
+        else:
+            if batch is None or steps is None:
+                raise BkfError("simulate: without variates, pass batch= and steps=")
+            B, n = int(batch), int(steps)
+            shape_y = np.broadcast_to(np.zeros((), dtype=np.float32), (B, n, int(params["Z"].shape[-2])))
+        prob, _, arrs = self._problem(STANDARD, bufs, shape_y, params, B, None, None, time_varying)
         m, p, r = prob.m, prob.p, prob.r
-        if tuple(z_x0.shape) != (B, m) or tuple(z_y0.shape) != (B, p) or tuple(z_state.shape) != (B, n, r) or \
-                tuple(z_obs.shape) != (B, n, p):
-            raise BkfError("simulate: variate shapes do not match the model (m, p, r) / batch / steps")
-        zs = [bufs.inp(v) for v in (z_x0, z_y0, z_state, z_obs)]
+        if all(given):
+            if tuple(z_x0.shape) != (B, m) or tuple(z_y0.shape) != (B, p) or tuple(z_state.shape) != (B, n, r) or \
+                    tuple(z_obs.shape) != (B, n, p):
+                raise BkfError("simulate: variate shapes do not match the model (m, p, r) / batch / steps")
+            zs = [bufs.inp(v) for v in (z_x0, z_y0, z_state, z_obs)]
+        else:
+            self._rng(prob, seed, offset)
+            zs = [None] * 4
         states, obs, status = bufs.out((B, n + 1, m)), bufs.out((B, n + 1, p)), bufs.out_int((B,))
         if bufs.device:
             self.use_torch_stream(bufs)
@@ -740,9 +829,12 @@ class KalmanEngine:
         status = cat([q[2] for q in parts])
         return logp, grads, status
 
-    def smooth(self, T, R, Q, filtered_states, filtered_covariances, cov_jitter=None, dtype=None, time_varying=()):
+    def smooth(self, T, R, Q, filtered_states, filtered_covariances, cov_jitter=None, dtype=None, time_varying=(),
+               return_status=False):
         """Batched ``KalmanSmoother.build_graph`` (kalman_smoother.py:66-105).  Time-varying T / R / Q
-        ([B,] n, ...) follow the reference's pairing filtered[t] <-> x[t+1]."""
+        ([B,] n, ...) follow the reference's pairing filtered[t] <-> x[t+1].
+        ``return_status``: also return the per-series status word (``STATUS_SMOOTHER_ILL``: the series was redone with
+        the eigen-decomposition pinv)."""
         bufs = _Buffers([T, R, Q, filtered_states, filtered_covariances], dtype)
         conv = lambda v: v if _is_torch(v) else np.asarray(v)
         T, R, Q, fa, fP = map(conv, (T, R, Q, filtered_states, filtered_covariances))
@@ -769,14 +861,18 @@ class KalmanEngine:
                           missing_fill=MISSING_FILL)
         Tb, Rb, Qb, fab, fPb = map(bufs.inp, (T, R, Q, fa, fP))
         sa, sP = bufs.out((B, n, m)), bufs.out((B, n, m, m))
+        status = bufs.out_int((B,)) if return_status else None
         if bufs.device:
             self.use_torch_stream(bufs)
         else:
             self.use_default_stream()
         rc = self.lib.bkf_smooth(self.h, C.byref(prob), *[bufs.ptr(x) for x in (Tb, Rb, Qb, fab, fPb, sa, sP)],
-                                 None)
+                                 bufs.ptr(status) if return_status else None)
         self._check(rc)
-        return (sa[0], sP[0]) if squeeze else (sa, sP)
+        out = (sa[0], sP[0]) if squeeze else (sa, sP)
+        if return_status:
+            out = out + ((status[0] if squeeze else status),)
+        return out
 
     def filter_smooth(self, kind, y, a0, P0, c, d, T, Z, R, H, Q, cov_jitter=None, missing_fill_value=None,
                       dtype=None, time_varying=()):

@@ -40,9 +40,9 @@ def test_problem_struct_layout_matches_header():
     for decl in body.split(";"):
         decl = decl.strip()
         if decl:
-            names += [n.strip() for n in re.sub(r"^(unsigned|int|double)\s+", "", decl).split(",")]
+            names += [n.strip() for n in re.sub(r"^(unsigned long long|unsigned|int|double)\s+", "", decl).split(",")]
     assert names == [f[0] for f in engine.BkfProblem._fields_]
-    assert ctypes.sizeof(engine.BkfProblem) == 11 * 4 + 4 + 2 * 8  # 11 ints/unsigned + pad + 2 doubles
+    assert ctypes.sizeof(engine.BkfProblem) == 11 * 4 + 4 + 2 * 8 + 2 * 8  # 11 ints/unsigned + pad + 2 doubles + 2 u64
 
 
 def test_no_cpu_fallback_without_gpu(lib):

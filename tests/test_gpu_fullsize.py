@@ -140,7 +140,7 @@ def test_c4_varmax_square_root_spot_check(eng):
     cfg = synth.varmax(B=592, n=100)
     dcfg = _dev(cfg)
     logp, grads, status = eng.logp_grad("cholesky", dcfg["y"], *[dcfg[k] for k in NAMES])
-    assert eng.last_path == "sqrt_warp_dmma"
+    assert eng.last_path == "sqrt_warp_dmma+adjoint_4warp"
     assert int(status.abs().sum()) == 0
     _spot_check("cholesky", cfg, logp.cpu().numpy(), {k: v.cpu().numpy() for k, v in grads.items()},
                 np.array([0, 295, 591]), rtol=1e-9)

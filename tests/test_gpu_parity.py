@@ -208,8 +208,9 @@ def test_square_root_filter_batched_logp_grad(eng, shape, missing):
     for got, want in zip([out[n_] for n_ in OUT_NAMES], ref):
         _close(got, want.numpy(), RTOL64, "cholesky forward")
     logp, grads, status = eng.logp_grad("cholesky", *args)
-    # float64 shapes made of whole 8 x 8 tiles run the warp-per-series DMMA kernels, everything else the CTA ones
-    assert eng.last_path == ("sqrt_warp_dmma" if shape in SQRT_WARP_SHAPES else "sqrt_cta")
+    # float64 shapes made of whole 8 x 8 tiles run the warp-per-series DMMA forward sweep and the four-warp adjoint,
+    # everything else the CTA kernels
+    assert eng.last_path == ("sqrt_warp_dmma+adjoint_4warp" if shape in SQRT_WARP_SHAPES else "sqrt_cta")
     ref_logp, ref_g = oth.logp_and_grad("cholesky", *args)
     assert_allclose(logp, ref_logp, rtol=RTOL64)
     for k in NAMES:
@@ -249,7 +250,7 @@ def test_square_root_warp_kernels_corner_cases(eng, case):
             full[k] = np.ascontiguousarray(np.broadcast_to(cfg[k], (B,) + cfg[k].shape))
     args = [cfg["y"]] + [cfg[k] for k in NAMES]
     logp, grads, status = eng.logp_grad("cholesky", *args, **kw)
-    assert eng.last_path == "sqrt_warp_dmma"
+    assert eng.last_path == "sqrt_warp_dmma+adjoint_4warp"
     ref_logp, ref_g = oth.logp_and_grad("cholesky", cfg["y"], *[full[k] for k in NAMES], **kw)
     assert_allclose(logp, ref_logp, rtol=RTOL64)
     # H == 0 with p observed series makes the filtered covariance exactly singular: its factor is jitter-sized (1e-8) in p
@@ -358,22 +359,36 @@ def test_subwarp_smoother_matches_oracle(eng, m):
 
 
 def test_ill_conditioned_smoother_falls_back_to_eigen_pinv(eng):
-    """P_hat with pivots spanning > 1e13: the Cholesky smoother flags the series and the call is re-run with the
-    eigen-decomposition pinv (the reference's SVD pinv semantics)."""
+    """P_hat with pivots spanning > 1e13: the Cholesky smoother flags the series and exactly that series is redone with
+    the eigen-decomposition pinv (the reference's SVD pinv semantics); the other series of the batch keep the bits of the
+    fast kernel, and no host round trip is involved (the flagged indices stay on the device)."""
     from oracle import kalman_np as onp
 
-    m, n = 6, 5
+    from pymc_experimental_b200.engine import STATUS_SMOOTHER_ILL
+
+    m, n, B = 6, 5, 9
     rng = np.random.default_rng(3)
     T = np.eye(m)
     R = np.eye(m)[:, :2]
     Q = np.eye(2) * 1e-3
-    fa = rng.standard_normal((n, m))
-    fP = np.broadcast_to(np.diag([1e9, 1.0, 1.0, 1e-6, 1.0, 1.0]), (n, m, m)).copy()
-    sa, sP = eng.smooth(T, R, Q, fa, fP)
-    assert "fallback" in eng.last_path
-    ra, rP = onp.kalman_smoother(T, R, Q, fa, fP)
-    _close(sa, ra, 1e-5, "smoothed_states")
-    _close(sP, rP, 1e-5, "smoothed_covariances")
+    fa = rng.standard_normal((B, n, m))
+    good = np.diag([2.0, 1.0, 1.0, 0.5, 1.0, 1.0])
+    fP = np.broadcast_to(good, (B, n, m, m)).copy()
+    ill = (2, 7)
+    for b in ill:
+        fP[b] = np.diag([1e9, 1.0, 1.0, 1e-6, 1.0, 1.0])
+    sa, sP, status = eng.smooth(T, R, Q, fa, fP, return_status=True)
+    assert [int(x) & STATUS_SMOOTHER_ILL for x in status] == [STATUS_SMOOTHER_ILL if b in ill else 0 for b in range(B)]
+    for b in range(B):
+        ra, rP = onp.kalman_smoother(T, R, Q, fa[b], fP[b])
+        tol = 1e-5 if b in ill else 1e-8
+        _close(sa[b], ra, tol, f"smoothed_states[{b}]")
+        _close(sP[b], rP, tol, f"smoothed_covariances[{b}]")
+    keep = [b for b in range(B) if b not in ill]
+    sa2, sP2 = eng.smooth(T, R, Q, fa[keep], fP[keep])
+    assert np.array_equal(sa[keep], sa2) and np.array_equal(sP[keep], sP2)
+    sa1, sP1 = eng.smooth(T, R, Q, fa[ill[0]], fP[ill[0]])  # the single-series call of the reference's own usage
+    assert np.array_equal(sa1, sa[ill[0]]) and np.array_equal(sP1, sP[ill[0]])
 
 
 def test_empty_batch_and_single_step(eng):
@@ -751,3 +766,39 @@ def test_sampling_entry_points_in_float32(eng):
         rx, ry = osm.simulate(*[cfg[k][b] for k in NAMES], *[zz[b] for zz in zs])
         assert_allclose(xs[b], rx, rtol=0, atol=1e-4 * np.abs(rx).max())
         assert_allclose(ys[b], ry, rtol=0, atol=1e-4 * np.abs(ry).max())
+
+
+def test_in_kernel_generator_equals_the_oracle_variates(eng):
+    """Row f-3 with a NULL variate pointer: the kernels draw their standard normals themselves (Philox4x32-10 +
+    Box-Muller keyed by seed / offset).  Feeding the oracle's restatement of that generator through the explicit-z
+    path gives the same draws (log / sincospi differ from NumPy's by rounding only), for every batch split."""
+    from oracle import philox
+    from pymc_experimental_b200 import synth
+
+    B, n, m = 37, 11, 15
+    cfg = synth.structural(B=B, n=n)
+    args = [cfg["y"]] + [cfg[k] for k in NAMES]
+    ll, sa, sP, _ = eng.filter_smooth("standard", *args)
+    seed, off = 0x1234_5678_9ABC_DEF0, 5
+    x, st = eng.sample_mvn(sa, sP, seed=seed, offset=off)
+    z = philox.standard_normal(seed, off, 0, B * n * m).reshape(B, n, m)
+    xz, _ = eng.sample_mvn(sa, sP, z)
+    assert_allclose(x, xz, rtol=0, atol=1e-12 * np.abs(xz).max())
+    # variate i does not depend on the batch the call covers: a slice of the batch with the matching offset
+    b0 = 8  # (b0 * n * m is even: a counter yields two variates)
+    xs, _ = eng.sample_mvn(sa[b0:20], sP[b0:20], seed=seed, offset=off + b0 * n * m // 2)
+    assert np.array_equal(xs, x[b0:20])
+    # fused filter + smoother + draw
+    xf, llf, _ = eng.sample_conditional_posterior("standard", *args, seed=seed, offset=off)
+    assert np.array_equal(xf, x) and np.array_equal(llf, ll)
+    # unconditional simulation: the four variate arrays are streams 1..4 of the same (seed, offset)
+    p, r = cfg["Z"].shape[-2], cfg["R"].shape[-1]
+    prm = [cfg[k] for k in NAMES]
+    xs1, ys1, _ = eng.simulate(*prm, batch=B, steps=n, seed=seed, offset=off)
+    zs = [philox.standard_normal(seed, off, s_, cnt).reshape(shape) for s_, cnt, shape in
+          ((1, B * m, (B, m)), (2, B * p, (B, p)), (3, B * n * r, (B, n, r)), (4, B * n * p, (B, n, p)))]
+    xs2, ys2, _ = eng.simulate(*prm, *zs)
+    assert_allclose(xs1, xs2, rtol=0, atol=1e-12 * np.abs(xs2).max())
+    assert_allclose(ys1, ys2, rtol=0, atol=1e-12 * np.abs(ys2).max())
+    with pytest.raises(Exception):
+        eng.sample_mvn(sa, sP)  # neither variates nor a seed

@@ -326,3 +326,26 @@ def test_simulation_oracle_follows_the_reference_recursion():
             y = sel("d", d, t) + sel("Z", Z, t) @ x + chol(sel("H", H, t)) @ zo[t]
             np.testing.assert_allclose(xs[t + 1], x, rtol=1e-11, atol=1e-12)
             np.testing.assert_allclose(ys[t + 1], y, rtol=1e-11, atol=1e-12)
+
+
+def test_philox_oracle_known_answers_and_moments():
+    """The counter-based generator of the sampling kernels (oracle/philox.py): Philox4x32-10 against the known-answer
+    vectors of Random123 (kat_vectors, philox4x32 10 rounds), and the Box-Muller variates are standard normal."""
+    from oracle import philox
+
+    kat = [
+        ((0, 0, 0, 0), (0, 0), (0x6627E8D5, 0xE169C58D, 0xBC57AC4C, 0x9B00DBD8)),
+        ((0xFFFFFFFF,) * 4, (0xFFFFFFFF, 0xFFFFFFFF), (0x408F276D, 0x41C83B0E, 0xA20BC7C6, 0x6D5451FD)),
+        ((0x243F6A88, 0x85A308D3, 0x13198A2E, 0x03707344), (0xA4093822, 0x299F31D0),
+         (0xD16CFE09, 0x94FDCCEB, 0x5001E420, 0x24126EA1)),
+    ]
+    for counter, key, want in kat:
+        got = philox.philox4x32_10(np.array(counter, dtype=np.uint64)[None], key)[0]
+        assert tuple(int(v) for v in got) == want
+    z = philox.standard_normal(seed=20261020, offset=7, stream=0, count=400_000)
+    assert abs(z.mean()) < 5e-3 and abs(z.var() - 1.0) < 5e-3
+    assert abs((z ** 3).mean()) < 2e-2 and abs((z ** 4).mean() - 3.0) < 5e-2
+    # a variate is a function of (seed, offset, stream, i) only: offsets shift the sequence by two variates per count
+    z2 = philox.standard_normal(seed=20261020, offset=8, stream=0, count=100)
+    assert np.array_equal(z2, z[2:102])
+    assert not np.array_equal(philox.standard_normal(20261020, 7, 1, 100), z[:100])
