@@ -20,12 +20,27 @@
 // the four-warps-per-series kernel of bkf_sqrt_bwd4.cuh, which reads the record the sweep leaves: per (series, step)
 // [a | a_f | v | s | inner | tiles of Rf^T | tiles of Rp^T] with the tiles exactly as they lie in the arena.
 #pragma once
+#include <cstdio>
+
 #include "bkf_common.cuh"
 
 namespace bkf {
 namespace sqw {
 
 constexpr unsigned FULL = 0xffffffffu;
+
+#ifndef BKF_PANEL  // the reflector loop of a panel: panel_reflectors (plain), panel_reflectors_la (look-ahead)
+#define BKF_PANEL panel_reflectors_la
+#endif
+
+#ifdef BKF_SQW_PROFILE  // clock64 phase timers of block 0 (tools/build_variant.py sqwprof "-DBKF_SQW_PROFILE" ...)
+__device__ unsigned long long g_prof[8];
+#define BKF_PTICK() const long long _pt0 = clock64()
+#define BKF_PTOCK(i) do { if (blockIdx.x == 0 && (threadIdx.x & 31) == 0) g_prof[i] += (unsigned long long)(clock64() - _pt0); } while (0)
+#else
+#define BKF_PTICK() do { } while (0)
+#define BKF_PTOCK(i) do { } while (0)
+#endif
 
 __device__ __forceinline__ void dmma(double& c0, double& c1, double a, double b) {
     asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
@@ -110,30 +125,72 @@ __device__ __forceinline__ int elem_addr(int i, int j, int WT) {
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// One panel (8 columns, NQ active row blocks, the diagonal block first) of the Householder sweep and its trailing update.
-// tile(jt, rt) -> tile index.  The reflector loop is rolled (runtime k): see qr_tiles.
-template <int NQ, int WT, class ColF>
-__device__ __forceinline__ void qr_panel(double* __restrict__ S, double* __restrict__ tq, const int jt, const int np,
-                                         const int row0, ColF colf, const int lane) {
+// Sum over the four lanes of a group on the FP64 tensor pipe: in the m8n8k4 fragments lane (g, t) holds A[g][t], so
+// A x ones hands every lane of group g the group's sum -- one DMMA (26 cycles) instead of two shuffle + add rounds (70).
+__device__ __forceinline__ double red4_mma(double x) {
+    double c0 = 0.0, c1 = 0.0;
+    dmma(c0, c1, x, 1.0);
+    return c0;
+}
+
+// Scalars of one Householder reflector (dlarfg) from x2 = alpha^2 + |x|^2:
+//   beta = -sign(alpha) nrm,  tau = (beta - alpha) / beta = (|alpha| + nrm) / nrm,  scal = 1 / (alpha - beta).
+// 1 / sqrt and 1 / x come from the 20-bit hardware seeds and two Newton steps each (a quarter of the instructions and half
+// the latency of the IEEE sequences: measured dependent latencies sqrt 91, div 71 cycles).  The reciprocal of
+// |alpha| + nrm starts from a seed taken at the rsqrt SEED's accuracy (both seeds carry ~20 bits, two Newton steps each
+// reach full precision), so the second hardware approximation overlaps the Newton steps of the first.
+// (x2 subnormal, a column of magnitude < 1e-154, is out of range.)
+struct Refl {
+    double beta, tau, scal, ts;
+};
+__device__ __forceinline__ Refl reflector(const double x2, const double alpha) {
+    const double aa = fabs(alpha);
+    double rn, r0;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(rn) : "d"(x2));
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r0) : "d"(fma(x2, rn, aa)));
+    const double hx = 0.5 * x2;
+    rn = fma(rn, fma(-hx * rn, rn, 0.5), rn);
+    rn = fma(rn, fma(-hx * rn, rn, 0.5), rn);
+    const double nrm = x2 * rn;
+    const double den = aa + nrm;
+    r0 = fma(r0, fma(-den, r0, 1.0), r0);
+    const double rden = fma(r0, fma(-den, r0, 1.0), r0);
+    Refl R;
+    R.beta = copysign(nrm, -alpha);
+    R.tau = den * rn;
+    R.scal = copysign(rden, alpha);
+    R.ts = R.tau * R.scal;
+    return R;
+}
+
+// The eight reflectors of one panel (NQ active row blocks, the diagonal block first; lane group g owns column g, lane
+// (g, t) its rows 2t, 2t+1 of every block).  Per reflector: the pivot column goes through 64 NQ bytes of shared memory
+// to every group (NQ stores by four lanes + NQ broadcast loads: a quarter of the MIO slots of 4 NQ shuffles, which cost
+// 4.3 cycles each), ONE reduction window -- a DMMA against ones -- yields the pivot norm, the eight v^T a_c AND, in the
+// groups whose reflector is finished, the inner products v_i^T v_k of the compact-WY Gram matrix (same formula, free).
+// On return pa holds V^T (unit diagonal, scaled), Rd the diagonal tile of R, tq[8 i + l] = v_i^T v_l (i < l).
+// scratch: xb = 8 NQ doubles.
+template <int NQ>
+__device__ __forceinline__ void panel_reflectors(double2 (&pa)[NQ], double2& Rd, double& tauv, double* tq, double* xbuf,
+                                                 const int lane) {
+    // (no __restrict__ on xbuf: the compiler would forward a lane's own conditional stores to its loads across the
+    //  __syncwarp and never see the pivot group's)
     const int g = lane >> 2, t = lane & 3;
-    // tile (column block j, active row block q) = (row0 + j) * WT + col[q]: the column part is fixed for the panel
-    int col[NQ];
-#pragma unroll
-    for (int q = 0; q < NQ; ++q) col[q] = colf(jt + q);
-    auto tile = [&](int j, int rt) { return (row0 + j) * WT + col[rt - jt]; };
-    double2 pa[NQ];
-#pragma unroll
-    for (int q = 0; q < NQ; ++q) pa[q] = ldt(S, tile(jt, jt + q), lane);
-    double tauv = 0.0, scalv = 1.0;  // tau and 1 / (alpha - beta) of the reflector of column g (tau = 0: H = I)
+    tauv = 0.0;
+    double scalv = 1.0;  // tau and 1 / (alpha - beta) of the reflector of column g (tau = 0: H = I)
 #pragma unroll 2
     for (int k = 0; k < 8; ++k) {
-        // x = column k of the panel below its diagonal, handed to every group (lane (k, t) -> lanes (*, t))
+        // x = column k of the panel below its diagonal, handed to every group
+        if (g == k) {
+#pragma unroll
+            for (int q = 0; q < NQ; ++q) reinterpret_cast<double2*>(xbuf)[q * 4 + t] = pa[q];
+        }
+        __syncwarp();
         double2 xb[NQ];
 #pragma unroll
-        for (int q = 0; q < NQ; ++q) {
-            xb[q].x = __shfl_sync(FULL, pa[q].x, 4 * k + t);
-            xb[q].y = __shfl_sync(FULL, pa[q].y, 4 * k + t);
-        }
+        for (int q = 0; q < NQ; ++q) xb[q] = reinterpret_cast<const double2*>(xbuf)[q * 4 + t];
+        const double alpha = xbuf[k];  // [row k][col k]
+        const double akc = __shfl_sync(FULL, (k & 1) ? pa[0].y : pa[0].x, 4 * g + (k >> 1));  // [row k][col g]
         double2 xm = xb[0];
         if (2 * t <= k) xm.x = 0.0;
         if (2 * t + 1 <= k) xm.y = 0.0;
@@ -143,46 +200,30 @@ __device__ __forceinline__ void qr_panel(double* __restrict__ S, double* __restr
             d0 = fma(xb[q].x, pa[q].x, d0);
             d1 = fma(xb[q].y, pa[q].y, d1);
         }
-        // one reduction window: group k -> ss = x.x; group c > k -> x.a_c
-        const double dot = red_t(d0 + d1);
+        const double dsum = d0 + d1;
+        // |x|^2 != 0 (a sum of squares in group k); the vote also orders the loads of xbuf before its next stores
+        const bool nz = __any_sync(FULL, g == k && dsum != 0.0);
+        if (!nz) {  // dlarfg: tau = 0, H = I
+            if (g < k && t == 0) tq[g * 8 + k] = 0.0;
+            continue;
+        }
+        // one reduction window: group k -> ss = x.x; group c > k -> x.a_c; group i < k -> x_i.x_k
+        const double dot = red4_mma(dsum);
         const double ss = __shfl_sync(FULL, dot, 4 * k);
-        const double akc = __shfl_sync(FULL, (k & 1) ? pa[0].y : pa[0].x, 4 * g + (k >> 1));  // [row k][col g]
-        const double alpha = __shfl_sync(FULL, akc, 4 * k);
-        if (ss == 0.0) continue;  // dlarfg: tau = 0, H = I
-        // beta = -sign(alpha) nrm,  tau = (beta - alpha) / beta = (|alpha| + nrm) / nrm,  scal = 1 / (alpha - beta).
-        // 1 / sqrt and 1 / x come from the 20-bit hardware seeds and two Newton steps each (a quarter of the instructions
-        // and half the latency of the IEEE sequences: measured dependent latencies sqrt 91, div 71 cycles).
-        // Serial chain of the reflector, kept as short as it goes: the reciprocal of |alpha| + nrm starts from a seed
-        // taken at the rsqrt SEED's accuracy (both seeds carry ~20 bits, two Newton steps each reach full precision), so
-        // the second hardware approximation overlaps the Newton steps of the first instead of waiting for nrm.
-        const double x2 = fma(alpha, alpha, ss);  // (x2 subnormal, a column of magnitude < 1e-154, is out of range)
-        const double aa = fabs(alpha);
-        double rn, r0;
-        asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(rn) : "d"(x2));
-        asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r0) : "d"(fma(x2, rn, aa)));
-        const double hx = 0.5 * x2;
-        rn = fma(rn, fma(-hx * rn, rn, 0.5), rn);
-        rn = fma(rn, fma(-hx * rn, rn, 0.5), rn);
-        const double nrm = x2 * rn;
-        const double den = aa + nrm;
-        r0 = fma(r0, fma(-den, r0, 1.0), r0);
-        const double rden = fma(r0, fma(-den, r0, 1.0), r0);
-        const double beta = copysign(nrm, -alpha);
-        const double tau = den * rn;
-        const double scal = copysign(rden, alpha);
-        const double ts = tau * scal;
-        const double zz = fma(scal, dot, akc);  // v_k . a_c  (c > k)
+        const Refl R = reflector(fma(alpha, alpha, ss), alpha);
+        const double zz = fma(R.scal, dot, akc);  // v_k . a_c (c > k);  scal_i zz = v_i . v_k (i < k)
+        if (g < k && t == 0) tq[g * 8 + k] = scalv * zz;
         // Update with the UNSCALED reflector u = [alpha - beta; x] (v = u scal):  a_c -= (tau zz scal) u  for c > k.
         // The pivot column keeps x until the sweep of the panel is over (nothing reads v before) and is scaled once.
         const bool piv = g == k;
-        const double w = g > k ? ts * zz : 0.0;
+        const double w = g > k ? R.ts * zz : 0.0;
         double2 ud = xm;  // u on my rows of the diagonal block
-        if (2 * t == k) ud.x = alpha - beta;
-        if (2 * t + 1 == k) ud.y = alpha - beta;
+        if (2 * t == k) ud.x = alpha - R.beta;
+        if (2 * t + 1 == k) ud.y = alpha - R.beta;
         {
             const double nx = fma(-w, ud.x, pa[0].x), ny = fma(-w, ud.y, pa[0].y);
-            pa[0].x = (piv && 2 * t == k) ? beta : nx;
-            pa[0].y = (piv && 2 * t + 1 == k) ? beta : ny;
+            pa[0].x = (piv && 2 * t == k) ? R.beta : nx;
+            pa[0].y = (piv && 2 * t + 1 == k) ? R.beta : ny;
         }
 #pragma unroll
         for (int q = 1; q < NQ; ++q) {
@@ -190,86 +231,265 @@ __device__ __forceinline__ void qr_panel(double* __restrict__ S, double* __restr
             pa[q].y = fma(-w, xb[q].y, pa[q].y);
         }
         if (piv) {
-            tauv = tau;
-            scalv = scal;
+            tauv = R.tau;
+            scalv = R.scal;
         }
     }
-    // R goes back to the array (zeros below the diagonal); V^T = (x scal)^T with unit diagonal stays in registers (in pa)
-    {
-        const double2 r = pa[0];
-        stt(S, tile(jt, jt), lane, make_double2(2 * t <= g ? r.x : 0.0, 2 * t + 1 <= g ? r.y : 0.0));
-        pa[0].x = 2 * t > g ? r.x * scalv : (2 * t == g ? 1.0 : 0.0);
-        pa[0].y = 2 * t + 1 > g ? r.y * scalv : (2 * t + 1 == g ? 1.0 : 0.0);
-    }
+    // R (zeros below the diagonal) and V^T = (x scal)^T with unit diagonal
+    const double2 r = pa[0];
+    Rd = make_double2(2 * t <= g ? r.x : 0.0, 2 * t + 1 <= g ? r.y : 0.0);
+    pa[0].x = 2 * t > g ? r.x * scalv : (2 * t == g ? 1.0 : 0.0);
+    pa[0].y = 2 * t + 1 > g ? r.y * scalv : (2 * t + 1 == g ? 1.0 : 0.0);
 #pragma unroll
     for (int q = 1; q < NQ; ++q) {
         pa[q].x *= scalv;
         pa[q].y *= scalv;
-        stt(S, tile(jt, jt + q), lane, zero2());
     }
-    if (jt + 1 < np) {
-        // Compact-WY factor (dlarft) from the Gram matrix of the reflectors:  T^{-1} = striu(V^T V) + diag(1 / tau), so
-        // column j of T solves  x_i = tau_i (delta_ij - sum_{l > i} G_il x_l)  by back substitution -- no division, a
-        // reflector with tau = 0 gives a zero row and column.  G = V^T V is two short DMMA chains; group j solves column j
-        // with broadcast reads of G (all lanes read the same word).  Doing this once per panel instead of one
-        // three-stage shuffle reduction per reflector takes the T factor off the serial reflector chain.
-        double2 tt;  // T^T in C layout: lane (g = j, t) holds T[2t][j], T[2t+1][j]
-        {
-            double2 ga = zero2(), gb = zero2();
+}
+
+// The panel with BOTH serial pieces taken off the data path (measured on the C4 shape: broadcast of the pivot column
+// 137, reflector scalars 117, zero-column vote + branch 70, norm shuffle 34 of 525 cycles per reflector):
+//   * every lane keeps a private copy x of the CURRENT pivot column (its rows 2t, 2t+1).  The column after it travels
+//     through shared memory one reflector EARLY -- group k + 2 stores its column right after update k, everybody loads it
+//     during window k + 1 -- and turns into the next x by the same rank-one update the owning group applies
+//     (x_{k+1} = y - w_{k+1} u_k, bit-identical to the owner's), so no store -> load round trip sits between an update and
+//     the inner products of the next reflector;
+//   * the scalars of reflector k + 1 (rsqrt, reciprocal, Newton steps) need only |a_{k+1}[rows >= k+1]|^2 and the pivot
+//     element, and both are known as soon as the coefficient w of reflector k is: H_k is orthogonal on rows >= k, so the
+//     squared norm of every remaining column shrinks by exactly R[k][c]^2 (the partial-norm downdate of xGEQP3), and the
+//     new pivot element is one FMA.  Every lane evaluates them redundantly (no broadcast on the chain), so the scalar
+//     chain of reflector k + 1 runs beside window k + 1 instead of behind it.  Downdated norms lose digits when a column
+//     is nearly in the span of the earlier ones: a column whose remaining norm^2 fell below 2^-6 of its explicit value
+//     at the start of the panel takes the explicit norm from the window (bound: 8 downdates x 64 x a few ulps, < 1e-13
+//     relative on the norm); exact zero columns -- dlarfg's tau = 0 -- are detected on the explicit partial sums, and
+//     both tests are votes whose results are only selected at the join (no branch on the chain).
+// Measured (tools/refl_bench.cu, one warp per scheduler): 528 -> 408 cycles per reflector at six row blocks; what is left
+// is the warp's own issue time (~60 FP64 instructions at two cycles each, 14 shared-memory and 10 shuffle instructions).
+// Scratch: xbuf = 2 x 8 NQ doubles (double buffer of the travelling column).
+template <int NQ>
+__device__ __forceinline__ void panel_reflectors_la(double2 (&pa)[NQ], double2& Rd, double& tauv, double* tq,
+                                                    double* xbuf, const int lane) {
+    const int g = lane >> 2, t = lane & 3;
+    tauv = 0.0;
+    double scalv = 1.0;
+    double n2;  // |a_g[rows >= k]|^2: explicit at k = 0, then downdated by R[k][g]^2
+    {
+        double s0 = pa[0].x * pa[0].x, s1 = pa[0].y * pa[0].y;
 #pragma unroll
-            for (int q = 0; q < NQ; ++q) {
-                dmma(ga.x, ga.y, pa[q].x, pa[q].x);
-                dmma(gb.x, gb.y, pa[q].y, pa[q].y);
-            }
-            reinterpret_cast<double2*>(tq)[lane] = make_double2(ga.x + gb.x, ga.y + gb.y);  // G, row-major 8 x 8
-            if (t == 0) tq[64 + g] = tauv;
-            __syncwarp();
-            double x[8];
-#pragma unroll
-            for (int i = 7; i >= 0; --i) {
-                double acc = 0.0;
-#pragma unroll
-                for (int l = 7; l > i; --l) acc = fma(tq[i * 8 + l], x[l], acc);
-                const double ti = tq[64 + i];
-                x[i] = i == g ? ti : (i < g ? -ti * acc : 0.0);
-            }
-            tt.x = t == 0 ? x[0] : (t == 1 ? x[2] : (t == 2 ? x[4] : x[6]));
-            tt.y = t == 0 ? x[1] : (t == 1 ? x[3] : (t == 2 ? x[5] : x[7]));
-            __syncwarp();
+        for (int q = 1; q < NQ; ++q) {
+            s0 = fma(pa[q].x, pa[q].x, s0);
+            s1 = fma(pa[q].y, pa[q].y, s1);
         }
+        n2 = red4_mma(s0 + s1);
+    }
+    const double n2ref = n2 * (1.0 / 64.0);
+    double2* xb2 = reinterpret_cast<double2*>(xbuf);
+    constexpr int XS = 4 * NQ;  // double2 per buffer
+    // columns 0 and 1 as they are
+    if (g < 2) {
+#pragma unroll
+        for (int q = 0; q < NQ; ++q) xb2[g * XS + q * 4 + t] = pa[q];
+    }
+    __syncwarp();
+    double2 x[NQ];
+#pragma unroll
+    for (int q = 0; q < NQ; ++q) x[q] = xb2[q * 4 + t];
+    double alpha = xbuf[0];
+    Refl R = reflector(__shfl_sync(FULL, n2, 0), alpha);
+#pragma unroll 2
+    for (int k = 0; k < 8; ++k) {
+        const int kn = (k + 1) & 7;  // the next pivot (k = 7: results unused)
+        const double2* yb = xb2 + (kn & 1) * XS;
+        double2 y[NQ];
+#pragma unroll
+        for (int q = 0; q < NQ; ++q) y[q] = yb[q * 4 + t];
+        const double akn = reinterpret_cast<const double*>(yb)[k];   // [row k][col k+1]
+        const double ann = reinterpret_cast<const double*>(yb)[kn];  // [row k+1][col k+1]
+        const double akc = __shfl_sync(FULL, (k & 1) ? pa[0].y : pa[0].x, 4 * g + (k >> 1));  // [row k][col g]
+        const double xkn = __shfl_sync(FULL, (kn & 1) ? x[0].y : x[0].x, 4 * g + (kn >> 1));  // [row k+1][col k]
+        const double n2n = __shfl_sync(FULL, n2, 4 * kn);
+        double2 xm = x[0];
+        if (2 * t <= k) xm.x = 0.0;
+        if (2 * t + 1 <= k) xm.y = 0.0;
+        double d0 = xm.x * pa[0].x, d1 = xm.y * pa[0].y;
+#pragma unroll
+        for (int q = 1; q < NQ; ++q) {
+            d0 = fma(x[q].x, pa[q].x, d0);
+            d1 = fma(x[q].y, pa[q].y, d1);
+        }
+        const double dsum = d0 + d1;
+        const bool nz = __any_sync(FULL, g == k && dsum != 0.0);     // |x|^2 != 0 (a sum of squares in group k)
+        const bool low = __any_sync(FULL, g == k && !(n2 >= n2ref));  // the downdated norm lost too many digits
+        const double dot = red4_mma(dsum);
+        const double dn = __shfl_sync(FULL, dot, 4 * kn);
+        if (low) {
+            const double ss = __shfl_sync(FULL, dot, 4 * k);
+            R = reflector(fma(alpha, alpha, ss), alpha);
+        }
+        // dlarfg: tau = 0, H = I when the column below the pivot is exactly zero
+        const double ts = nz ? R.ts : 0.0, tau = nz ? R.tau : 0.0, beta = nz ? R.beta : alpha, scal = nz ? R.scal : 1.0;
+        const double amb = alpha - beta;
+        const double zz = fma(scal, dot, akc);  // v_k . a_c (c > k);  scal_i zz = v_i . v_k (i < k)
+        if (g < k && t == 0) tq[g * 8 + k] = nz ? scalv * zz : 0.0;
+        const bool piv = g == k;
+        const double w = g > k ? ts * zz : 0.0;
+        // the next reflector, in every lane: w, R[k][k+1], downdated norm and pivot element of column k + 1
+        const double wn = ts * fma(scal, dn, akn);
+        const double rkn = fma(-wn, amb, akn);
+        const double x2n = fma(-rkn, rkn, n2n);
+        const double alphan = fma(-wn, xkn, ann);
+        {
+            const double rkc = fma(-w, amb, akc);  // R[k][g]
+            n2 = fma(-rkc, rkc, n2);
+        }
+        double2 ud = xm;  // u on my rows of the diagonal block
+        if (2 * t == k) ud.x = amb;
+        if (2 * t + 1 == k) ud.y = amb;
+        {
+            const double nx = fma(-w, ud.x, pa[0].x), ny = fma(-w, ud.y, pa[0].y);
+            pa[0].x = (piv && 2 * t == k) ? beta : nx;
+            pa[0].y = (piv && 2 * t + 1 == k) ? beta : ny;
+        }
+#pragma unroll
+        for (int q = 1; q < NQ; ++q) {
+            pa[q].x = fma(-w, x[q].x, pa[q].x);
+            pa[q].y = fma(-w, x[q].y, pa[q].y);
+        }
+        // the column after the next one starts its trip (its owner is up to date through reflector k)
+        if (g == ((k + 2) & 7)) {
+#pragma unroll
+            for (int q = 0; q < NQ; ++q) xb2[(k & 1) * XS + q * 4 + t] = pa[q];
+        }
+        // x <- column k + 1 after reflector k
+        {
+            const double2 x0 = make_double2(fma(-wn, ud.x, y[0].x), fma(-wn, ud.y, y[0].y));
+#pragma unroll
+            for (int q = 1; q < NQ; ++q) {
+                x[q].x = fma(-wn, x[q].x, y[q].x);
+                x[q].y = fma(-wn, x[q].y, y[q].y);
+            }
+            x[0] = x0;
+        }
+        if (piv) {
+            tauv = tau;
+            scalv = scal;
+        }
+        alpha = alphan;
+        R = reflector(x2n, alphan);
+        __syncwarp();
+    }
+    const double2 r = pa[0];
+    Rd = make_double2(2 * t <= g ? r.x : 0.0, 2 * t + 1 <= g ? r.y : 0.0);
+    pa[0].x = 2 * t > g ? r.x * scalv : (2 * t == g ? 1.0 : 0.0);
+    pa[0].y = 2 * t + 1 > g ? r.y * scalv : (2 * t + 1 == g ? 1.0 : 0.0);
+#pragma unroll
+    for (int q = 1; q < NQ; ++q) {
+        pa[q].x *= scalv;
+        pa[q].y *= scalv;
+    }
+}
+
+// Compact-WY factor (dlarft) from the Gram matrix of the reflectors:  T^{-1} = striu(V^T V) + diag(1 / tau), so column j
+// of T solves  x_i = tau_i (delta_ij - sum_{l > i} G_il x_l)  by back substitution -- no division, a reflector with
+// tau = 0 gives a zero row and column.  Group j solves column j with broadcast reads of G; the sums are kept per row
+// and advanced as soon as an x_l is known (two dependent operations per level).  Returns T^T in C layout: lane
+// (g = j, t) holds T[2t][j], T[2t+1][j].  tq: G (64, written by panel_reflectors) + tau (8).
+__device__ __forceinline__ double2 t_factor(double* __restrict__ tq, const double tauv, const int lane) {
+    const int g = lane >> 2, t = lane & 3;
+    if (t == 0) tq[64 + g] = tauv;
+    __syncwarp();
+    double x[8], sacc[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) sacc[i] = 0.0;
+#pragma unroll
+    for (int i = 7; i >= 0; --i) {
+        const double ti = tq[64 + i];
+        x[i] = i == g ? ti : (i < g ? -ti * sacc[i] : 0.0);
+#pragma unroll
+        for (int l = 0; l < i; ++l) sacc[l] = fma(tq[l * 8 + i], x[i], sacc[l]);
+    }
+    double2 tt;
+    tt.x = t == 0 ? x[0] : (t == 1 ? x[2] : (t == 2 ? x[4] : x[6]));
+    tt.y = t == 0 ? x[1] : (t == 1 ? x[3] : (t == 2 ? x[5] : x[7]));
+    __syncwarp();
+    return tt;
+}
+
+// (A^T V) block of one column block: independent accumulator chains (even / odd q, first / second k-half)
+template <int NQ>
+__device__ __forceinline__ double2 block_w(const double2 (&c)[NQ], const double2 (&pa)[NQ]) {
+    double2 wa = zero2(), wb = zero2(), wc = zero2(), wd = zero2();
+#pragma unroll
+    for (int q = 0; q < NQ; q += 2) {
+        dmma(wa.x, wa.y, c[q].x, pa[q].x);
+        if (q + 1 < NQ) dmma(wc.x, wc.y, c[q + 1 < NQ ? q + 1 : q].x, pa[q + 1 < NQ ? q + 1 : q].x);
+        dmma(wb.x, wb.y, c[q].y, pa[q].y);
+        if (q + 1 < NQ) dmma(wd.x, wd.y, c[q + 1 < NQ ? q + 1 : q].y, pa[q + 1 < NQ ? q + 1 : q].y);
+    }
+    return make_double2((wa.x + wb.x) + (wc.x + wd.x), (wa.y + wb.y) + (wc.y + wd.y));
+}
+// A^T -= ((A^T V) T) V^T
+template <int NQ>
+__device__ __forceinline__ void block_apply(double2 (&c)[NQ], const double2 wt, const double2 tt, const double2 (&vv)[NQ]) {
+    double2 u0 = zero2(), u1 = zero2();  // (A^T V) T
+    dmma(u0.x, u0.y, wt.x, tt.x);
+    dmma(u1.x, u1.y, wt.y, tt.y);
+    const double2 ut = make_double2(-(u0.x + u1.x), -(u0.y + u1.y));
+    // first k-halves of every tile, then the second halves
+#pragma unroll
+    for (int q = 0; q < NQ; ++q) dmma(c[q].x, c[q].y, ut.x, vv[q].x);
+#pragma unroll
+    for (int q = 0; q < NQ; ++q) dmma(c[q].x, c[q].y, ut.y, vv[q].y);
+}
+
+// One panel (8 columns, NQ active row blocks, the diagonal block first) of the Householder sweep and its trailing update.
+// tile(jt, rt) -> tile index.  The reflector loop is rolled (runtime k): see qr_tiles.
+template <int NQ, int WT, class ColF>
+__device__ __forceinline__ void qr_panel(double* __restrict__ S, double* __restrict__ tq, const int jt, const int np,
+                                         const int row0, ColF colf, const int lane) {
+    // tile (column block j, active row block q) = (row0 + j) * WT + col[q]: the column part is fixed for the panel
+    int col[NQ];
+#pragma unroll
+    for (int q = 0; q < NQ; ++q) col[q] = colf(jt + q);
+    auto tile = [&](int j, int rt) { return (row0 + j) * WT + col[rt - jt]; };
+    double2 pa[NQ];
+#pragma unroll
+    for (int q = 0; q < NQ; ++q) pa[q] = ldt(S, tile(jt, jt + q), lane);
+    double tauv;
+    double2 Rd;
+    {
+        BKF_PTICK();
+        BKF_PANEL<NQ>(pa, Rd, tauv, tq, tq + 72, lane);
+        BKF_PTOCK(0);
+    }
+    BKF_PTICK();
+    stt(S, tile(jt, jt), lane, Rd);
+#pragma unroll
+    for (int q = 1; q < NQ; ++q) stt(S, tile(jt, jt + q), lane, zero2());
+    if (jt + 1 < np) {
+        // the first column block's A^T V does not need T: its DMMA chains run beside the back substitution
+        double2 c[NQ];
+#pragma unroll
+        for (int q = 0; q < NQ; ++q) c[q] = ldt(S, tile(jt + 1, jt + q), lane);
+        double2 wt = block_w<NQ>(c, pa);
+        const double2 tt = t_factor(tq, tauv, lane);
         double2 vv[NQ];
 #pragma unroll
         for (int q = 0; q < NQ; ++q) vv[q] = ttrans(pa[q], lane);
+        BKF_PTOCK(1);
 #pragma unroll 1
-        for (int j2 = jt + 1; j2 < np; ++j2) {
-            double2 c[NQ];
+        for (int j2 = jt + 1;;) {
+            block_apply<NQ>(c, wt, tt, vv);
+#pragma unroll
+            for (int q = 0; q < NQ; ++q) stt(S, tile(j2, jt + q), lane, c[q]);
+            if (++j2 >= np) break;
 #pragma unroll
             for (int q = 0; q < NQ; ++q) c[q] = ldt(S, tile(j2, jt + q), lane);
-            // (A^T V) block: independent accumulator chains (even / odd q, first / second k-half)
-            double2 wa = zero2(), wb = zero2(), wc = zero2(), wd = zero2();
-#pragma unroll
-            for (int q = 0; q < NQ; q += 2) {
-                dmma(wa.x, wa.y, c[q].x, pa[q].x);
-                if (q + 1 < NQ) dmma(wc.x, wc.y, c[q + 1 < NQ ? q + 1 : q].x, pa[q + 1 < NQ ? q + 1 : q].x);
-                dmma(wb.x, wb.y, c[q].y, pa[q].y);
-                if (q + 1 < NQ) dmma(wd.x, wd.y, c[q + 1 < NQ ? q + 1 : q].y, pa[q + 1 < NQ ? q + 1 : q].y);
-            }
-            const double2 wt = make_double2((wa.x + wb.x) + (wc.x + wd.x), (wa.y + wb.y) + (wc.y + wd.y));
-            double2 u0 = zero2(), u1 = zero2();  // (A^T V) T
-            dmma(u0.x, u0.y, wt.x, tt.x);
-            dmma(u1.x, u1.y, wt.y, tt.y);
-            const double2 ut = make_double2(-(u0.x + u1.x), -(u0.y + u1.y));
-            // A^T -= (A^T V T) V^T : first k-halves of every tile, then the second halves
-#pragma unroll
-            for (int q = 0; q < NQ; ++q) dmma(c[q].x, c[q].y, ut.x, vv[q].x);
-#pragma unroll
-            for (int q = 0; q < NQ; ++q) {
-                dmma(c[q].x, c[q].y, ut.y, vv[q].y);
-                stt(S, tile(j2, jt + q), lane, c[q]);
-            }
+            wt = block_w<NQ>(c, pa);
         }
     }
     __syncwarp();
+    BKF_PTOCK(2);
 }
 
 // Householder R factor of an array stored transposed in tiles (element [col][row] in C layout).  Two arrays share the
@@ -283,6 +503,7 @@ __device__ __forceinline__ void qr_panel(double* __restrict__ S, double* __restr
 template <int NRMAX, int MT, int PT, int WT>
 __device__ __noinline__ void qr_tiles(double* __restrict__ S, double* __restrict__ tq, const int np, const int nr,
                                       const bool predict, const int lane) {
+    static_assert(NRMAX <= 6, "the travelling-column buffer of panel_reflectors_la holds six row blocks (Dims::FWD_ELEMS)");
     const int row0 = predict ? PT : 0;
     auto colf = [&](int rt) { return predict ? (rt < MT ? PT + rt : rt - MT) : rt; };
 #pragma unroll 1
@@ -326,8 +547,8 @@ struct Dims {
     static constexpr int HC = RQ + MT * RT * 64;    // Hc, PT x PT tiles
     static constexpr int VA = HC + PT * PT * 64;    // vectors
     static constexpr int V_a = VA, V_af = V_a + m, V_c = V_af + m, V_d = V_c + m, V_v = V_d + p, V_sv = V_v + p,
-                         V_in = V_sv + p, V_w = V_in + p, V_ym = V_w + p, V_tq = V_ym + p;  // V_tq: Gram tile + taus (72)
-    static constexpr int FWD_ELEMS = V_tq + 72;
+                         V_in = V_sv + p, V_w = V_in + p, V_ym = V_w + p, V_tq = V_ym + p;  // V_tq: Gram tile + taus (72), travelling columns (2 x 48)
+    static constexpr int FWD_ELEMS = V_tq + 72 + 96;
 };
 
 // In-place lower Cholesky of a k x k row-major matrix in shared memory by one warp; the upper triangle is zeroed.
@@ -444,6 +665,7 @@ __global__ void __launch_bounds__(32) forward_kernel(KArgs<double> G) {
     constexpr size_t off_rf = (size_t)(2 * m + 3 * p), off_rp = off_rf + (size_t)NTRI1 * 64, tstride = off_rp + (size_t)NTRIP * 64;
     double logp = 0.0;
     for (int ts = 0; ts < n; ++ts) {
+        BKF_PTICK();
         const size_t bt = (size_t)b * n + ts;
         double* rec = G.traj ? G.traj + bt * tstride : nullptr;
         // ---- mask, innovation ----
@@ -634,7 +856,14 @@ __global__ void __launch_bounds__(32) forward_kernel(KArgs<double> G) {
                 for (int K = I; K < MT; ++K, ++idx)
                     reinterpret_cast<double2*>(rec + off_rp)[idx * 32 + lane] = ldt(SA, D::pc_tile(K, I), lane);
         }
+        BKF_PTOCK(3);
     }
+#ifdef BKF_SQW_PROFILE
+    if (b == 0 && lane == 0)
+        printf("sqw profile (cycles per step): reflectors %llu  T-factor+store %llu  (with trailing %llu)  step %llu\n",
+               g_prof[0] / n, g_prof[1] / n, g_prof[2] / n, g_prof[3] / n);
+    if (b == 0 && lane == 0) g_prof[0] = g_prof[1] = g_prof[2] = g_prof[3] = 0;
+#endif
     if (lane == 0) {
         if (!isfinite(logp)) st |= BKF_STATUS_NONFINITE;
         if (G.logp) G.logp[b] = logp;

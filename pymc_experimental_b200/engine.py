@@ -15,7 +15,7 @@ import weakref
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libbkf.so")
+LIB_PATH = os.path.join(_HERE, os.environ.get("BKF_LIB", "libbkf.so"))  # BKF_LIB: a tools/build_variant.py build
 
 STANDARD, UNIVARIATE, CHOLESKY = 0, 1, 2
 KINDS = {"standard": STANDARD, "univariate": UNIVARIATE, "cholesky": CHOLESKY}

@@ -17,9 +17,12 @@ def timing():
     sys.path.insert(0, ROOT)
     import torch
 
+    from pymc_experimental_b200 import engine as _eng
     from pymc_experimental_b200 import synth
     from pymc_experimental_b200.engine import KalmanEngine
 
+    if os.environ.get("DBG_LIB"):
+        _eng.LIB_PATH = os.path.join(os.path.dirname(_eng.LIB_PATH), os.environ["DBG_LIB"])
     eng = KalmanEngine(0)
     B, n = int(os.environ.get("DBG_B", 512)), int(os.environ.get("DBG_T", 200))
     cfg = synth.varmax(B, n)
