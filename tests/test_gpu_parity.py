@@ -553,6 +553,78 @@ def test_compact_parameterisation_equals_the_dense_call(eng, device):
                               np.concatenate([u, u[:, :1]], axis=1) if not device else torch.cat([uu, uu[:, :1]], 1))
 
 
+@pytest.mark.parametrize("device", [False, True])
+def test_theta_program_equals_the_compact_call_chained_by_hand(eng, device):
+    """The rest of row f-1 (bkf_filter_logp_grad_theta): the free parameters go in, the entries are evaluated and the chain
+    rule applied on the device.  SARIMA(1,1,1)x(1,0,1,12) (models/SARIMAX.py:404-458): logp equals the compact call fed with
+    u(theta) from the NumPy restatement of the program, g_theta = J^T g_u."""
+    import torch
+
+    from oracle import kalman_torch as oth
+    from pymc_experimental_b200 import synth, theta_maps
+
+    B, n = 23, 60
+    cfg = synth.sarima(B=1, n=n)
+    base = {k: np.array(cfg[k][0]) for k in NAMES}
+    positions, terms, ntheta = theta_maps.sarima_111_101_12()
+    rng = np.random.default_rng(77)
+    theta = np.column_stack([rng.uniform(-0.8, 0.8, B), rng.uniform(-0.8, 0.8, B), rng.uniform(-0.5, 0.5, B),
+                             rng.uniform(-0.5, 0.5, B), np.exp(rng.normal(0.0, 0.3, B))])
+    u = theta_maps.evaluate(terms, theta, len(positions))
+    J = theta_maps.jacobian(terms, theta, len(positions))
+    cot = rng.standard_normal((B, n))
+    wrap = (lambda a: torch.as_tensor(np.ascontiguousarray(a), device="cuda:0")) if device else (lambda a: a)
+    to_np = lambda x: x.cpu().numpy() if device else x
+    y, bb = wrap(cfg["y"]), {k: wrap(v) for k, v in base.items()}
+    logp_c, g_u, st_c = eng.logp_grad_compact("univariate", y, bb, positions, wrap(u), ll_cotangent=wrap(cot))
+    logp_t, g_t, st_t = eng.logp_grad_theta("univariate", y, bb, positions, terms, wrap(theta), ll_cotangent=wrap(cot))
+    np.testing.assert_allclose(to_np(logp_t), to_np(logp_c), rtol=1e-13)
+    np.testing.assert_array_equal(to_np(st_t), to_np(st_c))
+    ref = np.einsum("bk,bkt->bt", to_np(g_u), J)
+    _close(to_np(g_t), ref, 1e-12, "g_theta")
+    # and against the dense call + the oracle's gradient for one draw
+    dense = {k: np.repeat(base[k][None], B, 0) for k in NAMES}
+    for k, (name, idx) in enumerate(positions):
+        dense[name][(slice(None), *idx)] = u[:, k]
+    ref_logp, _ = oth.logp_and_grad("univariate", cfg["y"], *[dense[k][:3] for k in NAMES])
+    logp_plain, _, _ = eng.logp_grad_theta("univariate", y, bb, positions, terms, wrap(theta), want_grad=False)
+    np.testing.assert_allclose(to_np(logp_plain)[:3], ref_logp, rtol=RTOL64)
+
+
+def test_theta_program_with_every_function_code(eng):
+    """cos / sin / exp / 1 - x / x^2 and three-factor terms: a stochastic cycle (models/structural.py:1220-1237) inside the
+    C3 structural model, plus an artificial entry that uses the remaining codes; central differences of the device's own
+    logp tie g_theta to the function it is the gradient of."""
+    from pymc_experimental_b200 import synth, theta_maps
+    from pymc_experimental_b200.engine import FN_EXP, FN_ID, FN_ONE_MINUS
+
+    B, n = 9, 50
+    cfg = synth.structural(B=1, n=n)
+    base = {k: np.array(cfg[k][0]) for k in NAMES}
+    positions, terms, ntheta = theta_maps.structural_cycle(first_state=13, shock=3)
+    positions = positions + [("H", (0, 0)), ("c", (0,))]
+    terms = terms + [(6, 0.5, [(3, FN_EXP), (4, FN_ONE_MINUS), (3, FN_EXP)]), (7, 0.1, [(4, FN_ID)]), (7, 0.05, [])]
+    ntheta = 5
+    rng = np.random.default_rng(5)
+    theta = np.column_stack([rng.uniform(0.7, 0.98, B), rng.uniform(0.1, 0.5, B), rng.normal(-1.0, 0.2, B),
+                             rng.normal(-1.0, 0.2, B), rng.uniform(0.1, 0.6, B)])
+    u = theta_maps.evaluate(terms, theta, len(positions))
+    J = theta_maps.jacobian(terms, theta, len(positions))
+    logp_c, g_u, _ = eng.logp_grad_compact("standard", cfg["y"], base, positions, u)
+    logp_t, g_t, st = eng.logp_grad_theta("standard", cfg["y"], base, positions, terms, theta)
+    assert (st == 0).all()
+    np.testing.assert_allclose(logp_t, logp_c, rtol=1e-12)
+    _close(g_t, np.einsum("bk,bkt->bt", g_u, J), 1e-11, "g_theta")
+    h = 1e-6
+    for j in range(ntheta):
+        e = np.zeros(ntheta)
+        e[j] = h
+        lp, _, _ = eng.logp_grad_theta("standard", cfg["y"], base, positions, terms, theta + e, want_grad=False)
+        lm, _, _ = eng.logp_grad_theta("standard", cfg["y"], base, positions, terms, theta - e, want_grad=False)
+        fd = (lp - lm) / (2 * h)
+        np.testing.assert_allclose(g_t[:, j], fd, rtol=2e-5, atol=2e-5 * np.abs(g_t).max())
+
+
 @pytest.mark.parametrize("shape", [(3, 1), (6, 3), (15, 1), (16, 4), (32, 16)])
 @pytest.mark.parametrize("device", [False, True])
 def test_stationary_initialisation_matches_the_oracle(eng, shape, device):
