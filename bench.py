@@ -530,6 +530,9 @@ def measure_workload(args, ctx, name, batch, T_arg, steps, with_cpu):
     dom = max((k for k in model if ktimes[k][1] > 0), key=lambda k: ktimes[k][0])
     dom_ms = ktimes[dom][0] / ktimes[dom][1]
     flops, bytes_ = model[dom]
+    if args.dtype == "f32":  # step_model counts float64 bytes
+        model = {k: (f, b_ // 2) for k, (f, b_) in model.items()}
+        bytes_ //= 2
     Bl = B / (len(halves) or 1)  # series per kernel launch (N > 1 runs the batch as two launches per kernel)
     ach_tf = flops * Bl * T / (dom_ms * 1e-3) / 1e12
     ach_gbs = bytes_ * Bl * T / (dom_ms * 1e-3) / 1e9
@@ -541,7 +544,7 @@ def measure_workload(args, ctx, name, batch, T_arg, steps, with_cpu):
     else:
         roof = {"bound": "hbm", "achieved": ach_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": ach_gbs / hbm_peak,
                 "traffic": None}
-    tr = ncu_traffic(name, dom, B, T)
+    tr = ncu_traffic(name, dom, B, T) if args.dtype == "f64" else None  # the captures are of the float64 kernels
     if tr is not None:
         roof["traffic"] = tr["bytes_per_launch"]
         roof["traffic_source"] = tr["source"]

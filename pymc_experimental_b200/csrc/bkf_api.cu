@@ -287,6 +287,10 @@ static int run_forward(bkf_handle* h, const KArgs<float>& g, const char** err) {
         h->path = "thread_f32";
         return tps::launch_any<float>(g, false, h->stream, err);
     }
+    if (!g.tv_mask && swf::supported(g.kind, g.m, g.p)) {
+        h->path = "subwarp_f32";
+        return swf::launch_f32(g, false, h->stream, err);
+    }
     h->path = "generic_warp";
     return gen::launch_forward<float>(g, h->stream, err);
 }
@@ -309,6 +313,7 @@ static int run_backward(bkf_handle* h, const KArgs<float>& g, const char** err) 
     h->launches += 1;
     if (g.kind == BKF_CHOLESKY) return sq::launch_backward<float>(g, h->stream, err);
     if (!g.tv_mask && tps::supported(g.kind, g.m, g.p)) return tps::launch_any<float>(g, true, h->stream, err);
+    if (!g.tv_mask && swf::supported(g.kind, g.m, g.p)) return swf::launch_f32(g, true, h->stream, err);
     return gen::launch_backward<float>(g, h->stream, err);
 }
 

@@ -31,6 +31,10 @@ int launch_f64(const KArgs<double>& g, bool backward, cudaStream_t stream, const
 bool smoother_supported(int m);
 int launch_smoother_f64(const KArgs<double>& g, double jitter0, int* ill, cudaStream_t stream, const char** err);
 }  // namespace sw
+namespace swf {  // the same kernels in float32, 5 <= m <= 16, p = 1 (bkf_subwarp_f32.cu)
+bool supported(int kind, int m, int p);
+int launch_f32(const KArgs<float>& g, bool backward, cudaStream_t stream, const char** err);
+}  // namespace swf
 namespace tc {  // FP64 tensor-core (DMMA) warp-per-series kernels, 9 <= m <= 16, p = 1 (bkf_mma.cu)
 bool supported(int kind, int m, int p);
 size_t traj_record_elems();

@@ -321,10 +321,38 @@ def test_float32_within_stated_bound(eng, kind):
     cfg = synth.structural(B=8, n=60)
     args = [cfg["y"]] + [cfg[k] for k in NAMES]
     logp, grads, _ = eng.logp_grad(kind, *args, dtype=np.float32, cov_jitter=1e-6)
+    assert eng.last_path == "subwarp_f32"  # m = 15: the float32 sub-warp kernels, not the generic fallback
     ref_logp, ref_g = oth.logp_and_grad(kind, *args, cov_jitter=1e-6)
     assert_allclose(logp, ref_logp, rtol=1e-3)
     for k in NAMES:
         _close(grads[k], ref_g[k], 1e-2, f"f32 d/d{k}")
+
+
+@pytest.mark.parametrize("kind", ["standard", "univariate"])
+@pytest.mark.parametrize("m", [5, 8, 9, 12, 16])
+def test_float32_subwarp_kernels_every_width(eng, kind, m):
+    """The float32 instantiation of the sub-warp family (bkf_subwarp.cuh with real = float; 8 lanes per series up to m = 8,
+    16 above), forward outputs and logp + gradients against the float64 oracle at the stated float32 bound (1e-3 / 1e-2;
+    the reference's own float32 tolerance is 1e-3, tests/statespace/test_kalman_filter.py:30-31), with missing values, an
+    asymmetric P0 (first-step ASYM path) and a batch that does not fill the last warp."""
+    from oracle import kalman_torch as oth
+    from pymc_experimental_b200 import synth
+
+    B, n = 11, 30
+    cfg = synth.random_dense(B, n, m, 1, 3, seed=900 + m, missing=0.1)
+    args = [cfg["y"]] + [cfg[k] for k in NAMES]
+    logp, grads, status = eng.logp_grad(kind, *args, dtype=np.float32, cov_jitter=1e-6)
+    assert eng.last_path == "subwarp_f32" and logp.dtype == np.float32
+    assert (status == 0).all()
+    ref_logp, ref_g = oth.logp_and_grad(kind, *args, cov_jitter=1e-6)
+    assert_allclose(logp, ref_logp, rtol=1e-3)
+    for k in NAMES:
+        _close(grads[k], ref_g[k], 1e-2, f"f32 m={m} d/d{k}")
+    res = eng.filter(kind, *args, dtype=np.float32, cov_jitter=1e-6)
+    ref = oth.kalman_filter(kind, *[__import__("torch").as_tensor(a) for a in args], cov_jitter=1e-6)
+    for name, r in zip(("filtered_states", "predicted_states", "observed_states", "filtered_covariances",
+                        "predicted_covariances", "observed_covariances", "loglike_obs"), ref):
+        _close(res[name], r.numpy(), 2e-3, f"f32 m={m} {name}")
 
 
 def test_filter_smooth_fused_call(eng):
