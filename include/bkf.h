@@ -253,6 +253,22 @@ int bkf_simulate(bkf_handle* h, const bkf_problem* prob, const void* a0, const v
                  const void* T, const void* Z, const void* R, const void* H, const void* Q, const void* z_x0,
                  const void* z_y0, const void* z_state, const void* z_obs, void* states, void* obs, int* status);
 
+/* ---- The one collective of the path (SURVEY.md section 8 rows b / e): draws and series are sharded over the GPUs of a box
+ * with no traffic during filtering; at the end every rank contributes its packed [logp | gradients] buffer to ONE NCCL
+ * all-gather over NVLink.  These entry points let a C caller do that without PyTorch (the Python host side issues the same
+ * collective through torch.distributed on the buffer libbkf wrote in place).  NCCL (libnccl.so.2) is loaded on first use;
+ * without it the calls return BKF_ERR_UNSUPPORTED and the rest of the library is unaffected.
+ *   rank 0:      bkf_comm_unique_id(id)           -> ship the 128 bytes to the other ranks by any means
+ *   every rank:  bkf_comm_init(h, world, rank, id) -> a communicator on h's device (one process per GPU)
+ *                bkf_comm_allgather(h, send, recv, count, dtype): recv[world * count] = concatenation over ranks of
+ *                send[count]; DEVICE pointers, enqueued on the handle's stream behind the kernels that produced send
+ *                bkf_comm_destroy(h)                (bkf_destroy does it too) */
+#define BKF_COMM_ID_BYTES 128
+int bkf_comm_unique_id(void* id);
+int bkf_comm_init(bkf_handle* h, int world, int rank, const void* id);
+int bkf_comm_allgather(bkf_handle* h, const void* send, void* recv, size_t count, int dtype);
+int bkf_comm_destroy(bkf_handle* h);
+
 #ifdef __cplusplus
 }
 #endif

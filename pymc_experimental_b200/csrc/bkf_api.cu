@@ -43,6 +43,9 @@ struct bkf_handle {
         KArgs<double> gd;
         KArgs<float> gf;
     } saved;
+    // bkf_comm_*: the NCCL communicator of this rank (ncclComm_t), NULL until bkf_comm_init
+    void* comm = nullptr;
+    int comm_world = 0, comm_rank = 0;
 };
 
 // RAII bracket: records start/stop events around one kernel launch when timing is on.
@@ -138,6 +141,7 @@ extern "C" int bkf_create(int device, bkf_handle** out) {
 extern "C" int bkf_destroy(bkf_handle* h) {
     if (!h) return BKF_OK;
     cudaSetDevice(h->device);
+    bkf_comm_destroy(h);
     for (auto& b : h->slots)
         if (b.p) cudaFree(b.p);
     for (auto& v : h->ev)
@@ -1297,4 +1301,90 @@ extern "C" int bkf_filter_smooth(bkf_handle* h, const bkf_problem* P, const void
     if (!y || any_null(prm, BKF_NPARAM)) return fail(h, BKF_ERR_ARG, "null input pointer");
     return P->dtype == BKF_F64 ? filter_smooth_impl<double>(h, P, y, prm, ll, sa, sP, status)
                                : filter_smooth_impl<float>(h, P, y, prm, ll, sa, sP, status);
+}
+
+// ----------------------------------------------------------------------------------------------------
+// bkf_comm_*: the final all-gather of [logp | gradients] through NCCL, loaded at run time (no link-time dependency)
+#include <dlfcn.h>
+#include <nccl.h>
+
+namespace {
+struct NcclApi {
+    void* lib = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    const char* (*GetErrorString)(ncclResult_t) = nullptr;
+    bool ok = false;
+};
+NcclApi& nccl_api() {
+    static NcclApi api = [] {
+        NcclApi a;
+        static_assert(sizeof(ncclUniqueId) == BKF_COMM_ID_BYTES, "ncclUniqueId is 128 bytes");
+        for (const char* name : {"libnccl.so.2", "libnccl.so"}) {
+            a.lib = dlopen(name, RTLD_NOW | RTLD_LOCAL);
+            if (a.lib) break;
+        }
+        if (!a.lib) return a;
+        a.GetUniqueId = (decltype(a.GetUniqueId))dlsym(a.lib, "ncclGetUniqueId");
+        a.CommInitRank = (decltype(a.CommInitRank))dlsym(a.lib, "ncclCommInitRank");
+        a.AllGather = (decltype(a.AllGather))dlsym(a.lib, "ncclAllGather");
+        a.CommDestroy = (decltype(a.CommDestroy))dlsym(a.lib, "ncclCommDestroy");
+        a.GetErrorString = (decltype(a.GetErrorString))dlsym(a.lib, "ncclGetErrorString");
+        a.ok = a.GetUniqueId && a.CommInitRank && a.AllGather && a.CommDestroy && a.GetErrorString;
+        return a;
+    }();
+    return api;
+}
+int nccl_fail(bkf_handle* h, ncclResult_t r) {
+    if (h) h->err = std::string("NCCL: ") + nccl_api().GetErrorString(r);
+    return BKF_ERR_CUDA;
+}
+}  // namespace
+
+extern "C" int bkf_comm_unique_id(void* id) {
+    if (!id) return BKF_ERR_ARG;
+    NcclApi& a = nccl_api();
+    if (!a.ok) return BKF_ERR_UNSUPPORTED;
+    ncclUniqueId u;
+    if (a.GetUniqueId(&u) != ncclSuccess) return BKF_ERR_CUDA;
+    memcpy(id, &u, sizeof(u));
+    return BKF_OK;
+}
+
+extern "C" int bkf_comm_init(bkf_handle* h, int world, int rank, const void* id) {
+    if (!h || !id || world < 1 || rank < 0 || rank >= world) return BKF_ERR_ARG;
+    NcclApi& a = nccl_api();
+    if (!a.ok) { h->err = "libnccl.so.2 could not be loaded"; return BKF_ERR_UNSUPPORTED; }
+    if (h->comm) bkf_comm_destroy(h);
+    cudaSetDevice(h->device);
+    ncclUniqueId u;
+    memcpy(&u, id, sizeof(u));
+    ncclComm_t c = nullptr;
+    const ncclResult_t r = a.CommInitRank(&c, world, u, rank);
+    if (r != ncclSuccess) return nccl_fail(h, r);
+    h->comm = c;
+    h->comm_world = world;
+    h->comm_rank = rank;
+    return BKF_OK;
+}
+
+extern "C" int bkf_comm_allgather(bkf_handle* h, const void* send, void* recv, size_t count, int dtype) {
+    if (!h || !send || !recv || (dtype != BKF_F64 && dtype != BKF_F32)) return BKF_ERR_ARG;
+    if (!h->comm) { h->err = "bkf_comm_init has not been called on this handle"; return BKF_ERR_ARG; }
+    cudaSetDevice(h->device);
+    const ncclResult_t r = nccl_api().AllGather(send, recv, count, dtype == BKF_F64 ? ncclFloat64 : ncclFloat32,
+                                               (ncclComm_t)h->comm, h->stream);
+    return r == ncclSuccess ? BKF_OK : nccl_fail(h, r);
+}
+
+extern "C" int bkf_comm_destroy(bkf_handle* h) {
+    if (!h) return BKF_OK;
+    if (h->comm) {
+        nccl_api().CommDestroy((ncclComm_t)h->comm);
+        h->comm = nullptr;
+        h->comm_world = h->comm_rank = 0;
+    }
+    return BKF_OK;
 }

@@ -36,7 +36,9 @@ ABI_SYMBOLS = (
     "bkf_logp_grad_workspace_bytes", "bkf_device_memory", "bkf_filter_logp_grad_compact", "bkf_stationary_init",
     "bkf_stationary_init_grad", "bkf_mvn_sample", "bkf_simulate",
     "bkf_filter_smooth_sample", "bkf_filter_forward_saved", "bkf_filter_backward_saved", "bkf_filter_logp_grad_theta",
+    "bkf_comm_unique_id", "bkf_comm_init", "bkf_comm_allgather", "bkf_comm_destroy",
 )
+COMM_ID_BYTES = 128
 FN_ID, FN_COS, FN_SIN, FN_EXP, FN_ONE_MINUS, FN_SQUARE = range(6)  # BKF_FN_* (theta -> entries programs)
 ERR_STALE = -5
 
@@ -105,6 +107,10 @@ def load_library():
     lib.bkf_filter_smooth_sample.argtypes = [vp, pp] + [vp] * 10 + [vp] + [vp] * 2 + [vp]
     lib.bkf_smooth.argtypes = [vp, pp] + [vp] * 5 + [vp] * 2 + [vp]
     lib.bkf_filter_smooth.argtypes = [vp, pp] + [vp] * 10 + [vp] * 3 + [vp]
+    lib.bkf_comm_unique_id.argtypes = [vp]
+    lib.bkf_comm_init.argtypes = [vp, C.c_int, C.c_int, vp]
+    lib.bkf_comm_allgather.argtypes = [vp, vp, vp, C.c_size_t, C.c_int]
+    lib.bkf_comm_destroy.argtypes = [vp]
     _lib = lib
     return lib
 
@@ -247,6 +253,44 @@ class KalmanEngine:
         f, t = C.c_size_t(0), C.c_size_t(0)
         self._check(self.lib.bkf_device_memory(self.h, C.byref(f), C.byref(t)))
         return f.value, t.value
+
+    # ---- the one collective of the path through the C ABI (bkf_comm_*): for callers without torch.distributed ----
+    @staticmethod
+    def comm_unique_id() -> bytes:
+        """128 bytes that rank 0 hands to every rank (``ncclGetUniqueId``)."""
+        buf = C.create_string_buffer(COMM_ID_BYTES)
+        rc = load_library().bkf_comm_unique_id(buf)
+        if rc != 0:
+            raise BkfError(f"bkf_comm_unique_id failed ({rc}): is libnccl.so.2 installed?")
+        return buf.raw
+
+    def comm_init(self, world: int, rank: int, unique_id: bytes):
+        if len(unique_id) != COMM_ID_BYTES:
+            raise BkfError(f"unique_id must be {COMM_ID_BYTES} bytes")
+        self._check(self.lib.bkf_comm_init(self.h, int(world), int(rank), C.c_char_p(unique_id)))
+        self._comm_world = int(world)
+
+    def comm_allgather(self, send, out=None):
+        """All-gather of a contiguous device tensor over the communicator of ``comm_init`` (enqueued on the tensor's
+        current stream behind the kernels that wrote it); returns a tensor with a leading axis of length world."""
+        import torch
+
+        if not send.is_cuda or send.device.index != self.device or not send.is_contiguous():
+            raise BkfError("comm_allgather takes a contiguous tensor on the engine's device")
+        code = {torch.float64: F64, torch.float32: F32}.get(send.dtype)
+        if code is None:
+            raise BkfError("comm_allgather: float64 or float32")
+        world = getattr(self, "_comm_world", 0)
+        if out is None:
+            out = torch.empty((world,) + tuple(send.shape), dtype=send.dtype, device=send.device)
+        self._check(self.lib.bkf_set_stream(self.h, C.c_void_p(torch.cuda.current_stream(send.device).cuda_stream)))
+        self._check(self.lib.bkf_comm_allgather(self.h, C.c_void_p(send.data_ptr()), C.c_void_p(out.data_ptr()),
+                                                send.numel(), code))
+        return out
+
+    def comm_destroy(self):
+        self.lib.bkf_comm_destroy(self.h)
+        self._comm_world = 0
 
     def close(self):
         if getattr(self, "h", None):

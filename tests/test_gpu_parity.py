@@ -902,3 +902,26 @@ def test_in_kernel_generator_equals_the_oracle_variates(eng):
     assert_allclose(ys1, ys2, rtol=0, atol=1e-12 * np.abs(ys2).max())
     with pytest.raises(Exception):
         eng.sample_mvn(sa, sP)  # neither variates nor a seed
+
+
+def test_comm_entry_points_single_rank(eng):
+    """bkf_comm_* (the NCCL all-gather of [logp | grads] through the C ABI, SURVEY section 8 rows b / e) with a communicator
+    of one rank: the gather of a packed logp + gradient buffer returns that buffer.  The two-rank case is
+    tests/test_comm_two_gpus.py (needs two GPUs)."""
+    import torch
+
+    from pymc_experimental_b200 import synth
+    from pymc_experimental_b200.engine import KalmanEngine
+
+    cfg = synth.sarima(B=16, n=30)
+    dev = torch.device("cuda", 0)
+    dargs = [torch.as_tensor(cfg["y"], device=dev)] + [torch.as_tensor(cfg[k], device=dev) for k in NAMES]
+    layout, total = eng.packed_layout(16, 15, 1, 1)
+    packed = torch.empty(total, dtype=torch.float64, device=dev)
+    eng.logp_grad("univariate", *dargs, packed_out=packed)
+    eng.comm_init(1, 0, KalmanEngine.comm_unique_id())
+    out = eng.comm_allgather(packed)
+    torch.cuda.synchronize()
+    assert out.shape == (1, total)
+    assert torch.equal(out[0], packed)
+    eng.comm_destroy()
