@@ -380,8 +380,12 @@ def measure_workload(args, ctx, name, batch, T_arg, steps, with_cpu):
     # all-gather of the first half (NCCL's own stream, async_op) runs under the kernels of the second half, so only half of
     # the one collective of the path is exposed.  (Series are independent: halves give bit-identical results.)
     halves = []
-    if world > 1 and mode == "logp_grad" and B >= 2:
-        for lo, hi in ((0, B // 2), (B // 2, B)):
+    # (only where a part still fills the GPU: a latency-bound workload -- C4: 512 series, one per scheduler -- takes as long
+    #  for half the batch as for all of it, so it goes through in one piece; its gather is 8 MB)
+    parts = int(os.environ.get("BKF_BENCH_PARTS", "2"))
+    if world > 1 and mode == "logp_grad" and parts > 1 and B // parts >= 4096:
+        bounds = [B * i // parts for i in range(parts + 1)]
+        for lo, hi in zip(bounds[:-1], bounds[1:]):
             _, tot_h = eng.packed_layout(hi - lo, m, p, r)
             sl = [dargs[0][lo:hi] if cfg["y"].ndim == 3 else dargs[0]]
             sl += [a[lo:hi] if a.ndim == STATIC_NDIM[k] + 1 else a for k, a in zip(NAMES, dargs[1:])]
@@ -577,7 +581,7 @@ def measure_workload(args, ctx, name, batch, T_arg, steps, with_cpu):
                        "r": int(r), "mode": mode, "kernel_path": eng.last_path,
                        "l2": "working set (trajectory workspace + parameters) exceeds the 126 MB L2; no explicit flush",
                        "parallelism": f"independent series sharded over {world} GPU(s); one final NCCL all-gather of [logp | "
-                                      "grads]" + (", issued in two halves: the first under the second half's kernels" if halves else "")},
+                                      "grads]" + (f", issued in {len(halves)} parts: each under the next part's kernels" if halves else "")},
             "clocks": clocks, "gpu_launches": int(launches),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
             "roofline": roof,

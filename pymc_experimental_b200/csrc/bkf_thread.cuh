@@ -12,6 +12,11 @@
 #pragma once
 #include "bkf_common.cuh"
 
+#ifndef BKF_TPS_FWD_MINB  // minimum resident CTAs per SM the kernels are compiled for (register cap)
+#define BKF_TPS_FWD_MINB 4  // forward: 128 registers (4 CTAs per SM) measured 5 % faster than 168 (3); adjoint: any cap spills
+#define BKF_TPS_BWD_MINB 1
+#endif
+
 namespace bkf {
 namespace tps {
 
@@ -148,7 +153,7 @@ __device__ __forceinline__ void load_consts(Consts<R, M>& k, const KArgs<R>& g, 
 }
 
 template <typename R, int M, int KIND>
-__global__ void __launch_bounds__(128) forward_kernel(KArgs<R> g) {
+__global__ void __launch_bounds__(128, BKF_TPS_FWD_MINB) forward_kernel(KArgs<R> g) {
     using C = TCfg<M>;
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= g.B) return;
@@ -239,7 +244,7 @@ __global__ void __launch_bounds__(128) forward_kernel(KArgs<R> g) {
 }
 
 template <typename R, int M, int KIND>
-__global__ void __launch_bounds__(128) backward_kernel(KArgs<R> g) {
+__global__ void __launch_bounds__(128, BKF_TPS_BWD_MINB) backward_kernel(KArgs<R> g) {
     using C = TCfg<M>;
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= g.B) return;
