@@ -49,7 +49,10 @@ __device__ __forceinline__ void inv8(double (&a)[2], int g, int t, int nreal, do
     }
 }
 
-__global__ void __launch_bounds__(64) smoother_kernel(KArgs<double> G, double jitter0, int* ill_list) {
+#ifndef BKF_TC_SM_MINB
+#define BKF_TC_SM_MINB 1
+#endif
+__global__ void __launch_bounds__(64, BKF_TC_SM_MINB) smoother_kernel(KArgs<double> G, double jitter0, int* ill_list) {
     extern __shared__ __align__(16) double smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int g = lane >> 2, t = lane & 3;
