@@ -337,6 +337,13 @@ def run_b200(args):
                 for k in ("e2e_sample",):
                     if k in rec:
                         line["also"][extra][k] = rec[k]
+        # C4's BASELINE total (4 096 draws x T = 1 000) fits one GPU (35 GB of record): the same kernels with every SM holding
+        # several series -- the per-GPU share above (512 draws) leaves one series per scheduler and is latency-bound
+        rec = measure_workload(args, ctx, "C4", 4096, 0, 2, with_cpu=False)
+        if rank == 0:
+            line["also"]["C4"]["baseline_total_on_one_gpu"] = {
+                k: rec[k] for k in ("value", "unit", "ms_per_step", "steps", "warmup", "config", "clocks", "e2e", "roofline")
+                if k in rec}
     if world > 1 and not args.no_also and not args.batch:
         # strong scaling beside the (default) weak figure: the workload's BASELINE total split over the ranks
         _, _, dB, _, _ = WORKLOADS[name]
