@@ -28,18 +28,22 @@ namespace bkf {
 namespace sqw {
 
 constexpr unsigned FULL = 0xffffffffu;
+struct TrueT { static constexpr bool value = true; };
+struct FalseT { static constexpr bool value = false; };
 
 #ifndef BKF_PANEL  // the reflector loop of a panel: panel_reflectors (plain), panel_reflectors_la (look-ahead)
 #define BKF_PANEL panel_reflectors_la
 #endif
 
 #ifdef BKF_SQW_PROFILE  // clock64 phase timers of block 0 (tools/build_variant.py sqwprof "-DBKF_SQW_PROFILE" ...)
-__device__ unsigned long long g_prof[8];
+__device__ unsigned long long g_prof[16];
+#define BKF_PMARK(i) do { if (blockIdx.x == 0 && (threadIdx.x & 31) == 0) { const long long _n = clock64(); g_prof[i] += (unsigned long long)(_n - _pm); _pm = _n; } } while (0)
 #define BKF_PTICK() const long long _pt0 = clock64()
 #define BKF_PTOCK(i) do { if (blockIdx.x == 0 && (threadIdx.x & 31) == 0) g_prof[i] += (unsigned long long)(clock64() - _pt0); } while (0)
 #else
 #define BKF_PTICK() do { } while (0)
 #define BKF_PTOCK(i) do { } while (0)
+#define BKF_PMARK(i) do { } while (0)
 #endif
 
 __device__ __forceinline__ void dmma(double& c0, double& c1, double a, double b) {
@@ -625,7 +629,10 @@ __device__ __forceinline__ void store_square(double* __restrict__ dst, TileF L, 
     }
 }
 
-template <int MT, int PT, int RT>
+// TZS: T and Z are kept in shared memory as tiles (12 KB more per series at the C4 shape).  Chosen when every series has a
+// scheduler to itself anyway (B <= 4 series per SM): the per-step fetch of T from L2 then leaves the critical path;
+// larger batches keep the small arena (8 series per SM) and read T / Z through L1.
+template <int MT, int PT, int RT, bool TZS>
 __global__ void __launch_bounds__(32) forward_kernel(KArgs<double> G) {
     using D = Dims<MT, PT, RT>;
     constexpr int m = D::m, p = D::p, N1 = D::N1, WT = D::WT;
@@ -643,6 +650,15 @@ __global__ void __launch_bounds__(32) forward_kernel(KArgs<double> G) {
     int st = setup_consts<D>(G, b, HC, RQ, nullptr, SA, &Hzero, lane);
     const double* Tg = param_ptr(G.T, G.shared_mask, BKF_PARAM_T, b, (size_t)m * m);
     const double* Zg = param_ptr(G.Z, G.shared_mask, BKF_PARAM_Z, b, (size_t)p * m);
+    double* TTs = smem + D::FWD_ELEMS;          // TZS only: T tiles (I, K) at I MT + K, then Z tiles (I, J) at I MT + J
+    double* ZZs = TTs + MT * MT * 64;
+    if (TZS) {
+        for (int idx = 0; idx < MT * MT; ++idx) stt(TTs, idx, lane, ldg_tile(Tg, m, idx / MT, idx % MT, lane));
+        for (int idx = 0; idx < PT * MT; ++idx) stt(ZZs, idx, lane, ldg_tile(Zg, m, idx / MT, idx % MT, lane));
+        __syncwarp();
+    }
+    auto t_tile = [&](int I, int K) { return TZS ? ldt(TTs, I * MT + K, lane) : ldg_tile(Tg, m, I, K, lane); };
+    auto z_tile = [&](int I, int J) { return TZS ? ldt(ZZs, I * MT + J, lane) : ldg_tile(Zg, m, I, J, lane); };
     {
         const double* a0 = param_ptr(G.a0, G.shared_mask, BKF_PARAM_A0, b, (size_t)m);
         const double* P0 = param_ptr(G.P0, G.shared_mask, BKF_PARAM_P0, b, (size_t)m * m);
@@ -666,6 +682,9 @@ __global__ void __launch_bounds__(32) forward_kernel(KArgs<double> G) {
     double logp = 0.0;
     for (int ts = 0; ts < n; ++ts) {
         BKF_PTICK();
+#ifdef BKF_SQW_PROFILE
+        long long _pm = clock64();
+#endif
         const size_t bt = (size_t)b * n + ts;
         double* rec = G.traj ? G.traj + bt * tstride : nullptr;
         // ---- mask, innovation ----
@@ -693,7 +712,7 @@ __global__ void __launch_bounds__(32) forward_kernel(KArgs<double> G) {
             double acc = 0.0;
 #pragma unroll
             for (int J = 0; J < MT; ++J) {
-                double2 z = ldg_tile(Zg, m, I, J, lane);
+                double2 z = z_tile(I, J);
                 z.x *= wI;
                 z.y *= wI;
                 zf[I][J] = z;
@@ -712,6 +731,7 @@ __global__ void __launch_bounds__(32) forward_kernel(KArgs<double> G) {
             for (int i = lane; i < p * p; i += 32) G.obs_cov[bt * p * p + i] = 0.0;
         double ll = 0.0;
         if (!flag) {
+            BKF_PMARK(4);  // mask, innovation, Z tiles
             // ---- update array (transposed): [[Hc, Zm Pc], [0, Pc]] ----
 #pragma unroll
             for (int I = 0; I < PT; ++I)
@@ -722,26 +742,35 @@ __global__ void __launch_bounds__(32) forward_kernel(KArgs<double> G) {
                     else if (partial) h = make_double2(NAN, NAN);  // the reference's cholesky(W H) fails here
                     stt(SA, I * WT + J, lane, h);
                 }
+            // Zm Pc.  From the second step on Pc is a predict factor -- lower triangular, its tiles K < J exact zeros -- and
+            // the products with them are left out at compile time (one copy of the code per case, chosen per step).
+            auto zpc = [&](auto TRI) {
+                constexpr bool tri = decltype(TRI)::value;
 #pragma unroll
-            for (int J = 0; J < MT; ++J) {
-                double2 acc[PT];
+                for (int J = 0; J < MT; ++J) {
+                    double2 acc[PT];
 #pragma unroll
-                for (int I = 0; I < PT; ++I) acc[I] = zero2();
+                    for (int I = 0; I < PT; ++I) acc[I] = zero2();
 #pragma unroll
-                for (int K = 0; K < MT; ++K) {
-                    const double2 pt = ttrans(ldt(SA, D::pc_tile(K, J), lane), lane);  // (Pc[K][J])^T
+                    for (int K = tri ? J : 0; K < MT; ++K) {
+                        const double2 pt = ttrans(ldt(SA, D::pc_tile(K, J), lane), lane);  // (Pc[K][J])^T
 #pragma unroll
-                    for (int I = 0; I < PT; ++I) mma_nt(acc[I], zf[I][K], pt);
+                        for (int I = 0; I < PT; ++I) mma_nt(acc[I], zf[I][K], pt);
+                    }
+#pragma unroll
+                    for (int I = 0; I < PT; ++I) stt(SA, I * WT + PT + J, lane, acc[I]);
                 }
-#pragma unroll
-                for (int I = 0; I < PT; ++I) stt(SA, I * WT + PT + J, lane, acc[I]);
-            }
+            };
+            if (ts > 0) zpc(TrueT{});
+            else zpc(FalseT{});
 #pragma unroll
             for (int I = 0; I < MT; ++I)
 #pragma unroll
                 for (int J = 0; J < PT; ++J) stt(SA, (PT + I) * WT + J, lane, zero2());
             __syncwarp();
+            BKF_PMARK(5);  // update array set-up (Zm Pc)
             qr_tiles<D::NT1, MT, PT, WT>(SA, smem + D::V_tq, D::NT1, D::NT1, false, lane);
+            BKF_PMARK(6);  // update sweep
             if (rec) {
                 int idx = 0;
 #pragma unroll
@@ -752,6 +781,7 @@ __global__ void __launch_bounds__(32) forward_kernel(KArgs<double> G) {
             }
             if (G.obs_cov)  // F = Fc Fc^T, Fc = B[:p,:p]
                 store_square<PT>(G.obs_cov + bt * p * p, [&](int I, int K) { return ldt(SA, I * WT + K, lane); }, lane);
+            BKF_PMARK(7);  // record of Rf, obs_cov
             // ---- s = Fc^{-1} v, inner = Fc^{-1} s  (Fc = B[:p,:p], lower), lane q owns x[q] ----
             {
                 const int q = lane < p ? lane : p - 1;
@@ -776,6 +806,7 @@ __global__ void __launch_bounds__(32) forward_kernel(KArgs<double> G) {
                 ll = -0.5 * ((double)p * (kLog2Pi + 2.0 * logdet) + quad);  // :696 (quirk Q2)
             }
             __syncwarp();
+            BKF_PMARK(8);  // triangular solves, ll
             // ---- a_f = a + KF s ;  jitter on the factor (Q4) ----
 #pragma unroll
             for (int I = 0; I < MT; ++I) {
@@ -811,8 +842,11 @@ __global__ void __launch_bounds__(32) forward_kernel(KArgs<double> G) {
             store_square<MT>(G.filt_P + bt * m * m, [&](int I, int K) { return ldt(SA, D::pc_tile(I, K), lane); }, lane);
         if (G.ll && lane == 0) G.ll[bt] = ll;
         logp += ll;
-        // ---- predict array (transposed) [T Pcf, R Qc]; a+ = T a_f + c ----
-        {
+        // ---- predict array (transposed) [T Pcf, R Qc]; a+ = T a_f + c.  Pcf is a QR factor (tiles K < J exact zeros) unless
+        //      it still is the caller's P0 (first step with every observation missing) ----
+        BKF_PMARK(9);  // a_f, jitter, vector record, outputs
+        auto tpcf = [&](auto TRI) {
+            constexpr bool tri = decltype(TRI)::value;
             double2 tp[MT][MT];
             double an[MT];
 #pragma unroll
@@ -825,14 +859,14 @@ __global__ void __launch_bounds__(32) forward_kernel(KArgs<double> G) {
             for (int K = 0; K < MT; ++K) {
                 double2 pt[MT];
 #pragma unroll
-                for (int J = 0; J < MT; ++J) pt[J] = ttrans(ldt(SA, D::pc_tile(K, J), lane), lane);
+                for (int J = 0; J < (tri ? K + 1 : MT); ++J) pt[J] = ttrans(ldt(SA, D::pc_tile(K, J), lane), lane);
 #pragma unroll
                 for (int I = 0; I < MT; ++I) {
-                    const double2 tf = ldg_tile(Tg, m, I, K, lane);
+                    const double2 tf = t_tile(I, K);
                     an[I] = fma(tf.x, vaf[8 * K + 2 * t], an[I]);
                     an[I] = fma(tf.y, vaf[8 * K + 2 * t + 1], an[I]);
 #pragma unroll
-                    for (int J = 0; J < MT; ++J) mma_nt(tp[I][J], tf, pt[J]);
+                    for (int J = 0; J < (tri ? K + 1 : MT); ++J) mma_nt(tp[I][J], tf, pt[J]);
                 }
             }
             __syncwarp();
@@ -846,8 +880,12 @@ __global__ void __launch_bounds__(32) forward_kernel(KArgs<double> G) {
                 for (int J = 0; J < RT; ++J) stt(SA, (PT + I) * WT + J, lane, ldt(RQ, I * RT + J, lane));
             }
             __syncwarp();
-        }
+        };
+        if (ts > 0 || !flag) tpcf(TrueT{});
+        else tpcf(FalseT{});
+        BKF_PMARK(10);  // predict array (T Pcf), a+
         qr_tiles<D::NT1, MT, PT, WT>(SA, smem + D::V_tq, MT, MT + RT, true, lane);
+        BKF_PMARK(11);  // predict sweep
         if (rec) {
             int idx = 0;
 #pragma unroll
@@ -862,7 +900,12 @@ __global__ void __launch_bounds__(32) forward_kernel(KArgs<double> G) {
     if (b == 0 && lane == 0)
         printf("sqw profile (cycles per step): reflectors %llu  T-factor+store %llu  (with trailing %llu)  step %llu\n",
                g_prof[0] / n, g_prof[1] / n, g_prof[2] / n, g_prof[3] / n);
-    if (b == 0 && lane == 0) g_prof[0] = g_prof[1] = g_prof[2] = g_prof[3] = 0;
+    if (b == 0 && lane == 0) {
+        printf("   phases: innovation %llu  update set-up %llu  update sweep %llu  Rf record %llu  solves %llu  a_f/record %llu  predict set-up %llu  "
+               "predict sweep %llu\n", g_prof[4] / n, g_prof[5] / n, g_prof[6] / n, g_prof[7] / n, g_prof[8] / n, g_prof[9] / n,
+               g_prof[10] / n, g_prof[11] / n);
+        for (int i = 0; i < 16; ++i) g_prof[i] = 0;
+    }
 #endif
     if (lane == 0) {
         if (!isfinite(logp)) st |= BKF_STATUS_NONFINITE;
