@@ -253,6 +253,10 @@ __global__ void __launch_bounds__(64) forward_kernel(KArgs<real> g) {
     const bool valid = series < g.B;
     const int b = valid ? series : g.B - 1;
     real* sm = smem + (size_t)((warp * C::SPW + sub)) * S::TOTAL;
+    // Rows j >= M of the shared matrices are never written but are read by the idle lanes of a series (M < LPS), whose
+    // values then meet a zero weight: 0 * (whatever the previous kernel left there) must not be 0 * NaN.
+    for (int i = j; i < S::TOTAL; i += LPS) sm[i] = real(0.0);
+    __syncwarp();
     const int n = g.n;
     const bool act = j < M;
 
@@ -409,6 +413,10 @@ __global__ void __launch_bounds__(64) backward_kernel(KArgs<real> g) {
     const bool valid = series < g.B;
     const int b = valid ? series : g.B - 1;
     real* sm = smem + (size_t)((warp * C::SPW + sub)) * S::TOTAL;
+    // Rows j >= M of the shared matrices are never written but are read by the idle lanes of a series (M < LPS), whose
+    // values then meet a zero weight: 0 * (whatever the previous kernel left there) must not be 0 * NaN.
+    for (int i = j; i < S::TOTAL; i += LPS) sm[i] = real(0.0);
+    __syncwarp();
     const int n = g.n;
     const bool act = j < M;
 

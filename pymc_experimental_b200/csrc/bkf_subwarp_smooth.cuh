@@ -49,6 +49,8 @@ __global__ void __launch_bounds__(64) smoother_kernel(KArgs<double> g, double ji
     const bool valid = series < g.B;
     const int b = valid ? series : g.B - 1;
     double* sm = smem + (size_t)((warp * C::SPW + sub)) * S::TOTAL;
+    for (int i = j; i < S::TOTAL; i += LPS) sm[i] = 0.0;  // idle lanes (M < LPS) read rows nobody writes: see bkf_subwarp.cuh
+    __syncwarp();
     const int n = g.n;
     const bool act = j < M;
 
