@@ -61,6 +61,35 @@ def test_c4_full_horizon_against_the_oracle(eng):
         assert worst[k] <= 1e-9, (k, worst[k])
 
 
+@pytest.mark.parametrize("shape", [(16, 8, 8), (32, 16, 16)])
+@pytest.mark.parametrize("eps", [1e-3, 1e-5])
+def test_square_root_nearly_dependent_columns_take_the_explicit_norm(eng, shape, eps):
+    """The forward sweep's reflector scalars come from downdated column norms (panel_reflectors_la); a column that lost more
+    than 2^-6 of its squared norm inside a panel must fall back to the explicit norm.  The factor P0 handed in has pairs of
+    nearly parallel ROWS (= columns of the transposed update array), in the first and in a later panel, so the guard fires
+    in the first steps (dlarfg's tau = 0 is exercised by the H = 0 and zero-Z-row cases of test_gpu_parity.py).  The result must match the oracle as well as the
+    conditioning allows (cond(P0 factor) ~ 1/eps: bound 1e-9 / eps relative to the 1e-16 of the arithmetic, stated below)."""
+    from oracle import kalman_torch as oth
+    from pymc_experimental_b200 import synth
+
+    m, p, r = shape
+    B, n = 6, 12
+    cfg = synth.random_dense(B, n, m, p, r, seed=77 + m, missing=0.0)
+    rng = np.random.default_rng(5)
+    L = np.linalg.cholesky(cfg["P0"]) @ np.linalg.qr(rng.standard_normal((B, m, m)))[0]  # a dense factor of the same P0 (Q5)
+    L[:, 1, :] = L[:, 0, :] + eps * np.abs(L[:, 0, :]).max() * rng.standard_normal((B, m))    # first panel
+    L[:, 11, :] = L[:, 9, :] + eps * np.abs(L[:, 9, :]).max() * rng.standard_normal((B, m))   # second panel
+    cfg["P0"] = L
+    args = [cfg["y"]] + [cfg[k] for k in NAMES]
+    logp, grads, status = eng.logp_grad("cholesky", *args)
+    assert eng.last_path == "sqrt_warp_dmma+adjoint_4warp"
+    ref_logp, ref_g = oth.logp_and_grad("cholesky", *args)
+    tol = max(1e-9, 1e-13 / eps**2)  # the pull-back through the factor divides by its small pivots twice
+    assert_allclose(logp, ref_logp, rtol=tol)
+    for k in NAMES:
+        assert _rel(grads[k], ref_g[k]) <= 10 * tol, (k, _rel(grads[k], ref_g[k]))
+
+
 @pytest.mark.parametrize("shape", [(5, 2, 3), (16, 8, 8), (32, 16, 16)])
 def test_square_root_filter_float32(eng, shape):
     """float32 SquareRootFilter (CTA-per-series kernels) against the float64 oracle at the float32 bound of the
