@@ -321,8 +321,28 @@ class KalmanEngine:
             self.set_stream(s)
             self._stream = s
 
+    def use_private_stream(self):
+        """Give this engine a non-blocking CUDA stream of its own for host-pointer calls (kept alive by the engine): two
+        engines with private streams overlap their copies and kernels (:meth:`logp_grad_overlapped`); the legacy default
+        stream would serialise them."""
+        import torch
+
+        if getattr(self, "_own_stream", None) is None:
+            self._own_stream = torch.cuda.Stream(device=self.device)
+        return self._own_stream
+
     def use_default_stream(self):
-        """Host-pointer calls run on the legacy default stream (a torch stream set earlier may be gone by now)."""
+        """Host-pointer calls run on the legacy default stream (a torch stream set earlier may be gone by now), or on the
+        engine's private stream once :meth:`use_private_stream` was called."""
+        own = getattr(self, "_own_stream", None)
+        if own is not None:
+            if self._stream != own.cuda_stream:
+                import torch
+
+                torch.cuda.synchronize(self.device)
+                self.set_stream(own.cuda_stream)
+                self._stream = own.cuda_stream
+            return
         if self._stream != 0:
             import torch
 
@@ -474,11 +494,13 @@ class KalmanEngine:
         return layout, off
 
     def logp_grad(self, kind, y, a0, P0, c, d, T, Z, R, H, Q, ll_cotangent=None, cov_jitter=None,
-                  missing_fill_value=None, grads=PARAM_NAMES, dtype=None, packed_out=None, time_varying=()):
+                  missing_fill_value=None, grads=PARAM_NAMES, dtype=None, packed_out=None, time_varying=(), outs=None):
         """logp[b] = sum_t loglike_obs[b,t] and d(sum_t cot*ll)/d{a0..Q} (reverse-mode adjoint kernels).
 
         ``packed_out``: optional flat preallocated buffer (see :meth:`packed_layout`); logp and the gradients
-        are then written straight into it (views are returned), so a gather needs no packing kernel."""
+        are then written straight into it (views are returned), so a gather needs no packing kernel.
+        ``outs``: optional dict of preallocated contiguous arrays ("logp", "status" and the gradient names) to write into
+        (used by :meth:`logp_grad_overlapped`, whose chunks fill slices of one set of arrays)."""
         params = dict(zip(PARAM_NAMES, (a0, P0, c, d, T, Z, R, H, Q)))
         bufs = _Buffers([y, *params.values()], dtype)
         params = {k_: (v if _is_torch(v) else np.asarray(v)) for k_, v in params.items()}
@@ -512,10 +534,17 @@ class KalmanEngine:
             view = lambda k_: flat[layout[k_][0]:layout[k_][0] + layout[k_][1]].reshape(layout[k_][2])
             gouts = {k_: (view(k_) if k_ in grads else None) for k_ in PARAM_NAMES}
             logp = view("logp")
+        elif outs is not None:
+            for k_ in ("logp", "status", *grads):
+                want = {"logp": (B,), "status": (B,)}.get(k_) or gshape[k_]
+                if tuple(outs[k_].shape) != tuple(want) or not outs[k_].flags["C_CONTIGUOUS"]:
+                    raise BkfError(f"outs[{k_!r}] must be a contiguous array of shape {want}")
+            gouts = {k_: (outs[k_] if k_ in grads else None) for k_ in PARAM_NAMES}
+            logp = outs["logp"]
         else:
             gouts = {k_: (bufs.out(gshape[k_]) if k_ in grads else None) for k_ in PARAM_NAMES}
             logp = bufs.out((B,))
-        status = bufs.out_int((B,))
+        status = outs["status"] if outs is not None and packed_out is None else bufs.out_int((B,))
         cot = None
         if ll_cotangent is not None:
             cot = bufs.inp(ll_cotangent)
@@ -533,6 +562,65 @@ class KalmanEngine:
         if squeeze:
             return logp[0], {k_: v[0] for k_, v in g.items()}, status[0]
         return logp, g, status
+
+    def logp_grad_overlapped(self, kind, y, a0, P0, c, d, T, Z, R, H, Q, chunks=2, ll_cotangent=None, cov_jitter=None,
+                             missing_fill_value=None, dtype=None):
+        """:meth:`logp_grad` for HOST arrays with the host <-> device copies hidden: the batch goes through in ``chunks``
+        contiguous slices, alternately on this engine and on a sibling engine (second handle, second workspace), each on a
+        private non-blocking stream and driven by its own host thread (ctypes releases the GIL), so the H2D copy of one
+        slice and the D2H copy of another run under the kernels of a third.  Series are independent: the results are
+        bit-identical to one call.  Inputs should be page-locked (``bkf_host_alloc`` / ``torch`` pinned memory) for the
+        copies to be asynchronous; the outputs are."""
+        import threading
+
+        params = {k_: np.asarray(v) for k_, v in zip(PARAM_NAMES, (a0, P0, c, d, T, Z, R, H, Q))}
+        y = np.asarray(y)
+        if any(_is_torch(v) for v in (y, *params.values())):
+            raise BkfError("logp_grad_overlapped takes host (NumPy) arrays")
+        B = self._batch_size(y, params, ())
+        chunks = int(chunks)
+        if B is None or chunks < 2 or int(B) < 2 * chunks:
+            return self.logp_grad(kind, y, *params.values(), ll_cotangent=ll_cotangent, cov_jitter=cov_jitter,
+                                  missing_fill_value=missing_fill_value, dtype=dtype)
+        B = int(B)
+        nd = np.dtype(np.float64 if dtype is None else dtype)
+        m, r = params["R"].shape[-2:]
+        p = params["Z"].shape[-2]
+        pool = pinned_pool()
+        shapes = {"a0": (B, m), "P0": (B, m, m), "c": (B, m), "d": (B, p), "T": (B, m, m), "Z": (B, p, m), "R": (B, m, r),
+                  "H": (B, p, p), "Q": (B, r, r)}
+        outs = {k_: pool.empty(shapes[k_], nd) for k_ in PARAM_NAMES}
+        outs["logp"] = pool.empty((B,), nd)
+        outs["status"] = np.zeros((B,), dtype=np.int32)
+        if getattr(self, "_sibling", None) is None:
+            self._sibling = KalmanEngine(self.device)
+        engines = (self, self._sibling)
+        for e in engines:
+            e.use_private_stream()
+        bounds = [B * i // chunks // 32 * 32 for i in range(chunks)] + [B]
+        batched = lambda name, x: x.ndim == _STATIC_NDIM[name] + 1
+        errors = []
+
+        def work(which):
+            try:
+                for i in range(which, chunks, 2):
+                    sl = slice(bounds[i], bounds[i + 1])
+                    args = [params[k_][sl] if batched(k_, params[k_]) else params[k_] for k_ in PARAM_NAMES]
+                    engines[which].logp_grad(
+                        kind, y[sl] if y.ndim == 3 else y, *args,
+                        ll_cotangent=None if ll_cotangent is None else np.asarray(ll_cotangent)[sl], cov_jitter=cov_jitter,
+                        missing_fill_value=missing_fill_value, dtype=dtype, outs={k_: v[sl] for k_, v in outs.items()})
+            except Exception as exc:  # re-raised in the caller's thread
+                errors.append(exc)
+
+        threads = [threading.Thread(target=work, args=(w,)) for w in (0, 1)]
+        for th in threads:
+            th.start()
+        for th in threads:
+            th.join()
+        if errors:
+            raise errors[0]
+        return outs["logp"], {k_: outs[k_] for k_ in PARAM_NAMES}, outs["status"]
 
     def forward_saved(self, kind, y, a0, P0, c, d, T, Z, R, H, Q, cov_jitter=None, missing_fill_value=None, dtype=None,
                       time_varying=(), want_ll=True):
