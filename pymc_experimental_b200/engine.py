@@ -293,6 +293,10 @@ class KalmanEngine:
         self._comm_world = 0
 
     def close(self):
+        sib = getattr(self, "_sibling", None)
+        if sib is not None:
+            sib.close()
+            self._sibling = None
         if getattr(self, "h", None):
             self.lib.bkf_destroy(self.h)
             self.h = None
