@@ -261,11 +261,15 @@ static int run_forward(bkf_handle* h, const KArgs<double>& g, const char** err) 
         h->path = "sqrt_cta";
         return sq::launch_forward<double>(g, h->stream, err);
     }
-    if (g.tv_mask) {  // time-varying matrices: the generic kernels stream them per step
+    // time-varying matrices: the generic kernels stream them per step -- except a time axis on c, d, Z, H only at the DMMA
+    // kernels' shapes (the regression-component pattern), which those kernels re-read per step themselves
+    const bool tc_tv = g.tv_mask && tc::tv_supported(g.tv_mask) && !tps::supported(g.kind, g.m, g.p) &&
+                       tc::supported(g.kind, g.m, g.p);
+    if (g.tv_mask && !tc_tv) {
         h->path = "generic_warp";
         return gen::launch_forward<double>(g, h->stream, err);
     }
-    if (tps::supported(g.kind, g.m, g.p)) {
+    if (!g.tv_mask && tps::supported(g.kind, g.m, g.p)) {
         h->path = "thread_f64";
         return tps::launch_any<double>(g, false, h->stream, err);
     }
@@ -306,8 +310,10 @@ static int run_backward(bkf_handle* h, const KArgs<double>& g, const char** err)
         return sqb::launch_f64(g, h->stream, err);
     }
     if (g.kind == BKF_CHOLESKY) return sq::launch_backward<double>(g, h->stream, err);
-    if (g.tv_mask) return gen::launch_backward<double>(g, h->stream, err);
-    if (tps::supported(g.kind, g.m, g.p)) return tps::launch_any<double>(g, true, h->stream, err);
+    const bool tc_tv = g.tv_mask && tc::tv_supported(g.tv_mask) && !tps::supported(g.kind, g.m, g.p) &&
+                       tc::supported(g.kind, g.m, g.p);
+    if (g.tv_mask && !tc_tv) return gen::launch_backward<double>(g, h->stream, err);
+    if (!g.tv_mask && tps::supported(g.kind, g.m, g.p)) return tps::launch_any<double>(g, true, h->stream, err);
     if (tc::supported(g.kind, g.m, g.p)) return tc::launch_f64(g, true, h->stream, err);
     if (sw::supported(g.kind, g.m, g.p)) return sw::launch_f64(g, true, h->stream, err);
     return gen::launch_backward<double>(g, h->stream, err);
@@ -326,7 +332,8 @@ static int run_backward(bkf_handle* h, const KArgs<float>& g, const char** err) 
 static int run_smoother(bkf_handle* h, const KArgs<double>& g, const char** err) {
     const double jitter0 = 1e-8;  // JITTER_DEFAULT (float64), kalman_smoother.py:117
     const bool use_tc = tc::smoother_supported(g.m);
-    if (!g.tv_mask && (use_tc || sw::smoother_supported(g.m))) {
+    const unsigned sm_tv = g.tv_mask & ((1u << BKF_PARAM_T) | (1u << BKF_PARAM_R) | (1u << BKF_PARAM_Q));  // what it reads
+    if (!sm_tv && (use_tc || sw::smoother_supported(g.m))) {
         // The fast kernels invert P_hat directly and list the series where that is not safe (pivot <= 0 or spanning
         // > 1e13); the generic kernel then redoes exactly those with the eigen-decomposition pinv.  The list lives on
         // the device and the second launch strides over it (it returns at once when the list is empty): no host round
@@ -506,7 +513,8 @@ static size_t traj_record_elems(const bkf_problem* P) {
     // square-root family's [a | Pc | triu(R_update) | triu(R_predict)]
     const bool f64 = P->dtype == BKF_F64;
     if (P->kind == BKF_CHOLESKY) return sq::traj_record_elems_host(P->m, P->p);
-    const bool frag = f64 && !P->tv_mask && !tps::supported(P->kind, P->m, P->p) && tc::supported(P->kind, P->m, P->p);
+    const bool frag = f64 && tc::tv_supported(P->tv_mask) && !tps::supported(P->kind, P->m, P->p) &&
+                      tc::supported(P->kind, P->m, P->p);
     return frag ? tc::traj_record_elems() : (size_t)P->m + (size_t)P->m * P->m;
 }
 

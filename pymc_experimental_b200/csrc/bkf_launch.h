@@ -37,6 +37,7 @@ int launch_f32(const KArgs<float>& g, bool backward, cudaStream_t stream, const 
 }  // namespace swf
 namespace tc {  // FP64 tensor-core (DMMA) warp-per-series kernels, 9 <= m <= 16, p = 1 (bkf_mma.cu)
 bool supported(int kind, int m, int p);
+bool tv_supported(unsigned tv_mask);  // time axes on c, d, Z, H only
 size_t traj_record_elems();
 int launch_f64(const KArgs<double>& g, bool backward, cudaStream_t stream, const char** err);
 bool smoother_supported(int m);

@@ -572,7 +572,10 @@ __device__ __forceinline__ void fwd_step(const KArgs<double>& G, const FwdConst&
     }
 }
 
-template <int KIND, bool OUT, int OCC>
+// TV: c, d, Z and / or H carry a time axis (G.tv_mask; the RegressionComponent pattern Z[t], structural.py:1601-1617, and
+// time-varying intercepts / measurement noise): the vectors and scalars of the step are re-read from x[t] at the top of
+// every step (a few L1-resident loads; T, R, Q with a time axis stay on the generic kernels).
+template <int KIND, bool OUT, int OCC, bool TV = false>
 __global__ void __launch_bounds__(64, OCC) forward_kernel(KArgs<double> G) {
     extern __shared__ double smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -614,6 +617,14 @@ __global__ void __launch_bounds__(64, OCC) forward_kernel(KArgs<double> G) {
     Frag P;
     load_frag<false>(P, P0g, m, g, t);
     const double* yb = G.y_shared ? G.y : G.y + (size_t)b * n;
+    auto refresh = [&](int ts) {  // TV: the observation-side parameters of step ts
+        const double* Zt = param_ptr_t(G.Z, G.shared_mask, G.tv_mask, BKF_PARAM_Z, b, ts, n, (size_t)m);
+        K.z_r = load_rvec(Zt, m, g);
+        K.z_c = load_cvec(Zt, m, t);
+        K.c_r = load_rvec(param_ptr_t(G.c, G.shared_mask, G.tv_mask, BKF_PARAM_C, b, ts, n, (size_t)m), m, g);
+        K.H0 = *param_ptr_t(G.H, G.shared_mask, G.tv_mask, BKF_PARAM_H, b, ts, n, 1);
+        K.d0 = *param_ptr_t(G.d, G.shared_mask, G.tv_mask, BKF_PARAM_D, b, ts, n, 1);
+    };
     LlBuf L;
     L.F = 1.0;
     L.v = 0.0;
@@ -622,6 +633,7 @@ __global__ void __launch_bounds__(64, OCC) forward_kernel(KArgs<double> G) {
     {
         Frag Pt;
         load_frag<true>(Pt, P0g, m, g, t);
+        if (TV) refresh(0);
         fwd_step_first<KIND>(G, K, P, Pt, a_r, a_c, L, b, yb[0], sc, lane);
         if (n == 1) ll_flush<KIND>(L, G, b, 0, lane);
     }
@@ -630,6 +642,7 @@ __global__ void __launch_bounds__(64, OCC) forward_kernel(KArgs<double> G) {
     for (int ts = 1; ts < n; ++ts) {
         const double yv = ynext;
         if (ts + 1 < n) ynext = yb[ts + 1];
+        if (TV) refresh(ts);
         fwd_step<KIND, OUT>(G, K, P, a_r, a_c, L, b, ts, yv, sc, lane);
         if ((ts & 31) == 31 || ts == n - 1) ll_flush<KIND>(L, G, b, ts, lane);
     }
@@ -972,7 +985,7 @@ __device__ __forceinline__ void bwd_step_sym(const KArgs<double>& G, const BwdCo
     S.abar_c = row2col(S.abar_r, t);
 }
 
-template <int KIND>
+template <int KIND, bool TV = false>
 __global__ void __launch_bounds__(64) backward_kernel(KArgs<double> G) {
     extern __shared__ __align__(16) double smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -1007,6 +1020,36 @@ __global__ void __launch_bounds__(64) backward_kernel(KArgs<double> G) {
     const double* yb = G.y_shared ? G.y : G.y + (size_t)b * n;
     const double* traj = G.traj + (size_t)b * n * REC;
     const double* cot = G.ll_cot ? G.ll_cot + (size_t)b * n : nullptr;
+    // TV: c, d, Z, H of step ts are read at the top of the step; the gradient of a parameter with a time axis keeps that
+    // axis -- its accumulator is written out and cleared after every step instead of once at the end.
+    const bool tvC = TV && ((G.tv_mask >> BKF_PARAM_C) & 1u), tvD = TV && ((G.tv_mask >> BKF_PARAM_D) & 1u),
+               tvZ = TV && ((G.tv_mask >> BKF_PARAM_Z) & 1u), tvH = TV && ((G.tv_mask >> BKF_PARAM_H) & 1u);
+    auto refresh = [&](int ts) {
+        const double* Zt = param_ptr_t(G.Z, G.shared_mask, G.tv_mask, BKF_PARAM_Z, b, ts, n, (size_t)m);
+        K.z_r = load_rvec(Zt, m, g);
+        K.z_c = load_cvec(Zt, m, t);
+        K.H0 = *param_ptr_t(G.H, G.shared_mask, G.tv_mask, BKF_PARAM_H, b, ts, n, 1);
+        K.d0 = *param_ptr_t(G.d, G.shared_mask, G.tv_mask, BKF_PARAM_D, b, ts, n, 1);
+    };
+    auto flush = [&](int ts) {
+        const size_t bt = (size_t)b * n + ts;
+        if (tvC) {
+            if (G.g_c) store_rvec(G.g_c + bt * m, S.gc_r, m, g, t);
+            S.gc_r.v[0] = S.gc_r.v[1] = 0.0;
+        }
+        if (tvZ) {
+            if (G.g_Z) store_rvec(G.g_Z + bt * m, S.gz_r, m, g, t);
+            S.gz_r.v[0] = S.gz_r.v[1] = 0.0;
+        }
+        if (tvD) {
+            if (G.g_d && lane == 0) G.g_d[bt] = S.gd;
+            S.gd = 0.0;
+        }
+        if (tvH) {
+            if (G.g_H && lane == 0) G.g_H[bt] = S.gH;
+            S.gH = 0.0;
+        }
+    };
     Frag P;
     RVec a_r;
     CVec a_c;
@@ -1029,7 +1072,9 @@ __global__ void __launch_bounds__(64) backward_kernel(KArgs<double> G) {
                 load_rec(traj + (size_t)(ts - 1) * REC, Pn, an_r, an_c, lane);
                 load_aux(traj + (size_t)(ts - 1) * REC, Xn, lane);
             }
+            if (TV) refresh(ts);
             bwd_step_sym<KIND>(G, K, S, P, a_r, a_c, X, yb[ts], cot ? cot[ts] : 1.0, sc, lane);
+            if (TV) flush(ts);
         }
     }
     {
@@ -1040,15 +1085,17 @@ __global__ void __launch_bounds__(64) backward_kernel(KArgs<double> G) {
         load_frag<true>(Pt, P0g, m, g, t);
         a_r = load_rvec(a0g, m, g);
         a_c = load_cvec(a0g, m, t);
+        if (TV) refresh(0);
         bwd_step<KIND, true>(G, K, S, P, Pt, a_r, a_c, yb[0], cot ? cot[0] : 1.0, sc, lane);
+        if (TV) flush(0);
     }
     // ---- gradients out ----
     if (G.g_a0) store_rvec(G.g_a0 + (size_t)b * m, S.abar_r, m, g, t);
-    if (G.g_c) store_rvec(G.g_c + (size_t)b * m, S.gc_r, m, g, t);
-    if (G.g_Z) store_rvec(G.g_Z + (size_t)b * m, S.gz_r, m, g, t);
+    if (G.g_c && !tvC) store_rvec(G.g_c + (size_t)b * m, S.gc_r, m, g, t);
+    if (G.g_Z && !tvZ) store_rvec(G.g_Z + (size_t)b * m, S.gz_r, m, g, t);
     if (lane == 0) {
-        if (G.g_d) G.g_d[b] = S.gd;
-        if (G.g_H) G.g_H[b] = S.gH;
+        if (G.g_d && !tvD) G.g_d[b] = S.gd;
+        if (G.g_H && !tvH) G.g_H[b] = S.gH;
     }
     if (G.g_P0) store_frag(G.g_P0 + (size_t)b * m * m, S.G, m, g, t, 1.0);
     if (G.g_T) store_frag(G.g_T + (size_t)b * m * m, S.Th, m, g, t, 2.0);

@@ -458,7 +458,9 @@ def test_time_varying_matrices_batched(eng, kind, tv, shape):
     cfg = synth.random_dense_tv(B, n, m, p, r, tv, seed=11 * m + p + len(tv), missing=0.1 if p == 1 else 0.0)
     args = [cfg["y"]] + [cfg[k] for k in NAMES]
     logp, grads, status = eng.logp_grad(kind, *args, time_varying=tv)
-    assert eng.last_path == "generic_warp"
+    # a time axis on c, d, Z, H only stays on the DMMA kernels at their shapes (9 <= m <= 16, p = 1)
+    fast = 9 <= m <= 16 and p == 1 and set(tv) <= {"c", "d", "Z", "H"}
+    assert eng.last_path == ("dmma_f64" if fast else "generic_warp")
     ref_logp, ref_g = oth.logp_and_grad(kind, *args, time_varying=tv)
     assert_allclose(logp, ref_logp, rtol=RTOL64)
     for k in NAMES:
@@ -477,6 +479,53 @@ def test_time_varying_matrices_batched(eng, kind, tv, shape):
                                      out["filtered_covariances"][b])
         _close(sa[b], ra, 1e-8, f"smoothed_states[{b}]")
         _close(sP[b], rP, 1e-8, f"smoothed_covariances[{b}]")
+
+
+@pytest.mark.parametrize("kind", ["standard", "univariate"])
+@pytest.mark.parametrize("tv", [("Z",), ("c", "d"), ("H",), ("c", "d", "Z", "H")])
+@pytest.mark.parametrize("m", [9, 15, 16])
+@pytest.mark.parametrize("shared", [False, True])
+def test_time_varying_observation_side_on_the_dmma_kernels(eng, kind, tv, m, shared):
+    """Row f-4 on the fast path: a time axis on c, d, Z and / or H (the RegressionComponent pattern Z[t],
+    structural.py:1601-1617; time-varying intercepts and measurement noise) is re-read per step by the DMMA kernels
+    themselves -- logp, gradients (which keep the time axis, also for an input shared by the batch), the seven filter
+    outputs and filter + smoother against the oracles, with missing observations."""
+    import torch
+
+    from oracle import kalman_np as onp
+    from oracle import kalman_torch as oth
+    from pymc_experimental_b200 import synth
+
+    B, n, r = 7, 21, 3
+    cfg = synth.random_dense_tv(B, n, m, 1, r, tv, seed=5 * m + len(tv), missing=0.15)
+    ref_cfg = dict(cfg)
+    if shared:  # the time-varying inputs once for the whole batch: [n, ...] instead of [B, n, ...]
+        for k in tv:
+            cfg[k] = np.ascontiguousarray(cfg[k][0])
+            ref_cfg[k] = np.repeat(cfg[k][None], B, 0)
+    args = [cfg["y"]] + [cfg[k] for k in NAMES]
+    ref_args = [ref_cfg["y"]] + [ref_cfg[k] for k in NAMES]
+    logp, grads, status = eng.logp_grad(kind, *args, time_varying=tv)
+    assert eng.last_path == "dmma_f64" and (status == 0).all()
+    ref_logp, ref_g = oth.logp_and_grad(kind, *ref_args, time_varying=tv)
+    assert_allclose(logp, ref_logp, rtol=RTOL64)
+    for k in NAMES:
+        assert grads[k].shape == ref_cfg[k].shape, k  # per-series gradients, time axis kept
+        for b in range(B):
+            _close(grads[k][b], ref_g[k][b], RTOL64, f"{kind} tv={tv} d/d{k}[{b}]")
+    out = eng.filter(kind, *args, time_varying=tv)
+    assert eng.last_path == "dmma_f64"
+    ref = oth.kalman_filter(kind, *[torch.as_tensor(a) for a in ref_args], time_varying=tv)
+    for got, want in zip([out[k] for k in OUT_NAMES], ref):
+        _close(got, want.numpy(), RTOL64, f"{kind} tv={tv}")
+    if kind == "standard":
+        ll, sa, sP, _ = eng.filter_smooth(kind, *args, time_varying=tv)
+        assert eng.last_path == "dmma_f64"
+        for b in (0, B - 1):
+            ra, rP = onp.kalman_smoother(cfg["T"][b], cfg["R"][b], cfg["Q"][b], out["filtered_states"][b],
+                                         out["filtered_covariances"][b])
+            _close(sa[b], ra, 1e-8, f"smoothed_states[{b}]")
+            _close(sP[b], rP, 1e-8, f"smoothed_covariances[{b}]")
 
 
 @pytest.mark.parametrize("shape", [(5, 2, 3), (16, 8, 8)])
