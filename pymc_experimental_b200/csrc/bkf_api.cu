@@ -261,15 +261,16 @@ static int run_forward(bkf_handle* h, const KArgs<double>& g, const char** err) 
         h->path = "sqrt_cta";
         return sq::launch_forward<double>(g, h->stream, err);
     }
-    // time-varying matrices: the generic kernels stream them per step -- except a time axis on c, d, Z, H only at the DMMA
-    // kernels' shapes (the regression-component pattern), which those kernels re-read per step themselves
-    const bool tc_tv = g.tv_mask && tc::tv_supported(g.tv_mask) && !tps::supported(g.kind, g.m, g.p) &&
-                       tc::supported(g.kind, g.m, g.p);
+    // time-varying matrices: the generic kernels stream them per step -- except a time axis on c, d, Z, H only (the
+    // regression-component pattern) for p = 1 and m <= 16, which the specialised float64 kernels re-read per step themselves
+    const bool tc_tv = g.tv_mask && tc::tv_supported(g.tv_mask) &&
+                       (tps::supported(g.kind, g.m, g.p) || tc::supported(g.kind, g.m, g.p) ||
+                        sw::supported(g.kind, g.m, g.p));
     if (g.tv_mask && !tc_tv) {
         h->path = "generic_warp";
         return gen::launch_forward<double>(g, h->stream, err);
     }
-    if (!g.tv_mask && tps::supported(g.kind, g.m, g.p)) {
+    if (tps::supported(g.kind, g.m, g.p)) {
         h->path = "thread_f64";
         return tps::launch_any<double>(g, false, h->stream, err);
     }
@@ -291,7 +292,7 @@ static int run_forward(bkf_handle* h, const KArgs<float>& g, const char** err) {
         h->path = "sqrt_cta";
         return sq::launch_forward<float>(g, h->stream, err);
     }
-    if (!g.tv_mask && tps::supported(g.kind, g.m, g.p)) {
+    if ((!g.tv_mask || tc::tv_supported(g.tv_mask)) && tps::supported(g.kind, g.m, g.p)) {
         h->path = "thread_f32";
         return tps::launch_any<float>(g, false, h->stream, err);
     }
@@ -310,10 +311,11 @@ static int run_backward(bkf_handle* h, const KArgs<double>& g, const char** err)
         return sqb::launch_f64(g, h->stream, err);
     }
     if (g.kind == BKF_CHOLESKY) return sq::launch_backward<double>(g, h->stream, err);
-    const bool tc_tv = g.tv_mask && tc::tv_supported(g.tv_mask) && !tps::supported(g.kind, g.m, g.p) &&
-                       tc::supported(g.kind, g.m, g.p);
+    const bool tc_tv = g.tv_mask && tc::tv_supported(g.tv_mask) &&
+                       (tps::supported(g.kind, g.m, g.p) || tc::supported(g.kind, g.m, g.p) ||
+                        sw::supported(g.kind, g.m, g.p));
     if (g.tv_mask && !tc_tv) return gen::launch_backward<double>(g, h->stream, err);
-    if (!g.tv_mask && tps::supported(g.kind, g.m, g.p)) return tps::launch_any<double>(g, true, h->stream, err);
+    if (tps::supported(g.kind, g.m, g.p)) return tps::launch_any<double>(g, true, h->stream, err);
     if (tc::supported(g.kind, g.m, g.p)) return tc::launch_f64(g, true, h->stream, err);
     if (sw::supported(g.kind, g.m, g.p)) return sw::launch_f64(g, true, h->stream, err);
     return gen::launch_backward<double>(g, h->stream, err);
@@ -322,7 +324,8 @@ static int run_backward(bkf_handle* h, const KArgs<float>& g, const char** err) 
     KernelTimer kt(h, BKF_KERNEL_BACKWARD);
     h->launches += 1;
     if (g.kind == BKF_CHOLESKY) return sq::launch_backward<float>(g, h->stream, err);
-    if (!g.tv_mask && tps::supported(g.kind, g.m, g.p)) return tps::launch_any<float>(g, true, h->stream, err);
+    if ((!g.tv_mask || tc::tv_supported(g.tv_mask)) && tps::supported(g.kind, g.m, g.p))
+        return tps::launch_any<float>(g, true, h->stream, err);
     if (!g.tv_mask && swf::supported(g.kind, g.m, g.p)) return swf::launch_f32(g, true, h->stream, err);
     return gen::launch_backward<float>(g, h->stream, err);
 }

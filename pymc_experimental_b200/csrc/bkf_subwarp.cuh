@@ -241,7 +241,9 @@ __device__ __forceinline__ void update(Upd<M>& u, const real (&Pc)[M], const rea
 // ---------------------------------------------------------------------------------------------------
 // forward kernel
 // ---------------------------------------------------------------------------------------------------
-template <int M, int KIND>
+// TV: c, d, Z and / or H carry a time axis (g.tv_mask): re-read from x[t] at the top of every step (regression
+// components, time-varying intercepts / measurement noise); gradients with a time axis are flushed per step.
+template <int M, int KIND, bool TV = false>
 __global__ void __launch_bounds__(64) forward_kernel(KArgs<real> g) {
     using C = Cfg<M>;
     using S = FwdSmem<M>;
@@ -265,8 +267,8 @@ __global__ void __launch_bounds__(64) forward_kernel(KArgs<real> g) {
     const real* Zg = param_ptr(g.Z, g.shared_mask, BKF_PARAM_Z, b, (size_t)M);
     const real* Rg = param_ptr(g.Rm, g.shared_mask, BKF_PARAM_R, b, (size_t)M * g.r);
     const real* Qg = param_ptr(g.Q, g.shared_mask, BKF_PARAM_Q, b, (size_t)g.r * g.r);
-    const real H0 = *param_ptr(g.H, g.shared_mask, BKF_PARAM_H, b, 1);
-    const real d0 = *param_ptr(g.d, g.shared_mask, BKF_PARAM_D, b, 1);
+    real H0 = *param_ptr(g.H, g.shared_mask, BKF_PARAM_H, b, 1);
+    real d0 = *param_ptr(g.d, g.shared_mask, BKF_PARAM_D, b, 1);
     const real* cg = param_ptr(g.c, g.shared_mask, BKF_PARAM_C, b, (size_t)M);
     const real* a0g = param_ptr(g.a0, g.shared_mask, BKF_PARAM_A0, b, (size_t)M);
     const real* P0g = param_ptr(g.P0, g.shared_mask, BKF_PARAM_P0, b, (size_t)M * M);
@@ -275,9 +277,9 @@ __global__ void __launch_bounds__(64) forward_kernel(KArgs<real> g) {
     for (int k = 0; k < M; ++k) Trow[k] = act ? Tg[j * M + k] : real(0.0);
 #pragma unroll
     for (int k = 0; k < M; ++k) sm[S::T_cm + k * LD + j] = Trow[k];  // T[j,k] -> column k, row j
-    const real Zj = act ? Zg[j] : real(0.0);
+    real Zj = act ? Zg[j] : real(0.0);
     sm[S::VZ + j] = Zj;
-    const real cj = act ? cg[j] : real(0.0);
+    real cj = act ? cg[j] : real(0.0);
     {  // RQR = sym(R Q R^T): lane j computes column j (and row j) once per series
         const int r = g.r;
 #pragma unroll 1
@@ -336,6 +338,16 @@ __global__ void __launch_bounds__(64) forward_kernel(KArgs<real> g) {
                     for (int q = j; q < M * M; q += LPS) g.pred_P[bt * M * M + q] = o[M + q];
             }
             __syncwarp();
+        }
+        if (TV) {
+            const real* Zt = param_ptr_t(g.Z, g.shared_mask, g.tv_mask, BKF_PARAM_Z, b, t, n, (size_t)M);
+            const real* ct = param_ptr_t(g.c, g.shared_mask, g.tv_mask, BKF_PARAM_C, b, t, n, (size_t)M);
+#pragma unroll
+            for (int i = 0; i < M; ++i) zv[i] = Zt[i];
+            Zj = act ? Zt[j] : real(0.0);
+            cj = act ? ct[j] : real(0.0);
+            H0 = *param_ptr_t(g.H, g.shared_mask, g.tv_mask, BKF_PARAM_H, b, t, n, 1);
+            d0 = *param_ptr_t(g.d, g.shared_mask, g.tv_mask, BKF_PARAM_D, b, t, n, 1);
         }
         if (t == 0)
             update<M, KIND, true>(u, Pc, Pr, a_j, j, yv, g.fill, g.jitter, Zj, zv, d0, H0, sm + S::VK, sm + S::VP, sm + S::VQ);
@@ -401,7 +413,7 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
 
-template <int M, int KIND>
+template <int M, int KIND, bool TV = false>
 __global__ void __launch_bounds__(64) backward_kernel(KArgs<real> g) {
     using C = Cfg<M>;
     using S = BwdSmem<M>;
@@ -422,14 +434,14 @@ __global__ void __launch_bounds__(64) backward_kernel(KArgs<real> g) {
 
     const real* Tg = param_ptr(g.T, g.shared_mask, BKF_PARAM_T, b, (size_t)M * M);
     const real* Zg = param_ptr(g.Z, g.shared_mask, BKF_PARAM_Z, b, (size_t)M);
-    const real H0 = *param_ptr(g.H, g.shared_mask, BKF_PARAM_H, b, 1);
-    const real d0 = *param_ptr(g.d, g.shared_mask, BKF_PARAM_D, b, 1);
+    real H0 = *param_ptr(g.H, g.shared_mask, BKF_PARAM_H, b, 1);
+    real d0 = *param_ptr(g.d, g.shared_mask, BKF_PARAM_D, b, 1);
     real Tcol[M];  // column j of T
 #pragma unroll
     for (int k = 0; k < M; ++k) Tcol[k] = act ? Tg[k * M + j] : real(0.0);
 #pragma unroll
     for (int k = 0; k < M; ++k) sm[S::T_rm + k * LD + j] = Tcol[k];  // T[k,j] -> "column" k (row k of T), entry j
-    const real Zj = act ? Zg[j] : real(0.0);
+    real Zj = act ? Zg[j] : real(0.0);
     sm[S::VZ + j] = Zj;
 #pragma unroll
     for (int i = 0; i < LPS; ++i) {
@@ -463,6 +475,14 @@ __global__ void __launch_bounds__(64) backward_kernel(KArgs<real> g) {
         __syncwarp();
         if (t > 0) prefetch(t - 1, (t - 1) & 1);
         const real* in = sm + ((t & 1) ? S::IN1 : S::IN0);
+        if (TV) {
+            const real* Zt = param_ptr_t(g.Z, g.shared_mask, g.tv_mask, BKF_PARAM_Z, b, t, n, (size_t)M);
+#pragma unroll
+            for (int i = 0; i < M; ++i) zv[i] = Zt[i];
+            Zj = act ? Zt[j] : real(0.0);
+            H0 = *param_ptr_t(g.H, g.shared_mask, g.tv_mask, BKF_PARAM_H, b, t, n, 1);
+            d0 = *param_ptr_t(g.d, g.shared_mask, g.tv_mask, BKF_PARAM_D, b, t, n, 1);
+        }
         const real a_j = act ? in[j] : real(0.0);
         real Pc[M];
         real S2c[M];  // column j of P + P^T (standard adjoint only)
@@ -612,14 +632,34 @@ __global__ void __launch_bounds__(64) backward_kernel(KArgs<real> g) {
             }
             __syncwarp();
         }
+        if (TV) {  // a gradient with a time axis is written out and cleared after every step
+            if ((g.tv_mask >> BKF_PARAM_C) & 1u) {
+                if (valid && g.g_c && act) g.g_c[bt * M + j] = gc;
+                gc = real(0.0);
+            }
+            if ((g.tv_mask >> BKF_PARAM_Z) & 1u) {
+                if (valid && g.g_Z && act) g.g_Z[bt * M + j] = gz;
+                gz = real(0.0);
+            }
+            if ((g.tv_mask >> BKF_PARAM_D) & 1u) {
+                if (valid && g.g_d && j == 0) g.g_d[bt] = gd;
+                gd = real(0.0);
+            }
+            if ((g.tv_mask >> BKF_PARAM_H) & 1u) {
+                if (valid && g.g_H && j == 0) g.g_H[bt] = gH;
+                gH = real(0.0);
+            }
+        }
     }
     // ---- gradients out ----
     if (valid) {
+        const bool tvC = TV && ((g.tv_mask >> BKF_PARAM_C) & 1u), tvZ = TV && ((g.tv_mask >> BKF_PARAM_Z) & 1u),
+                   tvD = TV && ((g.tv_mask >> BKF_PARAM_D) & 1u), tvH = TV && ((g.tv_mask >> BKF_PARAM_H) & 1u);
         if (g.g_a0 && act) g.g_a0[(size_t)b * M + j] = abar;
-        if (g.g_c && act) g.g_c[(size_t)b * M + j] = gc;
-        if (g.g_Z && act) g.g_Z[(size_t)b * M + j] = gz;
-        if (g.g_d && j == 0) g.g_d[b] = gd;
-        if (g.g_H && j == 0) g.g_H[b] = gH;
+        if (g.g_c && act && !tvC) g.g_c[(size_t)b * M + j] = gc;
+        if (g.g_Z && act && !tvZ) g.g_Z[(size_t)b * M + j] = gz;
+        if (g.g_d && j == 0 && !tvD) g.g_d[b] = gd;
+        if (g.g_H && j == 0 && !tvH) g.g_H[b] = gH;
         if (g.g_P0 && act) {
 #pragma unroll
             for (int i = 0; i < M; ++i) g.g_P0[(size_t)b * M * M + i * M + j] = Pbar[i];
@@ -674,10 +714,25 @@ int launch(const KArgs<real>& g, bool backward, cudaStream_t stream, const char*
     e = cudaFuncSetAttribute(KERN, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);            \
     if (e != cudaSuccess) { *err = cudaGetErrorString(e); return BKF_ERR_CUDA; }                       \
     KERN<<<grid, 32 * warps, smem, stream>>>(g);
+#ifdef BKF_SW_F32
+    constexpr bool HAS_TV = false;  // the float32 build keeps time-varying inputs on the generic kernels
+#else
+    constexpr bool HAS_TV = true;
+#endif
+    const bool tv = g.tv_mask != 0;
+    if (tv && !HAS_TV) { *err = "time-varying inputs are not compiled into the float32 sub-warp kernels"; return BKF_ERR_UNSUPPORTED; }
     if (g.kind == BKF_UNIVARIATE) {
-        if (backward) { BKF_SW_LAUNCH((backward_kernel<M, K_UNI>)) } else { BKF_SW_LAUNCH((forward_kernel<M, K_UNI>)) }
+        if (tv) {
+            if (backward) { BKF_SW_LAUNCH((backward_kernel<M, K_UNI, HAS_TV>)) } else { BKF_SW_LAUNCH((forward_kernel<M, K_UNI, HAS_TV>)) }
+        } else {
+            if (backward) { BKF_SW_LAUNCH((backward_kernel<M, K_UNI>)) } else { BKF_SW_LAUNCH((forward_kernel<M, K_UNI>)) }
+        }
     } else {
-        if (backward) { BKF_SW_LAUNCH((backward_kernel<M, K_STD>)) } else { BKF_SW_LAUNCH((forward_kernel<M, K_STD>)) }
+        if (tv) {
+            if (backward) { BKF_SW_LAUNCH((backward_kernel<M, K_STD, HAS_TV>)) } else { BKF_SW_LAUNCH((forward_kernel<M, K_STD, HAS_TV>)) }
+        } else {
+            if (backward) { BKF_SW_LAUNCH((backward_kernel<M, K_STD>)) } else { BKF_SW_LAUNCH((forward_kernel<M, K_STD>)) }
+        }
     }
 #undef BKF_SW_LAUNCH
     e = cudaGetLastError();

@@ -152,7 +152,23 @@ __device__ __forceinline__ void load_consts(Consts<R, M>& k, const KArgs<R>& g, 
         for (int j = 0; j < M; ++j) k.RQR[i][j] = R(0.5) * (raw[i][j] + raw[j][i]);
 }
 
-template <typename R, int M, int KIND>
+// The observation-side / intercept parameters of step t when they carry a time axis (tv_mask on c, d, Z, H: regression
+// components, time-varying intercepts and measurement noise; T, R, Q with a time axis take the generic kernels).
+template <typename R, int M>
+__device__ __forceinline__ void refresh_tv(Consts<R, M>& k, const KArgs<R>& g, int b, int t) {
+    const int n = g.n;
+    const R* Zt = param_ptr_t(g.Z, g.shared_mask, g.tv_mask, BKF_PARAM_Z, b, t, n, (size_t)M);
+    const R* ct = param_ptr_t(g.c, g.shared_mask, g.tv_mask, BKF_PARAM_C, b, t, n, (size_t)M);
+#pragma unroll
+    for (int i = 0; i < M; ++i) {
+        k.Z[i] = Zt[i];
+        k.c[i] = ct[i];
+    }
+    k.H = *param_ptr_t(g.H, g.shared_mask, g.tv_mask, BKF_PARAM_H, b, t, n, 1);
+    k.d = *param_ptr_t(g.d, g.shared_mask, g.tv_mask, BKF_PARAM_D, b, t, n, 1);
+}
+
+template <typename R, int M, int KIND, bool TV = false>
 __global__ void __launch_bounds__(128, BKF_TPS_FWD_MINB) forward_kernel(KArgs<R> g) {
     using C = TCfg<M>;
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
@@ -196,6 +212,7 @@ __global__ void __launch_bounds__(128, BKF_TPS_FWD_MINB) forward_kernel(KArgs<R>
         if (g.pred_P)
 #pragma unroll
             for (int i = 0; i < M * M; ++i) g.pred_P[bt * M * M + i] = P[i / M][i % M];
+        if (TV) refresh_tv<R, M>(k, g, b, t);
         update<R, M, KIND>(s, k, a, P, yt, g.fill, g.jitter);
         logp += s.ll;
         if (g.ll) g.ll[bt] = s.ll;
@@ -243,7 +260,7 @@ __global__ void __launch_bounds__(128, BKF_TPS_FWD_MINB) forward_kernel(KArgs<R>
     if (g.status) g.status[b] = isfinite(logp) ? 0 : BKF_STATUS_NONFINITE;
 }
 
-template <typename R, int M, int KIND>
+template <typename R, int M, int KIND, bool TV = false>
 __global__ void __launch_bounds__(128, BKF_TPS_BWD_MINB) backward_kernel(KArgs<R> g) {
     using C = TCfg<M>;
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
@@ -302,6 +319,7 @@ __global__ void __launch_bounds__(128, BKF_TPS_BWD_MINB) backward_kernel(KArgs<R
                 for (int j = 0; j < M; ++j) P[i][j] = P0g[i * M + j];
             }
         }
+        if (TV) refresh_tv<R, M>(k, g, b, t);
         update<R, M, KIND>(s, k, a, P, yt, g.fill, g.jitter);
         // ---- predict adjoint ----
         R G[M][M], W[M][M], Pfb[M][M], afbar[M];
@@ -450,15 +468,43 @@ __global__ void __launch_bounds__(128, BKF_TPS_BWD_MINB) backward_kernel(KArgs<R
             gd -= vbar;
             gH += s.miss ? R(0) : Hmbar;
         }
+        if (TV) {  // a gradient with a time axis is written out and cleared after every step
+            const size_t bt = (size_t)b * n + t;
+            if ((g.tv_mask >> BKF_PARAM_C) & 1u) {
+#pragma unroll
+                for (int i = 0; i < M; ++i) {
+                    if (g.g_c) g.g_c[bt * M + i] = gc[i];
+                    gc[i] = 0;
+                }
+            }
+            if ((g.tv_mask >> BKF_PARAM_Z) & 1u) {
+#pragma unroll
+                for (int i = 0; i < M; ++i) {
+                    if (g.g_Z) g.g_Z[bt * M + i] = gZ[i];
+                    gZ[i] = 0;
+                }
+            }
+            if ((g.tv_mask >> BKF_PARAM_D) & 1u) {
+                if (g.g_d) g.g_d[bt] = gd;
+                gd = 0;
+            }
+            if ((g.tv_mask >> BKF_PARAM_H) & 1u) {
+                if (g.g_H) g.g_H[bt] = gH;
+                gH = 0;
+            }
+        }
     }
     auto put = [&](R* dst, const R* src, int sz) {
         if (dst)
             for (int i = 0; i < sz; ++i) dst[(size_t)b * sz + i] = src[i];
     };
-    put(g.g_a0, abar, M); put(g.g_P0, &Pbar[0][0], M * M); put(g.g_c, gc, M); put(g.g_T, &gT[0][0], M * M);
-    put(g.g_Z, gZ, M);
-    if (g.g_d) g.g_d[b] = gd;
-    if (g.g_H) g.g_H[b] = gH;
+    const bool tvC = TV && ((g.tv_mask >> BKF_PARAM_C) & 1u), tvZ = TV && ((g.tv_mask >> BKF_PARAM_Z) & 1u),
+               tvD = TV && ((g.tv_mask >> BKF_PARAM_D) & 1u), tvH = TV && ((g.tv_mask >> BKF_PARAM_H) & 1u);
+    put(g.g_a0, abar, M); put(g.g_P0, &Pbar[0][0], M * M); put(g.g_T, &gT[0][0], M * M);
+    if (!tvC) put(g.g_c, gc, M);
+    if (!tvZ) put(g.g_Z, gZ, M);
+    if (g.g_d && !tvD) g.g_d[b] = gd;
+    if (g.g_H && !tvH) g.g_H[b] = gH;
     const int r = g.r;
     const R* Rg = param_ptr(g.Rm, g.shared_mask, BKF_PARAM_R, b, (size_t)M * r);
     const R* Qg = param_ptr(g.Q, g.shared_mask, BKF_PARAM_Q, b, (size_t)r * r);
@@ -489,13 +535,17 @@ __global__ void __launch_bounds__(128, BKF_TPS_BWD_MINB) backward_kernel(KArgs<R
 template <typename R, int M>
 int launch(const KArgs<R>& g, bool backward, cudaStream_t stream, const char** err) {
     const int block = 128, grid = (g.B + block - 1) / block;
-    if (g.kind == BKF_UNIVARIATE) {
-        if (backward) backward_kernel<R, M, K_UNI><<<grid, block, 0, stream>>>(g);
-        else forward_kernel<R, M, K_UNI><<<grid, block, 0, stream>>>(g);
-    } else {
-        if (backward) backward_kernel<R, M, K_STD><<<grid, block, 0, stream>>>(g);
-        else forward_kernel<R, M, K_STD><<<grid, block, 0, stream>>>(g);
+    const bool tv = g.tv_mask != 0;  // c, d, Z, H only (tv_supported)
+#define BKF_TPS_LAUNCH(KIND)                                                                    \
+    if (backward) {                                                                             \
+        if (tv) backward_kernel<R, M, KIND, true><<<grid, block, 0, stream>>>(g);               \
+        else backward_kernel<R, M, KIND, false><<<grid, block, 0, stream>>>(g);                 \
+    } else {                                                                                    \
+        if (tv) forward_kernel<R, M, KIND, true><<<grid, block, 0, stream>>>(g);                \
+        else forward_kernel<R, M, KIND, false><<<grid, block, 0, stream>>>(g);                  \
     }
+    if (g.kind == BKF_UNIVARIATE) { BKF_TPS_LAUNCH(K_UNI) } else { BKF_TPS_LAUNCH(K_STD) }
+#undef BKF_TPS_LAUNCH
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { *err = cudaGetErrorString(e); return BKF_ERR_CUDA; }
     return BKF_OK;

@@ -458,9 +458,12 @@ def test_time_varying_matrices_batched(eng, kind, tv, shape):
     cfg = synth.random_dense_tv(B, n, m, p, r, tv, seed=11 * m + p + len(tv), missing=0.1 if p == 1 else 0.0)
     args = [cfg["y"]] + [cfg[k] for k in NAMES]
     logp, grads, status = eng.logp_grad(kind, *args, time_varying=tv)
-    # a time axis on c, d, Z, H only stays on the DMMA kernels at their shapes (9 <= m <= 16, p = 1)
-    fast = 9 <= m <= 16 and p == 1 and set(tv) <= {"c", "d", "Z", "H"}
-    assert eng.last_path == ("dmma_f64" if fast else "generic_warp")
+    # a time axis on c, d, Z, H only stays on the fast kernels (p = 1): thread per series (m <= 4), sub-warp (5..8), DMMA (9..16)
+    obs_side = p == 1 and set(tv) <= {"c", "d", "Z", "H"}
+    want = "generic_warp"
+    if obs_side:
+        want = "thread_f64" if m <= 4 else ("subwarp_f64" if m <= 8 else ("dmma_f64" if m <= 16 else "generic_warp"))
+    assert eng.last_path == want
     ref_logp, ref_g = oth.logp_and_grad(kind, *args, time_varying=tv)
     assert_allclose(logp, ref_logp, rtol=RTOL64)
     for k in NAMES:
@@ -483,20 +486,22 @@ def test_time_varying_matrices_batched(eng, kind, tv, shape):
 
 @pytest.mark.parametrize("kind", ["standard", "univariate"])
 @pytest.mark.parametrize("tv", [("Z",), ("c", "d"), ("H",), ("c", "d", "Z", "H")])
-@pytest.mark.parametrize("m", [9, 15, 16])
+@pytest.mark.parametrize("m", [2, 3, 4, 5, 7, 8, 9, 15, 16])
 @pytest.mark.parametrize("shared", [False, True])
-def test_time_varying_observation_side_on_the_dmma_kernels(eng, kind, tv, m, shared):
+def test_time_varying_observation_side_on_the_fast_kernels(eng, kind, tv, m, shared):
     """Row f-4 on the fast path: a time axis on c, d, Z and / or H (the RegressionComponent pattern Z[t],
     structural.py:1601-1617; time-varying intercepts and measurement noise) is re-read per step by the DMMA kernels
-    themselves -- logp, gradients (which keep the time axis, also for an input shared by the batch), the seven filter
-    outputs and filter + smoother against the oracles, with missing observations."""
+    and by the thread-per-series kernels (m <= 4: local level / trend + regression) themselves -- logp, gradients (which
+    keep the time axis, also for an input shared by the batch), the seven filter outputs and filter + smoother against the
+    oracles, with missing observations."""
     import torch
 
     from oracle import kalman_np as onp
     from oracle import kalman_torch as oth
     from pymc_experimental_b200 import synth
 
-    B, n, r = 7, 21, 3
+    B, n, r = 7, 21, min(3, m)
+    fast_path = "thread_f64" if m <= 4 else ("subwarp_f64" if m <= 8 else "dmma_f64")
     cfg = synth.random_dense_tv(B, n, m, 1, r, tv, seed=5 * m + len(tv), missing=0.15)
     ref_cfg = dict(cfg)
     if shared:  # the time-varying inputs once for the whole batch: [n, ...] instead of [B, n, ...]
@@ -506,7 +511,7 @@ def test_time_varying_observation_side_on_the_dmma_kernels(eng, kind, tv, m, sha
     args = [cfg["y"]] + [cfg[k] for k in NAMES]
     ref_args = [ref_cfg["y"]] + [ref_cfg[k] for k in NAMES]
     logp, grads, status = eng.logp_grad(kind, *args, time_varying=tv)
-    assert eng.last_path == "dmma_f64" and (status == 0).all()
+    assert eng.last_path == fast_path and (status == 0).all()
     ref_logp, ref_g = oth.logp_and_grad(kind, *ref_args, time_varying=tv)
     assert_allclose(logp, ref_logp, rtol=RTOL64)
     for k in NAMES:
@@ -514,18 +519,36 @@ def test_time_varying_observation_side_on_the_dmma_kernels(eng, kind, tv, m, sha
         for b in range(B):
             _close(grads[k][b], ref_g[k][b], RTOL64, f"{kind} tv={tv} d/d{k}[{b}]")
     out = eng.filter(kind, *args, time_varying=tv)
-    assert eng.last_path == "dmma_f64"
+    assert eng.last_path == fast_path
     ref = oth.kalman_filter(kind, *[torch.as_tensor(a) for a in ref_args], time_varying=tv)
     for got, want in zip([out[k] for k in OUT_NAMES], ref):
         _close(got, want.numpy(), RTOL64, f"{kind} tv={tv}")
     if kind == "standard":
         ll, sa, sP, _ = eng.filter_smooth(kind, *args, time_varying=tv)
-        assert eng.last_path == "dmma_f64"
+        if m > 4:
+            assert eng.last_path == fast_path
         for b in (0, B - 1):
             ra, rP = onp.kalman_smoother(cfg["T"][b], cfg["R"][b], cfg["Q"][b], out["filtered_states"][b],
                                          out["filtered_covariances"][b])
             _close(sa[b], ra, 1e-8, f"smoothed_states[{b}]")
             _close(sP[b], rP, 1e-8, f"smoothed_covariances[{b}]")
+
+
+def test_time_varying_observation_side_float32_thread_kernels(eng):
+    """The float32 instantiation of the same path (m <= 4): a regression design row Z[t] and d[t], stated float32 bound."""
+    from oracle import kalman_torch as oth
+    from pymc_experimental_b200 import synth
+
+    tv = ("Z", "d")
+    cfg = synth.random_dense_tv(6, 25, 3, 1, 2, tv, seed=3, missing=0.1)
+    args = [cfg["y"]] + [cfg[k] for k in NAMES]
+    logp, grads, status = eng.logp_grad("standard", *args, time_varying=tv, dtype=np.float32, cov_jitter=1e-6)
+    assert eng.last_path == "thread_f32" and logp.dtype == np.float32
+    ref_logp, ref_g = oth.logp_and_grad("standard", *args, time_varying=tv, cov_jitter=1e-6)
+    assert_allclose(logp, ref_logp, rtol=1e-3)
+    for k in NAMES:
+        assert grads[k].shape == cfg[k].shape
+        _close(grads[k], ref_g[k], 1e-2, f"f32 tv d/d{k}")
 
 
 @pytest.mark.parametrize("shape", [(5, 2, 3), (16, 8, 8)])
