@@ -248,6 +248,17 @@ extern "C" int bkf_set_stream(bkf_handle* h, void* s) {
     return BKF_OK;
 }
 
+// generic kernels, float64: the build with DMMA tile products from m = 16 on (bkf_generic_tc.cu), the scalar one below
+static int gen_forward_f64(const KArgs<double>& g, cudaStream_t st, const char** err) {
+    return g.m >= 16 ? gent::launch_forward<double>(g, st, err) : gen::launch_forward<double>(g, st, err);
+}
+static int gen_backward_f64(const KArgs<double>& g, cudaStream_t st, const char** err) {
+    return g.m >= 16 ? gent::launch_backward<double>(g, st, err) : gen::launch_backward<double>(g, st, err);
+}
+static int gen_smoother_f64(const KArgs<double>& g, const int* list, const int* count, cudaStream_t st, const char** err) {
+    return g.m >= 16 ? gent::launch_smoother<double>(g, list, count, st, err) : gen::launch_smoother<double>(g, list, count, st, err);
+}
+
 // ----------------------------------------------------------------------------------------------------
 // kernel-family dispatch: specialised register-tiled kernels where they exist, the generic path otherwise
 static int run_forward(bkf_handle* h, const KArgs<double>& g, const char** err) {
@@ -268,7 +279,7 @@ static int run_forward(bkf_handle* h, const KArgs<double>& g, const char** err) 
                         sw::supported(g.kind, g.m, g.p));
     if (g.tv_mask && !tc_tv) {
         h->path = "generic_warp";
-        return gen::launch_forward<double>(g, h->stream, err);
+        return gen_forward_f64(g, h->stream, err);
     }
     if (tps::supported(g.kind, g.m, g.p)) {
         h->path = "thread_f64";
@@ -283,7 +294,7 @@ static int run_forward(bkf_handle* h, const KArgs<double>& g, const char** err) 
         return sw::launch_f64(g, false, h->stream, err);
     }
     h->path = "generic_warp";
-    return gen::launch_forward<double>(g, h->stream, err);
+    return gen_forward_f64(g, h->stream, err);
 }
 static int run_forward(bkf_handle* h, const KArgs<float>& g, const char** err) {
     KernelTimer kt(h, BKF_KERNEL_FORWARD);
@@ -314,11 +325,11 @@ static int run_backward(bkf_handle* h, const KArgs<double>& g, const char** err)
     const bool tc_tv = g.tv_mask && tc::tv_supported(g.tv_mask) &&
                        (tps::supported(g.kind, g.m, g.p) || tc::supported(g.kind, g.m, g.p) ||
                         sw::supported(g.kind, g.m, g.p));
-    if (g.tv_mask && !tc_tv) return gen::launch_backward<double>(g, h->stream, err);
+    if (g.tv_mask && !tc_tv) return gen_backward_f64(g, h->stream, err);
     if (tps::supported(g.kind, g.m, g.p)) return tps::launch_any<double>(g, true, h->stream, err);
     if (tc::supported(g.kind, g.m, g.p)) return tc::launch_f64(g, true, h->stream, err);
     if (sw::supported(g.kind, g.m, g.p)) return sw::launch_f64(g, true, h->stream, err);
-    return gen::launch_backward<double>(g, h->stream, err);
+    return gen_backward_f64(g, h->stream, err);
 }
 static int run_backward(bkf_handle* h, const KArgs<float>& g, const char** err) {
     KernelTimer kt(h, BKF_KERNEL_BACKWARD);
@@ -354,11 +365,11 @@ static int run_smoother(bkf_handle* h, const KArgs<double>& g, const char** err)
         if (rc != BKF_OK) return rc;
         h->path = use_tc ? "dmma_f64" : "subwarp_f64";
         h->launches += 1;
-        return gen::launch_smoother<double>(g, ill + 1, ill, h->stream, err);
+        return gen_smoother_f64(g, ill + 1, ill, h->stream, err);
     }
     KernelTimer kt(h, BKF_KERNEL_SMOOTHER);
     h->launches += 1;
-    return gen::launch_smoother<double>(g, nullptr, nullptr, h->stream, err);
+    return gen_smoother_f64(g, nullptr, nullptr, h->stream, err);
 }
 static int run_smoother(bkf_handle* h, const KArgs<float>& g, const char** err) {
     KernelTimer kt(h, BKF_KERNEL_SMOOTHER);

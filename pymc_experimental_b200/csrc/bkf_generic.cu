@@ -7,18 +7,84 @@
 //
 // Formulas: see bkf_common.cuh for the reference file:line map; the adjoint recurrences are those of
 // SURVEY.md Appendix B (Standard) and their rank-1 analogue (Univariate).
+//
+// The file is compiled twice: as namespace gen (this unit: scalar products, float and double) and, through
+// bkf_generic_tc.cu with BKF_GEN_DMMA defined, as namespace gent (double only), where every dense product of at least
+// 8 x 8 x 8 runs on the FP64 tensor pipe.  The dispatcher sends m >= 16 to gent: the tile products are 1.6 x (m = 16) to
+// 2.1 x (m = 32) faster there, but they cost the kernels ~120 more registers, which halves the occupancy the small shapes
+// live on (m = 8 and m = 4 measured 1.9 x slower in one combined build).
 #include "bkf_common.cuh"
 #include "bkf_launch.h"
 
+#ifndef BKF_GEN_NS
+#define BKF_GEN_NS gen
+#endif
+
 namespace bkf {
-namespace gen {
+namespace BKF_GEN_NS {
 
 enum { SET = 0, ADD = 1, SUB = 2 };
+
+// The same product on the FP64 tensor pipe (mma.sync.m8n8k4.f64, SASS DMMA.8x8x4): the warp walks the 8 x 8 output tiles,
+// every DMMA takes one A and one B element per lane straight from shared memory (arbitrary strides, zero-filled borders),
+// 256 FMAs for two loads per lane where the scalar loop below spends two loads per FMA.  Two tiles are in flight per
+// round so that their dependent accumulator chains overlap.  Same sums in a different order: equal to rounding.
+template <int MODE>
+__device__ __forceinline__ void mm_dmma(double* __restrict__ C, const double* __restrict__ A, int as0, int as1,
+                                        const double* __restrict__ Bm, int bs0, int bs1, int M, int N, int K, int lane) {
+    const int g = lane >> 2, t = lane & 3;
+    const int tn = (N + 7) >> 3, ntile = ((M + 7) >> 3) * tn;
+    for (int tile = 0; tile < ntile; tile += 2) {
+        const int i0 = (tile / tn) * 8, j0 = (tile % tn) * 8;
+        const bool two = tile + 1 < ntile;
+        const int i1 = two ? ((tile + 1) / tn) * 8 : i0, j1 = two ? ((tile + 1) % tn) * 8 : j0;
+        double c00 = 0.0, c01 = 0.0, c10 = 0.0, c11 = 0.0;
+        const bool ra0 = i0 + g < M, rb0 = j0 + g < N, ra1 = i1 + g < M, rb1 = j1 + g < N;
+        const double* a0 = A + (i0 + g) * as0;
+        const double* b0 = Bm + (j0 + g) * bs1;
+        const double* a1 = A + (i1 + g) * as0;
+        const double* b1 = Bm + (j1 + g) * bs1;
+        for (int k0 = 0; k0 < K; k0 += 4) {
+            const int k = k0 + t;
+            const bool kk = k < K;
+            const double x0 = (ra0 && kk) ? a0[k * as1] : 0.0, y0 = (rb0 && kk) ? b0[k * bs0] : 0.0;
+            const double x1 = (ra1 && kk) ? a1[k * as1] : 0.0, y1 = (rb1 && kk) ? b1[k * bs0] : 0.0;
+            asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                : "+d"(c00), "+d"(c01) : "d"(x0), "d"(y0));
+            asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                : "+d"(c10), "+d"(c11) : "d"(x1), "d"(y1));
+        }
+        auto put = [&](int i, int j, double v) {
+            if (i < M && j < N) {
+                double* c = C + i * N + j;
+                if (MODE == SET) *c = v;
+                else if (MODE == ADD) *c += v;
+                else *c -= v;
+            }
+        };
+        put(i0 + g, j0 + 2 * t, c00);
+        put(i0 + g, j0 + 2 * t + 1, c01);
+        if (two) {
+            put(i1 + g, j1 + 2 * t, c10);
+            put(i1 + g, j1 + 2 * t + 1, c11);
+        }
+    }
+    __syncwarp();
+}
 
 // C[M,N] (row-major) (op)= sum_k A(i,k) * B(k,j) with A(i,k) = A[i*as0 + k*as1], B(k,j) = B[k*bs0 + j*bs1]
 template <int MODE, typename R>
 __device__ __forceinline__ void mm(R* __restrict__ C, const R* __restrict__ A, int as0, int as1,
                                    const R* __restrict__ Bm, int bs0, int bs1, int M, int N, int K, int lane) {
+#ifdef BKF_GEN_DMMA
+    if constexpr (sizeof(R) == 8) {
+        if (M >= 8 && N >= 8 && K >= 8) {  // (smaller products: a DMMA tile would be mostly padding)
+            mm_dmma<MODE>(reinterpret_cast<double*>(C), reinterpret_cast<const double*>(A), as0, as1,
+                          reinterpret_cast<const double*>(Bm), bs0, bs1, M, N, K, lane);
+            return;
+        }
+    }
+#endif
     for (int idx = lane; idx < M * N; idx += 32) {
         int i = idx / N, j = idx - i * N;
         const R* a = A + i * as0;
@@ -859,11 +925,13 @@ int launch_smoother(const KArgs<R>& g, const int* list, const int* count, cudaSt
 }
 
 template int launch_forward<double>(const KArgs<double>&, cudaStream_t, const char**);
-template int launch_forward<float>(const KArgs<float>&, cudaStream_t, const char**);
 template int launch_backward<double>(const KArgs<double>&, cudaStream_t, const char**);
-template int launch_backward<float>(const KArgs<float>&, cudaStream_t, const char**);
 template int launch_smoother<double>(const KArgs<double>&, const int*, const int*, cudaStream_t, const char**);
+#ifndef BKF_GEN_DMMA
+template int launch_forward<float>(const KArgs<float>&, cudaStream_t, const char**);
+template int launch_backward<float>(const KArgs<float>&, cudaStream_t, const char**);
 template int launch_smoother<float>(const KArgs<float>&, const int*, const int*, cudaStream_t, const char**);
+#endif
 
-}  // namespace gen
+}  // namespace BKF_GEN_NS
 }  // namespace bkf

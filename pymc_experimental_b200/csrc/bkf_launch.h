@@ -11,6 +11,11 @@ template <typename R> int launch_backward(const KArgs<R>& g, cudaStream_t stream
 // list / count (nullable): only the series list[0 .. *count), both on the device
 template <typename R> int launch_smoother(const KArgs<R>& g, const int* list, const int* count, cudaStream_t stream, const char** err);
 }  // namespace gen
+namespace gent {  // the same kernels with DMMA tile products, float64 (bkf_generic_tc.cu); the dispatcher uses them for m >= 16
+template <typename R> int launch_forward(const KArgs<R>& g, cudaStream_t stream, const char** err);
+template <typename R> int launch_backward(const KArgs<R>& g, cudaStream_t stream, const char** err);
+template <typename R> int launch_smoother(const KArgs<R>& g, const int* list, const int* count, cudaStream_t stream, const char** err);
+}  // namespace gent
 namespace sq {  // square-root filter, CTA per series (bkf_sqrt.cu)
 size_t traj_record_elems_host(int m, int p);  // forward-sweep record kept for the adjoint (a, Pc, R factors)
 template <typename R> int launch_forward(const KArgs<R>& g, cudaStream_t stream, const char** err);
