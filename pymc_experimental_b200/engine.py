@@ -283,7 +283,11 @@ class KalmanEngine:
         world = getattr(self, "_comm_world", 0)
         if out is None:
             out = torch.empty((world,) + tuple(send.shape), dtype=send.dtype, device=send.device)
-        self._check(self.lib.bkf_set_stream(self.h, C.c_void_p(torch.cuda.current_stream(send.device).cuda_stream)))
+        stream = torch.cuda.current_stream(send.device).cuda_stream
+        if self._stream != stream:  # the same bookkeeping as use_torch_stream: later calls must see the change
+            torch.cuda.synchronize(self.device)
+            self.set_stream(stream)
+            self._stream = stream
         self._check(self.lib.bkf_comm_allgather(self.h, C.c_void_p(send.data_ptr()), C.c_void_p(out.data_ptr()),
                                                 send.numel(), code))
         return out
