@@ -259,6 +259,11 @@ static int gen_smoother_f64(const KArgs<double>& g, const int* list, const int* 
     return g.m >= 16 ? gent::launch_smoother<double>(g, list, count, st, err) : gen::launch_smoother<double>(g, list, count, st, err);
 }
 
+// "generic_cta" when the launcher gives a series more than one warp (large arenas, bkf_generic.cu pick_w)
+static const char* gen_path_f64(const KArgs<double>& g) {
+    return g.m >= 16 && (gent::width(g, false) > 1 || gent::width(g, true) > 1) ? "generic_cta" : "generic_warp";
+}
+
 // ----------------------------------------------------------------------------------------------------
 // kernel-family dispatch: specialised register-tiled kernels where they exist, the generic path otherwise
 static int run_forward(bkf_handle* h, const KArgs<double>& g, const char** err) {
@@ -278,7 +283,7 @@ static int run_forward(bkf_handle* h, const KArgs<double>& g, const char** err) 
                        (tps::supported(g.kind, g.m, g.p) || tc::supported(g.kind, g.m, g.p) ||
                         sw::supported(g.kind, g.m, g.p));
     if (g.tv_mask && !tc_tv) {
-        h->path = "generic_warp";
+        h->path = gen_path_f64(g);
         return gen_forward_f64(g, h->stream, err);
     }
     if (tps::supported(g.kind, g.m, g.p)) {
@@ -293,7 +298,7 @@ static int run_forward(bkf_handle* h, const KArgs<double>& g, const char** err) 
         h->path = "subwarp_f64";
         return sw::launch_f64(g, false, h->stream, err);
     }
-    h->path = "generic_warp";
+    h->path = gen_path_f64(g);
     return gen_forward_f64(g, h->stream, err);
 }
 static int run_forward(bkf_handle* h, const KArgs<float>& g, const char** err) {

@@ -19,24 +19,62 @@
 #ifndef BKF_GEN_NS
 #define BKF_GEN_NS gen
 #endif
+#ifndef BKF_GEN_W
+#define BKF_GEN_W 1
+#endif
+#include <cstdlib>
 
 namespace bkf {
 namespace BKF_GEN_NS {
 
 enum { SET = 0, ADD = 1, SUB = 2 };
 
+// Who runs one series.  W = 1: one warp (several series per CTA, the original mapping; the barrier is __syncwarp).
+// W > 1: one CTA of W warps (one series per CTA, the barrier is __syncthreads): chosen by the launcher when the arena of
+// a series is so large that only a few of them fit one SM, so that the SM still has W warps per series to issue from.
+// L.v is the thread's index within the group, 32 * W the stride of every element loop.
+template <int W>
+struct Lane { int v; };
+
+template <int W>
+__device__ __forceinline__ void gsync() {
+    if constexpr (W == 1) __syncwarp();
+    else __syncthreads();
+}
+
+// Three sums over the group at once (every thread gets the totals).  red: 3 * W values of scratch.
+template <int W, typename R>
+__device__ __forceinline__ void gsum3(R& a, R& b, R& c, R* red, int lane) {
+    a = warp_sum(a); b = warp_sum(b); c = warp_sum(c);
+    if constexpr (W > 1) {
+        if ((lane & 31) == 0) {
+            red[3 * (lane >> 5)] = a; red[3 * (lane >> 5) + 1] = b; red[3 * (lane >> 5) + 2] = c;
+        }
+        __syncthreads();
+        a = red[0]; b = red[1]; c = red[2];
+#pragma unroll
+        for (int w = 1; w < W; ++w) { a += red[3 * w]; b += red[3 * w + 1]; c += red[3 * w + 2]; }
+        __syncthreads();
+    }
+}
+
 // The same product on the FP64 tensor pipe (mma.sync.m8n8k4.f64, SASS DMMA.8x8x4): the warp walks the 8 x 8 output tiles,
 // every DMMA takes one A and one B element per lane straight from shared memory (arbitrary strides, zero-filled borders),
 // 256 FMAs for two loads per lane where the scalar loop below spends two loads per FMA.  Two tiles are in flight per
 // round so that their dependent accumulator chains overlap.  Same sums in a different order: equal to rounding.
-template <int MODE>
+template <int MODE, int W>
 __device__ __forceinline__ void mm_dmma(double* __restrict__ C, const double* __restrict__ A, int as0, int as1,
-                                        const double* __restrict__ Bm, int bs0, int bs1, int M, int N, int K, int lane) {
-    const int g = lane >> 2, t = lane & 3;
+                                        const double* __restrict__ Bm, int bs0, int bs1, int M, int N, int K, Lane<W> L) {
+    const int lane = L.v;
+    constexpr int NT = 32 * W;
+    (void)lane; (void)NT;
+    const int g = (lane & 31) >> 2, t = lane & 3;
     const int tn = (N + 7) >> 3, ntile = ((M + 7) >> 3) * tn;
-    for (int tile = 0; tile < ntile; tile += 2) {
+    // two tiles in flight per warp, or one when the group has a warp for every tile
+    const int per = (W > 1 && ntile <= W) ? 1 : 2;
+    for (int tile = per * (lane >> 5); tile < ntile; tile += per * W) {
         const int i0 = (tile / tn) * 8, j0 = (tile % tn) * 8;
-        const bool two = tile + 1 < ntile;
+        const bool two = per == 2 && tile + 1 < ntile;
         const int i1 = two ? ((tile + 1) / tn) * 8 : i0, j1 = two ? ((tile + 1) % tn) * 8 : j0;
         double c00 = 0.0, c01 = 0.0, c10 = 0.0, c11 = 0.0;
         const bool ra0 = i0 + g < M, rb0 = j0 + g < N, ra1 = i1 + g < M, rb1 = j1 + g < N;
@@ -69,23 +107,26 @@ __device__ __forceinline__ void mm_dmma(double* __restrict__ C, const double* __
             put(i1 + g, j1 + 2 * t + 1, c11);
         }
     }
-    __syncwarp();
+    gsync<W>();
 }
 
 // C[M,N] (row-major) (op)= sum_k A(i,k) * B(k,j) with A(i,k) = A[i*as0 + k*as1], B(k,j) = B[k*bs0 + j*bs1]
-template <int MODE, typename R>
+template <int MODE, int W, typename R>
 __device__ __forceinline__ void mm(R* __restrict__ C, const R* __restrict__ A, int as0, int as1,
-                                   const R* __restrict__ Bm, int bs0, int bs1, int M, int N, int K, int lane) {
+                                   const R* __restrict__ Bm, int bs0, int bs1, int M, int N, int K, Lane<W> L) {
+    const int lane = L.v;
+    constexpr int NT = 32 * W;
+    (void)lane; (void)NT;
 #ifdef BKF_GEN_DMMA
     if constexpr (sizeof(R) == 8) {
         if (M >= 8 && N >= 8 && K >= 8) {  // (smaller products: a DMMA tile would be mostly padding)
-            mm_dmma<MODE>(reinterpret_cast<double*>(C), reinterpret_cast<const double*>(A), as0, as1,
-                          reinterpret_cast<const double*>(Bm), bs0, bs1, M, N, K, lane);
+            mm_dmma<MODE, W>(reinterpret_cast<double*>(C), reinterpret_cast<const double*>(A), as0, as1,
+                          reinterpret_cast<const double*>(Bm), bs0, bs1, M, N, K, L);
             return;
         }
     }
 #endif
-    for (int idx = lane; idx < M * N; idx += 32) {
+    for (int idx = lane; idx < M * N; idx += NT) {
         int i = idx / N, j = idx - i * N;
         const R* a = A + i * as0;
         const R* b = Bm + j * bs1;
@@ -95,70 +136,86 @@ __device__ __forceinline__ void mm(R* __restrict__ C, const R* __restrict__ A, i
         else if (MODE == ADD) C[idx] += acc;
         else C[idx] -= acc;
     }
-    __syncwarp();
+    gsync<W>();
 }
 
 // y[M] (op)= sum_k A(i,k) x[k]
-template <int MODE, typename R>
+template <int MODE, int W, typename R>
 __device__ __forceinline__ void mv(R* __restrict__ y, const R* __restrict__ A, int as0, int as1,
-                                   const R* __restrict__ x, int M, int K, int lane) {
-    for (int i = lane; i < M; i += 32) {
+                                   const R* __restrict__ x, int M, int K, Lane<W> L) {
+    const int lane = L.v;
+    constexpr int NT = 32 * W;
+    (void)lane; (void)NT;
+    for (int i = lane; i < M; i += NT) {
         R acc = 0;
         for (int k = 0; k < K; ++k) acc = fma(A[i * as0 + k * as1], x[k], acc);
         if (MODE == SET) y[i] = acc;
         else if (MODE == ADD) y[i] += acc;
         else y[i] -= acc;
     }
-    __syncwarp();
+    gsync<W>();
 }
 
-template <typename R>
-__device__ __forceinline__ void wcopy(R* __restrict__ dst, const R* __restrict__ src, int n, int lane) {
-    for (int i = lane; i < n; i += 32) dst[i] = src[i];
-    __syncwarp();
+template <typename R, int W>
+__device__ __forceinline__ void wcopy(R* __restrict__ dst, const R* __restrict__ src, int n, Lane<W> L) {
+    const int lane = L.v;
+    constexpr int NT = 32 * W;
+    (void)lane; (void)NT;
+    for (int i = lane; i < n; i += NT) dst[i] = src[i];
+    gsync<W>();
 }
-template <typename R>
-__device__ __forceinline__ void wzero(R* dst, int n, int lane) {
-    for (int i = lane; i < n; i += 32) dst[i] = 0;
-    __syncwarp();
+template <typename R, int W>
+__device__ __forceinline__ void wzero(R* dst, int n, Lane<W> L) {
+    const int lane = L.v;
+    constexpr int NT = 32 * W;
+    (void)lane; (void)NT;
+    for (int i = lane; i < n; i += NT) dst[i] = 0;
+    gsync<W>();
 }
 
 // D = 0.5 (X + X^T) [+ Add] [+ jit * I]      (utilities.py:57-59 followed by stabilize :50-54)
-template <typename R>
+template <typename R, int W>
 __device__ __forceinline__ void sym_into(R* __restrict__ D, const R* __restrict__ X, const R* __restrict__ Add,
-                                         R jit, int m, int lane) {
-    for (int idx = lane; idx < m * m; idx += 32) {
+                                         R jit, int m, Lane<W> L) {
+    const int lane = L.v;
+    constexpr int NT = 32 * W;
+    (void)lane; (void)NT;
+    for (int idx = lane; idx < m * m; idx += NT) {
         int i = idx / m, j = idx - i * m;
         R v = R(0.5) * (X[idx] + X[j * m + i]);
         if (Add) v += Add[idx];
         if (i == j) v += jit;
         D[idx] = v;
     }
-    __syncwarp();
+    gsync<W>();
 }
 
-// In-place lower Cholesky of the k x k matrix A (reads the lower triangle), executed by lane 0.
-// Returns false when a pivot is not positive.
-template <typename R>
-__device__ bool chol_lower(R* A, int k, int lane) {
-    int ok = 1;
-    if (lane == 0) {
+// In-place lower Cholesky of the k x k matrix A (reads the lower triangle), column by column on the first warp of the
+// group: every lane forms the pivot, the lanes split the rows below it (the sums run in the order of the one-lane loop
+// this replaces, so the factor has the same bits).  Returns false when a pivot is not positive (its entry is NaN then).
+template <typename R, int W>
+__device__ bool chol_lower(R* A, int k, Lane<W> L) {
+    const int lane = L.v;
+    if (lane < 32) {
         for (int j = 0; j < k; ++j) {
             R s = A[j * k + j];
             for (int q = 0; q < j; ++q) s -= A[j * k + q] * A[j * k + q];
-            if (!(s > 0)) { ok = 0; s = R(NAN); }
-            R ljj = sqrt(s);
-            A[j * k + j] = ljj;
-            for (int i = j + 1; i < k; ++i) {
+            if (!(s > 0)) s = R(NAN);
+            const R ljj = sqrt(s);
+            __syncwarp();  // every lane has read the pivot before it is overwritten
+            for (int i = j + 1 + lane; i < k; i += 32) {
                 R t = A[i * k + j];
                 for (int q = 0; q < j; ++q) t -= A[i * k + q] * A[j * k + q];
                 A[i * k + j] = t / ljj;
             }
+            if (lane == 0) A[j * k + j] = ljj;
+            __syncwarp();
         }
     }
-    ok = __shfl_sync(0xffffffffu, ok, 0);
-    __syncwarp();
-    return ok != 0;
+    gsync<W>();
+    bool ok = true;
+    for (int j = 0; j < k; ++j) ok = ok && !isnan(A[j * k + j]);
+    return ok;
 }
 
 // x <- (L L^T)^{-1} x for one right-hand side held by ONE lane (x has stride xs).
@@ -223,9 +280,12 @@ __device__ void carve(Arena<R>& A, R* s, int m, int p, int r, bool backward) {
 }
 
 // dst = sym(R Q R^T) for global-memory R [m,r], Q [r,r] (once per series; no r <= m assumption). tmp: m*m.
-template <typename R>
-__device__ void rqr_sym(R* dst, R* tmp, const R* __restrict__ Rg, const R* __restrict__ Qg, int m, int r, int lane) {
-    for (int idx = lane; idx < m * m; idx += 32) {
+template <typename R, int W>
+__device__ void rqr_sym(R* dst, R* tmp, const R* __restrict__ Rg, const R* __restrict__ Qg, int m, int r, Lane<W> L) {
+    const int lane = L.v;
+    constexpr int NT = 32 * W;
+    (void)lane; (void)NT;
+    for (int idx = lane; idx < m * m; idx += NT) {
         int i = idx / m, j = idx - i * m;
         R acc = 0;
         for (int k = 0; k < r; ++k) {
@@ -235,38 +295,44 @@ __device__ void rqr_sym(R* dst, R* tmp, const R* __restrict__ Rg, const R* __res
         }
         tmp[idx] = acc;
     }
-    __syncwarp();
-    sym_into<R>(dst, tmp, nullptr, R(0), m, lane);
+    gsync<W>();
+    sym_into<R>(dst, tmp, nullptr, R(0), m, L);
 }
 
 // Load T, Z, H, c, d and RQR = sym(R Q R^T) (kalman_filter.py:408, second term) for series b at step t.
 // all = true loads everything (first step of a sweep); otherwise only the time-varying parameters are refreshed
 // (kalman_filter.py:110-142: the scan hands matrix[t] of every sequence parameter to kalman_step).
-template <typename R>
-__device__ void load_params(const KArgs<R>& g, Arena<R>& A, int b, int t, bool all, int lane) {
+template <typename R, int W>
+__device__ void load_params(const KArgs<R>& g, Arena<R>& A, int b, int t, bool all, Lane<W> L) {
+    const int lane = L.v;
+    constexpr int NT = 32 * W;
+    (void)lane; (void)NT;
     const int m = g.m, p = g.p, r = g.r, n = g.n;
     const unsigned tv = g.tv_mask;
     auto at = [&](const R* base, int which, size_t sz) {
         return param_ptr_t(base, g.shared_mask, tv, which, b, t, n, sz);
     };
     auto need = [&](int which) { return all || ((tv >> which) & 1u); };
-    if (need(BKF_PARAM_T)) wcopy(A.T, at(g.T, BKF_PARAM_T, (size_t)m * m), m * m, lane);
-    if (need(BKF_PARAM_Z)) wcopy(A.Z, at(g.Z, BKF_PARAM_Z, (size_t)p * m), p * m, lane);
-    if (need(BKF_PARAM_H)) wcopy(A.H, at(g.H, BKF_PARAM_H, (size_t)p * p), p * p, lane);
-    if (need(BKF_PARAM_C)) wcopy(A.c, at(g.c, BKF_PARAM_C, (size_t)m), m, lane);
-    if (need(BKF_PARAM_D)) wcopy(A.d, at(g.d, BKF_PARAM_D, (size_t)p), p, lane);
+    if (need(BKF_PARAM_T)) wcopy(A.T, at(g.T, BKF_PARAM_T, (size_t)m * m), m * m, L);
+    if (need(BKF_PARAM_Z)) wcopy(A.Z, at(g.Z, BKF_PARAM_Z, (size_t)p * m), p * m, L);
+    if (need(BKF_PARAM_H)) wcopy(A.H, at(g.H, BKF_PARAM_H, (size_t)p * p), p * p, L);
+    if (need(BKF_PARAM_C)) wcopy(A.c, at(g.c, BKF_PARAM_C, (size_t)m), m, L);
+    if (need(BKF_PARAM_D)) wcopy(A.d, at(g.d, BKF_PARAM_D, (size_t)p), p, L);
     if (need(BKF_PARAM_R) || need(BKF_PARAM_Q))
-        rqr_sym(A.RQR, A.Y, at(g.Rm, BKF_PARAM_R, (size_t)m * r), at(g.Q, BKF_PARAM_Q, (size_t)r * r), m, r, lane);
+        rqr_sym(A.RQR, A.Y, at(g.Rm, BKF_PARAM_R, (size_t)m * r), at(g.Q, BKF_PARAM_Q, (size_t)r * r), m, r, L);
 }
 
 // a+ = T af + c ; P+ = sym(T Pf T^T) + RQR         (kalman_filter.py:407-408).  Leaves X = T Pf.
-template <typename R>
-__device__ __forceinline__ void predict(Arena<R>& A, int m, int lane) {
-    mv<SET>(A.a, A.T, m, 1, A.af, m, m, lane);
-    for (int i = lane; i < m; i += 32) A.a[i] += A.c[i];
-    mm<SET>(A.X, A.T, m, 1, A.Pf, m, 1, m, m, m, lane);
-    mm<SET>(A.Y, A.X, m, 1, A.T, 1, m, m, m, m, lane);
-    sym_into<R>(A.P, A.Y, A.RQR, R(0), m, lane);
+template <typename R, int W>
+__device__ __forceinline__ void predict(Arena<R>& A, int m, Lane<W> L) {
+    const int lane = L.v;
+    constexpr int NT = 32 * W;
+    (void)lane; (void)NT;
+    mv<SET>(A.a, A.T, m, 1, A.af, m, m, L);
+    for (int i = lane; i < m; i += NT) A.a[i] += A.c[i];
+    mm<SET>(A.X, A.T, m, 1, A.Pf, m, 1, m, m, m, L);
+    mm<SET>(A.Y, A.X, m, 1, A.T, 1, m, m, m, m, L);
+    sym_into<R>(A.P, A.Y, A.RQR, R(0), m, L);
 }
 
 // ----------------------------------------------------------------------------------------------------
@@ -274,25 +340,35 @@ __device__ __forceinline__ void predict(Arena<R>& A, int m, int lane) {
 // In: A.a, A.P, y_t.  Out: A.af, A.Pf (jittered), A.v, A.Zm, A.Hm, A.PZT, A.F, A.Lf, A.K, A.Lm, A.wv.
 // Returns ll; *flag_out = all-missing; *ok = F positive definite.
 // ----------------------------------------------------------------------------------------------------
-template <typename R>
+// Right-hand sides of the update's solve with F (rows of P Z^T, v, and the identity when the adjoint wants F^{-1}) and
+// whether their transposed copy fits the X..Y scratch (2 m^2 values; it does unless p is about m).
+__host__ __device__ inline int solve_rhs(int m, int p, bool finv) { return m + 1 + (finv ? p : 0); }
+__host__ __device__ inline bool solve_scratch_fits(int m, int p, bool finv) {
+    return (size_t)p * (solve_rhs(m, p, finv) | 1) <= 2 * (size_t)m * m;
+}
+
+template <typename R, int W>
 __device__ R std_update(const KArgs<R>& g, Arena<R>& A, const R* yt, R* obs_mu, R* obs_cov, bool* flag_out,
-                        bool* ok, int lane) {
+                        bool* ok, R* Finv_out, Lane<W> L) {
+    const int lane = L.v;
+    constexpr int NT = 32 * W;
+    (void)lane; (void)NT;
     const int m = g.m, p = g.p;
-    for (int o = lane; o < p; o += 32) {
+    for (int o = lane; o < p; o += NT) {
         R yv = yt[o];
         bool miss = is_missing(yv, g.fill, true);
         A.w[o] = miss ? R(0) : R(1);
         A.ym[o] = miss ? R(0) : yv;
     }
-    __syncwarp();
+    gsync<W>();
     R nobs = 0;
     for (int o = 0; o < p; ++o) nobs += A.w[o];
     const bool flag = (nobs == R(0));
-    for (int idx = lane; idx < p * m; idx += 32) A.Zm[idx] = A.w[idx / m] * A.Z[idx];
-    for (int idx = lane; idx < p * p; idx += 32) A.Hm[idx] = A.w[idx / p] * A.H[idx];
-    __syncwarp();
+    for (int idx = lane; idx < p * m; idx += NT) A.Zm[idx] = A.w[idx / m] * A.Z[idx];
+    for (int idx = lane; idx < p * p; idx += NT) A.Hm[idx] = A.w[idx / p] * A.H[idx];
+    gsync<W>();
     // y_hat = d + Zm a ; v = ym - y_hat
-    for (int o = lane; o < p; o += 32) {
+    for (int o = lane; o < p; o += NT) {
         R acc = 0;
         for (int j = 0; j < m; ++j) acc = fma(A.Zm[o * m + j], A.a[j], acc);
         R yh = A.d[o] + acc;
@@ -300,47 +376,70 @@ __device__ R std_update(const KArgs<R>& g, Arena<R>& A, const R* yt, R* obs_mu, 
         if (obs_mu) obs_mu[o] = yh;
     }
     // PZT = P Zm^T ; F = Zm PZT + (Hm + eps I)
-    mm<SET>(A.PZT, A.P, m, 1, A.Zm, 1, m, m, p, m, lane);
-    mm<SET>(A.F, A.Zm, m, 1, A.PZT, p, 1, p, p, m, lane);
-    for (int idx = lane; idx < p * p; idx += 32) {
+    mm<SET>(A.PZT, A.P, m, 1, A.Zm, 1, m, m, p, m, L);
+    mm<SET>(A.F, A.Zm, m, 1, A.PZT, p, 1, p, p, m, L);
+    for (int idx = lane; idx < p * p; idx += NT) {
         int o = idx / p, q = idx - o * p;
         R f = A.F[idx] + (A.Hm[idx] + (o == q ? g.jitter : R(0)));
         A.F[idx] = f;
         A.Lf[idx] = f;
         if (obs_cov) obs_cov[idx] = f;
     }
-    __syncwarp();
-    *ok = chol_lower(A.Lf, p, lane);
-    // K = PZT F^{-1} (row i of K solves F k = pzt_i, F symmetric) ; wv = F^{-1} v
-    for (int idx = lane; idx < m * p; idx += 32) A.K[idx] = A.PZT[idx];
-    for (int o = lane; o < p; o += 32) A.wv[o] = A.v[o];
-    __syncwarp();
-    for (int i = lane; i < m + 1; i += 32) {
-        if (i < m) chol_solve_vec(A.Lf, p, A.K + i * p, 1);
-        else chol_solve_vec(A.Lf, p, A.wv, 1);
+    gsync<W>();
+    *ok = chol_lower(A.Lf, p, L);
+    // K = PZT F^{-1} (row i of K solves F k = pzt_i, F symmetric) ; wv = F^{-1} v ; for the adjoint also Finv = F^{-1}.
+    // One right-hand side per thread, all solved at once in a transposed scratch (X..Y, free here) whose odd leading
+    // dimension puts the threads' columns into distinct banks (in place, row i of K sits p doubles from row i + 1: every
+    // access of the substitution was a 16-way bank conflict at p = 16).
+    const int nrhs = solve_rhs(m, p, Finv_out != nullptr), ld = nrhs | 1;
+    if (solve_scratch_fits(m, p, Finv_out != nullptr)) {
+        R* S = A.X;
+        for (int idx = lane; idx < p * nrhs; idx += NT) {
+            const int q = idx / nrhs, i = idx - q * nrhs;
+            S[q * ld + i] = i < m ? A.PZT[i * p + q] : (i == m ? A.v[q] : (i - m - 1 == q ? R(1) : R(0)));
+        }
+        gsync<W>();
+        for (int i = lane; i < nrhs; i += NT) chol_solve_vec(A.Lf, p, S + i, ld);
+        gsync<W>();
+        for (int idx = lane; idx < p * nrhs; idx += NT) {
+            const int q = idx / nrhs, i = idx - q * nrhs;
+            const R x = S[q * ld + i];
+            if (i < m) A.K[i * p + q] = x;
+            else if (i == m) A.wv[q] = x;
+            else Finv_out[q * p + (i - m - 1)] = x;
+        }
+        gsync<W>();
+    } else {
+        for (int idx = lane; idx < m * p; idx += NT) A.K[idx] = A.PZT[idx];
+        for (int o = lane; o < p; o += NT) A.wv[o] = A.v[o];
+        gsync<W>();
+        for (int i = lane; i < m + 1; i += NT) {
+            if (i < m) chol_solve_vec(A.Lf, p, A.K + i * p, 1);
+            else chol_solve_vec(A.Lf, p, A.wv, 1);
+        }
+        gsync<W>();
     }
-    __syncwarp();
     // Lm = I - K Zm ; af = a + K v
-    mm<SET>(A.Lm, A.K, p, 1, A.Zm, m, 1, m, m, p, lane);
-    for (int idx = lane; idx < m * m; idx += 32) A.Lm[idx] = ((idx / m) == (idx % m) ? R(1) : R(0)) - A.Lm[idx];
-    for (int i = lane; i < m; i += 32) {
+    mm<SET>(A.Lm, A.K, p, 1, A.Zm, m, 1, m, m, p, L);
+    for (int idx = lane; idx < m * m; idx += NT) A.Lm[idx] = ((idx / m) == (idx % m) ? R(1) : R(0)) - A.Lm[idx];
+    for (int i = lane; i < m; i += NT) {
         R acc = 0;
         for (int o = 0; o < p; ++o) acc = fma(A.K[i * p + o], A.v[o], acc);
         A.af[i] = A.a[i] + acc;
     }
-    __syncwarp();
+    gsync<W>();
     // Pf = sym(Lm P Lm^T) + sym(K Hm K^T) + eps I
-    mm<SET>(A.X, A.Lm, m, 1, A.P, m, 1, m, m, m, lane);
-    mm<SET>(A.Y, A.X, m, 1, A.Lm, 1, m, m, m, m, lane);
-    mm<SET>(A.KH, A.K, p, 1, A.Hm, p, 1, m, p, p, lane);
-    mm<SET>(A.X, A.KH, p, 1, A.K, 1, p, m, m, p, lane);
-    for (int idx = lane; idx < m * m; idx += 32) {
+    mm<SET>(A.X, A.Lm, m, 1, A.P, m, 1, m, m, m, L);
+    mm<SET>(A.Y, A.X, m, 1, A.Lm, 1, m, m, m, m, L);
+    mm<SET>(A.KH, A.K, p, 1, A.Hm, p, 1, m, p, p, L);
+    mm<SET>(A.X, A.KH, p, 1, A.K, 1, p, m, m, p, L);
+    for (int idx = lane; idx < m * m; idx += NT) {
         int i = idx / m, j = idx - i * m;
         R v1 = R(0.5) * (A.Y[idx] + A.Y[j * m + i]);
         R v2 = R(0.5) * (A.X[idx] + A.X[j * m + i]);
         A.Pf[idx] = (v1 + v2) + (i == j ? g.jitter : R(0));
     }
-    __syncwarp();
+    gsync<W>();
     // ll = -0.5 (log 2pi + log det F + v' F^{-1} v)   (:609-615; log2pi counted once)
     R quad = 0, logdet = 0;
     for (int o = 0; o < p; ++o) {
@@ -356,17 +455,20 @@ __device__ R std_update(const KArgs<R>& g, Arena<R>& A, const R* yt, R* obs_mu, 
 // UnivariateFilter inner loop + symmetrise/stabilise (kalman_filter.py:769-815).
 // In: A.a, A.P.  Out: A.af, A.Pf (sym + jitter), A.Pu (P before symmetrisation), A.Kst/Fst/vst/zfst, A.w.
 // ----------------------------------------------------------------------------------------------------
-template <typename R>
-__device__ R uni_update(const KArgs<R>& g, Arena<R>& A, const R* yt, R* obs_mu, R* obs_cov, int lane) {
+template <typename R, int W>
+__device__ R uni_update(const KArgs<R>& g, Arena<R>& A, const R* yt, R* obs_mu, R* obs_cov, Lane<W> L) {
+    const int lane = L.v;
+    constexpr int NT = 32 * W;
+    (void)lane; (void)NT;
     const int m = g.m, p = g.p;
-    for (int o = lane; o < p; o += 32) {
+    for (int o = lane; o < p; o += NT) {
         R yv = yt[o];
         bool miss = isnan(yv);  // :792 -- the fill value is ignored here
         A.w[o] = miss ? R(0) : R(1);
         A.ym[o] = miss ? R(0) : yv;
     }
-    wcopy(A.af, A.a, m, lane);
-    wcopy(A.Pu, A.P, m * m, lane);
+    wcopy(A.af, A.a, m, L);
+    wcopy(A.Pu, A.P, m * m, L);
     R llsum = 0;
     int nnz = 0;
     for (int o = 0; o < p; ++o) {
@@ -377,23 +479,23 @@ __device__ R uni_update(const KArgs<R>& g, Arena<R>& A, const R* yt, R* obs_mu, 
         yh += A.d[o];
         const R v = A.ym[o] - yh;
         // pz = P z^T  (kept in K row o), F0 = z pz + H_oo
-        for (int i = lane; i < m; i += 32) {
+        for (int i = lane; i < m; i += NT) {
             R acc = 0;
             for (int j = 0; j < m; ++j) acc = fma(A.Pu[i * m + j], wo * z[j], acc);
             A.Kst[o * m + i] = acc;
         }
-        __syncwarp();
+        gsync<W>();
         R F0 = 0;
         for (int j = 0; j < m; ++j) F0 = fma(wo * z[j], A.Kst[o * m + j], F0);
         F0 += wo * A.H[o * p + o];
         const bool zf = (F0 == R(0)) || (wo == R(0));
         const R F = F0 + g.jitter;
         const R keep = zf ? R(0) : R(1);
-        __syncwarp();
-        for (int i = lane; i < m; i += 32) A.Kst[o * m + i] = A.Kst[o * m + i] / F * keep;
-        __syncwarp();
-        for (int i = lane; i < m; i += 32) A.af[i] = fma(A.Kst[o * m + i], v, A.af[i]);
-        for (int idx = lane; idx < m * m; idx += 32) {
+        gsync<W>();
+        for (int i = lane; i < m; i += NT) A.Kst[o * m + i] = A.Kst[o * m + i] / F * keep;
+        gsync<W>();
+        for (int i = lane; i < m; i += NT) A.af[i] = fma(A.Kst[o * m + i], v, A.af[i]);
+        for (int idx = lane; idx < m * m; idx += NT) {
             int i = idx / m, j = idx - i * m;
             A.Pu[idx] -= (A.Kst[o * m + i] * A.Kst[o * m + j]) * F;
         }
@@ -409,56 +511,58 @@ __device__ R uni_update(const KArgs<R>& g, Arena<R>& A, const R* yt, R* obs_mu, 
                 if (obs_cov) obs_cov[0] = F;
             }
         }
-        __syncwarp();
+        gsync<W>();
     }
-    sym_into<R>(A.Pf, A.Pu, nullptr, g.jitter, m, lane);
+    sym_into<R>(A.Pf, A.Pu, nullptr, g.jitter, m, L);
     return R(-0.5) * (R(nnz) * R(kLog2Pi) + llsum);
 }
 
 // ----------------------------------------------------------------------------------------------------
 // forward kernel: standard / univariate
 // ----------------------------------------------------------------------------------------------------
-template <typename R>
-__global__ void forward_kernel(KArgs<R> g, int wpc, size_t arena) {
+template <typename R, int W>
+__global__ void __launch_bounds__(W == 1 ? 128 : 32 * W) forward_kernel(KArgs<R> g, int wpc, size_t arena) {
     extern __shared__ double smem_raw[];
     R* smem = reinterpret_cast<R*>(smem_raw);
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int b = blockIdx.x * wpc + warp;
+    constexpr int NT = 32 * W;
+    const int warp = W == 1 ? threadIdx.x >> 5 : 0, lane = W == 1 ? threadIdx.x & 31 : threadIdx.x;
+    const Lane<W> L{lane};
+    const int b = W == 1 ? blockIdx.x * wpc + warp : blockIdx.x;
     if (b >= g.B) return;
     const int m = g.m, p = g.p, n = g.n;
     const int po = (g.kind == BKF_UNIVARIATE) ? 1 : p;
     Arena<R> A;
     carve(A, smem + (size_t)warp * arena, m, p, g.r, false);
-    wcopy(A.a, param_ptr(g.a0, g.shared_mask, BKF_PARAM_A0, b, (size_t)m), m, lane);
-    wcopy(A.P, param_ptr(g.P0, g.shared_mask, BKF_PARAM_P0, b, (size_t)m * m), m * m, lane);
+    wcopy(A.a, param_ptr(g.a0, g.shared_mask, BKF_PARAM_A0, b, (size_t)m), m, L);
+    wcopy(A.P, param_ptr(g.P0, g.shared_mask, BKF_PARAM_P0, b, (size_t)m * m), m * m, L);
     const R* yb = g.y_shared ? g.y : g.y + (size_t)b * n * p;
     const size_t tstride = (size_t)m + (size_t)m * m;
     R logp = 0;
     int st = 0;
     for (int t = 0; t < n; ++t) {
         const size_t bt = (size_t)b * n + t;
-        if (t == 0 || g.tv_mask) load_params(g, A, b, t, t == 0, lane);
+        if (t == 0 || g.tv_mask) load_params(g, A, b, t, t == 0, L);
         if (g.traj) {
-            wcopy(g.traj + bt * tstride, A.a, m, lane);
-            wcopy(g.traj + bt * tstride + m, A.P, m * m, lane);
+            wcopy(g.traj + bt * tstride, A.a, m, L);
+            wcopy(g.traj + bt * tstride + m, A.P, m * m, L);
         }
-        if (g.pred_a) wcopy(g.pred_a + bt * m, A.a, m, lane);
-        if (g.pred_P) wcopy(g.pred_P + bt * m * m, A.P, m * m, lane);
+        if (g.pred_a) wcopy(g.pred_a + bt * m, A.a, m, L);
+        if (g.pred_P) wcopy(g.pred_P + bt * m * m, A.P, m * m, L);
         R* om = g.obs_mu ? g.obs_mu + bt * po : nullptr;
         R* oc = g.obs_cov ? g.obs_cov + bt * po * po : nullptr;
         R ll;
         if (g.kind == BKF_STANDARD) {
             bool flag, ok;
-            ll = std_update(g, A, yb + (size_t)t * p, om, oc, &flag, &ok, lane);
+            ll = std_update(g, A, yb + (size_t)t * p, om, oc, &flag, &ok, (R*)nullptr, L);
             if (!ok) st |= BKF_STATUS_NOT_PD;
         } else {
-            ll = uni_update(g, A, yb + (size_t)t * p, om, oc, lane);
+            ll = uni_update(g, A, yb + (size_t)t * p, om, oc, L);
         }
-        if (g.filt_a) wcopy(g.filt_a + bt * m, A.af, m, lane);
-        if (g.filt_P) wcopy(g.filt_P + bt * m * m, A.Pf, m * m, lane);
+        if (g.filt_a) wcopy(g.filt_a + bt * m, A.af, m, L);
+        if (g.filt_P) wcopy(g.filt_P + bt * m * m, A.Pf, m * m, L);
         if (g.ll && lane == 0) g.ll[bt] = ll;
         logp += ll;
-        predict(A, m, lane);
+        predict(A, m, L);
     }
     if (!isfinite(logp)) st |= BKF_STATUS_NONFINITE;
     if (lane == 0) {
@@ -470,12 +574,14 @@ __global__ void forward_kernel(KArgs<R> g, int wpc, size_t arena) {
 // ----------------------------------------------------------------------------------------------------
 // backward kernel (standard / univariate): reverse sweep over the stored predictions
 // ----------------------------------------------------------------------------------------------------
-template <typename R>
-__global__ void backward_kernel(KArgs<R> g, int wpc, size_t arena) {
+template <typename R, int W>
+__global__ void __launch_bounds__(W == 1 ? 128 : 32 * W) backward_kernel(KArgs<R> g, int wpc, size_t arena) {
     extern __shared__ double smem_raw[];
     R* smem = reinterpret_cast<R*>(smem_raw);
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int b = blockIdx.x * wpc + warp;
+    constexpr int NT = 32 * W;
+    const int warp = W == 1 ? threadIdx.x >> 5 : 0, lane = W == 1 ? threadIdx.x & 31 : threadIdx.x;
+    const Lane<W> L{lane};
+    const int b = W == 1 ? blockIdx.x * wpc + warp : blockIdx.x;
     if (b >= g.B) return;
     const int m = g.m, p = g.p, r = g.r, n = g.n;
     Arena<R> A;
@@ -486,37 +592,37 @@ __global__ void backward_kernel(KArgs<R> g, int wpc, size_t arena) {
     // gradient of a time-varying parameter has a time axis: element offset of (b, t) in units of one parameter
     auto grec = [&](int which, int t) { return is_tv(which) ? (size_t)b * n + t : (size_t)b; };
     if (tvRQ) {  // accumulated in place (one lane owns each element; the sweep over t is sequential)
-        if (g.g_R && !is_tv(BKF_PARAM_R)) wzero(g.g_R + (size_t)b * m * r, m * r, lane);
-        if (g.g_Q && !is_tv(BKF_PARAM_Q)) wzero(g.g_Q + (size_t)b * r * r, r * r, lane);
+        if (g.g_R && !is_tv(BKF_PARAM_R)) wzero(g.g_R + (size_t)b * m * r, m * r, L);
+        if (g.g_Q && !is_tv(BKF_PARAM_Q)) wzero(g.g_Q + (size_t)b * r * r, r * r, L);
     }
-    wzero(A.abar, m, lane); wzero(A.Pbar, m * m, lane); wzero(A.gT, m * m, lane); wzero(A.Gsum, m * m, lane);
-    wzero(A.gZ, p * m, lane); wzero(A.gH, p * p, lane); wzero(A.gc, m, lane); wzero(A.gd, p, lane);
+    wzero(A.abar, m, L); wzero(A.Pbar, m * m, L); wzero(A.gT, m * m, L); wzero(A.Gsum, m * m, L);
+    wzero(A.gZ, p * m, L); wzero(A.gH, p * p, L); wzero(A.gc, m, L); wzero(A.gd, p, L);
     const R* yb = g.y_shared ? g.y : g.y + (size_t)b * n * p;
     const size_t tstride = (size_t)m + (size_t)m * m;
     for (int t = n - 1; t >= 0; --t) {
         const size_t bt = (size_t)b * n + t;
         const R gcot = g.ll_cot ? g.ll_cot[bt] : R(1);
-        if (t == n - 1 || tv) load_params(g, A, b, t, t == n - 1, lane);
-        wcopy(A.a, g.traj + bt * tstride, m, lane);
-        wcopy(A.P, g.traj + bt * tstride + m, m * m, lane);
+        if (t == n - 1 || tv) load_params(g, A, b, t, t == n - 1, L);
+        wcopy(A.a, g.traj + bt * tstride, m, L);
+        wcopy(A.P, g.traj + bt * tstride + m, m * m, L);
         bool flag = false, ok = true;
-        if (g.kind == BKF_STANDARD) std_update(g, A, yb + (size_t)t * p, (R*)nullptr, (R*)nullptr, &flag, &ok, lane);
-        else uni_update(g, A, yb + (size_t)t * p, (R*)nullptr, (R*)nullptr, lane);
+        if (g.kind == BKF_STANDARD) std_update(g, A, yb + (size_t)t * p, (R*)nullptr, (R*)nullptr, &flag, &ok, A.Finv, L);
+        else uni_update(g, A, yb + (size_t)t * p, (R*)nullptr, (R*)nullptr, L);
         // ---------------- predict adjoint ----------------
         // G = S(Pbar+); Gsum += G; gT += G T (Pf + Pf^T) + abar+ af^T; Pfbar = T^T G T; afbar = T^T abar+; gc += abar+
-        sym_into<R>(A.G, A.Pbar, nullptr, R(0), m, lane);
-        for (int idx = lane; idx < m * m; idx += 32) {
+        sym_into<R>(A.G, A.Pbar, nullptr, R(0), m, L);
+        for (int idx = lane; idx < m * m; idx += NT) {
             A.Gsum[idx] += A.G[idx];
             A.Y[idx] = A.Pf[idx] + A.Pf[(idx % m) * m + idx / m];
         }
-        __syncwarp();
+        gsync<W>();
         if (tvRQ) {
             // R or Q varies in time: Rbar_t = G_t R_t (Q_t + Q_t^T), Qbar_t = R_t^T G_t R_t, per step
             const R* Rg = param_ptr_t(g.Rm, g.shared_mask, tv, BKF_PARAM_R, b, t, n, (size_t)m * r);
             const R* Qg = param_ptr_t(g.Q, g.shared_mask, tv, BKF_PARAM_Q, b, t, n, (size_t)r * r);
             if (g.g_R) {
                 R* dst = g.g_R + grec(BKF_PARAM_R, t) * m * r;
-                for (int idx = lane; idx < m * r; idx += 32) {
+                for (int idx = lane; idx < m * r; idx += NT) {
                     int i = idx / r, j = idx - i * r;
                     R acc = 0;
                     for (int k = 0; k < r; ++k) {
@@ -529,7 +635,7 @@ __global__ void backward_kernel(KArgs<R> g, int wpc, size_t arena) {
             }
             if (g.g_Q) {
                 R* dst = g.g_Q + grec(BKF_PARAM_Q, t) * r * r;
-                for (int idx = lane; idx < r * r; idx += 32) {
+                for (int idx = lane; idx < r * r; idx += NT) {
                     int i = idx / r, j = idx - i * r;
                     R acc = 0;
                     for (int k = 0; k < m; ++k) {
@@ -540,75 +646,77 @@ __global__ void backward_kernel(KArgs<R> g, int wpc, size_t arena) {
                     dst[idx] = is_tv(BKF_PARAM_Q) ? acc : dst[idx] + acc;
                 }
             }
-            __syncwarp();
+            gsync<W>();
         }
-        mm<SET>(A.X, A.T, m, 1, A.Y, m, 1, m, m, m, lane);
-        mm<ADD>(A.gT, A.G, m, 1, A.X, m, 1, m, m, m, lane);
-        for (int idx = lane; idx < m * m; idx += 32) A.gT[idx] = fma(A.abar[idx / m], A.af[idx % m], A.gT[idx]);
-        mm<SET>(A.X, A.G, m, 1, A.T, m, 1, m, m, m, lane);
-        mm<SET>(A.Y, A.T, 1, m, A.X, m, 1, m, m, m, lane);  // Y = Pfbar
-        mv<SET>(A.afbar, A.T, 1, m, A.abar, m, m, lane);
-        for (int i = lane; i < m; i += 32) A.gc[i] += A.abar[i];
-        __syncwarp();
+        mm<SET>(A.X, A.T, m, 1, A.Y, m, 1, m, m, m, L);
+        mm<ADD>(A.gT, A.G, m, 1, A.X, m, 1, m, m, m, L);
+        for (int idx = lane; idx < m * m; idx += NT) A.gT[idx] = fma(A.abar[idx / m], A.af[idx % m], A.gT[idx]);
+        mm<SET>(A.X, A.G, m, 1, A.T, m, 1, m, m, m, L);
+        mm<SET>(A.Y, A.T, 1, m, A.X, m, 1, m, m, m, L);  // Y = Pfbar
+        mv<SET>(A.afbar, A.T, 1, m, A.abar, m, m, L);
+        for (int i = lane; i < m; i += NT) A.gc[i] += A.abar[i];
+        gsync<W>();
         if (g.kind == BKF_STANDARD) {
             // ---------------- Joseph-form adjoint ----------------
-            sym_into<R>(A.G, A.Y, nullptr, R(0), m, lane);  // G2
-            for (int idx = lane; idx < m * m; idx += 32) A.Y[idx] = A.P[idx] + A.P[(idx % m) * m + idx / m];
-            __syncwarp();
-            mm<SET>(A.X, A.Lm, m, 1, A.Y, m, 1, m, m, m, lane);
-            mm<SET>(A.Lbar, A.G, m, 1, A.X, m, 1, m, m, m, lane);       // Lbar = G2 Lm (P + P^T)
-            mm<SET>(A.X, A.G, m, 1, A.Lm, m, 1, m, m, m, lane);
-            mm<SET>(A.Pbar, A.Lm, 1, m, A.X, m, 1, m, m, m, lane);       // Pbar = Lm^T G2 Lm
-            for (int idx = lane; idx < p * p; idx += 32) A.Fbar[idx] = A.Hm[idx] + A.Hm[(idx % p) * p + idx / p];
-            __syncwarp();
-            mm<SET>(A.tmp_mp, A.K, p, 1, A.Fbar, p, 1, m, p, p, lane);   // K (Hm + Hm^T)
-            mm<SET>(A.Kbar, A.G, m, 1, A.tmp_mp, p, 1, m, p, m, lane);   // Kbar = G2 K (Hm + Hm^T)
-            mm<SET>(A.tmp_mp, A.G, m, 1, A.K, p, 1, m, p, m, lane);      // G2 K
-            mm<SET>(A.Hmbar, A.K, 1, p, A.tmp_mp, p, 1, p, p, m, lane);  // Hmbar = K^T G2 K
+            sym_into<R>(A.G, A.Y, nullptr, R(0), m, L);  // G2
+            for (int idx = lane; idx < m * m; idx += NT) A.Y[idx] = A.P[idx] + A.P[(idx % m) * m + idx / m];
+            gsync<W>();
+            mm<SET>(A.X, A.Lm, m, 1, A.Y, m, 1, m, m, m, L);
+            mm<SET>(A.Lbar, A.G, m, 1, A.X, m, 1, m, m, m, L);       // Lbar = G2 Lm (P + P^T)
+            mm<SET>(A.X, A.G, m, 1, A.Lm, m, 1, m, m, m, L);
+            mm<SET>(A.Pbar, A.Lm, 1, m, A.X, m, 1, m, m, m, L);       // Pbar = Lm^T G2 Lm
+            for (int idx = lane; idx < p * p; idx += NT) A.Fbar[idx] = A.Hm[idx] + A.Hm[(idx % p) * p + idx / p];
+            gsync<W>();
+            mm<SET>(A.tmp_mp, A.K, p, 1, A.Fbar, p, 1, m, p, p, L);   // K (Hm + Hm^T)
+            mm<SET>(A.Kbar, A.G, m, 1, A.tmp_mp, p, 1, m, p, m, L);   // Kbar = G2 K (Hm + Hm^T)
+            mm<SET>(A.tmp_mp, A.G, m, 1, A.K, p, 1, m, p, m, L);      // G2 K
+            mm<SET>(A.Hmbar, A.K, 1, p, A.tmp_mp, p, 1, p, p, m, L);  // Hmbar = K^T G2 K
             // a_f = a + K v
-            wcopy(A.abar, A.afbar, m, lane);
-            for (int idx = lane; idx < m * p; idx += 32) A.Kbar[idx] = fma(A.afbar[idx / p], A.v[idx % p], A.Kbar[idx]);
-            mv<SET>(A.vbar, A.K, 1, p, A.afbar, p, m, lane);
+            wcopy(A.abar, A.afbar, m, L);
+            for (int idx = lane; idx < m * p; idx += NT) A.Kbar[idx] = fma(A.afbar[idx / p], A.v[idx % p], A.Kbar[idx]);
+            mv<SET>(A.vbar, A.K, 1, p, A.afbar, p, m, L);
             // Lm = I - K Zm
-            mm<SUB>(A.Kbar, A.Lbar, m, 1, A.Zm, 1, m, m, p, m, lane);    // Kbar -= Lbar Zm^T
-            mm<SET>(A.Zmbar, A.K, 1, p, A.Lbar, m, 1, p, m, m, lane);    // K^T Lbar
-            for (int idx = lane; idx < p * m; idx += 32) A.Zmbar[idx] = -A.Zmbar[idx];
-            // Finv = F^{-1}
-            for (int idx = lane; idx < p * p; idx += 32) A.Finv[idx] = ((idx / p) == (idx % p)) ? R(1) : R(0);
-            __syncwarp();
-            for (int q = lane; q < p; q += 32) chol_solve_vec(A.Lf, p, A.Finv + q, p);
-            __syncwarp();
+            mm<SUB>(A.Kbar, A.Lbar, m, 1, A.Zm, 1, m, m, p, m, L);    // Kbar -= Lbar Zm^T
+            mm<SET>(A.Zmbar, A.K, 1, p, A.Lbar, m, 1, p, m, m, L);    // K^T Lbar
+            for (int idx = lane; idx < p * m; idx += NT) A.Zmbar[idx] = -A.Zmbar[idx];
+            // Finv = F^{-1} (already there when std_update solved for it beside K)
+            if (!solve_scratch_fits(m, p, true)) {
+                for (int idx = lane; idx < p * p; idx += NT) A.Finv[idx] = ((idx / p) == (idx % p)) ? R(1) : R(0);
+                gsync<W>();
+                for (int q = lane; q < p; q += NT) chol_solve_vec(A.Lf, p, A.Finv + q, p);
+            }
+            gsync<W>();
             // ll adjoint
-            for (int idx = lane; idx < p * p; idx += 32) {
+            for (int idx = lane; idx < p * p; idx += NT) {
                 int o = idx / p, q = idx - o * p;
                 A.Fbar[idx] = flag ? R(0) : R(-0.5) * gcot * (A.Finv[q * p + o] - A.wv[o] * A.wv[q]);
             }
             if (!flag)
-                for (int o = lane; o < p; o += 32) A.vbar[o] -= gcot * A.wv[o];
-            __syncwarp();
+                for (int o = lane; o < p; o += NT) A.vbar[o] -= gcot * A.wv[o];
+            gsync<W>();
             // K = PZT F^{-1}
-            mm<SET>(A.PZTbar, A.Kbar, p, 1, A.Finv, 1, p, m, p, p, lane);  // Kbar F^{-T}
-            mm<SUB>(A.Fbar, A.K, 1, p, A.PZTbar, p, 1, p, p, m, lane);     // Fbar -= K^T PZTbar
+            mm<SET>(A.PZTbar, A.Kbar, p, 1, A.Finv, 1, p, m, p, p, L);  // Kbar F^{-T}
+            mm<SUB>(A.Fbar, A.K, 1, p, A.PZTbar, p, 1, p, p, m, L);     // Fbar -= K^T PZTbar
             // F = Zm PZT + Hm + eps I
-            mm<ADD>(A.Zmbar, A.Fbar, p, 1, A.PZT, 1, p, p, m, p, lane);    // Zmbar += Fbar PZT^T
-            mm<ADD>(A.PZTbar, A.Zm, 1, m, A.Fbar, p, 1, m, p, p, lane);    // PZTbar += Zm^T Fbar
-            for (int idx = lane; idx < p * p; idx += 32) A.Hmbar[idx] += A.Fbar[idx];
+            mm<ADD>(A.Zmbar, A.Fbar, p, 1, A.PZT, 1, p, p, m, p, L);    // Zmbar += Fbar PZT^T
+            mm<ADD>(A.PZTbar, A.Zm, 1, m, A.Fbar, p, 1, m, p, p, L);    // PZTbar += Zm^T Fbar
+            for (int idx = lane; idx < p * p; idx += NT) A.Hmbar[idx] += A.Fbar[idx];
             // PZT = P Zm^T
-            mm<ADD>(A.Pbar, A.PZTbar, p, 1, A.Zm, m, 1, m, m, p, lane);    // Pbar += PZTbar Zm
-            mm<ADD>(A.Zmbar, A.PZTbar, 1, p, A.P, m, 1, p, m, m, lane);    // Zmbar += PZTbar^T P
+            mm<ADD>(A.Pbar, A.PZTbar, p, 1, A.Zm, m, 1, m, m, p, L);    // Pbar += PZTbar Zm
+            mm<ADD>(A.Zmbar, A.PZTbar, 1, p, A.P, m, 1, p, m, m, L);    // Zmbar += PZTbar^T P
             // v = ym - d - Zm a
-            for (int o = lane; o < p; o += 32) A.gd[o] -= A.vbar[o];
-            for (int idx = lane; idx < p * m; idx += 32) A.Zmbar[idx] = fma(-A.vbar[idx / m], A.a[idx % m], A.Zmbar[idx]);
-            mv<SUB>(A.abar, A.Zm, 1, m, A.vbar, m, p, lane);               // abar -= Zm^T vbar
+            for (int o = lane; o < p; o += NT) A.gd[o] -= A.vbar[o];
+            for (int idx = lane; idx < p * m; idx += NT) A.Zmbar[idx] = fma(-A.vbar[idx / m], A.a[idx % m], A.Zmbar[idx]);
+            mv<SUB>(A.abar, A.Zm, 1, m, A.vbar, m, p, L);               // abar -= Zm^T vbar
             // mask
-            for (int idx = lane; idx < p * m; idx += 32) A.gZ[idx] = fma(A.w[idx / m], A.Zmbar[idx], A.gZ[idx]);
-            for (int idx = lane; idx < p * p; idx += 32) A.gH[idx] = fma(A.w[idx / p], A.Hmbar[idx], A.gH[idx]);
-            __syncwarp();
+            for (int idx = lane; idx < p * m; idx += NT) A.gZ[idx] = fma(A.w[idx / m], A.Zmbar[idx], A.gZ[idx]);
+            for (int idx = lane; idx < p * p; idx += NT) A.gH[idx] = fma(A.w[idx / p], A.Hmbar[idx], A.gH[idx]);
+            gsync<W>();
         } else {
             // ---------------- univariate adjoint ----------------
             // Pf = 0.5 (Pu + Pu^T) + eps I
-            sym_into<R>(A.Pbar, A.Y, nullptr, R(0), m, lane);
-            wcopy(A.abar, A.afbar, m, lane);
+            sym_into<R>(A.Pbar, A.Y, nullptr, R(0), m, L);
+            wcopy(A.abar, A.afbar, m, L);
             const R llbar = R(-0.5) * gcot;
             for (int o = p - 1; o >= 0; --o) {
                 const R keep = A.zfst[o];
@@ -617,12 +725,12 @@ __global__ void backward_kernel(KArgs<R> g, int wpc, size_t arena) {
                 const R* K = A.Kst + o * m;
                 const R* z = A.Z + o * m;  // wo == 1 here
                 // state before this inner update
-                for (int idx = lane; idx < m * m; idx += 32) A.Pu[idx] += (K[idx / m] * K[idx % m]) * F;
-                for (int i = lane; i < m; i += 32) A.af[i] = fma(-K[i], v, A.af[i]);
-                __syncwarp();
+                for (int idx = lane; idx < m * m; idx += NT) A.Pu[idx] += (K[idx / m] * K[idx % m]) * F;
+                for (int i = lane; i < m; i += NT) A.af[i] = fma(-K[i], v, A.af[i]);
+                gsync<W>();
                 // Kbar_i = -sum_j (Pbar_ij + Pbar_ji) K_j F + abar_i v   (tmp in X[0:m])
                 R kpk = 0, ka = 0, kk = 0;
-                for (int i = lane; i < m; i += 32) {
+                for (int i = lane; i < m; i += NT) {
                     R acc = 0;
                     for (int j = 0; j < m; ++j) acc = fma(A.Pbar[i * m + j] + A.Pbar[j * m + i], K[j], acc);
                     R pk = 0;
@@ -633,16 +741,16 @@ __global__ void backward_kernel(KArgs<R> g, int wpc, size_t arena) {
                     ka = fma(K[i], A.abar[i], ka);
                     kk = fma(kb, K[i], kk);
                 }
-                kpk = warp_sum(kpk); ka = warp_sum(ka); kk = warp_sum(kk);
+                gsum3<W>(kpk, ka, kk, A.X, lane);  // (X is free in this branch: scratch of the CTA-wide sum)
                 R Fbar = -kpk + llbar * (R(1) / F - v * v / (F * F));
                 const R vbar = ka + llbar * R(2) * v / F;
                 Fbar -= kk / F;
-                __syncwarp();
+                gsync<W>();
                 // pzbar = Kbar / F + Fbar z ; zbar = Fbar pz + P^T pzbar - vbar a ; (pz = K F)
-                for (int i = lane; i < m; i += 32) A.PZTbar[i] = A.Kbar[i] / F + Fbar * z[i];
-                __syncwarp();
+                for (int i = lane; i < m; i += NT) A.PZTbar[i] = A.Kbar[i] / F + Fbar * z[i];
+                gsync<W>();
                 const R* pzbar = A.PZTbar;
-                for (int j = lane; j < m; j += 32) {
+                for (int j = lane; j < m; j += NT) {
                     R acc = 0;
                     for (int i = 0; i < m; ++i) acc = fma(A.Pu[i * m + j], pzbar[i], acc);
                     R zb = fma(Fbar, K[j] * F, acc);
@@ -650,19 +758,19 @@ __global__ void backward_kernel(KArgs<R> g, int wpc, size_t arena) {
                     A.gZ[o * m + j] = fma(wo, zb, A.gZ[o * m + j]);
                     A.abar[j] = fma(-vbar, z[j], A.abar[j]);
                 }
-                for (int idx = lane; idx < m * m; idx += 32) A.Pbar[idx] = fma(pzbar[idx / m], z[idx % m], A.Pbar[idx]);
+                for (int idx = lane; idx < m * m; idx += NT) A.Pbar[idx] = fma(pzbar[idx / m], z[idx % m], A.Pbar[idx]);
                 if (lane == 0) {
                     A.gH[o * p + o] = fma(wo, Fbar, A.gH[o * p + o]);
                     A.gd[o] -= vbar;
                 }
-                __syncwarp();
+                gsync<W>();
             }
         }
         if (tv) {  // time-varying parameters: this step's contribution IS the gradient of x[t]
             auto flush = [&](int which, R* dst, R* acc, size_t sz) {
                 if (!is_tv(which)) return;
-                if (dst) wcopy(dst + ((size_t)b * n + t) * sz, acc, (int)sz, lane);
-                wzero(acc, (int)sz, lane);
+                if (dst) wcopy(dst + ((size_t)b * n + t) * sz, acc, (int)sz, L);
+                wzero(acc, (int)sz, L);
             };
             flush(BKF_PARAM_T, g.g_T, A.gT, (size_t)m * m);
             flush(BKF_PARAM_C, g.g_c, A.gc, m);
@@ -673,7 +781,7 @@ __global__ void backward_kernel(KArgs<R> g, int wpc, size_t arena) {
     }
     // ---------------- write gradients ----------------
     auto put = [&](int which, R* dst, const R* src, size_t sz) {
-        if (dst && !is_tv(which)) wcopy(dst + (size_t)b * sz, src, (int)sz, lane);
+        if (dst && !is_tv(which)) wcopy(dst + (size_t)b * sz, src, (int)sz, L);
     };
     put(BKF_PARAM_A0, g.g_a0, A.abar, m); put(BKF_PARAM_P0, g.g_P0, A.Pbar, (size_t)m * m);
     put(BKF_PARAM_C, g.g_c, A.gc, m); put(BKF_PARAM_D, g.g_d, A.gd, p);
@@ -684,7 +792,7 @@ __global__ void backward_kernel(KArgs<R> g, int wpc, size_t arena) {
     const R* Rg = param_ptr(g.Rm, g.shared_mask, BKF_PARAM_R, b, (size_t)m * r);
     const R* Qg = param_ptr(g.Q, g.shared_mask, BKF_PARAM_Q, b, (size_t)r * r);
     if (g.g_R) {
-        for (int idx = lane; idx < m * r; idx += 32) {
+        for (int idx = lane; idx < m * r; idx += NT) {
             int i = idx / r, j = idx - i * r;
             R acc = 0;
             for (int k = 0; k < r; ++k) {
@@ -696,7 +804,7 @@ __global__ void backward_kernel(KArgs<R> g, int wpc, size_t arena) {
         }
     }
     if (g.g_Q) {
-        for (int idx = lane; idx < r * r; idx += 32) {
+        for (int idx = lane; idx < r * r; idx += NT) {
             int i = idx / r, j = idx - i * r;
             R acc = 0;
             for (int k = 0; k < m; ++k) {
@@ -720,12 +828,13 @@ __host__ __device__ inline size_t smooth_arena_elems(int m, int r) {
 // Symmetric eigen-decomposition by cyclic Jacobi: A (destroyed; diag -> eigenvalues), V (eigenvectors in columns).
 template <typename R>
 __device__ void jacobi_eig(R* A, R* V, int m, int lane) {
-    for (int idx = lane; idx < m * m; idx += 32) V[idx] = ((idx / m) == (idx % m)) ? R(1) : R(0);
-    __syncwarp();
+    constexpr int W = 1, NT = 32;  // the smoother stays one warp per series
+    for (int idx = lane; idx < m * m; idx += NT) V[idx] = ((idx / m) == (idx % m)) ? R(1) : R(0);
+    gsync<W>();
     const R tol2 = sizeof(R) == 8 ? R(1e-34) : R(1e-15);
     for (int sweep = 0; sweep < 30; ++sweep) {
         R off = 0, dg = 0;
-        for (int idx = lane; idx < m * m; idx += 32) {
+        for (int idx = lane; idx < m * m; idx += NT) {
             R x = A[idx];
             if ((idx / m) == (idx % m)) dg = fma(x, x, dg); else off = fma(x, x, off);
         }
@@ -735,12 +844,12 @@ __device__ void jacobi_eig(R* A, R* V, int m, int lane) {
             for (int qi = pi + 1; qi < m; ++qi) {
                 const R apq = A[pi * m + qi];
                 const R app = A[pi * m + pi], aqq = A[qi * m + qi];
-                __syncwarp();
+                gsync<W>();
                 if (apq == R(0)) continue;
                 const R theta = (aqq - app) / (R(2) * apq);
                 const R tt = (theta >= R(0) ? R(1) : R(-1)) / (fabs(theta) + sqrt(fma(theta, theta, R(1))));
                 const R cs = R(1) / sqrt(fma(tt, tt, R(1))), sn = tt * cs;
-                for (int k = lane; k < m; k += 32) {
+                for (int k = lane; k < m; k += NT) {
                     if (k != pi && k != qi) {
                         R akp = A[k * m + pi], akq = A[k * m + qi];
                         R np_ = cs * akp - sn * akq, nq = sn * akp + cs * akq;
@@ -756,7 +865,7 @@ __device__ void jacobi_eig(R* A, R* V, int m, int lane) {
                     A[qi * m + qi] = aqq + tt * apq;
                     A[pi * m + qi] = 0; A[qi * m + pi] = 0;
                 }
-                __syncwarp();
+                gsync<W>();
             }
         }
     }
@@ -765,6 +874,8 @@ __device__ void jacobi_eig(R* A, R* V, int m, int lane) {
 // One series of the smoother sweep by one warp (s: the warp's arena).
 template <typename R>
 __device__ void smooth_series(const KArgs<R>& g, const int b, R* s, const R jitter0, const int lane) {
+    constexpr int W = 1, NT = 32;
+    const Lane<1> L{lane};
     const int m = g.m, r = g.r, n = g.n;
     const size_t mm_ = (size_t)m * m;
     auto take = [&](size_t k) { R* q = s; s += k; return q; };
@@ -776,71 +887,71 @@ __device__ void smooth_series(const KArgs<R>& g, const int b, R* s, const R jitt
     const unsigned tv = g.tv_mask;
     auto load_trq = [&](int t, bool all) {
         if (all || ((tv >> BKF_PARAM_T) & 1u))
-            wcopy(T, param_ptr_t(g.T, g.shared_mask, tv, BKF_PARAM_T, b, t, n, mm_), m * m, lane);
+            wcopy(T, param_ptr_t(g.T, g.shared_mask, tv, BKF_PARAM_T, b, t, n, mm_), m * m, L);
         if (all || (((tv >> BKF_PARAM_R) | (tv >> BKF_PARAM_Q)) & 1u))
             rqr_sym(RQR, Y, param_ptr_t(g.Rm, g.shared_mask, tv, BKF_PARAM_R, b, t, n, (size_t)m * r),
-                    param_ptr_t(g.Q, g.shared_mask, tv, BKF_PARAM_Q, b, t, n, (size_t)r * r), m, r, lane);
+                    param_ptr_t(g.Q, g.shared_mask, tv, BKF_PARAM_Q, b, t, n, (size_t)r * r), m, r, L);
     };
     load_trq(n - 1, true);
     const R* fa = g.sm_filt_a + (size_t)b * n * m;
     const R* fP = g.sm_filt_P + (size_t)b * n * mm_;
     R* oa = g.sm_a ? g.sm_a + (size_t)b * n * m : nullptr;
     R* oP = g.sm_P ? g.sm_P + (size_t)b * n * mm_ : nullptr;
-    wcopy(as, fa + (size_t)(n - 1) * m, m, lane);
-    wcopy(Ps, fP + (size_t)(n - 1) * mm_, m * m, lane);
-    if (oa) wcopy(oa + (size_t)(n - 1) * m, as, m, lane);
-    if (oP) wcopy(oP + (size_t)(n - 1) * mm_, Ps, m * m, lane);
+    wcopy(as, fa + (size_t)(n - 1) * m, m, L);
+    wcopy(Ps, fP + (size_t)(n - 1) * mm_, m * m, L);
+    if (oa) wcopy(oa + (size_t)(n - 1) * m, as, m, L);
+    if (oP) wcopy(oP + (size_t)(n - 1) * mm_, Ps, m * m, L);
     int st = 0;
     for (int t = n - 2; t >= 0; --t) {
         if (tv && t != n - 2) load_trq(t + 1, false);
-        wcopy(a, fa + (size_t)t * m, m, lane);
-        wcopy(P, fP + (size_t)t * mm_, m * m, lane);
-        mv<SET>(ah, T, m, 1, a, m, m, lane);  // no state intercept (:122, quirk Q8)
-        mm<SET>(X, T, m, 1, P, m, 1, m, m, m, lane);
-        mm<SET>(Y, X, m, 1, T, 1, m, m, m, m, lane);
-        sym_into<R>(Ph, Y, RQR, g.jitter, m, lane);
+        wcopy(a, fa + (size_t)t * m, m, L);
+        wcopy(P, fP + (size_t)t * mm_, m * m, L);
+        mv<SET>(ah, T, m, 1, a, m, m, L);  // no state intercept (:122, quirk Q8)
+        mm<SET>(X, T, m, 1, P, m, 1, m, m, m, L);
+        mm<SET>(Y, X, m, 1, T, 1, m, m, m, m, L);
+        sym_into<R>(Ph, Y, RQR, g.jitter, m, L);
         // pinv(P_hat) (:112): symmetric eigen-decomposition, singular values below 1e-15 * max dropped
-        wcopy(Y, Ph, m * m, lane);
+        wcopy(Y, Ph, m * m, L);
         jacobi_eig(Y, V, m, lane);
         R lmax = 0;
         for (int i = 0; i < m; ++i) lmax = fmax(lmax, fabs(Y[i * m + i]));
         const R cutoff = R(1e-15) * lmax;
-        for (int i = lane; i < m; i += 32) {
+        for (int i = lane; i < m; i += NT) {
             R l = Y[i * m + i];
             lam[i] = fabs(l) > cutoff ? R(1) / l : R(0);
         }
-        __syncwarp();
-        for (int idx = lane; idx < m * m; idx += 32) {  // Y = V diag(lam) V^T
+        gsync<W>();
+        for (int idx = lane; idx < m * m; idx += NT) {  // Y = V diag(lam) V^T
             int i = idx / m, j = idx - i * m;
             R acc = 0;
             for (int k = 0; k < m; ++k) acc = fma(V[i * m + k] * lam[k], V[j * m + k], acc);
             X[idx] = acc;
         }
-        __syncwarp();
+        gsync<W>();
         // G = (pinv T P)^T
-        mm<SET>(Y, X, m, 1, T, m, 1, m, m, m, lane);
-        mm<SET>(X, Y, m, 1, P, m, 1, m, m, m, lane);
-        for (int idx = lane; idx < m * m; idx += 32) G[idx] = X[(idx % m) * m + idx / m];
-        for (int i = lane; i < m; i += 32) ah[i] = as[i] - ah[i];
-        __syncwarp();
-        for (int i = lane; i < m; i += 32) {
+        mm<SET>(Y, X, m, 1, T, m, 1, m, m, m, L);
+        mm<SET>(X, Y, m, 1, P, m, 1, m, m, m, L);
+        for (int idx = lane; idx < m * m; idx += NT) G[idx] = X[(idx % m) * m + idx / m];
+        for (int i = lane; i < m; i += NT) ah[i] = as[i] - ah[i];
+        gsync<W>();
+        for (int i = lane; i < m; i += NT) {
             R acc = 0;
             for (int k = 0; k < m; ++k) acc = fma(G[i * m + k], ah[k], acc);
             as[i] = a[i] + acc;
         }
-        for (int idx = lane; idx < m * m; idx += 32) Y[idx] = Ps[idx] - Ph[idx];
-        __syncwarp();
-        mm<SET>(X, G, m, 1, Y, m, 1, m, m, m, lane);
-        mm<SET>(Y, X, m, 1, G, 1, m, m, m, m, lane);
-        for (int idx = lane; idx < m * m; idx += 32) {
+        for (int idx = lane; idx < m * m; idx += NT) Y[idx] = Ps[idx] - Ph[idx];
+        gsync<W>();
+        mm<SET>(X, G, m, 1, Y, m, 1, m, m, m, L);
+        mm<SET>(Y, X, m, 1, G, 1, m, m, m, m, L);
+        for (int idx = lane; idx < m * m; idx += NT) {
             int i = idx / m, j = idx - i * m;
             R val = P[idx] + R(0.5) * (Y[idx] + Y[j * m + i]);
             if (i == j) val = (val + g.jitter) + jitter0;  // double jitter (:116-117, quirk Q8)
             Ps[idx] = val;
         }
-        __syncwarp();
-        if (oa) wcopy(oa + (size_t)t * m, as, m, lane);
-        if (oP) wcopy(oP + (size_t)t * mm_, Ps, m * m, lane);
+        gsync<W>();
+        if (oa) wcopy(oa + (size_t)t * m, as, m, L);
+        if (oP) wcopy(oP + (size_t)t * mm_, Ps, m * m, L);
     }
     if (lane == 0 && g.status) g.status[b] |= st;
 }
@@ -877,32 +988,99 @@ static int pick_wpc(size_t arena_bytes, int B) {
     return wpc;
 }
 
-template <typename R, typename KernelT>
-static int launch_warp_kernel(KernelT kern, const KArgs<R>& g, size_t arena, cudaStream_t stream, const char** err) {
+// W == 1: wpc series per CTA, one warp each.  W > 1: one series per CTA of W warps.
+template <typename R, int W, typename KernelT>
+static int launch_group_kernel(KernelT kern, const KArgs<R>& g, size_t arena, cudaStream_t stream, const char** err) {
     size_t arena_bytes = arena * sizeof(R);
     if (arena_bytes > 227 * 1024) {
         *err = "problem too large for the generic shared-memory kernel (m, p, r)";
         return BKF_ERR_UNSUPPORTED;
     }
-    int wpc = pick_wpc(arena_bytes, g.B);
+    int wpc = W == 1 ? pick_wpc(arena_bytes, g.B) : 1;
     size_t smem = arena_bytes * wpc;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) { *err = cudaGetErrorString(e); return BKF_ERR_CUDA; }
     int grid = (g.B + wpc - 1) / wpc;
-    kern<<<grid, 32 * wpc, smem, stream>>>(g, wpc, arena);
+    kern<<<grid, W == 1 ? 32 * wpc : 32 * W, smem, stream>>>(g, wpc, arena);
     e = cudaGetLastError();
     if (e != cudaSuccess) { *err = cudaGetErrorString(e); return BKF_ERR_CUDA; }
     return BKF_OK;
 }
 
+template <typename R, int W>
+int launch_forward_w(const KArgs<R>& g, cudaStream_t stream, const char** err) {
+    return launch_group_kernel<R, W>(forward_kernel<R, W>, g, arena_elems(g.m, g.p, g.r, false), stream, err);
+}
+template <typename R, int W>
+int launch_backward_w(const KArgs<R>& g, cudaStream_t stream, const char** err) {
+    return launch_group_kernel<R, W>(backward_kernel<R, W>, g, arena_elems(g.m, g.p, g.r, true), stream, err);
+}
+
+#if BKF_GEN_W == 1
+#ifdef BKF_GEN_DMMA
+// The CTA-per-series builds live in their own translation units (bkf_generic_tc_w{2,4,8}.cu).
+extern template int launch_forward_w<double, 2>(const KArgs<double>&, cudaStream_t, const char**);
+extern template int launch_forward_w<double, 4>(const KArgs<double>&, cudaStream_t, const char**);
+extern template int launch_forward_w<double, 8>(const KArgs<double>&, cudaStream_t, const char**);
+extern template int launch_backward_w<double, 2>(const KArgs<double>&, cudaStream_t, const char**);
+extern template int launch_backward_w<double, 4>(const KArgs<double>&, cudaStream_t, const char**);
+extern template int launch_backward_w<double, 8>(const KArgs<double>&, cudaStream_t, const char**);
+
+// Warps per series.  The arena bounds the series one SM can hold (227 KB), the registers its warps (forward: 16, adjoint
+// at 235-240 registers: 8).  Measured (tools/bench_generic_groups.py): a series runs about sqrt(W) times faster on W warps
+// (the dense products scale, the Cholesky and the substitutions do not), so the launcher takes the width with the largest
+// (series per SM) * sqrt(W).  With small arenas that is the one-warp mapping, at the VARMAX shape (one series per SM) it is
+// eight warps.  BKF_GEN_W=<1|2|4|8> in the environment overrides the choice.
+static int pick_w(size_t arena_bytes, int warps_per_sm) {
+    if (const char* e = getenv("BKF_GEN_W")) {
+        int w = atoi(e);
+        if (w == 1 || w == 2 || w == 4 || w == 8) return w;
+    }
+    const size_t smem = 227 * 1024;
+    const int per_sm = (int)(smem / (arena_bytes ? arena_bytes : 1));
+    const int wpc = pick_wpc(arena_bytes, 0);
+    int ctas = (int)(smem / (arena_bytes * wpc));
+    if (ctas > warps_per_sm / wpc) ctas = warps_per_sm / wpc;
+    double best = (double)(ctas * wpc);  // W = 1
+    int w_best = 1;
+    const double gain[4] = {1.0, 1.41, 2.0, 2.83};
+    for (int k = 1; k < 4; ++k) {
+        const int w = 1 << k;
+        int series = per_sm < warps_per_sm / w ? per_sm : warps_per_sm / w;
+        const double score = series * gain[k];
+        if (score > best * 1.05) { best = score; w_best = w; }
+    }
+    return w_best;
+}
+int width(const KArgs<double>& g, bool backward) {
+    return pick_w(arena_elems(g.m, g.p, g.r, backward) * sizeof(double), backward ? 8 : 16);
+}
+#endif
+
 template <typename R>
 int launch_forward(const KArgs<R>& g, cudaStream_t stream, const char** err) {
-    return launch_warp_kernel<R>(forward_kernel<R>, g, arena_elems(g.m, g.p, g.r, false), stream, err);
+#ifdef BKF_GEN_DMMA
+    switch (width(g, false)) {
+        case 2: return launch_forward_w<R, 2>(g, stream, err);
+        case 4: return launch_forward_w<R, 4>(g, stream, err);
+        case 8: return launch_forward_w<R, 8>(g, stream, err);
+        default: break;
+    }
+#endif
+    return launch_forward_w<R, 1>(g, stream, err);
 }
 
 template <typename R>
 int launch_backward(const KArgs<R>& g, cudaStream_t stream, const char** err) {
-    return launch_warp_kernel<R>(backward_kernel<R>, g, arena_elems(g.m, g.p, g.r, true), stream, err);
+#ifdef BKF_GEN_DMMA
+    switch (width(g, true)) {
+        case 2: return launch_backward_w<R, 2>(g, stream, err);
+        case 4: return launch_backward_w<R, 4>(g, stream, err);
+        case 8: return launch_backward_w<R, 8>(g, stream, err);
+        default: break;
+    }
+#endif
+    return launch_backward_w<R, 1>(g, stream, err);
 }
 
 template <typename R>
@@ -931,6 +1109,10 @@ template int launch_smoother<double>(const KArgs<double>&, const int*, const int
 template int launch_forward<float>(const KArgs<float>&, cudaStream_t, const char**);
 template int launch_backward<float>(const KArgs<float>&, cudaStream_t, const char**);
 template int launch_smoother<float>(const KArgs<float>&, const int*, const int*, cudaStream_t, const char**);
+#endif
+#else   // BKF_GEN_W > 1: this unit holds one CTA-per-series build of the two sweeps
+template int launch_forward_w<double, BKF_GEN_W>(const KArgs<double>&, cudaStream_t, const char**);
+template int launch_backward_w<double, BKF_GEN_W>(const KArgs<double>&, cudaStream_t, const char**);
 #endif
 
 }  // namespace BKF_GEN_NS

@@ -15,6 +15,7 @@ namespace gent {  // the same kernels with DMMA tile products, float64 (bkf_gene
 template <typename R> int launch_forward(const KArgs<R>& g, cudaStream_t stream, const char** err);
 template <typename R> int launch_backward(const KArgs<R>& g, cudaStream_t stream, const char** err);
 template <typename R> int launch_smoother(const KArgs<R>& g, const int* list, const int* count, cudaStream_t stream, const char** err);
+int width(const KArgs<double>& g, bool backward);  // warps per series the launcher picks for this shape (1: warp per series)
 }  // namespace gent
 namespace sq {  // square-root filter, CTA per series (bkf_sqrt.cu)
 size_t traj_record_elems_host(int m, int p);  // forward-sweep record kept for the adjoint (a, Pc, R factors)
