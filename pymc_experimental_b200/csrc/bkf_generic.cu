@@ -531,8 +531,19 @@ __global__ void __launch_bounds__(W == 1 ? 128 : 32 * W) forward_kernel(KArgs<R>
     if (b >= g.B) return;
     const int m = g.m, p = g.p, n = g.n;
     const int po = (g.kind == BKF_UNIVARIATE) ? 1 : p;
+#ifdef BKF_GEN_DMMA
     Arena<R> A;
     carve(A, smem + (size_t)warp * arena, m, p, g.r, false);
+#else
+    // Small shapes (this build serves m < 16): the arena's pointer table lives in shared memory.  Its some 45 pointers cost
+    // 90 registers otherwise; measured +10 to 15 % at (8, 2, 2) and (4, 2, 2).  The DMMA build keeps them in registers: with
+    // large arenas the shared memory bounds the occupancy, not the registers, and the re-loads after every barrier cost
+    // the univariate loops 20 to 45 % (tools/bench_generic_groups.py).
+    __shared__ Arena<R> arenas[4];
+    Arena<R>& A = arenas[warp];
+    if (lane == 0) carve(A, smem + (size_t)warp * arena, m, p, g.r, false);
+    gsync<W>();
+#endif
     wcopy(A.a, param_ptr(g.a0, g.shared_mask, BKF_PARAM_A0, b, (size_t)m), m, L);
     wcopy(A.P, param_ptr(g.P0, g.shared_mask, BKF_PARAM_P0, b, (size_t)m * m), m * m, L);
     const R* yb = g.y_shared ? g.y : g.y + (size_t)b * n * p;
@@ -584,8 +595,19 @@ __global__ void __launch_bounds__(W == 1 ? 128 : 32 * W) backward_kernel(KArgs<R
     const int b = W == 1 ? blockIdx.x * wpc + warp : blockIdx.x;
     if (b >= g.B) return;
     const int m = g.m, p = g.p, r = g.r, n = g.n;
+#ifdef BKF_GEN_DMMA
     Arena<R> A;
     carve(A, smem + (size_t)warp * arena, m, p, r, true);
+#else
+    // Small shapes (this build serves m < 16): the arena's pointer table lives in shared memory.  Its some 45 pointers cost
+    // 90 registers otherwise; measured +10 to 15 % at (8, 2, 2) and (4, 2, 2).  The DMMA build keeps them in registers: with
+    // large arenas the shared memory bounds the occupancy, not the registers, and the re-loads after every barrier cost
+    // the univariate loops 20 to 45 % (tools/bench_generic_groups.py).
+    __shared__ Arena<R> arenas[4];
+    Arena<R>& A = arenas[warp];
+    if (lane == 0) carve(A, smem + (size_t)warp * arena, m, p, r, true);
+    gsync<W>();
+#endif
     const unsigned tv = g.tv_mask;
     const bool tvRQ = ((tv >> BKF_PARAM_R) | (tv >> BKF_PARAM_Q)) & 1u;
     auto is_tv = [&](int which) { return ((tv >> which) & 1u) != 0; };
@@ -992,7 +1014,7 @@ static int pick_wpc(size_t arena_bytes, int B) {
 template <typename R, int W, typename KernelT>
 static int launch_group_kernel(KernelT kern, const KArgs<R>& g, size_t arena, cudaStream_t stream, const char** err) {
     size_t arena_bytes = arena * sizeof(R);
-    if (arena_bytes > 227 * 1024) {
+    if (arena_bytes > 225 * 1024) {  // (227 KB less the static pointer tables)
         *err = "problem too large for the generic shared-memory kernel (m, p, r)";
         return BKF_ERR_UNSUPPORTED;
     }
@@ -1036,7 +1058,7 @@ static int pick_w(size_t arena_bytes, int warps_per_sm) {
         int w = atoi(e);
         if (w == 1 || w == 2 || w == 4 || w == 8) return w;
     }
-    const size_t smem = 227 * 1024;
+    const size_t smem = 225 * 1024;
     const int per_sm = (int)(smem / (arena_bytes ? arena_bytes : 1));
     const int wpc = pick_wpc(arena_bytes, 0);
     int ctas = (int)(smem / (arena_bytes * wpc));
