@@ -23,6 +23,9 @@
 #define BKF_GEN_W 1
 #endif
 #include <cstdlib>
+#include <map>
+#include <mutex>
+#include <utility>
 
 namespace bkf {
 namespace BKF_GEN_NS {
@@ -41,6 +44,14 @@ __device__ __forceinline__ void gsync() {
     if constexpr (W == 1) __syncwarp();
     else __syncthreads();
 }
+
+// One element global -> shared by the asynchronous copy unit (LDGSTS): the adjoint fetches the record of the NEXT step while it works on this one.
+template <typename R>
+__device__ __forceinline__ void cp_async_elem(R* dst_smem, const R* src) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(dst_smem);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], %2;\n" ::"r"(d), "l"(src), "n"(sizeof(R)) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;\n" ::: "memory"); }
 
 // Three sums over the group at once (every thread gets the totals).  red: 3 * W values of scratch.
 template <int W, typename R>
@@ -257,6 +268,14 @@ __host__ __device__ inline size_t arena_elems(int m, int p, int r, bool backward
                  /*gH,Fbar,Finv,Hmbar*/ 4 * pp + /*abar,gc,afbar*/ 3 * (size_t)m + /*gd,vbar*/ 2 * (size_t)p;
     size_t tot = fwd + (backward ? bwd : 0);
     return (tot + 1) & ~(size_t)1;
+}
+
+// The adjoint's arena with a staging buffer for the next step's record [a | P] behind it, when that still fits.
+__host__ __device__ inline size_t stage_elems(int m) { return ((size_t)m + (size_t)m * m + 1) & ~(size_t)1; }
+template <typename R>
+__host__ __device__ inline size_t bwd_arena_elems(int m, int p, int r) {
+    const size_t base = arena_elems(m, p, r, true), with = base + stage_elems(m);
+    return with * sizeof(R) <= 225 * 1024 ? with : base;
 }
 
 template <typename R>
@@ -621,12 +640,29 @@ __global__ void __launch_bounds__(W == 1 ? 128 : 32 * W) backward_kernel(KArgs<R
     wzero(A.gZ, p * m, L); wzero(A.gH, p * p, L); wzero(A.gc, m, L); wzero(A.gd, p, L);
     const R* yb = g.y_shared ? g.y : g.y + (size_t)b * n * p;
     const size_t tstride = (size_t)m + (size_t)m * m;
+    // With room behind the arena the record [a | P] of step t - 1 travels by cp.async while step t is worked on (the
+    // synchronous copy was 18 % of the univariate adjoint's samples at m = 27: global-memory latency with nothing to hide it).
+    R* const stage = arena > arena_elems(m, p, r, true) ? smem + (size_t)warp * arena + arena_elems(m, p, r, true) : nullptr;
+    auto fetch = [&](int t) {
+        const R* src = g.traj + ((size_t)b * n + t) * tstride;
+        for (int i = lane; i < (int)tstride; i += NT) cp_async_elem(stage + i, src + i);
+    };
+    if (stage) fetch(n - 1);
     for (int t = n - 1; t >= 0; --t) {
         const size_t bt = (size_t)b * n + t;
         const R gcot = g.ll_cot ? g.ll_cot[bt] : R(1);
         if (t == n - 1 || tv) load_params(g, A, b, t, t == n - 1, L);
-        wcopy(A.a, g.traj + bt * tstride, m, L);
-        wcopy(A.P, g.traj + bt * tstride + m, m * m, L);
+        if (stage) {  // the record was fetched during the previous step; start on the next one
+            cp_async_wait_all();
+            gsync<W>();
+            for (int i = lane; i < m; i += NT) A.a[i] = stage[i];
+            for (int i = lane; i < m * m; i += NT) A.P[i] = stage[m + i];
+            gsync<W>();
+            if (t > 0) fetch(t - 1);
+        } else {
+            wcopy(A.a, g.traj + bt * tstride, m, L);
+            wcopy(A.P, g.traj + bt * tstride + m, m * m, L);
+        }
         bool flag = false, ok = true;
         if (g.kind == BKF_STANDARD) std_update(g, A, yb + (size_t)t * p, (R*)nullptr, (R*)nullptr, &flag, &ok, A.Finv, L);
         else uni_update(g, A, yb + (size_t)t * p, (R*)nullptr, (R*)nullptr, L);
@@ -1035,7 +1071,28 @@ int launch_forward_w(const KArgs<R>& g, cudaStream_t stream, const char** err) {
 }
 template <typename R, int W>
 int launch_backward_w(const KArgs<R>& g, cudaStream_t stream, const char** err) {
-    return launch_group_kernel<R, W>(backward_kernel<R, W>, g, arena_elems(g.m, g.p, g.r, true), stream, err);
+    return launch_group_kernel<R, W>(backward_kernel<R, W>, g, bwd_arena_elems<R>(g.m, g.p, g.r), stream, err);
+}
+
+// Series of this build that one SM holds at a time (registers, shared memory and the CTA limit, from the runtime's
+// occupancy calculator); W == 1 packs wpc series into a CTA.
+template <typename R, int W>
+int resident_series_w(bool backward, size_t arena_bytes) {
+    const int wpc = W == 1 ? pick_wpc(arena_bytes, 0) : 1;
+    const size_t smem = arena_bytes * wpc;
+    int ctas = 0;
+    cudaError_t e;
+    if (backward) {
+        auto kern = backward_kernel<R, W>;
+        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas, kern, W == 1 ? 32 * wpc : 32 * W, smem);
+    } else {
+        auto kern = forward_kernel<R, W>;
+        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas, kern, W == 1 ? 32 * wpc : 32 * W, smem);
+    }
+    if (e != cudaSuccess) { cudaGetLastError(); return 0; }
+    return ctas * wpc;
 }
 
 #if BKF_GEN_W == 1
@@ -1047,35 +1104,39 @@ extern template int launch_forward_w<double, 8>(const KArgs<double>&, cudaStream
 extern template int launch_backward_w<double, 2>(const KArgs<double>&, cudaStream_t, const char**);
 extern template int launch_backward_w<double, 4>(const KArgs<double>&, cudaStream_t, const char**);
 extern template int launch_backward_w<double, 8>(const KArgs<double>&, cudaStream_t, const char**);
+extern template int resident_series_w<double, 2>(bool, size_t);
+extern template int resident_series_w<double, 4>(bool, size_t);
+extern template int resident_series_w<double, 8>(bool, size_t);
 
-// Warps per series.  The arena bounds the series one SM can hold (227 KB), the registers its warps (forward: 16, adjoint
-// at 235-240 registers: 8).  Measured (tools/bench_generic_groups.py): a series runs about sqrt(W) times faster on W warps
-// (the dense products scale, the Cholesky and the substitutions do not), so the launcher takes the width with the largest
-// (series per SM) * sqrt(W).  With small arenas that is the one-warp mapping, at the VARMAX shape (one series per SM) it is
-// eight warps.  BKF_GEN_W=<1|2|4|8> in the environment overrides the choice.
-static int pick_w(size_t arena_bytes, int warps_per_sm) {
+// Warps per series.  Measured (tools/bench_generic_groups.py): a series runs about sqrt(W) times faster on W warps (the
+// dense products scale, the Cholesky, the substitutions and the barriers do not), so the launcher takes the width with the
+// largest (series resident per SM) * sqrt(W); the resident series come from the occupancy calculator, i.e. from the
+// registers the build at hand really has.  With small arenas that is the one-warp mapping, at the VARMAX shape (one series
+// per SM) it is eight warps.  BKF_GEN_W=<1|2|4|8> in the environment overrides the choice.
+static int pick_w(size_t arena_bytes, bool backward) {
     if (const char* e = getenv("BKF_GEN_W")) {
         int w = atoi(e);
         if (w == 1 || w == 2 || w == 4 || w == 8) return w;
     }
-    const size_t smem = 225 * 1024;
-    const int per_sm = (int)(smem / (arena_bytes ? arena_bytes : 1));
-    const int wpc = pick_wpc(arena_bytes, 0);
-    int ctas = (int)(smem / (arena_bytes * wpc));
-    if (ctas > warps_per_sm / wpc) ctas = warps_per_sm / wpc;
-    double best = (double)(ctas * wpc);  // W = 1
-    int w_best = 1;
+    if (arena_bytes > 225 * 1024) return 1;  // (the launch reports the error)
+    static std::mutex mu;
+    static std::map<std::pair<size_t, bool>, int> cache;
+    std::lock_guard<std::mutex> lk(mu);
+    auto it = cache.find({arena_bytes, backward});
+    if (it != cache.end()) return it->second;
+    const int series[4] = {resident_series_w<double, 1>(backward, arena_bytes), resident_series_w<double, 2>(backward, arena_bytes),
+                           resident_series_w<double, 4>(backward, arena_bytes), resident_series_w<double, 8>(backward, arena_bytes)};
     const double gain[4] = {1.0, 1.41, 2.0, 2.83};
-    for (int k = 1; k < 4; ++k) {
-        const int w = 1 << k;
-        int series = per_sm < warps_per_sm / w ? per_sm : warps_per_sm / w;
-        const double score = series * gain[k];
-        if (score > best * 1.05) { best = score; w_best = w; }
-    }
+    double best = series[0] * gain[0];
+    int w_best = 1;
+    for (int k = 1; k < 4; ++k)
+        if (series[k] * gain[k] > best * 1.05) { best = series[k] * gain[k]; w_best = 1 << k; }
+    cache[{arena_bytes, backward}] = w_best;
     return w_best;
 }
 int width(const KArgs<double>& g, bool backward) {
-    return pick_w(arena_elems(g.m, g.p, g.r, backward) * sizeof(double), backward ? 8 : 16);
+    return pick_w((backward ? bwd_arena_elems<double>(g.m, g.p, g.r) : arena_elems(g.m, g.p, g.r, false)) * sizeof(double),
+                  backward);
 }
 #endif
 
@@ -1135,6 +1196,7 @@ template int launch_smoother<float>(const KArgs<float>&, const int*, const int*,
 #else   // BKF_GEN_W > 1: this unit holds one CTA-per-series build of the two sweeps
 template int launch_forward_w<double, BKF_GEN_W>(const KArgs<double>&, cudaStream_t, const char**);
 template int launch_backward_w<double, BKF_GEN_W>(const KArgs<double>&, cudaStream_t, const char**);
+template int resident_series_w<double, BKF_GEN_W>(bool, size_t);
 #endif
 
 }  // namespace BKF_GEN_NS
