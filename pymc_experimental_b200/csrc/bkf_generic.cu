@@ -931,7 +931,7 @@ __device__ void jacobi_eig(R* A, R* V, int m, int lane) {
 
 // One series of the smoother sweep by one warp (s: the warp's arena).
 template <typename R>
-__device__ void smooth_series(const KArgs<R>& g, const int b, R* s, const R jitter0, const int lane) {
+__device__ void smooth_series(const KArgs<R>& g, const int b, R* s, const R jitter0, const bool force_pinv, const int lane) {
     constexpr int W = 1, NT = 32;
     const Lane<1> L{lane};
     const int m = g.m, r = g.r, n = g.n;
@@ -968,7 +968,25 @@ __device__ void smooth_series(const KArgs<R>& g, const int b, R* s, const R jitt
         mm<SET>(X, T, m, 1, P, m, 1, m, m, m, L);
         mm<SET>(Y, X, m, 1, T, 1, m, m, m, m, L);
         sym_into<R>(Ph, Y, RQR, g.jitter, m, L);
-        // pinv(P_hat) (:112): symmetric eigen-decomposition, singular values below 1e-15 * max dropped
+        // pinv(P_hat) T P (:112).  P_hat is symmetric positive definite but for degenerate models, and then its
+        // pseudo-inverse IS its inverse: float64 steps whose Cholesky pivots are positive and span less than 1e13 (the
+        // test of the specialised smoothers, bkf_mma_smooth.cuh) solve P_hat W = T P by substitution, one column per lane
+        // -- some 10 k cycles at m = 27 where the eigen-decomposition below takes several 100 k.  Everything else (a
+        // failed test, float32, the series a specialised smoother handed over: force_pinv) takes the eigen-decomposition.
+        bool direct = false;
+        if (sizeof(R) == 8 && !force_pinv) {
+            wcopy(V, Ph, m * m, L);
+            const bool ok = chol_lower(V, m, L);
+            R dmin = V[0], dmax = V[0];
+            for (int i = 1; i < m; ++i) { dmin = fmin(dmin, V[i * m + i]); dmax = fmax(dmax, V[i * m + i]); }
+            direct = ok && !(dmin * dmin < R(1e-13) * (dmax * dmax));
+            if (direct) {
+                for (int c = lane; c < m; c += NT) chol_solve_vec(V, m, X + c, m);  // X = T P  ->  P_hat^{-1} T P
+                gsync<W>();
+            }
+        }
+        if (!direct) {
+        // symmetric eigen-decomposition, singular values below 1e-15 * max dropped
         wcopy(Y, Ph, m * m, L);
         jacobi_eig(Y, V, m, lane);
         R lmax = 0;
@@ -986,9 +1004,11 @@ __device__ void smooth_series(const KArgs<R>& g, const int b, R* s, const R jitt
             X[idx] = acc;
         }
         gsync<W>();
-        // G = (pinv T P)^T
+        // X = pinv T P
         mm<SET>(Y, X, m, 1, T, m, 1, m, m, m, L);
         mm<SET>(X, Y, m, 1, P, m, 1, m, m, m, L);
+        }
+        // G = (pinv T P)^T
         for (int idx = lane; idx < m * m; idx += NT) G[idx] = X[(idx % m) * m + idx / m];
         for (int i = lane; i < m; i += NT) ah[i] = as[i] - ah[i];
         gsync<W>();
@@ -1018,19 +1038,20 @@ __device__ void smooth_series(const KArgs<R>& g, const int b, R* s, const R jitt
 // smoother flagged as ill-conditioned, bkf_api.cu::run_smoother): the grid strides over them and a launch with
 // *count == 0 returns at once -- no host round trip decides whether this kernel has work.
 template <typename R>
-__global__ void smoother_kernel(KArgs<R> g, int wpc, size_t arena, R jitter0, const int* list, const int* count) {
+__global__ void smoother_kernel(KArgs<R> g, int wpc, size_t arena, R jitter0, const int* list, const int* count,
+                                bool force_pinv) {
     extern __shared__ double smem_raw[];
     R* s = reinterpret_cast<R*>(smem_raw);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     s += (size_t)warp * arena;
     if (!list) {
         const int b = blockIdx.x * wpc + warp;
-        if (b < g.B) smooth_series<R>(g, b, s, jitter0, lane);
+        if (b < g.B) smooth_series<R>(g, b, s, jitter0, force_pinv, lane);
         return;
     }
     const int cnt = *count;
     for (int i = blockIdx.x * wpc + warp; i < cnt; i += gridDim.x * wpc) {
-        smooth_series<R>(g, list[i], s, jitter0, lane);
+        smooth_series<R>(g, list[i], s, jitter0, true, lane);
         __syncwarp();
     }
 }
@@ -1179,7 +1200,10 @@ int launch_smoother(const KArgs<R>& g, const int* list, const int* count, cudaSt
     int grid = (g.B + wpc - 1) / wpc;
     if (list && grid > 148) grid = 148;  // flagged series only: a small strided grid (usually there are none)
     R jitter0 = sizeof(R) == 8 ? R(1e-8) : R(1e-6);  // JITTER_DEFAULT, utils/constants.py:20
-    kern<<<grid, 32 * wpc, smem, stream>>>(g, wpc, arena, jitter0, list, count);
+    // BKF_GEN_SMOOTH_PINV=1: the eigen-decomposition pinv at every step (what this kernel did before it tried a Cholesky solve)
+    const char* env = getenv("BKF_GEN_SMOOTH_PINV");
+    const bool force_pinv = env && env[0] == '1';
+    kern<<<grid, 32 * wpc, smem, stream>>>(g, wpc, arena, jitter0, list, count, force_pinv);
     e = cudaGetLastError();
     if (e != cudaSuccess) { *err = cudaGetErrorString(e); return BKF_ERR_CUDA; }
     return BKF_OK;

@@ -116,3 +116,37 @@ def test_group_kernels_all_widths_agree_and_repeat_bit_for_bit(eng, kind):
         assert_allclose(res[w][0], res[1][0], rtol=1e-12)
         for k in NAMES:
             _close(res[w][1][k], res[1][1][k], 1e-11, f"W={w} {kind} d/d{k}")
+
+
+@pytest.mark.parametrize("m,r", [(20, 20), (27, 27), (36, 8)])
+def test_generic_smoother_cholesky_solve_and_pinv_paths_match_the_oracle(eng, m, r):
+    """State widths without a specialised smoother (m > 16): the generic smoother solves P_hat W = T P by Cholesky when the
+    pivots allow it and keeps the eigen-decomposition pinv otherwise (kalman_smoother.py:107-126, `pt.linalg.pinv`); both
+    against the numpy oracle (numpy's SVD pinv) on systems with a well-conditioned P_hat."""
+    from oracle import kalman_np as onp
+    from pymc_experimental_b200 import synth
+
+    B, n = 4, 12
+    cfg = synth.random_dense(B, n, m, 2, r, seed=100 + m, missing=0.0)
+    args = [cfg["y"]] + [cfg[k] for k in NAMES]
+    out = eng.filter("standard", *args, outputs=("filtered_states", "filtered_covariances"))
+    old = os.environ.get("BKF_GEN_SMOOTH_PINV")
+    try:
+        for mode in ("chol", "pinv"):
+            if mode == "pinv":
+                os.environ["BKF_GEN_SMOOTH_PINV"] = "1"
+            else:
+                os.environ.pop("BKF_GEN_SMOOTH_PINV", None)
+            sa, sP, status = eng.smooth(cfg["T"], cfg["R"], cfg["Q"], out["filtered_states"], out["filtered_covariances"],
+                                        return_status=True)
+            assert (status == 0).all()
+            for b in range(B):
+                ra, rP = onp.kalman_smoother(cfg["T"][b], cfg["R"][b], cfg["Q"][b], out["filtered_states"][b],
+                                             out["filtered_covariances"][b])
+                _close(sa[b], ra, 1e-8, f"{mode} smoothed_states[{b}]")
+                _close(sP[b], rP, 1e-8, f"{mode} smoothed_covariances[{b}]")
+    finally:
+        if old is None:
+            os.environ.pop("BKF_GEN_SMOOTH_PINV", None)
+        else:
+            os.environ["BKF_GEN_SMOOTH_PINV"] = old
