@@ -475,7 +475,7 @@ __device__ R std_update(const KArgs<R>& g, Arena<R>& A, const R* yt, R* obs_mu, 
 // In: A.a, A.P.  Out: A.af, A.Pf (sym + jitter), A.Pu (P before symmetrisation), A.Kst/Fst/vst/zfst, A.w.
 // ----------------------------------------------------------------------------------------------------
 template <typename R, int W>
-__device__ R uni_update(const KArgs<R>& g, Arena<R>& A, const R* yt, R* obs_mu, R* obs_cov, Lane<W> L) {
+__device__ R uni_update(const KArgs<R>& g, Arena<R>& A, const R* yt, R* obs_mu, R* obs_cov, const bool psym, Lane<W> L) {
     const int lane = L.v;
     constexpr int NT = 32 * W;
     (void)lane; (void)NT;
@@ -498,9 +498,13 @@ __device__ R uni_update(const KArgs<R>& g, Arena<R>& A, const R* yt, R* obs_mu, 
         yh += A.d[o];
         const R v = A.ym[o] - yh;
         // pz = P z^T  (kept in K row o), F0 = z pz + H_oo
+        // psym: P is bitwise symmetric (every prediction is, sym_into; the rank-one updates below keep it so), and lane i
+        // reads column i instead of row i -- the same values in the same order, without the bank conflicts of rows that
+        // lie m doubles apart (16-way at m = 16, 24, 32, 40).  Only P0 (step 0) may be asymmetric and is read by rows.
+        const int s_row = psym ? 1 : m, s_col = psym ? m : 1;
         for (int i = lane; i < m; i += NT) {
             R acc = 0;
-            for (int j = 0; j < m; ++j) acc = fma(A.Pu[i * m + j], wo * z[j], acc);
+            for (int j = 0; j < m; ++j) acc = fma(A.Pu[i * s_row + j * s_col], wo * z[j], acc);
             A.Kst[o * m + i] = acc;
         }
         gsync<W>();
@@ -586,7 +590,7 @@ __global__ void __launch_bounds__(W == 1 ? 128 : 32 * W) forward_kernel(KArgs<R>
             ll = std_update(g, A, yb + (size_t)t * p, om, oc, &flag, &ok, (R*)nullptr, L);
             if (!ok) st |= BKF_STATUS_NOT_PD;
         } else {
-            ll = uni_update(g, A, yb + (size_t)t * p, om, oc, L);
+            ll = uni_update(g, A, yb + (size_t)t * p, om, oc, t > 0, L);
         }
         if (g.filt_a) wcopy(g.filt_a + bt * m, A.af, m, L);
         if (g.filt_P) wcopy(g.filt_P + bt * m * m, A.Pf, m * m, L);
@@ -665,7 +669,7 @@ __global__ void __launch_bounds__(W == 1 ? 128 : 32 * W) backward_kernel(KArgs<R
         }
         bool flag = false, ok = true;
         if (g.kind == BKF_STANDARD) std_update(g, A, yb + (size_t)t * p, (R*)nullptr, (R*)nullptr, &flag, &ok, A.Finv, L);
-        else uni_update(g, A, yb + (size_t)t * p, (R*)nullptr, (R*)nullptr, L);
+        else uni_update(g, A, yb + (size_t)t * p, (R*)nullptr, (R*)nullptr, t > 0, L);
         // ---------------- predict adjoint ----------------
         // G = S(Pbar+); Gsum += G; gT += G T (Pf + Pf^T) + abar+ af^T; Pfbar = T^T G T; afbar = T^T abar+; gc += abar+
         sym_into<R>(A.G, A.Pbar, nullptr, R(0), m, L);
@@ -788,11 +792,32 @@ __global__ void __launch_bounds__(W == 1 ? 128 : 32 * W) backward_kernel(KArgs<R
                 gsync<W>();
                 // Kbar_i = -sum_j (Pbar_ij + Pbar_ji) K_j F + abar_i v   (tmp in X[0:m])
                 R kpk = 0, ka = 0, kk = 0;
+                if constexpr (W > 1) {
+                    // (Pbar K)_i and (Pbar^T K)_i: warp w sums its share of the j, lane i of every warp holds row / column i;
+                    // the partial sums meet in the scratch (X is free in this branch; gsum3 uses its first 3 W values)
+                    R* part = A.X + 32;
+                    const int wq = lane >> 5;
+                    for (int i = lane & 31; i < m; i += 32) {
+                        R rs = 0, cs = 0;
+                        for (int j = wq; j < m; j += W) {
+                            rs = fma(A.Pbar[i * m + j], K[j], rs);
+                            cs = fma(A.Pbar[j * m + i], K[j], cs);
+                        }
+                        part[(2 * wq) * m + i] = rs;
+                        part[(2 * wq + 1) * m + i] = cs;
+                    }
+                    gsync<W>();
+                }
                 for (int i = lane; i < m; i += NT) {
-                    R acc = 0;
-                    for (int j = 0; j < m; ++j) acc = fma(A.Pbar[i * m + j] + A.Pbar[j * m + i], K[j], acc);
-                    R pk = 0;
-                    for (int j = 0; j < m; ++j) pk = fma(A.Pbar[i * m + j], K[j], pk);
+                    R acc = 0, pk = 0;
+                    if constexpr (W > 1) {
+                        R cs = 0;
+                        for (int w = 0; w < W; ++w) { pk += A.X[32 + (2 * w) * m + i]; cs += A.X[32 + (2 * w + 1) * m + i]; }
+                        acc = pk + cs;
+                    } else {
+                        for (int j = 0; j < m; ++j) acc = fma(A.Pbar[i * m + j] + A.Pbar[j * m + i], K[j], acc);
+                        for (int j = 0; j < m; ++j) pk = fma(A.Pbar[i * m + j], K[j], pk);
+                    }
                     R kb = fma(-acc, F, A.abar[i] * v);
                     A.Kbar[i] = kb;
                     kpk = fma(K[i], pk, kpk);
