@@ -911,7 +911,7 @@ __host__ __device__ inline size_t smooth_arena_elems(int m, int r) {
 // Symmetric eigen-decomposition by cyclic Jacobi: A (destroyed; diag -> eigenvalues), V (eigenvectors in columns).
 template <typename R>
 __device__ void jacobi_eig(R* A, R* V, int m, int lane) {
-    constexpr int W = 1, NT = 32;  // the smoother stays one warp per series
+    constexpr int W = 1, NT = 32;  // the eigen-decomposition runs on one warp
     for (int idx = lane; idx < m * m; idx += NT) V[idx] = ((idx / m) == (idx % m)) ? R(1) : R(0);
     gsync<W>();
     const R tol2 = sizeof(R) == 8 ? R(1e-34) : R(1e-15);
@@ -954,11 +954,11 @@ __device__ void jacobi_eig(R* A, R* V, int m, int lane) {
     }
 }
 
-// One series of the smoother sweep by one warp (s: the warp's arena).
-template <typename R>
+// One series of the smoother sweep by one warp or, W > 1, by a CTA of W warps (s: the series' arena).
+template <typename R, int W>
 __device__ void smooth_series(const KArgs<R>& g, const int b, R* s, const R jitter0, const bool force_pinv, const int lane) {
-    constexpr int W = 1, NT = 32;
-    const Lane<1> L{lane};
+    constexpr int NT = 32 * W;
+    const Lane<W> L{lane};
     const int m = g.m, r = g.r, n = g.n;
     const size_t mm_ = (size_t)m * m;
     auto take = [&](size_t k) { R* q = s; s += k; return q; };
@@ -1013,7 +1013,8 @@ __device__ void smooth_series(const KArgs<R>& g, const int b, R* s, const R jitt
         if (!direct) {
         // symmetric eigen-decomposition, singular values below 1e-15 * max dropped
         wcopy(Y, Ph, m * m, L);
-        jacobi_eig(Y, V, m, lane);
+        if (lane < 32) jacobi_eig(Y, V, m, lane);  // (one warp; the rest of a CTA-per-series group waits)
+        gsync<W>();
         R lmax = 0;
         for (int i = 0; i < m; ++i) lmax = fmax(lmax, fabs(Y[i * m + i]));
         const R cutoff = R(1e-15) * lmax;
@@ -1062,22 +1063,26 @@ __device__ void smooth_series(const KArgs<R>& g, const int b, R* s, const R jitt
 // list == nullptr: warp w of the grid takes series w.  Otherwise the series are list[0 .. *count) (the ones a fast
 // smoother flagged as ill-conditioned, bkf_api.cu::run_smoother): the grid strides over them and a launch with
 // *count == 0 returns at once -- no host round trip decides whether this kernel has work.
-template <typename R>
-__global__ void smoother_kernel(KArgs<R> g, int wpc, size_t arena, R jitter0, const int* list, const int* count,
-                                bool force_pinv) {
+template <typename R, int W>
+__global__ void __launch_bounds__(W == 1 ? 128 : 32 * W)
+smoother_kernel(KArgs<R> g, int wpc, size_t arena, R jitter0, const int* list, const int* count, bool force_pinv) {
     extern __shared__ double smem_raw[];
     R* s = reinterpret_cast<R*>(smem_raw);
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    s += (size_t)warp * arena;
-    if (!list) {
-        const int b = blockIdx.x * wpc + warp;
-        if (b < g.B) smooth_series<R>(g, b, s, jitter0, force_pinv, lane);
-        return;
-    }
-    const int cnt = *count;
-    for (int i = blockIdx.x * wpc + warp; i < cnt; i += gridDim.x * wpc) {
-        smooth_series<R>(g, list[i], s, jitter0, true, lane);
-        __syncwarp();
+    if constexpr (W > 1) {  // one series per CTA (never with a list: the launcher keeps W = 1 there)
+        if ((int)blockIdx.x < g.B) smooth_series<R, W>(g, blockIdx.x, s, jitter0, force_pinv, threadIdx.x);
+    } else {
+        const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+        s += (size_t)warp * arena;
+        if (!list) {
+            const int b = blockIdx.x * wpc + warp;
+            if (b < g.B) smooth_series<R, 1>(g, b, s, jitter0, force_pinv, lane);
+            return;
+        }
+        const int cnt = *count;
+        for (int i = blockIdx.x * wpc + warp; i < cnt; i += gridDim.x * wpc) {
+            smooth_series<R, 1>(g, list[i], s, jitter0, true, lane);
+            __syncwarp();
+        }
     }
 }
 
@@ -1122,23 +1127,44 @@ int launch_backward_w(const KArgs<R>& g, cudaStream_t stream, const char** err) 
 
 // Series of this build that one SM holds at a time (registers, shared memory and the CTA limit, from the runtime's
 // occupancy calculator); W == 1 packs wpc series into a CTA.
+enum { K_FWD = 0, K_BWD = 1, K_SMOOTH = 2 };
 template <typename R, int W>
-int resident_series_w(bool backward, size_t arena_bytes) {
+int resident_series_w(int which, size_t arena_bytes) {
     const int wpc = W == 1 ? pick_wpc(arena_bytes, 0) : 1;
     const size_t smem = arena_bytes * wpc;
+    const int threads = W == 1 ? 32 * wpc : 32 * W;
     int ctas = 0;
-    cudaError_t e;
-    if (backward) {
-        auto kern = backward_kernel<R, W>;
+    auto query = [&](auto kern) {
         cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas, kern, W == 1 ? 32 * wpc : 32 * W, smem);
-    } else {
-        auto kern = forward_kernel<R, W>;
-        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas, kern, W == 1 ? 32 * wpc : 32 * W, smem);
-    }
+        return cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas, kern, threads, smem);
+    };
+    const cudaError_t e = which == K_FWD ? query(forward_kernel<R, W>)
+                        : which == K_BWD ? query(backward_kernel<R, W>) : query(smoother_kernel<R, W>);
     if (e != cudaSuccess) { cudaGetLastError(); return 0; }
     return ctas * wpc;
+}
+
+// The smoother sweep of one build (list / count: the W = 1 build only).
+template <typename R, int W>
+int launch_smoother_w(const KArgs<R>& g, const int* list, const int* count, cudaStream_t stream, const char** err) {
+    size_t arena = smooth_arena_elems(g.m, g.r);
+    size_t arena_bytes = arena * sizeof(R);
+    if (arena_bytes > 227 * 1024) { *err = "problem too large for the generic smoother kernel"; return BKF_ERR_UNSUPPORTED; }
+    int wpc = W == 1 ? pick_wpc(arena_bytes, g.B) : 1;
+    size_t smem = arena_bytes * wpc;
+    auto kern = smoother_kernel<R, W>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) { *err = cudaGetErrorString(e); return BKF_ERR_CUDA; }
+    int grid = (g.B + wpc - 1) / wpc;
+    if (list && grid > 148) grid = 148;  // flagged series only: a small strided grid (usually there are none)
+    R jitter0 = sizeof(R) == 8 ? R(1e-8) : R(1e-6);  // JITTER_DEFAULT, utils/constants.py:20
+    // BKF_GEN_SMOOTH_PINV=1: the eigen-decomposition pinv at every step (what this kernel did before it tried a Cholesky solve)
+    const char* env = getenv("BKF_GEN_SMOOTH_PINV");
+    const bool force_pinv = env && env[0] == '1';
+    kern<<<grid, W == 1 ? 32 * wpc : 32 * W, smem, stream>>>(g, wpc, arena, jitter0, list, count, force_pinv);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) { *err = cudaGetErrorString(e); return BKF_ERR_CUDA; }
+    return BKF_OK;
 }
 
 #if BKF_GEN_W == 1
@@ -1150,39 +1176,42 @@ extern template int launch_forward_w<double, 8>(const KArgs<double>&, cudaStream
 extern template int launch_backward_w<double, 2>(const KArgs<double>&, cudaStream_t, const char**);
 extern template int launch_backward_w<double, 4>(const KArgs<double>&, cudaStream_t, const char**);
 extern template int launch_backward_w<double, 8>(const KArgs<double>&, cudaStream_t, const char**);
-extern template int resident_series_w<double, 2>(bool, size_t);
-extern template int resident_series_w<double, 4>(bool, size_t);
-extern template int resident_series_w<double, 8>(bool, size_t);
+extern template int resident_series_w<double, 2>(int, size_t);
+extern template int resident_series_w<double, 4>(int, size_t);
+extern template int resident_series_w<double, 8>(int, size_t);
+extern template int launch_smoother_w<double, 2>(const KArgs<double>&, const int*, const int*, cudaStream_t, const char**);
+extern template int launch_smoother_w<double, 4>(const KArgs<double>&, const int*, const int*, cudaStream_t, const char**);
+extern template int launch_smoother_w<double, 8>(const KArgs<double>&, const int*, const int*, cudaStream_t, const char**);
 
 // Warps per series.  Measured (tools/bench_generic_groups.py): a series runs about sqrt(W) times faster on W warps (the
 // dense products scale, the Cholesky, the substitutions and the barriers do not), so the launcher takes the width with the
 // largest (series resident per SM) * sqrt(W); the resident series come from the occupancy calculator, i.e. from the
 // registers the build at hand really has.  With small arenas that is the one-warp mapping, at the VARMAX shape (one series
 // per SM) it is eight warps.  BKF_GEN_W=<1|2|4|8> in the environment overrides the choice.
-static int pick_w(size_t arena_bytes, bool backward) {
+static int pick_w(size_t arena_bytes, int which) {
     if (const char* e = getenv("BKF_GEN_W")) {
         int w = atoi(e);
         if (w == 1 || w == 2 || w == 4 || w == 8) return w;
     }
     if (arena_bytes > 225 * 1024) return 1;  // (the launch reports the error)
     static std::mutex mu;
-    static std::map<std::pair<size_t, bool>, int> cache;
+    static std::map<std::pair<size_t, int>, int> cache;
     std::lock_guard<std::mutex> lk(mu);
-    auto it = cache.find({arena_bytes, backward});
+    auto it = cache.find({arena_bytes, which});
     if (it != cache.end()) return it->second;
-    const int series[4] = {resident_series_w<double, 1>(backward, arena_bytes), resident_series_w<double, 2>(backward, arena_bytes),
-                           resident_series_w<double, 4>(backward, arena_bytes), resident_series_w<double, 8>(backward, arena_bytes)};
+    const int series[4] = {resident_series_w<double, 1>(which, arena_bytes), resident_series_w<double, 2>(which, arena_bytes),
+                           resident_series_w<double, 4>(which, arena_bytes), resident_series_w<double, 8>(which, arena_bytes)};
     const double gain[4] = {1.0, 1.41, 2.0, 2.83};
     double best = series[0] * gain[0];
     int w_best = 1;
     for (int k = 1; k < 4; ++k)
         if (series[k] * gain[k] > best * 1.05) { best = series[k] * gain[k]; w_best = 1 << k; }
-    cache[{arena_bytes, backward}] = w_best;
+    cache[{arena_bytes, which}] = w_best;
     return w_best;
 }
 int width(const KArgs<double>& g, bool backward) {
     return pick_w((backward ? bwd_arena_elems<double>(g.m, g.p, g.r) : arena_elems(g.m, g.p, g.r, false)) * sizeof(double),
-                  backward);
+                  backward ? K_BWD : K_FWD);
 }
 #endif
 
@@ -1214,24 +1243,17 @@ int launch_backward(const KArgs<R>& g, cudaStream_t stream, const char** err) {
 
 template <typename R>
 int launch_smoother(const KArgs<R>& g, const int* list, const int* count, cudaStream_t stream, const char** err) {
-    size_t arena = smooth_arena_elems(g.m, g.r);
-    size_t arena_bytes = arena * sizeof(R);
-    if (arena_bytes > 227 * 1024) { *err = "problem too large for the generic smoother kernel"; return BKF_ERR_UNSUPPORTED; }
-    int wpc = pick_wpc(arena_bytes, g.B);
-    size_t smem = arena_bytes * wpc;
-    auto kern = smoother_kernel<R>;
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) { *err = cudaGetErrorString(e); return BKF_ERR_CUDA; }
-    int grid = (g.B + wpc - 1) / wpc;
-    if (list && grid > 148) grid = 148;  // flagged series only: a small strided grid (usually there are none)
-    R jitter0 = sizeof(R) == 8 ? R(1e-8) : R(1e-6);  // JITTER_DEFAULT, utils/constants.py:20
-    // BKF_GEN_SMOOTH_PINV=1: the eigen-decomposition pinv at every step (what this kernel did before it tried a Cholesky solve)
-    const char* env = getenv("BKF_GEN_SMOOTH_PINV");
-    const bool force_pinv = env && env[0] == '1';
-    kern<<<grid, 32 * wpc, smem, stream>>>(g, wpc, arena, jitter0, list, count, force_pinv);
-    e = cudaGetLastError();
-    if (e != cudaSuccess) { *err = cudaGetErrorString(e); return BKF_ERR_CUDA; }
-    return BKF_OK;
+#ifdef BKF_GEN_DMMA
+    if (!list) {  // (the flagged series of a specialised smoother are few: one warp each)
+        switch (pick_w(smooth_arena_elems(g.m, g.r) * sizeof(R), K_SMOOTH)) {
+            case 2: return launch_smoother_w<R, 2>(g, list, count, stream, err);
+            case 4: return launch_smoother_w<R, 4>(g, list, count, stream, err);
+            case 8: return launch_smoother_w<R, 8>(g, list, count, stream, err);
+            default: break;
+        }
+    }
+#endif
+    return launch_smoother_w<R, 1>(g, list, count, stream, err);
 }
 
 template int launch_forward<double>(const KArgs<double>&, cudaStream_t, const char**);
@@ -1245,7 +1267,8 @@ template int launch_smoother<float>(const KArgs<float>&, const int*, const int*,
 #else   // BKF_GEN_W > 1: this unit holds one CTA-per-series build of the two sweeps
 template int launch_forward_w<double, BKF_GEN_W>(const KArgs<double>&, cudaStream_t, const char**);
 template int launch_backward_w<double, BKF_GEN_W>(const KArgs<double>&, cudaStream_t, const char**);
-template int resident_series_w<double, BKF_GEN_W>(bool, size_t);
+template int resident_series_w<double, BKF_GEN_W>(int, size_t);
+template int launch_smoother_w<double, BKF_GEN_W>(const KArgs<double>&, const int*, const int*, cudaStream_t, const char**);
 #endif
 
 }  // namespace BKF_GEN_NS

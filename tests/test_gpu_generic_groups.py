@@ -130,23 +130,28 @@ def test_generic_smoother_cholesky_solve_and_pinv_paths_match_the_oracle(eng, m,
     cfg = synth.random_dense(B, n, m, 2, r, seed=100 + m, missing=0.0)
     args = [cfg["y"]] + [cfg[k] for k in NAMES]
     out = eng.filter("standard", *args, outputs=("filtered_states", "filtered_covariances"))
-    old = os.environ.get("BKF_GEN_SMOOTH_PINV")
+    old, old_w = os.environ.get("BKF_GEN_SMOOTH_PINV"), os.environ.get("BKF_GEN_W")
     try:
-        for mode in ("chol", "pinv"):
+        for mode, width in (("chol", None), ("pinv", None), ("chol", 1), ("chol", 4), ("pinv", 8)):
             if mode == "pinv":
                 os.environ["BKF_GEN_SMOOTH_PINV"] = "1"
             else:
                 os.environ.pop("BKF_GEN_SMOOTH_PINV", None)
+            if width is None:  # the launcher's own choice of warps per series
+                os.environ.pop("BKF_GEN_W", None)
+            else:
+                os.environ["BKF_GEN_W"] = str(width)
             sa, sP, status = eng.smooth(cfg["T"], cfg["R"], cfg["Q"], out["filtered_states"], out["filtered_covariances"],
                                         return_status=True)
             assert (status == 0).all()
             for b in range(B):
                 ra, rP = onp.kalman_smoother(cfg["T"][b], cfg["R"][b], cfg["Q"][b], out["filtered_states"][b],
                                              out["filtered_covariances"][b])
-                _close(sa[b], ra, 1e-8, f"{mode} smoothed_states[{b}]")
-                _close(sP[b], rP, 1e-8, f"{mode} smoothed_covariances[{b}]")
+                _close(sa[b], ra, 1e-8, f"{mode} W={width} smoothed_states[{b}]")
+                _close(sP[b], rP, 1e-8, f"{mode} W={width} smoothed_covariances[{b}]")
     finally:
-        if old is None:
-            os.environ.pop("BKF_GEN_SMOOTH_PINV", None)
-        else:
-            os.environ["BKF_GEN_SMOOTH_PINV"] = old
+        for key, val in (("BKF_GEN_SMOOTH_PINV", old), ("BKF_GEN_W", old_w)):
+            if val is None:
+                os.environ.pop(key, None)
+            else:
+                os.environ[key] = val
