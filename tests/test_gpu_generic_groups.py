@@ -155,3 +155,24 @@ def test_generic_smoother_cholesky_solve_and_pinv_paths_match_the_oracle(eng, m,
                 os.environ.pop(key, None)
             else:
                 os.environ[key] = val
+
+
+@pytest.mark.parametrize("kind", ["standard", "univariate"])
+@pytest.mark.parametrize("shape", [(6, 6, 3), (8, 8, 4), (16, 16, 4), (5, 7, 2)])
+def test_as_many_observed_series_as_states(eng, kind, shape):
+    """p about m (or above it): the transposed scratch of the update's solves no longer fits X..Y and the kernels take the
+    in-place substitution and a separate solve for F^-1 (bkf_generic.cu solve_scratch_fits); both builds (m < 16 and m >= 16)."""
+    from oracle import kalman_torch as oth
+    from pymc_experimental_b200 import synth
+
+    m, p, r = shape
+    B, n = 5, 10
+    cfg = synth.random_dense(B, n, m, p, r, seed=7 * m + p, missing=0.0)
+    args = [cfg["y"]] + [cfg[k] for k in NAMES]
+    logp, grads, status = eng.logp_grad(kind, *args)
+    assert eng.last_path in ("generic_warp", "generic_cta") and (status == 0).all()
+    ref_logp, ref_g = oth.logp_and_grad(kind, *args)
+    assert_allclose(logp, ref_logp, rtol=RTOL64)
+    for k in NAMES:
+        for b in range(B):
+            _close(grads[k][b], ref_g[k][b], RTOL64, f"{kind} {shape} d/d{k}[{b}]")
