@@ -122,8 +122,15 @@ __device__ __forceinline__ void mm_dmma(double* __restrict__ C, const double* __
 }
 
 // C[M,N] (row-major) (op)= sum_k A(i,k) * B(k,j) with A(i,k) = A[i*as0 + k*as1], B(k,j) = B[k*bs0 + j*bs1]
+// (One copy per MODE in the DMMA build: inlined at its fifty call sites the adjoint kernel was 460 KB of SASS and its top stall
+// in the tile products was instruction fetch.)
+#ifdef BKF_GEN_DMMA
+#define BKF_MM_INLINE __noinline__
+#else
+#define BKF_MM_INLINE __forceinline__
+#endif
 template <int MODE, int W, typename R>
-__device__ __forceinline__ void mm(R* __restrict__ C, const R* __restrict__ A, int as0, int as1,
+__device__ BKF_MM_INLINE void mm(R* __restrict__ C, const R* __restrict__ A, int as0, int as1,
                                    const R* __restrict__ Bm, int bs0, int bs1, int M, int N, int K, Lane<W> L) {
     const int lane = L.v;
     constexpr int NT = 32 * W;
@@ -609,7 +616,15 @@ __global__ void __launch_bounds__(W == 1 ? 128 : 32 * W) forward_kernel(KArgs<R>
 // backward kernel (standard / univariate): reverse sweep over the stored predictions
 // ----------------------------------------------------------------------------------------------------
 template <typename R, int W>
-__global__ void __launch_bounds__(W == 1 ? 128 : 32 * W) backward_kernel(KArgs<R> g, int wpc, size_t arena) {
+// (minimum CTAs per SM: keeps the two- and four-warp builds at 168 registers = 12 warps per SM and the one-warp build for
+//  small shapes at 128, whatever ptxas would pick; measured, tools/bench_generic_groups.py / bench_multivariate.py)
+#ifdef BKF_GEN_DMMA
+#define BKF_BWD_MINB(W) ((W) == 1 ? 2 : ((W) == 2 ? 6 : ((W) == 4 ? 3 : 1)))
+#else
+#define BKF_BWD_MINB(W) 4
+#endif
+__global__ void __launch_bounds__(W == 1 ? 128 : 32 * W, BKF_BWD_MINB(W))
+backward_kernel(KArgs<R> g, int wpc, size_t arena) {
     extern __shared__ double smem_raw[];
     R* smem = reinterpret_cast<R*>(smem_raw);
     constexpr int NT = 32 * W;
