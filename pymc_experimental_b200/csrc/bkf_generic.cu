@@ -1,9 +1,12 @@
-// bkf_generic.cu -- generic (any m, p, r that fits shared memory) warp-per-series kernels.
+// bkf_generic.cu -- generic (any m, p, r that fits shared memory) kernels: one warp, or one CTA of 2, 4 or 8 warps, per series.
 //
-// One warp owns one time-sequential filter; every matrix of that series lives in the warp's shared-memory
-// arena and the warp's 32 lanes split each small dense operation.  This family is the always-available
-// correct path (and the fallback for shapes without a specialised kernel); the hot shapes of BASELINE.json
-// are served by the register-tiled kernels in bkf_subwarp.cu / bkf_thread.cu.
+// One group of threads (Lane<W>: a warp, W = 1, or a CTA of W warps) owns one time-sequential filter; every matrix of
+// that series lives in the group's shared-memory arena and the group's lanes split each small dense operation.  This
+// family is the always-available correct path (and the fallback for shapes without a specialised kernel: several observed
+// series under the Standard / Univariate filters, more than 16 states, float32 above the sub-warp sizes, T / R / Q with a
+// time axis); the hot shapes of BASELINE.json are served by the register-tiled kernels in bkf_mma / bkf_subwarp /
+// bkf_thread / bkf_sqrt_warp.  The launcher picks W from the arena size (pick_w): large arenas leave an SM only a few
+// series, which then get the warps the SM would otherwise leave idle.
 //
 // Formulas: see bkf_common.cuh for the reference file:line map; the adjoint recurrences are those of
 // SURVEY.md Appendix B (Standard) and their rank-1 analogue (Univariate).
